@@ -1,0 +1,198 @@
+"""ctypes binding of the C ABI declared in ``include/cultionet_b200.h``.
+
+The product path loads exactly one library -- ``cultionet_b200/libcultionet_b200.so`` built by nvcc for sm_100a
+(``python -m cultionet_b200.build``) -- and raises when it is missing: there is no CPU or PyTorch fallback.
+``use_library(path)`` exists for the CPU test interpreter build (``tests/emu``), which the ``-m "not gpu"`` tests
+load explicitly; the package never selects it on its own.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import torch
+
+PKG_DIR = Path(__file__).resolve().parent
+DEFAULT_LIB = PKG_DIR / "libcultionet_b200.so"
+
+CNB_F32, CNB_BF16 = 0, 1
+CNB_MAX_SRC = 6
+TN_MAX_TERMS = 4
+
+_lib = None
+_lib_path = None
+_is_emulator = False
+
+
+class CnbError(RuntimeError):
+    pass
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [
+        ("src", C.c_void_p * CNB_MAX_SRC),
+        ("src_c", C.c_int32 * CNB_MAX_SRC),
+        ("src_stride", C.c_int32 * CNB_MAX_SRC),
+        ("nsrc", C.c_int32),
+        ("B", C.c_int32), ("Hin", C.c_int32), ("Win", C.c_int32), ("Hout", C.c_int32), ("Wout", C.c_int32),
+        ("KH", C.c_int32), ("KW", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32), ("dil", C.c_int32),
+        ("transposed", C.c_int32),
+        ("w_packed", C.c_void_p),
+        ("w_tap_stride", C.c_int64),
+        ("w_row_stride", C.c_int32),
+        ("N", C.c_int32),
+        ("bias", C.c_void_p),
+        ("out", C.c_void_p),
+        ("out_stride", C.c_int32),
+    ]
+
+
+class WgradDesc(C.Structure):
+    _fields_ = [
+        ("src", C.c_void_p), ("src_c", C.c_int32), ("src_stride", C.c_int32),
+        ("k_off", C.c_int32), ("Ctot", C.c_int32),
+        ("B", C.c_int32), ("Hin", C.c_int32), ("Win", C.c_int32), ("Hout", C.c_int32), ("Wout", C.c_int32),
+        ("KH", C.c_int32), ("KW", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32), ("dil", C.c_int32),
+        ("transposed", C.c_int32),
+        ("dy", C.c_void_p), ("dy_stride", C.c_int32), ("N", C.c_int32),
+        ("dwp", C.c_void_p),
+    ]
+
+
+class TanimotoTerm(C.Structure):
+    _fields_ = [
+        ("pred", C.c_void_p), ("target", C.c_void_p), ("mask", C.c_void_p), ("dpred", C.c_void_p),
+        ("C", C.c_int32), ("tgt_c", C.c_int32),
+        ("target_mode", C.c_int32), ("mask_mode", C.c_int32), ("edge_class", C.c_int32),
+        ("weight", C.c_float),
+    ]
+
+
+_vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
+
+# name -> argtypes; every function returns int
+_PROTOS = {
+    "cnb_conv2d_fwd": [C.POINTER(ConvDesc), _i, _vp],
+    "cnb_conv2d_wgrad": [C.POINTER(WgradDesc), _i, _vp],
+    "cnb_pack_weight": [_vp, _vp, _i, _i, _i, _i, _i64, _i64, _i64, _vp],
+    "cnb_unpack_wgrad": [_vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i, _vp],
+    "cnb_bias_grad": [_vp, _i, _i64, _i, _vp, _i, _i, _vp],
+    "cnb_bn_stats": [_vp, _i64, _i, _i, _i, _vp, _i, _vp],
+    "cnb_bn_finalize": [_vp, _i64, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "cnb_bn_act_fwd": [_vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp],
+    "cnb_bn_act_bwd_reduce": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _i, _vp],
+    "cnb_bn_act_bwd_apply": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _i, _vp],
+    "cnb_add_n": [_vp, _vp, _vp, _vp, _vp, _i64, _i, _vp],
+    "cnb_layernorm_fwd": [_vp, _vp, _vp, _f, _vp, _vp, _vp, _i64, _i, _i, _vp],
+    "cnb_layernorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp],
+    "cnb_na2d_fwd": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp],
+    "cnb_na2d_bwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp],
+    "cnb_resize_bilinear_fwd": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "cnb_resize_bilinear_bwd": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "cnb_pretime_conv_fwd": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "cnb_pretime_conv_wgrad": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "cnb_final_combine_fwd": [_vp, _vp, _vp, _vp, _f, _i, _vp, _vp, _vp, _i64, _i, _vp],
+    "cnb_final_combine_bwd": [_vp, _vp, _vp, _vp, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _vp],
+    "cnb_tanimoto_fwd": [C.POINTER(TanimotoTerm), _i, _i, _i64, _f, _i, _vp, _vp, _vp, _vp],
+    "cnb_tanimoto_bwd": [C.POINTER(TanimotoTerm), _i, _i, _i64, _vp, _vp, _vp],
+    "cnb_grad_sqnorm": [_vp, _i64, _vp, _vp],
+    "cnb_adamw_step": [_vp, _vp, _vp, _vp, _i64, _vp, _f, _f, _f, _f, _f, _f, _vp, _vp],
+}
+
+# entry points that only exist in the nvcc build (tcgen05 / TMA kernels); filled in by later sections
+_CUDA_ONLY_PROTOS: dict = {}
+
+EXPORTED_SYMBOLS = ["cnb_version", "cnb_sm_arch", "cnb_last_error", *_PROTOS.keys()]
+
+
+def _bind(lib) -> None:
+    lib.cnb_version.restype = C.c_int
+    lib.cnb_sm_arch.restype = C.c_int
+    lib.cnb_last_error.restype = C.c_char_p
+    for name, argtypes in _PROTOS.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+    for name, argtypes in _CUDA_ONLY_PROTOS.items():
+        if hasattr(lib, name):
+            fn = getattr(lib, name)
+            fn.argtypes = argtypes
+            fn.restype = C.c_int
+
+
+def use_library(path) -> None:
+    """Bind a specific build of the C ABI (tests use this for the CPU interpreter build)."""
+    global _lib, _lib_path, _is_emulator
+    path = Path(path)
+    if not path.is_file():
+        raise CnbError(f"cultionet_b200: native library not found at {path}")
+    lib = C.CDLL(str(path))
+    _bind(lib)
+    _lib, _lib_path = lib, path
+    _is_emulator = lib.cnb_sm_arch() == 0
+
+
+def lib():
+    """The bound library; loads the nvcc build on first use and fails loudly when it is absent."""
+    if _lib is None:
+        if not DEFAULT_LIB.is_file():
+            raise CnbError(
+                f"cultionet_b200: {DEFAULT_LIB.name} is not built (run `python -m cultionet_b200.build`); "
+                "there is no CPU or PyTorch fallback for the TowerUNet hot path."
+            )
+        use_library(DEFAULT_LIB)
+    return _lib
+
+
+def library_path():
+    lib()
+    return _lib_path
+
+
+def is_emulator() -> bool:
+    lib()
+    return _is_emulator
+
+
+def has_symbol(name: str) -> bool:
+    return hasattr(lib(), name)
+
+
+def call(name: str, *args) -> None:
+    rc = getattr(lib(), name)(*args)
+    if rc != 0:
+        msg = lib().cnb_last_error().decode("utf-8", "replace")
+        raise CnbError(f"{name} failed (code {rc}): {msg}")
+
+
+def dtype_code(dtype: torch.dtype) -> int:
+    if dtype == torch.float32:
+        return CNB_F32
+    if dtype == torch.bfloat16:
+        return CNB_BF16
+    raise CnbError(f"cultionet_b200: unsupported activation dtype {dtype} (float32 or bfloat16)")
+
+
+def check_device(*tensors) -> None:
+    """Tensors must live on a CUDA device (or on the CPU when the test interpreter build is bound)."""
+    emu = is_emulator()
+    for t in tensors:
+        if t is None:
+            continue
+        if emu:
+            if t.device.type != "cpu":
+                raise CnbError("the CPU test interpreter build takes CPU tensors")
+        elif t.device.type != "cuda":
+            raise CnbError(
+                "cultionet_b200 kernels need CUDA tensors (sm_100a); there is no CPU fallback -- move the model and batch to cuda"
+            )
+
+
+def stream_ptr(ref: torch.Tensor):
+    if ref.device.type == "cuda":
+        return C.c_void_p(torch.cuda.current_stream(ref.device).cuda_stream)
+    return C.c_void_p(0)
+
+
+def ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)

@@ -1,0 +1,415 @@
+// extern "C" entry points of libcultionet_b200.so (see include/cultionet_b200.h for the contract).
+// Argument validation + launch only: no allocation, no synchronisation, everything on the caller's stream.
+#include "cnb_common.cuh"
+#include "k_conv_generic.cuh"
+#include "k_loss.cuh"
+#include "k_misc.cuh"
+#include "k_na.cuh"
+#include "k_norm.cuh"
+
+using namespace cnb;
+
+static inline int stream_grid(long n, int per_block = 256, int waves = 8) {
+    return cnb_clamp_grid(cnb_div_up(n, per_block), (long)CNB_NUM_SMS * waves);
+}
+
+extern "C" {
+
+int cnb_version(void) { return CNB_VERSION; }
+int cnb_sm_arch(void) {
+#ifdef CNB_EMU
+    return 0;
+#else
+    return 100;
+#endif
+}
+const char* cnb_last_error(void) { return cnb_err_buf(); }
+
+// ------------------------------------------------------------------------------------------------
+static int check_conv_geom(int B, int Hin, int Win, int Hout, int Wout, int KH, int KW, int stride, int pad, int dil, int transposed) {
+    CNB_REQUIRE(B > 0 && Hin > 0 && Win > 0 && Hout > 0 && Wout > 0, "conv: empty geometry B=%d in=%dx%d out=%dx%d", B, Hin, Win, Hout, Wout);
+    CNB_REQUIRE(KH > 0 && KW > 0 && stride > 0 && dil > 0 && pad >= 0, "conv: bad kernel k=%dx%d stride=%d pad=%d dil=%d", KH, KW, stride, pad, dil);
+    if (!transposed) {
+        const int eh = (Hin + 2 * pad - dil * (KH - 1) - 1) / stride + 1;
+        const int ew = (Win + 2 * pad - dil * (KW - 1) - 1) / stride + 1;
+        CNB_REQUIRE(eh == Hout && ew == Wout, "conv: output %dx%d does not match geometry (expected %dx%d)", Hout, Wout, eh, ew);
+    } else {
+        CNB_REQUIRE(Hout <= (Hin - 1) * stride - 2 * pad + dil * (KH - 1) + 1 + (stride - 1) &&
+                        Hout >= (Hin - 1) * stride - 2 * pad + dil * (KH - 1) + 1,
+                    "transposed conv: output height %d inconsistent with input %d", Hout, Hin);
+        CNB_REQUIRE(Wout <= (Win - 1) * stride - 2 * pad + dil * (KW - 1) + 1 + (stride - 1) &&
+                        Wout >= (Win - 1) * stride - 2 * pad + dil * (KW - 1) + 1,
+                    "transposed conv: output width %d inconsistent with input %d", Wout, Win);
+    }
+    return CNB_OK;
+}
+
+int cnb_conv2d_fwd(const cnb_conv_desc* d, int dtype, void* stream) {
+    CNB_REQUIRE(d != nullptr, "conv2d_fwd: null descriptor");
+    CNB_REQUIRE(d->nsrc >= 1 && d->nsrc <= CNB_MAX_SRC, "conv2d_fwd: nsrc=%d", d->nsrc);
+    int rc = check_conv_geom(d->B, d->Hin, d->Win, d->Hout, d->Wout, d->KH, d->KW, d->stride, d->pad, d->dil, d->transposed);
+    if (rc) return rc;
+    int ctot = 0;
+    for (int s = 0; s < d->nsrc; ++s) {
+        CNB_REQUIRE(d->src[s] != nullptr && d->src_c[s] > 0 && d->src_stride[s] >= d->src_c[s], "conv2d_fwd: bad source %d", s);
+        ctot += d->src_c[s];
+    }
+    CNB_REQUIRE(d->w_packed && d->out && d->N > 0 && d->out_stride >= d->N && d->w_row_stride >= ctot, "conv2d_fwd: bad weight/output");
+    const long M = (long)d->B * d->Hout * d->Wout;
+    dim3 grid(cnb_div_up(M, CG_BM), cnb_div_up(d->N, CG_BN));
+    CNB_DISPATCH_DTYPE(dtype, { CNB_LAUNCH((conv_fwd_generic_kernel<T>), grid, dim3(256), 0, (cudaStream_t)stream, *d); });
+    CNB_CHECK_LAUNCH("conv_fwd_generic_kernel");
+    return CNB_OK;
+}
+
+int cnb_conv2d_wgrad(const cnb_wgrad_desc* d, int dtype, void* stream) {
+    CNB_REQUIRE(d != nullptr, "conv2d_wgrad: null descriptor");
+    int rc = check_conv_geom(d->B, d->Hin, d->Win, d->Hout, d->Wout, d->KH, d->KW, d->stride, d->pad, d->dil, d->transposed);
+    if (rc) return rc;
+    CNB_REQUIRE(d->src && d->dy && d->dwp && d->src_c > 0 && d->N > 0 && d->k_off >= 0 && d->k_off + d->src_c <= d->Ctot, "conv2d_wgrad: bad operands");
+    const long M = (long)d->B * d->Hout * d->Wout;
+    const int taps = d->KH * d->KW;
+    const int tiles = cnb_div_up(d->src_c, CG_BM) * cnb_div_up(d->N, CG_BN) * taps;
+    // enough pixel splits for ~4 waves of CTAs, each split a multiple of the 16-pixel chunk
+    int splits = cnb_clamp_grid((4L * CNB_NUM_SMS + tiles - 1) / tiles, cnb_div_up(M, 4 * CG_BK));
+    long m_per_split = ((M + splits - 1) / splits + CG_BK - 1) / CG_BK * CG_BK;
+    splits = cnb_div_up(M, m_per_split);
+    CNB_REQUIRE((long)taps * splits <= 65535, "conv2d_wgrad: grid.z overflow");
+    dim3 grid(cnb_div_up(d->src_c, CG_BM), cnb_div_up(d->N, CG_BN), taps * splits);
+    CNB_DISPATCH_DTYPE(dtype, { CNB_LAUNCH((conv_wgrad_generic_kernel<T>), grid, dim3(256), 0, (cudaStream_t)stream, *d, splits, m_per_split); });
+    CNB_CHECK_LAUNCH("conv_wgrad_generic_kernel");
+    return CNB_OK;
+}
+
+int cnb_pack_weight(const float* w, void* wp, int dtype, int taps, int N, int K, int64_t s_n, int64_t s_k, int64_t s_tap, void* stream) {
+    CNB_REQUIRE(w && wp && taps > 0 && N > 0 && K > 0, "pack_weight: bad arguments");
+    const long total = (long)taps * N * K;
+    CNB_DISPATCH_DTYPE(dtype, {
+        CNB_LAUNCH((pack_weight_kernel<T>), dim3(stream_grid(total)), dim3(256), 0, (cudaStream_t)stream, w, (T*)wp, taps, N, K, (long)s_n,
+                   (long)s_k, (long)s_tap);
+    });
+    CNB_CHECK_LAUNCH("pack_weight_kernel");
+    return CNB_OK;
+}
+
+int cnb_unpack_wgrad(const float* dwp, float* g, int taps, int N, int K, int64_t s_n, int64_t s_k, int64_t s_tap, int accumulate, void* stream) {
+    CNB_REQUIRE(dwp && g && taps > 0 && N > 0 && K > 0, "unpack_wgrad: bad arguments");
+    const long total = (long)taps * N * K;
+    CNB_LAUNCH(unpack_wgrad_kernel, dim3(stream_grid(total)), dim3(256), 0, (cudaStream_t)stream, dwp, g, taps, N, K, (long)s_n, (long)s_k,
+               (long)s_tap, accumulate);
+    CNB_CHECK_LAUNCH("unpack_wgrad_kernel");
+    return CNB_OK;
+}
+
+int cnb_bias_grad(const void* dy, int dy_stride, int64_t P, int N, float* db, int accumulate, int dtype, void* stream) {
+    CNB_REQUIRE(dy && db && P > 0 && N > 0 && dy_stride >= N, "bias_grad: bad arguments");
+    if (!accumulate) CNB_MEMSET_ASYNC(db, 0, sizeof(float) * N, (cudaStream_t)stream);
+    const int cols = cnb_div_up(N, 32);
+    const int splits = cnb_clamp_grid((4L * CNB_NUM_SMS + cols - 1) / cols, cnb_div_up(P, 64));
+    CNB_DISPATCH_DTYPE(dtype, {
+        CNB_LAUNCH((bias_grad_kernel<T>), dim3(cols, splits), dim3(256), 0, (cudaStream_t)stream, (const T*)dy, dy_stride, (long)P, N, db);
+    });
+    CNB_CHECK_LAUNCH("bias_grad_kernel");
+    return CNB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+static inline long column_stride(long total, int L, int* blocks) {
+    // total threads rounded down to a multiple of L (>= L), at most ~8 waves
+    long want = (long)CNB_NUM_SMS * 8 * 256;
+    if (want > total) want = total;
+    long stride = want / L * L;
+    if (stride < L) stride = L;
+    *blocks = cnb_div_up(stride, 256);
+    return stride;
+}
+
+int cnb_bn_stats(const void* x, int64_t P, int L, int C, int ch_div, float* sums, int dtype, void* stream) {
+    CNB_REQUIRE(x && sums && P > 0 && L > 0 && C > 0 && ch_div > 0, "bn_stats: bad arguments");
+    CNB_MEMSET_ASYNC(sums, 0, sizeof(float) * 2 * C, (cudaStream_t)stream);
+    int blocks;
+    const long total = (long)P * L;
+    const long stride = column_stride(total, L, &blocks);
+    CNB_DISPATCH_DTYPE(dtype, {
+        CNB_LAUNCH((bn_stats_kernel<T>), dim3(blocks), dim3(256), 0, (cudaStream_t)stream, (const T*)x, total, L, C, ch_div, stride, sums);
+    });
+    CNB_CHECK_LAUNCH("bn_stats_kernel");
+    return CNB_OK;
+}
+
+int cnb_bn_finalize(const float* sums, int64_t count, int C, const float* gamma, const float* beta, float eps, float momentum,
+                    float* running_mean, float* running_var, float* save_mean, float* save_rstd, float* scale, float* shift, void* stream) {
+    CNB_REQUIRE(C > 0 && scale && shift, "bn_finalize: bad arguments");
+    CNB_REQUIRE(sums || (running_mean && running_var), "bn_finalize: eval mode needs running statistics");
+    CNB_REQUIRE(!sums || count > 0, "bn_finalize: count must be positive");
+    CNB_LAUNCH(bn_finalize_kernel, dim3(cnb_div_up(C, 128)), dim3(128), 0, (cudaStream_t)stream, sums, (long)count, C, gamma, beta, eps,
+               momentum, running_mean, running_var, save_mean, save_rstd, scale, shift);
+    CNB_CHECK_LAUNCH("bn_finalize_kernel");
+    return CNB_OK;
+}
+
+int cnb_bn_act_fwd(const void* x, const float* scale, const float* shift, const void* residual, void* y, int64_t P, int L, int C, int ch_div,
+                   int act, int dtype, void* stream) {
+    CNB_REQUIRE(x && y && scale && shift && P > 0 && L > 0 && C > 0 && ch_div > 0, "bn_act_fwd: bad arguments");
+    const long total = (long)P * L;
+    CNB_DISPATCH_DTYPE(dtype, {
+        CNB_LAUNCH((bn_act_fwd_kernel<T>), dim3(stream_grid(total)), dim3(256), 0, (cudaStream_t)stream, (const T*)x, scale, shift,
+                   (const T*)residual, (T*)y, total, L, C, ch_div, act);
+    });
+    CNB_CHECK_LAUNCH("bn_act_fwd_kernel");
+    return CNB_OK;
+}
+
+int cnb_bn_act_bwd_reduce(const void* x, const void* dy, const float* save_mean, const float* save_rstd, const float* gamma, const float* beta,
+                          int64_t P, int L, int C, int ch_div, int act, float* dsums, int dtype, void* stream) {
+    CNB_REQUIRE(x && dy && save_mean && save_rstd && dsums && P > 0 && L > 0 && C > 0 && ch_div > 0, "bn_act_bwd_reduce: bad arguments");
+    CNB_MEMSET_ASYNC(dsums, 0, sizeof(float) * 2 * C, (cudaStream_t)stream);
+    int blocks;
+    const long total = (long)P * L;
+    const long stride = column_stride(total, L, &blocks);
+    CNB_DISPATCH_DTYPE(dtype, {
+        CNB_LAUNCH((bn_act_bwd_reduce_kernel<T>), dim3(blocks), dim3(256), 0, (cudaStream_t)stream, (const T*)x, (const T*)dy, save_mean,
+                   save_rstd, gamma, beta, total, L, C, ch_div, act, stride, dsums);
+    });
+    CNB_CHECK_LAUNCH("bn_act_bwd_reduce_kernel");
+    return CNB_OK;
+}
+
+int cnb_bn_act_bwd_apply(const void* x, const void* dy, const float* save_mean, const float* save_rstd, const float* gamma, const float* beta,
+                         const float* dsums, int64_t count, void* dx, int64_t P, int L, int C, int ch_div, int act, int train_stats, int dtype,
+                         void* stream) {
+    CNB_REQUIRE(x && dy && dx && save_mean && save_rstd && dsums && count > 0 && P > 0 && L > 0 && C > 0 && ch_div > 0,
+                "bn_act_bwd_apply: bad arguments");
+    const long total = (long)P * L;
+    CNB_DISPATCH_DTYPE(dtype, {
+        CNB_LAUNCH((bn_act_bwd_apply_kernel<T>), dim3(stream_grid(total)), dim3(256), 0, (cudaStream_t)stream, (const T*)x, (const T*)dy,
+                   save_mean, save_rstd, gamma, beta, dsums, 1.0f / (float)count, (T*)dx, total, L, C, ch_div, act, train_stats);
+    });
+    CNB_CHECK_LAUNCH("bn_act_bwd_apply_kernel");
+    return CNB_OK;
+}
+
+int cnb_add_n(const void* a, const void* b, const void* c, const void* d, void* out, int64_t n, int dtype, void* stream) {
+    CNB_REQUIRE(a && b && out && n > 0, "add_n: bad arguments");
+    CNB_DISPATCH_DTYPE(dtype, {
+        CNB_LAUNCH((add_n_kernel<T>), dim3(stream_grid(n)), dim3(256), 0, (cudaStream_t)stream, (const T*)a, (const T*)b, (const T*)c,
+                   (const T*)d, (T*)out, (long)n);
+    });
+    CNB_CHECK_LAUNCH("add_n_kernel");
+    return CNB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+int cnb_layernorm_fwd(const void* x, const float* gamma, const float* beta, float eps, void* y, float* save_mean, float* save_rstd, int64_t P,
+                      int C, int dtype, void* stream) {
+    CNB_REQUIRE(x && y && gamma && beta && save_mean && save_rstd && P > 0 && C > 0, "layernorm_fwd: bad arguments");
+    CNB_DISPATCH_DTYPE(dtype, {
+        CNB_LAUNCH((layernorm_fwd_kernel<T>), dim3(stream_grid(P, 8)), dim3(256), 0, (cudaStream_t)stream, (const T*)x, gamma, beta, eps, (T*)y,
+                   save_mean, save_rstd, (long)P, C);
+    });
+    CNB_CHECK_LAUNCH("layernorm_fwd_kernel");
+    return CNB_OK;
+}
+
+int cnb_layernorm_bwd(const void* x, const void* dy, const float* gamma, const float* save_mean, const float* save_rstd, void* dx,
+                      float* dgamma, float* dbeta, int64_t P, int C, int dtype, void* stream) {
+    CNB_REQUIRE(x && dy && dx && gamma && save_mean && save_rstd && dgamma && dbeta && P > 0 && C > 0, "layernorm_bwd: bad arguments");
+    CNB_REQUIRE(C <= 32 * LN_MAX_CPL, "layernorm_bwd: C=%d exceeds %d", C, 32 * LN_MAX_CPL);
+    CNB_DISPATCH_DTYPE(dtype, {
+        CNB_LAUNCH((layernorm_bwd_kernel<T>), dim3(stream_grid(P, 8, 2)), dim3(256), 0, (cudaStream_t)stream, (const T*)x, (const T*)dy, gamma,
+                   save_mean, save_rstd, (T*)dx, dgamma, dbeta, (long)P, C);
+    });
+    CNB_CHECK_LAUNCH("layernorm_bwd_kernel");
+    return CNB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+static int check_na(int B, int H, int W, int heads, int hd, int ksize, int dilation) {
+    CNB_REQUIRE(B > 0 && H > 0 && W > 0 && heads > 0 && hd > 0, "na2d: bad shape");
+    CNB_REQUIRE(ksize >= 1 && (ksize & 1) && ksize <= NA_MAX_K, "na2d: kernel_size=%d must be odd and <= %d", ksize, NA_MAX_K);
+    CNB_REQUIRE(hd <= 32 * NA_MAX_DPL, "na2d: head_dim=%d exceeds %d", hd, 32 * NA_MAX_DPL);
+    CNB_REQUIRE(dilation >= 1 && ksize * dilation <= H && ksize * dilation <= W,
+                "na2d: kernel_size*dilation=%d exceeds the %dx%d input (natten raises here too)", ksize * dilation, H, W);
+    return CNB_OK;
+}
+
+int cnb_na2d_fwd(const void* qkv, void* out, int B, int H, int W, int heads, int hd, int ksize, int dilation, float scale, int dtype,
+                 void* stream) {
+    int rc = check_na(B, H, W, heads, hd, ksize, dilation);
+    if (rc) return rc;
+    CNB_REQUIRE(qkv && out, "na2d_fwd: null pointer");
+    const long items = (long)B * H * W * heads;
+    CNB_DISPATCH_DTYPE(dtype, {
+        CNB_LAUNCH((na2d_fwd_kernel<T>), dim3(stream_grid(items, 8)), dim3(256), 0, (cudaStream_t)stream, (const T*)qkv, (T*)out, B, H, W, heads,
+                   hd, ksize, dilation, scale);
+    });
+    CNB_CHECK_LAUNCH("na2d_fwd_kernel");
+    return CNB_OK;
+}
+
+int cnb_na2d_bwd(const void* qkv, const void* dout, float* dqkv_acc, void* dqkv, int B, int H, int W, int heads, int hd, int ksize, int dilation,
+                 float scale, int dtype, void* stream) {
+    int rc = check_na(B, H, W, heads, hd, ksize, dilation);
+    if (rc) return rc;
+    CNB_REQUIRE(qkv && dout && dqkv_acc && dqkv, "na2d_bwd: null pointer");
+    const long items = (long)B * H * W * heads;
+    const long n = (long)B * H * W * 3 * heads * hd;
+    CNB_MEMSET_ASYNC(dqkv_acc, 0, sizeof(float) * n, (cudaStream_t)stream);
+    CNB_DISPATCH_DTYPE(dtype, {
+        CNB_LAUNCH((na2d_bwd_kernel<T>), dim3(stream_grid(items, 8)), dim3(256), 0, (cudaStream_t)stream, (const T*)qkv, (const T*)dout,
+                   dqkv_acc, B, H, W, heads, hd, ksize, dilation, scale);
+        CNB_LAUNCH((cast_from_f32_kernel<T>), dim3(stream_grid(n)), dim3(256), 0, (cudaStream_t)stream, (const float*)dqkv_acc, (T*)dqkv, n);
+    });
+    CNB_CHECK_LAUNCH("na2d_bwd_kernel");
+    return CNB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+static inline float align_corners_scale(int in_len, int out_len) { return out_len > 1 ? (float)(in_len - 1) / (float)(out_len - 1) : 0.f; }
+
+int cnb_resize_bilinear_fwd(const void* x, void* y, int B, int Hin, int Win, int Hout, int Wout, int C, int dtype, void* stream) {
+    CNB_REQUIRE(x && y && B > 0 && Hin > 0 && Win > 0 && Hout > 0 && Wout > 0 && C > 0, "resize_bilinear_fwd: bad arguments");
+    const long total = (long)B * Hout * Wout * C;
+    CNB_DISPATCH_DTYPE(dtype, {
+        CNB_LAUNCH((resize_bilinear_fwd_kernel<T>), dim3(stream_grid(total)), dim3(256), 0, (cudaStream_t)stream, (const T*)x, (T*)y, B, Hin,
+                   Win, Hout, Wout, C, align_corners_scale(Hin, Hout), align_corners_scale(Win, Wout));
+    });
+    CNB_CHECK_LAUNCH("resize_bilinear_fwd_kernel");
+    return CNB_OK;
+}
+
+int cnb_resize_bilinear_bwd(const void* dy, void* dx, int B, int Hin, int Win, int Hout, int Wout, int C, int dtype, void* stream) {
+    CNB_REQUIRE(dy && dx && B > 0 && Hin > 0 && Win > 0 && Hout > 0 && Wout > 0 && C > 0, "resize_bilinear_bwd: bad arguments");
+    const long total = (long)B * Hin * Win * C;
+    CNB_DISPATCH_DTYPE(dtype, {
+        CNB_LAUNCH((resize_bilinear_bwd_kernel<T>), dim3(stream_grid(total)), dim3(256), 0, (cudaStream_t)stream, (const T*)dy, (T*)dx, B, Hin,
+                   Win, Hout, Wout, C, align_corners_scale(Hin, Hout), align_corners_scale(Win, Wout));
+    });
+    CNB_CHECK_LAUNCH("resize_bilinear_bwd_kernel");
+    return CNB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+int cnb_pretime_conv_fwd(const float* x, const float* w1, void* u, int B, int C, int T_, int H, int W, int k, int dtype, void* stream) {
+    CNB_REQUIRE(x && w1 && u && B > 0 && C > 0 && H > 0 && W > 0 && k > 0 && T_ >= k, "pretime_conv_fwd: bad arguments (T=%d, k=%d)", T_, k);
+    const long P = (long)B * H * W;
+    dim3 grid(stream_grid(P, 256, 4), C);
+    CNB_DISPATCH_DTYPE(dtype, {
+        CNB_LAUNCH((pretime_conv_fwd_kernel<T>), grid, dim3(256), 0, (cudaStream_t)stream, x, w1, (T*)u, B, C, T_, H, W, k);
+    });
+    CNB_CHECK_LAUNCH("pretime_conv_fwd_kernel");
+    return CNB_OK;
+}
+
+int cnb_pretime_conv_wgrad(const float* x, const void* du, float* dw1, int B, int C, int T_, int H, int W, int k, int dtype, void* stream) {
+    CNB_REQUIRE(x && du && dw1 && B > 0 && C > 0 && H > 0 && W > 0 && k > 0 && k <= PT_MAX_K && T_ >= k, "pretime_conv_wgrad: bad arguments");
+    CNB_REQUIRE(C * C <= 65535, "pretime_conv_wgrad: too many channels");
+    const long P = (long)B * H * W;
+    dim3 grid(stream_grid(P, 256, 1), C * C);
+    CNB_DISPATCH_DTYPE(dtype, {
+        CNB_LAUNCH((pretime_conv_wgrad_kernel<T>), grid, dim3(256), 0, (cudaStream_t)stream, x, (const T*)du, dw1, B, C, T_, H, W, k);
+    });
+    CNB_CHECK_LAUNCH("pretime_conv_wgrad_kernel");
+    return CNB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+int cnb_final_combine_fwd(const void* ha, const void* hb, const void* hc, const float* params, float smooth, int flags, float* distance,
+                          float* edge, float* crop, int64_t P, int dtype, void* stream) {
+    CNB_REQUIRE(ha && hb && hc && params && distance && edge && crop && P > 0, "final_combine_fwd: bad arguments");
+    CNB_DISPATCH_DTYPE(dtype, {
+        CNB_LAUNCH((final_combine_fwd_kernel<T>), dim3(stream_grid(P)), dim3(256), 0, (cudaStream_t)stream, (const T*)ha, (const T*)hb,
+                   (const T*)hc, params, smooth, flags, distance, edge, crop, (long)P);
+    });
+    CNB_CHECK_LAUNCH("final_combine_fwd_kernel");
+    return CNB_OK;
+}
+
+int cnb_final_combine_bwd(const void* ha, const void* hb, const void* hc, const float* params, float smooth, int flags, const float* d_distance,
+                          const float* d_edge, const float* d_crop, void* dha, void* dhb, void* dhc, float* dparams, float* red_ws, int64_t P,
+                          int dtype, void* stream) {
+    CNB_REQUIRE(ha && hb && hc && params && d_distance && d_edge && d_crop && dha && dhb && dhc && dparams && red_ws && P > 0,
+                "final_combine_bwd: bad arguments");
+    CNB_MEMSET_ASYNC(red_ws, 0, sizeof(float) * 32, (cudaStream_t)stream);
+    CNB_DISPATCH_DTYPE(dtype, {
+        CNB_LAUNCH((final_combine_bwd_kernel<T>), dim3(stream_grid(P, 256, 2)), dim3(256), 0, (cudaStream_t)stream, (const T*)ha, (const T*)hb,
+                   (const T*)hc, params, smooth, flags, d_distance, d_edge, d_crop, (T*)dha, (T*)dhb, (T*)dhc, red_ws, (long)P);
+    });
+    CNB_LAUNCH(final_combine_param_grad_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, params, (const float*)red_ws, smooth, flags, dparams);
+    CNB_CHECK_LAUNCH("final_combine_bwd_kernel");
+    return CNB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+static int check_terms(const cnb_tanimoto_term* terms, int nterms, int B, int64_t HW, int backward) {
+    CNB_REQUIRE(terms && nterms >= 1 && nterms <= TN_MAX_TERMS, "tanimoto: nterms=%d (max %d)", nterms, TN_MAX_TERMS);
+    CNB_REQUIRE(B > 0 && B <= 65535 && HW > 0, "tanimoto: bad batch geometry");
+    for (int t = 0; t < nterms; ++t) {
+        const cnb_tanimoto_term& tm = terms[t];
+        CNB_REQUIRE(tm.pred && tm.target && tm.C > 0, "tanimoto: term %d has null operands", t);
+        CNB_REQUIRE(tm.target_mode >= 0 && tm.target_mode <= 3 && tm.mask_mode >= 0 && tm.mask_mode <= 3, "tanimoto: term %d bad modes", t);
+        CNB_REQUIRE(tm.mask_mode == 0 || tm.mask, "tanimoto: term %d needs a mask pointer", t);
+        CNB_REQUIRE(tm.target_mode != 0 || tm.tgt_c == tm.C || tm.tgt_c == 1, "tanimoto: term %d target channels %d vs %d", t, tm.tgt_c, tm.C);
+        CNB_REQUIRE(!backward || tm.dpred, "tanimoto: term %d needs dpred", t);
+    }
+    return CNB_OK;
+}
+
+int cnb_tanimoto_fwd(const cnb_tanimoto_term* terms, int nterms, int B, int64_t HW, float smooth, int depth, double* sums, float* coef,
+                     float* loss, void* stream) {
+    int rc = check_terms(terms, nterms, B, HW, 0);
+    if (rc) return rc;
+    CNB_REQUIRE(sums && coef && loss && depth >= 1 && depth <= 32, "tanimoto_fwd: bad arguments");
+    TanimotoTerms pack;
+    memset(&pack, 0, sizeof(pack));
+    int cmax = 1;
+    for (int t = 0; t < nterms; ++t) {
+        pack.t[t] = terms[t];
+        if (terms[t].C > cmax) cmax = terms[t].C;
+    }
+    CNB_MEMSET_ASYNC(sums, 0, sizeof(double) * 4 * nterms * B, (cudaStream_t)stream);
+    const int chunks = cnb_clamp_grid(cnb_div_up((long)cmax * HW, 256 * 8), cnb_div_up(4L * CNB_NUM_SMS, (long)B * nterms));
+    CNB_LAUNCH(tanimoto_sums_kernel, dim3(chunks, B, nterms), dim3(256), 0, (cudaStream_t)stream, pack, B, (long)HW, sums);
+    CNB_LAUNCH(tanimoto_finalize_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, pack, nterms, B, (long)HW, smooth, depth,
+               (const double*)sums, coef, loss);
+    CNB_CHECK_LAUNCH("tanimoto_fwd");
+    return CNB_OK;
+}
+
+int cnb_tanimoto_bwd(const cnb_tanimoto_term* terms, int nterms, int B, int64_t HW, const float* coef, const float* gscale, void* stream) {
+    int rc = check_terms(terms, nterms, B, HW, 1);
+    if (rc) return rc;
+    CNB_REQUIRE(coef, "tanimoto_bwd: null coef");
+    TanimotoTerms pack;
+    memset(&pack, 0, sizeof(pack));
+    int cmax = 1;
+    for (int t = 0; t < nterms; ++t) {
+        pack.t[t] = terms[t];
+        if (terms[t].C > cmax) cmax = terms[t].C;
+    }
+    const int chunks = cnb_clamp_grid(cnb_div_up((long)cmax * HW, 256 * 4), cnb_div_up(8L * CNB_NUM_SMS, (long)B * nterms));
+    CNB_LAUNCH(tanimoto_bwd_kernel, dim3(chunks, B, nterms), dim3(256), 0, (cudaStream_t)stream, pack, B, (long)HW, coef, gscale);
+    CNB_CHECK_LAUNCH("tanimoto_bwd_kernel");
+    return CNB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+int cnb_grad_sqnorm(const float* g, int64_t n, float* norm_ws, void* stream) {
+    CNB_REQUIRE(g && norm_ws && n > 0, "grad_sqnorm: bad arguments");
+    CNB_MEMSET_ASYNC(norm_ws, 0, sizeof(float), (cudaStream_t)stream);
+    CNB_LAUNCH(grad_sqnorm_kernel, dim3(stream_grid(n, 1024, 4)), dim3(256), 0, (cudaStream_t)stream, g, (long)n, norm_ws);
+    CNB_CHECK_LAUNCH("grad_sqnorm_kernel");
+    return CNB_OK;
+}
+
+int cnb_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper, float beta1, float beta2, float eps,
+                   float weight_decay, float grad_scale, float clip_norm, const float* norm_ws, void* stream) {
+    CNB_REQUIRE(p && g && m && v && hyper && n > 0, "adamw_step: bad arguments");
+    CNB_REQUIRE(clip_norm <= 0.f || norm_ws, "adamw_step: clipping needs norm_ws");
+    CNB_LAUNCH(adamw_kernel, dim3(stream_grid(n, 1024, 4)), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, (long)n, hyper, beta1, beta2, eps,
+               weight_decay, grad_scale, clip_norm, norm_ws);
+    CNB_CHECK_LAUNCH("adamw_kernel");
+    return CNB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,112 @@
+// Shared device/host helpers for the cultionet_b200 kernels (sm_100a).
+//
+// Every kernel in this directory is written against NHWC ("pixel-major") activations: a tensor is
+// [P = B*H*W pixels][C channels] with the channel index contiguous, in either fp32 (parity mode) or
+// bf16 (throughput mode); statistics, accumulators and parameter gradients are always fp32.
+#pragma once
+
+#ifndef CNB_EMU
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#define CNB_LAUNCH(kfn, grid, block, smem, stream, ...) kfn<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#define CNB_DYN_SMEM(name) extern __shared__ __align__(1024) unsigned char name[]
+#define CNB_MEMSET_ASYNC(ptr, val, bytes, stream) cudaMemsetAsync((ptr), (val), (bytes), (stream))
+#define CNB_PEEK_ERROR() cudaPeekAtLastError()
+#define CNB_CLEAR_ERROR() ((void)cudaGetLastError())
+#define CNB_ERROR_STRING(e) cudaGetErrorString(e)
+#endif
+
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/cultionet_b200.h"
+
+typedef __nv_bfloat16 bf16_t;
+
+// ---------------------------------------------------------------------------------------------
+// error reporting: every extern "C" entry point returns 0 or a CNB_ERR_* code and leaves a message
+// ---------------------------------------------------------------------------------------------
+inline char* cnb_err_buf() {
+    static thread_local char buf[512] = {0};
+    return buf;
+}
+#define CNB_FAIL(code, ...)                               \
+    do {                                                  \
+        snprintf(cnb_err_buf(), 512, __VA_ARGS__);        \
+        return (code);                                    \
+    } while (0)
+#define CNB_REQUIRE(cond, ...)                            \
+    do {                                                  \
+        if (!(cond)) CNB_FAIL(CNB_ERR_INVALID, __VA_ARGS__); \
+    } while (0)
+#define CNB_CHECK_LAUNCH(name)                                                          \
+    do {                                                                                \
+        cudaError_t e__ = CNB_PEEK_ERROR();                                             \
+        if (e__ != cudaSuccess) {                                                       \
+            CNB_CLEAR_ERROR();                                                          \
+            CNB_FAIL(CNB_ERR_CUDA, "%s: %s", name, CNB_ERROR_STRING(e__));              \
+        }                                                                               \
+    } while (0)
+
+// dispatch on the activation dtype enum
+#define CNB_DISPATCH_DTYPE(dtype, ...)                                 \
+    do {                                                               \
+        if ((dtype) == CNB_F32) {                                      \
+            typedef float T;                                           \
+            __VA_ARGS__                                                \
+        } else if ((dtype) == CNB_BF16) {                              \
+            typedef bf16_t T;                                          \
+            __VA_ARGS__                                                \
+        } else {                                                       \
+            CNB_FAIL(CNB_ERR_INVALID, "unsupported dtype %d", (int)(dtype)); \
+        }                                                              \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// element access
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float cnb_ld(const float* p) { return *p; }
+__device__ __forceinline__ float cnb_ld(const bf16_t* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void cnb_st(float* p, float v) { *p = v; }
+__device__ __forceinline__ void cnb_st(bf16_t* p, float v) { *p = __float2bfloat16(v); }
+// value after a round trip through the storage type (what a later kernel will read back)
+__device__ __forceinline__ float cnb_round(float v, const float*) { return v; }
+__device__ __forceinline__ float cnb_round(float v, const bf16_t*) { return __bfloat162float(__float2bfloat16(v)); }
+
+__device__ __forceinline__ float cnb_exp(float x) {
+#ifdef CNB_EMU
+    return expf(x);
+#else
+    return __expf(x);
+#endif
+}
+__device__ __forceinline__ float cnb_sigmoid(float x) { return 1.0f / (1.0f + cnb_exp(-x)); }
+__device__ __forceinline__ float cnb_silu(float x) { return x * cnb_sigmoid(x); }
+// d/dx [x * sigmoid(x)]
+__device__ __forceinline__ float cnb_silu_grad(float x) {
+    float s = cnb_sigmoid(x);
+    return s * (1.0f + x * (1.0f - s));
+}
+
+__device__ __forceinline__ float cnb_warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double cnb_warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float cnb_warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+static inline int cnb_div_up(long a, long b) { return (int)((a + b - 1) / b); }
+static inline int cnb_clamp_grid(long blocks, long cap) { return (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks)); }
+
+// 148 SMs on a B200; grids of grid-stride kernels are sized in multiples of this.
+#define CNB_NUM_SMS 148

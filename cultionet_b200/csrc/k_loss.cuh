@@ -1,0 +1,186 @@
+// Tanimoto-with-complement loss and its gradient as warp-shuffle reductions, plus the flat-buffer
+// optimiser kernels.  Closed form: per (term, sample) accumulate
+//   P = sum t'p', S = sum t'^2 + p'^2, St = sum t', Sp = sum p'   (t' = t*mask, p' = p*mask, N = C*H*W elements)
+//   P' = N - St - Sp + P,  S' = 2N - 2St - 2Sp + S                 (the complement pair (1-t', 1-p'))
+//   T(P,S) = (P+eps) * (1/D) * sum_d 1/(2^d S - (2^(d+1)-1) P + eps)
+//   loss = 0.5*((1-T(P,S)) + (1-T(P',S'))), averaged over the batch.
+#pragma once
+#include "cnb_common.cuh"
+
+namespace cnb {
+
+constexpr int TN_MAX_TERMS = 4;
+struct TanimotoTerms {
+    cnb_tanimoto_term t[TN_MAX_TERMS];
+};
+
+__device__ __forceinline__ void tanimoto_elem(const cnb_tanimoto_term& tm, long b, long e, long HW, float& tq, float& pq, float& mk) {
+    const long c = e / HW, hw = e - c * HW;
+    const float p = tm.pred[(b * tm.C + c) * HW + hw];
+    float t;
+    if (tm.target_mode == 0) {
+        const float* tp = reinterpret_cast<const float*>(tm.target);
+        t = (tm.tgt_c == tm.C) ? tp[(b * tm.C + c) * HW + hw] : tp[b * HW + hw];
+    } else {
+        const long long lab = reinterpret_cast<const long long*>(tm.target)[b * HW + hw];
+        if (tm.target_mode == 1)
+            t = (lab == c) ? 1.f : 0.f;
+        else if (tm.target_mode == 2)
+            t = (lab == tm.edge_class) ? 1.f : 0.f;
+        else
+            t = (lab > 0 && lab < tm.edge_class) ? 1.f : 0.f;
+    }
+    float m = 1.f;
+    if (tm.mask_mode == 1)
+        m = reinterpret_cast<const float*>(tm.mask)[b * HW + hw];
+    else if (tm.mask_mode == 2)
+        m = (float)reinterpret_cast<const long long*>(tm.mask)[b * HW + hw];
+    else if (tm.mask_mode == 3)
+        m = (reinterpret_cast<const long long*>(tm.mask)[b * HW + hw] != -1) ? 1.f : 0.f;
+    tq = t * m;
+    pq = p * m;
+    mk = m;
+}
+
+// grid = (chunks, B, nterms); sums[(term*B + b)*4 + {P, S, St, Sp}] in fp64
+__global__ void __launch_bounds__(256) tanimoto_sums_kernel(TanimotoTerms terms, int B, long HW, double* __restrict__ sums) {
+    __shared__ double sh[4];
+    if (threadIdx.x < 4) sh[threadIdx.x] = 0.0;
+    __syncthreads();
+    const int term = blockIdx.z;
+    const long b = blockIdx.y;
+    const cnb_tanimoto_term& tm = terms.t[term];
+    const long n = (long)tm.C * HW;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long)gridDim.x * blockDim.x) {
+        float t, p, m;
+        tanimoto_elem(tm, b, e, HW, t, p, m);
+        a0 = fmaf(t, p, a0);
+        a1 += t * t + p * p;
+        a2 += t;
+        a3 += p;
+    }
+    double d0 = cnb_warp_sum((double)a0), d1 = cnb_warp_sum((double)a1), d2 = cnb_warp_sum((double)a2), d3 = cnb_warp_sum((double)a3);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&sh[0], d0);
+        atomicAdd(&sh[1], d1);
+        atomicAdd(&sh[2], d2);
+        atomicAdd(&sh[3], d3);
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) atomicAdd(sums + ((long)term * B + b) * 4 + threadIdx.x, sh[threadIdx.x]);
+}
+
+__device__ __forceinline__ void tanimoto_T(double P, double S, double eps, int depth, double& Tv, double& dP, double& dS) {
+    double sum_inv = 0.0, sum_b = 0.0, sum_a = 0.0;
+    double a = 1.0;
+    for (int d = 0; d < depth; ++d) {
+        const double bb = -(2.0 * a - 1.0);
+        const double den = a * S + bb * P + eps;
+        const double inv = 1.0 / den;
+        sum_inv += inv;
+        sum_b += bb * inv * inv;
+        sum_a += a * inv * inv;
+        a *= 2.0;
+    }
+    const double sc = 1.0 / (double)depth;
+    Tv = (P + eps) * sum_inv * sc;
+    dP = sc * (sum_inv - (P + eps) * sum_b);
+    dS = -sc * (P + eps) * sum_a;
+}
+
+// one CTA; coef[(term*B+b)*4] = dloss/d{P, S, P', S'} folded with weight/(2B); loss[0] total, loss[1+term] per term
+__global__ void __launch_bounds__(256) tanimoto_finalize_kernel(TanimotoTerms terms, int nterms, int B, long HW, float smooth, int depth,
+                                                               const double* __restrict__ sums, float* __restrict__ coef,
+                                                               float* __restrict__ loss) {
+    __shared__ double lsum[TN_MAX_TERMS];
+    if (threadIdx.x < TN_MAX_TERMS) lsum[threadIdx.x] = 0.0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < nterms * B; i += blockDim.x) {
+        const int term = i / B;
+        const double N = (double)terms.t[term].C * (double)HW;
+        const double P = sums[i * 4 + 0], S = sums[i * 4 + 1], St = sums[i * 4 + 2], Sp = sums[i * 4 + 3];
+        const double Pc = N - St - Sp + P, Sc = 2.0 * N - 2.0 * St - 2.0 * Sp + S;
+        double T1, T1p, T1s, T2, T2p, T2s;
+        tanimoto_T(P, S, (double)smooth, depth, T1, T1p, T1s);
+        tanimoto_T(Pc, Sc, (double)smooth, depth, T2, T2p, T2s);
+        const double l = 0.5 * ((1.0 - T1) + (1.0 - T2));
+        atomicAdd(&lsum[term], l / (double)B);
+        const double k = -(double)terms.t[term].weight / (2.0 * (double)B);
+        coef[i * 4 + 0] = (float)(k * T1p);
+        coef[i * 4 + 1] = (float)(k * 2.0 * T1s);
+        coef[i * 4 + 2] = (float)(-k * T2p);
+        coef[i * 4 + 3] = (float)(-k * 2.0 * T2s);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int t = 0; t < nterms; ++t) {
+            loss[1 + t] = (float)lsum[t];
+            tot += (double)terms.t[t].weight * lsum[t];
+        }
+        loss[0] = (float)tot;
+    }
+}
+
+// dpred = g * mask * (c0 t' + c1 p' + c2 (1-t') + c3 (1-p'))
+__global__ void __launch_bounds__(256) tanimoto_bwd_kernel(TanimotoTerms terms, int B, long HW, const float* __restrict__ coef,
+                                                          const float* __restrict__ gscale) {
+    const int term = blockIdx.z;
+    const long b = blockIdx.y;
+    const cnb_tanimoto_term& tm = terms.t[term];
+    const long n = (long)tm.C * HW;
+    const float g = gscale ? gscale[0] : 1.f;
+    const float* cf = coef + ((long)term * B + b) * 4;
+    const float c0 = cf[0] * g, c1 = cf[1] * g, c2 = cf[2] * g, c3 = cf[3] * g;
+    for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long)gridDim.x * blockDim.x) {
+        float t, p, m;
+        tanimoto_elem(tm, b, e, HW, t, p, m);
+        tm.dpred[b * n + e] = m * (c0 * t + c1 * p + c2 * (1.f - t) + c3 * (1.f - p));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// optimiser
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) grad_sqnorm_kernel(const float* __restrict__ g, long n, float* __restrict__ out) {
+    __shared__ float sh;
+    if (threadIdx.x == 0) sh = 0.f;
+    __syncthreads();
+    float s = 0.f;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) s = fmaf(g[i], g[i], s);
+    s = cnb_warp_sum(s);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&sh, s);
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(out, sh);
+}
+
+// torch.optim.AdamW semantics (decoupled decay, bias-corrected); optional global-norm clipping as torch.nn.utils.clip_grad_norm_
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                   float* __restrict__ v, long n, const float* __restrict__ hyper, float beta1,
+                                                   float beta2, float eps, float wd, float grad_scale, float clip_norm,
+                                                   const float* __restrict__ norm_ws) {
+    const float lr = hyper[0], step = hyper[1];
+    float gs = grad_scale;
+    if (clip_norm > 0.f) {
+        const float total = sqrtf(norm_ws[0]) * fabsf(grad_scale);
+        const float coef = clip_norm / (total + 1e-6f);
+        if (coef < 1.f) gs *= coef;
+    }
+    const float bc1 = 1.f - powf(beta1, step);
+    const float bc2 = 1.f - powf(beta2, step);
+    const float step_size = lr / bc1;
+    const float inv_sqrt_bc2 = rsqrtf(bc2);
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const float gi = g[i] * gs;
+        float pi = p[i] * (1.f - lr * wd);
+        const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+        const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        pi -= step_size * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
+        p[i] = pi;
+    }
+}
+
+}  // namespace cnb

@@ -1,0 +1,507 @@
+"""Autograd operators of the TowerUNet hot path, each a thin wrapper over the C ABI (``include/cultionet_b200.h``).
+
+Activations are pixel-major ``[B, H, W, C]`` tensors (float32 in parity mode, bfloat16 in throughput mode); parameters
+stay fp32 in the reference's own layouts so reference checkpoints load unchanged, and are repacked on the fly for the
+kernels.  Nothing here computes with torch ops: torch only owns memory, streams and the autograd tape.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, TanimotoTerm, WgradDesc, call, check_device, dtype_code, ptr, stream_ptr
+
+# weight layouts (of the fp32 parameter)
+W_CONV = "conv"      # nn.Conv2d            [N, Ctot, KH, KW]
+W_CONVT = "convT"    # nn.ConvTranspose2d   [Ctot, N, KH, KW]
+W_LINEAR = "linear"  # nn.Linear            [N, Ctot]
+
+
+def _contig(t: torch.Tensor) -> torch.Tensor:
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _weight_strides(kind: str, N: int, K: int, taps: int, for_dgrad: bool):
+    """(rows, cols, s_n, s_k, s_tap) of the packed [taps][rows][cols] view of a parameter; see cnb_pack_weight."""
+    if kind in (W_CONV, W_LINEAR):  # parameter [N][K][taps]
+        s_out, s_in = K * taps, taps
+    elif kind == W_CONVT:  # parameter [K][N][taps]
+        s_out, s_in = taps, N * taps
+    else:
+        raise ValueError(kind)
+    if not for_dgrad:
+        return N, K, s_out, s_in, 1
+    return K, N, s_in, s_out, 1
+
+
+def pack_weight(weight: torch.Tensor, kind: str, N: int, K: int, taps: int, dtype: torch.dtype, for_dgrad: bool) -> torch.Tensor:
+    rows, cols, s_n, s_k, s_tap = _weight_strides(kind, N, K, taps, for_dgrad)
+    w = _contig(weight)
+    out = torch.empty((taps, rows, cols), dtype=dtype, device=w.device)
+    call("cnb_pack_weight", ptr(w), ptr(out), dtype_code(dtype), taps, rows, cols, s_n, s_k, s_tap, stream_ptr(w))
+    return out
+
+
+def _conv_out_size(n: int, k: int, stride: int, pad: int, dil: int) -> int:
+    return (n + 2 * pad - dil * (k - 1) - 1) // stride + 1
+
+
+def _convT_out_size(n: int, k: int, stride: int, pad: int, dil: int) -> int:
+    return (n - 1) * stride - 2 * pad + dil * (k - 1) + 1
+
+
+def _launch_conv(sources, src_channels, wp, w_row_off, w_row_stride, w_tap_stride, N, bias, out, geom, transposed, dtype):
+    d = ConvDesc()
+    B, Hin, Win, Hout, Wout, KH, KW, stride, pad, dil = geom
+    esize = wp.element_size()
+    for s, (t, c) in enumerate(zip(sources, src_channels)):
+        d.src[s] = t.data_ptr()
+        d.src_c[s] = c
+        d.src_stride[s] = t.shape[-1]
+    d.nsrc = len(sources)
+    d.B, d.Hin, d.Win, d.Hout, d.Wout = B, Hin, Win, Hout, Wout
+    d.KH, d.KW, d.stride, d.pad, d.dil, d.transposed = KH, KW, stride, pad, dil, int(transposed)
+    d.w_packed = wp.data_ptr() + w_row_off * w_row_stride * esize
+    d.w_tap_stride = w_tap_stride
+    d.w_row_stride = w_row_stride
+    d.N = N
+    d.bias = bias.data_ptr() if bias is not None else None
+    d.out = out.data_ptr()
+    d.out_stride = out.shape[-1]
+    call("cnb_conv2d_fwd", C.byref(d), dtype_code(dtype), stream_ptr(out))
+
+
+class _Conv2dFn(torch.autograd.Function):
+    """y = conv(cat(sources, channel), weight) + bias over pixel-major tensors; see ``cnb_conv2d_fwd``."""
+
+    @staticmethod
+    def forward(ctx, weight, bias, kind, ksize, stride, pad, dil, transposed, out_hw, *sources):
+        check_device(weight, bias, *sources)
+        sources = [_contig(s) for s in sources]
+        x0 = sources[0]
+        dtype = x0.dtype
+        B, Hin, Win = x0.shape[0], x0.shape[1], x0.shape[2]
+        src_channels = [s.shape[-1] for s in sources]
+        Ctot = sum(src_channels)
+        KH = KW = ksize
+        taps = KH * KW
+        if kind == W_CONVT:
+            assert transposed
+            N = weight.shape[1]
+            assert weight.shape[0] == Ctot, (weight.shape, Ctot)
+        else:
+            N = weight.shape[0]
+            assert weight.shape[1] == Ctot, (weight.shape, Ctot)
+        if transposed:
+            Hout, Wout = _convT_out_size(Hin, KH, stride, pad, dil), _convT_out_size(Win, KW, stride, pad, dil)
+        else:
+            Hout, Wout = _conv_out_size(Hin, KH, stride, pad, dil), _conv_out_size(Win, KW, stride, pad, dil)
+        if out_hw is not None:
+            assert tuple(out_hw) == (Hout, Wout), (out_hw, Hout, Wout)
+        wp = pack_weight(weight, kind, N, Ctot, taps, dtype, for_dgrad=False)
+        out = torch.empty((B, Hout, Wout, N), dtype=dtype, device=x0.device)
+        geom = (B, Hin, Win, Hout, Wout, KH, KW, stride, pad, dil)
+        bias_c = _contig(bias) if bias is not None else None
+        _launch_conv(sources, src_channels, wp, 0, Ctot, N * Ctot, N, bias_c, out, geom, transposed, dtype)
+        ctx.save_for_backward(weight, *sources)
+        ctx.meta = (kind, geom, transposed, src_channels, N, Ctot, bias is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        weight, *sources = ctx.saved_tensors
+        kind, geom, transposed, src_channels, N, Ctot, has_bias = ctx.meta
+        B, Hin, Win, Hout, Wout, KH, KW, stride, pad, dil = geom
+        taps = KH * KW
+        dy = _contig(dy)
+        dtype = dy.dtype
+        dev = dy.device
+        need_w = ctx.needs_input_grad[0]
+        need_b = has_bias and ctx.needs_input_grad[1]
+        src_grads = [None] * len(sources)
+        need_src = [ctx.needs_input_grad[9 + i] for i in range(len(sources))]
+
+        if any(need_src):
+            # dgrad: the adjoint gather with the per-tap transposed weights [taps][Ctot][N]; one launch per source slice
+            wd = pack_weight(weight, kind, N, Ctot, taps, dtype, for_dgrad=True)
+            dgeom = (B, Hout, Wout, Hin, Win, KH, KW, stride, pad, dil)
+            coff = 0
+            for i, (s, c) in enumerate(zip(sources, src_channels)):
+                if need_src[i]:
+                    dx = torch.empty_like(s)
+                    _launch_conv([dy], [N], wd, coff, N, Ctot * N, c, None, dx, dgeom, not transposed, dtype)
+                    src_grads[i] = dx
+                coff += c
+
+        dw = None
+        if need_w:
+            dwp = torch.zeros((taps, N, Ctot), dtype=torch.float32, device=dev)
+            coff = 0
+            for s, c in zip(sources, src_channels):
+                d = WgradDesc()
+                d.src, d.src_c, d.src_stride = s.data_ptr(), c, s.shape[-1]
+                d.k_off, d.Ctot = coff, Ctot
+                d.B, d.Hin, d.Win, d.Hout, d.Wout = B, Hin, Win, Hout, Wout
+                d.KH, d.KW, d.stride, d.pad, d.dil, d.transposed = KH, KW, stride, pad, dil, int(transposed)
+                d.dy, d.dy_stride, d.N = dy.data_ptr(), N, N
+                d.dwp = dwp.data_ptr()
+                call("cnb_conv2d_wgrad", C.byref(d), dtype_code(dtype), stream_ptr(dy))
+                coff += c
+            dw = torch.empty_like(weight, dtype=torch.float32, memory_format=torch.contiguous_format)
+            rows, cols, s_n, s_k, s_tap = _weight_strides(kind, N, Ctot, taps, for_dgrad=False)
+            call("cnb_unpack_wgrad", ptr(dwp), ptr(dw), taps, rows, cols, s_n, s_k, s_tap, 0, stream_ptr(dy))
+
+        db = None
+        if need_b:
+            db = torch.empty((N,), dtype=torch.float32, device=dev)
+            call("cnb_bias_grad", ptr(dy), N, B * Hout * Wout, N, ptr(db), 0, dtype_code(dtype), stream_ptr(dy))
+        return (dw, db, None, None, None, None, None, None, None, *src_grads)
+
+
+def conv2d(sources: Sequence[torch.Tensor], weight, bias=None, ksize=3, stride=1, pad=1, dil=1) -> torch.Tensor:
+    """nn.Conv2d over the channel concatenation of ``sources`` (each ``[B,H,W,Cs]``)."""
+    return _Conv2dFn.apply(weight, bias, W_CONV, ksize, stride, pad, dil, False, None, *sources)
+
+
+def conv_transpose2d(x: torch.Tensor, weight, bias=None, ksize=3, stride=2, pad=1, dil=1) -> torch.Tensor:
+    """nn.ConvTranspose2d (output_padding=0): ``[B,H,W,C] -> [B,(H-1)s-2p+d(k-1)+1, ..., N]``."""
+    return _Conv2dFn.apply(weight, bias, W_CONVT, ksize, stride, pad, dil, True, None, x)
+
+
+def linear(x: torch.Tensor, weight, bias=None) -> torch.Tensor:
+    """nn.Linear over the channel axis of a pixel-major tensor."""
+    return _Conv2dFn.apply(weight, bias, W_LINEAR, 1, 1, 0, 1, False, None, x)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+class _BatchNormActFn(torch.autograd.Function):
+    """BatchNorm (batch statistics in training, running statistics in eval) + optional SiLU (+ residual)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, training, momentum, eps, act, ch_div, residual):
+        check_device(x, gamma, beta, running_mean, running_var, residual)
+        x = _contig(x)
+        dev, dtype = x.device, x.dtype
+        L = x.shape[-1]
+        P = x.numel() // L
+        Cn = gamma.shape[0]
+        st = stream_ptr(x)
+        stats = torch.empty((6, Cn), dtype=torch.float32, device=dev)  # sum, sumsq, mean, rstd, scale, shift
+        count = P * (L // Cn)
+        if training:
+            call("cnb_bn_stats", ptr(x), P, L, Cn, ch_div, ptr(stats[0]), dtype_code(dtype), st)
+            call("cnb_bn_finalize", ptr(stats[0]), count, Cn, ptr(gamma), ptr(beta), eps, momentum, ptr(running_mean),
+                 ptr(running_var), ptr(stats[2]), ptr(stats[3]), ptr(stats[4]), ptr(stats[5]), st)
+        else:
+            call("cnb_bn_finalize", None, count, Cn, ptr(gamma), ptr(beta), eps, momentum, ptr(running_mean),
+                 ptr(running_var), ptr(stats[2]), ptr(stats[3]), ptr(stats[4]), ptr(stats[5]), st)
+        y = torch.empty_like(x)
+        res = _contig(residual) if residual is not None else None
+        call("cnb_bn_act_fwd", ptr(x), ptr(stats[4]), ptr(stats[5]), ptr(res), ptr(y), P, L, Cn, ch_div, int(act),
+             dtype_code(dtype), st)
+        ctx.save_for_backward(x, gamma, beta, stats)
+        ctx.meta = (P, L, Cn, ch_div, int(act), bool(training), count, residual is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, beta, stats = ctx.saved_tensors
+        P, L, Cn, ch_div, act, training, count, has_res = ctx.meta
+        dy = _contig(dy)
+        dtype = x.dtype
+        st = stream_ptr(x)
+        dsums = torch.empty((2, Cn), dtype=torch.float32, device=x.device)
+        call("cnb_bn_act_bwd_reduce", ptr(x), ptr(dy), ptr(stats[2]), ptr(stats[3]), ptr(gamma), ptr(beta), P, L, Cn, ch_div, act,
+             ptr(dsums), dtype_code(dtype), st)
+        dx = torch.empty_like(x)
+        call("cnb_bn_act_bwd_apply", ptr(x), ptr(dy), ptr(stats[2]), ptr(stats[3]), ptr(gamma), ptr(beta), ptr(dsums), count, ptr(dx),
+             P, L, Cn, ch_div, act, int(training), dtype_code(dtype), st)
+        dres = dy if has_res else None
+        return dx, dsums[1], dsums[0], None, None, None, None, None, None, None, dres
+
+
+def batchnorm_act(x, gamma, beta, running_mean, running_var, training: bool, momentum: float = 0.1, eps: float = 1e-5,
+                  act: bool = True, ch_div: int = 1, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    return _BatchNormActFn.apply(x, gamma, beta, running_mean, running_var, training, momentum, eps, act, ch_div, residual)
+
+
+class _AddNFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, *xs):
+        check_device(*xs)
+        xs = [_contig(t) for t in xs]
+        out = torch.empty_like(xs[0])
+        p = [ptr(t) for t in xs] + [ptr(None)] * (4 - len(xs))
+        call("cnb_add_n", p[0], p[1], p[2], p[3], ptr(out), out.numel(), dtype_code(out.dtype), stream_ptr(out))
+        ctx.n = len(xs)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        return (dy,) * ctx.n
+
+
+def add_n(*xs: torch.Tensor) -> torch.Tensor:
+    xs = [t for t in xs if t is not None]
+    assert 2 <= len(xs) <= 4
+    return _AddNFn.apply(*xs)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+class _LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        check_device(x, gamma, beta)
+        x = _contig(x)
+        Cn = x.shape[-1]
+        P = x.numel() // Cn
+        y = torch.empty_like(x)
+        ms = torch.empty((2, P), dtype=torch.float32, device=x.device)
+        call("cnb_layernorm_fwd", ptr(x), ptr(gamma), ptr(beta), eps, ptr(y), ptr(ms[0]), ptr(ms[1]), P, Cn, dtype_code(x.dtype),
+             stream_ptr(x))
+        ctx.save_for_backward(x, gamma, ms)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, ms = ctx.saved_tensors
+        dy = _contig(dy)
+        Cn = x.shape[-1]
+        P = x.numel() // Cn
+        dx = torch.empty_like(x)
+        dgb = torch.zeros((2, Cn), dtype=torch.float32, device=x.device)
+        call("cnb_layernorm_bwd", ptr(x), ptr(dy), ptr(gamma), ptr(ms[0]), ptr(ms[1]), ptr(dx), ptr(dgb[0]), ptr(dgb[1]), P, Cn,
+             dtype_code(x.dtype), stream_ptr(x))
+        return dx, dgb[0], dgb[1], None
+
+
+def layernorm(x, gamma, beta, eps: float = 1e-5) -> torch.Tensor:
+    return _LayerNormFn.apply(x, gamma, beta, eps)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+class _NA2DFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, heads, ksize, dilation, scale):
+        check_device(qkv)
+        qkv = _contig(qkv)
+        B, H, W, C3 = qkv.shape
+        Cn = C3 // 3
+        hd = Cn // heads
+        out = torch.empty((B, H, W, Cn), dtype=qkv.dtype, device=qkv.device)
+        call("cnb_na2d_fwd", ptr(qkv), ptr(out), B, H, W, heads, hd, ksize, dilation, scale, dtype_code(qkv.dtype), stream_ptr(qkv))
+        ctx.save_for_backward(qkv)
+        ctx.meta = (heads, hd, ksize, dilation, scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (qkv,) = ctx.saved_tensors
+        heads, hd, ksize, dilation, scale = ctx.meta
+        dout = _contig(dout)
+        B, H, W, _ = qkv.shape
+        acc = torch.empty(qkv.shape, dtype=torch.float32, device=qkv.device)
+        dqkv = torch.empty_like(qkv)
+        call("cnb_na2d_bwd", ptr(qkv), ptr(dout), ptr(acc), ptr(dqkv), B, H, W, heads, hd, ksize, dilation, scale,
+             dtype_code(qkv.dtype), stream_ptr(qkv))
+        return dqkv, None, None, None, None
+
+
+def na2d(qkv: torch.Tensor, heads: int, ksize: int, dilation: int, scale: float) -> torch.Tensor:
+    """Neighbourhood attention core over a packed ``[B,H,W,3*heads*hd]`` qkv tensor."""
+    return _NA2DFn.apply(qkv, heads, ksize, dilation, scale)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+class _ResizeBilinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, Hout, Wout):
+        check_device(x)
+        x = _contig(x)
+        B, Hin, Win, Cn = x.shape
+        y = torch.empty((B, Hout, Wout, Cn), dtype=x.dtype, device=x.device)
+        call("cnb_resize_bilinear_fwd", ptr(x), ptr(y), B, Hin, Win, Hout, Wout, Cn, dtype_code(x.dtype), stream_ptr(x))
+        ctx.meta = (B, Hin, Win, Hout, Wout, Cn)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, Hin, Win, Hout, Wout, Cn = ctx.meta
+        dy = _contig(dy)
+        dx = torch.empty((B, Hin, Win, Cn), dtype=dy.dtype, device=dy.device)
+        call("cnb_resize_bilinear_bwd", ptr(dy), ptr(dx), B, Hin, Win, Hout, Wout, Cn, dtype_code(dy.dtype), stream_ptr(dy))
+        return dx, None, None
+
+
+def resize_bilinear(x: torch.Tensor, size) -> torch.Tensor:
+    """``check_upsample``: bilinear, align_corners=True, only when the spatial size differs."""
+    if tuple(x.shape[1:3]) == tuple(size):
+        return x
+    return _ResizeBilinearFn.apply(x, int(size[0]), int(size[1]))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+class _PreTimeConvFn(torch.autograd.Function):
+    """Conv3d(C->C, (k,1,1), bias=False) over x[B,C,T,H,W] -> pixel-major u[B,H,W,C*T'] (column = c*T' + t')."""
+
+    @staticmethod
+    def forward(ctx, x, w1, dtype):
+        check_device(x, w1)
+        if x.dtype != torch.float32:
+            raise _lib.CnbError("PreTimeReduction takes the float32 [B,C,T,H,W] input of the reference")
+        x = _contig(x)
+        w1c = _contig(w1)
+        B, Cn, Tn, H, W = x.shape
+        k = w1.shape[2]
+        Tp = Tn - k + 1
+        u = torch.empty((B, H, W, Cn * Tp), dtype=dtype, device=x.device)
+        call("cnb_pretime_conv_fwd", ptr(x), ptr(w1c), ptr(u), B, Cn, Tn, H, W, k, dtype_code(dtype), stream_ptr(x))
+        ctx.save_for_backward(x, w1)
+        return u
+
+    @staticmethod
+    def backward(ctx, du):
+        x, w1 = ctx.saved_tensors
+        if ctx.needs_input_grad[0]:
+            raise NotImplementedError("cultionet_b200: the network input x does not receive a gradient")
+        du = _contig(du)
+        B, Cn, Tn, H, W = x.shape
+        k = w1.shape[2]
+        dw = torch.zeros(w1.shape, dtype=torch.float32, device=x.device)
+        call("cnb_pretime_conv_wgrad", ptr(x), ptr(du), ptr(dw), B, Cn, Tn, H, W, k, dtype_code(du.dtype), stream_ptr(x))
+        return None, dw, None
+
+
+def pretime_conv(x: torch.Tensor, w1: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    return _PreTimeConvFn.apply(x, w1, dtype)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+class _FinalCombineFn(torch.autograd.Function):
+    """TowerUNetFinalCombine + SigmoidCrisp over the three towers' fused [B,H,W,3] streams; 16 scalar parameters."""
+
+    @staticmethod
+    def forward(ctx, ha, hb, hc, smooth, flags, *params):
+        check_device(ha, hb, hc, *params)
+        ha, hb, hc = _contig(ha), _contig(hb), _contig(hc)
+        B, H, W, _ = ha.shape
+        P = B * H * W
+        prm = torch.cat([p.reshape(-1).float() for p in params])  # 16 scalars: plumbing, not compute
+        assert prm.numel() == 16
+        out = [torch.empty((B, 1, H, W), dtype=torch.float32, device=ha.device) for _ in range(3)]
+        call("cnb_final_combine_fwd", ptr(ha), ptr(hb), ptr(hc), ptr(prm), smooth, flags, ptr(out[0]), ptr(out[1]), ptr(out[2]), P,
+             dtype_code(ha.dtype), stream_ptr(ha))
+        ctx.save_for_backward(ha, hb, hc, prm)
+        ctx.meta = (smooth, flags, P, [p.shape for p in params])
+        return out[0], out[1], out[2]
+
+    @staticmethod
+    def backward(ctx, d_dist, d_edge, d_crop):
+        ha, hb, hc, prm = ctx.saved_tensors
+        smooth, flags, P, shapes = ctx.meta
+        dev = ha.device
+        zeros = None
+
+        def g(t):
+            nonlocal zeros
+            if t is None:
+                if zeros is None:
+                    zeros = torch.zeros((P,), dtype=torch.float32, device=dev)
+                return zeros
+            return _contig(t.float())
+
+        d_dist, d_edge, d_crop = g(d_dist), g(d_edge), g(d_crop)
+        dha, dhb, dhc = torch.empty_like(ha), torch.empty_like(hb), torch.empty_like(hc)
+        dprm = torch.empty((16,), dtype=torch.float32, device=dev)
+        ws = torch.empty((32,), dtype=torch.float32, device=dev)
+        call("cnb_final_combine_bwd", ptr(ha), ptr(hb), ptr(hc), ptr(prm), smooth, flags, ptr(d_dist), ptr(d_edge), ptr(d_crop),
+             ptr(dha), ptr(dhb), ptr(dhc), ptr(dprm), ptr(ws), P, dtype_code(ha.dtype), stream_ptr(ha))
+        pgrads = [dprm[i:i + 1].view(s) for i, s in enumerate(shapes)]
+        return (dha, dhb, dhc, None, None, *pgrads)
+
+
+def final_combine(ha, hb, hc, params: Sequence[torch.Tensor], smooth: float = 1e-2, edge_activation: bool = True,
+                  mask_activation: bool = True):
+    """params: 9 gammas (dist 1-3, edge 1-3, crop 1-3), 3 conv weights, 3 conv biases, crisp gamma."""
+    flags = (1 if edge_activation else 0) | (2 if mask_activation else 0)
+    return _FinalCombineFn.apply(ha, hb, hc, smooth, flags, *params)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+TARGET_FLOAT, TARGET_ONEHOT, TARGET_EDGE, TARGET_CROP = 0, 1, 2, 3
+MASK_NONE, MASK_FLOAT, MASK_INT64, MASK_FROM_LABELS = 0, 1, 2, 3
+
+
+class TanimotoTermSpec:
+    """One (prediction, target) pair of the Tanimoto-complement loss; see ``cnb_tanimoto_term``."""
+
+    def __init__(self, target, target_mode, mask=None, mask_mode=MASK_NONE, edge_class=2, weight=1.0):
+        self.target, self.target_mode = target, target_mode
+        self.mask, self.mask_mode = mask, mask_mode
+        self.edge_class, self.weight = edge_class, weight
+
+
+class _TanimotoFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, smooth, depth, specs, *preds):
+        nterms = len(preds)
+        assert 1 <= nterms <= _lib.TN_MAX_TERMS and len(specs) == nterms
+        preds = [_contig(p.float()) for p in preds]
+        B = preds[0].shape[0]
+        HW = preds[0].shape[-2] * preds[0].shape[-1]
+        dev = preds[0].device
+        keep = []
+        terms = (TanimotoTerm * nterms)()
+        for i, (p, s) in enumerate(zip(preds, specs)):
+            assert p.dim() == 4 and p.shape[0] == B and p.shape[-2] * p.shape[-1] == HW
+            tgt = s.target
+            if s.target_mode == TARGET_FLOAT:
+                tgt = _contig(tgt.float())
+                tgt_c = 1 if tgt.dim() == 3 else tgt.shape[1]
+            else:
+                tgt = _contig(tgt.long())
+                tgt_c = 1
+            msk = s.mask
+            if s.mask_mode == MASK_FLOAT:
+                msk = _contig(msk.float())
+            elif s.mask_mode in (MASK_INT64, MASK_FROM_LABELS):
+                msk = _contig(msk.long())
+            check_device(p, tgt, msk)
+            keep += [tgt, msk]
+            terms[i].pred = p.data_ptr()
+            terms[i].target = tgt.data_ptr()
+            terms[i].mask = msk.data_ptr() if msk is not None else None
+            terms[i].dpred = None
+            terms[i].C, terms[i].tgt_c = p.shape[1], tgt_c
+            terms[i].target_mode, terms[i].mask_mode, terms[i].edge_class = s.target_mode, s.mask_mode, s.edge_class
+            terms[i].weight = s.weight
+        sums = torch.empty((nterms, B, 4), dtype=torch.float64, device=dev)
+        coef = torch.empty((nterms, B, 4), dtype=torch.float32, device=dev)
+        loss = torch.empty((1 + nterms,), dtype=torch.float32, device=dev)
+        call("cnb_tanimoto_fwd", terms, nterms, B, HW, smooth, depth, ptr(sums), ptr(coef), ptr(loss), stream_ptr(preds[0]))
+        ctx.terms, ctx.keep, ctx.preds, ctx.coef = terms, keep, preds, coef
+        ctx.meta = (nterms, B, HW)
+        ctx.mark_non_differentiable(loss)
+        total = loss[0].clone()
+        return total, loss
+
+    @staticmethod
+    def backward(ctx, gtotal, _gparts):
+        nterms, B, HW = ctx.meta
+        terms = ctx.terms
+        grads = []
+        for i, p in enumerate(ctx.preds):
+            g = torch.empty_like(p)
+            terms[i].dpred = g.data_ptr()
+            grads.append(g)
+        gs = _contig(gtotal.float().reshape(1))
+        call("cnb_tanimoto_bwd", terms, nterms, B, HW, ptr(ctx.coef), ptr(gs), stream_ptr(gs))
+        return (None, None, None, *grads)
+
+
+def tanimoto_complement(preds: Sequence[torch.Tensor], specs: Sequence[TanimotoTermSpec], smooth: float = 1e-5, depth: int = 5):
+    """Returns (sum_t weight_t * loss_t, tensor[1 + nterms] of total and per-term losses)."""
+    return _TanimotoFn.apply(smooth, depth, list(specs), *preds)

@@ -1,0 +1,200 @@
+"""ResUNet-a building blocks over pixel-major activations.
+
+Module / parameter names follow ``src/cultionet/nn/modules/convolution.py`` so reference ``state_dict``s load unchanged:
+the ``torch.nn`` layers below only *hold* parameters and buffers in the reference's layouts; every forward runs the
+sm_100a kernels of ``cultionet_b200.functional``.  Activations are ``[B, H, W, C]`` (the reference is ``[B, C, H, W]``);
+a "source list" stands for the channel concatenation the reference materialises with ``torch.cat``.
+"""
+from __future__ import annotations
+
+import typing as T
+
+import torch
+import torch.nn as nn
+
+from ... import functional as F
+from ...enums import AttentionTypes, ResBlockTypes
+from .attention import NeighborhoodAttention2D
+
+Sources = T.Union[torch.Tensor, T.Sequence[torch.Tensor]]
+
+
+def _as_sources(x: Sources) -> T.List[torch.Tensor]:
+    return [x] if isinstance(x, torch.Tensor) else list(x)
+
+
+def _require_silu(activation_type: str) -> None:
+    if activation_type != "SiLU":
+        raise NotImplementedError(
+            f"cultionet_b200 fuses SiLU into its normalisation kernels; activation_type={activation_type!r} is not built"
+        )
+
+
+def batchnorm_act(bn: nn.modules.batchnorm._BatchNorm, x: torch.Tensor, act: bool, ch_div: int = 1) -> torch.Tensor:
+    """BatchNorm2d/3d (+SiLU) with the module's parameters; batch statistics iff the module is in training mode."""
+    training = bn.training
+    if training and bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    return F.batchnorm_act(
+        x, bn.weight, bn.bias, bn.running_mean, bn.running_var, training,
+        momentum=bn.momentum if bn.momentum is not None else 0.1, eps=bn.eps, act=act, ch_div=ch_div,
+    )
+
+
+class ConvTranspose2d(nn.Module):
+    """``nn.ConvTranspose2d(k, stride, pad)`` then the bilinear ``align_corners=True`` fix-up to ``size``
+    (reference ``convolution.py:45-68`` + ``nn/functional.py:72-81``)."""
+
+    def __init__(self, in_channels: int, out_channels: int, kernel_size: int = 3, stride: int = 2, padding: int = 1):
+        super().__init__()
+        self.up_conv = nn.ConvTranspose2d(in_channels, out_channels, kernel_size=kernel_size, stride=stride, padding=padding)
+
+    def forward(self, x: torch.Tensor, size) -> torch.Tensor:
+        m = self.up_conv
+        y = F.conv_transpose2d(x, m.weight, m.bias, ksize=m.kernel_size[0], stride=m.stride[0], pad=m.padding[0])
+        return F.resize_bilinear(y, size)
+
+
+class ConvBlock2d(nn.Module):
+    """Conv2d(bias=False) -> BatchNorm2d -> [SiLU]  (reference ``convolution.py:71-120``, default ordering)."""
+
+    def __init__(self, in_channels: int, out_channels: int, kernel_size: int, padding: int = 0, dilation: int = 1,
+                 stride: int = 1, add_activation: bool = True, activation_type: str = "SiLU", batchnorm_first: bool = False):
+        super().__init__()
+        if batchnorm_first:
+            raise NotImplementedError("cultionet_b200: batchnorm_first=True is outside the built hot path (SURVEY.md 8f N4)")
+        _require_silu(activation_type)
+        layers = [
+            nn.Conv2d(in_channels, out_channels, kernel_size=kernel_size, padding=padding, dilation=dilation, stride=stride, bias=False),
+            nn.BatchNorm2d(out_channels),
+        ]
+        if add_activation:
+            layers.append(nn.SiLU())
+        self.add_activation = add_activation
+        self.seq = nn.Sequential(*layers)
+
+    def forward(self, x: Sources) -> torch.Tensor:
+        conv, bn = self.seq[0], self.seq[1]
+        y = F.conv2d(_as_sources(x), conv.weight, None, ksize=conv.kernel_size[0], stride=conv.stride[0], pad=conv.padding[0],
+                     dil=conv.dilation[0])
+        return batchnorm_act(bn, y, act=self.add_activation)
+
+
+class ResConvBlock2d(nn.Module):
+    """``num_blocks`` ConvBlock2d in sequence; block 0 always runs at dilation 1, later blocks at ``max(1, dilation-1)``
+    (reference ``convolution.py:123-176``)."""
+
+    def __init__(self, in_channels: int, out_channels: int, kernel_size: int = 3, dilation: int = 1, activation_type: str = "SiLU",
+                 num_blocks: int = 2, batchnorm_first: bool = False):
+        super().__init__()
+        assert num_blocks > 0, "There must be at least one block."
+        later = 1 if kernel_size == 1 else max(1, dilation - 1)
+        blocks = [
+            ConvBlock2d(in_channels, out_channels, kernel_size, padding=0 if kernel_size == 1 else kernel_size // 2, dilation=1,
+                        activation_type=activation_type, batchnorm_first=batchnorm_first)
+        ]
+        for _ in range(num_blocks - 1):
+            blocks.append(
+                ConvBlock2d(out_channels, out_channels, kernel_size, padding=0 if kernel_size == 1 else later, dilation=later,
+                            activation_type=activation_type, batchnorm_first=batchnorm_first)
+            )
+        self.block = nn.ModuleList(blocks)
+
+    def forward(self, x: Sources) -> torch.Tensor:
+        for layer in self.block:
+            x = layer(x)
+        return x
+
+
+class ResidualConv(nn.Module):
+    def __init__(self, *args, **kwargs):
+        super().__init__()
+        raise NotImplementedError("cultionet_b200: res_block_type='res' is outside the built hot path (SURVEY.md 8f N4)")
+
+
+class ResidualAConv(nn.Module):
+    """``skip(x) + sum_d ResConvBlock2d_d(x) [+ LN(NA(LN(skip(x))))]`` (reference ``convolution.py:250-395``)."""
+
+    def __init__(self, in_channels: int, out_channels: int, kernel_size: int = 3, num_blocks: int = 2,
+                 dilations: T.Optional[T.List[int]] = None, attention_weights: T.Optional[str] = None, activation_type: str = "SiLU",
+                 batchnorm_first: bool = False, natten_num_heads: int = 8, natten_kernel_size: int = 3, natten_dilation: int = 1,
+                 natten_attn_drop: float = 0.0, natten_proj_drop: float = 0.0):
+        super().__init__()
+        if dilations is None:
+            dilations = [1, 2]
+        self.attention_weights = attention_weights
+        if in_channels != out_channels:
+            self.skip = nn.Conv2d(in_channels, out_channels, kernel_size=1, padding=0)
+        else:
+            self.skip = nn.Identity()
+        if attention_weights is not None:
+            assert attention_weights in [AttentionTypes.NATTEN, AttentionTypes.SPATIAL_CHANNEL], "The attention method is not supported."
+            if attention_weights != AttentionTypes.NATTEN:
+                raise NotImplementedError("cultionet_b200: attention_weights='spatial_channel' is outside the built hot path (SURVEY.md 8f N4)")
+            # indices 1..3 carry the parameters (the reference has einops Rearrange layers at 0 and 4)
+            self.attention_conv = nn.Sequential(
+                nn.Identity(),
+                nn.LayerNorm(out_channels),
+                NeighborhoodAttention2D(out_channels, num_heads=natten_num_heads, kernel_size=natten_kernel_size, dilation=natten_dilation,
+                                        attn_drop=natten_attn_drop, proj_drop=natten_proj_drop),
+                nn.LayerNorm(out_channels),
+                nn.Identity(),
+            )
+        self.res_modules = nn.ModuleList([
+            ResConvBlock2d(in_channels, out_channels, kernel_size=kernel_size, dilation=d, activation_type=activation_type,
+                           num_blocks=num_blocks, batchnorm_first=batchnorm_first)
+            for d in dilations
+        ])
+
+    def forward(self, x: Sources) -> torch.Tensor:
+        sources = _as_sources(x)
+        if isinstance(self.skip, nn.Identity):
+            assert len(sources) == 1
+            skip = sources[0]
+        else:
+            skip = F.conv2d(sources, self.skip.weight, self.skip.bias, ksize=1, stride=1, pad=0)
+        terms = [skip] + [layer(sources) for layer in self.res_modules]
+        if self.attention_weights is not None:
+            ln1, na, ln2 = self.attention_conv[1], self.attention_conv[2], self.attention_conv[3]
+            a = F.layernorm(skip, ln1.weight, ln1.bias, ln1.eps)
+            a = na(a)
+            terms.append(F.layernorm(a, ln2.weight, ln2.bias, ln2.eps))
+        out = F.add_n(*terms[:4])
+        for i in range(4, len(terms), 3):
+            out = F.add_n(out, *terms[i:i + 3])
+        return out
+
+
+class PoolResidualConv(nn.Module):
+    """[3x3 stride-2 conv + BN] -> ResidualAConv -> Dropout2d (reference ``convolution.py:398-513``)."""
+
+    def __init__(self, in_channels: int, out_channels: int, dropout: float = 0.0, kernel_size: int = 3, num_blocks: int = 2,
+                 attention_weights: T.Optional[str] = None, activation_type: str = "SiLU", res_block_type: str = ResBlockTypes.RESA,
+                 dilations: T.Sequence[int] = None, pool_first: bool = True, pool_by_max: bool = False, batchnorm_first: bool = False,
+                 natten_num_heads: int = 8, natten_kernel_size: int = 3, natten_dilation: int = 1, natten_attn_drop: float = 0.0,
+                 natten_proj_drop: float = 0.0):
+        super().__init__()
+        assert res_block_type in (ResBlockTypes.RES, ResBlockTypes.RESA)
+        if res_block_type != ResBlockTypes.RESA:
+            raise NotImplementedError("cultionet_b200: res_block_type='res' is outside the built hot path (SURVEY.md 8f N4)")
+        if pool_by_max:
+            raise NotImplementedError("cultionet_b200: pool_by_max=True is outside the built hot path (SURVEY.md 8f N4)")
+        self.pool_first = pool_first
+        self.pool_by_max = pool_by_max
+        if pool_first:
+            self.pool_conv = ConvBlock2d(in_channels, out_channels, kernel_size=3, padding=1, stride=2, add_activation=False,
+                                         batchnorm_first=False)
+            in_channels = out_channels
+        self.res_conv = ResidualAConv(in_channels, out_channels, kernel_size=kernel_size, dilations=dilations, num_blocks=num_blocks,
+                                      attention_weights=attention_weights, activation_type=activation_type, batchnorm_first=batchnorm_first,
+                                      natten_num_heads=natten_num_heads, natten_kernel_size=natten_kernel_size,
+                                      natten_dilation=natten_dilation, natten_attn_drop=natten_attn_drop, natten_proj_drop=natten_proj_drop)
+        self.dropout_layer = nn.Dropout2d(p=dropout)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self.pool_first:
+            x = self.pool_conv(x)
+        x = self.res_conv(x)
+        if self.training and self.dropout_layer.p > 0:
+            raise NotImplementedError("cultionet_b200: Dropout2d in training mode is not built yet; construct with dropout=0.0")
+        return x

@@ -1,0 +1,208 @@
+/* cultionet_b200 -- C ABI of the B200-native TowerUNet hot path.
+ *
+ * One shared object (cultionet_b200/libcultionet_b200.so), extern "C", plain pointers and sizes.
+ * The reference (jgrss/cultionet) has no FFI of its own: it is pure Python over torch/cuDNN/natten.
+ * Each entry point below therefore names the reference *Python call site* whose device work it
+ * replaces (paths relative to the reference repo root, `src/cultionet/...`).
+ *
+ * Conventions
+ *   - activations are pixel-major ("NHWC"): [P = B*H*W][C], channel contiguous; `dtype` selects the
+ *     storage type of activations and packed weights (CNB_F32 parity mode, CNB_BF16 throughput mode);
+ *     statistics, parameter gradients, loss terms are always fp32 (loss partial sums fp64);
+ *   - every pointer is a device pointer unless stated; outputs and workspaces are caller-allocated;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no entry point synchronises,
+ *     allocates or frees, so calls are legal under CUDA-graph capture and from autograd worker threads;
+ *   - return value 0 = OK, otherwise a CNB_ERR_* code with a message in cnb_last_error() (thread-local).
+ */
+#ifndef CULTIONET_B200_H
+#define CULTIONET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CNB_VERSION 100 /* 0.1.0 */
+
+enum { CNB_OK = 0, CNB_ERR_INVALID = 1, CNB_ERR_CUDA = 2, CNB_ERR_UNSUPPORTED = 3 };
+enum { CNB_F32 = 0, CNB_BF16 = 1 };
+enum { CNB_MAX_SRC = 6 };
+
+int cnb_version(void);
+/* compiled-for architecture (100 for sm_100a); 0 for the CPU test interpreter build */
+int cnb_sm_arch(void);
+const char* cnb_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Implicit-GEMM convolution over a *virtual concatenation* of up to CNB_MAX_SRC pixel-major sources.
+ *   y[b,oy,ox,n] = bias[n] + sum_{tap=(ky,kx)} sum_{c} X[b, iy, ix, c] * Wp[tap][n][c]
+ *   direct     (transposed=0): iy = oy*stride - pad + ky*dil              (nn.Conv2d, nn.Linear, dgrad of ConvTranspose2d)
+ *   transposed (transposed=1): iy = (oy + pad - ky*dil)/stride if exact   (nn.ConvTranspose2d, dgrad of strided Conv2d)
+ * X is the channel-wise concatenation of the sources (torch.cat(dim=1) in the reference is never materialised).
+ * Replaces: nn.Conv2d in ConvBlock2d (nn/modules/convolution.py:88-116), the 1x1 skips (:311-318), StreamConv2d
+ * (nn/modules/unet_parts.py:205-221), nn.ConvTranspose2d (convolution.py:56-62), the qkv/proj nn.Linear of
+ * natten.NeighborhoodAttention2D (convolution.py:341-350), torch.cat in TowerUNetBlock.forward (unet_parts.py:733-758)
+ * and the autograd dgrad/wgrad of all of these.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+    const void* src[CNB_MAX_SRC];   /* source s: element (pixel p, channel c) at src[s] + p*src_stride[s] + c */
+    int32_t src_c[CNB_MAX_SRC];     /* channels taken from source s */
+    int32_t src_stride[CNB_MAX_SRC];/* elements between consecutive pixels of source s */
+    int32_t nsrc;
+    int32_t B, Hin, Win, Hout, Wout;
+    int32_t KH, KW, stride, pad, dil, transposed;
+    const void* w_packed;           /* [KH*KW][N][Ctot] in `dtype`; Ctot = sum(src_c) */
+    int64_t w_tap_stride;           /* elements between taps */
+    int32_t w_row_stride;           /* elements between rows n */
+    int32_t N;                      /* output channels */
+    const float* bias;              /* [N] fp32 or NULL */
+    void* out;                      /* element (p, n) at out + p*out_stride + n */
+    int32_t out_stride;
+} cnb_conv_desc;
+
+int cnb_conv2d_fwd(const cnb_conv_desc* d, int dtype, void* stream);
+
+/* Weight gradient of the same convolution for ONE source slice:
+ *   dWp[tap][n][k_off + c] += sum_p X_s[gather(p, tap)][c] * dY[p][n]         (fp32, atomically accumulated)
+ * `dwp` has the packed geometry [taps][N][Ctot] fp32 and must be zeroed by the caller before the first slice. */
+typedef struct {
+    const void* src; int32_t src_c, src_stride;
+    int32_t k_off, Ctot;
+    int32_t B, Hin, Win, Hout, Wout;
+    int32_t KH, KW, stride, pad, dil, transposed;
+    const void* dy; int32_t dy_stride; int32_t N;
+    float* dwp;
+} cnb_wgrad_desc;
+
+int cnb_conv2d_wgrad(const cnb_wgrad_desc* d, int dtype, void* stream);
+
+/* fp32 parameter (any strided [n][k][tap] view) -> packed [tap][N][K] in `dtype`:
+ *   wp[tap][n][k] = w[n*s_n + k*s_k + tap*s_tap]
+ * nn.Conv2d weight [Cout,Cin,kh,kw]: forward (n=Cout,k=Cin) s_n=Cin*taps,s_k=taps; dgrad (n=Cin,k=Cout) s_n=taps,s_k=Cin*taps.
+ * nn.ConvTranspose2d weight [Cin,Cout,kh,kw]: forward (n=Cout,k=Cin) s_n=taps,s_k=Cout*taps; dgrad s_n=Cout*taps,s_k=taps. */
+int cnb_pack_weight(const float* w, void* wp, int dtype, int taps, int N, int K,
+                    int64_t s_n, int64_t s_k, int64_t s_tap, void* stream);
+/* inverse scatter of a packed fp32 gradient into the parameter layout: g[...] (+)= dwp[tap][n][k] */
+int cnb_unpack_wgrad(const float* dwp, float* g, int taps, int N, int K,
+                     int64_t s_n, int64_t s_k, int64_t s_tap, int accumulate, void* stream);
+/* db[n] (+)= sum_p dy[p][n] (bias gradient) */
+int cnb_bias_grad(const void* dy, int dy_stride, int64_t P, int N, float* db, int accumulate, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * BatchNorm (+SiLU) over a [P][L] matrix whose column j belongs to channel (j / ch_div) % C.
+ * (L == C, ch_div == 1 for BatchNorm2d on pixel-major data; PreTimeReduction's BatchNorm3d uses ch_div = T'.)
+ * Replaces nn.BatchNorm2d/3d + SetActivation("SiLU") in ConvBlock2d (convolution.py:112-116) and Conv3d (models/nunet.py:40-54).
+ * ------------------------------------------------------------------------------------------------ */
+/* sums[0..C) = sum x, sums[C..2C) = sum x^2 (fp32; zeroed inside) */
+int cnb_bn_stats(const void* x, int64_t P, int L, int C, int ch_div, float* sums, int dtype, void* stream);
+/* training: mean/var from sums -> save_mean, save_rstd, scale = gamma*rstd, shift = beta - mean*scale; updates running stats
+ * (momentum, unbiased variance) when running_mean != NULL.  eval (sums == NULL): uses the running stats. */
+int cnb_bn_finalize(const float* sums, int64_t count, int C, const float* gamma, const float* beta, float eps, float momentum,
+                    float* running_mean, float* running_var, float* save_mean, float* save_rstd, float* scale, float* shift,
+                    void* stream);
+/* y = act(x*scale[ch] + shift[ch]) (+ residual) ; act: 0 none, 1 SiLU */
+int cnb_bn_act_fwd(const void* x, const float* scale, const float* shift, const void* residual, void* y,
+                   int64_t P, int L, int C, int ch_div, int act, int dtype, void* stream);
+/* backward pass 1: dsums[0..C) = sum dz, dsums[C..2C) = sum dz*xhat, dz = dy * act'(z) */
+int cnb_bn_act_bwd_reduce(const void* x, const void* dy, const float* save_mean, const float* save_rstd, const float* gamma,
+                          const float* beta, int64_t P, int L, int C, int ch_div, int act, float* dsums, int dtype, void* stream);
+/* backward pass 2: dx = gamma*rstd*(dz - dsum/count - xhat*dsum_xhat/count); also writes dgamma = dsums[C..2C), dbeta = dsums[0..C)
+ * when train_stats != 0; with train_stats == 0 (eval BN) dx = dz*gamma*rstd. */
+int cnb_bn_act_bwd_apply(const void* x, const void* dy, const float* save_mean, const float* save_rstd, const float* gamma,
+                         const float* beta, const float* dsums, int64_t count, void* dx, int64_t P, int L, int C, int ch_div,
+                         int act, int train_stats, int dtype, void* stream);
+
+/* out = a + b (+ c) (+ d), elementwise over n elements (ResidualAConv.forward sums, convolution.py:377-395) */
+int cnb_add_n(const void* a, const void* b, const void* c, const void* d, void* out, int64_t n, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * LayerNorm over the channel axis of [P][C] (nn.LayerNorm in models/nunet.py:86-90 and convolution.py:340,351)
+ * ------------------------------------------------------------------------------------------------ */
+int cnb_layernorm_fwd(const void* x, const float* gamma, const float* beta, float eps, void* y, float* save_mean, float* save_rstd,
+                      int64_t P, int C, int dtype, void* stream);
+/* dgamma/dbeta are accumulated atomically: zero them first */
+int cnb_layernorm_bwd(const void* x, const void* dy, const float* gamma, const float* save_mean, const float* save_rstd, void* dx,
+                      float* dgamma, float* dbeta, int64_t P, int C, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * 2-D neighbourhood attention core (natten==0.17.1 NeighborhoodAttention2D between its qkv and proj Linears,
+ * as configured at convolution.py:341-350; window rule in oracle/natten_ref.py).
+ * qkv: [B,H,W,3*heads*hd] with channel order (3, heads, hd); out: [B,H,W,heads*hd].
+ * ------------------------------------------------------------------------------------------------ */
+int cnb_na2d_fwd(const void* qkv, void* out, int B, int H, int W, int heads, int hd, int ksize, int dilation, float scale,
+                 int dtype, void* stream);
+/* dqkv_acc: fp32 [B,H,W,3*heads*hd] scratch (zeroed inside); dqkv: same shape in `dtype` */
+int cnb_na2d_bwd(const void* qkv, const void* dout, float* dqkv_acc, void* dqkv, int B, int H, int W, int heads, int hd, int ksize,
+                 int dilation, float scale, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Bilinear resize, align_corners=True, pixel-major (check_upsample, nn/functional.py:72-81)
+ * ------------------------------------------------------------------------------------------------ */
+int cnb_resize_bilinear_fwd(const void* x, void* y, int B, int Hin, int Win, int Hout, int Wout, int C, int dtype, void* stream);
+int cnb_resize_bilinear_bwd(const void* dy, void* dx, int B, int Hin, int Win, int Hout, int Wout, int C, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * PreTimeReduction first stage (models/nunet.py:31-39): Conv3d(C->C,(k,1,1), bias=False) over x[B,C,T,H,W] fp32.
+ *   u[p][c2*T' + t'] = sum_{c,dt} w1[c2][c][dt] * x[b,c,t'+dt,h,w],  T' = T-k+1, p = (b,h,w)
+ * ------------------------------------------------------------------------------------------------ */
+int cnb_pretime_conv_fwd(const float* x, const float* w1, void* u, int B, int C, int T, int H, int W, int k, int dtype, void* stream);
+/* dw1 (fp32 [C][C][k]) is atomically accumulated: zero it first.  The network input needs no gradient. */
+int cnb_pretime_conv_wgrad(const float* x, const void* du, float* dw1, int B, int C, int T, int H, int W, int k, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * TowerUNetFinalCombine + SigmoidCrisp (nn/modules/unet_parts.py:86-98, :148-193)
+ *   z_t = w_t * (ha[p][t]/g[t][0] + hb[p][t]/g[t][1] + hc[p][t]/g[t][2]) + b_t,  t in {0 distance, 1 edge, 2 crop}
+ *   distance = sigmoid(z_0); edge = sigmoid(z_1 / (smooth + sigmoid(crisp_gamma))); crop = sigmoid(z_2)
+ * params: fp32[16] = g[3][3], w[3], b[3], crisp_gamma ; flags bit0 edge_activation, bit1 mask_activation
+ * ------------------------------------------------------------------------------------------------ */
+int cnb_final_combine_fwd(const void* ha, const void* hb, const void* hc, const float* params, float smooth, int flags,
+                          float* distance, float* edge, float* crop, int64_t P, int dtype, void* stream);
+/* dparams fp32[16] is overwritten; red_ws: fp32[32] scratch */
+int cnb_final_combine_bwd(const void* ha, const void* hb, const void* hc, const float* params, float smooth, int flags,
+                          const float* d_distance, const float* d_edge, const float* d_crop, void* dha, void* dhb, void* dhc,
+                          float* dparams, float* red_ws, int64_t P, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Tanimoto-with-complement loss (losses/losses.py:152-218) incl. LossPreprocessing (:9-59) and the label recoding of
+ * LightningModuleMixin.get_true_labels (models/lightning.py:161-207).
+ * One "term" = one (prediction, target) pair reduced per sample over (C,H,W); the loss is
+ *   sum_terms weight_t * mean_b 0.5*((1 - T(P,S)) + (1 - T(P',S')))
+ * target_mode: 0 float targets [B,C,HW] (or [B,1,HW] broadcast when tgt_c==1)
+ *              1 int64 labels [B,HW], one-hot against the channel index      (LossPreprocessing one_hot_targets)
+ *              2 int64 labels [B,HW], target = (label == edge_class)         (true_edge)
+ *              3 int64 labels [B,HW], target = (0 < label < edge_class)      (true_crop)
+ * mask_mode:   0 none, 1 float mask [B,HW], 2 int64 mask [B,HW], 3 derived from labels: (label != -1)
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+    const float* pred;      /* [B][C][HW] fp32 */
+    const void* target;     /* see target_mode */
+    const void* mask;       /* see mask_mode (labels for mode 3) */
+    float* dpred;           /* backward only: [B][C][HW] */
+    int32_t C, tgt_c;
+    int32_t target_mode, mask_mode, edge_class;
+    float weight;
+} cnb_tanimoto_term;
+
+/* sums: fp64 [nterms][B][4] scratch {P,S,sum t,sum p} (zeroed inside); coef: fp32 [nterms][B][4] (d loss / d{P,S,P',S'} already scaled by
+ * weight/(2B)); loss: fp32[1 + nterms] = total, then each term's unweighted loss */
+int cnb_tanimoto_fwd(const cnb_tanimoto_term* terms, int nterms, int B, int64_t HW, float smooth, int depth,
+                     double* sums, float* coef, float* loss, void* stream);
+/* dpred = gscale[0] * dloss/dpred */
+int cnb_tanimoto_bwd(const cnb_tanimoto_term* terms, int nterms, int B, int64_t HW, const float* coef, const float* gscale,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Optimiser step over flat fp32 buffers (LightningModuleMixin.configure_optimizers, models/lightning.py:611-683; gradient
+ * clipping = Trainer(gradient_clip_val=1.0), model.py:168-186).
+ * ------------------------------------------------------------------------------------------------ */
+/* norm_ws: fp32[1] receives sum(g^2) (zeroed inside) */
+int cnb_grad_sqnorm(const float* g, int64_t n, float* norm_ws, void* stream);
+/* AdamW with decoupled weight decay; clip_norm <= 0 disables clipping; hyper: device fp32[2] = {lr, step (as float, >= 1)} */
+int cnb_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper, float beta1, float beta2, float eps,
+                   float weight_decay, float grad_scale, float clip_norm, const float* norm_ws, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CULTIONET_B200_H */
