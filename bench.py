@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py -- train chips/s of the TowerUNet hot path (BASELINE.json metric) on N B200s of one node.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg1|tiny] [--batch B]
+
+A step = one pass of the hot path over one batch of synthetic chips: forward + Tanimoto-complement loss + backward +
+data-parallel gradient all-reduce + AdamW, through the reference-facing API (``CultionetLitModel.training_step`` driven by
+``cultionet_b200.engine.TrainStep``).  One process per GPU (torchrun); rank 0 prints ONE JSON line.
+
+  value     chips/s with the batch already resident in HBM (CUDA events, barrier + synchronize both sides, max over ranks)
+  e2e       the same steps with the batch in pinned HOST memory: H2D copy of x/y/bdist and a D2H read of the loss inside the region
+  roofline  the dominant kernel class (implicit-GEMM convolution: fwd/dgrad/wgrad launches) timed per launch with CUDA events
+            on the launching stream in a separate instrumented pass: algorithmic FLOPs / summed launch time vs the measured
+            bf16 peak in MEASURED_PEAKS.json
+  cpu_baseline  the oracle port (oracle/towerunet_port.py: the reference's arithmetic in plain PyTorch fp32) on the host cores,
+            rank 0, N=1 only, on a bounded sample (batch 1 of the same chip shape)
+
+``--impl reference`` times that CPU port alone with all host threads (the reference is pure Python over torch and cannot travel
+to the GPU box), same metric/unit/config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+os.environ.setdefault("TORCHDYNAMO_DISABLE", "1")
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # BASELINE.json configs[1]/[2]: TowerUNet bf16 training step, batch 32 per GPU, x=[32,5,24,128,128], hidden 64
+    "cfg2": dict(B=32, C=5, T=24, H=128, W=128, hidden=64, dilations=[1, 2], dtype="bf16", fwd_gflop_per_chip=423.0),
+    # BASELINE.json configs[0]: fp32, x=[4,3,12,100,100], hidden 32 (the reference's CPU-runnable case)
+    "cfg1": dict(B=4, C=3, T=12, H=100, W=100, hidden=32, dilations=[1, 2], dtype="f32", fwd_gflop_per_chip=64.9),
+    "tiny": dict(B=2, C=3, T=8, H=32, W=32, hidden=16, dilations=[1, 2], dtype="bf16", fwd_gflop_per_chip=0.0),
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch override")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md's clocks line)."""
+
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks() -> dict:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.is_file():
+        d = json.loads(p.read_text())
+        return {"bf16_tflops": d.get("bf16_tflops_sustained", d.get("bf16_tflops")), "bf16_tflops_burst": d.get("bf16_tflops"),
+                "hbm_gbs": d.get("hbm_gbs"), "source": "measured"}
+    return {"bf16_tflops": 1400.0, "bf16_tflops_burst": 1590.0, "hbm_gbs": 6650.0, "source": "fallback"}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def make_host_batch(w: dict, batch: int, rank: int, pin: bool):
+    """Synthetic chips as SURVEY.md 8(d): x = rand, y in {0,1,2} (edge class 2), bdist = rand; seeded per rank."""
+    g = torch.Generator().manual_seed(100 + rank)
+    x = torch.rand(batch, w["C"], w["T"], w["H"], w["W"], generator=g)
+    y = torch.randint(0, 3, (batch, w["H"], w["W"]), generator=g)
+    bdist = torch.rand(batch, w["H"], w["W"], generator=g)
+    if pin:
+        x, y, bdist = x.pin_memory(), y.pin_memory(), bdist.pin_memory()
+    return x, y, bdist
+
+
+def cpu_port_chips_per_s(w: dict, steps: int, warmup: int, batch: int = 1) -> dict:
+    """fwd + loss + bwd of the oracle port on the host cores (fp32), a bounded sample of the workload."""
+    from oracle import towerunet_port as port
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    spec = port.param_spec(w["C"], w["T"], w["hidden"], w["dilations"])
+    sd = port.synth_state_dict(spec, seed=0)
+    sd = {k: (v.requires_grad_(True) if v.is_floating_point() and "running" not in k else v) for k, v in sd.items()}
+    x, y, bdist = make_host_batch(w, batch, 0, pin=False)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        out = port.towerunet_forward(sd, x, w["dilations"], training=True)
+        loss, _ = port.training_loss(out, y, bdist)
+        loss.backward()
+        for v in sd.values():
+            if v.grad is not None:
+                v.grad = None
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    sec = statistics.median(times)
+    return {"value": batch / sec, "unit": "chips/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"oracle port fp32, fwd+loss+bwd, batch {batch} of x=[{w['C']},{w['T']},{w['H']},{w['W']}] hidden {w['hidden']}, "
+                      f"median of {steps} steps after {warmup} warm-up", "s_per_step": sec}
+
+
+def run_reference_arm(args, w: dict) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base = cpu_port_chips_per_s(w, steps=args.steps, warmup=args.warmup, batch=1)
+    line = {
+        "impl": "reference", "metric": "train chips/s", "value": base["value"], "unit": "chips/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["s_per_step"] * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: TowerUNet train step x=[B,{w['C']},{w['T']},{w['H']},{w['W']}] hidden {w['hidden']}",
+                   "sample_batch": 1},
+        "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": base["value"], "unit": "chips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def main() -> None:
+    args = parse_args()
+    w = dict(WORKLOADS[args.workload])
+    if args.batch:
+        w["B"] = args.batch
+    if args.impl == "reference":
+        run_reference_arm(args, w)
+        return
+
+    import torch.distributed as dist
+
+    import cultionet_b200 as cb
+    from cultionet_b200 import _lib
+    from cultionet_b200.engine import TrainStep
+    from cultionet_b200.models.lightning import CultionetLitModel
+    from cultionet_b200.parallel import init_distributed
+
+    rank, local, world = init_distributed()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the TowerUNet hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dtype = torch.bfloat16 if w["dtype"] == "bf16" else torch.float32
+    B = w["B"]
+
+    torch.manual_seed(1234)  # identical replicas
+    model = CultionetLitModel(in_channels=w["C"], in_time=w["T"], hidden_channels=w["hidden"], dilations=w["dilations"], dropout=0.0,
+                              compute_dtype=dtype).to(dev)
+    step = TrainStep(model, total_steps=10_000)
+    hx, hy, hb = make_host_batch(w, B, rank, pin=True)
+    dbatch = cb.Data(x=hx.to(dev), y=hy.to(dev), bdist=hb.to(dev))
+    h2d_bytes = hx.numel() * hx.element_size() + hy.numel() * hy.element_size() + hb.numel() * hb.element_size()
+    # L2 hygiene: every step streams > 126 MB of activations (the input batch alone is larger at cfg2); a 256 MB flush buffer is
+    # also written between timed steps
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n) -> float:
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+            flush.zero_()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    def flush_ms(n) -> float:
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            flush.zero_()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    losses = []
+
+    def resident_step():
+        losses.append(step(dbatch))
+
+    def e2e_step():
+        b = cb.Data(x=hx.to(dev, non_blocking=True), y=hy.to(dev, non_blocking=True), bdist=hb.to(dev, non_blocking=True))
+        loss = step(b)
+        losses.append(float(loss.cpu()))  # D2H read of the step's result
+
+    for _ in range(max(args.warmup, 3)):
+        resident_step()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = _lib.launch_count()
+    ms_res = timed(resident_step, args.steps)
+    launches = (_lib.launch_count() - l0) // max(args.steps, 1)
+    clocks = sampler.stop()
+    e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    fl = flush_ms(args.steps)
+    ms_res -= fl
+    ms_e2e -= fl
+
+    chips = B * world * args.steps
+    value = chips / (ms_res / 1e3)
+    e2e_value = chips / (ms_e2e / 1e3)
+    peaks = measured_peaks()
+
+    roofline = None
+    if not args.no_roofline and rank == 0:
+        _lib.TIMER = _lib.KernelTimer()
+        nprof = min(args.steps, 3)
+        for _ in range(nprof):
+            resident_step()
+        summ = _lib.TIMER.summary()
+        _lib.TIMER = None
+        conv = {k: v for k, v in summ.items() if k.startswith("conv") and v["flops"] > 0}
+        if conv:
+            flops = sum(v["flops"] for v in conv.values())
+            ms = sum(v["ms"] for v in conv.values())
+            calls = sum(v["calls"] for v in conv.values())
+            total_ms = sum(v["ms"] for v in summ.values())
+            achieved = flops / (ms / 1e3) / 1e12
+            roofline = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                        "frac": achieved / peaks["bf16_tflops"], "traffic": None,
+                        "kernel": "implicit-GEMM convolution (fwd + dgrad + wgrad launches)", "launches_per_step": calls // nprof,
+                        "avg_launch_ms": ms / calls, "share_of_step_kernel_time": ms / total_ms, "peak_source": peaks["source"] + " (sustained)",
+                        "by_class": {k: {"calls_per_step": v["calls"] // nprof, "ms_per_step": v["ms"] / nprof,
+                                         "tflops": v["flops"] / (v["ms"] / 1e3) / 1e12} for k, v in conv.items()},
+                        "other_ms_per_step": {k: v["ms"] / nprof for k, v in sorted(summ.items(), key=lambda kv: -kv[1]["ms"])
+                                              if not k.startswith("conv")}}
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_base = cpu_port_chips_per_s(w, steps=3, warmup=1, batch=1)
+        cpu_base = {k: cpu_base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {
+            "metric": "train chips/s", "value": value, "unit": "chips/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": w["dtype"],
+            "data": "synthetic",
+            "config": {"workload": f"{args.workload}: TowerUNet train step (fwd + Tanimoto-complement loss + bwd + all-reduce + AdamW), "
+                                   f"x=[{B},{w['C']},{w['T']},{w['H']},{w['W']}] per GPU, hidden {w['hidden']}, dilations {w['dilations']}, dropout 0",
+                       "global_batch": B * world, "parallelism": f"dp{world}", "l2": "256 MB flush buffer written between timed steps "
+                       "(its time subtracted); per-step activations exceed L2",
+                       "train_gflop_per_chip": 3 * w["fwd_gflop_per_chip"]},
+            "e2e": {"value": e2e_value, "unit": "chips/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_base,
+            "model_tflops": 3 * w["fwd_gflop_per_chip"] * 1e9 * value / 1e12 if w["fwd_gflop_per_chip"] else None,
+            "final_loss": float(losses[-1]),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -102,13 +102,14 @@ _PROTOS = {
 # entry points that only exist in the nvcc build (tcgen05 / TMA kernels); filled in by later sections
 _CUDA_ONLY_PROTOS: dict = {}
 
-EXPORTED_SYMBOLS = ["cnb_version", "cnb_sm_arch", "cnb_last_error", *_PROTOS.keys()]
+EXPORTED_SYMBOLS = ["cnb_version", "cnb_sm_arch", "cnb_last_error", "cnb_launch_count", *_PROTOS.keys()]
 
 
 def _bind(lib) -> None:
     lib.cnb_version.restype = C.c_int
     lib.cnb_sm_arch.restype = C.c_int
     lib.cnb_last_error.restype = C.c_char_p
+    lib.cnb_launch_count.restype = C.c_int64
     for name, argtypes in _PROTOS.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
@@ -158,8 +159,42 @@ def has_symbol(name: str) -> bool:
     return hasattr(lib(), name)
 
 
-def call(name: str, *args) -> None:
-    rc = getattr(lib(), name)(*args)
+class KernelTimer:
+    """Optional per-call CUDA-event timing (bench.py's roofline pass): records (name, flops, bytes, start, end) per C-ABI call on
+    the stream the kernels are launched on."""
+
+    def __init__(self):
+        self.records = []
+
+    def summary(self) -> dict:
+        torch.cuda.synchronize()
+        out: dict = {}
+        for name, flops, nbytes, e0, e1 in self.records:
+            d = out.setdefault(name, {"calls": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+            d["calls"] += 1
+            d["ms"] += e0.elapsed_time(e1)
+            d["flops"] += flops or 0.0
+            d["bytes"] += nbytes or 0.0
+        return out
+
+
+TIMER: "KernelTimer | None" = None
+
+
+def launch_count() -> int:
+    return int(lib().cnb_launch_count())
+
+
+def call(name: str, *args, flops: float = None, nbytes: float = None, tag: str = None) -> None:
+    fn = getattr(lib(), name)
+    if TIMER is not None and not _is_emulator:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        TIMER.records.append((tag or name, flops, nbytes, e0, e1))
+    else:
+        rc = fn(*args)
     if rc != 0:
         msg = lib().cnb_last_error().decode("utf-8", "replace")
         raise CnbError(f"{name} failed (code {rc}): {msg}")

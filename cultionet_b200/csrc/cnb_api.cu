@@ -24,6 +24,7 @@ int cnb_sm_arch(void) {
 #endif
 }
 const char* cnb_last_error(void) { return cnb_err_buf(); }
+int64_t cnb_launch_count(void) { return (int64_t)cnb_launch_counter().load(); }
 
 // ------------------------------------------------------------------------------------------------
 static int check_conv_geom(int B, int Hin, int Win, int Hout, int Wout, int KH, int KW, int stride, int pad, int dil, int transposed) {

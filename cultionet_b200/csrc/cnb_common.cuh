@@ -9,7 +9,8 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
-#define CNB_LAUNCH(kfn, grid, block, smem, stream, ...) kfn<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#define CNB_LAUNCH(kfn, grid, block, smem, stream, ...) \
+    (cnb_count_launch(), kfn<<<grid, block, smem, stream>>>(__VA_ARGS__))
 #define CNB_DYN_SMEM(name) extern __shared__ __align__(1024) unsigned char name[]
 #define CNB_MEMSET_ASYNC(ptr, val, bytes, stream) cudaMemsetAsync((ptr), (val), (bytes), (stream))
 #define CNB_PEEK_ERROR() cudaPeekAtLastError()
@@ -17,8 +18,16 @@
 #define CNB_ERROR_STRING(e) cudaGetErrorString(e)
 #endif
 
+#include <atomic>
 #include <cstdio>
 #include <cstring>
+
+// number of kernels this library has launched (reported by bench.py as `gpu_launches`)
+inline std::atomic<long long>& cnb_launch_counter() {
+    static std::atomic<long long> n{0};
+    return n;
+}
+inline void cnb_count_launch() { cnb_launch_counter().fetch_add(1, std::memory_order_relaxed); }
 
 #include "../../include/cultionet_b200.h"
 

@@ -71,7 +71,8 @@ def _launch_conv(sources, src_channels, wp, w_row_off, w_row_stride, w_tap_strid
     d.bias = bias.data_ptr() if bias is not None else None
     d.out = out.data_ptr()
     d.out_stride = out.shape[-1]
-    call("cnb_conv2d_fwd", C.byref(d), dtype_code(dtype), stream_ptr(out))
+    flops = 2.0 * B * Hout * Wout * N * sum(src_channels) * KH * KW
+    call("cnb_conv2d_fwd", C.byref(d), dtype_code(dtype), stream_ptr(out), flops=flops, tag="conv_fwd/dgrad")
 
 
 class _Conv2dFn(torch.autograd.Function):
@@ -148,7 +149,8 @@ class _Conv2dFn(torch.autograd.Function):
                 d.KH, d.KW, d.stride, d.pad, d.dil, d.transposed = KH, KW, stride, pad, dil, int(transposed)
                 d.dy, d.dy_stride, d.N = dy.data_ptr(), N, N
                 d.dwp = dwp.data_ptr()
-                call("cnb_conv2d_wgrad", C.byref(d), dtype_code(dtype), stream_ptr(dy))
+                call("cnb_conv2d_wgrad", C.byref(d), dtype_code(dtype), stream_ptr(dy), flops=2.0 * B * Hout * Wout * N * c * taps,
+                     tag="conv_wgrad")
                 coff += c
             dw = torch.empty_like(weight, dtype=torch.float32, memory_format=torch.contiguous_format)
             rows, cols, s_n, s_k, s_tap = _weight_strides(kind, N, Ctot, taps, for_dgrad=False)

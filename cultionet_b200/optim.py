@@ -1,0 +1,98 @@
+"""Flat-buffer AdamW + global-norm clipping + OneCycle schedule on the sm_100a optimiser kernels.
+
+Mirrors ``LightningModuleMixin.configure_optimizers`` (``src/cultionet/models/lightning.py:611-683``: AdamW, betas (0.9, 0.98),
+eps 1e-4, weight decay 1e-3, OneCycleLR stepped per batch) and ``Trainer(gradient_clip_val=1.0)`` (``model.py:168-186``).
+All parameters live in ONE fp32 buffer and all gradients in another, so a step is two launches (|g|^2, AdamW) and the
+data-parallel gradient exchange is a bucketed all-reduce over contiguous slices of the gradient buffer.
+"""
+from __future__ import annotations
+
+import math
+from typing import Iterable, List, Optional
+
+import torch
+
+from . import _lib
+from ._lib import call, ptr, stream_ptr
+
+
+def one_cycle_lr(step: int, total_steps: int, max_lr: float, pct_start: float = 0.3, div_factor: float = 25.0,
+                 final_div_factor: float = 1e4) -> float:
+    """torch.optim.lr_scheduler.OneCycleLR (cosine annealing, two phases) evaluated at ``step`` (0-based)."""
+    initial = max_lr / div_factor
+    minimum = initial / final_div_factor
+    up_end = float(pct_start * total_steps) - 1.0
+    down_end = float(total_steps) - 1.0
+
+    def cos(a, b, pct):
+        return b + (a - b) / 2.0 * (math.cos(math.pi * pct) + 1.0)
+
+    if step <= up_end or down_end <= up_end:
+        return cos(initial, max_lr, step / max(up_end, 1e-12)) if up_end > 0 else max_lr
+    return cos(max_lr, minimum, min(1.0, (step - up_end) / (down_end - up_end)))
+
+
+class FlatAdamW:
+    def __init__(self, params: Iterable[torch.nn.Parameter], lr: float = 0.01, betas=(0.9, 0.98), eps: float = 1e-4,
+                 weight_decay: float = 1e-3, clip_norm: float = 1.0, total_steps: Optional[int] = None):
+        self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("FlatAdamW: no trainable parameters")
+        dev = self.params[0].device
+        _lib.check_device(*self.params)
+        n = sum(p.numel() for p in self.params)
+        self.numel = n
+        self.flat_param = torch.empty(n, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.offsets = []
+        off = 0
+        with torch.no_grad():
+            for p in self.params:
+                k = p.numel()
+                self.flat_param[off:off + k].copy_(p.detach().reshape(-1))
+                p.data = self.flat_param[off:off + k].view(p.shape)
+                p.grad = self.flat_grad[off:off + k].view(p.shape)
+                self.offsets.append((off, k))
+                off += k
+        self.lr, self.betas, self.eps, self.weight_decay, self.clip_norm = lr, betas, eps, weight_decay, clip_norm
+        self.total_steps = total_steps
+        self.step_count = 0
+        self.hyper = torch.zeros(2, dtype=torch.float32, device=dev)
+        self._hyper_host = torch.zeros(2, dtype=torch.float32).pin_memory() if dev.type == "cuda" else torch.zeros(2)
+        self.norm_ws = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.grad_scale = 1.0
+
+    def zero_grad(self) -> None:
+        """Gradients are accumulated in place into the flat buffer by autograd; re-attach views torch may have dropped."""
+        self.flat_grad.zero_()
+        for p, (off, k) in zip(self.params, self.offsets):
+            if p.grad is None or p.grad.data_ptr() != self.flat_grad.data_ptr() + 4 * off:
+                p.grad = self.flat_grad[off:off + k].view(p.shape)
+
+    def current_lr(self) -> float:
+        if self.total_steps:
+            return one_cycle_lr(min(self.step_count, self.total_steps - 1), self.total_steps, self.lr)
+        return self.lr
+
+    def step(self) -> None:
+        lr = self.current_lr()
+        self.step_count += 1
+        self._hyper_host[0] = lr
+        self._hyper_host[1] = float(self.step_count)
+        self.hyper.copy_(self._hyper_host, non_blocking=True)
+        st = stream_ptr(self.flat_param)
+        if self.clip_norm and self.clip_norm > 0:
+            call("cnb_grad_sqnorm", ptr(self.flat_grad), self.numel, ptr(self.norm_ws), st)
+        call("cnb_adamw_step", ptr(self.flat_param), ptr(self.flat_grad), ptr(self.exp_avg), ptr(self.exp_avg_sq), self.numel,
+             ptr(self.hyper), self.betas[0], self.betas[1], self.eps, self.weight_decay, self.grad_scale,
+             float(self.clip_norm or 0.0), ptr(self.norm_ws), st)
+
+    def state_dict(self) -> dict:
+        return {"step": self.step_count, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq}
+
+    def load_state_dict(self, sd: dict) -> None:
+        self.step_count = int(sd["step"])
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])

@@ -33,6 +33,8 @@ int cnb_version(void);
 /* compiled-for architecture (100 for sm_100a); 0 for the CPU test interpreter build */
 int cnb_sm_arch(void);
 const char* cnb_last_error(void);
+/* kernels launched by this library since load (bench.py reports the per-step delta as `gpu_launches`) */
+int64_t cnb_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Implicit-GEMM convolution over a *virtual concatenation* of up to CNB_MAX_SRC pixel-major sources.

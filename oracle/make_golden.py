@@ -1,0 +1,95 @@
+"""TEST INFRASTRUCTURE ONLY -- generate tests/golden/*.npz by running the REAL reference (imported from /root/reference via
+oracle/ref_loader.py) on seeded inputs and weights.  Run in the authoring container:  python -m oracle.make_golden
+
+Each fixture stores the configuration and seeds (inputs and weights are re-drawn from numpy's PCG64 by the tests, see
+``golden_case``), the three outputs on a stride-3 pixel grid, the loss terms, the L2 norm of every parameter gradient, a few
+full gradients and the updated BatchNorm running statistics digest.
+"""
+from __future__ import annotations
+
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+from oracle import towerunet_port as port  # noqa: E402
+
+CASES = {
+    "small_masked": dict(B=2, C=3, T=7, H=24, W=24, hidden=8, dilations=[1, 2], seed=11, y_low=-1),
+    "odd_dil3": dict(B=1, C=2, T=6, H=25, W=25, hidden=8, dilations=[1, 2, 3], seed=23, y_low=0),
+}
+FULL_GRADS = [
+    "pre_unet.conv3.seq.0.weight",
+    "final_combine.edge_gamma2",
+    "final_combine.final_edge.1.gamma",
+    "decoder.up_cu.res_conv.attention_conv.2.qkv.bias",
+    "final_a.fuse_conv.seq.0.weight",
+    "encoder.down_b.pool_conv.seq.1.weight",
+]
+
+
+def golden_case(cfg: dict):
+    """Seeded weights and inputs of a case (shared by the generator and the tests)."""
+    spec = port.param_spec(cfg["C"], cfg["T"], cfg["hidden"], cfg["dilations"])
+    sd = port.synth_state_dict(spec, seed=cfg["seed"])
+    rng = np.random.default_rng(cfg["seed"] + 1000)
+    x = torch.from_numpy(rng.random((cfg["B"], cfg["C"], cfg["T"], cfg["H"], cfg["W"]), dtype=np.float32))
+    y = torch.from_numpy(rng.integers(cfg["y_low"], 3, size=(cfg["B"], cfg["H"], cfg["W"]))).long()
+    bdist = torch.from_numpy(rng.random((cfg["B"], cfg["H"], cfg["W"]), dtype=np.float32))
+    return spec, sd, x, y, bdist
+
+
+def run_reference(cfg: dict):
+    from oracle.ref_loader import load_reference
+
+    ref = load_reference()
+    spec, sd, x, y, bdist = golden_case(cfg)
+    model = ref.TowerUNet(in_channels=cfg["C"], in_time=cfg["T"], hidden_channels=cfg["hidden"], dilations=cfg["dilations"])
+    model.load_state_dict(sd, strict=True)
+    model.train()
+    out = model(x)
+    cls = ref.TanimotoComplementLoss()
+    reg = ref.TanimotoComplementLoss(transform_logits=False, one_hot_targets=False)
+    mask = (y != -1).long().unsqueeze(1) if int(y.min()) == -1 else None
+    d = reg(out["distance"], bdist, mask=mask)
+    e = cls(out["edge"], (y == 2).long(), mask=mask)
+    c = cls(out["crop"], ((y > 0) & (y < 2)).long(), mask=mask)
+    loss = (d + e + c) / 3.0
+    loss.backward()
+    grads = {n: p.grad.detach().clone() for n, p in model.named_parameters()}
+    buffers = {n: b.detach().clone() for n, b in model.named_buffers()}
+    return out, (loss, d, e, c), grads, buffers
+
+
+def main() -> None:
+    out_dir = ROOT / "tests" / "golden"
+    out_dir.mkdir(parents=True, exist_ok=True)
+    for name, cfg in CASES.items():
+        out, losses, grads, buffers = run_reference(cfg)
+        names = sorted(grads)
+        arrays = {
+            "grad_names": np.array(names),
+            "grad_norms": np.array([float(grads[n].double().norm()) for n in names], dtype=np.float64),
+            "losses": np.array([float(v) for v in losses], dtype=np.float64),
+        }
+        for k in ("distance", "edge", "crop"):
+            arrays["out_" + k] = out[k].detach().numpy()[:, :, ::3, ::3].astype(np.float32)
+        for n in FULL_GRADS:
+            arrays["grad::" + n] = grads[n].numpy().astype(np.float32)
+        rm = sorted(n for n in buffers if n.endswith("running_mean"))
+        arrays["bn_names"] = np.array(rm)
+        arrays["bn_mean_norms"] = np.array([float(buffers[n].double().norm()) for n in rm])
+        arrays["bn_var_norms"] = np.array([float(buffers[n.replace("running_mean", "running_var")].double().norm()) for n in rm])
+        arrays["cfg_keys"] = np.array(sorted(k for k in cfg if k != "dilations"))
+        arrays["cfg_vals"] = np.array([cfg[k] for k in sorted(k for k in cfg if k != "dilations")], dtype=np.int64)
+        arrays["dilations"] = np.array(cfg["dilations"], dtype=np.int64)
+        np.savez_compressed(out_dir / f"towerunet_{name}.npz", **arrays)
+        print(name, "loss", arrays["losses"], "size", (out_dir / f"towerunet_{name}.npz").stat().st_size)
+
+
+if __name__ == "__main__":
+    main()

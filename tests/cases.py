@@ -1,0 +1,335 @@
+"""Operator and model parity cases shared by the CPU-interpreter tests and the `-m gpu` tests.
+
+Operator checks compare a kernel with the plain PyTorch fp32 op of the same name on the same device; in bf16 mode the inputs
+are rounded to bf16 first and the comparison tolerance is the bf16 one.  Model checks compare with the oracle port."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn.functional as TF
+
+from cultionet_b200 import functional as F
+from oracle import natten_ref
+from tests.util import rel_err
+
+
+def _tol(dtype):
+    return 2e-5 if dtype == torch.float32 else 1.5e-2
+
+
+def _mk(shape, dev, dtype, grad=True, scale=1.0, shift=0.0):
+    t = (torch.randn(*shape, device=dev) * scale + shift).to(dtype)
+    return t.requires_grad_(grad)
+
+
+def _f(t):
+    return t.detach().float().requires_grad_(t.requires_grad)
+
+
+def _check(tag, got, want, tol):
+    e = rel_err(got.float(), want)
+    assert e < tol, f"{tag}: rel err {e:.3e} >= {tol:.1e}"
+
+
+def conv_case(dev, dtype, B, H, W, cins, cout, k, stride, pad, dil, seed=0):
+    torch.manual_seed(seed)
+    xs = [_mk((B, H, W, c), dev, dtype) for c in cins]
+    w = torch.randn(cout, sum(cins), k, k, device=dev) / (sum(cins) * k * k) ** 0.5
+    w.requires_grad_(True)
+    b = torch.randn(cout, device=dev, requires_grad=True)
+    y = F.conv2d(xs, w, b, k, stride, pad, dil)
+    xr = [_f(x) for x in xs]
+    yr = TF.conv2d(torch.cat(xr, -1).permute(0, 3, 1, 2), w, b, stride=stride, padding=pad, dilation=dil).permute(0, 2, 3, 1)
+    tol = _tol(dtype)
+    _check("conv fwd", y, yr, tol)
+    g = torch.randn_like(yr)
+    gm = torch.autograd.grad(y, [*xs, w, b], g.to(dtype))
+    gr = torch.autograd.grad(yr, [*xr, w, b], g.to(dtype).float())
+    for i, (a, c) in enumerate(zip(gm, gr)):
+        _check(f"conv grad {i}", a, c, tol)
+
+
+def convT_case(dev, dtype, B, H, W, cin, cout, stride, seed=0):
+    torch.manual_seed(seed)
+    x = _mk((B, H, W, cin), dev, dtype)
+    w = torch.randn(cin, cout, 3, 3, device=dev) / (cin * 9) ** 0.5
+    w.requires_grad_(True)
+    b = torch.randn(cout, device=dev, requires_grad=True)
+    y = F.conv_transpose2d(x, w, b, 3, stride, 1)
+    xr = _f(x)
+    yr = TF.conv_transpose2d(xr.permute(0, 3, 1, 2), w, b, stride=stride, padding=1).permute(0, 2, 3, 1)
+    tol = _tol(dtype)
+    _check("convT fwd", y, yr, tol)
+    g = torch.randn_like(yr)
+    for i, (a, c) in enumerate(zip(torch.autograd.grad(y, [x, w, b], g.to(dtype)), torch.autograd.grad(yr, [xr, w, b], g.to(dtype).float()))):
+        _check(f"convT grad {i}", a, c, tol)
+
+
+def linear_case(dev, dtype, B, H, W, cin, cout, seed=0):
+    torch.manual_seed(seed)
+    x = _mk((B, H, W, cin), dev, dtype)
+    w = (torch.randn(cout, cin, device=dev) / cin ** 0.5).requires_grad_(True)
+    b = torch.randn(cout, device=dev, requires_grad=True)
+    y = F.linear(x, w, b)
+    xr = _f(x)
+    yr = TF.linear(xr, w, b)
+    tol = _tol(dtype)
+    _check("linear fwd", y, yr, tol)
+    g = torch.randn_like(yr)
+    for i, (a, c) in enumerate(zip(torch.autograd.grad(y, [x, w, b], g.to(dtype)), torch.autograd.grad(yr, [xr, w, b], g.to(dtype).float()))):
+        _check(f"linear grad {i}", a, c, tol)
+
+
+def batchnorm_case(dev, dtype, B, H, W, C, training=True, act=True, with_res=True, seed=0):
+    torch.manual_seed(seed)
+    x = _mk((B, H, W, C), dev, dtype, scale=2.0, shift=0.7)
+    gam = (torch.rand(C, device=dev) + 0.5).requires_grad_(True)
+    bet = torch.randn(C, device=dev, requires_grad=True)
+    rm, rv = torch.randn(C, device=dev) * 0.1, torch.rand(C, device=dev) + 0.5
+    rm2, rv2 = rm.clone(), rv.clone()
+    res = _mk((B, H, W, C), dev, dtype) if with_res else None
+    y = F.batchnorm_act(x, gam, bet, rm, rv, training, 0.1, 1e-5, act, 1, res)
+    xr = _f(x)
+    rr = _f(res) if with_res else None
+    z = TF.batch_norm(xr.permute(0, 3, 1, 2), rm2, rv2, gam, bet, training, 0.1, 1e-5).permute(0, 2, 3, 1)
+    yr = TF.silu(z) if act else z
+    if with_res:
+        yr = yr + rr
+    tol = _tol(dtype)
+    _check("bn fwd", y, yr, tol)
+    if training:
+        _check("bn running_mean", rm, rm2, 1e-4)
+        _check("bn running_var", rv, rv2, 1e-4)
+    g = torch.randn_like(yr)
+    ins_m = [x, gam, bet] + ([res] if with_res else [])
+    ins_r = [xr, gam, bet] + ([rr] if with_res else [])
+    for i, (a, c) in enumerate(zip(torch.autograd.grad(y, ins_m, g.to(dtype)), torch.autograd.grad(yr, ins_r, g.to(dtype).float()))):
+        _check(f"bn grad {i}", a, c, tol * (3 if dtype == torch.bfloat16 else 5))
+
+
+def batchnorm3d_case(dev, dtype, B, H, W, C, Tp, seed=0):
+    torch.manual_seed(seed)
+    u = _mk((B, H, W, C * Tp), dev, dtype)
+    gam = (torch.rand(C, device=dev) + 0.5).requires_grad_(True)
+    bet = torch.randn(C, device=dev, requires_grad=True)
+    rm, rv = torch.zeros(C, device=dev), torch.ones(C, device=dev)
+    y = F.batchnorm_act(u, gam, bet, rm, rv, True, 0.1, 1e-5, True, Tp, None)
+    ur = _f(u)
+    yr = TF.silu(TF.batch_norm(ur.reshape(B, H, W, C, Tp).permute(0, 3, 4, 1, 2), None, None, gam, bet, True, 0.1, 1e-5))
+    yr = yr.permute(0, 3, 4, 1, 2).reshape(B, H, W, C * Tp)
+    tol = _tol(dtype)
+    _check("bn3d fwd", y, yr, tol)
+    g = torch.randn_like(yr)
+    for i, (a, c) in enumerate(zip(torch.autograd.grad(y, [u, gam, bet], g.to(dtype)), torch.autograd.grad(yr, [ur, gam, bet], g.to(dtype).float()))):
+        _check(f"bn3d grad {i}", a, c, tol * 5)
+
+
+def layernorm_case(dev, dtype, B, H, W, C, seed=0):
+    torch.manual_seed(seed)
+    x = _mk((B, H, W, C), dev, dtype, scale=1.5, shift=0.3)
+    gam = torch.randn(C, device=dev, requires_grad=True)
+    bet = torch.randn(C, device=dev, requires_grad=True)
+    y = F.layernorm(x, gam, bet, 1e-5)
+    xr = _f(x)
+    yr = TF.layer_norm(xr, (C,), gam, bet, 1e-5)
+    tol = _tol(dtype)
+    _check("ln fwd", y, yr, tol)
+    g = torch.randn_like(yr)
+    for i, (a, c) in enumerate(zip(torch.autograd.grad(y, [x, gam, bet], g.to(dtype)), torch.autograd.grad(yr, [xr, gam, bet], g.to(dtype).float()))):
+        _check(f"ln grad {i}", a, c, tol * 3)
+
+
+def na_case(dev, dtype, B, H, W, heads, hd, k, d, seed=0):
+    torch.manual_seed(seed)
+    Cn = heads * hd
+    qkv = _mk((B, H, W, 3 * Cn), dev, dtype)
+    y = F.na2d(qkv, heads, k, d, hd ** -0.5)
+    qr = _f(qkv)
+    t = qr.reshape(B, H, W, 3, heads, hd).permute(3, 0, 4, 1, 2, 5)
+    a = natten_ref.na2d_qk(t[0] * hd ** -0.5, t[1], k, d).softmax(-1)
+    yr = natten_ref.na2d_av(a, t[2], k, d).permute(0, 2, 3, 1, 4).reshape(B, H, W, Cn)
+    tol = _tol(dtype)
+    _check("na fwd", y, yr, tol)
+    g = torch.randn_like(yr)
+    _check("na grad", torch.autograd.grad(y, qkv, g.to(dtype))[0], torch.autograd.grad(yr, qr, g.to(dtype).float())[0], tol * 2)
+
+
+def resize_case(dev, dtype, B, hi, wi, ho, wo, C, seed=0):
+    torch.manual_seed(seed)
+    x = _mk((B, hi, wi, C), dev, dtype)
+    y = F.resize_bilinear(x, (ho, wo))
+    xr = _f(x)
+    yr = TF.interpolate(xr.permute(0, 3, 1, 2), size=(ho, wo), mode="bilinear", align_corners=True).permute(0, 2, 3, 1)
+    tol = _tol(dtype)
+    _check("resize fwd", y, yr, tol)
+    g = torch.randn_like(yr)
+    _check("resize grad", torch.autograd.grad(y, x, g.to(dtype))[0], torch.autograd.grad(yr, xr, g.to(dtype).float())[0], tol)
+
+
+def pretime_case(dev, dtype, B, C, T, H, W, k, seed=0):
+    torch.manual_seed(seed)
+    x = torch.randn(B, C, T, H, W, device=dev)
+    w1 = torch.randn(C, C, k, 1, 1, device=dev, requires_grad=True)
+    u = F.pretime_conv(x, w1, dtype)
+    Tp = T - k + 1
+    ur = TF.conv3d(x, w1).permute(0, 3, 4, 1, 2).reshape(B, H, W, C * Tp)
+    tol = _tol(dtype)
+    _check("pretime fwd", u, ur, tol)
+    g = torch.randn_like(ur)
+    _check("pretime wgrad", torch.autograd.grad(u, w1, g.to(dtype))[0], torch.autograd.grad(ur, w1, g.to(dtype).float())[0], tol)
+
+
+def final_combine_case(dev, dtype, B, H, W, edge_activation=True, mask_activation=True, seed=0):
+    torch.manual_seed(seed)
+    hs = [_mk((B, H, W, 3), dev, dtype) for _ in range(3)]
+    params = [(torch.rand(1, device=dev) * 0.5 + 0.75).requires_grad_(True) for _ in range(9)]
+    params += [torch.randn(1, 1, 1, 1, device=dev, requires_grad=True) for _ in range(3)]
+    params += [torch.randn(1, device=dev, requires_grad=True) for _ in range(3)]
+    params += [torch.randn(1, device=dev, requires_grad=True)]
+    outs = F.final_combine(*hs, params, 1e-2, edge_activation, mask_activation)
+    hr = [_f(h) for h in hs]
+    refs = []
+    for t in range(3):
+        z = sum(hr[j][..., t] / params[t * 3 + j] for j in range(3)) * params[9 + t].reshape(()) + params[12 + t]
+        if t == 1 and edge_activation:
+            z = torch.sigmoid(z / (1e-2 + torch.sigmoid(params[15])))
+        elif t == 0 or (t == 2 and mask_activation):
+            z = torch.sigmoid(z)
+        refs.append(z.unsqueeze(1))
+    tol = _tol(dtype)
+    gs = [torch.randn_like(r) for r in refs]
+    for o, r in zip(outs, refs):
+        assert o.shape == r.shape
+        _check("combine fwd", o, r, tol)
+    gm = torch.autograd.grad(outs, [*hs, *params], gs, allow_unused=True)
+    gr = torch.autograd.grad(refs, [*hr, *params], gs, allow_unused=True)
+    for i, (a, c) in enumerate(zip(gm, gr)):
+        if c is None:
+            continue
+        _check(f"combine grad {i}", a, c, tol * 3)
+
+
+def loss_case(dev, B, H, W, y_low=-1, seed=0):
+    from cultionet_b200.losses import tower_unet_loss
+    from oracle import towerunet_port as port
+
+    torch.manual_seed(seed)
+    preds = {k: torch.rand(B, 1, H, W, device=dev, requires_grad=True) for k in ("distance", "edge", "crop")}
+    y = torch.randint(y_low, 3, (B, H, W), device=dev)
+    bdist = torch.rand(B, H, W, device=dev)
+    total, parts = tower_unet_loss(preds, y, bdist)
+    want, wparts = port.training_loss(preds, y, bdist)
+    assert abs(float(total) - float(want)) < 1e-5 * max(1.0, abs(float(want)))
+    assert np.allclose(parts[1:].cpu().numpy(), [float(wparts[k]) for k in ("dloss", "eloss", "closs")], rtol=1e-5)
+    gm = torch.autograd.grad(total, list(preds.values()))
+    gr = torch.autograd.grad(want, list(preds.values()))
+    for a, c in zip(gm, gr):
+        _check("loss grad", a, c, 1e-4)
+
+
+def adamw_case(dev, n=10007, steps=3, clip=1.0, seed=0):
+    import ctypes as C
+
+    from cultionet_b200 import _lib
+
+    torch.manual_seed(seed)
+    p = torch.randn(n, device=dev)
+    pr = p.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([pr], lr=0.01, weight_decay=1e-3, eps=1e-4, betas=(0.9, 0.98))
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    hyper = torch.zeros(2, device=dev)
+    ws = torch.zeros(1, device=dev)
+    for s in range(1, steps + 1):
+        g = torch.randn(n, device=dev) * (3.0 if s == 1 else 0.001)
+        pr.grad = g.clone()
+        torch.nn.utils.clip_grad_norm_([pr], clip)
+        opt.step()
+        hyper.copy_(torch.tensor([0.01, float(s)]))
+        st = _lib.stream_ptr(p)
+        _lib.call("cnb_grad_sqnorm", _lib.ptr(g), n, _lib.ptr(ws), st)
+        _lib.call("cnb_adamw_step", _lib.ptr(p), _lib.ptr(g), _lib.ptr(m), _lib.ptr(v), n, _lib.ptr(hyper), 0.9, 0.98, 1e-4, 1e-3, 1.0, clip,
+                  _lib.ptr(ws), st)
+        assert rel_err(p, pr) < 1e-5, f"adamw step {s}"
+
+
+def model_vs_golden(dev, name, dtype=torch.float32):
+    """The product model against the golden vectors the REAL reference produced (tests/golden, oracle/make_golden.py)."""
+    from cultionet_b200.losses import tower_unet_loss
+    from oracle.make_golden import FULL_GRADS, golden_case
+    from tests.util import MASK_AGREEMENT, TOL_GRAD_FP32, TOL_OUT_BF16, TOL_OUT_FP32, load_golden, mine_from_state_dict
+
+    cfg, z = load_golden(name)
+    spec, sd, x, y, bdist = golden_case(cfg)
+    model = mine_from_state_dict(cfg, sd, dev, dtype).train()
+    out = model(x.to(dev))
+    tol = TOL_OUT_FP32 if dtype == torch.float32 else TOL_OUT_BF16
+    for k in ("distance", "edge", "crop"):
+        got = out[k][:, :, ::3, ::3]
+        want = torch.from_numpy(z["out_" + k])
+        assert rel_err(got, want) < tol, (k, rel_err(got, want))
+    crop_agree = ((out["crop"][:, :, ::3, ::3].cpu() > 0.5) == (torch.from_numpy(z["out_crop"]) > 0.5)).float().mean()
+    if dtype == torch.float32:
+        assert float(crop_agree) >= MASK_AGREEMENT
+    loss, parts = tower_unet_loss(out, y.to(dev), bdist.to(dev))
+    assert np.allclose(parts.detach().cpu().numpy(), z["losses"], rtol=tol, atol=1e-6), (parts, z["losses"])
+    loss.backward()
+    if dtype == torch.float32:
+        grads = dict(model.named_parameters())
+        names = [str(n) for n in z["grad_names"]]
+        norms = np.array([float(grads[n].grad.double().norm()) for n in names])
+        big = z["grad_norms"] > 1e-6
+        assert np.allclose(norms[big], z["grad_norms"][big], rtol=TOL_GRAD_FP32), np.abs(norms[big] / z["grad_norms"][big] - 1).max()
+        for n in FULL_GRADS:
+            assert rel_err(grads[n].grad, torch.from_numpy(z["grad::" + n])) < TOL_GRAD_FP32, n
+        bufs = dict(model.named_buffers())
+        rmn = np.array([float(bufs[str(n)].double().norm()) for n in z["bn_names"]])
+        rvn = np.array([float(bufs[str(n).replace("running_mean", "running_var")].double().norm()) for n in z["bn_names"]])
+        assert np.allclose(rvn, z["bn_var_norms"], rtol=1e-3)
+        assert np.allclose(rmn, z["bn_mean_norms"], rtol=1e-3, atol=1e-5)
+
+
+def model_vs_port(dev, cfg, dtype=torch.float32, training=True, seed=3, check_grads=True):
+    """The product model against the oracle port on the same seeded inputs and weights (any size)."""
+    from cultionet_b200.losses import tower_unet_loss
+    from oracle import towerunet_port as port
+    from tests.util import MASK_AGREEMENT, TOL_GRAD_FP32, TOL_OUT_BF16, TOL_OUT_FP32, mine_from_state_dict
+
+    spec = port.param_spec(cfg["C"], cfg["T"], cfg["hidden"], cfg["dilations"])
+    sd = port.synth_state_dict(spec, seed=seed)
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(cfg["B"], cfg["C"], cfg["T"], cfg["H"], cfg["W"], generator=g)
+    y = torch.randint(cfg.get("y_low", 0), 3, (cfg["B"], cfg["H"], cfg["W"]), generator=g)
+    bdist = torch.rand(cfg["B"], cfg["H"], cfg["W"], generator=g)
+    model = mine_from_state_dict(cfg, sd, dev, dtype).train(training)
+    odev = dev  # the port runs in fp32 on the same device (TF32 disabled by conftest)
+    sdo = {k: v.to(odev) for k, v in sd.items()}
+    sdo = {k: (v.requires_grad_(True) if v.is_floating_point() and "running" not in k else v) for k, v in sdo.items()}
+    want = port.towerunet_forward(sdo, x.to(odev), cfg["dilations"], training=training, natten_params=cfg.get("natten"))
+    out = model(x.to(dev))
+    tol = TOL_OUT_FP32 if dtype == torch.float32 else TOL_OUT_BF16
+    errs = {k: rel_err(out[k], want[k]) for k in ("distance", "edge", "crop")}
+    assert all(e < tol for e in errs.values()), errs
+    agree = float(((out["crop"] > 0.5) == (want["crop"] > 0.5)).float().mean())
+    if dtype == torch.float32:
+        assert agree >= MASK_AGREEMENT, agree
+    report = {"out_err": errs, "crop_agreement": agree}
+    if training and check_grads:
+        loss, parts = tower_unet_loss(out, y.to(dev), bdist.to(dev))
+        wloss, _ = port.training_loss(want, y.to(odev), bdist.to(odev))
+        assert abs(float(loss) - float(wloss)) < tol * abs(float(wloss)), (float(loss), float(wloss))
+        report["loss"] = (float(loss), float(wloss))
+        loss.backward()
+        wloss.backward()
+        worst = 0.0
+        worst_name = ""
+        for n, p in model.named_parameters():
+            gw = sdo[n].grad
+            if gw is None or float(gw.norm()) < 1e-7:
+                continue
+            e = rel_err(p.grad, gw)
+            if e > worst:
+                worst, worst_name = e, n
+        report["worst_grad"] = (worst, worst_name)
+        if dtype == torch.float32:
+            assert worst < TOL_GRAD_FP32, (worst, worst_name)
+    return report

@@ -315,6 +315,7 @@ inline T __ldg(const T* p) {
 inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 
+inline void cnb_count_launch();
 #define CNB_LAUNCH(kfn, grid, block, smem, stream, ...) \
-    cnb_emu::launch(dim3(grid), dim3(block), (size_t)(smem), [=]() { kfn(__VA_ARGS__); })
+    (cnb_count_launch(), cnb_emu::launch(dim3(grid), dim3(block), (size_t)(smem), [=]() { kfn(__VA_ARGS__); }))
 #define CNB_DYN_SMEM(name) unsigned char* name = cnb_emu::g_blk->dyn_smem

@@ -1,0 +1,62 @@
+"""Host-side behaviour of the reference-facing surface (no kernels beyond the CPU interpreter)."""
+import pytest
+import torch
+
+import cultionet_b200 as cb
+from cultionet_b200.enums import InferenceNames
+
+
+def test_state_dict_keys_match_reference_inventory():
+    from oracle import towerunet_port as port
+
+    m = cb.TowerUNet(in_channels=3, in_time=8, hidden_channels=8, dilations=[1, 2, 3])
+    spec = dict(port.param_spec(3, 8, 8, [1, 2, 3]))
+    sd = m.state_dict()
+    assert sorted(sd) == sorted(spec)
+    assert all(tuple(sd[k].shape) == tuple(spec[k]) for k in sd)
+
+
+def test_loads_torch_compile_prefixed_checkpoints():
+    # the reference wraps pre_unet in torch.compile (nunet.py:141): keys may be `pre_unet._orig_mod.*`
+    m = cb.TowerUNet(in_channels=2, in_time=6, hidden_channels=8)
+    sd = {k.replace("pre_unet.", "pre_unet._orig_mod."): v for k, v in m.state_dict().items()}
+    m2 = cb.TowerUNet(in_channels=2, in_time=6, hidden_channels=8)
+    m2.load_state_dict(sd, strict=True)
+    assert torch.equal(m2.pre_unet.conv3.seq[0].weight, m.pre_unet.conv3.seq[0].weight)
+
+
+def test_data_container_contract():
+    d = cb.Data(x=torch.zeros(2, 3, 4, 5, 6), y=torch.zeros(2, 5, 6), bdist=torch.zeros(2, 5, 6), lon=torch.zeros(2), lat=torch.zeros(2))
+    assert (d.num_samples, d.num_channels, d.num_time, d.height, d.width) == (2, 3, 4, 5, 6)
+    c = d.copy()
+    c.x += 1
+    assert float(d.x.sum()) == 0.0
+    with pytest.raises(AssertionError):
+        cb.Data(x=torch.zeros(1), bad="string")
+
+
+def test_unbuilt_options_fail_loudly():
+    with pytest.raises(NotImplementedError):
+        cb.TowerUNet(in_channels=2, in_time=6, hidden_channels=8, res_block_type="res")
+    with pytest.raises(NotImplementedError):
+        cb.TowerUNet(in_channels=2, in_time=6, hidden_channels=8, pool_by_max=True)
+    with pytest.raises(NotImplementedError):
+        cb.TowerUNet(in_channels=2, in_time=6, hidden_channels=8, attention_weights="spatial_channel")
+    with pytest.raises(AssertionError):
+        cb.CultioNet(in_channels=2, in_time=6, model_type="UNet3")
+
+
+def test_cultionet_forward_adds_reference_keys(dev):
+    model = cb.CultioNet(in_channels=2, in_time=6, hidden_channels=8, dropout=0.0)
+    batch = cb.Data(x=torch.rand(1, 2, 6, 16, 16), lon=torch.zeros(1), lat=torch.zeros(1))
+    out = model(batch)
+    for k in (InferenceNames.DISTANCE, InferenceNames.EDGE, InferenceNames.CROP):
+        assert out[k].shape == (1, 1, 16, 16)
+        assert float(out[k].min()) >= 0.0 and float(out[k].max()) <= 1.0
+    assert out[InferenceNames.CROP_TYPE] is None and out["classes_l2"] is None and out["classes_l3"] is None
+
+
+def test_bad_input_shape_raises(dev):
+    m = cb.TowerUNet(in_channels=2, in_time=6, hidden_channels=8)
+    with pytest.raises(ValueError):
+        m(torch.rand(1, 3, 6, 16, 16))

@@ -1,0 +1,94 @@
+"""`-m "not gpu"`: kernel arithmetic and module wiring checked on the CPU kernel interpreter (tests/emu) at small sizes."""
+import pytest
+import torch
+
+from tests import cases
+
+F32 = torch.float32
+BF16 = torch.bfloat16
+
+
+@pytest.mark.parametrize("dtype", [F32, BF16])
+@pytest.mark.parametrize("geom", [(3, 1, 1, 1), (3, 2, 1, 1), (3, 1, 2, 2), (1, 1, 0, 1)])
+def test_conv(dev, dtype, geom):
+    k, s, p, d = geom
+    cases.conv_case(dev, dtype, 2, 9, 11, [5, 7], 6, k, s, p, d)
+
+
+def test_conv_wide_tiles(dev):
+    cases.conv_case(dev, F32, 1, 10, 13, [70, 3], 67, 3, 1, 1, 1)
+
+
+@pytest.mark.parametrize("stride", [2, 4])
+def test_conv_transpose(dev, stride):
+    cases.convT_case(dev, F32, 2, 7, 6, 5, 4, stride)
+
+
+def test_linear(dev):
+    cases.linear_case(dev, F32, 2, 5, 7, 10, 21)
+
+
+@pytest.mark.parametrize("training,act,res", [(True, True, True), (True, False, False), (False, True, False)])
+def test_batchnorm(dev, training, act, res):
+    cases.batchnorm_case(dev, F32, 2, 9, 11, 6, training, act, res)
+
+
+def test_batchnorm_bf16(dev):
+    cases.batchnorm_case(dev, BF16, 2, 9, 11, 6)
+
+
+def test_batchnorm3d_channel_map(dev):
+    cases.batchnorm3d_case(dev, F32, 2, 5, 6, 3, 4)
+
+
+@pytest.mark.parametrize("C", [8, 40, 100])
+def test_layernorm(dev, C):
+    cases.layernorm_case(dev, F32, 2, 5, 7, C)
+
+
+@pytest.mark.parametrize("cfg", [(2, 8, 3, 1, 7, 9), (2, 16, 3, 2, 9, 8), (1, 40, 7, 2, 15, 14), (4, 4, 5, 1, 6, 6), (8, 2, 3, 1, 3, 3)])
+def test_neighborhood_attention(dev, cfg):
+    heads, hd, k, d, H, W = cfg
+    cases.na_case(dev, F32, 2, H, W, heads, hd, k, d)
+
+
+def test_neighborhood_attention_rejects_small_input(dev):
+    from cultionet_b200 import _lib
+    from cultionet_b200 import functional as F
+
+    with pytest.raises(_lib.CnbError):
+        F.na2d(torch.zeros(1, 4, 4, 3 * 8), 2, 3, 2, 0.5)  # k*d = 6 > 4, natten raises too
+
+
+@pytest.mark.parametrize("sizes", [(7, 7, 8, 8), (13, 13, 25, 25), (5, 9, 12, 10), (10, 10, 7, 7), (1, 1, 4, 4)])
+def test_resize_bilinear(dev, sizes):
+    cases.resize_case(dev, F32, 2, *sizes, 3)
+
+
+@pytest.mark.parametrize("k", [3, 5])
+def test_pretime_conv(dev, k):
+    cases.pretime_case(dev, F32, 2, 3, 12, 5, 6, k)
+
+
+@pytest.mark.parametrize("flags", [(True, True), (False, False)])
+def test_final_combine(dev, flags):
+    cases.final_combine_case(dev, F32, 2, 6, 7, *flags)
+
+
+@pytest.mark.parametrize("y_low", [-1, 0])
+def test_training_loss(dev, y_low):
+    cases.loss_case(dev, 3, 10, 12, y_low)
+
+
+def test_adamw_and_clipping(dev):
+    cases.adamw_case(dev)
+
+
+@pytest.mark.parametrize("name", ["small_masked", "odd_dil3"])
+def test_model_reproduces_reference_golden(dev, name):
+    cases.model_vs_golden(dev, name)
+
+
+def test_model_eval_mode_matches_port(dev):
+    cfg = dict(B=1, C=2, T=6, H=16, W=16, hidden=8, dilations=[1, 2])
+    cases.model_vs_port(dev, cfg, training=False)
