@@ -73,6 +73,9 @@ _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 # name -> argtypes; every function returns int
 _PROTOS = {
     "cnb_conv2d_fwd": [C.POINTER(ConvDesc), _i, _vp],
+    "cnb_conv2d_fwd_generic": [C.POINTER(ConvDesc), _i, _vp],
+    "cnb_conv2d_fwd_tc": [C.POINTER(ConvDesc), _i, _vp],
+    "cnb_conv2d_tc_eligible": [C.POINTER(ConvDesc), _i],
     "cnb_conv2d_wgrad": [C.POINTER(WgradDesc), _i, _vp],
     "cnb_pack_weight": [_vp, _vp, _i, _i, _i, _i, _i64, _i64, _i64, _vp],
     "cnb_unpack_wgrad": [_vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i, _vp],

@@ -2,6 +2,7 @@
 // Argument validation + launch only: no allocation, no synchronisation, everything on the caller's stream.
 #include "cnb_common.cuh"
 #include "k_conv_generic.cuh"
+#include "k_conv_tc.cuh"
 #include "k_loss.cuh"
 #include "k_misc.cuh"
 #include "k_na.cuh"
@@ -45,7 +46,7 @@ static int check_conv_geom(int B, int Hin, int Win, int Hout, int Wout, int KH, 
     return CNB_OK;
 }
 
-int cnb_conv2d_fwd(const cnb_conv_desc* d, int dtype, void* stream) {
+static int check_conv_desc(const cnb_conv_desc* d) {
     CNB_REQUIRE(d != nullptr, "conv2d_fwd: null descriptor");
     CNB_REQUIRE(d->nsrc >= 1 && d->nsrc <= CNB_MAX_SRC, "conv2d_fwd: nsrc=%d", d->nsrc);
     int rc = check_conv_geom(d->B, d->Hin, d->Win, d->Hout, d->Wout, d->KH, d->KW, d->stride, d->pad, d->dil, d->transposed);
@@ -56,11 +57,50 @@ int cnb_conv2d_fwd(const cnb_conv_desc* d, int dtype, void* stream) {
         ctot += d->src_c[s];
     }
     CNB_REQUIRE(d->w_packed && d->out && d->N > 0 && d->out_stride >= d->N && d->w_row_stride >= ctot, "conv2d_fwd: bad weight/output");
+    return CNB_OK;
+}
+
+int cnb_conv2d_fwd_generic(const cnb_conv_desc* d, int dtype, void* stream) {
+    int rc = check_conv_desc(d);
+    if (rc) return rc;
     const long M = (long)d->B * d->Hout * d->Wout;
     dim3 grid(cnb_div_up(M, CG_BM), cnb_div_up(d->N, CG_BN));
     CNB_DISPATCH_DTYPE(dtype, { CNB_LAUNCH((conv_fwd_generic_kernel<T>), grid, dim3(256), 0, (cudaStream_t)stream, *d); });
     CNB_CHECK_LAUNCH("conv_fwd_generic_kernel");
     return CNB_OK;
+}
+
+int cnb_conv2d_tc_eligible(const cnb_conv_desc* d, int dtype) {
+#ifdef CNB_EMU
+    (void)d;
+    (void)dtype;
+    return 0;
+#else
+    if (check_conv_desc(d)) return 0;
+    return tc::eligible(d, dtype) ? 1 : 0;
+#endif
+}
+
+int cnb_conv2d_fwd_tc(const cnb_conv_desc* d, int dtype, void* stream) {
+#ifdef CNB_EMU
+    (void)d;
+    (void)dtype;
+    (void)stream;
+    CNB_FAIL(CNB_ERR_UNSUPPORTED, "the tcgen05 kernel exists only in the sm_100a build");
+#else
+    int rc = check_conv_desc(d);
+    if (rc) return rc;
+    if (!tc::eligible(d, dtype)) CNB_FAIL(CNB_ERR_UNSUPPORTED, "conv2d_fwd_tc: shape/dtype not eligible for the tcgen05 kernel");
+    rc = tc::conv_tc_launch(d, (cudaStream_t)stream);
+    if (rc) CNB_FAIL(CNB_ERR_CUDA, "conv2d_fwd_tc: tensor-map encode or launch configuration failed (%d)", rc);
+    CNB_CHECK_LAUNCH("conv_tc_kernel");
+    return CNB_OK;
+#endif
+}
+
+int cnb_conv2d_fwd(const cnb_conv_desc* d, int dtype, void* stream) {
+    if (cnb_conv2d_tc_eligible(d, dtype)) return cnb_conv2d_fwd_tc(d, dtype, stream);
+    return cnb_conv2d_fwd_generic(d, dtype, stream);
 }
 
 int cnb_conv2d_wgrad(const cnb_wgrad_desc* d, int dtype, void* stream) {

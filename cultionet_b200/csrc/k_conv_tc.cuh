@@ -1,0 +1,462 @@
+// Implicit-GEMM convolution on the 5th-generation tensor cores (sm_100a): tcgen05.mma with TMEM accumulators, operands
+// staged by TMA (cp.async.bulk.tensor) into 128B-swizzled shared memory, warp-specialised and persistent.
+//
+//   D[128 pixels x BN channels] += A[128 pixels x 64 ch] * B[BN x 64 ch]^T   per (tap, source, 64-channel chunk)
+//
+// * A tile = a TH x TW patch of ONE image (TH*TW = 128) of a pixel-major bf16 tensor, fetched with a 4-D tensor map
+//   {C, W, H, B} and box {64, TW, TH, 1} at the tap-shifted coordinate; out-of-image coordinates are zero-filled by TMA, which
+//   IS the convolution's zero padding.  Box rows are 128 bytes => the K-major SWIZZLE_128B canonical UMMA layout (SBO 1024 B).
+// * B tile = BN rows of the packed weights [tap][N][Ctot] (3-D map, box {64, BN, 1}), same layout.
+// * the K loop walks taps x sources x chunks, so the UNet3+ concatenation is never materialised (one tensor map per source).
+// * accumulators are double-buffered in TMEM (2 x BN fp32 columns): the 4 epilogue warps drain tile i (tcgen05.ld -> +bias ->
+//   bf16 -> global) while the MMA warp already runs tile i+1.
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue (TMEM lane
+// quadrant = warp_id % 4).  One CTA per SM, static round-robin tile schedule.
+#pragma once
+#ifndef CNB_EMU
+#include <cuda.h>
+
+#include "cnb_common.cuh"
+
+namespace cnb {
+namespace tc {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int A_BYTES = BM * BK * 2;
+constexpr int NUM_THREADS = 192;
+constexpr int MAX_TAPS = 16;
+
+struct ConvTcParams {
+    CUtensorMap tmA[CNB_MAX_SRC];
+    CUtensorMap tmB;
+    int nsrc;
+    int chunks[CNB_MAX_SRC];  // 64-channel chunks per source
+    int koff[CNB_MAX_SRC];    // channel offset of the source inside Ctot
+    int ntaps;
+    int tap_dy[MAX_TAPS], tap_dx[MAX_TAPS], tap_w[MAX_TAPS];  // input offset and weight-tap index per tap
+    int Bn, Hv, Wv;           // iteration domain per image
+    int TH, TW, tiles_h, tiles_w;
+    int N, n_tiles;
+    int Hout, Wout, osy, osx, ooy, oox;  // output pixel = (vy*osy + ooy, vx*osx + oox)
+    bf16_t* out;
+    int out_stride;
+    const float* bias;
+    int num_tiles;
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// bounded wait: a protocol bug must trap (error returned to the host) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) break;
+        if (clock64() - t0 > 4000000000LL) {
+            printf("cultionet_b200: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", (int)blockIdx.x, (int)threadIdx.x, bar,
+                   parity);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+                 "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+                 "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);  // start address            bits [0,14)
+    d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major) bits [16,30)
+    d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset       bits [32,46)
+    d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell) bits [46,48)
+    d |= (uint64_t)2 << 61;                        // SWIZZLE_128B             bits [61,64)
+    return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=BN
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+template <int BN>
+struct Cfg {
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+    static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // power of two for BN in {64,128,256}
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
+    using C = Cfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;          // SWIZZLE_128B atoms need 1024 B alignment
+    uint8_t* base_ptr = smem_raw + (base - raw);
+    const uint32_t bars = base + C::STAGES * C::STAGE_BYTES;  // full[S] empty[S] tmem_full[2] tmem_empty[2] slot
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (C::STAGES + s); };
+    auto tfull_bar = [&](int a) { return bars + 8u * (2 * C::STAGES + a); };
+    auto tempty_bar = [&](int a) { return bars + 8u * (2 * C::STAGES + 2 + a); };
+    const uint32_t slot = bars + 8u * (2 * C::STAGES + 4);
+    volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + C::STAGES * C::STAGE_BYTES + 8 * (2 * C::STAGES + 4));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < p.nsrc; ++s) tma_prefetch_desc(&p.tmA[s]);
+        tma_prefetch_desc(&p.tmB);
+        for (int s = 0; s < C::STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 4);  // one arrive per epilogue warp
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(slot, C::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *slot_ptr;
+
+    int chunks_per_tap = 0;
+    for (int s = 0; s < p.nsrc; ++s) chunks_per_tap += p.chunks[s];
+    const int m_tiles = p.Bn * p.tiles_h * p.tiles_w;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int nt = tile / m_tiles;
+                int mt = tile - nt * m_tiles;
+                const int tw = mt % p.tiles_w;
+                mt /= p.tiles_w;
+                const int th = mt % p.tiles_h;
+                const int b = mt / p.tiles_h;
+                const int y0 = th * p.TH, x0 = tw * p.TW, n0 = nt * BN;
+                for (int t = 0; t < p.ntaps; ++t) {
+                    const int cy = y0 + p.tap_dy[t], cx = x0 + p.tap_dx[t], wt = p.tap_w[t];
+                    for (int s = 0; s < p.nsrc; ++s) {
+                        for (int kc = 0; kc < p.chunks[s]; ++kc) {
+                            mbar_wait(empty_bar(stage), phase ^ 1u);
+                            mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
+                            const uint32_t a_dst = base + stage * C::STAGE_BYTES;
+                            tma_load_4d(a_dst, &p.tmA[s], full_bar(stage), kc * BK, cx, cy, b);
+                            tma_load_3d(a_dst + A_BYTES, &p.tmB, full_bar(stage), p.koff[s] + kc * BK, n0, wt);
+                            if (++stage == C::STAGES) {
+                                stage = 0;
+                                phase ^= 1u;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            const int total_chunks = p.ntaps * chunks_per_tap;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+                for (int c = 0; c < total_chunks; ++c) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = base + stage * C::STAGE_BYTES;
+                    const uint64_t adesc = umma_desc_sw128(a_addr);
+                    const uint64_t bdesc = umma_desc_sw128(a_addr + A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        // +32 bytes per UMMA_K step inside the 128-byte swizzled row => +2 in the (addr >> 4) field
+                        umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (c > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs have read it
+                    if (++stage == C::STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================== epilogue: TMEM -> registers -> bf16 -> global =====================
+        const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+        const int row = quad * 32 + lane;
+        const int ly = row / p.TW, lx = row - ly * p.TW;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+            const int nt = tile / m_tiles;
+            int mt = tile - nt * m_tiles;
+            const int tw = mt % p.tiles_w;
+            mt /= p.tiles_w;
+            const int th = mt % p.tiles_h;
+            const int b = mt / p.tiles_h;
+            const int vy = th * p.TH + ly, vx = tw * p.TW + lx;
+            const int oy = vy * p.osy + p.ooy, ox = vx * p.osx + p.oox;
+            const bool valid = vy < p.Hv && vx < p.Wv && oy < p.Hout && ox < p.Wout;
+            const int n0 = nt * BN;
+            bf16_t* orow = p.out + (((long)b * p.Hout + oy) * p.Wout + ox) * p.out_stride + n0;
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld32(taddr + (uint32_t)(c * 32), v);
+                if (valid) {
+                    uint32_t packed[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float f0 = __uint_as_float(v[2 * j]), f1 = __uint_as_float(v[2 * j + 1]);
+                        if (p.bias) {
+                            f0 += __ldg(p.bias + n0 + c * 32 + 2 * j);
+                            f1 += __ldg(p.bias + n0 + c * 32 + 2 * j + 1);
+                        }
+                        __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
+                        packed[j] = *reinterpret_cast<uint32_t*>(&h);
+                    }
+                    uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(f);
+    }();
+    return fn;
+}
+
+inline int num_sms() {
+    static int n = [] {
+        int dev = 0, v = CNB_NUM_SMS;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        return v > 0 ? v : CNB_NUM_SMS;
+    }();
+    return n;
+}
+
+// bf16 tensor map over a pixel-major activation [B][H][W][stride_px] taking C channels; box {64, TW, TH, 1}
+inline int make_act_map(CUtensorMap* m, const void* ptr, int C, int W, int H, int B, int stride_px, int TW, int TH) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return 1;
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)stride_px * 2, (cuuint64_t)W * stride_px * 2, (cuuint64_t)H * W * stride_px * 2};
+    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)TW, (cuuint32_t)TH, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : 2;
+}
+
+// bf16 tensor map over packed weights [taps][rows][row_stride] taking K columns; box {64, BN, 1}
+inline int make_weight_map(CUtensorMap* m, const void* ptr, int K, int rows, int taps, long row_stride, long tap_stride, int BN) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return 1;
+    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)taps};
+    cuuint64_t strides[2] = {(cuuint64_t)row_stride * 2, (cuuint64_t)tap_stride * 2};
+    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BN, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : 2;
+}
+
+inline void pick_tile(int Hv, int Wv, int* TH, int* TW) {
+    long best = -1;
+    for (int tw = 128; tw >= 8; tw >>= 1) {
+        const int th = BM / tw;
+        const long cover = (long)cnb_div_up(Wv, tw) * tw * cnb_div_up(Hv, th) * th;
+        if (best < 0 || cover < best) {
+            best = cover;
+            *TW = tw;
+            *TH = th;
+        }
+    }
+}
+
+// Is this convolution one the tensor-core kernel takes?  (bf16, unit stride, 64-channel granularity, 16-byte aligned operands)
+inline bool eligible(const cnb_conv_desc* d, int dtype) {
+    if (dtype != CNB_BF16 || d->stride != 1) return false;
+    if (d->KH * d->KW > MAX_TAPS) return false;
+    if (d->N % 64 != 0) return false;
+    for (int s = 0; s < d->nsrc; ++s) {
+        if (d->src_c[s] % BK != 0 || d->src_stride[s] % 8 != 0) return false;
+        if (reinterpret_cast<uintptr_t>(d->src[s]) % 16 != 0) return false;
+    }
+    if (d->w_row_stride % 8 != 0 || d->w_tap_stride % 8 != 0 || reinterpret_cast<uintptr_t>(d->w_packed) % 16 != 0) return false;
+    if (d->out_stride % 8 != 0 || reinterpret_cast<uintptr_t>(d->out) % 16 != 0) return false;
+    return encode_tiled_fn() != nullptr;
+}
+
+template <int BN>
+inline int launch_bn(const ConvTcParams& p, cudaStream_t stream) {
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES) != cudaSuccess) return 1;
+        configured = true;
+    }
+    const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+    cnb_count_launch();
+    conv_tc_kernel<BN><<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(p);
+    return 0;
+}
+
+// Unit-stride direct or transposed gather (the latter is the data gradient of a unit-stride convolution).
+inline int conv_tc_launch(const cnb_conv_desc* d, cudaStream_t stream) {
+    ConvTcParams p;
+    memset(&p, 0, sizeof(p));
+    const int BN = d->N % 256 == 0 ? 256 : (d->N % 128 == 0 ? 128 : 64);
+    pick_tile(d->Hout, d->Wout, &p.TH, &p.TW);
+    int koff = 0;
+    for (int s = 0; s < d->nsrc; ++s) {
+        if (make_act_map(&p.tmA[s], d->src[s], d->src_c[s], d->Win, d->Hin, d->B, d->src_stride[s], p.TW, p.TH)) return 2;
+        p.chunks[s] = d->src_c[s] / BK;
+        p.koff[s] = koff;
+        koff += d->src_c[s];
+    }
+    if (make_weight_map(&p.tmB, d->w_packed, koff, d->N, d->KH * d->KW, d->w_row_stride, d->w_tap_stride, BN)) return 2;
+    p.nsrc = d->nsrc;
+    p.ntaps = d->KH * d->KW;
+    for (int ky = 0; ky < d->KH; ++ky)
+        for (int kx = 0; kx < d->KW; ++kx) {
+            const int t = ky * d->KW + kx;
+            p.tap_dy[t] = d->transposed ? d->pad - ky * d->dil : ky * d->dil - d->pad;
+            p.tap_dx[t] = d->transposed ? d->pad - kx * d->dil : kx * d->dil - d->pad;
+            p.tap_w[t] = t;
+        }
+    p.Bn = d->B;
+    p.Hv = d->Hout;
+    p.Wv = d->Wout;
+    p.tiles_h = cnb_div_up(d->Hout, p.TH);
+    p.tiles_w = cnb_div_up(d->Wout, p.TW);
+    p.N = d->N;
+    p.n_tiles = d->N / BN;
+    p.Hout = d->Hout;
+    p.Wout = d->Wout;
+    p.osy = p.osx = 1;
+    p.ooy = p.oox = 0;
+    p.out = reinterpret_cast<bf16_t*>(d->out);
+    p.out_stride = d->out_stride;
+    p.bias = d->bias;
+    p.num_tiles = p.n_tiles * d->B * p.tiles_h * p.tiles_w;
+    int rc;
+    if (BN == 256)
+        rc = launch_bn<256>(p, stream);
+    else if (BN == 128)
+        rc = launch_bn<128>(p, stream);
+    else
+        rc = launch_bn<64>(p, stream);
+    return rc;
+}
+
+}  // namespace tc
+}  // namespace cnb
+#endif  // CNB_EMU

@@ -53,6 +53,11 @@ def _convT_out_size(n: int, k: int, stride: int, pad: int, dil: int) -> int:
     return (n - 1) * stride - 2 * pad + dil * (k - 1) + 1
 
 
+# "auto": tcgen05 kernel when eligible, CUDA-core kernel otherwise; "generic" / "tc" force one (tests, A/B timing)
+CONV_BACKEND = "auto"
+_CONV_ENTRY = {"auto": "cnb_conv2d_fwd", "generic": "cnb_conv2d_fwd_generic", "tc": "cnb_conv2d_fwd_tc"}
+
+
 def _launch_conv(sources, src_channels, wp, w_row_off, w_row_stride, w_tap_stride, N, bias, out, geom, transposed, dtype):
     d = ConvDesc()
     B, Hin, Win, Hout, Wout, KH, KW, stride, pad, dil = geom
@@ -72,7 +77,7 @@ def _launch_conv(sources, src_channels, wp, w_row_off, w_row_stride, w_tap_strid
     d.out = out.data_ptr()
     d.out_stride = out.shape[-1]
     flops = 2.0 * B * Hout * Wout * N * sum(src_channels) * KH * KW
-    call("cnb_conv2d_fwd", C.byref(d), dtype_code(dtype), stream_ptr(out), flops=flops, tag="conv_fwd/dgrad")
+    call(_CONV_ENTRY[CONV_BACKEND], C.byref(d), dtype_code(dtype), stream_ptr(out), flops=flops, tag="conv_fwd/dgrad")
 
 
 class _Conv2dFn(torch.autograd.Function):

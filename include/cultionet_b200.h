@@ -63,7 +63,13 @@ typedef struct {
     int32_t out_stride;
 } cnb_conv_desc;
 
+/* picks the tcgen05/TMA kernel when cnb_conv2d_tc_eligible(), else the CUDA-core kernel */
 int cnb_conv2d_fwd(const cnb_conv_desc* d, int dtype, void* stream);
+/* CUDA-core implicit GEMM (any shape, fp32 or bf16 storage, fp32 accumulate): the parity-mode path */
+int cnb_conv2d_fwd_generic(const cnb_conv_desc* d, int dtype, void* stream);
+/* tcgen05.mma + TMEM + TMA implicit GEMM (bf16, unit stride, channel counts multiples of 64); CNB_ERR_UNSUPPORTED otherwise */
+int cnb_conv2d_fwd_tc(const cnb_conv_desc* d, int dtype, void* stream);
+int cnb_conv2d_tc_eligible(const cnb_conv_desc* d, int dtype);
 
 /* Weight gradient of the same convolution for ONE source slice:
  *   dWp[tap][n][k_off + c] += sum_p X_s[gather(p, tap)][c] * dY[p][n]         (fp32, atomically accumulated)

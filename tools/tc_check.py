@@ -1,0 +1,83 @@
+"""GPU bring-up check of the tcgen05 convolution against the CUDA-core kernel (same bf16 inputs, both through the C ABI).
+Prints one line per case and flushes, so a trap or a hang is attributable.  Run under `timeout`."""
+import sys
+import time
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import torch
+
+from cultionet_b200 import functional as F
+
+dev = "cuda"
+torch.manual_seed(0)
+CASES = [
+    # (B, H, W, cins, cout, k, pad, dil, bias, transposed-dgrad?)
+    (1, 16, 16, [64], 64, 1, 0, 1, False),
+    (1, 16, 16, [64], 64, 3, 1, 1, False),
+    (2, 32, 32, [128], 128, 3, 1, 1, True),
+    (2, 32, 32, [256], 256, 3, 1, 1, True),
+    (2, 16, 16, [512], 512, 1, 0, 1, False),
+    (2, 32, 32, [256], 768, 1, 0, 1, True),
+    (2, 25, 25, [64, 128], 192, 3, 1, 1, False),
+    (2, 13, 13, [256, 512, 256, 256], 256, 3, 1, 1, False),
+    (3, 100, 100, [64], 64, 3, 1, 1, False),
+    (2, 50, 50, [128], 128, 3, 2, 2, False),
+    (4, 128, 128, [64, 128, 256, 256, 256], 256, 3, 1, 1, False),
+]
+
+
+def run(backend, xs, w, b, k, pad, dil):
+    F.CONV_BACKEND = backend
+    try:
+        return F.conv2d(xs, w, b, k, 1, pad, dil)
+    finally:
+        F.CONV_BACKEND = "auto"
+
+
+ok = True
+for case in CASES:
+    B, H, W, cins, cout, k, pad, dil, bias = case
+    xs = [torch.randn(B, H, W, c, device=dev).bfloat16().requires_grad_(True) for c in cins]
+    w = (torch.randn(cout, sum(cins), k, k, device=dev) / (sum(cins) * k * k) ** 0.5).requires_grad_(True)
+    b = torch.randn(cout, device=dev, requires_grad=True) if bias else None
+    print("case", case, end=" ... ", flush=True)
+    yg = run("generic", xs, w, b, k, pad, dil)
+    torch.cuda.synchronize()
+    yt = run("tc", xs, w, b, k, pad, dil)
+    torch.cuda.synchronize()
+    err = float((yt.float() - yg.float()).norm() / yg.float().norm())
+    mx = float((yt.float() - yg.float()).abs().max())
+    # data gradient through each backend (the adjoint gather = unit-stride transposed conv)
+    g = torch.randn_like(yg)
+    F.CONV_BACKEND = "generic"
+    gg = torch.autograd.grad(yg, xs, g)
+    F.CONV_BACKEND = "tc"
+    gt = torch.autograd.grad(yt, xs, g)
+    F.CONV_BACKEND = "auto"
+    torch.cuda.synchronize()
+    gerr = max(float((a.float() - c.float()).norm() / c.float().norm()) for a, c in zip(gt, gg))
+    good = err < 2e-3 and gerr < 2e-3
+    ok &= good
+    print(f"fwd rel {err:.2e} max {mx:.2e} | dgrad rel {gerr:.2e} {'OK' if good else 'MISMATCH'}", flush=True)
+
+# timing of the hot shapes (cfg2): tower_a 960->256 3x3 at 128^2, B=32 and a 256->256 3x3
+for (B, H, W, cins, cout) in [(32, 128, 128, [64, 128, 256, 256, 256], 256), (32, 128, 128, [256], 256), (32, 64, 64, [128, 256, 256, 256, 256], 256)]:
+    xs = [torch.randn(B, H, W, c, device=dev).bfloat16() for c in cins]
+    w = torch.randn(cout, sum(cins), 3, 3, device=dev) / (sum(cins) * 9) ** 0.5
+    for backend in ("tc",):
+        for _ in range(2):
+            run(backend, xs, w, None, 3, 1, 1)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        n = 5
+        for _ in range(n):
+            run(backend, xs, w, None, 3, 1, 1)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        fl = 2.0 * B * H * W * cout * sum(cins) * 9
+        print(f"time {backend} B{B} {H}x{W} {sum(cins)}->{cout}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s (incl. weight pack)", flush=True)
+print("ALL OK" if ok else "FAILURES")
+sys.exit(0 if ok else 1)
