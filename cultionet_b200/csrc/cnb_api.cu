@@ -3,6 +3,7 @@
 #include "cnb_common.cuh"
 #include "k_conv_generic.cuh"
 #include "k_conv_tc.cuh"
+#include "k_wgrad_tc.cuh"
 #include "k_loss.cuh"
 #include "k_misc.cuh"
 #include "k_na.cuh"
@@ -103,11 +104,17 @@ int cnb_conv2d_fwd(const cnb_conv_desc* d, int dtype, void* stream) {
     return cnb_conv2d_fwd_generic(d, dtype, stream);
 }
 
-int cnb_conv2d_wgrad(const cnb_wgrad_desc* d, int dtype, void* stream) {
+static int check_wgrad_desc(const cnb_wgrad_desc* d) {
     CNB_REQUIRE(d != nullptr, "conv2d_wgrad: null descriptor");
     int rc = check_conv_geom(d->B, d->Hin, d->Win, d->Hout, d->Wout, d->KH, d->KW, d->stride, d->pad, d->dil, d->transposed);
     if (rc) return rc;
     CNB_REQUIRE(d->src && d->dy && d->dwp && d->src_c > 0 && d->N > 0 && d->k_off >= 0 && d->k_off + d->src_c <= d->Ctot, "conv2d_wgrad: bad operands");
+    return CNB_OK;
+}
+
+int cnb_conv2d_wgrad_generic(const cnb_wgrad_desc* d, int dtype, void* stream) {
+    int rc = check_wgrad_desc(d);
+    if (rc) return rc;
     const long M = (long)d->B * d->Hout * d->Wout;
     const int taps = d->KH * d->KW;
     const int tiles = cnb_div_up(d->src_c, CG_BM) * cnb_div_up(d->N, CG_BN) * taps;
@@ -120,6 +127,39 @@ int cnb_conv2d_wgrad(const cnb_wgrad_desc* d, int dtype, void* stream) {
     CNB_DISPATCH_DTYPE(dtype, { CNB_LAUNCH((conv_wgrad_generic_kernel<T>), grid, dim3(256), 0, (cudaStream_t)stream, *d, splits, m_per_split); });
     CNB_CHECK_LAUNCH("conv_wgrad_generic_kernel");
     return CNB_OK;
+}
+
+int cnb_conv2d_wgrad_tc_eligible(const cnb_wgrad_desc* d, int dtype) {
+#ifdef CNB_EMU
+    (void)d;
+    (void)dtype;
+    return 0;
+#else
+    if (check_wgrad_desc(d)) return 0;
+    return tc::wgrad_eligible(d, dtype) ? 1 : 0;
+#endif
+}
+
+int cnb_conv2d_wgrad_tc(const cnb_wgrad_desc* d, int dtype, void* stream) {
+#ifdef CNB_EMU
+    (void)d;
+    (void)dtype;
+    (void)stream;
+    CNB_FAIL(CNB_ERR_UNSUPPORTED, "the tcgen05 kernel exists only in the sm_100a build");
+#else
+    int rc = check_wgrad_desc(d);
+    if (rc) return rc;
+    if (!tc::wgrad_eligible(d, dtype)) CNB_FAIL(CNB_ERR_UNSUPPORTED, "conv2d_wgrad_tc: shape/dtype not eligible for the tcgen05 kernel");
+    rc = tc::wgrad_tc_launch(d, (cudaStream_t)stream);
+    if (rc) CNB_FAIL(CNB_ERR_CUDA, "conv2d_wgrad_tc: tensor-map encode or launch configuration failed (%d)", rc);
+    CNB_CHECK_LAUNCH("wgrad_tc_kernel");
+    return CNB_OK;
+#endif
+}
+
+int cnb_conv2d_wgrad(const cnb_wgrad_desc* d, int dtype, void* stream) {
+    if (cnb_conv2d_wgrad_tc_eligible(d, dtype)) return cnb_conv2d_wgrad_tc(d, dtype, stream);
+    return cnb_conv2d_wgrad_generic(d, dtype, stream);
 }
 
 int cnb_pack_weight(const float* w, void* wp, int dtype, int taps, int N, int K, int64_t s_n, int64_t s_k, int64_t s_tap, void* stream) {

@@ -1,0 +1,253 @@
+// Weight gradient of the implicit-GEMM convolution on tcgen05 tensor cores.
+//
+//   dWp[tap][n][koff_s + c] += sum_pixels dY[p][n] * X_s[p + tap offset][c]
+//
+// GEMM view: D[M = 128 output channels][N = CW <= 256 source channels] over K = pixels.  Both operands are pixel-major in
+// HBM, i.e. MN-major for UMMA (the M/N index is the contiguous one): a TMA box {64 ch, TWp, THp, 1} (TWp*THp = 64 pixels)
+// lands as 64 rows (one per pixel = one K index) of 128 bytes with the 128B swizzle = the canonical MN-major SWIZZLE_128B
+// atom stack (8 K-rows x 128 B, atoms 1024 B apart along K = SBO); wider M/N extents are further boxes LBO = 8192 B apart.
+// Each CTA owns one (tap, 128-row n tile, source channel tile) and a slice of the pixel range (split-K); partial sums leave
+// TMEM through tcgen05.ld and are accumulated into the fp32 packed gradient with red.global.add.
+#pragma once
+#ifndef CNB_EMU
+#include "k_conv_tc.cuh"
+
+namespace cnb {
+namespace tc {
+
+constexpr int WG_PIX = 64;                    // pixels (K) per pipeline stage
+constexpr int WG_BOX_BYTES = WG_PIX * 128;    // one {64 ch x 64 px} box
+constexpr int WG_STAGES = 4;
+constexpr int WG_MAX_CTILES = 64;
+
+struct WgradTcParams {
+    CUtensorMap tmX[CNB_MAX_SRC];
+    CUtensorMap tmDY;
+    int n_ctiles;                 // channel tiles over all sources
+    short ct_src[WG_MAX_CTILES];  // source of the tile
+    short ct_c0[WG_MAX_CTILES];   // first channel inside the source
+    short ct_cw[WG_MAX_CTILES];   // width (multiple of 64, <= 256)
+    short ct_koff[WG_MAX_CTILES]; // column in Ctot
+    int ntaps;
+    int tap_dy[MAX_TAPS], tap_dx[MAX_TAPS];
+    int Bn, THp, TWp, tiles_h, tiles_w;  // pixel tiling of the OUTPUT (dY) domain
+    int N, n_tiles, Ctot;
+    int splits, pt_per_split, pixel_tiles;
+    float* dwp;
+};
+
+// MN-major SWIZZLE_128B descriptor: LBO = stride between 64-element atoms along M/N, SBO = stride between 8-row groups along K
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ uint32_t umma_idesc_bf16_mn(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+constexpr int WG_STAGE_BYTES = 2 * WG_BOX_BYTES + 4 * WG_BOX_BYTES;  // dY: 128 rows, X: up to 256 columns
+constexpr int WG_SMEM_BYTES = WG_STAGES * WG_STAGE_BYTES + 1024 + 256;
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const __grid_constant__ WgradTcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_raw + (base - raw);
+    const uint32_t bars = base + WG_STAGES * WG_STAGE_BYTES;  // full[S] empty[S] done slot
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (WG_STAGES + s); };
+    const uint32_t done_bar = bars + 8u * (2 * WG_STAGES);
+    const uint32_t slot = bars + 8u * (2 * WG_STAGES + 1);
+    volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + WG_STAGES * WG_STAGE_BYTES + 8 * (2 * WG_STAGES + 1));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // work item: blockIdx.x = ((tap * n_tiles + nt) * n_ctiles + ct) * splits + split
+    int w = blockIdx.x;
+    const int split = w % p.splits;
+    w /= p.splits;
+    const int ct = w % p.n_ctiles;
+    w /= p.n_ctiles;
+    const int nt = w % p.n_tiles;
+    const int tap = w / p.n_tiles;
+    const int src = p.ct_src[ct], c0 = p.ct_c0[ct], cw = p.ct_cw[ct], koff = p.ct_koff[ct];
+    const int n0 = nt * BM;
+    const int pt_begin = split * p.pt_per_split;
+    int pt_end = pt_begin + p.pt_per_split;
+    if (pt_end > p.pixel_tiles) pt_end = p.pixel_tiles;
+    const int nboxes_x = cw / 64;
+    const uint32_t stage_tx = (uint32_t)(2 + nboxes_x) * WG_BOX_BYTES;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.tmX[src]);
+        tma_prefetch_desc(&p.tmDY);
+        for (int s = 0; s < WG_STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(done_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(slot, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *slot_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const int dy = p.tap_dy[tap], dx = p.tap_dx[tap];
+            for (int pt = pt_begin; pt < pt_end; ++pt) {
+                int t = pt;
+                const int tw = t % p.tiles_w;
+                t /= p.tiles_w;
+                const int th = t % p.tiles_h;
+                const int b = t / p.tiles_h;
+                const int y0 = th * p.THp, x0 = tw * p.TWp;
+                mbar_wait(empty_bar(stage), phase ^ 1u);
+                mbar_arrive_expect_tx(full_bar(stage), stage_tx);
+                const uint32_t dst = base + stage * WG_STAGE_BYTES;
+                tma_load_4d(dst, &p.tmDY, full_bar(stage), n0, x0, y0, b);
+                tma_load_4d(dst + WG_BOX_BYTES, &p.tmDY, full_bar(stage), n0 + 64, x0, y0, b);
+                for (int j = 0; j < nboxes_x; ++j)
+                    tma_load_4d(dst + (2 + j) * WG_BOX_BYTES, &p.tmX[src], full_bar(stage), c0 + 64 * j, x0 + dx, y0 + dy, b);
+                if (++stage == WG_STAGES) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16_mn(cw);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int pt = pt_begin; pt < pt_end; ++pt) {
+                mbar_wait(full_bar(stage), phase);
+                tc_fence_after();
+                const uint32_t a_addr = base + stage * WG_STAGE_BYTES;
+                const uint32_t b_addr = a_addr + 2 * WG_BOX_BYTES;
+#pragma unroll
+                for (int k = 0; k < WG_PIX / 16; ++k) {
+                    // 16 pixels (K) per instruction = two 8-row groups = 2048 bytes inside every box
+                    const uint64_t adesc = umma_desc_mn_sw128(a_addr + k * 2048, WG_BOX_BYTES);
+                    const uint64_t bdesc = umma_desc_mn_sw128(b_addr + k * 2048, WG_BOX_BYTES);
+                    umma_bf16(tmem_base, adesc, bdesc, idesc, (pt > pt_begin || k > 0) ? 1u : 0u);
+                }
+                umma_commit(empty_bar(stage));
+                if (++stage == WG_STAGES) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+            umma_commit(done_bar);
+        }
+        __syncwarp();
+    } else {
+        const int quad = warp & 3;
+        const int n = n0 + quad * 32 + lane;
+        mbar_wait(done_bar, 0);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+        float* drow = p.dwp + ((long)tap * p.N + n) * p.Ctot + koff;
+        if (pt_end > pt_begin) {
+            for (int c = 0; c < cw / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld32(taddr + (uint32_t)(c * 32), v);
+                if (n < p.N) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) atomicAdd(drow + c * 32 + j, __uint_as_float(v[j]));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 256);
+    }
+}
+
+inline bool wgrad_eligible(const cnb_wgrad_desc* d, int dtype) {
+    if (dtype != CNB_BF16 || d->stride != 1) return false;
+    if (d->KH * d->KW > MAX_TAPS) return false;
+    if (d->src_c % 64 != 0 || d->src_stride % 8 != 0 || reinterpret_cast<uintptr_t>(d->src) % 16 != 0) return false;
+    if (d->N % 64 != 0 || d->dy_stride % 8 != 0 || reinterpret_cast<uintptr_t>(d->dy) % 16 != 0) return false;
+    if (d->k_off % 64 != 0) return false;
+    return encode_tiled_fn() != nullptr;
+}
+
+inline void pick_pixel_tile(int Hv, int Wv, int* TH, int* TW) {
+    long best = -1;
+    for (int tw = 64; tw >= 8; tw >>= 1) {
+        const int th = WG_PIX / tw;
+        const long cover = (long)cnb_div_up(Wv, tw) * tw * cnb_div_up(Hv, th) * th;
+        if (best < 0 || cover < best) {
+            best = cover;
+            *TW = tw;
+            *TH = th;
+        }
+    }
+}
+
+// one source slice per call (mirrors cnb_conv2d_wgrad); unit-stride direct or transposed gather
+inline int wgrad_tc_launch(const cnb_wgrad_desc* d, cudaStream_t stream) {
+    WgradTcParams p;
+    memset(&p, 0, sizeof(p));
+    pick_pixel_tile(d->Hout, d->Wout, &p.THp, &p.TWp);
+    if (make_act_map(&p.tmX[0], d->src, d->src_c, d->Win, d->Hin, d->B, d->src_stride, p.TWp, p.THp)) return 2;
+    if (make_act_map(&p.tmDY, d->dy, d->N, d->Wout, d->Hout, d->B, d->dy_stride, p.TWp, p.THp)) return 2;
+    int nct = 0;
+    for (int c0 = 0; c0 < d->src_c; c0 += 256) {
+        if (nct >= WG_MAX_CTILES) return 3;
+        p.ct_src[nct] = 0;
+        p.ct_c0[nct] = (short)c0;
+        p.ct_cw[nct] = (short)(d->src_c - c0 < 256 ? d->src_c - c0 : 256);
+        p.ct_koff[nct] = (short)(d->k_off + c0);
+        ++nct;
+    }
+    p.n_ctiles = nct;
+    p.ntaps = d->KH * d->KW;
+    for (int ky = 0; ky < d->KH; ++ky)
+        for (int kx = 0; kx < d->KW; ++kx) {
+            const int t = ky * d->KW + kx;
+            p.tap_dy[t] = d->transposed ? d->pad - ky * d->dil : ky * d->dil - d->pad;
+            p.tap_dx[t] = d->transposed ? d->pad - kx * d->dil : kx * d->dil - d->pad;
+        }
+    p.Bn = d->B;
+    p.tiles_h = cnb_div_up(d->Hout, p.THp);
+    p.tiles_w = cnb_div_up(d->Wout, p.TWp);
+    p.pixel_tiles = d->B * p.tiles_h * p.tiles_w;
+    p.N = d->N;
+    p.n_tiles = cnb_div_up(d->N, BM);
+    p.Ctot = d->Ctot;
+    p.dwp = d->dwp;
+    const int base_items = p.ntaps * p.n_tiles * p.n_ctiles;
+    int splits = cnb_div_up(3L * num_sms(), base_items);
+    const int max_splits = p.pixel_tiles / 8 > 0 ? p.pixel_tiles / 8 : 1;
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    p.pt_per_split = cnb_div_up(p.pixel_tiles, splits);
+    p.splits = cnb_div_up(p.pixel_tiles, p.pt_per_split);
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES) != cudaSuccess) return 1;
+        configured = true;
+    }
+    cnb_count_launch();
+    wgrad_tc_kernel<<<base_items * p.splits, NUM_THREADS, WG_SMEM_BYTES, stream>>>(p);
+    return 0;
+}
+
+}  // namespace tc
+}  // namespace cnb
+#endif

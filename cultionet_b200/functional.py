@@ -56,6 +56,7 @@ def _convT_out_size(n: int, k: int, stride: int, pad: int, dil: int) -> int:
 # "auto": tcgen05 kernel when eligible, CUDA-core kernel otherwise; "generic" / "tc" force one (tests, A/B timing)
 CONV_BACKEND = "auto"
 _CONV_ENTRY = {"auto": "cnb_conv2d_fwd", "generic": "cnb_conv2d_fwd_generic", "tc": "cnb_conv2d_fwd_tc"}
+_WGRAD_ENTRY = {"auto": "cnb_conv2d_wgrad", "generic": "cnb_conv2d_wgrad_generic", "tc": "cnb_conv2d_wgrad_tc"}
 
 
 def _launch_conv(sources, src_channels, wp, w_row_off, w_row_stride, w_tap_stride, N, bias, out, geom, transposed, dtype):
@@ -154,7 +155,7 @@ class _Conv2dFn(torch.autograd.Function):
                 d.KH, d.KW, d.stride, d.pad, d.dil, d.transposed = KH, KW, stride, pad, dil, int(transposed)
                 d.dy, d.dy_stride, d.N = dy.data_ptr(), N, N
                 d.dwp = dwp.data_ptr()
-                call("cnb_conv2d_wgrad", C.byref(d), dtype_code(dtype), stream_ptr(dy), flops=2.0 * B * Hout * Wout * N * c * taps,
+                call(_WGRAD_ENTRY[CONV_BACKEND], C.byref(d), dtype_code(dtype), stream_ptr(dy), flops=2.0 * B * Hout * Wout * N * c * taps,
                      tag="conv_wgrad")
                 coff += c
             dw = torch.empty_like(weight, dtype=torch.float32, memory_format=torch.contiguous_format)

@@ -83,7 +83,11 @@ typedef struct {
     float* dwp;
 } cnb_wgrad_desc;
 
+/* picks the tcgen05 split-K kernel when cnb_conv2d_wgrad_tc_eligible(), else the CUDA-core kernel */
 int cnb_conv2d_wgrad(const cnb_wgrad_desc* d, int dtype, void* stream);
+int cnb_conv2d_wgrad_generic(const cnb_wgrad_desc* d, int dtype, void* stream);
+int cnb_conv2d_wgrad_tc(const cnb_wgrad_desc* d, int dtype, void* stream);
+int cnb_conv2d_wgrad_tc_eligible(const cnb_wgrad_desc* d, int dtype);
 
 /* fp32 parameter (any strided [n][k][tap] view) -> packed [tap][N][K] in `dtype`:
  *   wp[tap][n][k] = w[n*s_n + k*s_k + tap*s_tap]

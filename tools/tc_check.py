@@ -51,15 +51,24 @@ for case in CASES:
     # data gradient through each backend (the adjoint gather = unit-stride transposed conv)
     g = torch.randn_like(yg)
     F.CONV_BACKEND = "generic"
-    gg = torch.autograd.grad(yg, xs, g)
+    gg = torch.autograd.grad(yg, xs, g, retain_graph=True)
     F.CONV_BACKEND = "tc"
-    gt = torch.autograd.grad(yt, xs, g)
+    gt = torch.autograd.grad(yt, xs, g, retain_graph=True)
     F.CONV_BACKEND = "auto"
     torch.cuda.synchronize()
     gerr = max(float((a.float() - c.float()).norm() / c.float().norm()) for a, c in zip(gt, gg))
-    good = err < 2e-3 and gerr < 2e-3
+    print(f"fwd rel {err:.2e} max {mx:.2e} | dgrad rel {gerr:.2e}", end=" ", flush=True)
+    F.CONV_BACKEND = "generic"
+    wg = torch.autograd.grad(yg, w, g)[0]
+    torch.cuda.synchronize()
+    F.CONV_BACKEND = "tc"
+    wt = torch.autograd.grad(yt, w, g)[0]
+    F.CONV_BACKEND = "auto"
+    torch.cuda.synchronize()
+    werr = float((wt - wg).norm() / wg.norm())
+    good = err < 2e-3 and gerr < 2e-3 and werr < 2e-3
     ok &= good
-    print(f"fwd rel {err:.2e} max {mx:.2e} | dgrad rel {gerr:.2e} {'OK' if good else 'MISMATCH'}", flush=True)
+    print(f"| wgrad rel {werr:.2e} {'OK' if good else 'MISMATCH'}", flush=True)
 
 # timing of the hot shapes (cfg2): tower_a 960->256 3x3 at 128^2, B=32 and a 256->256 3x3
 for (B, H, W, cins, cout) in [(32, 128, 128, [64, 128, 256, 256, 256], 256), (32, 128, 128, [256], 256), (32, 64, 64, [128, 256, 256, 256, 256], 256)]:
@@ -79,5 +88,21 @@ for (B, H, W, cins, cout) in [(32, 128, 128, [64, 128, 256, 256, 256], 256), (32
         ms = e0.elapsed_time(e1) / n
         fl = 2.0 * B * H * W * cout * sum(cins) * 9
         print(f"time {backend} B{B} {H}x{W} {sum(cins)}->{cout}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s (incl. weight pack)", flush=True)
+# wgrad timing on the hot shapes
+from cultionet_b200 import _lib
+for (B, H, W, cins, cout) in [(32, 128, 128, [64, 128, 256, 256, 256], 256), (32, 128, 128, [256], 256), (32, 32, 32, [256], 256)]:
+    xs = [torch.randn(B, H, W, c, device=dev).bfloat16() for c in cins]
+    w = (torch.randn(cout, sum(cins), 3, 3, device=dev) / (sum(cins) * 9) ** 0.5).requires_grad_(True)
+    y = run("tc", xs, w, None, 3, 1, 1)
+    g = torch.randn_like(y)
+    F.CONV_BACKEND = "tc"
+    _lib.TIMER = _lib.KernelTimer()
+    for _ in range(4):
+        torch.autograd.grad(y, w, g, retain_graph=True)
+    summ = _lib.TIMER.summary()
+    _lib.TIMER = None
+    F.CONV_BACKEND = "auto"
+    v = summ["conv_wgrad"]
+    print(f"time wgrad tc B{B} {H}x{W} {sum(cins)}->{cout}: {v['ms'] / 4:.3f} ms per conv ({v['calls'] // 4} launches) {v['flops'] / v['ms'] / 1e9:.1f} TFLOP/s", flush=True)
 print("ALL OK" if ok else "FAILURES")
 sys.exit(0 if ok else 1)
