@@ -76,11 +76,14 @@ _PROTOS = {
     "cnb_conv2d_fwd_generic": [C.POINTER(ConvDesc), _i, _vp],
     "cnb_conv2d_fwd_tc": [C.POINTER(ConvDesc), _i, _vp],
     "cnb_conv2d_tc_eligible": [C.POINTER(ConvDesc), _i],
+    "cnb_conv2d_fwd_tiny": [C.POINTER(ConvDesc), _i, _vp],
     "cnb_conv2d_wgrad": [C.POINTER(WgradDesc), _i, _vp],
     "cnb_conv2d_wgrad_generic": [C.POINTER(WgradDesc), _i, _vp],
     "cnb_conv2d_wgrad_tc": [C.POINTER(WgradDesc), _i, _vp],
     "cnb_conv2d_wgrad_tc_eligible": [C.POINTER(WgradDesc), _i],
-    "cnb_pack_weight": [_vp, _vp, _i, _i, _i, _i, _i64, _i64, _i64, _vp],
+    "cnb_conv2d_wgrad_tiny": [C.POINTER(WgradDesc), _i, _vp],
+    "cnb_repitch": [_vp, _i, _vp, _i, _i64, _i, _i, _vp],
+    "cnb_pack_weight": [_vp, _vp, _i, _i, _i, _i, _i, _i64, _i64, _i64, _vp],
     "cnb_unpack_wgrad": [_vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i, _vp],
     "cnb_bias_grad": [_vp, _i, _i64, _i, _vp, _i, _i, _vp],
     "cnb_bn_stats": [_vp, _i64, _i, _i, _i, _vp, _i, _vp],

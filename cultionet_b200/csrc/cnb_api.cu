@@ -2,6 +2,7 @@
 // Argument validation + launch only: no allocation, no synchronisation, everything on the caller's stream.
 #include "cnb_common.cuh"
 #include "k_conv_generic.cuh"
+#include "k_conv_tiny.cuh"
 #include "k_conv_tc.cuh"
 #include "k_wgrad_tc.cuh"
 #include "k_loss.cuh"
@@ -99,7 +100,20 @@ int cnb_conv2d_fwd_tc(const cnb_conv_desc* d, int dtype, void* stream) {
 #endif
 }
 
+int cnb_conv2d_fwd_tiny(const cnb_conv_desc* d, int dtype, void* stream) {
+    int rc = check_conv_desc(d);
+    if (rc) return rc;
+    if (!conv_tiny_eligible(d)) CNB_FAIL(CNB_ERR_UNSUPPORTED, "conv2d_fwd_tiny: needs N <= %d and at most %d input channels", TINY_MAX_N, TINY_MAX_C);
+    int ctot = 0;
+    for (int s = 0; s < d->nsrc; ++s) ctot += d->src_c[s];
+    const long M = (long)d->B * d->Hout * d->Wout;
+    CNB_DISPATCH_DTYPE(dtype, { CNB_LAUNCH((conv_tiny_kernel<T>), dim3(stream_grid(M, 256, 4)), dim3(256), 0, (cudaStream_t)stream, *d, ctot); });
+    CNB_CHECK_LAUNCH("conv_tiny_kernel");
+    return CNB_OK;
+}
+
 int cnb_conv2d_fwd(const cnb_conv_desc* d, int dtype, void* stream) {
+    if (check_conv_desc(d) == CNB_OK && conv_tiny_eligible(d)) return cnb_conv2d_fwd_tiny(d, dtype, stream);
     if (cnb_conv2d_tc_eligible(d, dtype)) return cnb_conv2d_fwd_tc(d, dtype, stream);
     return cnb_conv2d_fwd_generic(d, dtype, stream);
 }
@@ -157,17 +171,40 @@ int cnb_conv2d_wgrad_tc(const cnb_wgrad_desc* d, int dtype, void* stream) {
 #endif
 }
 
+int cnb_conv2d_wgrad_tiny(const cnb_wgrad_desc* d, int dtype, void* stream) {
+    int rc = check_wgrad_desc(d);
+    if (rc) return rc;
+    if (!wgrad_tiny_eligible(d)) CNB_FAIL(CNB_ERR_UNSUPPORTED, "conv2d_wgrad_tiny: needs N <= %d and a source slice of at most %d channels", TINY_MAX_N, TINY_WG_MAX_C);
+    const long M = (long)d->B * d->Hout * d->Wout;
+    dim3 grid(stream_grid(M, 256, 1), d->KH * d->KW);
+    CNB_DISPATCH_DTYPE(dtype, { CNB_LAUNCH((conv_tiny_wgrad_kernel<T>), grid, dim3(256), 0, (cudaStream_t)stream, *d); });
+    CNB_CHECK_LAUNCH("conv_tiny_wgrad_kernel");
+    return CNB_OK;
+}
+
 int cnb_conv2d_wgrad(const cnb_wgrad_desc* d, int dtype, void* stream) {
+    if (check_wgrad_desc(d) == CNB_OK && wgrad_tiny_eligible(d)) return cnb_conv2d_wgrad_tiny(d, dtype, stream);
     if (cnb_conv2d_wgrad_tc_eligible(d, dtype)) return cnb_conv2d_wgrad_tc(d, dtype, stream);
     return cnb_conv2d_wgrad_generic(d, dtype, stream);
 }
 
-int cnb_pack_weight(const float* w, void* wp, int dtype, int taps, int N, int K, int64_t s_n, int64_t s_k, int64_t s_tap, void* stream) {
-    CNB_REQUIRE(w && wp && taps > 0 && N > 0 && K > 0, "pack_weight: bad arguments");
-    const long total = (long)taps * N * K;
+int cnb_repitch(const void* src, int src_stride, void* dst, int dst_stride, int64_t P, int C, int dtype, void* stream) {
+    CNB_REQUIRE(src && dst && P > 0 && C > 0 && src_stride >= C && dst_stride >= C, "repitch: bad arguments");
     CNB_DISPATCH_DTYPE(dtype, {
-        CNB_LAUNCH((pack_weight_kernel<T>), dim3(stream_grid(total)), dim3(256), 0, (cudaStream_t)stream, w, (T*)wp, taps, N, K, (long)s_n,
-                   (long)s_k, (long)s_tap);
+        CNB_LAUNCH((repitch_kernel<T>), dim3(stream_grid((long)P * dst_stride)), dim3(256), 0, (cudaStream_t)stream, (const T*)src, src_stride,
+                   (T*)dst, dst_stride, (long)P, C);
+    });
+    CNB_CHECK_LAUNCH("repitch_kernel");
+    return CNB_OK;
+}
+
+int cnb_pack_weight(const float* w, void* wp, int dtype, int taps, int N, int K, int wp_pitch, int64_t s_n, int64_t s_k, int64_t s_tap,
+                    void* stream) {
+    CNB_REQUIRE(w && wp && taps > 0 && N > 0 && K > 0 && wp_pitch >= K, "pack_weight: bad arguments");
+    const long total = (long)taps * N * wp_pitch;
+    CNB_DISPATCH_DTYPE(dtype, {
+        CNB_LAUNCH((pack_weight_kernel<T>), dim3(stream_grid(total)), dim3(256), 0, (cudaStream_t)stream, w, (T*)wp, taps, N, K, wp_pitch,
+                   (long)s_n, (long)s_k, (long)s_tap);
     });
     CNB_CHECK_LAUNCH("pack_weight_kernel");
     return CNB_OK;

@@ -200,15 +200,15 @@ __global__ void __launch_bounds__(256) conv_wgrad_generic_kernel(cnb_wgrad_desc 
 }
 
 template <typename T>
-__global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ wp, int taps, int N, int K, long s_n, long s_k,
+__global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ wp, int taps, int N, int K, int pitch, long s_n, long s_k,
                                    long s_tap) {
-    const long total = (long)taps * N * K;
+    const long total = (long)taps * N * pitch;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        const int k = (int)(i % K);
-        const long t = i / K;
+        const int k = (int)(i % pitch);
+        const long t = i / pitch;
         const int n = (int)(t % N);
         const int tap = (int)(t / N);
-        cnb_st(wp + i, w[n * s_n + k * s_k + tap * s_tap]);
+        cnb_st(wp + i, k < K ? w[n * s_n + k * s_k + tap * s_tap] : 0.f);
     }
 }
 

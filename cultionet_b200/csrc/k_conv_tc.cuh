@@ -25,24 +25,39 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int NUM_THREADS = 192;
-constexpr int MAX_TAPS = 16;
+constexpr int MAX_TAPS = 16;    // taps summed over all phases
+constexpr int MAX_PHASES = 16;  // sub-pixel phases of a transposed convolution (stride^2)
+constexpr int MAX_MAPS = 9;     // A-operand tensor maps: one per source (unit stride) or one per tap (strided direct gather)
 
+// The iteration space is a list of PHASES.  A phase is a unit-stride gather over a (Hv x Wv) domain per image with its own taps;
+// domain pixel (vy, vx) produces output pixel (vy*osy + ooy, vx*osx + oox).
+//   * unit-stride direct / transposed convolution: one phase, k*k taps, identity output map, one tensor map per source;
+//   * ConvTranspose2d with stride s (and the data gradient of a stride-s convolution): s*s sub-pixel phases; phase (py, px) owns
+//     the taps with (py + pad - ky*dil) % s == 0 and reads the input at domain offset (py + pad - ky*dil) / s;
+//   * stride-s direct convolution (and the data gradient of a stride-s ConvTranspose2d): one phase; tap (ky, kx) reads the
+//     parity sub-grid {s*i + r} of the input through its OWN tensor map (base offset r, strides x s) at domain offset floor(q/s),
+//     q = ky*dil - pad, r = q mod s.
 struct ConvTcParams {
-    CUtensorMap tmA[CNB_MAX_SRC];
+    CUtensorMap tmA[MAX_MAPS];
     CUtensorMap tmB;
-    int nsrc;
-    int chunks[CNB_MAX_SRC];  // 64-channel chunks per source
+    int nsrc, per_tap_map;
+    int chunks[CNB_MAX_SRC];  // 64-channel chunks per source (the last one may be partial: TMA zero-fills the tail)
     int koff[CNB_MAX_SRC];    // channel offset of the source inside Ctot
-    int ntaps;
-    int tap_dy[MAX_TAPS], tap_dx[MAX_TAPS], tap_w[MAX_TAPS];  // input offset and weight-tap index per tap
-    int Bn, Hv, Wv;           // iteration domain per image
-    int TH, TW, tiles_h, tiles_w;
-    int N, n_tiles;
-    int Hout, Wout, osy, osx, ooy, oox;  // output pixel = (vy*osy + ooy, vx*osx + oox)
+    int nphases;
+    int ph_tap0[MAX_PHASES + 1];   // taps of phase p: [ph_tap0[p], ph_tap0[p+1])
+    int ph_tile0[MAX_PHASES + 1];  // first pixel tile of phase p
+    short ph_hv[MAX_PHASES], ph_wv[MAX_PHASES], ph_tiles_h[MAX_PHASES], ph_tiles_w[MAX_PHASES], ph_ooy[MAX_PHASES], ph_oox[MAX_PHASES];
+    short tap_dy[MAX_TAPS], tap_dx[MAX_TAPS], tap_w[MAX_TAPS], tap_map[MAX_TAPS];
+    int TH, TW;
+    int N, m_tiles, num_tiles;
+    int Hout, Wout, osy, osx;
     bf16_t* out;
-    int out_stride;
+    int out_stride, vec_ok;
     const float* bias;
-    int num_tiles;
+};
+
+struct TileCoord {
+    int ph, b, y0, x0, n0;
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -147,9 +162,26 @@ struct Cfg {
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
-    static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // power of two for BN in {64,128,256}
+    static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // power of two for BN in {32,64,128,256}
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
+
+__device__ __forceinline__ void decode_tile(const ConvTcParams& p, int tile, int bn, TileCoord& t) {
+    const int nt = tile / p.m_tiles;
+    int mt = tile - nt * p.m_tiles;
+    int ph = 0;
+    while (ph + 1 < p.nphases && mt >= p.ph_tile0[ph + 1]) ++ph;
+    mt -= p.ph_tile0[ph];
+    const int tiles_w = p.ph_tiles_w[ph], tiles_h = p.ph_tiles_h[ph];
+    const int tw = mt % tiles_w;
+    mt /= tiles_w;
+    const int th = mt % tiles_h;
+    t.ph = ph;
+    t.b = mt / tiles_h;
+    t.y0 = th * p.TH;
+    t.x0 = tw * p.TW;
+    t.n0 = nt * bn;
+}
 
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
@@ -169,7 +201,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < p.nsrc; ++s) tma_prefetch_desc(&p.tmA[s]);
+        const int nmaps = p.per_tap_map ? p.ph_tap0[p.nphases] : p.nsrc;
+        for (int s = 0; s < nmaps; ++s) tma_prefetch_desc(&p.tmA[s]);
         tma_prefetch_desc(&p.tmB);
         for (int s = 0; s < C::STAGES; ++s) {
             mbar_init(full_bar(s), 1);
@@ -189,30 +222,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
 
     int chunks_per_tap = 0;
     for (int s = 0; s < p.nsrc; ++s) chunks_per_tap += p.chunks[s];
-    const int m_tiles = p.Bn * p.tiles_h * p.tiles_w;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            TileCoord tc;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                const int nt = tile / m_tiles;
-                int mt = tile - nt * m_tiles;
-                const int tw = mt % p.tiles_w;
-                mt /= p.tiles_w;
-                const int th = mt % p.tiles_h;
-                const int b = mt / p.tiles_h;
-                const int y0 = th * p.TH, x0 = tw * p.TW, n0 = nt * BN;
-                for (int t = 0; t < p.ntaps; ++t) {
-                    const int cy = y0 + p.tap_dy[t], cx = x0 + p.tap_dx[t], wt = p.tap_w[t];
+                decode_tile(p, tile, BN, tc);
+                for (int t = p.ph_tap0[tc.ph]; t < p.ph_tap0[tc.ph + 1]; ++t) {
+                    const int cy = tc.y0 + p.tap_dy[t], cx = tc.x0 + p.tap_dx[t], wt = p.tap_w[t];
                     for (int s = 0; s < p.nsrc; ++s) {
+                        const CUtensorMap* am = &p.tmA[p.per_tap_map ? p.tap_map[t] : s];
                         for (int kc = 0; kc < p.chunks[s]; ++kc) {
                             mbar_wait(empty_bar(stage), phase ^ 1u);
                             mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
                             const uint32_t a_dst = base + stage * C::STAGE_BYTES;
-                            tma_load_4d(a_dst, &p.tmA[s], full_bar(stage), kc * BK, cx, cy, b);
-                            tma_load_3d(a_dst + A_BYTES, &p.tmB, full_bar(stage), p.koff[s] + kc * BK, n0, wt);
+                            tma_load_4d(a_dst, am, full_bar(stage), kc * BK, cx, cy, tc.b);
+                            tma_load_3d(a_dst + A_BYTES, &p.tmB, full_bar(stage), p.koff[s] + kc * BK, tc.n0, wt);
                             if (++stage == C::STAGES) {
                                 stage = 0;
                                 phase ^= 1u;
@@ -230,8 +258,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            const int total_chunks = p.ntaps * chunks_per_tap;
+            TileCoord tc;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+                decode_tile(p, tile, BN, tc);
+                const int total_chunks = (p.ph_tap0[tc.ph + 1] - p.ph_tap0[tc.ph]) * chunks_per_tap;
                 const int acc = it & 1;
                 const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator
@@ -254,7 +284,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                         phase ^= 1u;
                     }
                 }
-                umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+                if (total_chunks > 0)
+                    umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+                else
+                    mbar_arrive(tfull_bar(acc));  // tap-less phase (bias only): nothing in flight, hand over directly
             }
         }
         __syncwarp();
@@ -264,35 +297,35 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         const int row = quad * 32 + lane;
         const int ly = row / p.TW, lx = row - ly * p.TW;
         int it = 0;
+        TileCoord tc;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            decode_tile(p, tile, BN, tc);
             const int acc = it & 1;
             const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-            const int nt = tile / m_tiles;
-            int mt = tile - nt * m_tiles;
-            const int tw = mt % p.tiles_w;
-            mt /= p.tiles_w;
-            const int th = mt % p.tiles_h;
-            const int b = mt / p.tiles_h;
-            const int vy = th * p.TH + ly, vx = tw * p.TW + lx;
-            const int oy = vy * p.osy + p.ooy, ox = vx * p.osx + p.oox;
-            const bool valid = vy < p.Hv && vx < p.Wv && oy < p.Hout && ox < p.Wout;
-            const int n0 = nt * BN;
-            bf16_t* orow = p.out + (((long)b * p.Hout + oy) * p.Wout + ox) * p.out_stride + n0;
+            const int vy = tc.y0 + ly, vx = tc.x0 + lx;
+            const int oy = vy * p.osy + p.ph_ooy[tc.ph], ox = vx * p.osx + p.ph_oox[tc.ph];
+            const bool valid = vy < p.ph_hv[tc.ph] && vx < p.ph_wv[tc.ph] && oy < p.Hout && ox < p.Wout;
+            const bool has_taps = p.ph_tap0[tc.ph + 1] > p.ph_tap0[tc.ph];
+            const int n0 = tc.n0;
+            bf16_t* orow = p.out + (((long)tc.b * p.Hout + oy) * p.Wout + ox) * p.out_stride + n0;
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
+                const int col0 = n0 + c * 32;
+                if (col0 >= p.N) break;
                 uint32_t v[32];
                 tmem_ld32(taddr + (uint32_t)(c * 32), v);
-                if (valid) {
+                if (!valid) continue;
+                if (p.vec_ok && col0 + 32 <= p.N) {
                     uint32_t packed[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        float f0 = __uint_as_float(v[2 * j]), f1 = __uint_as_float(v[2 * j + 1]);
+                        float f0 = has_taps ? __uint_as_float(v[2 * j]) : 0.f, f1 = has_taps ? __uint_as_float(v[2 * j + 1]) : 0.f;
                         if (p.bias) {
-                            f0 += __ldg(p.bias + n0 + c * 32 + 2 * j);
-                            f1 += __ldg(p.bias + n0 + c * 32 + 2 * j + 1);
+                            f0 += __ldg(p.bias + col0 + 2 * j);
+                            f1 += __ldg(p.bias + col0 + 2 * j + 1);
                         }
                         __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
                         packed[j] = *reinterpret_cast<uint32_t*>(&h);
@@ -300,6 +333,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                     uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (col0 + j < p.N) {
+                            float f = has_taps ? __uint_as_float(v[j]) : 0.f;
+                            if (p.bias) f += __ldg(p.bias + col0 + j);
+                            orow[c * 32 + j] = __float2bfloat16(f);
+                        }
+                    }
                 }
             }
             tc_fence_before();
@@ -343,17 +385,32 @@ inline int num_sms() {
     return n;
 }
 
-// bf16 tensor map over a pixel-major activation [B][H][W][stride_px] taking C channels; box {64, TW, TH, 1}
-inline int make_act_map(CUtensorMap* m, const void* ptr, int C, int W, int H, int B, int stride_px, int TW, int TH) {
+// bf16 tensor map over a strided pixel grid: element (c, x, y, b) at ptr + c + x*sx + y*sy + b*sb (strides in elements);
+// box {64, TW, TH, 1}; coordinates outside [0,C) x [0,W) x [0,H) read as zero
+inline int make_grid_map(CUtensorMap* m, const void* ptr, int C, int W, int H, int B, long sx, long sy, long sb, int TW, int TH) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return 1;
+    if (C <= 0 || W <= 0 || H <= 0 || B <= 0) return 3;
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-    cuuint64_t strides[3] = {(cuuint64_t)stride_px * 2, (cuuint64_t)W * stride_px * 2, (cuuint64_t)H * W * stride_px * 2};
+    cuuint64_t strides[3] = {(cuuint64_t)sx * 2, (cuuint64_t)sy * 2, (cuuint64_t)sb * 2};
     cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)TW, (cuuint32_t)TH, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : 2;
+}
+
+// dense pixel-major activation [B][H][W][stride_px] taking C channels
+inline int make_act_map(CUtensorMap* m, const void* ptr, int C, int W, int H, int B, int stride_px, int TW, int TH) {
+    return make_grid_map(m, ptr, C, W, H, B, stride_px, (long)W * stride_px, (long)H * W * stride_px, TW, TH);
+}
+
+// parity sub-grid {(s*y + ry, s*x + rx)} of a dense activation
+inline int make_subgrid_map(CUtensorMap* m, const void* ptr, int C, int W, int H, int B, int stride_px, int s, int ry, int rx, int TW,
+                            int TH) {
+    const int Hs = (H - ry + s - 1) / s, Ws = (W - rx + s - 1) / s;
+    const bf16_t* base = reinterpret_cast<const bf16_t*>(ptr) + ((long)ry * W + rx) * stride_px;
+    return make_grid_map(m, base, C, Ws, Hs, B, (long)s * stride_px, (long)s * W * stride_px, (long)H * W * stride_px, TW, TH);
 }
 
 // bf16 tensor map over packed weights [taps][rows][row_stride] taking K columns; box {64, BN, 1}
@@ -382,17 +439,22 @@ inline void pick_tile(int Hv, int Wv, int* TH, int* TW) {
     }
 }
 
-// Is this convolution one the tensor-core kernel takes?  (bf16, unit stride, 64-channel granularity, 16-byte aligned operands)
+static inline int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+static inline int pos_mod(int a, int b) { return a - floor_div(a, b) * b; }
+
+// Is this convolution one the tensor-core kernel takes?  bf16; every source pixel pitch a multiple of 8 channels (16 bytes) and
+// 16-byte aligned; strided / stride-transposed gathers need a single source and at most 9 taps.  Channel counts are free: partial
+// 64-channel chunks and partial N tiles are zero-filled by TMA and masked in the epilogue.
 inline bool eligible(const cnb_conv_desc* d, int dtype) {
-    if (dtype != CNB_BF16 || d->stride != 1) return false;
+    if (dtype != CNB_BF16) return false;
     if (d->KH * d->KW > MAX_TAPS) return false;
-    if (d->N % 64 != 0) return false;
+    if (d->stride > 1 && (d->nsrc != 1 || d->KH * d->KW > MAX_MAPS || d->stride > 4)) return false;
+    if (d->Hin > 32000 || d->Win > 32000 || d->Hout > 32000 || d->Wout > 32000) return false;
     for (int s = 0; s < d->nsrc; ++s) {
-        if (d->src_c[s] % BK != 0 || d->src_stride[s] % 8 != 0) return false;
+        if (d->src_stride[s] % 8 != 0) return false;
         if (reinterpret_cast<uintptr_t>(d->src[s]) % 16 != 0) return false;
     }
     if (d->w_row_stride % 8 != 0 || d->w_tap_stride % 8 != 0 || reinterpret_cast<uintptr_t>(d->w_packed) % 16 != 0) return false;
-    if (d->out_stride % 8 != 0 || reinterpret_cast<uintptr_t>(d->out) % 16 != 0) return false;
     return encode_tiled_fn() != nullptr;
 }
 
@@ -409,52 +471,136 @@ inline int launch_bn(const ConvTcParams& p, cudaStream_t stream) {
     return 0;
 }
 
-// Unit-stride direct or transposed gather (the latter is the data gradient of a unit-stride convolution).
+inline int pick_bn(int N) {
+    if (N % 256 == 0) return 256;
+    if (N % 128 == 0) return 128;
+    if (N % 64 == 0) return 64;
+    if (N <= 32) return 32;
+    if (N <= 64) return 64;
+    return N > 512 ? 256 : 128;  // ragged N: the last tile is masked
+}
+
 inline int conv_tc_launch(const cnb_conv_desc* d, cudaStream_t stream) {
     ConvTcParams p;
     memset(&p, 0, sizeof(p));
-    const int BN = d->N % 256 == 0 ? 256 : (d->N % 128 == 0 ? 128 : 64);
-    pick_tile(d->Hout, d->Wout, &p.TH, &p.TW);
-    int koff = 0;
-    for (int s = 0; s < d->nsrc; ++s) {
-        if (make_act_map(&p.tmA[s], d->src[s], d->src_c[s], d->Win, d->Hin, d->B, d->src_stride[s], p.TW, p.TH)) return 2;
-        p.chunks[s] = d->src_c[s] / BK;
-        p.koff[s] = koff;
-        koff += d->src_c[s];
+    const int BN = pick_bn(d->N);
+    const int s = d->stride;
+    const int taps = d->KH * d->KW;
+
+    // ---- phases, taps, output map ----
+    int dom_h, dom_w;  // largest per-image iteration domain
+    if (s == 1 || !d->transposed) {
+        p.nphases = 1;
+        p.ph_tap0[0] = 0;
+        p.ph_hv[0] = (short)d->Hout;
+        p.ph_wv[0] = (short)d->Wout;
+        p.osy = p.osx = 1;
+        dom_h = d->Hout;
+        dom_w = d->Wout;
+        int nt = 0;
+        for (int ky = 0; ky < d->KH; ++ky)
+            for (int kx = 0; kx < d->KW; ++kx) {
+                const int t = ky * d->KW + kx;
+                if (s == 1) {
+                    p.tap_dy[nt] = (short)(d->transposed ? d->pad - ky * d->dil : ky * d->dil - d->pad);
+                    p.tap_dx[nt] = (short)(d->transposed ? d->pad - kx * d->dil : kx * d->dil - d->pad);
+                    p.tap_map[nt] = 0;
+                } else {
+                    const int qy = ky * d->dil - d->pad, qx = kx * d->dil - d->pad;
+                    const int ry = pos_mod(qy, s), rx = pos_mod(qx, s);
+                    if (ry >= d->Hin || rx >= d->Win) continue;  // the parity sub-grid is empty: the tap never lands inside
+                    p.tap_dy[nt] = (short)floor_div(qy, s);
+                    p.tap_dx[nt] = (short)floor_div(qx, s);
+                    p.tap_map[nt] = (short)nt;
+                }
+                p.tap_w[nt] = (short)t;
+                ++nt;
+            }
+        p.ph_tap0[1] = nt;
+        p.per_tap_map = s > 1;
+    } else {
+        // transposed, stride s: sub-pixel phases
+        p.osy = p.osx = s;
+        int np = 0, nt = 0;
+        dom_h = dom_w = 0;
+        for (int py = 0; py < s; ++py)
+            for (int px = 0; px < s; ++px) {
+                const int hv = (d->Hout - py + s - 1) / s, wv = (d->Wout - px + s - 1) / s;
+                if (d->Hout <= py || d->Wout <= px) continue;
+                if (np >= MAX_PHASES) return 3;
+                p.ph_tap0[np] = nt;
+                p.ph_hv[np] = (short)hv;
+                p.ph_wv[np] = (short)wv;
+                p.ph_ooy[np] = (short)py;
+                p.ph_oox[np] = (short)px;
+                if (hv > dom_h) dom_h = hv;
+                if (wv > dom_w) dom_w = wv;
+                for (int ky = 0; ky < d->KH; ++ky) {
+                    const int ny = py + d->pad - ky * d->dil;
+                    if (pos_mod(ny, s) != 0) continue;
+                    for (int kx = 0; kx < d->KW; ++kx) {
+                        const int nx = px + d->pad - kx * d->dil;
+                        if (pos_mod(nx, s) != 0) continue;
+                        if (nt >= MAX_TAPS) return 3;
+                        p.tap_dy[nt] = (short)floor_div(ny, s);
+                        p.tap_dx[nt] = (short)floor_div(nx, s);
+                        p.tap_w[nt] = (short)(ky * d->KW + kx);
+                        p.tap_map[nt] = 0;
+                        ++nt;
+                    }
+                }
+                ++np;
+            }
+        p.nphases = np;
+        p.ph_tap0[np] = nt;
+        p.per_tap_map = 0;
     }
-    if (make_weight_map(&p.tmB, d->w_packed, koff, d->N, d->KH * d->KW, d->w_row_stride, d->w_tap_stride, BN)) return 2;
+    if (p.nphases < 1) return 3;
+    pick_tile(dom_h, dom_w, &p.TH, &p.TW);
+    int mt = 0;
+    for (int ph = 0; ph < p.nphases; ++ph) {
+        p.ph_tile0[ph] = mt;
+        p.ph_tiles_h[ph] = (short)cnb_div_up(p.ph_hv[ph], p.TH);
+        p.ph_tiles_w[ph] = (short)cnb_div_up(p.ph_wv[ph], p.TW);
+        mt += d->B * p.ph_tiles_h[ph] * p.ph_tiles_w[ph];
+    }
+    p.ph_tile0[p.nphases] = mt;
+    p.m_tiles = mt;
+
+    // ---- operand maps ----
+    int koff = 0;
+    for (int si = 0; si < d->nsrc; ++si) {
+        p.chunks[si] = cnb_div_up(d->src_c[si], BK);
+        p.koff[si] = koff;
+        koff += d->src_c[si];
+    }
     p.nsrc = d->nsrc;
-    p.ntaps = d->KH * d->KW;
-    for (int ky = 0; ky < d->KH; ++ky)
-        for (int kx = 0; kx < d->KW; ++kx) {
-            const int t = ky * d->KW + kx;
-            p.tap_dy[t] = d->transposed ? d->pad - ky * d->dil : ky * d->dil - d->pad;
-            p.tap_dx[t] = d->transposed ? d->pad - kx * d->dil : kx * d->dil - d->pad;
-            p.tap_w[t] = t;
+    if (p.per_tap_map) {
+        for (int t = 0; t < p.ph_tap0[1]; ++t) {
+            const int ky = p.tap_w[t] / d->KW, kx = p.tap_w[t] % d->KW;
+            const int ry = pos_mod(ky * d->dil - d->pad, s), rx = pos_mod(kx * d->dil - d->pad, s);
+            if (make_subgrid_map(&p.tmA[t], d->src[0], d->src_c[0], d->Win, d->Hin, d->B, d->src_stride[0], s, ry, rx, p.TW, p.TH)) return 2;
         }
-    p.Bn = d->B;
-    p.Hv = d->Hout;
-    p.Wv = d->Wout;
-    p.tiles_h = cnb_div_up(d->Hout, p.TH);
-    p.tiles_w = cnb_div_up(d->Wout, p.TW);
+    } else {
+        for (int si = 0; si < d->nsrc; ++si)
+            if (make_act_map(&p.tmA[si], d->src[si], d->src_c[si], d->Win, d->Hin, d->B, d->src_stride[si], p.TW, p.TH)) return 2;
+    }
+    if (make_weight_map(&p.tmB, d->w_packed, koff, d->N, taps, d->w_row_stride, d->w_tap_stride, BN)) return 2;
+
     p.N = d->N;
-    p.n_tiles = d->N / BN;
     p.Hout = d->Hout;
     p.Wout = d->Wout;
-    p.osy = p.osx = 1;
-    p.ooy = p.oox = 0;
     p.out = reinterpret_cast<bf16_t*>(d->out);
     p.out_stride = d->out_stride;
+    p.vec_ok = (d->out_stride % 8 == 0 && reinterpret_cast<uintptr_t>(d->out) % 16 == 0) ? 1 : 0;
     p.bias = d->bias;
-    p.num_tiles = p.n_tiles * d->B * p.tiles_h * p.tiles_w;
-    int rc;
-    if (BN == 256)
-        rc = launch_bn<256>(p, stream);
-    else if (BN == 128)
-        rc = launch_bn<128>(p, stream);
-    else
-        rc = launch_bn<64>(p, stream);
-    return rc;
+    p.num_tiles = cnb_div_up(d->N, BN) * p.m_tiles;
+    switch (BN) {
+        case 256: return launch_bn<256>(p, stream);
+        case 128: return launch_bn<128>(p, stream);
+        case 64: return launch_bn<64>(p, stream);
+        default: return launch_bn<32>(p, stream);
+    }
 }
 
 }  // namespace tc

@@ -1,0 +1,140 @@
+// Convolutions with a handful of channels on both sides (the Psi-Net heads' 3->1 and 3->3 convolutions,
+// reference nn/modules/unet_parts.py:196-309): pure bandwidth / latency work, one thread per output pixel with the whole
+// filter bank in shared memory.  Same descriptor and gather rules as the implicit-GEMM kernels (any stride, direct or
+// transposed, several sources), fp32 or bf16 storage, fp32 accumulate.
+#pragma once
+#include "cnb_common.cuh"
+#include "k_conv_generic.cuh"
+
+namespace cnb {
+
+constexpr int TINY_MAX_N = 8;     // output channels
+constexpr int TINY_MAX_C = 16;    // input channels over all sources
+constexpr int TINY_MAX_TAPS = 16;
+constexpr int TINY_WG_MAX_C = 4;  // source-slice channels of the weight-gradient kernel
+
+inline bool conv_tiny_eligible(const cnb_conv_desc* d) {
+    int ctot = 0;
+    for (int s = 0; s < d->nsrc; ++s) ctot += d->src_c[s];
+    return d->N <= TINY_MAX_N && ctot <= TINY_MAX_C && d->KH * d->KW <= TINY_MAX_TAPS;
+}
+
+inline bool wgrad_tiny_eligible(const cnb_wgrad_desc* d) {
+    return d->N <= TINY_MAX_N && d->src_c <= TINY_WG_MAX_C && d->KH * d->KW <= TINY_MAX_TAPS;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) conv_tiny_kernel(cnb_conv_desc d, int ctot) {
+    __shared__ float ws[TINY_MAX_TAPS * TINY_MAX_N * TINY_MAX_C];
+    __shared__ float bs[TINY_MAX_N];
+    const int taps = d.KH * d.KW;
+    const T* wbase = reinterpret_cast<const T*>(d.w_packed);
+    for (int i = threadIdx.x; i < taps * d.N * ctot; i += blockDim.x) {
+        const int c = i % ctot;
+        const int t = i / ctot;
+        const int n = t % d.N, tap = t / d.N;
+        ws[i] = cnb_ld(wbase + (long)tap * d.w_tap_stride + (long)n * d.w_row_stride + c);
+    }
+    if (threadIdx.x < TINY_MAX_N) bs[threadIdx.x] = (d.bias && (int)threadIdx.x < d.N) ? d.bias[threadIdx.x] : 0.f;
+    __syncthreads();
+
+    const long M = (long)d.B * d.Hout * d.Wout;
+    T* out = reinterpret_cast<T*>(d.out);
+    for (long m = (long)blockIdx.x * blockDim.x + threadIdx.x; m < M; m += (long)gridDim.x * blockDim.x) {
+        const int ox = (int)(m % d.Wout);
+        const long t = m / d.Wout;
+        const int oy = (int)(t % d.Hout);
+        const int ob = (int)(t / d.Hout);
+        float acc[TINY_MAX_N];
+#pragma unroll
+        for (int n = 0; n < TINY_MAX_N; ++n) acc[n] = bs[n];
+        for (int tap = 0; tap < taps; ++tap) {
+            const int ky = tap / d.KW, kx = tap - ky * d.KW;
+            int iy, ix;
+            if (!conv_src_coord(oy, ky, d.stride, d.pad, d.dil, d.transposed, d.Hin, iy)) continue;
+            if (!conv_src_coord(ox, kx, d.stride, d.pad, d.dil, d.transposed, d.Win, ix)) continue;
+            const long pix = ((long)ob * d.Hin + iy) * d.Win + ix;
+            const float* wt = ws + tap * d.N * ctot;
+            int coff = 0;
+            for (int s = 0; s < d.nsrc; ++s) {
+                const T* sp = reinterpret_cast<const T*>(d.src[s]) + pix * d.src_stride[s];
+                for (int c = 0; c < d.src_c[s]; ++c) {
+                    const float x = cnb_ld(sp + c);
+#pragma unroll
+                    for (int n = 0; n < TINY_MAX_N; ++n)
+                        if (n < d.N) acc[n] = fmaf(x, wt[n * ctot + coff + c], acc[n]);
+                }
+                coff += d.src_c[s];
+            }
+        }
+#pragma unroll
+        for (int n = 0; n < TINY_MAX_N; ++n)
+            if (n < d.N) cnb_st(out + m * d.out_stride + n, acc[n]);
+    }
+}
+
+// dWp[tap][n][k_off + c] += sum_p dY[p][n] * X[gather(p, tap)][c]; grid = (pixel blocks, taps)
+template <typename T>
+__global__ void __launch_bounds__(256) conv_tiny_wgrad_kernel(cnb_wgrad_desc d) {
+    __shared__ float red[TINY_MAX_N * TINY_WG_MAX_C];
+    const int tap = blockIdx.y;
+    const int ky = tap / d.KW, kx = tap - ky * d.KW;
+    if (threadIdx.x < TINY_MAX_N * TINY_WG_MAX_C) red[threadIdx.x] = 0.f;
+    __syncthreads();
+    float acc[TINY_MAX_N][TINY_WG_MAX_C];
+#pragma unroll
+    for (int n = 0; n < TINY_MAX_N; ++n)
+#pragma unroll
+        for (int c = 0; c < TINY_WG_MAX_C; ++c) acc[n][c] = 0.f;
+    const long M = (long)d.B * d.Hout * d.Wout;
+    const T* src = reinterpret_cast<const T*>(d.src);
+    const T* dy = reinterpret_cast<const T*>(d.dy);
+    for (long m = (long)blockIdx.x * blockDim.x + threadIdx.x; m < M; m += (long)gridDim.x * blockDim.x) {
+        const int ox = (int)(m % d.Wout);
+        const long t = m / d.Wout;
+        const int oy = (int)(t % d.Hout);
+        const int ob = (int)(t / d.Hout);
+        int iy, ix;
+        if (!conv_src_coord(oy, ky, d.stride, d.pad, d.dil, d.transposed, d.Hin, iy)) continue;
+        if (!conv_src_coord(ox, kx, d.stride, d.pad, d.dil, d.transposed, d.Win, ix)) continue;
+        const T* sp = src + (((long)ob * d.Hin + iy) * d.Win + ix) * d.src_stride;
+        float xs[TINY_WG_MAX_C];
+#pragma unroll
+        for (int c = 0; c < TINY_WG_MAX_C; ++c) xs[c] = c < d.src_c ? cnb_ld(sp + c) : 0.f;
+#pragma unroll
+        for (int n = 0; n < TINY_MAX_N; ++n) {
+            if (n < d.N) {
+                const float g = cnb_ld(dy + m * d.dy_stride + n);
+#pragma unroll
+                for (int c = 0; c < TINY_WG_MAX_C; ++c) acc[n][c] = fmaf(g, xs[c], acc[n][c]);
+            }
+        }
+    }
+#pragma unroll
+    for (int n = 0; n < TINY_MAX_N; ++n)
+#pragma unroll
+        for (int c = 0; c < TINY_WG_MAX_C; ++c) {
+            if (n < d.N && c < d.src_c) {  // uniform across the block
+                const float v = cnb_warp_sum(acc[n][c]);
+                if ((threadIdx.x & 31) == 0) atomicAdd(&red[n * TINY_WG_MAX_C + c], v);
+            }
+        }
+    __syncthreads();
+    if (threadIdx.x < TINY_MAX_N * TINY_WG_MAX_C) {
+        const int n = threadIdx.x / TINY_WG_MAX_C, c = threadIdx.x % TINY_WG_MAX_C;
+        if (n < d.N && c < d.src_c) atomicAdd(d.dwp + ((long)tap * d.N + n) * d.Ctot + d.k_off + c, red[threadIdx.x]);
+    }
+}
+
+// dst[p][0..C) = src[p][0..C), dst[p][C..dst_stride) = 0: gives a skinny tensor the 16-byte pixel pitch TMA needs
+template <typename T>
+__global__ void repitch_kernel(const T* __restrict__ src, int src_stride, T* __restrict__ dst, int dst_stride, long P, int C) {
+    const long total = P * dst_stride;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % dst_stride);
+        const long p = i / dst_stride;
+        dst[i] = c < C ? src[p * src_stride + c] : T(0.f);
+    }
+}
+
+}  // namespace cnb

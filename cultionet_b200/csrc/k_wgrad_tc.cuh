@@ -20,17 +20,21 @@ constexpr int WG_BOX_BYTES = WG_PIX * 128;    // one {64 ch x 64 px} box
 constexpr int WG_STAGES = 4;
 constexpr int WG_MAX_CTILES = 64;
 
+// The pixel loop runs over the domain of the operand that is read at UNIT coordinates (U); the other operand (G) is gathered at
+// s*p + q per tap through a parity sub-grid tensor map (see k_conv_tc.cuh):
+//   direct convolution      (transposed = 0): U = dY (output pixels),  G = X at  s*o + (k*dil - pad)
+//   transposed convolution  (transposed = 1): U = X  (input pixels),   G = dY at s*i + (k*dil - pad)
 struct WgradTcParams {
-    CUtensorMap tmX[CNB_MAX_SRC];
-    CUtensorMap tmDY;
-    int n_ctiles;                 // channel tiles over all sources
-    short ct_src[WG_MAX_CTILES];  // source of the tile
+    CUtensorMap tmU;
+    CUtensorMap tmG[MAX_MAPS];
+    int u_is_dy;
+    int n_ctiles;                 // channel tiles of the source slice
     short ct_c0[WG_MAX_CTILES];   // first channel inside the source
-    short ct_cw[WG_MAX_CTILES];   // width (multiple of 64, <= 256)
-    short ct_koff[WG_MAX_CTILES]; // column in Ctot
+    short ct_cw[WG_MAX_CTILES];   // tile width (multiple of 64, <= 256; may run past src_c: zero-filled and masked)
+    int src_c, k_off;
     int ntaps;
-    int tap_dy[MAX_TAPS], tap_dx[MAX_TAPS];
-    int Bn, THp, TWp, tiles_h, tiles_w;  // pixel tiling of the OUTPUT (dY) domain
+    short tap_dy[MAX_TAPS], tap_dx[MAX_TAPS], tap_map[MAX_TAPS], tap_w[MAX_TAPS];
+    int Bn, THp, TWp, tiles_h, tiles_w;  // pixel tiling of the U domain
     int N, n_tiles, Ctot;
     int splits, pt_per_split, pixel_tiles;
     float* dwp;
@@ -75,17 +79,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const __grid_c
     w /= p.n_ctiles;
     const int nt = w % p.n_tiles;
     const int tap = w / p.n_tiles;
-    const int src = p.ct_src[ct], c0 = p.ct_c0[ct], cw = p.ct_cw[ct], koff = p.ct_koff[ct];
+    const int c0 = p.ct_c0[ct], cw = p.ct_cw[ct];
     const int n0 = nt * BM;
     const int pt_begin = split * p.pt_per_split;
     int pt_end = pt_begin + p.pt_per_split;
     if (pt_end > p.pixel_tiles) pt_end = p.pixel_tiles;
     const int nboxes_x = cw / 64;
     const uint32_t stage_tx = (uint32_t)(2 + nboxes_x) * WG_BOX_BYTES;
+    const CUtensorMap* mapG = &p.tmG[p.tap_map[tap]];
+    const CUtensorMap* mapDY = p.u_is_dy ? &p.tmU : mapG;
+    const CUtensorMap* mapX = p.u_is_dy ? mapG : &p.tmU;
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&p.tmX[src]);
-        tma_prefetch_desc(&p.tmDY);
+        tma_prefetch_desc(mapDY);
+        tma_prefetch_desc(mapX);
         for (int s = 0; s < WG_STAGES; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
@@ -103,7 +110,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const __grid_c
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            const int dy = p.tap_dy[tap], dx = p.tap_dx[tap];
+            const int gy = p.tap_dy[tap], gx = p.tap_dx[tap];
+            const int dy_oy = p.u_is_dy ? 0 : gy, dy_ox = p.u_is_dy ? 0 : gx;
+            const int x_oy = p.u_is_dy ? gy : 0, x_ox = p.u_is_dy ? gx : 0;
             for (int pt = pt_begin; pt < pt_end; ++pt) {
                 int t = pt;
                 const int tw = t % p.tiles_w;
@@ -114,10 +123,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const __grid_c
                 mbar_wait(empty_bar(stage), phase ^ 1u);
                 mbar_arrive_expect_tx(full_bar(stage), stage_tx);
                 const uint32_t dst = base + stage * WG_STAGE_BYTES;
-                tma_load_4d(dst, &p.tmDY, full_bar(stage), n0, x0, y0, b);
-                tma_load_4d(dst + WG_BOX_BYTES, &p.tmDY, full_bar(stage), n0 + 64, x0, y0, b);
+                tma_load_4d(dst, mapDY, full_bar(stage), n0, x0 + dy_ox, y0 + dy_oy, b);
+                tma_load_4d(dst + WG_BOX_BYTES, mapDY, full_bar(stage), n0 + 64, x0 + dy_ox, y0 + dy_oy, b);
                 for (int j = 0; j < nboxes_x; ++j)
-                    tma_load_4d(dst + (2 + j) * WG_BOX_BYTES, &p.tmX[src], full_bar(stage), c0 + 64 * j, x0 + dx, y0 + dy, b);
+                    tma_load_4d(dst + (2 + j) * WG_BOX_BYTES, mapX, full_bar(stage), c0 + 64 * j, x0 + x_ox, y0 + x_oy, b);
                 if (++stage == WG_STAGES) {
                     stage = 0;
                     phase ^= 1u;
@@ -148,7 +157,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const __grid_c
                     phase ^= 1u;
                 }
             }
-            umma_commit(done_bar);
+            if (pt_end > pt_begin)
+                umma_commit(done_bar);
+            else
+                mbar_arrive(done_bar);
         }
         __syncwarp();
     } else {
@@ -157,14 +169,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const __grid_c
         mbar_wait(done_bar, 0);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
-        float* drow = p.dwp + ((long)tap * p.N + n) * p.Ctot + koff;
+        float* drow = p.dwp + ((long)p.tap_w[tap] * p.N + n) * p.Ctot + p.k_off + c0;
+        const int cvalid = p.src_c - c0;  // columns of this tile that exist
         if (pt_end > pt_begin) {
             for (int c = 0; c < cw / 32; ++c) {
+                if (c * 32 >= cvalid) break;
                 uint32_t v[32];
                 tmem_ld32(taddr + (uint32_t)(c * 32), v);
                 if (n < p.N) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) atomicAdd(drow + c * 32 + j, __uint_as_float(v[j]));
+                    for (int j = 0; j < 32; ++j)
+                        if (c * 32 + j < cvalid) atomicAdd(drow + c * 32 + j, __uint_as_float(v[j]));
                 }
             }
         }
@@ -178,11 +193,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const __grid_c
 }
 
 inline bool wgrad_eligible(const cnb_wgrad_desc* d, int dtype) {
-    if (dtype != CNB_BF16 || d->stride != 1) return false;
+    if (dtype != CNB_BF16) return false;
     if (d->KH * d->KW > MAX_TAPS) return false;
-    if (d->src_c % 64 != 0 || d->src_stride % 8 != 0 || reinterpret_cast<uintptr_t>(d->src) % 16 != 0) return false;
-    if (d->N % 64 != 0 || d->dy_stride % 8 != 0 || reinterpret_cast<uintptr_t>(d->dy) % 16 != 0) return false;
-    if (d->k_off % 64 != 0) return false;
+    if (d->stride > 1 && (d->KH * d->KW > MAX_MAPS || d->stride > 4)) return false;
+    if (d->Hin > 32000 || d->Win > 32000 || d->Hout > 32000 || d->Wout > 32000) return false;
+    if (d->src_stride % 8 != 0 || reinterpret_cast<uintptr_t>(d->src) % 16 != 0) return false;
+    if (d->dy_stride % 8 != 0 || reinterpret_cast<uintptr_t>(d->dy) % 16 != 0) return false;
+    if (cnb_div_up(d->src_c, 256) > WG_MAX_CTILES) return false;
     return encode_tiled_fn() != nullptr;
 }
 
@@ -199,33 +216,59 @@ inline void pick_pixel_tile(int Hv, int Wv, int* TH, int* TW) {
     }
 }
 
-// one source slice per call (mirrors cnb_conv2d_wgrad); unit-stride direct or transposed gather
+// one source slice per call (mirrors cnb_conv2d_wgrad)
 inline int wgrad_tc_launch(const cnb_wgrad_desc* d, cudaStream_t stream) {
     WgradTcParams p;
     memset(&p, 0, sizeof(p));
-    pick_pixel_tile(d->Hout, d->Wout, &p.THp, &p.TWp);
-    if (make_act_map(&p.tmX[0], d->src, d->src_c, d->Win, d->Hin, d->B, d->src_stride, p.TWp, p.THp)) return 2;
-    if (make_act_map(&p.tmDY, d->dy, d->N, d->Wout, d->Hout, d->B, d->dy_stride, p.TWp, p.THp)) return 2;
+    const int s = d->stride;
+    p.u_is_dy = d->transposed ? 0 : 1;
+    // U = operand at unit coordinates, G = gathered operand
+    const void* u_ptr = p.u_is_dy ? d->dy : d->src;
+    const int u_c = p.u_is_dy ? d->N : d->src_c, u_pitch = p.u_is_dy ? d->dy_stride : d->src_stride;
+    const int u_h = p.u_is_dy ? d->Hout : d->Hin, u_w = p.u_is_dy ? d->Wout : d->Win;
+    const void* g_ptr = p.u_is_dy ? d->src : d->dy;
+    const int g_c = p.u_is_dy ? d->src_c : d->N, g_pitch = p.u_is_dy ? d->src_stride : d->dy_stride;
+    const int g_h = p.u_is_dy ? d->Hin : d->Hout, g_w = p.u_is_dy ? d->Win : d->Wout;
+
+    pick_pixel_tile(u_h, u_w, &p.THp, &p.TWp);
+    if (make_act_map(&p.tmU, u_ptr, u_c, u_w, u_h, d->B, u_pitch, p.TWp, p.THp)) return 2;
+    int nt = 0;
+    for (int ky = 0; ky < d->KH; ++ky)
+        for (int kx = 0; kx < d->KW; ++kx) {
+            const int qy = ky * d->dil - d->pad, qx = kx * d->dil - d->pad;
+            if (s == 1) {
+                p.tap_dy[nt] = (short)qy;
+                p.tap_dx[nt] = (short)qx;
+                p.tap_map[nt] = 0;
+            } else {
+                const int ry = pos_mod(qy, s), rx = pos_mod(qx, s);
+                if (ry >= g_h || rx >= g_w) continue;  // empty parity sub-grid: this tap's gradient stays zero
+                p.tap_dy[nt] = (short)floor_div(qy, s);
+                p.tap_dx[nt] = (short)floor_div(qx, s);
+                p.tap_map[nt] = (short)nt;
+                if (make_subgrid_map(&p.tmG[nt], g_ptr, g_c, g_w, g_h, d->B, g_pitch, s, ry, rx, p.TWp, p.THp)) return 2;
+            }
+            p.tap_w[nt] = (short)(ky * d->KW + kx);
+            ++nt;
+        }
+    if (s == 1 && make_act_map(&p.tmG[0], g_ptr, g_c, g_w, g_h, d->B, g_pitch, p.TWp, p.THp)) return 2;
+    p.ntaps = nt;
+    if (nt == 0) return 0;
+
     int nct = 0;
     for (int c0 = 0; c0 < d->src_c; c0 += 256) {
         if (nct >= WG_MAX_CTILES) return 3;
-        p.ct_src[nct] = 0;
+        const int rem = d->src_c - c0;
         p.ct_c0[nct] = (short)c0;
-        p.ct_cw[nct] = (short)(d->src_c - c0 < 256 ? d->src_c - c0 : 256);
-        p.ct_koff[nct] = (short)(d->k_off + c0);
+        p.ct_cw[nct] = (short)(rem >= 256 ? 256 : cnb_div_up(rem, 64) * 64);
         ++nct;
     }
     p.n_ctiles = nct;
-    p.ntaps = d->KH * d->KW;
-    for (int ky = 0; ky < d->KH; ++ky)
-        for (int kx = 0; kx < d->KW; ++kx) {
-            const int t = ky * d->KW + kx;
-            p.tap_dy[t] = d->transposed ? d->pad - ky * d->dil : ky * d->dil - d->pad;
-            p.tap_dx[t] = d->transposed ? d->pad - kx * d->dil : kx * d->dil - d->pad;
-        }
+    p.src_c = d->src_c;
+    p.k_off = d->k_off;
     p.Bn = d->B;
-    p.tiles_h = cnb_div_up(d->Hout, p.THp);
-    p.tiles_w = cnb_div_up(d->Wout, p.TWp);
+    p.tiles_h = cnb_div_up(u_h, p.THp);
+    p.tiles_w = cnb_div_up(u_w, p.TWp);
     p.pixel_tiles = d->B * p.tiles_h * p.tiles_w;
     p.N = d->N;
     p.n_tiles = cnb_div_up(d->N, BM);

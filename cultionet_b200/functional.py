@@ -38,10 +38,13 @@ def _weight_strides(kind: str, N: int, K: int, taps: int, for_dgrad: bool):
 
 
 def pack_weight(weight: torch.Tensor, kind: str, N: int, K: int, taps: int, dtype: torch.dtype, for_dgrad: bool) -> torch.Tensor:
+    """[taps][rows][pitch] packed copy of a parameter; the row pitch is rounded up to 8 elements in bf16 (16-byte rows for TMA),
+    the padding columns are zero."""
     rows, cols, s_n, s_k, s_tap = _weight_strides(kind, N, K, taps, for_dgrad)
     w = _contig(weight)
-    out = torch.empty((taps, rows, cols), dtype=dtype, device=w.device)
-    call("cnb_pack_weight", ptr(w), ptr(out), dtype_code(dtype), taps, rows, cols, s_n, s_k, s_tap, stream_ptr(w))
+    pitch = (cols + 7) // 8 * 8 if dtype == torch.bfloat16 else cols
+    out = torch.empty((taps, rows, pitch), dtype=dtype, device=w.device)
+    call("cnb_pack_weight", ptr(w), ptr(out), dtype_code(dtype), taps, rows, cols, pitch, s_n, s_k, s_tap, stream_ptr(w))
     return out
 
 
@@ -52,6 +55,8 @@ def _conv_out_size(n: int, k: int, stride: int, pad: int, dil: int) -> int:
 def _convT_out_size(n: int, k: int, stride: int, pad: int, dil: int) -> int:
     return (n - 1) * stride - 2 * pad + dil * (k - 1) + 1
 
+
+TINY_MAX_C = 16  # csrc/k_conv_tiny.cuh
 
 # "auto": tcgen05 kernel when eligible, CUDA-core kernel otherwise; "generic" / "tc" force one (tests, A/B timing)
 CONV_BACKEND = "auto"
@@ -77,7 +82,7 @@ def _launch_conv(sources, src_channels, wp, w_row_off, w_row_stride, w_tap_strid
     d.bias = bias.data_ptr() if bias is not None else None
     d.out = out.data_ptr()
     d.out_stride = out.shape[-1]
-    flops = 2.0 * B * Hout * Wout * N * sum(src_channels) * KH * KW
+    flops = 2.0 * B * (Hin * Win if transposed else Hout * Wout) * N * sum(src_channels) * KH * KW  # algorithmic
     call(_CONV_ENTRY[CONV_BACKEND], C.byref(d), dtype_code(dtype), stream_ptr(out), flops=flops, tag="conv_fwd/dgrad")
 
 
@@ -112,7 +117,7 @@ class _Conv2dFn(torch.autograd.Function):
         out = torch.empty((B, Hout, Wout, N), dtype=dtype, device=x0.device)
         geom = (B, Hin, Win, Hout, Wout, KH, KW, stride, pad, dil)
         bias_c = _contig(bias) if bias is not None else None
-        _launch_conv(sources, src_channels, wp, 0, Ctot, N * Ctot, N, bias_c, out, geom, transposed, dtype)
+        _launch_conv(sources, src_channels, wp, 0, wp.shape[2], N * wp.shape[2], N, bias_c, out, geom, transposed, dtype)
         ctx.save_for_backward(weight, *sources)
         ctx.meta = (kind, geom, transposed, src_channels, N, Ctot, bias is not None)
         return out
@@ -126,6 +131,13 @@ class _Conv2dFn(torch.autograd.Function):
         dy = _contig(dy)
         dtype = dy.dtype
         dev = dy.device
+        dy_pitch = N
+        if dtype == torch.bfloat16 and N % 8 != 0 and Ctot > TINY_MAX_C:
+            # a skinny gradient (Psi-Net streams: N = 3) gets the 16-byte pixel pitch the TMA-fed dgrad / wgrad kernels need
+            dy_pitch = (N + 7) // 8 * 8
+            dyp = torch.empty((*dy.shape[:-1], dy_pitch), dtype=dtype, device=dev)
+            call("cnb_repitch", ptr(dy), N, ptr(dyp), dy_pitch, B * Hout * Wout, N, dtype_code(dtype), stream_ptr(dy))
+            dy = dyp
         need_w = ctx.needs_input_grad[0]
         need_b = has_bias and ctx.needs_input_grad[1]
         src_grads = [None] * len(sources)
@@ -139,7 +151,7 @@ class _Conv2dFn(torch.autograd.Function):
             for i, (s, c) in enumerate(zip(sources, src_channels)):
                 if need_src[i]:
                     dx = torch.empty_like(s)
-                    _launch_conv([dy], [N], wd, coff, N, Ctot * N, c, None, dx, dgeom, not transposed, dtype)
+                    _launch_conv([dy], [N], wd, coff, wd.shape[2], Ctot * wd.shape[2], c, None, dx, dgeom, not transposed, dtype)
                     src_grads[i] = dx
                 coff += c
 
@@ -153,9 +165,9 @@ class _Conv2dFn(torch.autograd.Function):
                 d.k_off, d.Ctot = coff, Ctot
                 d.B, d.Hin, d.Win, d.Hout, d.Wout = B, Hin, Win, Hout, Wout
                 d.KH, d.KW, d.stride, d.pad, d.dil, d.transposed = KH, KW, stride, pad, dil, int(transposed)
-                d.dy, d.dy_stride, d.N = dy.data_ptr(), N, N
+                d.dy, d.dy_stride, d.N = dy.data_ptr(), dy_pitch, N
                 d.dwp = dwp.data_ptr()
-                call(_WGRAD_ENTRY[CONV_BACKEND], C.byref(d), dtype_code(dtype), stream_ptr(dy), flops=2.0 * B * Hout * Wout * N * c * taps,
+                call(_WGRAD_ENTRY[CONV_BACKEND], C.byref(d), dtype_code(dtype), stream_ptr(dy), flops=2.0 * B * (Hin * Win if transposed else Hout * Wout) * N * c * taps,
                      tag="conv_wgrad")
                 coff += c
             dw = torch.empty_like(weight, dtype=torch.float32, memory_format=torch.contiguous_format)
@@ -165,7 +177,7 @@ class _Conv2dFn(torch.autograd.Function):
         db = None
         if need_b:
             db = torch.empty((N,), dtype=torch.float32, device=dev)
-            call("cnb_bias_grad", ptr(dy), N, B * Hout * Wout, N, ptr(db), 0, dtype_code(dtype), stream_ptr(dy))
+            call("cnb_bias_grad", ptr(dy), dy_pitch, B * Hout * Wout, N, ptr(db), 0, dtype_code(dtype), stream_ptr(dy))
         return (dw, db, None, None, None, None, None, None, None, *src_grads)
 
 

@@ -63,13 +63,18 @@ typedef struct {
     int32_t out_stride;
 } cnb_conv_desc;
 
-/* picks the tcgen05/TMA kernel when cnb_conv2d_tc_eligible(), else the CUDA-core kernel */
+/* picks the tiny-channel kernel, else the tcgen05/TMA kernel when cnb_conv2d_tc_eligible(), else the CUDA-core kernel */
 int cnb_conv2d_fwd(const cnb_conv_desc* d, int dtype, void* stream);
 /* CUDA-core implicit GEMM (any shape, fp32 or bf16 storage, fp32 accumulate): the parity-mode path */
 int cnb_conv2d_fwd_generic(const cnb_conv_desc* d, int dtype, void* stream);
-/* tcgen05.mma + TMEM + TMA implicit GEMM (bf16, unit stride, channel counts multiples of 64); CNB_ERR_UNSUPPORTED otherwise */
+/* tcgen05.mma + TMEM + TMA implicit GEMM: bf16, every source with a 16-byte pixel pitch; any channel counts (partial tiles are
+ * zero-filled by TMA and masked); stride 1..4 direct or transposed (stride > 1 needs a single source and <= 9 taps).
+ * CNB_ERR_UNSUPPORTED otherwise */
 int cnb_conv2d_fwd_tc(const cnb_conv_desc* d, int dtype, void* stream);
 int cnb_conv2d_tc_eligible(const cnb_conv_desc* d, int dtype);
+/* one thread per output pixel, filter bank in shared memory: N <= 8 output and <= 16 input channels (the Psi-Net heads' 3->1 and
+ * 3->3 convolutions, nn/modules/unet_parts.py:215-220, :262-270); cnb_conv2d_fwd picks it first when it applies */
+int cnb_conv2d_fwd_tiny(const cnb_conv_desc* d, int dtype, void* stream);
 
 /* Weight gradient of the same convolution for ONE source slice:
  *   dWp[tap][n][k_off + c] += sum_p X_s[gather(p, tap)][c] * dY[p][n]         (fp32, atomically accumulated)
@@ -88,12 +93,17 @@ int cnb_conv2d_wgrad(const cnb_wgrad_desc* d, int dtype, void* stream);
 int cnb_conv2d_wgrad_generic(const cnb_wgrad_desc* d, int dtype, void* stream);
 int cnb_conv2d_wgrad_tc(const cnb_wgrad_desc* d, int dtype, void* stream);
 int cnb_conv2d_wgrad_tc_eligible(const cnb_wgrad_desc* d, int dtype);
+/* N <= 8 and a source slice of <= 4 channels: per-thread partial sums, one atomic per CTA */
+int cnb_conv2d_wgrad_tiny(const cnb_wgrad_desc* d, int dtype, void* stream);
+/* dst[p][c] = src[p][c] for c < C, 0 for C <= c < dst_stride: gives a skinny tensor (e.g. the 3-channel gradient of a Psi-Net
+ * stream) the 16-byte pixel pitch the TMA-fed kernels need */
+int cnb_repitch(const void* src, int src_stride, void* dst, int dst_stride, int64_t P, int C, int dtype, void* stream);
 
-/* fp32 parameter (any strided [n][k][tap] view) -> packed [tap][N][K] in `dtype`:
+/* fp32 parameter (any strided [n][k][tap] view) -> packed [tap][N][wp_pitch] in `dtype` (wp_pitch >= K; padding columns zeroed):
  *   wp[tap][n][k] = w[n*s_n + k*s_k + tap*s_tap]
  * nn.Conv2d weight [Cout,Cin,kh,kw]: forward (n=Cout,k=Cin) s_n=Cin*taps,s_k=taps; dgrad (n=Cin,k=Cout) s_n=taps,s_k=Cin*taps.
  * nn.ConvTranspose2d weight [Cin,Cout,kh,kw]: forward (n=Cout,k=Cin) s_n=taps,s_k=Cout*taps; dgrad s_n=Cout*taps,s_k=taps. */
-int cnb_pack_weight(const float* w, void* wp, int dtype, int taps, int N, int K,
+int cnb_pack_weight(const float* w, void* wp, int dtype, int taps, int N, int K, int wp_pitch,
                     int64_t s_n, int64_t s_k, int64_t s_tap, void* stream);
 /* inverse scatter of a packed fp32 gradient into the parameter layout: g[...] (+)= dwp[tap][n][k] */
 int cnb_unpack_wgrad(const float* dwp, float* g, int taps, int N, int K,

@@ -26,6 +26,22 @@ def test_conv_skinny_heads(dev):
     cases.conv_case(dev, F32, 2, 100, 100, [1, 1, 1], 3, 3, 1, 1, 1)
 
 
+def test_conv_tensor_core_shapes(dev):
+    """bf16 shapes that must take the tcgen05 kernel: strided single-source, ragged channel counts, skinny Psi-Net streams."""
+    from cultionet_b200 import functional as F
+
+    F.CONV_BACKEND = "tc"  # fail loudly if a shape is not accepted
+    try:
+        cases.conv_case(dev, BF16, 2, 50, 50, [64], 128, 3, 2, 1, 1)       # pool convolution, even size
+        cases.conv_case(dev, BF16, 2, 25, 25, [128], 256, 3, 2, 1, 1)      # pool convolution, odd size (25 -> 13)
+        cases.conv_case(dev, BF16, 2, 20, 20, [72, 24, 8], 136, 3, 1, 1, 1)  # partial 64-channel chunks and N tiles
+        cases.conv_case(dev, BF16, 2, 40, 40, [256], 3, 3, 1, 1, 1)        # 256 -> 3 stream convolution
+        cases.convT_case(dev, BF16, 2, 25, 25, 128, 128, 2)                  # 25 -> 49
+        cases.convT_case(dev, BF16, 2, 13, 13, 64, 64, 4)                    # 13 -> 49 (final_c)
+    finally:
+        F.CONV_BACKEND = "auto"
+
+
 @pytest.mark.parametrize("dtype", [F32, BF16])
 @pytest.mark.parametrize("stride", [2, 4])
 def test_conv_transpose(dev, dtype, stride):
