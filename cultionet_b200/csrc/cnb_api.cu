@@ -9,6 +9,7 @@
 #include "k_misc.cuh"
 #include "k_na.cuh"
 #include "k_norm.cuh"
+#include "k_vec.cuh"
 
 using namespace cnb;
 
@@ -16,6 +17,21 @@ static inline int stream_grid(long n, int per_block = 256, int waves = 8) {
     return cnb_clamp_grid(cnb_div_up(n, per_block), (long)CNB_NUM_SMS * waves);
 }
 
+static inline int vec_width(int dtype) { return dtype == CNB_BF16 ? 8 : 4; }
+// pixel-major BatchNorm2d whose rows split into whole 16-byte vectors (and whose per-CTA channel sums fit in shared memory)
+static inline bool bn_vec_ok(int L, int C, int ch_div, int dtype) {
+    return ch_div == 1 && L == C && C % vec_width(dtype) == 0 && C <= 4096;
+}
+
+static inline long column_stride(long total, int L, int* blocks) {
+    // total threads rounded down to a multiple of L (>= L), at most ~8 waves
+    long want = (long)CNB_NUM_SMS * 8 * 256;
+    if (want > total) want = total;
+    long stride = want / L * L;
+    if (stride < L) stride = L;
+    *blocks = cnb_div_up(stride, 256);
+    return stride;
+}
 extern "C" {
 
 int cnb_version(void) { return CNB_VERSION; }
@@ -222,6 +238,18 @@ int cnb_unpack_wgrad(const float* dwp, float* g, int taps, int N, int K, int64_t
 int cnb_bias_grad(const void* dy, int dy_stride, int64_t P, int N, float* db, int accumulate, int dtype, void* stream) {
     CNB_REQUIRE(dy && db && P > 0 && N > 0 && dy_stride >= N, "bias_grad: bad arguments");
     if (!accumulate) CNB_MEMSET_ASYNC(db, 0, sizeof(float) * N, (cudaStream_t)stream);
+    if (dy_stride == N && N % vec_width(dtype) == 0 && N <= 8192 && cnb_aligned16(dy)) {
+        const int V = vec_width(dtype), CV = N / V;
+        int blocks;
+        const long total_v = (long)P * CV;
+        const long stride_v = column_stride(total_v, CV, &blocks);
+        CNB_DISPATCH_DTYPE(dtype, {
+            CNB_LAUNCH((colsum_vec_kernel<T>), dim3(blocks), dim3(256), N * sizeof(float), (cudaStream_t)stream, (const T*)dy, total_v, CV,
+                       stride_v, N, db);
+        });
+        CNB_CHECK_LAUNCH("colsum_vec_kernel");
+        return CNB_OK;
+    }
     const int cols = cnb_div_up(N, 32);
     const int splits = cnb_clamp_grid((4L * CNB_NUM_SMS + cols - 1) / cols, cnb_div_up(P, 64));
     CNB_DISPATCH_DTYPE(dtype, {
@@ -232,21 +260,22 @@ int cnb_bias_grad(const void* dy, int dy_stride, int64_t P, int N, float* db, in
 }
 
 // ------------------------------------------------------------------------------------------------
-static inline long column_stride(long total, int L, int* blocks) {
-    // total threads rounded down to a multiple of L (>= L), at most ~8 waves
-    long want = (long)CNB_NUM_SMS * 8 * 256;
-    if (want > total) want = total;
-    long stride = want / L * L;
-    if (stride < L) stride = L;
-    *blocks = cnb_div_up(stride, 256);
-    return stride;
-}
-
 int cnb_bn_stats(const void* x, int64_t P, int L, int C, int ch_div, float* sums, int dtype, void* stream) {
     CNB_REQUIRE(x && sums && P > 0 && L > 0 && C > 0 && ch_div > 0, "bn_stats: bad arguments");
     CNB_MEMSET_ASYNC(sums, 0, sizeof(float) * 2 * C, (cudaStream_t)stream);
     int blocks;
     const long total = (long)P * L;
+    if (bn_vec_ok(L, C, ch_div, dtype) && cnb_aligned16(x)) {
+        const int V = vec_width(dtype), CV = C / V;
+        const long total_v = total / V;
+        const long stride_v = column_stride(total_v, CV, &blocks);
+        CNB_DISPATCH_DTYPE(dtype, {
+            CNB_LAUNCH((bn_stats_vec_kernel<T>), dim3(blocks), dim3(256), 2 * C * sizeof(float), (cudaStream_t)stream, (const T*)x, total_v, CV,
+                       stride_v, C, sums);
+        });
+        CNB_CHECK_LAUNCH("bn_stats_vec_kernel");
+        return CNB_OK;
+    }
     const long stride = column_stride(total, L, &blocks);
     CNB_DISPATCH_DTYPE(dtype, {
         CNB_LAUNCH((bn_stats_kernel<T>), dim3(blocks), dim3(256), 0, (cudaStream_t)stream, (const T*)x, total, L, C, ch_div, stride, sums);
@@ -270,6 +299,18 @@ int cnb_bn_act_fwd(const void* x, const float* scale, const float* shift, const 
                    int act, int dtype, void* stream) {
     CNB_REQUIRE(x && y && scale && shift && P > 0 && L > 0 && C > 0 && ch_div > 0, "bn_act_fwd: bad arguments");
     const long total = (long)P * L;
+    if (bn_vec_ok(L, C, ch_div, dtype) && cnb_aligned16(x) && cnb_aligned16(y) && cnb_aligned16(residual)) {
+        const int V = vec_width(dtype), CV = C / V;
+        int blocks;
+        const long total_v = total / V;
+        const long stride_v = column_stride(total_v, CV, &blocks);
+        CNB_DISPATCH_DTYPE(dtype, {
+            CNB_LAUNCH((bn_act_fwd_vec_kernel<T>), dim3(blocks), dim3(256), 0, (cudaStream_t)stream, (const T*)x, scale, shift,
+                       (const T*)residual, (T*)y, total_v, CV, stride_v, act);
+        });
+        CNB_CHECK_LAUNCH("bn_act_fwd_vec_kernel");
+        return CNB_OK;
+    }
     CNB_DISPATCH_DTYPE(dtype, {
         CNB_LAUNCH((bn_act_fwd_kernel<T>), dim3(stream_grid(total)), dim3(256), 0, (cudaStream_t)stream, (const T*)x, scale, shift,
                    (const T*)residual, (T*)y, total, L, C, ch_div, act);
@@ -284,6 +325,17 @@ int cnb_bn_act_bwd_reduce(const void* x, const void* dy, const float* save_mean,
     CNB_MEMSET_ASYNC(dsums, 0, sizeof(float) * 2 * C, (cudaStream_t)stream);
     int blocks;
     const long total = (long)P * L;
+    if (bn_vec_ok(L, C, ch_div, dtype) && cnb_aligned16(x) && cnb_aligned16(dy)) {
+        const int V = vec_width(dtype), CV = C / V;
+        const long total_v = total / V;
+        const long stride_v = column_stride(total_v, CV, &blocks);
+        CNB_DISPATCH_DTYPE(dtype, {
+            CNB_LAUNCH((bn_act_bwd_reduce_vec_kernel<T>), dim3(blocks), dim3(256), 2 * C * sizeof(float), (cudaStream_t)stream, (const T*)x,
+                       (const T*)dy, save_mean, save_rstd, gamma, beta, total_v, CV, stride_v, C, act, dsums);
+        });
+        CNB_CHECK_LAUNCH("bn_act_bwd_reduce_vec_kernel");
+        return CNB_OK;
+    }
     const long stride = column_stride(total, L, &blocks);
     CNB_DISPATCH_DTYPE(dtype, {
         CNB_LAUNCH((bn_act_bwd_reduce_kernel<T>), dim3(blocks), dim3(256), 0, (cudaStream_t)stream, (const T*)x, (const T*)dy, save_mean,
@@ -299,6 +351,18 @@ int cnb_bn_act_bwd_apply(const void* x, const void* dy, const float* save_mean, 
     CNB_REQUIRE(x && dy && dx && save_mean && save_rstd && dsums && count > 0 && P > 0 && L > 0 && C > 0 && ch_div > 0,
                 "bn_act_bwd_apply: bad arguments");
     const long total = (long)P * L;
+    if (bn_vec_ok(L, C, ch_div, dtype) && cnb_aligned16(x) && cnb_aligned16(dy) && cnb_aligned16(dx)) {
+        const int V = vec_width(dtype), CV = C / V;
+        int blocks;
+        const long total_v = total / V;
+        const long stride_v = column_stride(total_v, CV, &blocks);
+        CNB_DISPATCH_DTYPE(dtype, {
+            CNB_LAUNCH((bn_act_bwd_apply_vec_kernel<T>), dim3(blocks), dim3(256), 0, (cudaStream_t)stream, (const T*)x, (const T*)dy,
+                       save_mean, save_rstd, gamma, beta, dsums, 1.0f / (float)count, (T*)dx, total_v, CV, stride_v, C, act, train_stats);
+        });
+        CNB_CHECK_LAUNCH("bn_act_bwd_apply_vec_kernel");
+        return CNB_OK;
+    }
     CNB_DISPATCH_DTYPE(dtype, {
         CNB_LAUNCH((bn_act_bwd_apply_kernel<T>), dim3(stream_grid(total)), dim3(256), 0, (cudaStream_t)stream, (const T*)x, (const T*)dy,
                    save_mean, save_rstd, gamma, beta, dsums, 1.0f / (float)count, (T*)dx, total, L, C, ch_div, act, train_stats);
@@ -309,6 +373,15 @@ int cnb_bn_act_bwd_apply(const void* x, const void* dy, const float* save_mean, 
 
 int cnb_add_n(const void* a, const void* b, const void* c, const void* d, void* out, int64_t n, int dtype, void* stream) {
     CNB_REQUIRE(a && b && out && n > 0, "add_n: bad arguments");
+    if (n % vec_width(dtype) == 0 && cnb_aligned16(a) && cnb_aligned16(b) && cnb_aligned16(c) && cnb_aligned16(d) && cnb_aligned16(out)) {
+        const long n_v = n / vec_width(dtype);
+        CNB_DISPATCH_DTYPE(dtype, {
+            CNB_LAUNCH((add_n_vec_kernel<T>), dim3(stream_grid(n_v)), dim3(256), 0, (cudaStream_t)stream, (const T*)a, (const T*)b,
+                       (const T*)c, (const T*)d, (T*)out, n_v);
+        });
+        CNB_CHECK_LAUNCH("add_n_vec_kernel");
+        return CNB_OK;
+    }
     CNB_DISPATCH_DTYPE(dtype, {
         CNB_LAUNCH((add_n_kernel<T>), dim3(stream_grid(n)), dim3(256), 0, (cudaStream_t)stream, (const T*)a, (const T*)b, (const T*)c,
                    (const T*)d, (T*)out, (long)n);
@@ -321,6 +394,24 @@ int cnb_add_n(const void* a, const void* b, const void* c, const void* d, void* 
 int cnb_layernorm_fwd(const void* x, const float* gamma, const float* beta, float eps, void* y, float* save_mean, float* save_rstd, int64_t P,
                       int C, int dtype, void* stream) {
     CNB_REQUIRE(x && y && gamma && beta && save_mean && save_rstd && P > 0 && C > 0, "layernorm_fwd: bad arguments");
+    if (C % vec_width(dtype) == 0 && C <= 128 * vec_width(dtype) && cnb_aligned16(x) && cnb_aligned16(y)) {
+        const int K = cnb_div_up(C, 32 * vec_width(dtype));
+        const dim3 grid(stream_grid(P, 8, 4));
+#define CNB_LN_FWD(KK)                                                                                                              \
+    CNB_DISPATCH_DTYPE(dtype, {                                                                                                     \
+        CNB_LAUNCH((layernorm_fwd_vec_kernel<T, KK>), grid, dim3(256), 0, (cudaStream_t)stream, (const T*)x, gamma, beta, eps, (T*)y, \
+                   save_mean, save_rstd, (long)P, C);                                                                               \
+    })
+        if (K == 1)
+            CNB_LN_FWD(1);
+        else if (K == 2)
+            CNB_LN_FWD(2);
+        else
+            CNB_LN_FWD(4);
+#undef CNB_LN_FWD
+        CNB_CHECK_LAUNCH("layernorm_fwd_vec_kernel");
+        return CNB_OK;
+    }
     CNB_DISPATCH_DTYPE(dtype, {
         CNB_LAUNCH((layernorm_fwd_kernel<T>), dim3(stream_grid(P, 8)), dim3(256), 0, (cudaStream_t)stream, (const T*)x, gamma, beta, eps, (T*)y,
                    save_mean, save_rstd, (long)P, C);
@@ -333,6 +424,24 @@ int cnb_layernorm_bwd(const void* x, const void* dy, const float* gamma, const f
                       float* dgamma, float* dbeta, int64_t P, int C, int dtype, void* stream) {
     CNB_REQUIRE(x && dy && dx && gamma && save_mean && save_rstd && dgamma && dbeta && P > 0 && C > 0, "layernorm_bwd: bad arguments");
     CNB_REQUIRE(C <= 32 * LN_MAX_CPL, "layernorm_bwd: C=%d exceeds %d", C, 32 * LN_MAX_CPL);
+    if (C % vec_width(dtype) == 0 && C <= 128 * vec_width(dtype) && cnb_aligned16(x) && cnb_aligned16(dy) && cnb_aligned16(dx)) {
+        const int K = cnb_div_up(C, 32 * vec_width(dtype));
+        const dim3 grid(stream_grid(P, 8, 2));
+#define CNB_LN_BWD(KK)                                                                                                               \
+    CNB_DISPATCH_DTYPE(dtype, {                                                                                                      \
+        CNB_LAUNCH((layernorm_bwd_vec_kernel<T, KK>), grid, dim3(256), 2 * C * sizeof(float), (cudaStream_t)stream, (const T*)x,     \
+                   (const T*)dy, gamma, save_mean, save_rstd, (T*)dx, dgamma, dbeta, (long)P, C);                                    \
+    })
+        if (K == 1)
+            CNB_LN_BWD(1);
+        else if (K == 2)
+            CNB_LN_BWD(2);
+        else
+            CNB_LN_BWD(4);
+#undef CNB_LN_BWD
+        CNB_CHECK_LAUNCH("layernorm_bwd_vec_kernel");
+        return CNB_OK;
+    }
     CNB_DISPATCH_DTYPE(dtype, {
         CNB_LAUNCH((layernorm_bwd_kernel<T>), dim3(stream_grid(P, 8, 2)), dim3(256), 0, (cudaStream_t)stream, (const T*)x, (const T*)dy, gamma,
                    save_mean, save_rstd, (T*)dx, dgamma, dbeta, (long)P, C);
@@ -388,6 +497,14 @@ static inline float align_corners_scale(int in_len, int out_len) { return out_le
 int cnb_resize_bilinear_fwd(const void* x, void* y, int B, int Hin, int Win, int Hout, int Wout, int C, int dtype, void* stream) {
     CNB_REQUIRE(x && y && B > 0 && Hin > 0 && Win > 0 && Hout > 0 && Wout > 0 && C > 0, "resize_bilinear_fwd: bad arguments");
     const long total = (long)B * Hout * Wout * C;
+    if (C % vec_width(dtype) == 0 && cnb_aligned16(x) && cnb_aligned16(y)) {
+        CNB_DISPATCH_DTYPE(dtype, {
+            CNB_LAUNCH((resize_bilinear_fwd_vec_kernel<T>), dim3(stream_grid(total / vec_width(dtype))), dim3(256), 0, (cudaStream_t)stream,
+                       (const T*)x, (T*)y, B, Hin, Win, Hout, Wout, C, align_corners_scale(Hin, Hout), align_corners_scale(Win, Wout));
+        });
+        CNB_CHECK_LAUNCH("resize_bilinear_fwd_vec_kernel");
+        return CNB_OK;
+    }
     CNB_DISPATCH_DTYPE(dtype, {
         CNB_LAUNCH((resize_bilinear_fwd_kernel<T>), dim3(stream_grid(total)), dim3(256), 0, (cudaStream_t)stream, (const T*)x, (T*)y, B, Hin,
                    Win, Hout, Wout, C, align_corners_scale(Hin, Hout), align_corners_scale(Win, Wout));
@@ -399,6 +516,14 @@ int cnb_resize_bilinear_fwd(const void* x, void* y, int B, int Hin, int Win, int
 int cnb_resize_bilinear_bwd(const void* dy, void* dx, int B, int Hin, int Win, int Hout, int Wout, int C, int dtype, void* stream) {
     CNB_REQUIRE(dy && dx && B > 0 && Hin > 0 && Win > 0 && Hout > 0 && Wout > 0 && C > 0, "resize_bilinear_bwd: bad arguments");
     const long total = (long)B * Hin * Win * C;
+    if (C % vec_width(dtype) == 0 && cnb_aligned16(dy) && cnb_aligned16(dx)) {
+        CNB_DISPATCH_DTYPE(dtype, {
+            CNB_LAUNCH((resize_bilinear_bwd_vec_kernel<T>), dim3(stream_grid(total / vec_width(dtype))), dim3(256), 0, (cudaStream_t)stream,
+                       (const T*)dy, (T*)dx, B, Hin, Win, Hout, Wout, C, align_corners_scale(Hin, Hout), align_corners_scale(Win, Wout));
+        });
+        CNB_CHECK_LAUNCH("resize_bilinear_bwd_vec_kernel");
+        return CNB_OK;
+    }
     CNB_DISPATCH_DTYPE(dtype, {
         CNB_LAUNCH((resize_bilinear_bwd_kernel<T>), dim3(stream_grid(total)), dim3(256), 0, (cudaStream_t)stream, (const T*)dy, (T*)dx, B, Hin,
                    Win, Hout, Wout, C, align_corners_scale(Hin, Hout), align_corners_scale(Win, Wout));

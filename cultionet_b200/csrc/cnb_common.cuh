@@ -83,6 +83,42 @@ __device__ __forceinline__ void cnb_st(bf16_t* p, float v) { *p = __float2bfloat
 __device__ __forceinline__ float cnb_round(float v, const float*) { return v; }
 __device__ __forceinline__ float cnb_round(float v, const bf16_t*) { return __bfloat162float(__float2bfloat16(v)); }
 
+// ---------------------------------------------------------------------------------------------
+// 16-byte vector access (8 x bf16 or 4 x fp32): what every bandwidth-bound kernel moves per thread per step
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct cnb_vec {
+    static constexpr int N = 16 / (int)sizeof(T);
+};
+__device__ __forceinline__ float cnb_bits2f(uint32_t u) {
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+__device__ __forceinline__ void cnb_ldv(const float* p, float* v) {
+    const float4 r = *reinterpret_cast<const float4*>(p);
+    v[0] = r.x, v[1] = r.y, v[2] = r.z, v[3] = r.w;
+}
+__device__ __forceinline__ void cnb_ldv(const bf16_t* p, float* v) {
+    const uint4 r = *reinterpret_cast<const uint4*>(p);
+    v[0] = cnb_bits2f(r.x << 16), v[1] = cnb_bits2f(r.x & 0xffff0000u);
+    v[2] = cnb_bits2f(r.y << 16), v[3] = cnb_bits2f(r.y & 0xffff0000u);
+    v[4] = cnb_bits2f(r.z << 16), v[5] = cnb_bits2f(r.z & 0xffff0000u);
+    v[6] = cnb_bits2f(r.w << 16), v[7] = cnb_bits2f(r.w & 0xffff0000u);
+}
+__device__ __forceinline__ void cnb_stv(float* p, const float* v) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+__device__ __forceinline__ uint32_t cnb_pack_bf16x2(float lo, float hi) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    uint32_t u;
+    memcpy(&u, &h, 4);
+    return u;
+}
+__device__ __forceinline__ void cnb_stv(bf16_t* p, const float* v) {
+    *reinterpret_cast<uint4*>(p) =
+        make_uint4(cnb_pack_bf16x2(v[0], v[1]), cnb_pack_bf16x2(v[2], v[3]), cnb_pack_bf16x2(v[4], v[5]), cnb_pack_bf16x2(v[6], v[7]));
+}
+static inline bool cnb_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
 __device__ __forceinline__ float cnb_exp(float x) {
 #ifdef CNB_EMU
     return expf(x);

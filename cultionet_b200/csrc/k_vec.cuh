@@ -1,0 +1,418 @@
+// 128-bit versions of the bandwidth-bound kernels (BatchNorm statistics / apply / backward, n-ary add, LayerNorm, bilinear
+// resize, bias gradient) for pixel-major [P][C] tensors whose channel count is a multiple of the 16-byte vector width
+// (8 x bf16 or 4 x fp32).  Every thread moves whole 16-byte vectors and stays on ONE channel group for its whole life
+// (the grid stride is a multiple of the row length), so per-channel parameters live in registers and there is no
+// integer division in the streaming loop.  cnb_api.cu picks these when alignment and divisibility allow and the scalar
+// kernels of k_norm.cuh / k_misc.cuh otherwise.
+#pragma once
+#include "cnb_common.cuh"
+#include "k_misc.cuh"
+#include "k_norm.cuh"
+
+namespace cnb {
+
+// ---------------------------------------------------------------------------------------------------------------------
+// BatchNorm: x is [P][C], vector index i covers channels (i % CV)*V .. +V
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) bn_stats_vec_kernel(const T* __restrict__ x, long total_v, int CV, long stride_v, int C,
+                                                          float* __restrict__ sums) {
+    constexpr int V = cnb_vec<T>::N;
+    CNB_DYN_SMEM(sh_raw);  // 2*C floats
+    float* sh_dyn = reinterpret_cast<float*>(sh_raw);
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh_dyn[i] = 0.f;
+    __syncthreads();
+    const long gid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid < stride_v) {
+        const int c0 = (int)(gid % CV) * V;
+        float s[V], q[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) s[j] = 0.f, q[j] = 0.f;
+#pragma unroll 4
+        for (long i = gid; i < total_v; i += stride_v) {
+            float v[V];
+            cnb_ldv(x + i * V, v);
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                s[j] += v[j];
+                q[j] = fmaf(v[j], v[j], q[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            atomicAdd(&sh_dyn[c0 + j], s[j]);
+            atomicAdd(&sh_dyn[C + c0 + j], q[j]);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&sums[i], sh_dyn[i]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_act_fwd_vec_kernel(const T* __restrict__ x, const float* __restrict__ scale,
+                                                            const float* __restrict__ shift, const T* __restrict__ residual,
+                                                            T* __restrict__ y, long total_v, int CV, long stride_v, int act) {
+    constexpr int V = cnb_vec<T>::N;
+    const long gid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= stride_v) return;
+    const int c0 = (int)(gid % CV) * V;
+    float sc[V], sf[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) sc[j] = scale[c0 + j], sf[j] = shift[c0 + j];
+#pragma unroll 2
+    for (long i = gid; i < total_v; i += stride_v) {
+        float v[V];
+        cnb_ldv(x + i * V, v);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            float z = fmaf(v[j], sc[j], sf[j]);
+            v[j] = act ? cnb_silu(z) : z;
+        }
+        if (residual) {
+            float r[V];
+            cnb_ldv(residual + i * V, r);
+#pragma unroll
+            for (int j = 0; j < V; ++j) v[j] += r[j];
+        }
+        cnb_stv(y + i * V, v);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_act_bwd_reduce_vec_kernel(const T* __restrict__ x, const T* __restrict__ dy,
+                                                                   const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                   long total_v, int CV, long stride_v, int C, int act,
+                                                                   float* __restrict__ dsums) {
+    constexpr int V = cnb_vec<T>::N;
+    CNB_DYN_SMEM(sh_raw);
+    float* sh_dyn = reinterpret_cast<float*>(sh_raw);
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh_dyn[i] = 0.f;
+    __syncthreads();
+    const long gid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid < stride_v) {
+        const int c0 = (int)(gid % CV) * V;
+        float mu[V], rs[V], g[V], b[V], s[V], sx[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            mu[j] = mean[c0 + j], rs[j] = rstd[c0 + j];
+            g[j] = gamma ? gamma[c0 + j] : 1.f, b[j] = beta ? beta[c0 + j] : 0.f;
+            s[j] = 0.f, sx[j] = 0.f;
+        }
+#pragma unroll 2
+        for (long i = gid; i < total_v; i += stride_v) {
+            float xv[V], dv[V];
+            cnb_ldv(x + i * V, xv);
+            cnb_ldv(dy + i * V, dv);
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                const float xh = (xv[j] - mu[j]) * rs[j];
+                float dz = dv[j];
+                if (act) dz *= cnb_silu_grad(fmaf(xh, g[j], b[j]));
+                s[j] += dz;
+                sx[j] = fmaf(dz, xh, sx[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            atomicAdd(&sh_dyn[c0 + j], s[j]);
+            atomicAdd(&sh_dyn[C + c0 + j], sx[j]);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&dsums[i], sh_dyn[i]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_act_bwd_apply_vec_kernel(const T* __restrict__ x, const T* __restrict__ dy,
+                                                                  const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                  const float* __restrict__ dsums, float inv_count, T* __restrict__ dx,
+                                                                  long total_v, int CV, long stride_v, int C, int act, int train_stats) {
+    constexpr int V = cnb_vec<T>::N;
+    const long gid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= stride_v) return;
+    const int c0 = (int)(gid % CV) * V;
+    float mu[V], rs[V], g[V], b[V], k0[V], k1[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        mu[j] = mean[c0 + j], rs[j] = rstd[c0 + j];
+        g[j] = gamma ? gamma[c0 + j] : 1.f, b[j] = beta ? beta[c0 + j] : 0.f;
+        k0[j] = train_stats ? dsums[c0 + j] * inv_count : 0.f;
+        k1[j] = train_stats ? dsums[C + c0 + j] * inv_count : 0.f;
+    }
+#pragma unroll 2
+    for (long i = gid; i < total_v; i += stride_v) {
+        float xv[V], dv[V];
+        cnb_ldv(x + i * V, xv);
+        cnb_ldv(dy + i * V, dv);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const float xh = (xv[j] - mu[j]) * rs[j];
+            float dz = dv[j];
+            if (act) dz *= cnb_silu_grad(fmaf(xh, g[j], b[j]));
+            xv[j] = g[j] * rs[j] * (dz - k0[j] - xh * k1[j]);
+        }
+        cnb_stv(dx + i * V, xv);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) add_n_vec_kernel(const T* __restrict__ a, const T* __restrict__ b, const T* __restrict__ c,
+                                                       const T* __restrict__ d, T* __restrict__ out, long n_v) {
+    constexpr int V = cnb_vec<T>::N;
+#pragma unroll 2
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n_v; i += (long)gridDim.x * blockDim.x) {
+        float v[V], w[V];
+        cnb_ldv(a + i * V, v);
+        cnb_ldv(b + i * V, w);
+#pragma unroll
+        for (int j = 0; j < V; ++j) v[j] += w[j];
+        if (c) {
+            cnb_ldv(c + i * V, w);
+#pragma unroll
+            for (int j = 0; j < V; ++j) v[j] += w[j];
+        }
+        if (d) {
+            cnb_ldv(d + i * V, w);
+#pragma unroll
+            for (int j = 0; j < V; ++j) v[j] += w[j];
+        }
+        cnb_stv(out + i * V, v);
+    }
+}
+
+// db[n] = sum_p dy[p][n] for a dense [P][N] gradient (N % V == 0)
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ dy, long total_v, int CV, long stride_v, int N,
+                                                        float* __restrict__ db) {
+    constexpr int V = cnb_vec<T>::N;
+    CNB_DYN_SMEM(sh_raw);
+    float* sh_dyn = reinterpret_cast<float*>(sh_raw);
+    for (int i = threadIdx.x; i < N; i += blockDim.x) sh_dyn[i] = 0.f;
+    __syncthreads();
+    const long gid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid < stride_v) {
+        const int c0 = (int)(gid % CV) * V;
+        float s[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) s[j] = 0.f;
+#pragma unroll 4
+        for (long i = gid; i < total_v; i += stride_v) {
+            float v[V];
+            cnb_ldv(dy + i * V, v);
+#pragma unroll
+            for (int j = 0; j < V; ++j) s[j] += v[j];
+        }
+#pragma unroll
+        for (int j = 0; j < V; ++j) atomicAdd(&sh_dyn[c0 + j], s[j]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < N; i += blockDim.x) atomicAdd(&db[i], sh_dyn[i]);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// LayerNorm over channels: one warp per pixel, K vectors per lane (C <= 32*V*K), one read of x
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename T, int K>
+__global__ void __launch_bounds__(256) layernorm_fwd_vec_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, float eps, T* __restrict__ y,
+                                                               float* __restrict__ save_mean, float* __restrict__ save_rstd, long P,
+                                                               int C) {
+    constexpr int V = cnb_vec<T>::N;
+    const int lane = threadIdx.x & 31;
+    const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+    const float invC = 1.0f / (float)C;
+    for (long p = warp; p < P; p += nwarps) {
+        float v[K][V];
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int c = (lane + 32 * k) * V;
+            if (c < C) {
+                cnb_ldv(x + p * C + c, v[k]);
+#pragma unroll
+                for (int j = 0; j < V; ++j) s += v[k][j];
+            }
+        }
+        const float mean = cnb_warp_sum(s) * invC;
+        float q = 0.f;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int c = (lane + 32 * k) * V;
+            if (c < C) {
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    const float d = v[k][j] - mean;
+                    q = fmaf(d, d, q);
+                }
+            }
+        }
+        const float rstd = rsqrtf(cnb_warp_sum(q) * invC + eps);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int c = (lane + 32 * k) * V;
+            if (c < C) {
+#pragma unroll
+                for (int j = 0; j < V; ++j) v[k][j] = fmaf((v[k][j] - mean) * rstd, gamma[c + j], beta[c + j]);
+                cnb_stv(y + p * C + c, v[k]);
+            }
+        }
+        if (lane == 0) {
+            save_mean[p] = mean;
+            save_rstd[p] = rstd;
+        }
+    }
+}
+
+template <typename T, int K>
+__global__ void __launch_bounds__(256) layernorm_bwd_vec_kernel(const T* __restrict__ x, const T* __restrict__ dy,
+                                                               const float* __restrict__ gamma, const float* __restrict__ save_mean,
+                                                               const float* __restrict__ save_rstd, T* __restrict__ dx,
+                                                               float* __restrict__ dgamma, float* __restrict__ dbeta, long P, int C) {
+    constexpr int V = cnb_vec<T>::N;
+    CNB_DYN_SMEM(sh_raw);  // 2*C floats
+    float* sh_dyn = reinterpret_cast<float*>(sh_raw);
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh_dyn[i] = 0.f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+    const float invC = 1.0f / (float)C;
+    float g[K][V], dg[K][V], db[K][V];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int c = (lane + 32 * k) * V;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            g[k][j] = c < C ? gamma[c + j] : 0.f;
+            dg[k][j] = 0.f;
+            db[k][j] = 0.f;
+        }
+    }
+    for (long p = warp; p < P; p += nwarps) {
+        const float mean = save_mean[p], rstd = save_rstd[p];
+        float xh[K][V], d[K][V];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int c = (lane + 32 * k) * V;
+            if (c < C) {
+                cnb_ldv(x + p * C + c, xh[k]);
+                cnb_ldv(dy + p * C + c, d[k]);
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    xh[k][j] = (xh[k][j] - mean) * rstd;
+                    const float gd = d[k][j] * g[k][j];
+                    s1 += gd;
+                    s2 = fmaf(gd, xh[k][j], s2);
+                }
+            }
+        }
+        s1 = cnb_warp_sum(s1) * invC;
+        s2 = cnb_warp_sum(s2) * invC;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int c = (lane + 32 * k) * V;
+            if (c < C) {
+                float o[V];
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    o[j] = rstd * (d[k][j] * g[k][j] - s1 - xh[k][j] * s2);
+                    dg[k][j] = fmaf(d[k][j], xh[k][j], dg[k][j]);
+                    db[k][j] += d[k][j];
+                }
+                cnb_stv(dx + p * C + c, o);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int c = (lane + 32 * k) * V;
+        if (c < C) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                atomicAdd(&sh_dyn[c + j], dg[k][j]);
+                atomicAdd(&sh_dyn[C + c + j], db[k][j]);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+        atomicAdd(dgamma + i, sh_dyn[i]);
+        atomicAdd(dbeta + i, sh_dyn[C + i]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// bilinear align_corners=True resize: one thread per (pixel, channel vector)
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) resize_bilinear_fwd_vec_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int Hin, int Win,
+                                                                     int Hout, int Wout, int C, float rh, float rw) {
+    constexpr int V = cnb_vec<T>::N;
+    const int CV = C / V;
+    const long total = (long)B * Hout * Wout * CV;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % CV) * V;
+        long t = i / CV;
+        const int ox = (int)(t % Wout);
+        t /= Wout;
+        const int oy = (int)(t % Hout);
+        const long b = t / Hout;
+        int y0, y1, x0, x1;
+        float ly0, ly1, lx0, lx1;
+        bilinear_src(oy, rh, Hin, y0, y1, ly0, ly1);
+        bilinear_src(ox, rw, Win, x0, x1, lx0, lx1);
+        const T* base = x + b * Hin * Win * C + c;
+        float v00[V], v01[V], v10[V], v11[V];
+        cnb_ldv(base + ((long)y0 * Win + x0) * C, v00);
+        cnb_ldv(base + ((long)y0 * Win + x1) * C, v01);
+        cnb_ldv(base + ((long)y1 * Win + x0) * C, v10);
+        cnb_ldv(base + ((long)y1 * Win + x1) * C, v11);
+#pragma unroll
+        for (int j = 0; j < V; ++j) v00[j] = ly0 * (lx0 * v00[j] + lx1 * v01[j]) + ly1 * (lx0 * v10[j] + lx1 * v11[j]);
+        cnb_stv(y + i * V, v00);
+    }
+}
+
+// gather form of the adjoint (deterministic, no atomics): input pixel (iy, ix) collects from the output pixels that read it
+template <typename T>
+__global__ void __launch_bounds__(256) resize_bilinear_bwd_vec_kernel(const T* __restrict__ dy, T* __restrict__ dx, int B, int Hin,
+                                                                     int Win, int Hout, int Wout, int C, float rh, float rw) {
+    constexpr int V = cnb_vec<T>::N;
+    const int CV = C / V;
+    const long total = (long)B * Hin * Win * CV;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % CV) * V;
+        long t = i / CV;
+        const int ix = (int)(t % Win);
+        t /= Win;
+        const int iy = (int)(t % Hin);
+        const long b = t / Hin;
+        int ylo, yhi, xlo, xhi;
+        bilinear_candidates(iy, rh, Hout, ylo, yhi);
+        bilinear_candidates(ix, rw, Wout, xlo, xhi);
+        const T* base = dy + b * Hout * Wout * C + c;
+        float acc[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc[j] = 0.f;
+        for (int oy = ylo; oy <= yhi; ++oy) {
+            const float wy = bilinear_weight(oy, iy, rh, Hin);
+            if (wy == 0.f) continue;
+            for (int ox = xlo; ox <= xhi; ++ox) {
+                const float w = wy * bilinear_weight(ox, ix, rw, Win);
+                if (w != 0.f) {
+                    float v[V];
+                    cnb_ldv(base + ((long)oy * Wout + ox) * C, v);
+#pragma unroll
+                    for (int j = 0; j < V; ++j) acc[j] = fmaf(w, v[j], acc[j]);
+                }
+            }
+        }
+        cnb_stv(dx + i * V, acc);
+    }
+}
+
+}  // namespace cnb

@@ -92,3 +92,34 @@ def test_model_reproduces_reference_golden(dev, name):
 def test_model_eval_mode_matches_port(dev):
     cfg = dict(B=1, C=2, T=6, H=16, W=16, hidden=8, dilations=[1, 2])
     cases.model_vs_port(dev, cfg, training=False)
+
+
+# ---- 128-bit ("vec") variants of the bandwidth kernels: channel counts that are multiples of the vector width take them ----
+@pytest.mark.parametrize("dtype,C", [(F32, 8), (F32, 12), (BF16, 8), (BF16, 24)])
+@pytest.mark.parametrize("training,act,res", [(True, True, True), (False, False, False)])
+def test_batchnorm_vector_path(dev, dtype, C, training, act, res):
+    cases.batchnorm_case(dev, dtype, 2, 9, 11, C, training, act, res)
+
+
+@pytest.mark.parametrize("dtype,C", [(F32, 132), (F32, 300), (BF16, 64), (BF16, 264)])
+def test_layernorm_vector_path(dev, dtype, C):
+    cases.layernorm_case(dev, dtype, 2, 3, 5, C)
+
+
+@pytest.mark.parametrize("sizes", [(7, 7, 8, 8), (13, 13, 25, 25), (10, 10, 7, 7)])
+def test_resize_bilinear_vector_path(dev, sizes):
+    cases.resize_case(dev, F32, 2, *sizes, 8)
+    cases.resize_case(dev, BF16, 2, *sizes, 16)
+
+
+def test_conv_bias_grad_vector_path(dev):
+    cases.conv_case(dev, F32, 2, 9, 11, [5, 7], 8, 3, 1, 1, 1)
+    cases.conv_case(dev, BF16, 2, 9, 11, [8], 16, 1, 1, 0, 1)
+
+
+def test_tiny_channel_convs(dev):
+    # Psi-Net second-stage convolutions: 3 -> 1 (bias) and the 3 x [1] -> 3 fuse convolution
+    cases.conv_case(dev, F32, 2, 9, 11, [3], 1, 3, 1, 1, 1)
+    cases.conv_case(dev, BF16, 2, 9, 11, [1, 1, 1], 3, 3, 1, 1, 1)
+    cases.conv_case(dev, F32, 1, 9, 11, [4], 2, 3, 2, 1, 1)
+    cases.convT_case(dev, F32, 1, 5, 6, 3, 2, 2)
