@@ -94,8 +94,9 @@ _PROTOS = {
     "cnb_add_n": [_vp, _vp, _vp, _vp, _vp, _i64, _i, _vp],
     "cnb_layernorm_fwd": [_vp, _vp, _vp, _f, _vp, _vp, _vp, _i64, _i, _i, _vp],
     "cnb_layernorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp],
-    "cnb_na2d_fwd": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp],
-    "cnb_na2d_bwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp],
+    "cnb_na2d_tiled_eligible": [_i, _i, _i, _i, _i, _i, _i, _i],
+    "cnb_na2d_fwd": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp],
+    "cnb_na2d_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp],
     "cnb_resize_bilinear_fwd": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "cnb_resize_bilinear_bwd": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "cnb_pretime_conv_fwd": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],

@@ -460,11 +460,74 @@ static int check_na(int B, int H, int W, int heads, int hd, int ksize, int dilat
     return CNB_OK;
 }
 
-int cnb_na2d_fwd(const void* qkv, void* out, int B, int H, int W, int heads, int hd, int ksize, int dilation, float scale, int dtype,
-                 void* stream) {
+// geometry of the tiled kernels; returns false when the shape must take the warp-per-(pixel, head) kernels instead
+static bool na_tile_setup(int B, int H, int W, int heads, int hd, int ksize, int dil, float scale, int dtype, bool with_stats, NaTile* g,
+                          int* lph, size_t* smem) {
+    const int V = vec_width(dtype);
+    const size_t es = dtype == CNB_BF16 ? 2 : 4;
+    if (hd % V != 0) return false;
+    const int l = hd / V;
+    if (l > 32 || (l & (l - 1)) != 0) return false;
+    if (dil > NA_TH) return false;  // the halo bound needs TILE >= dilation
+    const int span = (ksize - 1) * dil;
+    g->B = B, g->H = H, g->W = W, g->heads = heads, g->hd = hd, g->ksize = ksize, g->dil = dil, g->scale = scale;
+    g->RH = H < NA_TH + span ? H : NA_TH + span;
+    g->RW = W < NA_TW + span ? W : NA_TW + span;
+    g->tiles_y = cnb_div_up(H, NA_TH);
+    g->tiles_x = cnb_div_up(W, NA_TW);
+    *smem = (size_t)g->RH * g->RW * 2 * hd * es + (with_stats ? (size_t)g->RH * g->RW * 2 * sizeof(float) : 0);
+    if (*smem > (size_t)NA_MAX_SMEM) return false;
+    if ((long)B * g->tiles_y * g->tiles_x > 2147483647L || heads > 65535) return false;
+    *lph = l;
+    return true;
+}
+
+#ifdef CNB_EMU
+#define CNB_SET_SMEM(kfn, bytes) ((void)0)
+#else
+#define CNB_SET_SMEM(kfn, bytes) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))
+#endif
+// launch a `template <typename T, int LPH>` tiled NA kernel
+#define CNB_NA_LAUNCH_LPH(KERNEL, LPHV, ...)                                                                       \
+    CNB_DISPATCH_DTYPE(dtype, {                                                                                    \
+        CNB_SET_SMEM((KERNEL<T, LPHV>), smem);                                                                     \
+        CNB_LAUNCH((KERNEL<T, LPHV>), grid, dim3(NA_TILE_THREADS), smem, (cudaStream_t)stream, __VA_ARGS__);       \
+    })
+#define CNB_NA_LAUNCH(KERNEL, ...)                                   \
+    do {                                                             \
+        switch (lph) {                                               \
+            case 1: CNB_NA_LAUNCH_LPH(KERNEL, 1, __VA_ARGS__); break;   \
+            case 2: CNB_NA_LAUNCH_LPH(KERNEL, 2, __VA_ARGS__); break;   \
+            case 4: CNB_NA_LAUNCH_LPH(KERNEL, 4, __VA_ARGS__); break;   \
+            case 8: CNB_NA_LAUNCH_LPH(KERNEL, 8, __VA_ARGS__); break;   \
+            case 16: CNB_NA_LAUNCH_LPH(KERNEL, 16, __VA_ARGS__); break; \
+            default: CNB_NA_LAUNCH_LPH(KERNEL, 32, __VA_ARGS__); break; \
+        }                                                            \
+    } while (0)
+
+int cnb_na2d_tiled_eligible(int B, int H, int W, int heads, int hd, int ksize, int dilation, int dtype) {
+    if (check_na(B, H, W, heads, hd, ksize, dilation)) return 0;
+    NaTile g;
+    int lph;
+    size_t smem;
+    return na_tile_setup(B, H, W, heads, hd, ksize, dilation, 1.f, dtype, true, &g, &lph, &smem) ? 1 : 0;
+}
+
+int cnb_na2d_fwd(const void* qkv, void* out, float* lse, int B, int H, int W, int heads, int hd, int ksize, int dilation, float scale,
+                 int dtype, void* stream) {
     int rc = check_na(B, H, W, heads, hd, ksize, dilation);
     if (rc) return rc;
     CNB_REQUIRE(qkv && out, "na2d_fwd: null pointer");
+    NaTile g;
+    int lph;
+    size_t smem;
+    if (lse && cnb_aligned16(qkv) && cnb_aligned16(out) &&
+        na_tile_setup(B, H, W, heads, hd, ksize, dilation, scale, dtype, false, &g, &lph, &smem)) {
+        const dim3 grid(B * g.tiles_y * g.tiles_x, heads);
+        CNB_NA_LAUNCH(na2d_fwd_tile_kernel, (const T*)qkv, (T*)out, lse, g);
+        CNB_CHECK_LAUNCH("na2d_fwd_tile_kernel");
+        return CNB_OK;
+    }
     const long items = (long)B * H * W * heads;
     CNB_DISPATCH_DTYPE(dtype, {
         CNB_LAUNCH((na2d_fwd_kernel<T>), dim3(stream_grid(items, 8)), dim3(256), 0, (cudaStream_t)stream, (const T*)qkv, (T*)out, B, H, W, heads,
@@ -474,11 +537,23 @@ int cnb_na2d_fwd(const void* qkv, void* out, int B, int H, int W, int heads, int
     return CNB_OK;
 }
 
-int cnb_na2d_bwd(const void* qkv, const void* dout, float* dqkv_acc, void* dqkv, int B, int H, int W, int heads, int hd, int ksize, int dilation,
-                 float scale, int dtype, void* stream) {
+int cnb_na2d_bwd(const void* qkv, const void* dout, const void* out, const float* lse, float* dvec, float* dqkv_acc, void* dqkv, int B, int H,
+                 int W, int heads, int hd, int ksize, int dilation, float scale, int dtype, void* stream) {
     int rc = check_na(B, H, W, heads, hd, ksize, dilation);
     if (rc) return rc;
-    CNB_REQUIRE(qkv && dout && dqkv_acc && dqkv, "na2d_bwd: null pointer");
+    CNB_REQUIRE(qkv && dout && dqkv, "na2d_bwd: null pointer");
+    NaTile g;
+    int lph;
+    size_t smem;
+    if (out && lse && dvec && cnb_aligned16(qkv) && cnb_aligned16(dout) && cnb_aligned16(out) && cnb_aligned16(dqkv) &&
+        na_tile_setup(B, H, W, heads, hd, ksize, dilation, scale, dtype, true, &g, &lph, &smem)) {
+        const dim3 grid(B * g.tiles_y * g.tiles_x, heads);
+        CNB_NA_LAUNCH(na2d_bwd_dq_tile_kernel, (const T*)qkv, (const T*)dout, (const T*)out, lse, dvec, (T*)dqkv, g);
+        CNB_NA_LAUNCH(na2d_bwd_dkv_tile_kernel, (const T*)qkv, (const T*)dout, lse, (const float*)dvec, (T*)dqkv, g);
+        CNB_CHECK_LAUNCH("na2d_bwd_tile_kernels");
+        return CNB_OK;
+    }
+    CNB_REQUIRE(dqkv_acc, "na2d_bwd: this shape takes the scatter kernel and needs the fp32 accumulation workspace");
     const long items = (long)B * H * W * heads;
     const long n = (long)B * H * W * 3 * heads * hd;
     CNB_MEMSET_ASYNC(dqkv_acc, 0, sizeof(float) * n, (cudaStream_t)stream);

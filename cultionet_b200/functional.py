@@ -312,21 +312,33 @@ class _NA2DFn(torch.autograd.Function):
         Cn = C3 // 3
         hd = Cn // heads
         out = torch.empty((B, H, W, Cn), dtype=qkv.dtype, device=qkv.device)
-        call("cnb_na2d_fwd", ptr(qkv), ptr(out), B, H, W, heads, hd, ksize, dilation, scale, dtype_code(qkv.dtype), stream_ptr(qkv))
-        ctx.save_for_backward(qkv)
-        ctx.meta = (heads, hd, ksize, dilation, scale)
+        # the eligibility query returns 1/0 directly (every other entry point returns an error code)
+        tiled = bool(_lib.lib().cnb_na2d_tiled_eligible(B, H, W, heads, hd, ksize, dilation, dtype_code(qkv.dtype)))
+        lse = torch.empty((B, H, W, heads), dtype=torch.float32, device=qkv.device) if tiled else None
+        call("cnb_na2d_fwd", ptr(qkv), ptr(out), ptr(lse), B, H, W, heads, hd, ksize, dilation, scale, dtype_code(qkv.dtype), stream_ptr(qkv))
+        if tiled:
+            ctx.save_for_backward(qkv, out, lse)
+        else:
+            ctx.save_for_backward(qkv)
+        ctx.meta = (heads, hd, ksize, dilation, scale, tiled)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        (qkv,) = ctx.saved_tensors
-        heads, hd, ksize, dilation, scale = ctx.meta
+        heads, hd, ksize, dilation, scale, tiled = ctx.meta
         dout = _contig(dout)
+        if tiled:
+            qkv, out, lse = ctx.saved_tensors
+            acc = None
+            dvec = torch.empty_like(lse)
+        else:
+            (qkv,) = ctx.saved_tensors
+            out = lse = dvec = None
+            acc = torch.empty(qkv.shape, dtype=torch.float32, device=qkv.device)
         B, H, W, _ = qkv.shape
-        acc = torch.empty(qkv.shape, dtype=torch.float32, device=qkv.device)
         dqkv = torch.empty_like(qkv)
-        call("cnb_na2d_bwd", ptr(qkv), ptr(dout), ptr(acc), ptr(dqkv), B, H, W, heads, hd, ksize, dilation, scale,
-             dtype_code(qkv.dtype), stream_ptr(qkv))
+        call("cnb_na2d_bwd", ptr(qkv), ptr(dout), ptr(out), ptr(lse), ptr(dvec), ptr(acc), ptr(dqkv), B, H, W, heads, hd, ksize, dilation,
+             scale, dtype_code(qkv.dtype), stream_ptr(qkv))
         return dqkv, None, None, None, None
 
 

@@ -152,11 +152,18 @@ int cnb_layernorm_bwd(const void* x, const void* dy, const float* gamma, const f
  * as configured at convolution.py:341-350; window rule in oracle/natten_ref.py).
  * qkv: [B,H,W,3*heads*hd] with channel order (3, heads, hd); out: [B,H,W,heads*hd].
  * ------------------------------------------------------------------------------------------------ */
-int cnb_na2d_fwd(const void* qkv, void* out, int B, int H, int W, int heads, int hd, int ksize, int dilation, float scale,
+/* Two implementations: a tiled one (8x16 pixel tile of one head per CTA, k/v + halo staged in shared memory, online softmax,
+ * gather-form backward without atomics) for head_dim a multiple of the 16-byte vector width, and a warp-per-(pixel, head) kernel
+ * for everything else.  cnb_na2d_tiled_eligible() tells the caller which workspaces the backward will need. */
+int cnb_na2d_tiled_eligible(int B, int H, int W, int heads, int hd, int ksize, int dilation, int dtype);
+/* lse: fp32 [B,H,W,heads] log-sum-exp of the scaled logits (written by the tiled kernel; may be NULL -> warp kernel) */
+int cnb_na2d_fwd(const void* qkv, void* out, float* lse, int B, int H, int W, int heads, int hd, int ksize, int dilation, float scale,
                  int dtype, void* stream);
-/* dqkv_acc: fp32 [B,H,W,3*heads*hd] scratch (zeroed inside); dqkv: same shape in `dtype` */
-int cnb_na2d_bwd(const void* qkv, const void* dout, float* dqkv_acc, void* dqkv, int B, int H, int W, int heads, int hd, int ksize,
-                 int dilation, float scale, int dtype, void* stream);
+/* tiled path: needs out (the forward result), lse and dvec (fp32 [B,H,W,heads] scratch); dqkv_acc may be NULL.
+ * warp path:  needs dqkv_acc, fp32 [B,H,W,3*heads*hd] scratch (zeroed inside); out/lse/dvec may be NULL.
+ * dqkv: [B,H,W,3*heads*hd] in `dtype`. */
+int cnb_na2d_bwd(const void* qkv, const void* dout, const void* out, const float* lse, float* dvec, float* dqkv_acc, void* dqkv,
+                 int B, int H, int W, int heads, int hd, int ksize, int dilation, float scale, int dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Bilinear resize, align_corners=True, pixel-major (check_upsample, nn/functional.py:72-81)
