@@ -270,6 +270,7 @@ def main() -> None:
         for _ in range(nprof):
             resident_step()
         summ = _lib.TIMER.summary()
+        shapes = _lib.TIMER.by_detail()
         _lib.TIMER = None
         conv = {k: v for k, v in summ.items() if k.startswith("conv") and v["flops"] > 0}
         if conv:
@@ -284,6 +285,10 @@ def main() -> None:
                         "avg_launch_ms": ms / calls, "share_of_step_kernel_time": ms / total_ms, "peak_source": peaks["source"] + " (sustained)",
                         "by_class": {k: {"calls_per_step": v["calls"] // nprof, "ms_per_step": v["ms"] / nprof,
                                          "tflops": v["flops"] / (v["ms"] / 1e3) / 1e12} for k, v in conv.items()},
+                        "top_conv_shapes": [
+                            {"shape": k, "calls_per_step": v["calls"] // nprof, "ms_per_step": round(v["ms"] / nprof, 4),
+                             "tflops": round(v["flops"] / (v["ms"] / 1e3) / 1e12, 1) if v["ms"] > 0 else None}
+                            for k, v in sorted(shapes.items(), key=lambda kv: -kv[1]["ms"]) if k.startswith("conv")][:40],
                         "other_ms_per_step": {k: v["ms"] / nprof for k, v in sorted(summ.items(), key=lambda kv: -kv[1]["ms"])
                                               if not k.startswith("conv")}}
 

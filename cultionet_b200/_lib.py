@@ -179,12 +179,24 @@ class KernelTimer:
     def summary(self) -> dict:
         torch.cuda.synchronize()
         out: dict = {}
-        for name, flops, nbytes, e0, e1 in self.records:
+        for name, flops, nbytes, e0, e1, _detail in self.records:
             d = out.setdefault(name, {"calls": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
             d["calls"] += 1
             d["ms"] += e0.elapsed_time(e1)
             d["flops"] += flops or 0.0
             d["bytes"] += nbytes or 0.0
+        return out
+
+
+    def by_detail(self) -> dict:
+        """Same records keyed by (tag, detail), e.g. one entry per convolution shape."""
+        torch.cuda.synchronize()
+        out: dict = {}
+        for name, flops, nbytes, e0, e1, detail in self.records:
+            d = out.setdefault(f"{name} {detail or ''}".strip(), {"calls": 0, "ms": 0.0, "flops": 0.0})
+            d["calls"] += 1
+            d["ms"] += e0.elapsed_time(e1)
+            d["flops"] += flops or 0.0
         return out
 
 
@@ -195,14 +207,14 @@ def launch_count() -> int:
     return int(lib().cnb_launch_count())
 
 
-def call(name: str, *args, flops: float = None, nbytes: float = None, tag: str = None) -> None:
+def call(name: str, *args, flops: float = None, nbytes: float = None, tag: str = None, detail: str = None) -> None:
     fn = getattr(lib(), name)
     if TIMER is not None and not _is_emulator:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         rc = fn(*args)
         e1.record()
-        TIMER.records.append((tag or name, flops, nbytes, e0, e1))
+        TIMER.records.append((tag or name, flops, nbytes, e0, e1, detail))
     else:
         rc = fn(*args)
     if rc != 0:

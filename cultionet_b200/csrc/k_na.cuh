@@ -213,10 +213,13 @@ __device__ __forceinline__ int na_region_origin(int t0, int halo, int len, int r
     return o;
 }
 
+// sum over the LPH lanes that share one (pixel, head).  The shuffle names only that lane group: near the image border different
+// pixels of a warp walk different neighbour lists, so the warp as a whole is NOT converged here.
 template <int LPH>
 __device__ __forceinline__ float na_group_sum(float v) {
+    const unsigned gmask = LPH == 32 ? 0xffffffffu : (((1u << (LPH & 31)) - 1u) << ((threadIdx.x & 31u) & ~(unsigned)(LPH - 1)));
 #pragma unroll
-    for (int o = LPH / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    for (int o = LPH / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
     return v;
 }
 
@@ -234,6 +237,21 @@ __device__ __forceinline__ void na_stage_region(T* sm, const T* a_base, const T*
         const long pix = img_pix0 + (long)(ry0 + ry) * g.W + (rx0 + rx);
         const T* src = (part < parts ? a_base + part * V : b_base + (part - parts) * V) + pix * pix_stride;
         *reinterpret_cast<uint4*>(sm + (long)r * 2 * g.hd + part * V) = *reinterpret_cast<const uint4*>(src);
+    }
+}
+
+// k / v row segment of neighbour (ny, nx): from the staged region, or straight from global memory should a neighbour ever fall
+// outside it (the region is sized so that it does not; this keeps correctness independent of that argument)
+template <typename T>
+__device__ __forceinline__ void na_kv_ptr(const T* sm, const T* qkv, const NaTile& g, int C, int head, int choff, long img_pix0, int ry0,
+                                          int rx0, int ny, int nx, const T*& kp, const T*& vp) {
+    const int ry = ny - ry0, rx = nx - rx0;
+    if (ry >= 0 && ry < g.RH && rx >= 0 && rx < g.RW) {
+        kp = sm + ((long)ry * g.RW + rx) * 2 * g.hd + choff;
+        vp = kp + g.hd;
+    } else {
+        kp = qkv + (img_pix0 + (long)ny * g.W + nx) * 3 * C + C + head * g.hd + choff;
+        vp = kp + C;
     }
 }
 
@@ -263,7 +281,8 @@ __global__ void __launch_bounds__(NA_TILE_THREADS) na2d_fwd_tile_kernel(const T*
         const int pl = it / LPH;
         const int lx = pl % NA_TW, ly = pl / NA_TW;
         const bool valid = (y0 + ly) < g.H && (x0 + lx) < g.W;
-        const int y = valid ? y0 + ly : g.H - 1, x = valid ? x0 + lx : g.W - 1;  // out-of-image lanes shadow a real pixel (shuffles stay uniform)
+        // out-of-image lanes shadow a real pixel OF THIS TILE (shuffles stay uniform, the staged region covers its window)
+        const int y = (y0 + ly) < g.H ? y0 + ly : g.H - 1, x = (x0 + lx) < g.W ? x0 + lx : g.W - 1;
         const long pix = img_pix0 + (long)y * g.W + x;
         float q[V];
         cnb_ldv(qkv + pix * 3 * C + head * g.hd + sub * V, q);
@@ -274,9 +293,11 @@ __global__ void __launch_bounds__(NA_TILE_THREADS) na2d_fwd_tile_kernel(const T*
 #pragma unroll
         for (int j = 0; j < V; ++j) o[j] = 0.f;
         for (int a = 0; a < g.ksize; ++a) {
-            const T* rowp = sm + ((long)(sy + a * g.dil - ry0) * g.RW + (sx - rx0)) * 2 * g.hd + sub * V;
+            const int ny = sy + a * g.dil;
             for (int bb = 0; bb < g.ksize; ++bb) {
-                const T* kp = rowp + (long)bb * g.dil * 2 * g.hd;
+                const int nx = sx + bb * g.dil;
+                const T *kp, *vp;
+                na_kv_ptr(sm, qkv, g, C, head, sub * V, img_pix0, ry0, rx0, ny, nx, kp, vp);
                 float kv[V];
                 cnb_ldv(kp, kv);
                 float part = 0.f;
@@ -285,7 +306,7 @@ __global__ void __launch_bounds__(NA_TILE_THREADS) na2d_fwd_tile_kernel(const T*
                 const float sc = na_group_sum<LPH>(part);
                 const float mn = fmaxf(m, sc);
                 const float corr = cnb_exp(m - mn), pe = cnb_exp(sc - mn);
-                cnb_ldv(kp + g.hd, kv);
+                cnb_ldv(vp, kv);
                 l = fmaf(l, corr, pe);
 #pragma unroll
                 for (int j = 0; j < V; ++j) o[j] = fmaf(o[j], corr, pe * kv[j]);
@@ -330,7 +351,7 @@ __global__ void __launch_bounds__(NA_TILE_THREADS) na2d_bwd_dq_tile_kernel(const
         const int pl = it / LPH;
         const int lx = pl % NA_TW, ly = pl / NA_TW;
         const bool valid = (y0 + ly) < g.H && (x0 + lx) < g.W;
-        const int y = valid ? y0 + ly : g.H - 1, x = valid ? x0 + lx : g.W - 1;
+        const int y = (y0 + ly) < g.H ? y0 + ly : g.H - 1, x = (x0 + lx) < g.W ? x0 + lx : g.W - 1;
         const long pix = img_pix0 + (long)y * g.W + x;
         float q[V], go[V], dq[V];
         cnb_ldv(qkv + pix * 3 * C + head * g.hd + sub * V, q);
@@ -351,12 +372,14 @@ __global__ void __launch_bounds__(NA_TILE_THREADS) na2d_bwd_dq_tile_kernel(const
         }
         const int sy = na_window_start(y, g.H, g.ksize, g.dil), sx = na_window_start(x, g.W, g.ksize, g.dil);
         for (int a = 0; a < g.ksize; ++a) {
-            const T* rowp = sm + ((long)(sy + a * g.dil - ry0) * g.RW + (sx - rx0)) * 2 * g.hd + sub * V;
+            const int ny = sy + a * g.dil;
             for (int bb = 0; bb < g.ksize; ++bb) {
-                const T* kp = rowp + (long)bb * g.dil * 2 * g.hd;
+                const int nx = sx + bb * g.dil;
+                const T *kp, *vp;
+                na_kv_ptr(sm, qkv, g, C, head, sub * V, img_pix0, ry0, rx0, ny, nx, kp, vp);
                 float kv[V], vv[V];
                 cnb_ldv(kp, kv);
-                cnb_ldv(kp + g.hd, vv);
+                cnb_ldv(vp, vv);
                 float ps = 0.f, pd = 0.f;
 #pragma unroll
                 for (int j = 0; j < V; ++j) {
@@ -438,7 +461,7 @@ __global__ void __launch_bounds__(NA_TILE_THREADS) na2d_bwd_dkv_tile_kernel(cons
         const int pl = it / LPH;
         const int lx = pl % NA_TW, ly = pl / NA_TW;
         const bool valid = (y0 + ly) < g.H && (x0 + lx) < g.W;
-        const int y = valid ? y0 + ly : g.H - 1, x = valid ? x0 + lx : g.W - 1;
+        const int y = (y0 + ly) < g.H ? y0 + ly : g.H - 1, x = (x0 + lx) < g.W ? x0 + lx : g.W - 1;
         const long pix = img_pix0 + (long)y * g.W + x;
         float kj[V], vj[V], dk[V], dv[V];
         cnb_ldv(qkv + pix * 3 * C + C + head * g.hd + sub * V, kj);
@@ -452,11 +475,19 @@ __global__ void __launch_bounds__(NA_TILE_THREADS) na2d_bwd_dkv_tile_kernel(cons
             for (int mx = 0; mx < 2 * g.ksize - 1; ++mx) {
                 if (!((xmask >> mx) & 1u)) continue;
                 const int ix = x + (mx - (g.ksize - 1)) * g.dil;
-                const int r = (iy - ry0) * g.RW + (ix - rx0);
-                const T* qp = sm + (long)r * 2 * g.hd + sub * V;
+                // a query clamped at the image border can attend a key up to (k-1)*d away, i.e. outside the staged region of an
+                // interior-side tile: those few candidates are read from global memory
+                const int ry = iy - ry0, rx = ix - rx0;
+                const bool staged = ry >= 0 && ry < g.RH && rx >= 0 && rx < g.RW;
+                const int r = ry * g.RW + rx;
+                const long ipix = img_pix0 + (long)iy * g.W + ix;
+                const T* qp = staged ? sm + (long)r * 2 * g.hd + sub * V : qkv + ipix * 3 * C + head * g.hd + sub * V;
+                const T* gp = staged ? qp + g.hd : dout + ipix * C + head * g.hd + sub * V;
+                const float Li = staged ? sm_l[r] : lse[ipix * g.heads + head];
+                const float Di = staged ? sm_d[r] : dvec[ipix * g.heads + head];
                 float qi[V], gi[V];
                 cnb_ldv(qp, qi);
-                cnb_ldv(qp + g.hd, gi);
+                cnb_ldv(gp, gi);
                 float ps = 0.f, pd = 0.f;
 #pragma unroll
                 for (int j = 0; j < V; ++j) {
@@ -464,8 +495,8 @@ __global__ void __launch_bounds__(NA_TILE_THREADS) na2d_bwd_dkv_tile_kernel(cons
                     pd = fmaf(gi[j], vj[j], pd);
                 }
                 const float sc = na_group_sum<LPH>(ps) * g.scale, dp = na_group_sum<LPH>(pd);
-                const float p = cnb_exp(sc - sm_l[r]);
-                const float ds = p * (dp - sm_d[r]) * g.scale;
+                const float p = cnb_exp(sc - Li);
+                const float ds = p * (dp - Di) * g.scale;
 #pragma unroll
                 for (int j = 0; j < V; ++j) {
                     dk[j] = fmaf(ds, qi[j], dk[j]);

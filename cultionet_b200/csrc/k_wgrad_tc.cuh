@@ -37,6 +37,7 @@ struct WgradTcParams {
     int Bn, THp, TWp, tiles_h, tiles_w;  // pixel tiling of the U domain
     int N, n_tiles, Ctot;
     int splits, pt_per_split, pixel_tiles;
+    int nsub, stages;  // 128-row dY sub-tiles per CTA (1 or 2, sharing the X tile) and pipeline depth
     float* dwp;
 };
 
@@ -54,20 +55,25 @@ __device__ __forceinline__ uint32_t umma_idesc_bf16_mn(int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
-constexpr int WG_STAGE_BYTES = 2 * WG_BOX_BYTES + 4 * WG_BOX_BYTES;  // dY: 128 rows, X: up to 256 columns
-constexpr int WG_SMEM_BYTES = WG_STAGES * WG_STAGE_BYTES + 1024 + 256;
+// stage = dY boxes (2 per 128-row sub-tile) followed by up to 4 X boxes; two sub-tiles share one X tile, which cuts the bytes
+// staged per MMA by a third (ncu: the single-sub-tile kernel was feed-bound at 46 % tensor-pipe activity)
+constexpr int WG_RING_BYTES = 192 * 1024;
+constexpr int WG_SMEM_BYTES = WG_RING_BYTES + 1024 + 256;
 
 __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const __grid_constant__ WgradTcParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* base_ptr = smem_raw + (base - raw);
-    const uint32_t bars = base + WG_STAGES * WG_STAGE_BYTES;  // full[S] empty[S] done slot
+    const uint32_t bars = base + WG_RING_BYTES;  // full[S] empty[S] done slot
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 8u * (WG_STAGES + s); };
     const uint32_t done_bar = bars + 8u * (2 * WG_STAGES);
     const uint32_t slot = bars + 8u * (2 * WG_STAGES + 1);
-    volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + WG_STAGES * WG_STAGE_BYTES + 8 * (2 * WG_STAGES + 1));
+    volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + WG_RING_BYTES + 8 * (2 * WG_STAGES + 1));
+    const int nsub = p.nsub, nstages = p.stages;
+    const uint32_t stage_bytes = (uint32_t)(2 * nsub + 4) * WG_BOX_BYTES;
+    const uint32_t tmem_cols = nsub == 2 ? 512u : 256u;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -82,12 +88,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const __grid_c
     const int nt = w % p.n_tiles;
     const int tap = w / p.n_tiles;
     const int c0 = p.ct_c0[ct], cw = p.ct_cw[ct];
-    const int n0 = nt * BM;
+    const int n0 = nt * BM * nsub;
     const int pt_begin = split * p.pt_per_split;
     int pt_end = pt_begin + p.pt_per_split;
     if (pt_end > p.pixel_tiles) pt_end = p.pixel_tiles;
     const int nboxes_x = cw / 64;
-    const uint32_t stage_tx = (uint32_t)(2 + nboxes_x) * WG_BOX_BYTES;
+    const uint32_t stage_tx = (uint32_t)(2 * nsub + nboxes_x) * WG_BOX_BYTES;
     const CUtensorMap* mapG = &p.tmG[p.tap_map[tap]];
     const CUtensorMap* mapDY = p.u_is_dy ? &p.tmU : mapG;
     const CUtensorMap* mapX = p.u_is_dy ? mapG : &p.tmU;
@@ -102,7 +108,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const __grid_c
         mbar_init(done_bar, 1);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(slot, 256);
+    if (warp == 1) tmem_alloc(slot, tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -124,12 +130,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const __grid_c
                 const int y0 = th * p.THp, x0 = tw * p.TWp;
                 mbar_wait(empty_bar(stage), phase ^ 1u);
                 mbar_arrive_expect_tx(full_bar(stage), stage_tx);
-                const uint32_t dst = base + stage * WG_STAGE_BYTES;
-                tma_load_4d(dst, mapDY, full_bar(stage), n0, x0 + dy_ox, y0 + dy_oy, b);
-                tma_load_4d(dst + WG_BOX_BYTES, mapDY, full_bar(stage), n0 + 64, x0 + dy_ox, y0 + dy_oy, b);
+                const uint32_t dst = base + stage * stage_bytes;
+                for (int j = 0; j < 2 * nsub; ++j)
+                    tma_load_4d(dst + j * WG_BOX_BYTES, mapDY, full_bar(stage), n0 + 64 * j, x0 + dy_ox, y0 + dy_oy, b);
                 for (int j = 0; j < nboxes_x; ++j)
-                    tma_load_4d(dst + (2 + j) * WG_BOX_BYTES, mapX, full_bar(stage), c0 + 64 * j, x0 + x_ox, y0 + x_oy, b);
-                if (++stage == WG_STAGES) {
+                    tma_load_4d(dst + (2 * nsub + j) * WG_BOX_BYTES, mapX, full_bar(stage), c0 + 64 * j, x0 + x_ox, y0 + x_oy, b);
+                if (++stage == nstages) {
                     stage = 0;
                     phase ^= 1u;
                 }
@@ -144,17 +150,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const __grid_c
             for (int pt = pt_begin; pt < pt_end; ++pt) {
                 mbar_wait(full_bar(stage), phase);
                 tc_fence_after();
-                const uint32_t a_addr = base + stage * WG_STAGE_BYTES;
-                const uint32_t b_addr = a_addr + 2 * WG_BOX_BYTES;
+                const uint32_t a_addr = base + stage * stage_bytes;
+                const uint32_t b_addr = a_addr + 2 * nsub * WG_BOX_BYTES;
+                for (int sub = 0; sub < nsub; ++sub) {
 #pragma unroll
-                for (int k = 0; k < WG_PIX / 16; ++k) {
-                    // 16 pixels (K) per instruction = two 8-row groups = 2048 bytes inside every box
-                    const uint64_t adesc = umma_desc_mn_sw128(a_addr + k * 2048, WG_BOX_BYTES);
-                    const uint64_t bdesc = umma_desc_mn_sw128(b_addr + k * 2048, WG_BOX_BYTES);
-                    umma_bf16(tmem_base, adesc, bdesc, idesc, (pt > pt_begin || k > 0) ? 1u : 0u);
+                    for (int k = 0; k < WG_PIX / 16; ++k) {
+                        // 16 pixels (K) per instruction = two 8-row groups = 2048 bytes inside every box
+                        const uint64_t adesc = umma_desc_mn_sw128(a_addr + sub * 2 * WG_BOX_BYTES + k * 2048, WG_BOX_BYTES);
+                        const uint64_t bdesc = umma_desc_mn_sw128(b_addr + k * 2048, WG_BOX_BYTES);
+                        umma_bf16(tmem_base + (uint32_t)(sub * 256), adesc, bdesc, idesc, (pt > pt_begin || k > 0) ? 1u : 0u);
+                    }
                 }
                 umma_commit(empty_bar(stage));
-                if (++stage == WG_STAGES) {
+                if (++stage == nstages) {
                     stage = 0;
                     phase ^= 1u;
                 }
@@ -167,29 +175,32 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const __grid_c
         __syncwarp();
     } else {
         const int quad = warp & 3;
-        const int n = n0 + quad * 32 + lane;
         mbar_wait(done_bar, 0);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
-        float* drow = p.dwp + ((long)p.tap_w[tap] * p.N + n) * p.Ctot + p.k_off + c0;
         const int cvalid = p.src_c - c0;  // columns of this tile that exist
-        const bool vec_red = (reinterpret_cast<uintptr_t>(drow) & 15u) == 0;  // rows are 16-byte aligned when Ctot, k_off are multiples of 4
-        if (pt_end > pt_begin) {
-            for (int c = 0; c < cw / 32; ++c) {
-                if (c * 32 >= cvalid) break;
-                uint32_t v[32];
-                tmem_ld32(taddr + (uint32_t)(c * 32), v);
-                if (n < p.N) {
-                    if (vec_red && c * 32 + 32 <= cvalid) {
+        for (int sub = 0; sub < nsub; ++sub) {
+            const int n = n0 + sub * BM + quad * 32 + lane;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(sub * 256);
+            float* drow = p.dwp + ((long)p.tap_w[tap] * p.N + n) * p.Ctot + p.k_off + c0;
+            const bool vec_red = (reinterpret_cast<uintptr_t>(drow) & 15u) == 0;  // 16-byte aligned rows when Ctot, k_off are multiples of 4
+            if (pt_end > pt_begin && n0 + sub * BM < p.N) {
+                for (int c = 0; c < cw / 32; ++c) {
+                    if (c * 32 >= cvalid) break;
+                    uint32_t v[32];
+                    tmem_ld32(taddr + (uint32_t)(c * 32), v);
+                    if (n < p.N) {
+                        if (vec_red && c * 32 + 32 <= cvalid) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(drow + c * 32 + j), "f"(__uint_as_float(v[j])),
-                                         "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
-                                         : "memory");
-                    } else {
+                            for (int j = 0; j < 32; j += 4)
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(drow + c * 32 + j),
+                                             "f"(__uint_as_float(v[j])), "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])),
+                                             "f"(__uint_as_float(v[j + 3]))
+                                             : "memory");
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (c * 32 + j < cvalid) atomicAdd(drow + c * 32 + j, __uint_as_float(v[j]));
+                            for (int j = 0; j < 32; ++j)
+                                if (c * 32 + j < cvalid) atomicAdd(drow + c * 32 + j, __uint_as_float(v[j]));
+                        }
                     }
                 }
             }
@@ -199,7 +210,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const __grid_c
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 256);
+        tmem_dealloc(tmem_base, tmem_cols);
     }
 }
 
@@ -282,7 +293,10 @@ inline int wgrad_tc_launch(const cnb_wgrad_desc* d, cudaStream_t stream) {
     p.tiles_w = cnb_div_up(u_w, p.TWp);
     p.pixel_tiles = d->B * p.tiles_h * p.tiles_w;
     p.N = d->N;
-    p.n_tiles = cnb_div_up(d->N, BM);
+    p.nsub = d->N > BM ? 2 : 1;
+    p.stages = WG_RING_BYTES / ((2 * p.nsub + 4) * WG_BOX_BYTES);
+    if (p.stages > WG_STAGES) p.stages = WG_STAGES;
+    p.n_tiles = cnb_div_up(d->N, BM * p.nsub);
     p.Ctot = d->Ctot;
     p.dwp = d->dwp;
     const int base_items = p.ntaps * p.n_tiles * p.n_ctiles;

@@ -83,7 +83,10 @@ def _launch_conv(sources, src_channels, wp, w_row_off, w_row_stride, w_tap_strid
     d.out = out.data_ptr()
     d.out_stride = out.shape[-1]
     flops = 2.0 * B * (Hin * Win if transposed else Hout * Wout) * N * sum(src_channels) * KH * KW  # algorithmic
-    call(_CONV_ENTRY[CONV_BACKEND], C.byref(d), dtype_code(dtype), stream_ptr(out), flops=flops, tag="conv_fwd/dgrad")
+    detail = None
+    if _lib.TIMER is not None:
+        detail = f"B{B} {Hin}x{Win}->{Hout}x{Wout} {'+'.join(map(str, src_channels))}->{N} k{KH} s{stride}{'T' if transposed else ''}"
+    call(_CONV_ENTRY[CONV_BACKEND], C.byref(d), dtype_code(dtype), stream_ptr(out), flops=flops, tag="conv_fwd/dgrad", detail=detail)
 
 
 class _Conv2dFn(torch.autograd.Function):
@@ -167,8 +170,11 @@ class _Conv2dFn(torch.autograd.Function):
                 d.KH, d.KW, d.stride, d.pad, d.dil, d.transposed = KH, KW, stride, pad, dil, int(transposed)
                 d.dy, d.dy_stride, d.N = dy.data_ptr(), dy_pitch, N
                 d.dwp = dwp.data_ptr()
+                detail = None
+                if _lib.TIMER is not None:
+                    detail = f"B{B} {Hin}x{Win}->{Hout}x{Wout} {c}(of {Ctot})->{N} k{KH} s{stride}{'T' if transposed else ''}"
                 call(_WGRAD_ENTRY[CONV_BACKEND], C.byref(d), dtype_code(dtype), stream_ptr(dy), flops=2.0 * B * (Hin * Win if transposed else Hout * Wout) * N * c * taps,
-                     tag="conv_wgrad")
+                     tag="conv_wgrad", detail=detail)
                 coff += c
             dw = torch.empty_like(weight, dtype=torch.float32, memory_format=torch.contiguous_format)
             rows, cols, s_n, s_k, s_tap = _weight_strides(kind, N, Ctot, taps, for_dgrad=False)

@@ -52,6 +52,17 @@ def test_neighborhood_attention(dev, cfg):
     cases.na_case(dev, F32, 2, H, W, heads, hd, k, d)
 
 
+@pytest.mark.parametrize("cfg", [(2, 8, 3, 2, 30, 41), (1, 16, 5, 1, 21, 37), (2, 4, 3, 1, 17, 50), (1, 8, 7, 2, 33, 35)])
+def test_neighborhood_attention_multi_tile(dev, cfg):
+    # images larger than one 8x16 tile + halo: interior tiles, slid border regions, border queries reaching across tiles
+    heads, hd, k, d, H, W = cfg
+    cases.na_case(dev, F32, 1, H, W, heads, hd, k, d)
+
+
+def test_neighborhood_attention_multi_tile_bf16(dev):
+    cases.na_case(dev, BF16, 1, 20, 40, 2, 16, 3, 2)
+
+
 def test_neighborhood_attention_rejects_small_input(dev):
     from cultionet_b200 import _lib
     from cultionet_b200 import functional as F
