@@ -190,9 +190,9 @@ int cnb_conv2d_wgrad_tc(const cnb_wgrad_desc* d, int dtype, void* stream) {
 int cnb_conv2d_wgrad_tiny(const cnb_wgrad_desc* d, int dtype, void* stream) {
     int rc = check_wgrad_desc(d);
     if (rc) return rc;
-    if (!wgrad_tiny_eligible(d)) CNB_FAIL(CNB_ERR_UNSUPPORTED, "conv2d_wgrad_tiny: needs N <= %d and a source slice of at most %d channels", TINY_MAX_N, TINY_WG_MAX_C);
+    if (!wgrad_tiny_eligible(d)) CNB_FAIL(CNB_ERR_UNSUPPORTED, "conv2d_wgrad_tiny: needs N <= %d and a source slice of at most %d channels", TINY_WG_MAX_N, TINY_MAX_C);
     const long M = (long)d->B * d->Hout * d->Wout;
-    dim3 grid(stream_grid(M, 256, 1), d->KH * d->KW);
+    dim3 grid(stream_grid(M, 256, 1), d->KH * d->KW, cnb_div_up(d->src_c, TINY_WG_MAX_C));
     CNB_DISPATCH_DTYPE(dtype, { CNB_LAUNCH((conv_tiny_wgrad_kernel<T>), grid, dim3(256), 0, (cudaStream_t)stream, *d); });
     CNB_CHECK_LAUNCH("conv_tiny_wgrad_kernel");
     return CNB_OK;

@@ -117,6 +117,19 @@ __device__ __forceinline__ void cnb_stv(bf16_t* p, const float* v) {
     *reinterpret_cast<uint4*>(p) =
         make_uint4(cnb_pack_bf16x2(v[0], v[1]), cnb_pack_bf16x2(v[2], v[3]), cnb_pack_bf16x2(v[4], v[5]), cnb_pack_bf16x2(v[6], v[7]));
 }
+// 16-byte asynchronous global -> shared copy (LDGSTS): a thread can keep many of these in flight while it issues more
+__device__ __forceinline__ void cnb_cp_async16(void* smem_dst, const void* gsrc) {
+#ifdef CNB_EMU
+    memcpy(smem_dst, gsrc, 16);
+#else
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+#endif
+}
+__device__ __forceinline__ void cnb_cp_async_wait_all() {
+#ifndef CNB_EMU
+    asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+}
 static inline bool cnb_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 __device__ __forceinline__ float cnb_exp(float x) {

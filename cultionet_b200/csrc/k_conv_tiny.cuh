@@ -8,10 +8,11 @@
 
 namespace cnb {
 
-constexpr int TINY_MAX_N = 8;     // output channels
+constexpr int TINY_MAX_N = 16;    // output channels
 constexpr int TINY_MAX_C = 16;    // input channels over all sources
 constexpr int TINY_MAX_TAPS = 16;
-constexpr int TINY_WG_MAX_C = 4;  // source-slice channels of the weight-gradient kernel
+constexpr int TINY_WG_MAX_C = 4;  // source channels per CTA of the weight-gradient kernel (blockIdx.z walks chunks of 4)
+constexpr int TINY_WG_MAX_N = 8;
 
 inline bool conv_tiny_eligible(const cnb_conv_desc* d) {
     int ctot = 0;
@@ -20,7 +21,7 @@ inline bool conv_tiny_eligible(const cnb_conv_desc* d) {
 }
 
 inline bool wgrad_tiny_eligible(const cnb_wgrad_desc* d) {
-    return d->N <= TINY_MAX_N && d->src_c <= TINY_WG_MAX_C && d->KH * d->KW <= TINY_MAX_TAPS;
+    return d->N <= TINY_WG_MAX_N && d->src_c <= TINY_MAX_C && d->KH * d->KW <= TINY_MAX_TAPS;
 }
 
 template <typename T>
@@ -73,17 +74,19 @@ __global__ void __launch_bounds__(256) conv_tiny_kernel(cnb_conv_desc d, int cto
     }
 }
 
-// dWp[tap][n][k_off + c] += sum_p dY[p][n] * X[gather(p, tap)][c]; grid = (pixel blocks, taps)
+// dWp[tap][n][k_off + c] += sum_p dY[p][n] * X[gather(p, tap)][c]; grid = (pixel blocks, taps, 4-channel chunks of the source)
 template <typename T>
 __global__ void __launch_bounds__(256) conv_tiny_wgrad_kernel(cnb_wgrad_desc d) {
-    __shared__ float red[TINY_MAX_N * TINY_WG_MAX_C];
+    __shared__ float red[TINY_WG_MAX_N * TINY_WG_MAX_C];
     const int tap = blockIdx.y;
+    const int cbase = blockIdx.z * TINY_WG_MAX_C;
+    const int cn = d.src_c - cbase < TINY_WG_MAX_C ? d.src_c - cbase : TINY_WG_MAX_C;  // channels of this chunk
     const int ky = tap / d.KW, kx = tap - ky * d.KW;
-    if (threadIdx.x < TINY_MAX_N * TINY_WG_MAX_C) red[threadIdx.x] = 0.f;
+    if (threadIdx.x < TINY_WG_MAX_N * TINY_WG_MAX_C) red[threadIdx.x] = 0.f;
     __syncthreads();
-    float acc[TINY_MAX_N][TINY_WG_MAX_C];
+    float acc[TINY_WG_MAX_N][TINY_WG_MAX_C];
 #pragma unroll
-    for (int n = 0; n < TINY_MAX_N; ++n)
+    for (int n = 0; n < TINY_WG_MAX_N; ++n)
 #pragma unroll
         for (int c = 0; c < TINY_WG_MAX_C; ++c) acc[n][c] = 0.f;
     const long M = (long)d.B * d.Hout * d.Wout;
@@ -97,12 +100,12 @@ __global__ void __launch_bounds__(256) conv_tiny_wgrad_kernel(cnb_wgrad_desc d) 
         int iy, ix;
         if (!conv_src_coord(oy, ky, d.stride, d.pad, d.dil, d.transposed, d.Hin, iy)) continue;
         if (!conv_src_coord(ox, kx, d.stride, d.pad, d.dil, d.transposed, d.Win, ix)) continue;
-        const T* sp = src + (((long)ob * d.Hin + iy) * d.Win + ix) * d.src_stride;
+        const T* sp = src + (((long)ob * d.Hin + iy) * d.Win + ix) * d.src_stride + cbase;
         float xs[TINY_WG_MAX_C];
 #pragma unroll
-        for (int c = 0; c < TINY_WG_MAX_C; ++c) xs[c] = c < d.src_c ? cnb_ld(sp + c) : 0.f;
+        for (int c = 0; c < TINY_WG_MAX_C; ++c) xs[c] = c < cn ? cnb_ld(sp + c) : 0.f;
 #pragma unroll
-        for (int n = 0; n < TINY_MAX_N; ++n) {
+        for (int n = 0; n < TINY_WG_MAX_N; ++n) {
             if (n < d.N) {
                 const float g = cnb_ld(dy + m * d.dy_stride + n);
 #pragma unroll
@@ -111,18 +114,18 @@ __global__ void __launch_bounds__(256) conv_tiny_wgrad_kernel(cnb_wgrad_desc d) 
         }
     }
 #pragma unroll
-    for (int n = 0; n < TINY_MAX_N; ++n)
+    for (int n = 0; n < TINY_WG_MAX_N; ++n)
 #pragma unroll
         for (int c = 0; c < TINY_WG_MAX_C; ++c) {
-            if (n < d.N && c < d.src_c) {  // uniform across the block
+            if (n < d.N && c < cn) {  // uniform across the block
                 const float v = cnb_warp_sum(acc[n][c]);
                 if ((threadIdx.x & 31) == 0) atomicAdd(&red[n * TINY_WG_MAX_C + c], v);
             }
         }
     __syncthreads();
-    if (threadIdx.x < TINY_MAX_N * TINY_WG_MAX_C) {
+    if (threadIdx.x < TINY_WG_MAX_N * TINY_WG_MAX_C) {
         const int n = threadIdx.x / TINY_WG_MAX_C, c = threadIdx.x % TINY_WG_MAX_C;
-        if (n < d.N && c < d.src_c) atomicAdd(d.dwp + ((long)tap * d.N + n) * d.Ctot + d.k_off + c, red[threadIdx.x]);
+        if (n < d.N && c < cn) atomicAdd(d.dwp + ((long)tap * d.N + n) * d.Ctot + d.k_off + cbase + c, red[threadIdx.x]);
     }
 }
 

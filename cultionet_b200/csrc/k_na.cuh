@@ -236,8 +236,9 @@ __device__ __forceinline__ void na_stage_region(T* sm, const T* a_base, const T*
         const int rx = r % g.RW, ry = r / g.RW;
         const long pix = img_pix0 + (long)(ry0 + ry) * g.W + (rx0 + rx);
         const T* src = (part < parts ? a_base + part * V : b_base + (part - parts) * V) + pix * pix_stride;
-        *reinterpret_cast<uint4*>(sm + (long)r * 2 * g.hd + part * V) = *reinterpret_cast<const uint4*>(src);
+        cnb_cp_async16(sm + (long)r * 2 * g.hd + part * V, src);
     }
+    cnb_cp_async_wait_all();
 }
 
 // k / v row segment of neighbour (ny, nx): from the staged region, or straight from global memory should a neighbour ever fall
@@ -442,7 +443,7 @@ __global__ void __launch_bounds__(NA_TILE_THREADS) na2d_bwd_dkv_tile_kernel(cons
             const int rx = r % g.RW, ry = r / g.RW;
             const long pix = img_pix0 + (long)(ry0 + ry) * g.W + (rx0 + rx);
             const T* src = part < parts ? qkv + pix * 3 * C + head * g.hd + part * V : dout + pix * C + head * g.hd + (part - parts) * V;
-            *reinterpret_cast<uint4*>(sm + (long)r * 2 * g.hd + part * V) = *reinterpret_cast<const uint4*>(src);
+            cnb_cp_async16(sm + (long)r * 2 * g.hd + part * V, src);
         }
     }
     float* sm_l = reinterpret_cast<float*>(sm + (long)g.RH * g.RW * 2 * g.hd);  // lse and D of the region
@@ -453,6 +454,7 @@ __global__ void __launch_bounds__(NA_TILE_THREADS) na2d_bwd_dkv_tile_kernel(cons
         sm_l[r] = lse[pix * g.heads + head];
         sm_d[r] = dvec[pix * g.heads + head];
     }
+    cnb_cp_async_wait_all();
     __syncthreads();
 
     const int items = NA_TH * NA_TW * LPH;

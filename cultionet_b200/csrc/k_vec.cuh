@@ -28,15 +28,22 @@ __global__ void __launch_bounds__(256) bn_stats_vec_kernel(const T* __restrict__
         float s[V], q[V];
 #pragma unroll
         for (int j = 0; j < V; ++j) s[j] = 0.f, q[j] = 0.f;
-#pragma unroll 4
-        for (long i = gid; i < total_v; i += stride_v) {
-            float v[V];
-            cnb_ldv(x + i * V, v);
+        // U independent 16-byte loads are issued before any of them is consumed: bytes in flight, not occupancy, feed HBM
+        constexpr int U = 4;
+        for (long i = gid; i < total_v; i += U * stride_v) {
+            float v[U][V];
 #pragma unroll
-            for (int j = 0; j < V; ++j) {
-                s[j] += v[j];
-                q[j] = fmaf(v[j], v[j], q[j]);
-            }
+            for (int u = 0; u < U; ++u)
+                if (i + u * stride_v < total_v) cnb_ldv(x + (i + u * stride_v) * V, v[u]);
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (i + u * stride_v < total_v) {
+#pragma unroll
+                    for (int j = 0; j < V; ++j) {
+                        s[j] += v[u][j];
+                        q[j] = fmaf(v[u][j], v[u][j], q[j]);
+                    }
+                }
         }
 #pragma unroll
         for (int j = 0; j < V; ++j) {
@@ -59,27 +66,31 @@ __global__ void __launch_bounds__(256) bn_act_fwd_vec_kernel(const T* __restrict
     float sc[V], sf[V];
 #pragma unroll
     for (int j = 0; j < V; ++j) sc[j] = scale[c0 + j], sf[j] = shift[c0 + j];
-#pragma unroll 2
-    for (long i = gid; i < total_v; i += stride_v) {
-        float v[V];
-        cnb_ldv(x + i * V, v);
+    constexpr int U = 4;
+    for (long i = gid; i < total_v; i += U * stride_v) {
+        float v[U][V], r[U][V];
 #pragma unroll
-        for (int j = 0; j < V; ++j) {
-            float z = fmaf(v[j], sc[j], sf[j]);
-            v[j] = act ? cnb_silu(z) : z;
-        }
-        if (residual) {
-            float r[V];
-            cnb_ldv(residual + i * V, r);
+        for (int u = 0; u < U; ++u)
+            if (i + u * stride_v < total_v) {
+                cnb_ldv(x + (i + u * stride_v) * V, v[u]);
+                if (residual) cnb_ldv(residual + (i + u * stride_v) * V, r[u]);
+            }
 #pragma unroll
-            for (int j = 0; j < V; ++j) v[j] += r[j];
-        }
-        cnb_stv(y + i * V, v);
+        for (int u = 0; u < U; ++u)
+            if (i + u * stride_v < total_v) {
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    float z = fmaf(v[u][j], sc[j], sf[j]);
+                    z = act ? cnb_silu(z) : z;
+                    v[u][j] = residual ? z + r[u][j] : z;
+                }
+                cnb_stv(y + (i + u * stride_v) * V, v[u]);
+            }
     }
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) bn_act_bwd_reduce_vec_kernel(const T* __restrict__ x, const T* __restrict__ dy,
+__global__ void __launch_bounds__(256, 3) bn_act_bwd_reduce_vec_kernel(const T* __restrict__ x, const T* __restrict__ dy,
                                                                    const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                    long total_v, int CV, long stride_v, int C, int act,
@@ -92,27 +103,40 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_vec_kernel(const T* __r
     const long gid = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid < stride_v) {
         const int c0 = (int)(gid % CV) * V;
-        float mu[V], rs[V], g[V], b[V], s[V], sx[V];
+        // z = x*A + Bc with A = gamma*rstd, Bc = beta - mean*A (the forward's scale/shift); xhat = (x - mean)*rstd is applied to the
+        // sum at the end, so only three per-channel constants stay in registers
+        float mu[V], A[V], Bc[V], s[V], sx[V];
 #pragma unroll
         for (int j = 0; j < V; ++j) {
-            mu[j] = mean[c0 + j], rs[j] = rstd[c0 + j];
-            g[j] = gamma ? gamma[c0 + j] : 1.f, b[j] = beta ? beta[c0 + j] : 0.f;
+            const float gj = gamma ? gamma[c0 + j] : 1.f, bj = beta ? beta[c0 + j] : 0.f;
+            mu[j] = mean[c0 + j];
+            A[j] = gj * rstd[c0 + j];
+            Bc[j] = bj - mu[j] * A[j];
             s[j] = 0.f, sx[j] = 0.f;
         }
-#pragma unroll 2
-        for (long i = gid; i < total_v; i += stride_v) {
-            float xv[V], dv[V];
-            cnb_ldv(x + i * V, xv);
-            cnb_ldv(dy + i * V, dv);
+        constexpr int U = 2;
+        for (long i = gid; i < total_v; i += U * stride_v) {
+            float xv[U][V], dv[U][V];
 #pragma unroll
-            for (int j = 0; j < V; ++j) {
-                const float xh = (xv[j] - mu[j]) * rs[j];
-                float dz = dv[j];
-                if (act) dz *= cnb_silu_grad(fmaf(xh, g[j], b[j]));
-                s[j] += dz;
-                sx[j] = fmaf(dz, xh, sx[j]);
-            }
+            for (int u = 0; u < U; ++u)
+                if (i + u * stride_v < total_v) {
+                    cnb_ldv(x + (i + u * stride_v) * V, xv[u]);
+                    cnb_ldv(dy + (i + u * stride_v) * V, dv[u]);
+                }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (i + u * stride_v < total_v) {
+#pragma unroll
+                    for (int j = 0; j < V; ++j) {
+                        float dz = dv[u][j];
+                        if (act) dz *= cnb_silu_grad(fmaf(xv[u][j], A[j], Bc[j]));
+                        s[j] += dz;
+                        sx[j] = fmaf(dz, xv[u][j] - mu[j], sx[j]);
+                    }
+                }
         }
+#pragma unroll
+        for (int j = 0; j < V; ++j) sx[j] *= rstd[c0 + j];
 #pragma unroll
         for (int j = 0; j < V; ++j) {
             atomicAdd(&sh_dyn[c0 + j], s[j]);
@@ -124,7 +148,7 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_vec_kernel(const T* __r
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) bn_act_bwd_apply_vec_kernel(const T* __restrict__ x, const T* __restrict__ dy,
+__global__ void __launch_bounds__(256, 3) bn_act_bwd_apply_vec_kernel(const T* __restrict__ x, const T* __restrict__ dy,
                                                                   const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                   const float* __restrict__ dsums, float inv_count, T* __restrict__ dx,
@@ -133,27 +157,37 @@ __global__ void __launch_bounds__(256) bn_act_bwd_apply_vec_kernel(const T* __re
     const long gid = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= stride_v) return;
     const int c0 = (int)(gid % CV) * V;
-    float mu[V], rs[V], g[V], b[V], k0[V], k1[V];
+    // dx = A*dz - x*K1 + Q with A = gamma*rstd, K1 = A*rstd*mean(dz*xhat), Q = mean*K1 - A*mean(dz); z = x*A + Bc
+    float A[V], Bc[V], K1[V], Q[V];
 #pragma unroll
     for (int j = 0; j < V; ++j) {
-        mu[j] = mean[c0 + j], rs[j] = rstd[c0 + j];
-        g[j] = gamma ? gamma[c0 + j] : 1.f, b[j] = beta ? beta[c0 + j] : 0.f;
-        k0[j] = train_stats ? dsums[c0 + j] * inv_count : 0.f;
-        k1[j] = train_stats ? dsums[C + c0 + j] * inv_count : 0.f;
+        const float gj = gamma ? gamma[c0 + j] : 1.f, bj = beta ? beta[c0 + j] : 0.f;
+        const float m = mean[c0 + j], r = rstd[c0 + j];
+        A[j] = gj * r;
+        Bc[j] = bj - m * A[j];
+        K1[j] = train_stats ? A[j] * r * dsums[C + c0 + j] * inv_count : 0.f;
+        Q[j] = train_stats ? m * K1[j] - A[j] * dsums[c0 + j] * inv_count : 0.f;
     }
-#pragma unroll 2
-    for (long i = gid; i < total_v; i += stride_v) {
-        float xv[V], dv[V];
-        cnb_ldv(x + i * V, xv);
-        cnb_ldv(dy + i * V, dv);
+    constexpr int U = 2;
+    for (long i = gid; i < total_v; i += U * stride_v) {
+        float xv[U][V], dv[U][V];
 #pragma unroll
-        for (int j = 0; j < V; ++j) {
-            const float xh = (xv[j] - mu[j]) * rs[j];
-            float dz = dv[j];
-            if (act) dz *= cnb_silu_grad(fmaf(xh, g[j], b[j]));
-            xv[j] = g[j] * rs[j] * (dz - k0[j] - xh * k1[j]);
-        }
-        cnb_stv(dx + i * V, xv);
+        for (int u = 0; u < U; ++u)
+            if (i + u * stride_v < total_v) {
+                cnb_ldv(x + (i + u * stride_v) * V, xv[u]);
+                cnb_ldv(dy + (i + u * stride_v) * V, dv[u]);
+            }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (i + u * stride_v < total_v) {
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    float dz = dv[u][j];
+                    if (act) dz *= cnb_silu_grad(fmaf(xv[u][j], A[j], Bc[j]));
+                    xv[u][j] = fmaf(A[j], dz, fmaf(-xv[u][j], K1[j], Q[j]));
+                }
+                cnb_stv(dx + (i + u * stride_v) * V, xv[u]);
+            }
     }
 }
 
@@ -197,12 +231,18 @@ __global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ d
         float s[V];
 #pragma unroll
         for (int j = 0; j < V; ++j) s[j] = 0.f;
-#pragma unroll 4
-        for (long i = gid; i < total_v; i += stride_v) {
-            float v[V];
-            cnb_ldv(dy + i * V, v);
+        constexpr int U = 4;
+        for (long i = gid; i < total_v; i += U * stride_v) {
+            float v[U][V];
 #pragma unroll
-            for (int j = 0; j < V; ++j) s[j] += v[j];
+            for (int u = 0; u < U; ++u)
+                if (i + u * stride_v < total_v) cnb_ldv(dy + (i + u * stride_v) * V, v[u]);
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (i + u * stride_v < total_v) {
+#pragma unroll
+                    for (int j = 0; j < V; ++j) s[j] += v[u][j];
+                }
         }
 #pragma unroll
         for (int j = 0; j < V; ++j) atomicAdd(&sh_dyn[c0 + j], s[j]);
@@ -398,16 +438,41 @@ __global__ void __launch_bounds__(256) resize_bilinear_bwd_vec_kernel(const T* _
         float acc[V];
 #pragma unroll
         for (int j = 0; j < V; ++j) acc[j] = 0.f;
-        for (int oy = ylo; oy <= yhi; ++oy) {
-            const float wy = bilinear_weight(oy, iy, rh, Hin);
-            if (wy == 0.f) continue;
-            for (int ox = xlo; ox <= xhi; ++ox) {
-                const float w = wy * bilinear_weight(ox, ix, rw, Win);
-                if (w != 0.f) {
-                    float v[V];
-                    cnb_ldv(base + ((long)oy * Wout + ox) * C, v);
+        // per-axis weights once per thread (the candidate ranges are a few pixels wide for the 2H-1 -> 2H fix-ups of this network)
+        constexpr int MAXC = 6;
+        if (yhi - ylo < MAXC && xhi - xlo < MAXC) {
+            float wy[MAXC], wx[MAXC];
 #pragma unroll
-                    for (int j = 0; j < V; ++j) acc[j] = fmaf(w, v[j], acc[j]);
+            for (int a = 0; a < MAXC; ++a) {
+                wy[a] = (ylo + a <= yhi) ? bilinear_weight(ylo + a, iy, rh, Hin) : 0.f;
+                wx[a] = (xlo + a <= xhi) ? bilinear_weight(xlo + a, ix, rw, Win) : 0.f;
+            }
+#pragma unroll
+            for (int a = 0; a < MAXC; ++a) {
+                if (wy[a] == 0.f) continue;
+#pragma unroll
+                for (int bb = 0; bb < MAXC; ++bb) {
+                    const float w = wy[a] * wx[bb];
+                    if (w != 0.f) {
+                        float v[V];
+                        cnb_ldv(base + ((long)(ylo + a) * Wout + (xlo + bb)) * C, v);
+#pragma unroll
+                        for (int j = 0; j < V; ++j) acc[j] = fmaf(w, v[j], acc[j]);
+                    }
+                }
+            }
+        } else {
+            for (int oy = ylo; oy <= yhi; ++oy) {
+                const float wy = bilinear_weight(oy, iy, rh, Hin);
+                if (wy == 0.f) continue;
+                for (int ox = xlo; ox <= xhi; ++ox) {
+                    const float w = wy * bilinear_weight(ox, ix, rw, Win);
+                    if (w != 0.f) {
+                        float v[V];
+                        cnb_ldv(base + ((long)oy * Wout + ox) * C, v);
+#pragma unroll
+                        for (int j = 0; j < V; ++j) acc[j] = fmaf(w, v[j], acc[j]);
+                    }
                 }
             }
         }

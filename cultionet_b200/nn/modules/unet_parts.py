@@ -114,10 +114,34 @@ class TowerUNetFinal(nn.Module):
         self.fuse_conv = ConvBlock2d(3, 3, kernel_size=3, padding=1, add_activation=True, activation_type=activation_type)
 
     def forward(self, x: torch.Tensor, size=None, suffix: str = "") -> torch.Tensor:
+        """The three streams read the same ``[B,H,W,C]`` tensor, so they run as ONE convolution with the three filter banks
+        stacked along the output axis (C -> 9), one BatchNorm+SiLU over the 9 channels (per-channel statistics are independent,
+        so this equals the three separate BatchNorm2d(3) of the reference) and one block-diagonal 9 -> 3 convolution for the
+        three 3 -> 1 stream outputs.  Stacking the (tiny) parameters is plumbing; the arithmetic per channel is unchanged."""
         if size is not None:
             x = self.up_conv(x, size=size)
-        streams = [self.dist_conv(x), self.edge_conv(x), self.crop_conv(x)]
-        return self.fuse_conv(streams)
+        streams = (self.dist_conv, self.edge_conv, self.crop_conv)
+        blocks = [s.conv[0] for s in streams]
+        w1 = torch.cat([b.seq[0].weight for b in blocks], dim=0)  # [9, C, 3, 3]
+        h = F.conv2d([x], w1, None, ksize=3, stride=1, pad=1)
+        bns = [b.seq[1] for b in blocks]
+        training = bns[0].training
+        rm = torch.cat([bn.running_mean for bn in bns])
+        rv = torch.cat([bn.running_var for bn in bns])
+        h = F.batchnorm_act(h, torch.cat([bn.weight for bn in bns]), torch.cat([bn.bias for bn in bns]), rm, rv, training,
+                            momentum=bns[0].momentum if bns[0].momentum is not None else 0.1, eps=bns[0].eps, act=True)
+        if training:
+            with torch.no_grad():
+                for i, bn in enumerate(bns):
+                    bn.running_mean.copy_(rm[3 * i:3 * i + 3])
+                    bn.running_var.copy_(rv[3 * i:3 * i + 3])
+                    if bn.num_batches_tracked is not None:
+                        bn.num_batches_tracked.add_(1)
+        # 3 x (3 -> 1) as one block-diagonal 9 -> 3 convolution
+        w2 = torch.cat([torch.nn.functional.pad(s.conv[1].weight, (0, 0, 0, 0, 3 * i, 6 - 3 * i)) for i, s in enumerate(streams)], dim=0)
+        b2 = torch.cat([s.conv[1].bias for s in streams])
+        z = F.conv2d([h], w2, b2, ksize=3, stride=1, pad=1)
+        return self.fuse_conv(z)
 
 
 class UNetUpBlock(nn.Module):

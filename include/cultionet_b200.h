@@ -72,7 +72,7 @@ int cnb_conv2d_fwd_generic(const cnb_conv_desc* d, int dtype, void* stream);
  * CNB_ERR_UNSUPPORTED otherwise */
 int cnb_conv2d_fwd_tc(const cnb_conv_desc* d, int dtype, void* stream);
 int cnb_conv2d_tc_eligible(const cnb_conv_desc* d, int dtype);
-/* one thread per output pixel, filter bank in shared memory: N <= 8 output and <= 16 input channels (the Psi-Net heads' 3->1 and
+/* one thread per output pixel, filter bank in shared memory: N <= 16 output and <= 16 input channels (the Psi-Net heads' 3->1 and
  * 3->3 convolutions, nn/modules/unet_parts.py:215-220, :262-270); cnb_conv2d_fwd picks it first when it applies */
 int cnb_conv2d_fwd_tiny(const cnb_conv_desc* d, int dtype, void* stream);
 
@@ -93,7 +93,7 @@ int cnb_conv2d_wgrad(const cnb_wgrad_desc* d, int dtype, void* stream);
 int cnb_conv2d_wgrad_generic(const cnb_wgrad_desc* d, int dtype, void* stream);
 int cnb_conv2d_wgrad_tc(const cnb_wgrad_desc* d, int dtype, void* stream);
 int cnb_conv2d_wgrad_tc_eligible(const cnb_wgrad_desc* d, int dtype);
-/* N <= 8 and a source slice of <= 4 channels: per-thread partial sums, one atomic per CTA */
+/* N <= 8 and a source slice of <= 16 channels: per-thread partial sums, one atomic per CTA */
 int cnb_conv2d_wgrad_tiny(const cnb_wgrad_desc* d, int dtype, void* stream);
 /* dst[p][c] = src[p][c] for c < C, 0 for C <= c < dst_stride: gives a skinny tensor (e.g. the 3-channel gradient of a Psi-Net
  * stream) the 16-byte pixel pitch the TMA-fed kernels need */
