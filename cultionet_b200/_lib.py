@@ -44,6 +44,7 @@ class ConvDesc(C.Structure):
         ("bias", C.c_void_p),
         ("out", C.c_void_p),
         ("out_stride", C.c_int32),
+        ("stats", C.c_void_p),
     ]
 
 

@@ -81,6 +81,7 @@ static int check_conv_desc(const cnb_conv_desc* d) {
 int cnb_conv2d_fwd_generic(const cnb_conv_desc* d, int dtype, void* stream) {
     int rc = check_conv_desc(d);
     if (rc) return rc;
+    CNB_REQUIRE(d->stats == nullptr, "conv2d_fwd_generic: fused BatchNorm statistics exist only in the tcgen05 kernel");
     const long M = (long)d->B * d->Hout * d->Wout;
     dim3 grid(cnb_div_up(M, CG_BM), cnb_div_up(d->N, CG_BN));
     CNB_DISPATCH_DTYPE(dtype, { CNB_LAUNCH((conv_fwd_generic_kernel<T>), grid, dim3(256), 0, (cudaStream_t)stream, *d); });
@@ -120,6 +121,7 @@ int cnb_conv2d_fwd_tiny(const cnb_conv_desc* d, int dtype, void* stream) {
     int rc = check_conv_desc(d);
     if (rc) return rc;
     if (!conv_tiny_eligible(d)) CNB_FAIL(CNB_ERR_UNSUPPORTED, "conv2d_fwd_tiny: needs N <= %d and at most %d input channels", TINY_MAX_N, TINY_MAX_C);
+    CNB_REQUIRE(d->stats == nullptr, "conv2d_fwd_tiny: fused BatchNorm statistics exist only in the tcgen05 kernel");
     int ctot = 0;
     for (int s = 0; s < d->nsrc; ++s) ctot += d->src_c[s];
     const long M = (long)d->B * d->Hout * d->Wout;
@@ -129,6 +131,7 @@ int cnb_conv2d_fwd_tiny(const cnb_conv_desc* d, int dtype, void* stream) {
 }
 
 int cnb_conv2d_fwd(const cnb_conv_desc* d, int dtype, void* stream) {
+    if (d && d->stats) return cnb_conv2d_fwd_tc(d, dtype, stream);
     if (check_conv_desc(d) == CNB_OK && conv_tiny_eligible(d)) return cnb_conv2d_fwd_tiny(d, dtype, stream);
     if (cnb_conv2d_tc_eligible(d, dtype)) return cnb_conv2d_fwd_tc(d, dtype, stream);
     return cnb_conv2d_fwd_generic(d, dtype, stream);
@@ -574,7 +577,7 @@ int cnb_resize_bilinear_fwd(const void* x, void* y, int B, int Hin, int Win, int
     const long total = (long)B * Hout * Wout * C;
     if (C % vec_width(dtype) == 0 && cnb_aligned16(x) && cnb_aligned16(y)) {
         CNB_DISPATCH_DTYPE(dtype, {
-            CNB_LAUNCH((resize_bilinear_fwd_vec_kernel<T>), dim3(stream_grid(total / vec_width(dtype))), dim3(256), 0, (cudaStream_t)stream,
+            CNB_LAUNCH((resize_bilinear_fwd_vec_kernel<T>), dim3(B * Hout), dim3(256), 0, (cudaStream_t)stream,
                        (const T*)x, (T*)y, B, Hin, Win, Hout, Wout, C, align_corners_scale(Hin, Hout), align_corners_scale(Win, Wout));
         });
         CNB_CHECK_LAUNCH("resize_bilinear_fwd_vec_kernel");
@@ -593,7 +596,7 @@ int cnb_resize_bilinear_bwd(const void* dy, void* dx, int B, int Hin, int Win, i
     const long total = (long)B * Hin * Win * C;
     if (C % vec_width(dtype) == 0 && cnb_aligned16(dy) && cnb_aligned16(dx)) {
         CNB_DISPATCH_DTYPE(dtype, {
-            CNB_LAUNCH((resize_bilinear_bwd_vec_kernel<T>), dim3(stream_grid(total / vec_width(dtype))), dim3(256), 0, (cudaStream_t)stream,
+            CNB_LAUNCH((resize_bilinear_bwd_vec_kernel<T>), dim3(B * Hin), dim3(256), 0, (cudaStream_t)stream,
                        (const T*)dy, (T*)dx, B, Hin, Win, Hout, Wout, C, align_corners_scale(Hin, Hout), align_corners_scale(Win, Wout));
         });
         CNB_CHECK_LAUNCH("resize_bilinear_bwd_vec_kernel");

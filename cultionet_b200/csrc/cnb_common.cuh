@@ -140,6 +140,30 @@ __device__ __forceinline__ float cnb_exp(float x) {
 #endif
 }
 __device__ __forceinline__ float cnb_sigmoid(float x) { return 1.0f / (1.0f + cnb_exp(-x)); }
+// One MUFU op instead of two (ex2 + rcp): sigmoid(x) = 0.5 + 0.5*tanh(x/2) with tanh.approx (abs. error < 3e-4, far inside a bf16 ulp).
+// Only the bf16 (throughput-mode) kernels use it; the fp32 parity path keeps the exact form.
+__device__ __forceinline__ float cnb_sigmoid_fast(float x) {
+#ifdef CNB_EMU
+    return 1.0f / (1.0f + expf(-x));
+#else
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+    return fmaf(0.5f, t, 0.5f);
+#endif
+}
+template <typename T>
+__device__ __forceinline__ float cnb_sigmoid_t(float x) {
+    return sizeof(T) == 2 ? cnb_sigmoid_fast(x) : cnb_sigmoid(x);
+}
+template <typename T>
+__device__ __forceinline__ float cnb_silu_t(float x) {
+    return x * cnb_sigmoid_t<T>(x);
+}
+template <typename T>
+__device__ __forceinline__ float cnb_silu_grad_t(float x) {
+    const float s = cnb_sigmoid_t<T>(x);
+    return s * (1.0f + x * (1.0f - s));
+}
 __device__ __forceinline__ float cnb_silu(float x) { return x * cnb_sigmoid(x); }
 // d/dx [x * sigmoid(x)]
 __device__ __forceinline__ float cnb_silu_grad(float x) {

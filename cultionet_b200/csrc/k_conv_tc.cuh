@@ -54,6 +54,7 @@ struct ConvTcParams {
     bf16_t* out;
     int out_stride, vec_ok;
     const float* bias;
+    float* stats;  // optional [2*N]: per-output-channel sum and sum of squares of the STORED (bf16-rounded) outputs, for BatchNorm
 };
 
 struct TileCoord {
@@ -165,6 +166,25 @@ struct Cfg {
     static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // power of two for BN in {32,64,128,256}
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
+constexpr int STATS_MAX_N = 1024;  // channels whose BatchNorm partial sums fit behind the barriers (8 KB)
+
+// Column sums across the 32 lanes of a warp for 32 columns at once: lane L ends up with sum over lanes of vals[L].  Recursive
+// halving: at each step a lane keeps one half of its columns and trades the other half with its partner (31 shuffles instead of
+// 32 x 5 for one butterfly per column).
+__device__ __forceinline__ float warp_transpose_sum32(float (&vals)[32]) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int step = 16; step >= 1; step >>= 1) {
+        const bool upper = (lane & step) != 0;
+#pragma unroll
+        for (int j = 0; j < step; ++j) {
+            const float send = upper ? vals[j] : vals[j + step];
+            const float keep = upper ? vals[j + step] : vals[j];
+            vals[j] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+        }
+    }
+    return vals[0];
+}
 
 __device__ __forceinline__ void decode_tile(const ConvTcParams& p, int tile, int bn, TileCoord& t) {
     const int nt = tile / p.m_tiles;
@@ -199,6 +219,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + C::STAGES * C::STAGE_BYTES + 8 * (2 * C::STAGES + 4));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* sm_stats = reinterpret_cast<float*>(base_ptr + C::STAGES * C::STAGE_BYTES + 256);  // [2*N] when p.stats
+    if (p.stats)
+        for (int i = threadIdx.x; i < 2 * p.N; i += NUM_THREADS) sm_stats[i] = 0.f;
 
     if (warp == 0 && lane == 0) {
         const int nmaps = p.per_tap_map ? p.ph_tap0[p.nphases] : p.nsrc;
@@ -317,30 +340,36 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 if (col0 >= p.N) break;
                 uint32_t v[32];
                 tmem_ld32(taddr + (uint32_t)(c * 32), v);
-                if (!valid) continue;
-                if (p.vec_ok && col0 + 32 <= p.N) {
-                    uint32_t packed[16];
+                if (!valid && !p.stats) continue;
+                float f[32];  // what gets stored: accumulator (+bias) rounded to bf16; zero for rows outside the image
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        float f0 = has_taps ? __uint_as_float(v[2 * j]) : 0.f, f1 = has_taps ? __uint_as_float(v[2 * j + 1]) : 0.f;
-                        if (p.bias) {
-                            f0 += __ldg(p.bias + col0 + 2 * j);
-                            f1 += __ldg(p.bias + col0 + 2 * j + 1);
-                        }
-                        __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
-                        packed[j] = *reinterpret_cast<uint32_t*>(&h);
+                for (int j = 0; j < 32; ++j) {
+                    float t = has_taps ? __uint_as_float(v[j]) : 0.f;
+                    if (p.bias && col0 + j < p.N) t += __ldg(p.bias + col0 + j);
+                    f[j] = valid ? __bfloat162float(__float2bfloat16(t)) : 0.f;
+                }
+                if (valid) {
+                    if (p.vec_ok && col0 + 32 <= p.N) {
+                        uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            dst[j] = make_uint4(cnb_pack_bf16x2(f[8 * j], f[8 * j + 1]), cnb_pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                                                cnb_pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), cnb_pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (col0 + j < p.N) orow[c * 32 + j] = __float2bfloat16(f[j]);
                     }
-                    uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
+                }
+                if (p.stats) {
+                    float q[32];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        if (col0 + j < p.N) {
-                            float f = has_taps ? __uint_as_float(v[j]) : 0.f;
-                            if (p.bias) f += __ldg(p.bias + col0 + j);
-                            orow[c * 32 + j] = __float2bfloat16(f);
-                        }
+                    for (int j = 0; j < 32; ++j) q[j] = f[j] * f[j];
+                    const float s1 = warp_transpose_sum32(f);
+                    const float s2 = warp_transpose_sum32(q);
+                    if (col0 + lane < p.N) {
+                        atomicAdd(&sm_stats[col0 + lane], s1);
+                        atomicAdd(&sm_stats[p.N + col0 + lane], s2);
                     }
                 }
             }
@@ -356,6 +385,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         tc_fence_after();
         tmem_dealloc(tmem_base, C::TMEM_COLS);
     }
+    if (p.stats)
+        for (int i = threadIdx.x; i < 2 * p.N; i += NUM_THREADS) {
+            const float t = sm_stats[i];
+            if (t != 0.f) atomicAdd(p.stats + i, t);
+        }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -462,12 +496,15 @@ template <int BN>
 inline int launch_bn(const ConvTcParams& p, cudaStream_t stream) {
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES) != cudaSuccess) return 1;
+        if (cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 Cfg<BN>::SMEM_BYTES + 2 * STATS_MAX_N * (int)sizeof(float)) != cudaSuccess)
+            return 1;
         configured = true;
     }
     const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+    const int smem = Cfg<BN>::SMEM_BYTES + (p.stats ? 2 * p.N * (int)sizeof(float) : 0);
     cnb_count_launch();
-    conv_tc_kernel<BN><<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(p);
+    conv_tc_kernel<BN><<<grid, NUM_THREADS, smem, stream>>>(p);
     return 0;
 }
 
@@ -594,6 +631,8 @@ inline int conv_tc_launch(const cnb_conv_desc* d, cudaStream_t stream) {
     p.out_stride = d->out_stride;
     p.vec_ok = (d->out_stride % 8 == 0 && reinterpret_cast<uintptr_t>(d->out) % 16 == 0) ? 1 : 0;
     p.bias = d->bias;
+    p.stats = d->N <= STATS_MAX_N ? d->stats : nullptr;
+    if (d->stats && !p.stats) return 3;
     p.num_tiles = cnb_div_up(d->N, BN) * p.m_tiles;
     switch (BN) {
         case 256: return launch_bn<256>(p, stream);

@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256) bn_act_fwd_vec_kernel(const T* __restrict
     float sc[V], sf[V];
 #pragma unroll
     for (int j = 0; j < V; ++j) sc[j] = scale[c0 + j], sf[j] = shift[c0 + j];
-    constexpr int U = 4;
+    constexpr int U = 2;
     for (long i = gid; i < total_v; i += U * stride_v) {
         float v[U][V], r[U][V];
 #pragma unroll
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(256) bn_act_fwd_vec_kernel(const T* __restrict
 #pragma unroll
                 for (int j = 0; j < V; ++j) {
                     float z = fmaf(v[u][j], sc[j], sf[j]);
-                    z = act ? cnb_silu(z) : z;
+                    z = act ? cnb_silu_t<T>(z) : z;
                     v[u][j] = residual ? z + r[u][j] : z;
                 }
                 cnb_stv(y + (i + u * stride_v) * V, v[u]);
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(256, 3) bn_act_bwd_reduce_vec_kernel(const T* 
 #pragma unroll
                     for (int j = 0; j < V; ++j) {
                         float dz = dv[u][j];
-                        if (act) dz *= cnb_silu_grad(fmaf(xv[u][j], A[j], Bc[j]));
+                        if (act) dz *= cnb_silu_grad_t<T>(fmaf(xv[u][j], A[j], Bc[j]));
                         s[j] += dz;
                         sx[j] = fmaf(dz, xv[u][j] - mu[j], sx[j]);
                     }
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(256, 3) bn_act_bwd_apply_vec_kernel(const T* _
 #pragma unroll
                 for (int j = 0; j < V; ++j) {
                     float dz = dv[u][j];
-                    if (act) dz *= cnb_silu_grad(fmaf(xv[u][j], A[j], Bc[j]));
+                    if (act) dz *= cnb_silu_grad_t<T>(fmaf(xv[u][j], A[j], Bc[j]));
                     xv[u][j] = fmaf(A[j], dz, fmaf(-xv[u][j], K1[j], Q[j]));
                 }
                 cnb_stv(dx + (i + u * stride_v) * V, xv[u]);
@@ -264,6 +264,16 @@ __global__ void __launch_bounds__(256) layernorm_fwd_vec_kernel(const T* __restr
     const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
     const float invC = 1.0f / (float)C;
+    float gm[K][V], bt[K][V];  // this lane's affine parameters (ncu: re-reading them per pixel kept L1 95 % busy)
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int c = (lane + 32 * k) * V;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            gm[k][j] = c < C ? gamma[c + j] : 0.f;
+            bt[k][j] = c < C ? beta[c + j] : 0.f;
+        }
+    }
     for (long p = warp; p < P; p += nwarps) {
         float v[K][V];
         float s = 0.f;
@@ -295,7 +305,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_vec_kernel(const T* __restr
             const int c = (lane + 32 * k) * V;
             if (c < C) {
 #pragma unroll
-                for (int j = 0; j < V; ++j) v[k][j] = fmaf((v[k][j] - mean) * rstd, gamma[c + j], beta[c + j]);
+                for (int j = 0; j < V; ++j) v[k][j] = fmaf((v[k][j] - mean) * rstd, gm[k][j], bt[k][j]);
                 cnb_stv(y + p * C + c, v[k]);
             }
         }
@@ -386,34 +396,38 @@ __global__ void __launch_bounds__(256) layernorm_bwd_vec_kernel(const T* __restr
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// bilinear align_corners=True resize: one thread per (pixel, channel vector)
+// bilinear align_corners=True resize.  One CTA per output (forward) / input (backward) image row: the row's vertical taps and
+// weights are computed once per CTA, threads walk (x, channel vector) with 32-bit index math only (ncu: the flat-index version
+// spent 72 % of its issue slots on 64-bit div/mod and was instruction-bound at 1.3-3.1 TB/s).
 // ---------------------------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) resize_bilinear_fwd_vec_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int Hin, int Win,
                                                                      int Hout, int Wout, int C, float rh, float rw) {
     constexpr int V = cnb_vec<T>::N;
     const int CV = C / V;
-    const long total = (long)B * Hout * Wout * CV;
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % CV) * V;
-        long t = i / CV;
-        const int ox = (int)(t % Wout);
-        t /= Wout;
-        const int oy = (int)(t % Hout);
-        const long b = t / Hout;
-        int y0, y1, x0, x1;
-        float ly0, ly1, lx0, lx1;
-        bilinear_src(oy, rh, Hin, y0, y1, ly0, ly1);
+    const int oy = blockIdx.x % Hout;
+    const int b = blockIdx.x / Hout;
+    int y0, y1;
+    float ly0, ly1;
+    bilinear_src(oy, rh, Hin, y0, y1, ly0, ly1);
+    const T* row0 = x + ((long)b * Hin + y0) * Win * C;
+    const T* row1 = x + ((long)b * Hin + y1) * Win * C;
+    T* orow = y + ((long)b * Hout + oy) * Wout * C;
+    const int n = Wout * CV;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int ox = i / CV;
+        const int c = (i - ox * CV) * V;
+        int x0, x1;
+        float lx0, lx1;
         bilinear_src(ox, rw, Win, x0, x1, lx0, lx1);
-        const T* base = x + b * Hin * Win * C + c;
         float v00[V], v01[V], v10[V], v11[V];
-        cnb_ldv(base + ((long)y0 * Win + x0) * C, v00);
-        cnb_ldv(base + ((long)y0 * Win + x1) * C, v01);
-        cnb_ldv(base + ((long)y1 * Win + x0) * C, v10);
-        cnb_ldv(base + ((long)y1 * Win + x1) * C, v11);
+        cnb_ldv(row0 + x0 * C + c, v00);
+        cnb_ldv(row0 + x1 * C + c, v01);
+        cnb_ldv(row1 + x0 * C + c, v10);
+        cnb_ldv(row1 + x1 * C + c, v11);
 #pragma unroll
         for (int j = 0; j < V; ++j) v00[j] = ly0 * (lx0 * v00[j] + lx1 * v01[j]) + ly1 * (lx0 * v10[j] + lx1 * v11[j]);
-        cnb_stv(y + i * V, v00);
+        cnb_stv(orow + ox * C + c, v00);
     }
 }
 
@@ -422,31 +436,31 @@ template <typename T>
 __global__ void __launch_bounds__(256) resize_bilinear_bwd_vec_kernel(const T* __restrict__ dy, T* __restrict__ dx, int B, int Hin,
                                                                      int Win, int Hout, int Wout, int C, float rh, float rw) {
     constexpr int V = cnb_vec<T>::N;
+    constexpr int MAXC = 6;  // candidate output rows / columns handled with per-axis weight tables
     const int CV = C / V;
-    const long total = (long)B * Hin * Win * CV;
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % CV) * V;
-        long t = i / CV;
-        const int ix = (int)(t % Win);
-        t /= Win;
-        const int iy = (int)(t % Hin);
-        const long b = t / Hin;
-        int ylo, yhi, xlo, xhi;
-        bilinear_candidates(iy, rh, Hout, ylo, yhi);
+    const int iy = blockIdx.x % Hin;
+    const int b = blockIdx.x / Hin;
+    int ylo, yhi;
+    bilinear_candidates(iy, rh, Hout, ylo, yhi);
+    const bool y_table = yhi - ylo < MAXC;
+    float wy[MAXC];
+#pragma unroll
+    for (int a = 0; a < MAXC; ++a) wy[a] = (y_table && ylo + a <= yhi) ? bilinear_weight(ylo + a, iy, rh, Hin) : 0.f;
+    const T* base = dy + (long)b * Hout * Wout * C;
+    T* orow = dx + ((long)b * Hin + iy) * Win * C;
+    const int n = Win * CV;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int ix = i / CV;
+        const int c = (i - ix * CV) * V;
+        int xlo, xhi;
         bilinear_candidates(ix, rw, Wout, xlo, xhi);
-        const T* base = dy + b * Hout * Wout * C + c;
         float acc[V];
 #pragma unroll
         for (int j = 0; j < V; ++j) acc[j] = 0.f;
-        // per-axis weights once per thread (the candidate ranges are a few pixels wide for the 2H-1 -> 2H fix-ups of this network)
-        constexpr int MAXC = 6;
-        if (yhi - ylo < MAXC && xhi - xlo < MAXC) {
-            float wy[MAXC], wx[MAXC];
+        if (y_table && xhi - xlo < MAXC) {
+            float wx[MAXC];
 #pragma unroll
-            for (int a = 0; a < MAXC; ++a) {
-                wy[a] = (ylo + a <= yhi) ? bilinear_weight(ylo + a, iy, rh, Hin) : 0.f;
-                wx[a] = (xlo + a <= xhi) ? bilinear_weight(xlo + a, ix, rw, Win) : 0.f;
-            }
+            for (int a = 0; a < MAXC; ++a) wx[a] = (xlo + a <= xhi) ? bilinear_weight(xlo + a, ix, rw, Win) : 0.f;
 #pragma unroll
             for (int a = 0; a < MAXC; ++a) {
                 if (wy[a] == 0.f) continue;
@@ -455,7 +469,7 @@ __global__ void __launch_bounds__(256) resize_bilinear_bwd_vec_kernel(const T* _
                     const float w = wy[a] * wx[bb];
                     if (w != 0.f) {
                         float v[V];
-                        cnb_ldv(base + ((long)(ylo + a) * Wout + (xlo + bb)) * C, v);
+                        cnb_ldv(base + ((long)(ylo + a) * Wout + (xlo + bb)) * C + c, v);
 #pragma unroll
                         for (int j = 0; j < V; ++j) acc[j] = fmaf(w, v[j], acc[j]);
                     }
@@ -463,20 +477,20 @@ __global__ void __launch_bounds__(256) resize_bilinear_bwd_vec_kernel(const T* _
             }
         } else {
             for (int oy = ylo; oy <= yhi; ++oy) {
-                const float wy = bilinear_weight(oy, iy, rh, Hin);
-                if (wy == 0.f) continue;
+                const float wyy = bilinear_weight(oy, iy, rh, Hin);
+                if (wyy == 0.f) continue;
                 for (int ox = xlo; ox <= xhi; ++ox) {
-                    const float w = wy * bilinear_weight(ox, ix, rw, Win);
+                    const float w = wyy * bilinear_weight(ox, ix, rw, Win);
                     if (w != 0.f) {
                         float v[V];
-                        cnb_ldv(base + ((long)oy * Wout + ox) * C, v);
+                        cnb_ldv(base + ((long)oy * Wout + ox) * C + c, v);
 #pragma unroll
                         for (int j = 0; j < V; ++j) acc[j] = fmaf(w, v[j], acc[j]);
                     }
                 }
             }
         }
-        cnb_stv(dx + i * V, acc);
+        cnb_stv(orow + ix * C + c, acc);
     }
 }
 

@@ -64,7 +64,13 @@ _CONV_ENTRY = {"auto": "cnb_conv2d_fwd", "generic": "cnb_conv2d_fwd_generic", "t
 _WGRAD_ENTRY = {"auto": "cnb_conv2d_wgrad", "generic": "cnb_conv2d_wgrad_generic", "tc": "cnb_conv2d_wgrad_tc"}
 
 
-def _launch_conv(sources, src_channels, wp, w_row_off, w_row_stride, w_tap_stride, N, bias, out, geom, transposed, dtype):
+STATS_MAX_N = 1024  # csrc/k_conv_tc.cuh
+
+
+def _launch_conv(sources, src_channels, wp, w_row_off, w_row_stride, w_tap_stride, N, bias, out, geom, transposed, dtype,
+                 want_stats=False):
+    """Launches the convolution; with ``want_stats`` returns the [2, N] fp32 BatchNorm partial sums the tcgen05 epilogue produced
+    (None when the shape takes another kernel and the caller has to run ``cnb_bn_stats``)."""
     d = ConvDesc()
     B, Hin, Win, Hout, Wout, KH, KW, stride, pad, dil = geom
     esize = wp.element_size()
@@ -82,18 +88,25 @@ def _launch_conv(sources, src_channels, wp, w_row_off, w_row_stride, w_tap_strid
     d.bias = bias.data_ptr() if bias is not None else None
     d.out = out.data_ptr()
     d.out_stride = out.shape[-1]
+    d.stats = None
+    stats = None
+    if want_stats and N <= STATS_MAX_N and CONV_BACKEND != "generic" and not _lib.is_emulator():
+        if _lib.lib().cnb_conv2d_tc_eligible(C.byref(d), dtype_code(dtype)):
+            stats = torch.zeros((2, N), dtype=torch.float32, device=out.device)
+            d.stats = stats.data_ptr()
     flops = 2.0 * B * (Hin * Win if transposed else Hout * Wout) * N * sum(src_channels) * KH * KW  # algorithmic
     detail = None
     if _lib.TIMER is not None:
         detail = f"B{B} {Hin}x{Win}->{Hout}x{Wout} {'+'.join(map(str, src_channels))}->{N} k{KH} s{stride}{'T' if transposed else ''}"
     call(_CONV_ENTRY[CONV_BACKEND], C.byref(d), dtype_code(dtype), stream_ptr(out), flops=flops, tag="conv_fwd/dgrad", detail=detail)
+    return stats
 
 
 class _Conv2dFn(torch.autograd.Function):
     """y = conv(cat(sources, channel), weight) + bias over pixel-major tensors; see ``cnb_conv2d_fwd``."""
 
     @staticmethod
-    def forward(ctx, weight, bias, kind, ksize, stride, pad, dil, transposed, out_hw, *sources):
+    def forward(ctx, weight, bias, kind, ksize, stride, pad, dil, transposed, out_hw, want_stats, *sources):
         check_device(weight, bias, *sources)
         sources = [_contig(s) for s in sources]
         x0 = sources[0]
@@ -120,13 +133,19 @@ class _Conv2dFn(torch.autograd.Function):
         out = torch.empty((B, Hout, Wout, N), dtype=dtype, device=x0.device)
         geom = (B, Hin, Win, Hout, Wout, KH, KW, stride, pad, dil)
         bias_c = _contig(bias) if bias is not None else None
-        _launch_conv(sources, src_channels, wp, 0, wp.shape[2], N * wp.shape[2], N, bias_c, out, geom, transposed, dtype)
+        stats = _launch_conv(sources, src_channels, wp, 0, wp.shape[2], N * wp.shape[2], N, bias_c, out, geom, transposed, dtype,
+                             want_stats=want_stats)
         ctx.save_for_backward(weight, *sources)
         ctx.meta = (kind, geom, transposed, src_channels, N, Ctot, bias is not None)
-        return out
+        if not want_stats:
+            return out
+        if stats is None:
+            stats = torch.empty((0,), dtype=torch.float32, device=out.device)  # "not produced": the caller runs cnb_bn_stats
+        ctx.mark_non_differentiable(stats)
+        return out, stats
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, _dstats=None):
         weight, *sources = ctx.saved_tensors
         kind, geom, transposed, src_channels, N, Ctot, has_bias = ctx.meta
         B, Hin, Win, Hout, Wout, KH, KW, stride, pad, dil = geom
@@ -144,7 +163,7 @@ class _Conv2dFn(torch.autograd.Function):
         need_w = ctx.needs_input_grad[0]
         need_b = has_bias and ctx.needs_input_grad[1]
         src_grads = [None] * len(sources)
-        need_src = [ctx.needs_input_grad[9 + i] for i in range(len(sources))]
+        need_src = [ctx.needs_input_grad[10 + i] for i in range(len(sources))]
 
         if any(need_src):
             # dgrad: the adjoint gather with the per-tap transposed weights [taps][Ctot][N]; one launch per source slice
@@ -184,22 +203,24 @@ class _Conv2dFn(torch.autograd.Function):
         if need_b:
             db = torch.empty((N,), dtype=torch.float32, device=dev)
             call("cnb_bias_grad", ptr(dy), dy_pitch, B * Hout * Wout, N, ptr(db), 0, dtype_code(dtype), stream_ptr(dy))
-        return (dw, db, None, None, None, None, None, None, None, *src_grads)
+        return (dw, db, None, None, None, None, None, None, None, None, *src_grads)
 
 
-def conv2d(sources: Sequence[torch.Tensor], weight, bias=None, ksize=3, stride=1, pad=1, dil=1) -> torch.Tensor:
-    """nn.Conv2d over the channel concatenation of ``sources`` (each ``[B,H,W,Cs]``)."""
-    return _Conv2dFn.apply(weight, bias, W_CONV, ksize, stride, pad, dil, False, None, *sources)
+def conv2d(sources: Sequence[torch.Tensor], weight, bias=None, ksize=3, stride=1, pad=1, dil=1, want_stats: bool = False):
+    """nn.Conv2d over the channel concatenation of ``sources`` (each ``[B,H,W,Cs]``).  With ``want_stats`` returns
+    ``(y, sums)`` where ``sums`` is the ``[2, N]`` per-channel (sum, sum of squares) of ``y`` computed in the convolution epilogue,
+    or an empty tensor when the shape took a kernel without that epilogue."""
+    return _Conv2dFn.apply(weight, bias, W_CONV, ksize, stride, pad, dil, False, None, want_stats, *sources)
 
 
 def conv_transpose2d(x: torch.Tensor, weight, bias=None, ksize=3, stride=2, pad=1, dil=1) -> torch.Tensor:
     """nn.ConvTranspose2d (output_padding=0): ``[B,H,W,C] -> [B,(H-1)s-2p+d(k-1)+1, ..., N]``."""
-    return _Conv2dFn.apply(weight, bias, W_CONVT, ksize, stride, pad, dil, True, None, x)
+    return _Conv2dFn.apply(weight, bias, W_CONVT, ksize, stride, pad, dil, True, None, False, x)
 
 
 def linear(x: torch.Tensor, weight, bias=None) -> torch.Tensor:
     """nn.Linear over the channel axis of a pixel-major tensor."""
-    return _Conv2dFn.apply(weight, bias, W_LINEAR, 1, 1, 0, 1, False, None, x)
+    return _Conv2dFn.apply(weight, bias, W_LINEAR, 1, 1, 0, 1, False, None, False, x)
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -207,7 +228,7 @@ class _BatchNormActFn(torch.autograd.Function):
     """BatchNorm (batch statistics in training, running statistics in eval) + optional SiLU (+ residual)."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, running_mean, running_var, training, momentum, eps, act, ch_div, residual):
+    def forward(ctx, x, gamma, beta, running_mean, running_var, training, momentum, eps, act, ch_div, residual, sums=None):
         check_device(x, gamma, beta, running_mean, running_var, residual)
         x = _contig(x)
         dev, dtype = x.device, x.dtype
@@ -218,8 +239,12 @@ class _BatchNormActFn(torch.autograd.Function):
         stats = torch.empty((6, Cn), dtype=torch.float32, device=dev)  # sum, sumsq, mean, rstd, scale, shift
         count = P * (L // Cn)
         if training:
-            call("cnb_bn_stats", ptr(x), P, L, Cn, ch_div, ptr(stats[0]), dtype_code(dtype), st)
-            call("cnb_bn_finalize", ptr(stats[0]), count, Cn, ptr(gamma), ptr(beta), eps, momentum, ptr(running_mean),
+            if sums is not None and sums.numel() == 2 * Cn:
+                sums_ptr = ptr(_contig(sums))  # batch statistics came out of the convolution epilogue
+            else:
+                sums_ptr = ptr(stats[0])
+                call("cnb_bn_stats", ptr(x), P, L, Cn, ch_div, sums_ptr, dtype_code(dtype), st)
+            call("cnb_bn_finalize", sums_ptr, count, Cn, ptr(gamma), ptr(beta), eps, momentum, ptr(running_mean),
                  ptr(running_var), ptr(stats[2]), ptr(stats[3]), ptr(stats[4]), ptr(stats[5]), st)
         else:
             call("cnb_bn_finalize", None, count, Cn, ptr(gamma), ptr(beta), eps, momentum, ptr(running_mean),
@@ -246,12 +271,13 @@ class _BatchNormActFn(torch.autograd.Function):
         call("cnb_bn_act_bwd_apply", ptr(x), ptr(dy), ptr(stats[2]), ptr(stats[3]), ptr(gamma), ptr(beta), ptr(dsums), count, ptr(dx),
              P, L, Cn, ch_div, act, int(training), dtype_code(dtype), st)
         dres = dy if has_res else None
-        return dx, dsums[1], dsums[0], None, None, None, None, None, None, None, dres
+        return dx, dsums[1], dsums[0], None, None, None, None, None, None, None, dres, None
 
 
 def batchnorm_act(x, gamma, beta, running_mean, running_var, training: bool, momentum: float = 0.1, eps: float = 1e-5,
-                  act: bool = True, ch_div: int = 1, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
-    return _BatchNormActFn.apply(x, gamma, beta, running_mean, running_var, training, momentum, eps, act, ch_div, residual)
+                  act: bool = True, ch_div: int = 1, residual: Optional[torch.Tensor] = None,
+                  sums: Optional[torch.Tensor] = None) -> torch.Tensor:
+    return _BatchNormActFn.apply(x, gamma, beta, running_mean, running_var, training, momentum, eps, act, ch_div, residual, sums)
 
 
 class _AddNFn(torch.autograd.Function):

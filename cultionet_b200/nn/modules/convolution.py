@@ -30,14 +30,15 @@ def _require_silu(activation_type: str) -> None:
         )
 
 
-def batchnorm_act(bn: nn.modules.batchnorm._BatchNorm, x: torch.Tensor, act: bool, ch_div: int = 1) -> torch.Tensor:
+def batchnorm_act(bn: nn.modules.batchnorm._BatchNorm, x: torch.Tensor, act: bool, ch_div: int = 1,
+                  sums: T.Optional[torch.Tensor] = None) -> torch.Tensor:
     """BatchNorm2d/3d (+SiLU) with the module's parameters; batch statistics iff the module is in training mode."""
     training = bn.training
     if training and bn.track_running_stats and bn.num_batches_tracked is not None:
         bn.num_batches_tracked.add_(1)
     return F.batchnorm_act(
         x, bn.weight, bn.bias, bn.running_mean, bn.running_var, training,
-        momentum=bn.momentum if bn.momentum is not None else 0.1, eps=bn.eps, act=act, ch_div=ch_div,
+        momentum=bn.momentum if bn.momentum is not None else 0.1, eps=bn.eps, act=act, ch_div=ch_div, sums=sums,
     )
 
 
@@ -75,9 +76,13 @@ class ConvBlock2d(nn.Module):
 
     def forward(self, x: Sources) -> torch.Tensor:
         conv, bn = self.seq[0], self.seq[1]
+        # in training mode the tcgen05 convolution epilogue also produces BatchNorm's per-channel sums (no separate statistics pass)
         y = F.conv2d(_as_sources(x), conv.weight, None, ksize=conv.kernel_size[0], stride=conv.stride[0], pad=conv.padding[0],
-                     dil=conv.dilation[0])
-        return batchnorm_act(bn, y, act=self.add_activation)
+                     dil=conv.dilation[0], want_stats=bn.training)
+        sums = None
+        if bn.training:
+            y, sums = y
+        return batchnorm_act(bn, y, act=self.add_activation, sums=sums)
 
 
 class ResConvBlock2d(nn.Module):

@@ -123,13 +123,16 @@ class TowerUNetFinal(nn.Module):
         streams = (self.dist_conv, self.edge_conv, self.crop_conv)
         blocks = [s.conv[0] for s in streams]
         w1 = torch.cat([b.seq[0].weight for b in blocks], dim=0)  # [9, C, 3, 3]
-        h = F.conv2d([x], w1, None, ksize=3, stride=1, pad=1)
         bns = [b.seq[1] for b in blocks]
         training = bns[0].training
+        h = F.conv2d([x], w1, None, ksize=3, stride=1, pad=1, want_stats=training)
+        sums = None
+        if training:
+            h, sums = h
         rm = torch.cat([bn.running_mean for bn in bns])
         rv = torch.cat([bn.running_var for bn in bns])
         h = F.batchnorm_act(h, torch.cat([bn.weight for bn in bns]), torch.cat([bn.bias for bn in bns]), rm, rv, training,
-                            momentum=bns[0].momentum if bns[0].momentum is not None else 0.1, eps=bns[0].eps, act=True)
+                            momentum=bns[0].momentum if bns[0].momentum is not None else 0.1, eps=bns[0].eps, act=True, sums=sums)
         if training:
             with torch.no_grad():
                 for i, bn in enumerate(bns):

@@ -61,6 +61,10 @@ typedef struct {
     const float* bias;              /* [N] fp32 or NULL */
     void* out;                      /* element (p, n) at out + p*out_stride + n */
     int32_t out_stride;
+    float* stats;                   /* optional [2*N] fp32, zeroed by the caller: the tcgen05 kernel adds sum(y) and sum(y^2) per output
+                                     * channel over all pixels (y = the stored, rounded value), i.e. BatchNorm's batch statistics come out
+                                     * of the convolution epilogue and cnb_bn_stats is skipped.  Only honoured by cnb_conv2d_fwd_tc
+                                     * (N <= 1024); the other kernels require NULL. */
 } cnb_conv_desc;
 
 /* picks the tiny-channel kernel, else the tcgen05/TMA kernel when cnb_conv2d_tc_eligible(), else the CUDA-core kernel */
