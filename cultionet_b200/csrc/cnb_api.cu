@@ -96,7 +96,8 @@ int cnb_conv2d_tc_eligible(const cnb_conv_desc* d, int dtype) {
     return 0;
 #else
     if (check_conv_desc(d)) return 0;
-    return tc::eligible(d, dtype) ? 1 : 0;
+    if (!tc::eligible(d, dtype)) return 0;
+    return 1;  // (2 would announce BatchNorm sums from the epilogue; no kernel offers that at present)
 #endif
 }
 

@@ -24,10 +24,13 @@ namespace tc {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_BYTES = BM * BK * 2;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quadrant)
+constexpr int NUM_EPI_WARPS = 8;
 constexpr int MAX_TAPS = 16;    // taps summed over all phases
 constexpr int MAX_PHASES = 16;  // sub-pixel phases of a transposed convolution (stride^2)
 constexpr int MAX_MAPS = 9;     // A-operand tensor maps: one per source (unit stride) or one per tap (strided direct gather)
+constexpr int EPI_CHUNK_BYTES = 32 * 128;           // 32 rows x 64 bf16 columns staged per warp per chunk
+constexpr int EPI_STAGING_BYTES = 0;  // (no shared-memory staging in the epilogue)
 
 // The iteration space is a list of PHASES.  A phase is a unit-stride gather over a (Hv x Wv) domain per image with its own taps;
 // domain pixel (vy, vx) produces output pixel (vy*osy + ooy, vx*osx + oox).
@@ -40,6 +43,8 @@ constexpr int MAX_MAPS = 9;     // A-operand tensor maps: one per source (unit s
 struct ConvTcParams {
     CUtensorMap tmA[MAX_MAPS];
     CUtensorMap tmB;
+    int vec_ok;   // 16-byte output pitch: 128-bit stores
+    int log2_tw;
     int nsrc, per_tap_map;
     int chunks[CNB_MAX_SRC];  // 64-channel chunks per source (the last one may be partial: TMA zero-fills the tail)
     int koff[CNB_MAX_SRC];    // channel offset of the source inside Ctot
@@ -52,7 +57,7 @@ struct ConvTcParams {
     int N, m_tiles, num_tiles;
     int Hout, Wout, osy, osx;
     bf16_t* out;
-    int out_stride, vec_ok;
+    int out_stride;
     const float* bias;
     float* stats;  // optional [2*N]: per-output-channel sum and sum of squares of the STORED (bf16-rounded) outputs, for BatchNorm
 };
@@ -109,6 +114,16 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint
                  "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
                  : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(reinterpret_cast<uint64_t>(tmap)),
+                 "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all but the most recent bulk group have finished READING shared memory (the buffer used two chunks ago is free again)
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -164,7 +179,8 @@ struct Cfg {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
     static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // power of two for BN in {32,64,128,256}
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
+    static constexpr int SMEM_BYTES = RING_BYTES + EPI_STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 constexpr int STATS_MAX_N = 1024;  // channels whose BatchNorm partial sums fit behind the barriers (8 KB)
 
@@ -210,16 +226,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;          // SWIZZLE_128B atoms need 1024 B alignment
     uint8_t* base_ptr = smem_raw + (base - raw);
-    const uint32_t bars = base + C::STAGES * C::STAGE_BYTES;  // full[S] empty[S] tmem_full[2] tmem_empty[2] slot
+    const uint32_t staging = base + C::RING_BYTES;                      // epilogue staging: [warp][2][32 rows x 64 B]
+    const uint32_t bars = staging + EPI_STAGING_BYTES;                  // full[S] empty[S] tmem_full[2] tmem_empty[2] slot
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 8u * (C::STAGES + s); };
     auto tfull_bar = [&](int a) { return bars + 8u * (2 * C::STAGES + a); };
     auto tempty_bar = [&](int a) { return bars + 8u * (2 * C::STAGES + 2 + a); };
     const uint32_t slot = bars + 8u * (2 * C::STAGES + 4);
-    volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + C::STAGES * C::STAGE_BYTES + 8 * (2 * C::STAGES + 4));
+    volatile uint32_t* slot_ptr =
+        reinterpret_cast<volatile uint32_t*>(base_ptr + C::RING_BYTES + EPI_STAGING_BYTES + 8 * (2 * C::STAGES + 4));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* sm_stats = reinterpret_cast<float*>(base_ptr + C::STAGES * C::STAGE_BYTES + 256);  // [2*N] when p.stats
+    float* sm_stats = reinterpret_cast<float*>(base_ptr + C::RING_BYTES + EPI_STAGING_BYTES + 256);  // [2*N] when p.stats
     if (p.stats)
         for (int i = threadIdx.x; i < 2 * p.N; i += NUM_THREADS) sm_stats[i] = 0.f;
 
@@ -233,7 +251,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), 4);  // one arrive per epilogue warp
+            mbar_init(tempty_bar(a), NUM_EPI_WARPS);  // one arrive per epilogue warp
         }
         fence_barrier_init();
     }
@@ -316,9 +334,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         __syncwarp();
     } else {
         // ===================== epilogue: TMEM -> registers -> bf16 -> global =====================
-        const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+        // A TMEM lane holds one pixel row; each lane converts and stores its own row, 64 bytes per 32-column chunk.  Measured
+        // alternatives (profiles/r01_epilogue_variants.md): staging through shared memory for whole-line stores and a TMA bulk
+        // store were both SLOWER -- the epilogue is bound by the instruction latency of a single warp, not by the store pattern --
+        // so the lean direct store stays and the work is split over EIGHT warps instead (two per TMEM lane quadrant, alternating
+        // 32-column chunks), which is what shortens the convolutions whose K loop is too short to hide it (1x1, transposed phases).
+        const int ew = warp - 2;
+        const int quad = warp & 3;   // TMEM lane quadrant this warp may access (warp id % 4)
+        const int half = ew >> 2;    // which of the two warps of that quadrant
         const int row = quad * 32 + lane;
-        const int ly = row / p.TW, lx = row - ly * p.TW;
+        const int ly = row >> p.log2_tw, lx = row & (p.TW - 1);
         int it = 0;
         TileCoord tc;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
@@ -335,41 +360,37 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = half; c < BN / 32; c += 2) {
                 const int col0 = n0 + c * 32;
                 if (col0 >= p.N) break;
                 uint32_t v[32];
                 tmem_ld32(taddr + (uint32_t)(c * 32), v);
-                if (!valid && !p.stats) continue;
-                float f[32];  // what gets stored: accumulator (+bias) rounded to bf16; zero for rows outside the image
+                if (!valid) continue;
+                if (p.vec_ok && col0 + 32 <= p.N) {
+                    uint32_t packed[16];
+                    if (p.bias) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float t = has_taps ? __uint_as_float(v[j]) : 0.f;
-                    if (p.bias && col0 + j < p.N) t += __ldg(p.bias + col0 + j);
-                    f[j] = valid ? __bfloat162float(__float2bfloat16(t)) : 0.f;
-                }
-                if (valid) {
-                    if (p.vec_ok && col0 + 32 <= p.N) {
-                        uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            dst[j] = make_uint4(cnb_pack_bf16x2(f[8 * j], f[8 * j + 1]), cnb_pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                                                cnb_pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), cnb_pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+                        for (int j = 0; j < 16; ++j) {
+                            const float f0 = (has_taps ? __uint_as_float(v[2 * j]) : 0.f) + __ldg(p.bias + col0 + 2 * j);
+                            const float f1 = (has_taps ? __uint_as_float(v[2 * j + 1]) : 0.f) + __ldg(p.bias + col0 + 2 * j + 1);
+                            packed[j] = cnb_pack_bf16x2(f0, f1);
+                        }
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (col0 + j < p.N) orow[c * 32 + j] = __float2bfloat16(f[j]);
+                        for (int j = 0; j < 16; ++j)
+                            packed[j] = has_taps ? cnb_pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])) : 0u;
                     }
-                }
-                if (p.stats) {
-                    float q[32];
+                    uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) q[j] = f[j] * f[j];
-                    const float s1 = warp_transpose_sum32(f);
-                    const float s2 = warp_transpose_sum32(q);
-                    if (col0 + lane < p.N) {
-                        atomicAdd(&sm_stats[col0 + lane], s1);
-                        atomicAdd(&sm_stats[p.N + col0 + lane], s2);
+                    for (int j = 0; j < 4; ++j) dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (col0 + j < p.N) {
+                            float f = has_taps ? __uint_as_float(v[j]) : 0.f;
+                            if (p.bias) f += __ldg(p.bias + col0 + j);
+                            orow[c * 32 + j] = __float2bfloat16(f);
+                        }
                     }
                 }
             }
@@ -629,10 +650,12 @@ inline int conv_tc_launch(const cnb_conv_desc* d, cudaStream_t stream) {
     p.Wout = d->Wout;
     p.out = reinterpret_cast<bf16_t*>(d->out);
     p.out_stride = d->out_stride;
-    p.vec_ok = (d->out_stride % 8 == 0 && reinterpret_cast<uintptr_t>(d->out) % 16 == 0) ? 1 : 0;
     p.bias = d->bias;
-    p.stats = d->N <= STATS_MAX_N ? d->stats : nullptr;
-    if (d->stats && !p.stats) return 3;
+    p.vec_ok = (d->out_stride % 8 == 0 && reinterpret_cast<uintptr_t>(d->out) % 16 == 0) ? 1 : 0;
+    p.log2_tw = 0;
+    while ((1 << p.log2_tw) < p.TW) ++p.log2_tw;
+    p.stats = nullptr;
+    if (d->stats) return 3;  // statistics in the epilogue: measured slower than the separate pass (see the epilogue note above)
     p.num_tiles = cnb_div_up(d->N, BN) * p.m_tiles;
     switch (BN) {
         case 256: return launch_bn<256>(p, stream);

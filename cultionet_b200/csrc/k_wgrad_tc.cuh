@@ -174,7 +174,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const __grid_c
         }
         __syncwarp();
     } else {
-        const int quad = warp & 3;
+        const int quad = warp & 3;          // TMEM lane quadrant (warp id % 4); warps 2..9: two per quadrant,
+        const int half = (warp - 2) >> 2;   // alternating 32-column chunks
         mbar_wait(done_bar, 0);
         tc_fence_after();
         const int cvalid = p.src_c - c0;  // columns of this tile that exist
@@ -184,7 +185,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const __grid_c
             float* drow = p.dwp + ((long)p.tap_w[tap] * p.N + n) * p.Ctot + p.k_off + c0;
             const bool vec_red = (reinterpret_cast<uintptr_t>(drow) & 15u) == 0;  // 16-byte aligned rows when Ctot, k_off are multiples of 4
             if (pt_end > pt_begin && n0 + sub * BM < p.N) {
-                for (int c = 0; c < cw / 32; ++c) {
+                for (int c = half; c < cw / 32; c += 2) {
                     if (c * 32 >= cvalid) break;
                     uint32_t v[32];
                     tmem_ld32(taddr + (uint32_t)(c * 32), v);

@@ -91,7 +91,7 @@ def _launch_conv(sources, src_channels, wp, w_row_off, w_row_stride, w_tap_strid
     d.stats = None
     stats = None
     if want_stats and N <= STATS_MAX_N and CONV_BACKEND != "generic" and not _lib.is_emulator():
-        if _lib.lib().cnb_conv2d_tc_eligible(C.byref(d), dtype_code(dtype)):
+        if _lib.lib().cnb_conv2d_tc_eligible(C.byref(d), dtype_code(dtype)) == 2:
             stats = torch.zeros((2, N), dtype=torch.float32, device=out.device)
             d.stats = stats.data_ptr()
     flops = 2.0 * B * (Hin * Win if transposed else Hout * Wout) * N * sum(src_channels) * KH * KW  # algorithmic

@@ -75,6 +75,7 @@ int cnb_conv2d_fwd_generic(const cnb_conv_desc* d, int dtype, void* stream);
  * zero-filled by TMA and masked); stride 1..4 direct or transposed (stride > 1 needs a single source and <= 9 taps).
  * CNB_ERR_UNSUPPORTED otherwise */
 int cnb_conv2d_fwd_tc(const cnb_conv_desc* d, int dtype, void* stream);
+/* 0: not eligible; 1: eligible; 2: eligible and able to fill `stats` */
 int cnb_conv2d_tc_eligible(const cnb_conv_desc* d, int dtype);
 /* one thread per output pixel, filter bank in shared memory: N <= 16 output and <= 16 input channels (the Psi-Net heads' 3->1 and
  * 3->3 convolutions, nn/modules/unet_parts.py:215-220, :262-270); cnb_conv2d_fwd picks it first when it applies */

@@ -14,7 +14,7 @@ torch.manual_seed(0)
 x = torch.randn(B, H, W, Cin, device="cuda").bfloat16().requires_grad_(True)
 w = (torch.randn(Cout, Cin, 3, 3, device="cuda") / (Cin * 9) ** 0.5).requires_grad_(True)
 for _ in range(3):
-    y = F.conv2d([x], w, None, 3, 1, 1, 1)
+    y, sums = F.conv2d([x], w, None, 3, 1, 1, 1, want_stats=True)
     gx, gw = torch.autograd.grad(y, [x, w], torch.ones_like(y))
 torch.cuda.synchronize()
 print("ok", float(gw.float().abs().mean()))
