@@ -7,6 +7,7 @@ of a bucket (parameters are laid out in forward order, so buckets complete from 
 """
 from __future__ import annotations
 
+import datetime
 import os
 from typing import List, Optional
 
@@ -26,7 +27,9 @@ def init_distributed(backend: Optional[str] = None) -> tuple:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
             torch.cuda.set_device(local)
-        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+        # a short timeout: a mismatched collective must fail in minutes, not hold a multi-GPU box for the 10-minute default
+        dist.init_process_group(backend=backend, rank=rank, world_size=world,
+                                timeout=datetime.timedelta(seconds=int(os.environ.get("CNB_DIST_TIMEOUT_S", "180"))))
     return rank, local, world
 
 
