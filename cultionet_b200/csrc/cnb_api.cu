@@ -13,14 +13,21 @@
 
 using namespace cnb;
 
+#ifdef CNB_EMU
+#define CNB_SET_SMEM(kfn, bytes) ((void)0)
+#else
+#define CNB_SET_SMEM(kfn, bytes) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))
+#endif
+
 static inline int stream_grid(long n, int per_block = 256, int waves = 8) {
     return cnb_clamp_grid(cnb_div_up(n, per_block), (long)CNB_NUM_SMS * waves);
 }
 
 static inline int vec_width(int dtype) { return dtype == CNB_BF16 ? 8 : 4; }
-// pixel-major BatchNorm2d whose rows split into whole 16-byte vectors (and whose per-CTA channel sums fit in shared memory)
+// rows that split into whole 16-byte vectors (and per-CTA channel sums that fit in shared memory); column j belongs to channel
+// j / ch_div, columns past C*ch_div are row padding
 static inline bool bn_vec_ok(int L, int C, int ch_div, int dtype) {
-    return ch_div == 1 && L == C && C % vec_width(dtype) == 0 && C <= 4096;
+    return L % vec_width(dtype) == 0 && (long)C * ch_div <= L && C <= 4096;
 }
 
 static inline long column_stride(long total, int L, int* blocks) {
@@ -270,12 +277,12 @@ int cnb_bn_stats(const void* x, int64_t P, int L, int C, int ch_div, float* sums
     int blocks;
     const long total = (long)P * L;
     if (bn_vec_ok(L, C, ch_div, dtype) && cnb_aligned16(x)) {
-        const int V = vec_width(dtype), CV = C / V;
+        const int V = vec_width(dtype), CV = L / V;
         const long total_v = total / V;
         const long stride_v = column_stride(total_v, CV, &blocks);
         CNB_DISPATCH_DTYPE(dtype, {
             CNB_LAUNCH((bn_stats_vec_kernel<T>), dim3(blocks), dim3(256), 2 * C * sizeof(float), (cudaStream_t)stream, (const T*)x, total_v, CV,
-                       stride_v, C, sums);
+                       stride_v, C, ch_div, sums);
         });
         CNB_CHECK_LAUNCH("bn_stats_vec_kernel");
         return CNB_OK;
@@ -304,13 +311,13 @@ int cnb_bn_act_fwd(const void* x, const float* scale, const float* shift, const 
     CNB_REQUIRE(x && y && scale && shift && P > 0 && L > 0 && C > 0 && ch_div > 0, "bn_act_fwd: bad arguments");
     const long total = (long)P * L;
     if (bn_vec_ok(L, C, ch_div, dtype) && cnb_aligned16(x) && cnb_aligned16(y) && cnb_aligned16(residual)) {
-        const int V = vec_width(dtype), CV = C / V;
+        const int V = vec_width(dtype), CV = L / V;
         int blocks;
         const long total_v = total / V;
         const long stride_v = column_stride(total_v, CV, &blocks);
         CNB_DISPATCH_DTYPE(dtype, {
             CNB_LAUNCH((bn_act_fwd_vec_kernel<T>), dim3(blocks), dim3(256), 0, (cudaStream_t)stream, (const T*)x, scale, shift,
-                       (const T*)residual, (T*)y, total_v, CV, stride_v, act);
+                       (const T*)residual, (T*)y, total_v, CV, stride_v, C, ch_div, act);
         });
         CNB_CHECK_LAUNCH("bn_act_fwd_vec_kernel");
         return CNB_OK;
@@ -330,12 +337,12 @@ int cnb_bn_act_bwd_reduce(const void* x, const void* dy, const float* save_mean,
     int blocks;
     const long total = (long)P * L;
     if (bn_vec_ok(L, C, ch_div, dtype) && cnb_aligned16(x) && cnb_aligned16(dy)) {
-        const int V = vec_width(dtype), CV = C / V;
+        const int V = vec_width(dtype), CV = L / V;
         const long total_v = total / V;
         const long stride_v = column_stride(total_v, CV, &blocks);
         CNB_DISPATCH_DTYPE(dtype, {
             CNB_LAUNCH((bn_act_bwd_reduce_vec_kernel<T>), dim3(blocks), dim3(256), 2 * C * sizeof(float), (cudaStream_t)stream, (const T*)x,
-                       (const T*)dy, save_mean, save_rstd, gamma, beta, total_v, CV, stride_v, C, act, dsums);
+                       (const T*)dy, save_mean, save_rstd, gamma, beta, total_v, CV, stride_v, C, ch_div, act, dsums);
         });
         CNB_CHECK_LAUNCH("bn_act_bwd_reduce_vec_kernel");
         return CNB_OK;
@@ -356,13 +363,14 @@ int cnb_bn_act_bwd_apply(const void* x, const void* dy, const float* save_mean, 
                 "bn_act_bwd_apply: bad arguments");
     const long total = (long)P * L;
     if (bn_vec_ok(L, C, ch_div, dtype) && cnb_aligned16(x) && cnb_aligned16(dy) && cnb_aligned16(dx)) {
-        const int V = vec_width(dtype), CV = C / V;
+        const int V = vec_width(dtype), CV = L / V;
         int blocks;
         const long total_v = total / V;
         const long stride_v = column_stride(total_v, CV, &blocks);
         CNB_DISPATCH_DTYPE(dtype, {
             CNB_LAUNCH((bn_act_bwd_apply_vec_kernel<T>), dim3(blocks), dim3(256), 0, (cudaStream_t)stream, (const T*)x, (const T*)dy,
-                       save_mean, save_rstd, gamma, beta, dsums, 1.0f / (float)count, (T*)dx, total_v, CV, stride_v, C, act, train_stats);
+                       save_mean, save_rstd, gamma, beta, dsums, 1.0f / (float)count, (T*)dx, total_v, CV, stride_v, C, ch_div, act,
+                       train_stats);
         });
         CNB_CHECK_LAUNCH("bn_act_bwd_apply_vec_kernel");
         return CNB_OK;
@@ -486,11 +494,6 @@ static bool na_tile_setup(int B, int H, int W, int heads, int hd, int ksize, int
     return true;
 }
 
-#ifdef CNB_EMU
-#define CNB_SET_SMEM(kfn, bytes) ((void)0)
-#else
-#define CNB_SET_SMEM(kfn, bytes) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))
-#endif
 // launch a `template <typename T, int LPH>` tiled NA kernel
 #define CNB_NA_LAUNCH_LPH(KERNEL, LPHV, ...)                                                                       \
     CNB_DISPATCH_DTYPE(dtype, {                                                                                    \
@@ -612,24 +615,43 @@ int cnb_resize_bilinear_bwd(const void* dy, void* dx, int B, int Hin, int Win, i
 }
 
 // ------------------------------------------------------------------------------------------------
-int cnb_pretime_conv_fwd(const float* x, const float* w1, void* u, int B, int C, int T_, int H, int W, int k, int dtype, void* stream) {
+static size_t pretime_smem(int C, int T_, int k, int up, int dtype, bool wgrad) {
+    const size_t es = dtype == CNB_BF16 ? 2 : 4;
+    const size_t xs = (size_t)C * T_ * PT_PIX * sizeof(float);
+    if (!wgrad) return xs + (size_t)PT_PIX * up * es + (size_t)C * C * k * sizeof(float) + 16;
+    return xs + (size_t)PT_PIX * (up + 2) * es + (size_t)C * C * k * sizeof(float) + 16;
+}
+
+int cnb_pretime_conv_fwd(const float* x, const float* w1, void* u, int B, int C, int T_, int H, int W, int k, int u_pitch, int dtype,
+                         void* stream) {
     CNB_REQUIRE(x && w1 && u && B > 0 && C > 0 && H > 0 && W > 0 && k > 0 && T_ >= k, "pretime_conv_fwd: bad arguments (T=%d, k=%d)", T_, k);
+    CNB_REQUIRE(u_pitch >= C * (T_ - k + 1), "pretime_conv_fwd: pitch %d < C*T' = %d", u_pitch, C * (T_ - k + 1));
+    const size_t smem = pretime_smem(C, T_, k, u_pitch, dtype, false);
+    CNB_REQUIRE(smem <= 200 * 1024, "pretime_conv_fwd: C*T = %d does not fit the shared-memory tile", C * T_);
     const long P = (long)B * H * W;
-    dim3 grid(stream_grid(P, 256, 4), C);
+    dim3 grid(cnb_clamp_grid(cnb_div_up(P, PT_PIX), (long)CNB_NUM_SMS * 4));
     CNB_DISPATCH_DTYPE(dtype, {
-        CNB_LAUNCH((pretime_conv_fwd_kernel<T>), grid, dim3(256), 0, (cudaStream_t)stream, x, w1, (T*)u, B, C, T_, H, W, k);
+        CNB_SET_SMEM((pretime_conv_fwd_kernel<T>), smem);
+        CNB_LAUNCH((pretime_conv_fwd_kernel<T>), grid, dim3(PT_THREADS), smem, (cudaStream_t)stream, x, w1, (T*)u, B, C, T_, H, W, k, u_pitch);
     });
     CNB_CHECK_LAUNCH("pretime_conv_fwd_kernel");
     return CNB_OK;
 }
 
-int cnb_pretime_conv_wgrad(const float* x, const void* du, float* dw1, int B, int C, int T_, int H, int W, int k, int dtype, void* stream) {
+int cnb_pretime_conv_wgrad(const float* x, const void* du, float* dw1, int B, int C, int T_, int H, int W, int k, int u_pitch, int dtype,
+                           void* stream) {
     CNB_REQUIRE(x && du && dw1 && B > 0 && C > 0 && H > 0 && W > 0 && k > 0 && k <= PT_MAX_K && T_ >= k, "pretime_conv_wgrad: bad arguments");
-    CNB_REQUIRE(C * C <= 65535, "pretime_conv_wgrad: too many channels");
+    CNB_REQUIRE(u_pitch >= C * (T_ - k + 1), "pretime_conv_wgrad: pitch %d < C*T'", u_pitch);
+    CNB_REQUIRE(C * C * k <= PT_WG_MAX_TRIPLES * (PT_THREADS / PT_PIX), "pretime_conv_wgrad: C*C*k = %d exceeds %d", C * C * k,
+                PT_WG_MAX_TRIPLES * (PT_THREADS / PT_PIX));
+    const size_t smem = pretime_smem(C, T_, k, u_pitch, dtype, true);
+    CNB_REQUIRE(smem <= 200 * 1024, "pretime_conv_wgrad: C*T = %d does not fit the shared-memory tile", C * T_);
     const long P = (long)B * H * W;
-    dim3 grid(stream_grid(P, 256, 1), C * C);
+    dim3 grid(cnb_clamp_grid(cnb_div_up(P, PT_PIX), (long)CNB_NUM_SMS * 2));
     CNB_DISPATCH_DTYPE(dtype, {
-        CNB_LAUNCH((pretime_conv_wgrad_kernel<T>), grid, dim3(256), 0, (cudaStream_t)stream, x, (const T*)du, dw1, B, C, T_, H, W, k);
+        CNB_SET_SMEM((pretime_conv_wgrad_kernel<T>), smem);
+        CNB_LAUNCH((pretime_conv_wgrad_kernel<T>), grid, dim3(PT_THREADS), smem, (cudaStream_t)stream, x, (const T*)du, dw1, B, C, T_, H, W, k,
+                   u_pitch);
     });
     CNB_CHECK_LAUNCH("pretime_conv_wgrad_kernel");
     return CNB_OK;

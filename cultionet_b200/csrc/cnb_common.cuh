@@ -130,6 +130,7 @@ __device__ __forceinline__ void cnb_cp_async_wait_all() {
     asm volatile("cp.async.wait_all;" ::: "memory");
 #endif
 }
+__device__ __forceinline__ bool cnb_aligned16_dev(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline bool cnb_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 __device__ __forceinline__ float cnb_exp(float x) {

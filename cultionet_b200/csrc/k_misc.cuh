@@ -96,82 +96,140 @@ __global__ void __launch_bounds__(256) resize_bilinear_bwd_kernel(const T* __res
 }
 
 // ---------------------------------------------------------------------------------------------
-// PreTimeReduction stage 1: valid temporal convolution C -> C with kernel k over x[B,C,T,H,W] (fp32)
-// output u[p][c2*T' + t'] pixel-major so that stage 2 is a plain 1x1 GEMM with K = C*T'
+// PreTimeReduction stage 1: valid temporal convolution C -> C with kernel k over x[B,C,T,H,W] (fp32).
+// Output u[p][c2*T' + t'] pixel-major with a pixel pitch `up` >= C*T' (padding columns are written as zero), so that stage 2 is a
+// plain 1x1 GEMM with K = C*T' that the TMA-fed kernels can read.
+//
+// One CTA = PT_PIX consecutive pixels.  x is channel/time-major, so for a fixed (c, t) those pixels are contiguous floats:
+// the tile is staged in shared memory with coalesced loads, every thread then owns one pixel and a quarter of the outputs
+// (bank = pixel: conflict-free; the filter taps are warp-uniform broadcasts), the results go back through shared memory and
+// leave as whole 16-byte vectors of the [pixels][pitch] output block.  (The first version wrote 2-byte elements 220 bytes
+// apart and ran at 1 TB/s, ncu r01i.)
 // ---------------------------------------------------------------------------------------------
-constexpr int PT_CHUNK = 8;
+constexpr int PT_PIX = 64;
+constexpr int PT_THREADS = 256;
+constexpr int PT_MAX_K = 8;
 
+// dynamic smem: xs[C*T][PT_PIX] floats, then the output tile us[PT_PIX][up] of T, then w[C*C*k] floats
 template <typename T>
-__global__ void __launch_bounds__(256) pretime_conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w1,
-                                                              T* __restrict__ u, int B, int C, int Tn, int H, int W, int k) {
+__global__ void __launch_bounds__(PT_THREADS) pretime_conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w1,
+                                                                     T* __restrict__ u, int B, int C, int Tn, int H, int W, int k, int up) {
+    CNB_DYN_SMEM(sm_raw);
     const int Tp = Tn - k + 1;
+    const int CT = C * Tn;
+    float* xs = reinterpret_cast<float*>(sm_raw);
+    T* us = reinterpret_cast<T*>(xs + (long)CT * PT_PIX);
+    float* ws = reinterpret_cast<float*>(us + (long)PT_PIX * up);
     const long HW = (long)H * W;
     const long total = (long)B * HW;
-    const int c2 = blockIdx.y;
-    for (long p = (long)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (long)gridDim.x * blockDim.x) {
-        const long b = p / HW, hw = p - b * HW;
-        const float* xb = x + b * C * Tn * HW + hw;
-        T* up = u + p * ((long)C * Tp) + (long)c2 * Tp;
-        for (int t0 = 0; t0 < Tp; t0 += PT_CHUNK) {
-            float acc[PT_CHUNK];
-#pragma unroll
-            for (int j = 0; j < PT_CHUNK; ++j) acc[j] = 0.f;
-            for (int c = 0; c < C; ++c) {
-                const float* xc = xb + (long)c * Tn * HW;
-                const float* wc = w1 + ((long)c2 * C + c) * k;
-                for (int dt = 0; dt < k; ++dt) {
-                    const float wv = wc[dt];
-#pragma unroll
-                    for (int j = 0; j < PT_CHUNK; ++j) {
-                        const int tt = t0 + j + dt;
-                        if (t0 + j < Tp) acc[j] = fmaf(wv, xc[(long)tt * HW], acc[j]);
-                    }
+    for (int i = threadIdx.x; i < C * C * k; i += blockDim.x) ws[i] = w1[i];
+    const int p_in = threadIdx.x % PT_PIX, grp = threadIdx.x / PT_PIX, ngrp = blockDim.x / PT_PIX;
+    for (long p0 = (long)blockIdx.x * PT_PIX; p0 < total; p0 += (long)gridDim.x * PT_PIX) {
+        __syncthreads();  // previous tile fully written out (and ws visible on the first pass)
+        // ---- stage x: row (c, t), PT_PIX pixels
+        for (int i = threadIdx.x; i < CT * PT_PIX; i += blockDim.x) {
+            const int pp = i % PT_PIX, ct = i / PT_PIX;
+            const long p = p0 + pp;
+            float v = 0.f;
+            if (p < total) {
+                const long b = p / HW, hw = p - b * HW;
+                v = x[(b * CT + ct) * HW + hw];
+            }
+            xs[ct * PT_PIX + pp] = v;
+        }
+        __syncthreads();
+        // ---- compute: thread = (pixel, output group)
+        for (int j = grp; j < up; j += ngrp) {
+            float acc = 0.f;
+            if (j < C * Tp) {
+                const int c2 = j / Tp, tp = j - c2 * Tp;
+                for (int c = 0; c < C; ++c) {
+                    const float* xr = xs + (c * Tn + tp) * PT_PIX + p_in;
+                    const float* wr = ws + (c2 * C + c) * k;
+                    for (int dt = 0; dt < k; ++dt) acc = fmaf(wr[dt], xr[dt * PT_PIX], acc);
                 }
             }
-#pragma unroll
-            for (int j = 0; j < PT_CHUNK; ++j)
-                if (t0 + j < Tp) cnb_st(up + t0 + j, acc[j]);
+            cnb_st(us + (long)p_in * up + j, acc);
+        }
+        __syncthreads();
+        // ---- write the [PT_PIX][up] block: contiguous in global memory
+        const long valid_px = total - p0 < PT_PIX ? total - p0 : PT_PIX;
+        const long nelem = valid_px * up;
+        T* dst = u + p0 * up;
+        constexpr int V = cnb_vec<T>::N;
+        if (up % V == 0 && cnb_aligned16_dev(dst)) {
+            for (long i = threadIdx.x; i < nelem / V; i += blockDim.x)
+                *reinterpret_cast<uint4*>(dst + i * V) = *reinterpret_cast<const uint4*>(us + i * V);
+        } else {
+            for (long i = threadIdx.x; i < nelem; i += blockDim.x) dst[i] = us[i];
         }
     }
 }
 
-constexpr int PT_MAX_K = 8;
-
-// dw1[c2][c][dt] += sum_{p,t'} du[p][c2*T'+t'] * x[b,c,t'+dt,hw] ; grid.y = C*C pairs
+// dw1[c2][c][dt] += sum_{p,t'} du[p][c2*T'+t'] * x[b,c,t'+dt,hw].  Same tiling; every thread owns one pixel of the tile and a
+// quarter of the (c2, c, dt) triples, keeps its partial sums in registers across all tiles of the CTA, and the CTA reduces once.
+constexpr int PT_WG_MAX_TRIPLES = 64;  // per thread: ceil(C*C*k / 4) must fit
 template <typename T>
-__global__ void __launch_bounds__(256) pretime_conv_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ du,
-                                                                float* __restrict__ dw1, int B, int C, int Tn, int H, int W, int k) {
-    __shared__ float red[PT_MAX_K][8];
+__global__ void __launch_bounds__(PT_THREADS) pretime_conv_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ du,
+                                                                       float* __restrict__ dw1, int B, int C, int Tn, int H, int W, int k,
+                                                                       int up) {
+    CNB_DYN_SMEM(sm_raw);
     const int Tp = Tn - k + 1;
+    const int CT = C * Tn;
+    float* xs = reinterpret_cast<float*>(sm_raw);
+    T* ds = reinterpret_cast<T*>(xs + (long)CT * PT_PIX);   // [PT_PIX][up + 2]: odd word pitch against bank conflicts
+    const int dpitch = up + 2;
+    float* red = reinterpret_cast<float*>(ds + (long)PT_PIX * dpitch);  // [C*C*k]
     const long HW = (long)H * W;
     const long total = (long)B * HW;
-    const int c2 = blockIdx.y / C, c = blockIdx.y - c2 * C;
-    float acc[PT_MAX_K];
+    const int ntr = C * C * k;
+    const int p_in = threadIdx.x % PT_PIX, grp = threadIdx.x / PT_PIX, ngrp = blockDim.x / PT_PIX;
+    float acc[PT_WG_MAX_TRIPLES];
 #pragma unroll
-    for (int j = 0; j < PT_MAX_K; ++j) acc[j] = 0.f;
-    for (long p = (long)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (long)gridDim.x * blockDim.x) {
-        const long b = p / HW, hw = p - b * HW;
-        const float* xc = x + (b * C + c) * Tn * HW + hw;
-        const T* dup = du + p * ((long)C * Tp) + (long)c2 * Tp;
-        for (int t = 0; t < Tp; ++t) {
-            const float g = cnb_ld(dup + t);
+    for (int i = 0; i < PT_WG_MAX_TRIPLES; ++i) acc[i] = 0.f;
+    for (int i = threadIdx.x; i < ntr; i += blockDim.x) red[i] = 0.f;
+    for (long p0 = (long)blockIdx.x * PT_PIX; p0 < total; p0 += (long)gridDim.x * PT_PIX) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < CT * PT_PIX; i += blockDim.x) {
+            const int pp = i % PT_PIX, ct = i / PT_PIX;
+            const long p = p0 + pp;
+            float v = 0.f;
+            if (p < total) {
+                const long b = p / HW, hw = p - b * HW;
+                v = x[(b * CT + ct) * HW + hw];
+            }
+            xs[ct * PT_PIX + pp] = v;
+        }
+        for (int i = threadIdx.x; i < PT_PIX * up; i += blockDim.x) {
+            const int pp = i / up, j = i - pp * up;
+            ds[pp * dpitch + j] = (p0 + pp < total) ? du[(p0 + pp) * up + j] : T(0.f);
+        }
+        __syncthreads();
 #pragma unroll
-            for (int dt = 0; dt < PT_MAX_K; ++dt)
-                if (dt < k) acc[dt] = fmaf(g, xc[(long)(t + dt) * HW], acc[dt]);
+        for (int i = 0; i < PT_WG_MAX_TRIPLES; ++i) {
+            const int tr = grp + i * ngrp;
+            if (tr < ntr) {
+                const int dt = tr % k, cc = tr / k;
+                const int c = cc % C, c2 = cc / C;
+                const float* xr = xs + (c * Tn + dt) * PT_PIX + p_in;
+                const T* dr = ds + p_in * dpitch + c2 * Tp;
+                float a = acc[i];
+                for (int tp = 0; tp < Tp; ++tp) a = fmaf(cnb_ld(dr + tp), xr[tp * PT_PIX], a);
+                acc[i] = a;
+            }
         }
     }
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();
 #pragma unroll
-    for (int dt = 0; dt < PT_MAX_K; ++dt) {
-        const float s = cnb_warp_sum(acc[dt]);
-        if (lane == 0) red[dt][wid] = s;
+    for (int i = 0; i < PT_WG_MAX_TRIPLES; ++i) {
+        const int tr = grp + i * ngrp;
+        if (tr < ntr) {  // uniform per warp: a warp holds 32 pixels of one group
+            const float v = cnb_warp_sum(acc[i]);
+            if ((threadIdx.x & 31) == 0) atomicAdd(&red[tr], v);
+        }
     }
     __syncthreads();
-    if (threadIdx.x < k) {
-        float s = 0.f;
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[threadIdx.x][w];
-        atomicAdd(dw1 + ((long)c2 * C + c) * k + threadIdx.x, s);
-    }
+    for (int i = threadIdx.x; i < ntr; i += blockDim.x) atomicAdd(dw1 + i, red[i]);
 }
 
 // ---------------------------------------------------------------------------------------------

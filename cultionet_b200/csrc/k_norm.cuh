@@ -19,9 +19,9 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ x, 
         __syncthreads();
     }
     const long gid = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid < stride) {
+    if (gid < stride && (int)(gid % L) / ch_div < C) {
         const int col = (int)(gid % L);
-        const int ch = (col / ch_div) % C;
+        const int ch = col / ch_div;  // columns with ch >= C are row padding and take no part
         float s = 0.f, s2 = 0.f;
         for (long i = gid; i < total; i += stride) {
             const float v = cnb_ld(x + i);
@@ -79,7 +79,11 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const T* __restrict__ x
                                                         T* __restrict__ y, long total, int L, int C, int ch_div, int act) {
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         const int col = (int)(i % L);
-        const int ch = (col / ch_div) % C;
+        const int ch = col / ch_div;
+        if (ch >= C) {  // row padding stays zero
+            cnb_st(y + i, 0.f);
+            continue;
+        }
         float z = fmaf(cnb_ld(x + i), scale[ch], shift[ch]);
         if (act) z = cnb_silu(z);
         if (residual) z += cnb_ld(residual + i);
@@ -100,9 +104,9 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(const T* __restr
         __syncthreads();
     }
     const long gid = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid < stride) {
+    if (gid < stride && (int)(gid % L) / ch_div < C) {
         const int col = (int)(gid % L);
-        const int ch = (col / ch_div) % C;
+        const int ch = col / ch_div;
         const float mu = mean[ch], rs = rstd[ch];
         const float g = gamma ? gamma[ch] : 1.f, b = beta ? beta[ch] : 0.f;
         float s = 0.f, sx = 0.f;
@@ -138,7 +142,11 @@ __global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(const T* __restri
                                                               long total, int L, int C, int ch_div, int act, int train_stats) {
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         const int col = (int)(i % L);
-        const int ch = (col / ch_div) % C;
+        const int ch = col / ch_div;
+        if (ch >= C) {  // row padding: zero gradient
+            cnb_st(dx + i, 0.f);
+            continue;
+        }
         const float rs = rstd[ch];
         const float g = gamma ? gamma[ch] : 1.f, b = beta ? beta[ch] : 0.f;
         const float xh = (cnb_ld(x + i) - mean[ch]) * rs;

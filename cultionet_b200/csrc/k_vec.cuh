@@ -16,7 +16,7 @@ namespace cnb {
 // ---------------------------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) bn_stats_vec_kernel(const T* __restrict__ x, long total_v, int CV, long stride_v, int C,
-                                                          float* __restrict__ sums) {
+                                                          int ch_div, float* __restrict__ sums) {
     constexpr int V = cnb_vec<T>::N;
     CNB_DYN_SMEM(sh_raw);  // 2*C floats
     float* sh_dyn = reinterpret_cast<float*>(sh_raw);
@@ -47,8 +47,11 @@ __global__ void __launch_bounds__(256) bn_stats_vec_kernel(const T* __restrict__
         }
 #pragma unroll
         for (int j = 0; j < V; ++j) {
-            atomicAdd(&sh_dyn[c0 + j], s[j]);
-            atomicAdd(&sh_dyn[C + c0 + j], q[j]);
+            const int ch = (c0 + j) / ch_div;  // columns past C*ch_div are row padding
+            if (ch < C) {
+                atomicAdd(&sh_dyn[ch], s[j]);
+                atomicAdd(&sh_dyn[C + ch], q[j]);
+            }
         }
     }
     __syncthreads();
@@ -58,14 +61,19 @@ __global__ void __launch_bounds__(256) bn_stats_vec_kernel(const T* __restrict__
 template <typename T>
 __global__ void __launch_bounds__(256) bn_act_fwd_vec_kernel(const T* __restrict__ x, const float* __restrict__ scale,
                                                             const float* __restrict__ shift, const T* __restrict__ residual,
-                                                            T* __restrict__ y, long total_v, int CV, long stride_v, int act) {
+                                                            T* __restrict__ y, long total_v, int CV, long stride_v, int C, int ch_div,
+                                                            int act) {
     constexpr int V = cnb_vec<T>::N;
     const long gid = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= stride_v) return;
     const int c0 = (int)(gid % CV) * V;
     float sc[V], sf[V];
 #pragma unroll
-    for (int j = 0; j < V; ++j) sc[j] = scale[c0 + j], sf[j] = shift[c0 + j];
+    for (int j = 0; j < V; ++j) {
+        const int ch = (c0 + j) / ch_div;
+        sc[j] = ch < C ? scale[ch] : 0.f;  // padding columns come out as act(0) = 0
+        sf[j] = ch < C ? shift[ch] : 0.f;
+    }
     constexpr int U = 2;
     for (long i = gid; i < total_v; i += U * stride_v) {
         float v[U][V], r[U][V];
@@ -93,7 +101,7 @@ template <typename T>
 __global__ void __launch_bounds__(256, 3) bn_act_bwd_reduce_vec_kernel(const T* __restrict__ x, const T* __restrict__ dy,
                                                                    const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                                   long total_v, int CV, long stride_v, int C, int act,
+                                                                   long total_v, int CV, long stride_v, int C, int ch_div, int act,
                                                                    float* __restrict__ dsums) {
     constexpr int V = cnb_vec<T>::N;
     CNB_DYN_SMEM(sh_raw);
@@ -107,10 +115,14 @@ __global__ void __launch_bounds__(256, 3) bn_act_bwd_reduce_vec_kernel(const T* 
         // sum at the end, so only three per-channel constants stay in registers
         float mu[V], A[V], Bc[V], s[V], sx[V];
 #pragma unroll
+        int chn[V];
         for (int j = 0; j < V; ++j) {
-            const float gj = gamma ? gamma[c0 + j] : 1.f, bj = beta ? beta[c0 + j] : 0.f;
-            mu[j] = mean[c0 + j];
-            A[j] = gj * rstd[c0 + j];
+            const int ch = (c0 + j) / ch_div;
+            chn[j] = ch < C ? ch : -1;
+            const int cc = ch < C ? ch : 0;
+            const float gj = gamma ? gamma[cc] : 1.f, bj = beta ? beta[cc] : 0.f;
+            mu[j] = mean[cc];
+            A[j] = gj * rstd[cc];
             Bc[j] = bj - mu[j] * A[j];
             s[j] = 0.f, sx[j] = 0.f;
         }
@@ -136,11 +148,11 @@ __global__ void __launch_bounds__(256, 3) bn_act_bwd_reduce_vec_kernel(const T* 
                 }
         }
 #pragma unroll
-        for (int j = 0; j < V; ++j) sx[j] *= rstd[c0 + j];
-#pragma unroll
         for (int j = 0; j < V; ++j) {
-            atomicAdd(&sh_dyn[c0 + j], s[j]);
-            atomicAdd(&sh_dyn[C + c0 + j], sx[j]);
+            if (chn[j] >= 0) {
+                atomicAdd(&sh_dyn[chn[j]], s[j]);
+                atomicAdd(&sh_dyn[C + chn[j]], sx[j] * rstd[chn[j]]);
+            }
         }
     }
     __syncthreads();
@@ -152,7 +164,8 @@ __global__ void __launch_bounds__(256, 3) bn_act_bwd_apply_vec_kernel(const T* _
                                                                   const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                   const float* __restrict__ dsums, float inv_count, T* __restrict__ dx,
-                                                                  long total_v, int CV, long stride_v, int C, int act, int train_stats) {
+                                                                  long total_v, int CV, long stride_v, int C, int ch_div, int act,
+                                                                  int train_stats) {
     constexpr int V = cnb_vec<T>::N;
     const long gid = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= stride_v) return;
@@ -161,12 +174,17 @@ __global__ void __launch_bounds__(256, 3) bn_act_bwd_apply_vec_kernel(const T* _
     float A[V], Bc[V], K1[V], Q[V];
 #pragma unroll
     for (int j = 0; j < V; ++j) {
-        const float gj = gamma ? gamma[c0 + j] : 1.f, bj = beta ? beta[c0 + j] : 0.f;
-        const float m = mean[c0 + j], r = rstd[c0 + j];
-        A[j] = gj * r;
-        Bc[j] = bj - m * A[j];
-        K1[j] = train_stats ? A[j] * r * dsums[C + c0 + j] * inv_count : 0.f;
-        Q[j] = train_stats ? m * K1[j] - A[j] * dsums[c0 + j] * inv_count : 0.f;
+        const int ch = (c0 + j) / ch_div;
+        if (ch < C) {
+            const float gj = gamma ? gamma[ch] : 1.f, bj = beta ? beta[ch] : 0.f;
+            const float m = mean[ch], r = rstd[ch];
+            A[j] = gj * r;
+            Bc[j] = bj - m * A[j];
+            K1[j] = train_stats ? A[j] * r * dsums[C + ch] * inv_count : 0.f;
+            Q[j] = train_stats ? m * K1[j] - A[j] * dsums[ch] * inv_count : 0.f;
+        } else {  // row padding: gradient zero (dy there must be finite)
+            A[j] = 0.f, Bc[j] = 0.f, K1[j] = 0.f, Q[j] = 0.f;
+        }
     }
     constexpr int U = 2;
     for (long i = gid; i < total_v; i += U * stride_v) {

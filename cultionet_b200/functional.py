@@ -106,13 +106,15 @@ class _Conv2dFn(torch.autograd.Function):
     """y = conv(cat(sources, channel), weight) + bias over pixel-major tensors; see ``cnb_conv2d_fwd``."""
 
     @staticmethod
-    def forward(ctx, weight, bias, kind, ksize, stride, pad, dil, transposed, out_hw, want_stats, *sources):
+    def forward(ctx, weight, bias, kind, ksize, stride, pad, dil, transposed, out_hw, want_stats, src_c, *sources):
         check_device(weight, bias, *sources)
         sources = [_contig(s) for s in sources]
         x0 = sources[0]
         dtype = x0.dtype
         B, Hin, Win = x0.shape[0], x0.shape[1], x0.shape[2]
-        src_channels = [s.shape[-1] for s in sources]
+        # logical channels per source; a source may carry row padding (last dim = pixel pitch > channels)
+        src_channels = list(src_c) if src_c is not None else [s.shape[-1] for s in sources]
+        assert all(c <= s.shape[-1] for c, s in zip(src_channels, sources))
         Ctot = sum(src_channels)
         KH = KW = ksize
         taps = KH * KW
@@ -163,7 +165,7 @@ class _Conv2dFn(torch.autograd.Function):
         need_w = ctx.needs_input_grad[0]
         need_b = has_bias and ctx.needs_input_grad[1]
         src_grads = [None] * len(sources)
-        need_src = [ctx.needs_input_grad[10 + i] for i in range(len(sources))]
+        need_src = [ctx.needs_input_grad[11 + i] for i in range(len(sources))]
 
         if any(need_src):
             # dgrad: the adjoint gather with the per-tap transposed weights [taps][Ctot][N]; one launch per source slice
@@ -172,7 +174,8 @@ class _Conv2dFn(torch.autograd.Function):
             coff = 0
             for i, (s, c) in enumerate(zip(sources, src_channels)):
                 if need_src[i]:
-                    dx = torch.empty_like(s)
+                    # a padded source gets zeros in its padding columns (the kernels only write the logical channels)
+                    dx = torch.empty_like(s) if s.shape[-1] == c else torch.zeros_like(s)
                     _launch_conv([dy], [N], wd, coff, wd.shape[2], Ctot * wd.shape[2], c, None, dx, dgeom, not transposed, dtype)
                     src_grads[i] = dx
                 coff += c
@@ -203,24 +206,24 @@ class _Conv2dFn(torch.autograd.Function):
         if need_b:
             db = torch.empty((N,), dtype=torch.float32, device=dev)
             call("cnb_bias_grad", ptr(dy), dy_pitch, B * Hout * Wout, N, ptr(db), 0, dtype_code(dtype), stream_ptr(dy))
-        return (dw, db, None, None, None, None, None, None, None, None, *src_grads)
+        return (dw, db, None, None, None, None, None, None, None, None, None, *src_grads)
 
 
 def conv2d(sources: Sequence[torch.Tensor], weight, bias=None, ksize=3, stride=1, pad=1, dil=1, want_stats: bool = False):
     """nn.Conv2d over the channel concatenation of ``sources`` (each ``[B,H,W,Cs]``).  With ``want_stats`` returns
     ``(y, sums)`` where ``sums`` is the ``[2, N]`` per-channel (sum, sum of squares) of ``y`` computed in the convolution epilogue,
     or an empty tensor when the shape took a kernel without that epilogue."""
-    return _Conv2dFn.apply(weight, bias, W_CONV, ksize, stride, pad, dil, False, None, want_stats, *sources)
+    return _Conv2dFn.apply(weight, bias, W_CONV, ksize, stride, pad, dil, False, None, want_stats, None, *sources)
 
 
 def conv_transpose2d(x: torch.Tensor, weight, bias=None, ksize=3, stride=2, pad=1, dil=1) -> torch.Tensor:
     """nn.ConvTranspose2d (output_padding=0): ``[B,H,W,C] -> [B,(H-1)s-2p+d(k-1)+1, ..., N]``."""
-    return _Conv2dFn.apply(weight, bias, W_CONVT, ksize, stride, pad, dil, True, None, False, x)
+    return _Conv2dFn.apply(weight, bias, W_CONVT, ksize, stride, pad, dil, True, None, False, None, x)
 
 
-def linear(x: torch.Tensor, weight, bias=None) -> torch.Tensor:
-    """nn.Linear over the channel axis of a pixel-major tensor."""
-    return _Conv2dFn.apply(weight, bias, W_LINEAR, 1, 1, 0, 1, False, None, False, x)
+def linear(x: torch.Tensor, weight, bias=None, in_features: Optional[int] = None) -> torch.Tensor:
+    """nn.Linear over the channel axis of a pixel-major tensor (``in_features`` < last dim: the rest is row padding)."""
+    return _Conv2dFn.apply(weight, bias, W_LINEAR, 1, 1, 0, 1, False, None, False, None if in_features is None else (in_features,), x)
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -237,7 +240,7 @@ class _BatchNormActFn(torch.autograd.Function):
         Cn = gamma.shape[0]
         st = stream_ptr(x)
         stats = torch.empty((6, Cn), dtype=torch.float32, device=dev)  # sum, sumsq, mean, rstd, scale, shift
-        count = P * (L // Cn)
+        count = P * ch_div  # elements per channel: ch_div columns of every row
         if training:
             if sums is not None and sums.numel() == 2 * Cn:
                 sums_ptr = ptr(_contig(sums))  # batch statistics came out of the convolution epilogue
@@ -409,7 +412,8 @@ def resize_bilinear(x: torch.Tensor, size) -> torch.Tensor:
 
 # ----------------------------------------------------------------------------------------------------------------
 class _PreTimeConvFn(torch.autograd.Function):
-    """Conv3d(C->C, (k,1,1), bias=False) over x[B,C,T,H,W] -> pixel-major u[B,H,W,C*T'] (column = c*T' + t')."""
+    """Conv3d(C->C, (k,1,1), bias=False) over x[B,C,T,H,W] -> pixel-major u[B,H,W,pitch] (column = c*T' + t'; pitch = C*T'
+    rounded up to 8, padding columns zero)."""
 
     @staticmethod
     def forward(ctx, x, w1, dtype):
@@ -421,8 +425,9 @@ class _PreTimeConvFn(torch.autograd.Function):
         B, Cn, Tn, H, W = x.shape
         k = w1.shape[2]
         Tp = Tn - k + 1
-        u = torch.empty((B, H, W, Cn * Tp), dtype=dtype, device=x.device)
-        call("cnb_pretime_conv_fwd", ptr(x), ptr(w1c), ptr(u), B, Cn, Tn, H, W, k, dtype_code(dtype), stream_ptr(x))
+        pitch = (Cn * Tp + 7) // 8 * 8  # 16-byte pixel rows in either dtype; the padding columns are written as zero
+        u = torch.empty((B, H, W, pitch), dtype=dtype, device=x.device)
+        call("cnb_pretime_conv_fwd", ptr(x), ptr(w1c), ptr(u), B, Cn, Tn, H, W, k, pitch, dtype_code(dtype), stream_ptr(x))
         ctx.save_for_backward(x, w1)
         return u
 
@@ -435,7 +440,7 @@ class _PreTimeConvFn(torch.autograd.Function):
         B, Cn, Tn, H, W = x.shape
         k = w1.shape[2]
         dw = torch.zeros(w1.shape, dtype=torch.float32, device=x.device)
-        call("cnb_pretime_conv_wgrad", ptr(x), ptr(du), ptr(dw), B, Cn, Tn, H, W, k, dtype_code(du.dtype), stream_ptr(x))
+        call("cnb_pretime_conv_wgrad", ptr(x), ptr(du), ptr(dw), B, Cn, Tn, H, W, k, du.shape[-1], dtype_code(du.dtype), stream_ptr(x))
         return None, dw, None
 
 

@@ -41,9 +41,10 @@ class Conv3d(nn.Module):
 
     def forward(self, x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
         conv1, bn1, conv2, bn2 = self.seq[0], self.seq[1], self.seq[3], self.seq[5]
-        u = F.pretime_conv(x, conv1.weight, dtype)  # [B,H,W,C*T'], column = c*T' + t'
+        u = F.pretime_conv(x, conv1.weight, dtype)  # [B,H,W,pitch >= C*T'], column = c*T' + t', zero row padding
         a = batchnorm_act(bn1, u, act=True, ch_div=self.remaining_time)
-        v = F.linear(a, conv2.weight.view(conv2.weight.shape[0], -1), None)
+        w2 = conv2.weight.view(conv2.weight.shape[0], -1)
+        v = F.linear(a, w2, None, in_features=w2.shape[1])
         return batchnorm_act(bn2, v, act=True)
 
 

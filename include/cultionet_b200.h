@@ -180,9 +180,11 @@ int cnb_resize_bilinear_bwd(const void* dy, void* dx, int B, int Hin, int Win, i
  * PreTimeReduction first stage (models/nunet.py:31-39): Conv3d(C->C,(k,1,1), bias=False) over x[B,C,T,H,W] fp32.
  *   u[p][c2*T' + t'] = sum_{c,dt} w1[c2][c][dt] * x[b,c,t'+dt,h,w],  T' = T-k+1, p = (b,h,w)
  * ------------------------------------------------------------------------------------------------ */
-int cnb_pretime_conv_fwd(const float* x, const float* w1, void* u, int B, int C, int T, int H, int W, int k, int dtype, void* stream);
+int cnb_pretime_conv_fwd(const float* x, const float* w1, void* u, int B, int C, int T, int H, int W, int k, int u_pitch, int dtype,
+                         void* stream);
 /* dw1 (fp32 [C][C][k]) is atomically accumulated: zero it first.  The network input needs no gradient. */
-int cnb_pretime_conv_wgrad(const float* x, const void* du, float* dw1, int B, int C, int T, int H, int W, int k, int dtype, void* stream);
+int cnb_pretime_conv_wgrad(const float* x, const void* du, float* dw1, int B, int C, int T, int H, int W, int k, int u_pitch, int dtype,
+                           void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * TowerUNetFinalCombine + SigmoidCrisp (nn/modules/unet_parts.py:86-98, :148-193)
