@@ -10,6 +10,7 @@
 #include "k_na.cuh"
 #include "k_norm.cuh"
 #include "k_vec.cuh"
+#include "k_stream.cuh"
 
 using namespace cnb;
 
@@ -22,6 +23,18 @@ using namespace cnb;
 static inline int stream_grid(long n, int per_block = 256, int waves = 8) {
     return cnb_clamp_grid(cnb_div_up(n, per_block), (long)CNB_NUM_SMS * waves);
 }
+
+#ifndef CNB_EMU
+// opt a streaming kernel into its dynamic shared memory once per process
+template <typename K>
+static inline bool stream_smem(K kfn, int bytes, bool* done) {
+    if (!*done) {
+        if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return false;
+        *done = true;
+    }
+    return true;
+}
+#endif
 
 static inline int vec_width(int dtype) { return dtype == CNB_BF16 ? 8 : 4; }
 // rows that split into whole 16-byte vectors (and per-CTA channel sums that fit in shared memory); column j belongs to channel
@@ -276,6 +289,18 @@ int cnb_bn_stats(const void* x, int64_t P, int L, int C, int ch_div, float* sums
     CNB_MEMSET_ASYNC(sums, 0, sizeof(float) * 2 * C, (cudaStream_t)stream);
     int blocks;
     const long total = (long)P * L;
+#ifndef CNB_EMU
+    if (st::eligible(L, C, ch_div, dtype, total / 8) && cnb_aligned16(x)) {
+        static bool cfg = false;
+        const int smem = (st::smem_bytes<1, st::S1>()) + 2 * C * (int)sizeof(float);
+        if (stream_smem(st::bn_stats_stream_kernel, (st::smem_bytes<1, st::S1>()) + 2 * 2048 * (int)sizeof(float), &cfg)) {
+            CNB_LAUNCH(st::bn_stats_stream_kernel, dim3(st::grid(total / 8)), dim3(st::THREADS), smem, (cudaStream_t)stream, (const bf16_t*)x,
+                       total / 8, L / 8, C, ch_div, sums);
+            CNB_CHECK_LAUNCH("bn_stats_stream_kernel");
+            return CNB_OK;
+        }
+    }
+#endif
     if (bn_vec_ok(L, C, ch_div, dtype) && cnb_aligned16(x)) {
         const int V = vec_width(dtype), CV = L / V;
         const long total_v = total / V;
@@ -310,6 +335,25 @@ int cnb_bn_act_fwd(const void* x, const float* scale, const float* shift, const 
                    int act, int dtype, void* stream) {
     CNB_REQUIRE(x && y && scale && shift && P > 0 && L > 0 && C > 0 && ch_div > 0, "bn_act_fwd: bad arguments");
     const long total = (long)P * L;
+#ifndef CNB_EMU
+    if (st::eligible(L, C, ch_div, dtype, total / 8) && cnb_aligned16(x) && cnb_aligned16(y) && cnb_aligned16(residual)) {
+        static bool cfg0 = false, cfg1 = false;
+        if (residual) {
+            if (stream_smem(st::bn_act_fwd_stream_kernel<true>, (st::smem_bytes<2, st::S2>()), &cfg1)) {
+                CNB_LAUNCH(st::bn_act_fwd_stream_kernel<true>, dim3(st::grid(total / 8)), dim3(st::THREADS), (st::smem_bytes<2, st::S2>()),
+                           (cudaStream_t)stream, (const bf16_t*)x, scale, shift, (const bf16_t*)residual, (bf16_t*)y, total / 8, L / 8, C, ch_div,
+                           act);
+                CNB_CHECK_LAUNCH("bn_act_fwd_stream_kernel<res>");
+                return CNB_OK;
+            }
+        } else if (stream_smem(st::bn_act_fwd_stream_kernel<false>, (st::smem_bytes<1, st::S1>()), &cfg0)) {
+            CNB_LAUNCH(st::bn_act_fwd_stream_kernel<false>, dim3(st::grid(total / 8)), dim3(st::THREADS), (st::smem_bytes<1, st::S1>()),
+                       (cudaStream_t)stream, (const bf16_t*)x, scale, shift, (const bf16_t*)nullptr, (bf16_t*)y, total / 8, L / 8, C, ch_div, act);
+            CNB_CHECK_LAUNCH("bn_act_fwd_stream_kernel");
+            return CNB_OK;
+        }
+    }
+#endif
     if (bn_vec_ok(L, C, ch_div, dtype) && cnb_aligned16(x) && cnb_aligned16(y) && cnb_aligned16(residual)) {
         const int V = vec_width(dtype), CV = L / V;
         int blocks;
@@ -336,6 +380,18 @@ int cnb_bn_act_bwd_reduce(const void* x, const void* dy, const float* save_mean,
     CNB_MEMSET_ASYNC(dsums, 0, sizeof(float) * 2 * C, (cudaStream_t)stream);
     int blocks;
     const long total = (long)P * L;
+#ifndef CNB_EMU
+    if (st::eligible(L, C, ch_div, dtype, total / 8) && cnb_aligned16(x) && cnb_aligned16(dy)) {
+        static bool cfg = false;
+        const int smem = (st::smem_bytes<2, st::S2>()) + 2 * C * (int)sizeof(float);
+        if (stream_smem(st::bn_act_bwd_reduce_stream_kernel, (st::smem_bytes<2, st::S2>()) + 2 * 2048 * (int)sizeof(float), &cfg)) {
+            CNB_LAUNCH(st::bn_act_bwd_reduce_stream_kernel, dim3(st::grid(total / 8)), dim3(st::THREADS), smem, (cudaStream_t)stream,
+                       (const bf16_t*)x, (const bf16_t*)dy, save_mean, save_rstd, gamma, beta, total / 8, L / 8, C, ch_div, act, dsums);
+            CNB_CHECK_LAUNCH("bn_act_bwd_reduce_stream_kernel");
+            return CNB_OK;
+        }
+    }
+#endif
     if (bn_vec_ok(L, C, ch_div, dtype) && cnb_aligned16(x) && cnb_aligned16(dy)) {
         const int V = vec_width(dtype), CV = L / V;
         const long total_v = total / V;
@@ -362,6 +418,18 @@ int cnb_bn_act_bwd_apply(const void* x, const void* dy, const float* save_mean, 
     CNB_REQUIRE(x && dy && dx && save_mean && save_rstd && dsums && count > 0 && P > 0 && L > 0 && C > 0 && ch_div > 0,
                 "bn_act_bwd_apply: bad arguments");
     const long total = (long)P * L;
+#ifndef CNB_EMU
+    if (st::eligible(L, C, ch_div, dtype, total / 8) && cnb_aligned16(x) && cnb_aligned16(dy) && cnb_aligned16(dx)) {
+        static bool cfg = false;
+        if (stream_smem(st::bn_act_bwd_apply_stream_kernel, (st::smem_bytes<2, st::S2>()), &cfg)) {
+            CNB_LAUNCH(st::bn_act_bwd_apply_stream_kernel, dim3(st::grid(total / 8)), dim3(st::THREADS), (st::smem_bytes<2, st::S2>()),
+                       (cudaStream_t)stream, (const bf16_t*)x, (const bf16_t*)dy, save_mean, save_rstd, gamma, beta, dsums,
+                       1.0f / (float)count, (bf16_t*)dx, total / 8, L / 8, C, ch_div, act, train_stats);
+            CNB_CHECK_LAUNCH("bn_act_bwd_apply_stream_kernel");
+            return CNB_OK;
+        }
+    }
+#endif
     if (bn_vec_ok(L, C, ch_div, dtype) && cnb_aligned16(x) && cnb_aligned16(dy) && cnb_aligned16(dx)) {
         const int V = vec_width(dtype), CV = L / V;
         int blocks;

@@ -59,6 +59,19 @@ def test_batchnorm(dev, dtype, training, act, res):
     cases.batchnorm_case(dev, dtype, 4, 50, 50, 96, training, act, res)
 
 
+@pytest.mark.parametrize("shape", [(4, 50, 50, 64), (3, 33, 31, 256), (2, 64, 64, 128), (5, 17, 19, 512), (2, 37, 41, 8)])
+@pytest.mark.parametrize("training,act,res", [(True, True, True), (True, True, False), (False, False, False)])
+def test_batchnorm_bulk_copy_streaming_shapes(dev, shape, training, act, res):
+    """bf16 shapes whose row length / 8 divides 256 take the bulk-copy ring kernels (k_stream.cuh); ragged last tiles included."""
+    cases.batchnorm_case(dev, BF16, *shape, training, act, res)
+
+
+def test_batchnorm3d_bulk_copy_streaming(dev):
+    cases.batchnorm3d_case(dev, BF16, 2, 40, 40, 5, 25)            # 125 columns: not a vector multiple, scalar kernel
+    cases.batchnorm3d_case(dev, BF16, 2, 40, 40, 4, 16)           # 64 columns: streaming kernel with ch_div = 16
+    cases.batchnorm3d_case(dev, BF16, 3, 33, 35, 8, 4)            # 32 columns, ch_div = 4
+
+
 def test_batchnorm_many_channels(dev):
     cases.batchnorm_case(dev, F32, 2, 13, 13, 1024)
 
