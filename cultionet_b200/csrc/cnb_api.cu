@@ -725,6 +725,35 @@ int cnb_pretime_conv_wgrad(const float* x, const void* du, float* dw1, int B, in
     return CNB_OK;
 }
 
+int cnb_time_to_pixel_major(const float* x, void* xp, int B, int CT, int64_t HW, int pitch, int dtype, void* stream) {
+    CNB_REQUIRE(x && xp && B > 0 && CT > 0 && HW > 0 && pitch >= CT, "time_to_pixel_major: bad arguments");
+    CNB_REQUIRE(pitch % vec_width(dtype) == 0 && cnb_aligned16(xp), "time_to_pixel_major: the pixel pitch must be whole 16-byte vectors");
+    const size_t smem = ((size_t)CT * TP_XPITCH + 3) / 4 * 4 * sizeof(float) + (size_t)TP_PIX * pitch * (dtype == CNB_BF16 ? 2 : 4);
+    CNB_REQUIRE(smem <= 200 * 1024, "time_to_pixel_major: C*T = %d does not fit the shared-memory tile", CT);
+    const long P = (long)B * HW;
+    dim3 grid(cnb_clamp_grid(cnb_div_up(P, TP_PIX), (long)CNB_NUM_SMS * 8));
+    CNB_DISPATCH_DTYPE(dtype, {
+        CNB_SET_SMEM((time_to_pixel_major_kernel<T>), smem);
+        CNB_LAUNCH((time_to_pixel_major_kernel<T>), grid, dim3(256), smem, (cudaStream_t)stream, x, (T*)xp, B, CT, (long)HW, pitch);
+    });
+    CNB_CHECK_LAUNCH("time_to_pixel_major_kernel");
+    return CNB_OK;
+}
+
+int cnb_toeplitz_expand(const float* w1, float* wt, int C, int T_, int k, int rows, void* stream) {
+    CNB_REQUIRE(w1 && wt && C > 0 && k > 0 && T_ >= k && rows >= C * (T_ - k + 1), "toeplitz_expand: bad arguments");
+    CNB_LAUNCH(toeplitz_expand_kernel, dim3(stream_grid((long)rows * C * T_)), dim3(256), 0, (cudaStream_t)stream, w1, wt, C, T_, k, rows);
+    CNB_CHECK_LAUNCH("toeplitz_expand_kernel");
+    return CNB_OK;
+}
+
+int cnb_toeplitz_fold(const float* dwt, float* dw1, int C, int T_, int k, void* stream) {
+    CNB_REQUIRE(dwt && dw1 && C > 0 && k > 0 && T_ >= k, "toeplitz_fold: bad arguments");
+    CNB_LAUNCH(toeplitz_fold_kernel, dim3(stream_grid((long)C * C * k)), dim3(256), 0, (cudaStream_t)stream, dwt, dw1, C, T_, k);
+    CNB_CHECK_LAUNCH("toeplitz_fold_kernel");
+    return CNB_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 int cnb_final_combine_fwd(const void* ha, const void* hb, const void* hc, const float* params, float smooth, int flags, float* distance,
                           float* edge, float* crop, int64_t P, int dtype, void* stream) {

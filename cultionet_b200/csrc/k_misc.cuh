@@ -233,6 +233,86 @@ __global__ void __launch_bounds__(PT_THREADS) pretime_conv_wgrad_kernel(const fl
 }
 
 // ---------------------------------------------------------------------------------------------
+// PreTimeReduction stage 1 as a GEMM (throughput mode).  The valid temporal convolution is a banded (Toeplitz) matrix product
+//   u[p][c2*T' + t'] = sum_{c,t} xp[p][c*T + t] * Wt[c2*T' + t'][c*T + t],   Wt[..][..] = w1[c2][c][t - t'] for 0 <= t - t' < k
+// so once x is pixel-major it is a 1x1 convolution with K = C*T that the tcgen05 kernels run in a few tens of microseconds
+// (13.8 GFLOP dense at cfg 2 instead of a shared-memory-bound SIMT loop), and ONE transposed copy of x serves both temporal
+// branches.  Three small kernels: the transpose, the expansion of w1 into Wt and the fold of dWt back onto dw1.
+// ---------------------------------------------------------------------------------------------
+constexpr int TP_PIX = 64;
+constexpr int TP_XPITCH = TP_PIX + 1;
+
+// x[B][CT][HW] fp32 -> xp[B*HW][pitch] (columns >= CT are zero).  dynamic smem: xs[CT][TP_XPITCH] floats, us[TP_PIX][pitch] of T
+template <typename T>
+__global__ void __launch_bounds__(256) time_to_pixel_major_kernel(const float* __restrict__ x, T* __restrict__ xp, int B, int CT, long HW,
+                                                                 int pitch) {
+    constexpr int V = cnb_vec<T>::N;
+    CNB_DYN_SMEM(sm_raw);
+    float* xs = reinterpret_cast<float*>(sm_raw);
+    T* us = reinterpret_cast<T*>(xs + ((long)CT * TP_XPITCH + 3) / 4 * 4);  // 16-byte aligned: whole-vector copies below
+    const long total = (long)B * HW;
+    const int groups = pitch / V;
+    for (long p0 = (long)blockIdx.x * TP_PIX; p0 < total; p0 += (long)gridDim.x * TP_PIX) {
+        __syncthreads();  // the previous tile has left shared memory
+        for (int i = threadIdx.x; i < CT * TP_PIX; i += blockDim.x) {
+            const int pp = i % TP_PIX, ct = i / TP_PIX;
+            const long p = p0 + pp;
+            float v = 0.f;
+            if (p < total) {
+                const long b = p / HW, hw = p - b * HW;
+                v = x[(b * CT + ct) * HW + hw];
+            }
+            xs[ct * TP_XPITCH + pp] = v;
+        }
+        __syncthreads();
+        // thread = (pixel, column group): lanes walk pixels, so the xs reads are conflict-free
+        for (int i = threadIdx.x; i < groups * TP_PIX; i += blockDim.x) {
+            const int pp = i % TP_PIX, g = i / TP_PIX;
+            float v[V];
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                const int ct = g * V + j;
+                v[j] = ct < CT ? xs[ct * TP_XPITCH + pp] : 0.f;
+            }
+            cnb_stv(us + (long)pp * pitch + g * V, v);
+        }
+        __syncthreads();
+        const long valid_px = total - p0 < TP_PIX ? total - p0 : TP_PIX;
+        const long nvec = valid_px * groups;
+        T* dst = xp + p0 * pitch;
+        for (long i = threadIdx.x; i < nvec; i += blockDim.x)
+            *reinterpret_cast<uint4*>(dst + i * V) = *reinterpret_cast<const uint4*>(us + i * V);
+    }
+}
+
+// Wt[n][c*T + t] (n < rows; rows past C*T' are zero)
+__global__ void __launch_bounds__(256) toeplitz_expand_kernel(const float* __restrict__ w1, float* __restrict__ wt, int C, int Tn, int k,
+                                                             int rows) {
+    const int Tp = Tn - k + 1, CT = C * Tn;
+    const int total = rows * CT;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int n = i / CT, kk = i - n * CT;
+        const int c2 = n / Tp, tp = n - c2 * Tp;
+        const int c = kk / Tn, t = kk - c * Tn;
+        const int dt = t - tp;
+        wt[i] = (c2 < C && dt >= 0 && dt < k) ? w1[(c2 * C + c) * k + dt] : 0.f;
+    }
+}
+
+// dw1[c2][c][dt] = sum_t' dWt[c2*T' + t'][c*T + t' + dt]
+__global__ void __launch_bounds__(256) toeplitz_fold_kernel(const float* __restrict__ dwt, float* __restrict__ dw1, int C, int Tn, int k) {
+    const int Tp = Tn - k + 1, CT = C * Tn;
+    const int total = C * C * k;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int dt = i % k, cc = i / k;
+        const int c = cc % C, c2 = cc / C;
+        float acc = 0.f;
+        for (int tp = 0; tp < Tp; ++tp) acc += dwt[(long)(c2 * Tp + tp) * CT + c * Tn + tp + dt];
+        dw1[i] = acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // TowerUNetFinalCombine (+ SigmoidCrisp).  params: g[3][3], w[3], b[3], crisp_gamma
 // ---------------------------------------------------------------------------------------------
 template <typename T>

@@ -448,6 +448,51 @@ def pretime_conv(x: torch.Tensor, w1: torch.Tensor, dtype: torch.dtype) -> torch
     return _PreTimeConvFn.apply(x, w1, dtype)
 
 
+def time_to_pixel_major(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """x[B,C,T,H,W] float32 -> pixel-major xp[B,H,W,pitch] (column = c*T + t; pitch = C*T rounded up to 8, padding zero).  The network
+    input carries no gradient, so this is a plain function."""
+    check_device(x)
+    if x.dtype != torch.float32:
+        raise _lib.CnbError("PreTimeReduction takes the float32 [B,C,T,H,W] input of the reference")
+    if x.requires_grad:
+        raise NotImplementedError("cultionet_b200: the network input x does not receive a gradient")
+    x = _contig(x)
+    B, Cn, Tn, H, W = x.shape
+    pitch = (Cn * Tn + 7) // 8 * 8
+    xp = torch.empty((B, H, W, pitch), dtype=dtype, device=x.device)
+    call("cnb_time_to_pixel_major", ptr(x), ptr(xp), B, Cn * Tn, H * W, pitch, dtype_code(dtype), stream_ptr(x))
+    return xp
+
+
+class _ToeplitzFn(torch.autograd.Function):
+    """w1[C,C,k,1,1] -> Wt[rows, C*T] with Wt[c2*T'+t'][c*T+t] = w1[c2,c,t-t'] (rows = C*T' rounded up to 8, padding rows zero)."""
+
+    @staticmethod
+    def forward(ctx, w1, Tn):
+        check_device(w1)
+        Cn, k = w1.shape[0], w1.shape[2]
+        rows = (Cn * (Tn - k + 1) + 7) // 8 * 8
+        wt = torch.empty((rows, Cn * Tn), dtype=torch.float32, device=w1.device)
+        call("cnb_toeplitz_expand", ptr(_contig(w1)), ptr(wt), Cn, Tn, k, rows, stream_ptr(w1))
+        ctx.meta = (Cn, Tn, k, tuple(w1.shape))
+        return wt
+
+    @staticmethod
+    def backward(ctx, dwt):
+        Cn, Tn, k, shape = ctx.meta
+        dwt = _contig(dwt.float())
+        dw = torch.empty(shape, dtype=torch.float32, device=dwt.device)
+        call("cnb_toeplitz_fold", ptr(dwt), ptr(dw), Cn, Tn, k, stream_ptr(dwt))
+        return dw, None
+
+
+def pretime_conv_gemm(xp: torch.Tensor, w1: torch.Tensor, in_time: int) -> torch.Tensor:
+    """The temporal convolution of ``pretime_conv`` over the pixel-major copy ``xp`` of x, as a 1x1 GEMM on the tensor cores:
+    returns u[B,H,W,rows] with the same column order and zero row padding as ``pretime_conv``."""
+    wt = _ToeplitzFn.apply(w1, in_time)
+    return linear(xp, wt, None, in_features=w1.shape[0] * in_time)
+
+
 # ----------------------------------------------------------------------------------------------------------------
 class _FinalCombineFn(torch.autograd.Function):
     """TowerUNetFinalCombine + SigmoidCrisp over the three towers' fused [B,H,W,3] streams; 16 scalar parameters."""

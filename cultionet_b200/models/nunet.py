@@ -39,9 +39,13 @@ class Conv3d(nn.Module):
             nn.SiLU(),
         )
 
-    def forward(self, x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, dtype: torch.dtype, xp: T.Optional[torch.Tensor] = None) -> torch.Tensor:
         conv1, bn1, conv2, bn2 = self.seq[0], self.seq[1], self.seq[3], self.seq[5]
-        u = F.pretime_conv(x, conv1.weight, dtype)  # [B,H,W,pitch >= C*T'], column = c*T' + t', zero row padding
+        # u: [B,H,W,pitch >= C*T'], column = c*T' + t', zero row padding
+        if xp is not None:  # throughput mode: banded GEMM over the pixel-major copy of x (tensor cores)
+            u = F.pretime_conv_gemm(xp, conv1.weight, x.shape[2])
+        else:
+            u = F.pretime_conv(x, conv1.weight, dtype)
         a = batchnorm_act(bn1, u, act=True, ch_div=self.remaining_time)
         w2 = conv2.weight.view(conv2.weight.shape[0], -1)
         v = F.linear(a, w2, None, in_features=w2.shape[1])
@@ -59,7 +63,9 @@ class PreTimeReduction(nn.Module):
 
     def forward(self, x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
         ln = self.layer_norm[1]
-        s = F.add_n(self.conv3(x, dtype), self.conv5(x, dtype))
+        # bf16: ONE pixel-major copy of x feeds both temporal branches, each a 1x1 GEMM; fp32 parity mode keeps the direct kernels
+        xp = F.time_to_pixel_major(x, dtype) if dtype == torch.bfloat16 else None
+        s = F.add_n(self.conv3(x, dtype, xp), self.conv5(x, dtype, xp))
         return F.layernorm(s, ln.weight, ln.bias, ln.eps)
 
 

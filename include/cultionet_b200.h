@@ -186,6 +186,13 @@ int cnb_pretime_conv_fwd(const float* x, const float* w1, void* u, int B, int C,
 int cnb_pretime_conv_wgrad(const float* x, const void* du, float* dw1, int B, int C, int T, int H, int W, int k, int u_pitch, int dtype,
                            void* stream);
 
+/* The same stage as a GEMM (throughput mode): x[B][C*T][H*W] fp32 -> pixel-major xp[B*H*W][pitch] (columns >= C*T zero), shared
+ * by both temporal branches; Wt[rows][C*T] = banded expansion of w1 (rows >= C*T' zero) so that u = xp * Wt^T is cnb_conv2d_fwd
+ * with a 1x1 kernel; cnb_toeplitz_fold maps the GEMM's weight gradient dWt[rows][C*T] back onto dw1[C][C][k] (overwritten). */
+int cnb_time_to_pixel_major(const float* x, void* xp, int B, int CT, int64_t HW, int pitch, int dtype, void* stream);
+int cnb_toeplitz_expand(const float* w1, float* wt, int C, int T, int k, int rows, void* stream);
+int cnb_toeplitz_fold(const float* dwt, float* dw1, int C, int T, int k, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * TowerUNetFinalCombine + SigmoidCrisp (nn/modules/unet_parts.py:86-98, :148-193)
  *   z_t = w_t * (ha[p][t]/g[t][0] + hb[p][t]/g[t][1] + hc[p][t]/g[t][2]) + b_t,  t in {0 distance, 1 edge, 2 crop}

@@ -183,6 +183,29 @@ def pretime_case(dev, dtype, B, C, T, H, W, k, seed=0):
     _check("pretime wgrad", torch.autograd.grad(u, w1, gp.to(dtype))[0], torch.autograd.grad(ur, w1, g.to(dtype).float())[0], tol)
 
 
+def pretime_gemm_case(dev, dtype, B, C, T, H, W, k, seed=0):
+    """The banded-GEMM form of the temporal convolution (throughput mode) against torch's conv3d."""
+    torch.manual_seed(seed)
+    x = torch.randn(B, C, T, H, W, device=dev)
+    w1 = torch.randn(C, C, k, 1, 1, device=dev, requires_grad=True)
+    xp = F.time_to_pixel_major(x, dtype)
+    CT, Tp = C * T, T - k + 1
+    assert xp.shape[-1] % 8 == 0 and xp.shape[-1] >= CT
+    xr = x.to(dtype).float()  # the GEMM reads x in the compute dtype
+    _check("time->pixel major", xp[..., :CT], xr.permute(0, 3, 4, 1, 2).reshape(B, H, W, CT), 1e-7)
+    assert float(xp[..., CT:].float().abs().sum()) == 0.0
+    u = F.pretime_conv_gemm(xp, w1, T)
+    ur = TF.conv3d(xr, w1).permute(0, 3, 4, 1, 2).reshape(B, H, W, C * Tp)
+    tol = _tol(dtype)
+    assert u.shape[-1] % 8 == 0 and u.shape[-1] >= C * Tp
+    assert float(u[..., C * Tp:].float().abs().sum()) == 0.0  # row padding is zero
+    _check("pretime gemm fwd", u[..., :C * Tp], ur, tol)
+    g = torch.randn_like(ur)
+    gp = torch.zeros_like(u, dtype=torch.float32)
+    gp[..., :C * Tp] = g
+    _check("pretime gemm wgrad", torch.autograd.grad(u, w1, gp.to(dtype))[0], torch.autograd.grad(ur, w1, g.to(dtype).float())[0], tol)
+
+
 def final_combine_case(dev, dtype, B, H, W, edge_activation=True, mask_activation=True, seed=0):
     torch.manual_seed(seed)
     hs = [_mk((B, H, W, 3), dev, dtype) for _ in range(3)]

@@ -105,6 +105,13 @@ def test_pretime_conv(dev, k):
     cases.pretime_case(dev, BF16, 2, 3, 12, 20, 20, k)
 
 
+@pytest.mark.parametrize("k", [3, 5])
+def test_pretime_conv_as_banded_gemm(dev, k):
+    cases.pretime_gemm_case(dev, BF16, 2, 5, 24, 32, 32, k)   # cfg 2 channel/time geometry (K = 120)
+    cases.pretime_gemm_case(dev, BF16, 3, 3, 12, 25, 13, k)   # cfg 1 geometry (K = 36 -> pitch 40), ragged pixel tiles
+    cases.pretime_gemm_case(dev, F32, 2, 3, 12, 20, 20, k)
+
+
 @pytest.mark.parametrize("flags", [(True, True), (False, False)])
 def test_final_combine(dev, flags):
     cases.final_combine_case(dev, F32, 4, 100, 100, *flags)

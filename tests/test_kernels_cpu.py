@@ -81,6 +81,12 @@ def test_pretime_conv(dev, k):
     cases.pretime_case(dev, F32, 2, 3, 12, 5, 6, k)
 
 
+@pytest.mark.parametrize("k", [3, 5])
+def test_pretime_conv_as_banded_gemm(dev, k):
+    cases.pretime_gemm_case(dev, F32, 2, 3, 12, 5, 6, k)
+    cases.pretime_gemm_case(dev, torch.bfloat16, 1, 5, 10, 9, 8, k)  # K = 50 -> pitch 56; 72 pixels = one full + one ragged tile
+
+
 @pytest.mark.parametrize("flags", [(True, True), (False, False)])
 def test_final_combine(dev, flags):
     cases.final_combine_case(dev, F32, 2, 6, 7, *flags)
