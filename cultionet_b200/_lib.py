@@ -97,7 +97,8 @@ _PROTOS = {
     "cnb_layernorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp],
     "cnb_na2d_tiled_eligible": [_i, _i, _i, _i, _i, _i, _i, _i],
     "cnb_na2d_fwd": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp],
-    "cnb_na2d_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp],
+    "cnb_na2d_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp],
+    "cnb_na2d_bwd_workspace_floats": [_i, _i, _i, _i, _i, _i, _i, _i],
     "cnb_resize_bilinear_fwd": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "cnb_resize_bilinear_bwd": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "cnb_pretime_conv_fwd": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
@@ -127,7 +128,7 @@ def _bind(lib) -> None:
     for name, argtypes in _PROTOS.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
-        fn.restype = C.c_int
+        fn.restype = C.c_int64 if name.endswith("_workspace_floats") else C.c_int
     for name, argtypes in _CUDA_ONLY_PROTOS.items():
         if hasattr(lib, name):
             fn = getattr(lib, name)

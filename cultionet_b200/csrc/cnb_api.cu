@@ -8,6 +8,7 @@
 #include "k_loss.cuh"
 #include "k_misc.cuh"
 #include "k_na.cuh"
+#include "k_na_fast.cuh"
 #include "k_norm.cuh"
 #include "k_vec.cuh"
 #include "k_stream.cuh"
@@ -580,6 +581,41 @@ static bool na_tile_setup(int B, int H, int W, int heads, int hd, int ksize, int
         }                                                            \
     } while (0)
 
+// launch a `template <int KS, int DIL, int LPH>` specialised NA kernel (naf::eligible shapes only)
+#define CNB_NAF_LAUNCH_KDL(KERNEL, KSV, DILV, LPHV, ...)                                                             \
+    do {                                                                                                             \
+        CNB_SET_SMEM((KERNEL<KSV, DILV, LPHV>), smem);                                                               \
+        CNB_LAUNCH((KERNEL<KSV, DILV, LPHV>), grid, dim3(NA_TILE_THREADS), smem, (cudaStream_t)stream, __VA_ARGS__); \
+    } while (0)
+#define CNB_NAF_LAUNCH_KD(KERNEL, KSV, DILV, ...)                                   \
+    do {                                                                            \
+        if (lph == 8)                                                               \
+            CNB_NAF_LAUNCH_KDL(KERNEL, KSV, DILV, 8, __VA_ARGS__);                  \
+        else                                                                        \
+            CNB_NAF_LAUNCH_KDL(KERNEL, KSV, DILV, 4, __VA_ARGS__);                  \
+    } while (0)
+#define CNB_NAF_LAUNCH(KERNEL, ...)                                                 \
+    do {                                                                            \
+        if (ksize == 3 && dilation == 1)                                            \
+            CNB_NAF_LAUNCH_KD(KERNEL, 3, 1, __VA_ARGS__);                           \
+        else if (ksize == 3)                                                        \
+            CNB_NAF_LAUNCH_KD(KERNEL, 3, 2, __VA_ARGS__);                           \
+        else if (dilation == 1)                                                     \
+            CNB_NAF_LAUNCH_KD(KERNEL, 7, 1, __VA_ARGS__);                           \
+        else                                                                        \
+            CNB_NAF_LAUNCH_KD(KERNEL, 7, 2, __VA_ARGS__);                           \
+    } while (0)
+
+int64_t cnb_na2d_bwd_workspace_floats(int B, int H, int W, int heads, int hd, int ksize, int dilation, int dtype) {
+    if (check_na(B, H, W, heads, hd, ksize, dilation)) return 0;
+    NaTile g;
+    int lph;
+    size_t smem;
+    if (!naf::eligible(hd, ksize, dilation, dtype) || !na_tile_setup(B, H, W, heads, hd, ksize, dilation, 1.f, dtype, false, &g, &lph, &smem))
+        return 0;
+    return (int64_t)B * H * W * heads * ksize * ksize * 2;
+}
+
 int cnb_na2d_tiled_eligible(int B, int H, int W, int heads, int hd, int ksize, int dilation, int dtype) {
     if (check_na(B, H, W, heads, hd, ksize, dilation)) return 0;
     NaTile g;
@@ -599,6 +635,11 @@ int cnb_na2d_fwd(const void* qkv, void* out, float* lse, int B, int H, int W, in
     if (lse && cnb_aligned16(qkv) && cnb_aligned16(out) &&
         na_tile_setup(B, H, W, heads, hd, ksize, dilation, scale, dtype, false, &g, &lph, &smem)) {
         const dim3 grid(B * g.tiles_y * g.tiles_x, heads);
+        if (naf::eligible(hd, ksize, dilation, dtype)) {
+            CNB_NAF_LAUNCH(naf::na2d_fwd_fast_kernel, (const bf16_t*)qkv, (bf16_t*)out, lse, g);
+            CNB_CHECK_LAUNCH("na2d_fwd_fast_kernel");
+            return CNB_OK;
+        }
         CNB_NA_LAUNCH(na2d_fwd_tile_kernel, (const T*)qkv, (T*)out, lse, g);
         CNB_CHECK_LAUNCH("na2d_fwd_tile_kernel");
         return CNB_OK;
@@ -612,8 +653,8 @@ int cnb_na2d_fwd(const void* qkv, void* out, float* lse, int B, int H, int W, in
     return CNB_OK;
 }
 
-int cnb_na2d_bwd(const void* qkv, const void* dout, const void* out, const float* lse, float* dvec, float* dqkv_acc, void* dqkv, int B, int H,
-                 int W, int heads, int hd, int ksize, int dilation, float scale, int dtype, void* stream) {
+int cnb_na2d_bwd(const void* qkv, const void* dout, const void* out, const float* lse, float* dvec, float* dqkv_acc, float* pds_ws, void* dqkv,
+                 int B, int H, int W, int heads, int hd, int ksize, int dilation, float scale, int dtype, void* stream) {
     int rc = check_na(B, H, W, heads, hd, ksize, dilation);
     if (rc) return rc;
     CNB_REQUIRE(qkv && dout && dqkv, "na2d_bwd: null pointer");
@@ -623,6 +664,15 @@ int cnb_na2d_bwd(const void* qkv, const void* dout, const void* out, const float
     if (out && lse && dvec && cnb_aligned16(qkv) && cnb_aligned16(dout) && cnb_aligned16(out) && cnb_aligned16(dqkv) &&
         na_tile_setup(B, H, W, heads, hd, ksize, dilation, scale, dtype, true, &g, &lph, &smem)) {
         const dim3 grid(B * g.tiles_y * g.tiles_x, heads);
+        if (pds_ws && naf::eligible(hd, ksize, dilation, dtype)) {
+            // the staged rows are k|v (query pass) or q|dout (key pass); no per-pixel statistics ride along
+            smem = (size_t)g.RH * g.RW * 2 * hd * 2;
+            CNB_NAF_LAUNCH(naf::na2d_bwd_dq_fast_kernel, (const bf16_t*)qkv, (const bf16_t*)dout, (const bf16_t*)out, lse, (float2*)pds_ws,
+                           (bf16_t*)dqkv, g);
+            CNB_NAF_LAUNCH(naf::na2d_bwd_dkv_fast_kernel, (const bf16_t*)qkv, (const bf16_t*)dout, (const float2*)pds_ws, (bf16_t*)dqkv, g);
+            CNB_CHECK_LAUNCH("na2d_bwd_fast_kernels");
+            return CNB_OK;
+        }
         CNB_NA_LAUNCH(na2d_bwd_dq_tile_kernel, (const T*)qkv, (const T*)dout, (const T*)out, lse, dvec, (T*)dqkv, g);
         CNB_NA_LAUNCH(na2d_bwd_dkv_tile_kernel, (const T*)qkv, (const T*)dout, lse, (const float*)dvec, (T*)dqkv, g);
         CNB_CHECK_LAUNCH("na2d_bwd_tile_kernels");

@@ -372,8 +372,11 @@ class _NA2DFn(torch.autograd.Function):
             acc = torch.empty(qkv.shape, dtype=torch.float32, device=qkv.device)
         B, H, W, _ = qkv.shape
         dqkv = torch.empty_like(qkv)
-        call("cnb_na2d_bwd", ptr(qkv), ptr(dout), ptr(out), ptr(lse), ptr(dvec), ptr(acc), ptr(dqkv), B, H, W, heads, hd, ksize, dilation,
-             scale, dtype_code(qkv.dtype), stream_ptr(qkv))
+        # specialised shapes keep (p, scaled dlogit) per (pixel, head, neighbour) between the query-side and key-side passes
+        nws = int(_lib.lib().cnb_na2d_bwd_workspace_floats(B, H, W, heads, hd, ksize, dilation, dtype_code(qkv.dtype))) if tiled else 0
+        pds = torch.empty((nws,), dtype=torch.float32, device=qkv.device) if nws > 0 else None
+        call("cnb_na2d_bwd", ptr(qkv), ptr(dout), ptr(out), ptr(lse), ptr(dvec), ptr(acc), ptr(pds), ptr(dqkv), B, H, W, heads, hd, ksize,
+             dilation, scale, dtype_code(qkv.dtype), stream_ptr(qkv))
         return dqkv, None, None, None, None
 
 

@@ -167,8 +167,12 @@ int cnb_na2d_fwd(const void* qkv, void* out, float* lse, int B, int H, int W, in
 /* tiled path: needs out (the forward result), lse and dvec (fp32 [B,H,W,heads] scratch); dqkv_acc may be NULL.
  * warp path:  needs dqkv_acc, fp32 [B,H,W,3*heads*hd] scratch (zeroed inside); out/lse/dvec may be NULL.
  * dqkv: [B,H,W,3*heads*hd] in `dtype`. */
-int cnb_na2d_bwd(const void* qkv, const void* dout, const void* out, const float* lse, float* dvec, float* dqkv_acc, void* dqkv,
-                 int B, int H, int W, int heads, int hd, int ksize, int dilation, float scale, int dtype, void* stream);
+int cnb_na2d_bwd(const void* qkv, const void* dout, const void* out, const float* lse, float* dvec, float* dqkv_acc, float* pds_ws,
+                 void* dqkv, int B, int H, int W, int heads, int hd, int ksize, int dilation, float scale, int dtype, void* stream);
+/* Specialised backward (bf16, kernel 3 or 7, dilation 1 or 2, head_dim 32 or 64): the query-side pass stores the attention
+ * probabilities and their scaled logit gradients so that the key-side pass is a pure gather.  Returns the number of fp32 elements
+ * of that scratch (pds_ws: [B,H,W,heads,k*k,2]) or 0 when the shape takes the generic kernels (pds_ws may then be NULL). */
+int64_t cnb_na2d_bwd_workspace_floats(int B, int H, int W, int heads, int hd, int ksize, int dilation, int dtype);
 
 /* ------------------------------------------------------------------------------------------------
  * Bilinear resize, align_corners=True, pixel-major (check_upsample, nn/functional.py:72-81)
