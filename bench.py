@@ -55,6 +55,7 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch override")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying the captured CUDA graph")
     return ap.parse_args()
 
 
@@ -197,7 +198,7 @@ def main() -> None:
     torch.manual_seed(1234)  # identical replicas
     model = CultionetLitModel(in_channels=w["C"], in_time=w["T"], hidden_channels=w["hidden"], dilations=w["dilations"], dropout=0.0,
                               compute_dtype=dtype).to(dev)
-    step = TrainStep(model, total_steps=10_000)
+    step = TrainStep(model, total_steps=10_000, cuda_graph=not args.no_graph)
     hx, hy, hb = make_host_batch(w, B, rank, pin=True)
     dbatch = cb.Data(x=hx.to(dev), y=hy.to(dev), bdist=hb.to(dev))
     h2d_bytes = hx.numel() * hx.element_size() + hy.numel() * hy.element_size() + hb.numel() * hb.element_size()
@@ -210,13 +211,17 @@ def main() -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_enqueue_ms = []  # host time to ENQUEUE one step (no synchronisation): below the device time = the GPU is the bottleneck
+
     def timed(fn, n) -> float:
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        t_host = time.perf_counter()
         for _ in range(n):
             fn()
             flush.zero_()
+        host_enqueue_ms.append((time.perf_counter() - t_host) * 1e3 / n)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -244,13 +249,16 @@ def main() -> None:
         loss = step(b)
         losses.append(float(loss.cpu()))  # D2H read of the step's result
 
-    for _ in range(max(args.warmup, 3)):
+    # warm-up: at least 3 steps; in graph mode a few more so that the timed region only replays (3 eager + capture + 2 replays)
+    for _ in range(max(args.warmup, 3) + (3 if step.cuda_graph else 0)):
         resident_step()
     sampler = ClockSampler(local)
     sampler.start()
     l0 = _lib.launch_count()
     ms_res = timed(resident_step, args.steps)
     launches = (_lib.launch_count() - l0) // max(args.steps, 1)
+    if step.cuda_graph and step.launches_per_step:
+        launches = step.launches_per_step  # a replay repeats the launches recorded at capture; the host-side counter does not see them
     clocks = sampler.stop()
     e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
@@ -321,10 +329,12 @@ def main() -> None:
                                    f"x=[{B},{w['C']},{w['T']},{w['H']},{w['W']}] per GPU, hidden {w['hidden']}, dilations {w['dilations']}, dropout 0",
                        "global_batch": B * world, "parallelism": f"dp{world}", "l2": "256 MB flush buffer written between timed steps "
                        "(its time subtracted); per-step activations exceed L2",
-                       "train_gflop_per_chip": 3 * w["fwd_gflop_per_chip"]},
+                       "train_gflop_per_chip": 3 * w["fwd_gflop_per_chip"],
+                       "execution": "one CUDA graph per step (captured after 3 eager steps), replayed" if step.cuda_graph
+                       else "eager launches through the C ABI"},
             "e2e": {"value": e2e_value, "unit": "chips/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_base,
+            "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_enqueue_ms[0] if host_enqueue_ms else None, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_base,
             "model_tflops": 3 * w["fwd_gflop_per_chip"] * 1e9 * value / 1e12 if w["fwd_gflop_per_chip"] else None,
             "final_loss": float(losses[-1]),
         }

@@ -85,11 +85,13 @@ _PROTOS = {
     "cnb_conv2d_wgrad_tiny": [C.POINTER(WgradDesc), _i, _vp],
     "cnb_repitch": [_vp, _i, _vp, _i, _i64, _i, _i, _vp],
     "cnb_pack_weight": [_vp, _vp, _i, _i, _i, _i, _i, _i64, _i64, _i64, _vp],
+    "cnb_pack_weight2": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i64, _i64, _i64, _vp],
     "cnb_unpack_wgrad": [_vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i, _vp],
     "cnb_bias_grad": [_vp, _i, _i64, _i, _vp, _i, _i, _vp],
     "cnb_bn_stats": [_vp, _i64, _i, _i, _i, _vp, _i, _vp],
     "cnb_bn_finalize": [_vp, _i64, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "cnb_bn_act_fwd": [_vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp],
+    "cnb_bn_train_fwd": [_vp, _vp, _i64, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp],
     "cnb_bn_act_bwd_reduce": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _i, _vp],
     "cnb_bn_act_bwd_apply": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _i, _vp],
     "cnb_add_n": [_vp, _vp, _vp, _vp, _vp, _i64, _i, _vp],

@@ -251,8 +251,30 @@ int cnb_pack_weight(const float* w, void* wp, int dtype, int taps, int N, int K,
     return CNB_OK;
 }
 
+int cnb_pack_weight2(const float* w, void* wp, void* wd, int dtype, int taps, int N, int K, int pitch_k, int pitch_n, int64_t s_n,
+                     int64_t s_k, int64_t s_tap, void* stream) {
+    CNB_REQUIRE(w && wp && taps > 0 && taps <= 32 && N > 0 && K > 0 && pitch_k >= K && (!wd || pitch_n >= N), "pack_weight2: bad arguments");
+    const size_t smem = (size_t)taps * PW_T * (PW_T + 1) * sizeof(float);
+    const dim3 grid(cnb_div_up(pitch_k > K ? pitch_k : K, PW_T), cnb_div_up(wd && pitch_n > N ? pitch_n : N, PW_T));
+    CNB_DISPATCH_DTYPE(dtype, {
+        CNB_SET_SMEM((pack_weight_tiled_kernel<T>), smem);
+        CNB_LAUNCH((pack_weight_tiled_kernel<T>), grid, dim3(256), smem, (cudaStream_t)stream, w, (T*)wp, (T*)wd, taps, N, K, pitch_k, pitch_n,
+                   (long)s_n, (long)s_k, (long)s_tap);
+    });
+    CNB_CHECK_LAUNCH("pack_weight_tiled_kernel");
+    return CNB_OK;
+}
+
 int cnb_unpack_wgrad(const float* dwp, float* g, int taps, int N, int K, int64_t s_n, int64_t s_k, int64_t s_tap, int accumulate, void* stream) {
     CNB_REQUIRE(dwp && g && taps > 0 && N > 0 && K > 0, "unpack_wgrad: bad arguments");
+    if (taps <= 32) {
+        const size_t smem = (size_t)taps * PW_T * (PW_T + 1) * sizeof(float);
+        CNB_SET_SMEM(unpack_wgrad_tiled_kernel, smem);
+        CNB_LAUNCH(unpack_wgrad_tiled_kernel, dim3(cnb_div_up(K, PW_T), cnb_div_up(N, PW_T)), dim3(256), smem, (cudaStream_t)stream, dwp, g, taps,
+                   N, K, (long)s_n, (long)s_k, (long)s_tap, accumulate);
+        CNB_CHECK_LAUNCH("unpack_wgrad_tiled_kernel");
+        return CNB_OK;
+    }
     const long total = (long)taps * N * K;
     CNB_LAUNCH(unpack_wgrad_kernel, dim3(stream_grid(total)), dim3(256), 0, (cudaStream_t)stream, dwp, g, taps, N, K, (long)s_n, (long)s_k,
                (long)s_tap, accumulate);
@@ -373,6 +395,38 @@ int cnb_bn_act_fwd(const void* x, const float* scale, const float* shift, const 
     });
     CNB_CHECK_LAUNCH("bn_act_fwd_kernel");
     return CNB_OK;
+}
+
+int cnb_bn_train_fwd(const void* x, const float* sums, int64_t count, const float* gamma, const float* beta, float eps, float momentum,
+                     float* running_mean, float* running_var, float* save_mean, float* save_rstd, float* scale, float* shift,
+                     const void* residual, void* y, int64_t P, int L, int C, int ch_div, int act, int dtype, void* stream) {
+    CNB_REQUIRE(x && y && sums && save_mean && save_rstd && scale && shift && count > 0 && P > 0 && L > 0 && C > 0 && ch_div > 0,
+                "bn_train_fwd: bad arguments");
+    CNB_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "bn_train_fwd: running statistics come in pairs");
+#ifndef CNB_EMU
+    const long total = (long)P * L;
+    if (st::eligible(L, C, ch_div, dtype, total / 8) && cnb_aligned16(x) && cnb_aligned16(y) && cnb_aligned16(residual)) {
+        static bool cfg0 = false, cfg1 = false;
+        if (residual) {
+            if (stream_smem(st::bn_train_fwd_stream_kernel<true>, (st::smem_bytes<2, st::S2>()), &cfg1)) {
+                CNB_LAUNCH(st::bn_train_fwd_stream_kernel<true>, dim3(st::grid(total / 8)), dim3(st::THREADS), (st::smem_bytes<2, st::S2>()),
+                           (cudaStream_t)stream, (const bf16_t*)x, sums, (long)count, gamma, beta, eps, momentum, running_mean, running_var,
+                           save_mean, save_rstd, scale, shift, (const bf16_t*)residual, (bf16_t*)y, total / 8, L / 8, C, ch_div, act);
+                CNB_CHECK_LAUNCH("bn_train_fwd_stream_kernel<res>");
+                return CNB_OK;
+            }
+        } else if (stream_smem(st::bn_train_fwd_stream_kernel<false>, (st::smem_bytes<1, st::S1>()), &cfg0)) {
+            CNB_LAUNCH(st::bn_train_fwd_stream_kernel<false>, dim3(st::grid(total / 8)), dim3(st::THREADS), (st::smem_bytes<1, st::S1>()),
+                       (cudaStream_t)stream, (const bf16_t*)x, sums, (long)count, gamma, beta, eps, momentum, running_mean, running_var,
+                       save_mean, save_rstd, scale, shift, (const bf16_t*)nullptr, (bf16_t*)y, total / 8, L / 8, C, ch_div, act);
+            CNB_CHECK_LAUNCH("bn_train_fwd_stream_kernel");
+            return CNB_OK;
+        }
+    }
+#endif
+    int rc = cnb_bn_finalize(sums, count, C, gamma, beta, eps, momentum, running_mean, running_var, save_mean, save_rstd, scale, shift, stream);
+    if (rc) return rc;
+    return cnb_bn_act_fwd(x, scale, shift, residual, y, P, L, C, ch_div, act, dtype, stream);
 }
 
 int cnb_bn_act_bwd_reduce(const void* x, const void* dy, const float* save_mean, const float* save_rstd, const float* gamma, const float* beta,
@@ -716,6 +770,18 @@ int cnb_resize_bilinear_fwd(const void* x, void* y, int B, int Hin, int Win, int
 int cnb_resize_bilinear_bwd(const void* dy, void* dx, int B, int Hin, int Win, int Hout, int Wout, int C, int dtype, void* stream) {
     CNB_REQUIRE(dy && dx && B > 0 && Hin > 0 && Win > 0 && Hout > 0 && Wout > 0 && C > 0, "resize_bilinear_bwd: bad arguments");
     const long total = (long)B * Hin * Win * C;
+    const float rh_ = align_corners_scale(Hin, Hout), rw_ = align_corners_scale(Win, Wout);
+    if (C % vec_width(dtype) == 0 && cnb_aligned16(dy) && cnb_aligned16(dx) && rh_ >= 0.5f && rw_ >= 0.5f && Win <= 4096) {
+        // scale >= 0.5: at most RB_NC outputs read an input index per axis (support of length 2/scale <= 4)
+        const size_t smem = (size_t)Win * (1 + RB_NC) * 4 + (1 + RB_NC) * 4;
+        CNB_DISPATCH_DTYPE(dtype, {
+            CNB_SET_SMEM((resize_bilinear_bwd_tab_kernel<T>), smem);
+            CNB_LAUNCH((resize_bilinear_bwd_tab_kernel<T>), dim3(B * Hin), dim3(256), smem, (cudaStream_t)stream, (const T*)dy, (T*)dx, B, Hin,
+                       Win, Hout, Wout, C, rh_, rw_);
+        });
+        CNB_CHECK_LAUNCH("resize_bilinear_bwd_tab_kernel");
+        return CNB_OK;
+    }
     if (C % vec_width(dtype) == 0 && cnb_aligned16(dy) && cnb_aligned16(dx)) {
         CNB_DISPATCH_DTYPE(dtype, {
             CNB_LAUNCH((resize_bilinear_bwd_vec_kernel<T>), dim3(B * Hin), dim3(256), 0, (cudaStream_t)stream,

@@ -225,6 +225,72 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, float* __rest
     }
 }
 
+// Tiled forms of the two kernels above.  A CTA owns a 32 (n) x 32 (k) tile of the parameter for all taps in shared memory, reads
+// the fp32 parameter in ITS memory order (the innermost pair of (n, k) and the taps are contiguous floats) and writes BOTH packed
+// layouts -- forward [tap][N][k-pitch] and data-gradient [tap][K][n-pitch] -- with the fastest index across the lanes, so the
+// parameter is read once per step instead of twice and no access is a 36-byte-strided scalar (the flat kernels: 8x sector
+// over-fetch on the gather, one launch per layout).  Padding columns (k >= K resp. n >= N up to the pitch) are written as zero.
+constexpr int PW_T = 32;
+template <typename T>
+__global__ void __launch_bounds__(256) pack_weight_tiled_kernel(const float* __restrict__ w, T* __restrict__ wp, T* __restrict__ wd, int taps,
+                                                               int N, int K, int pitch_k, int pitch_n, long s_n, long s_k, long s_tap) {
+    CNB_DYN_SMEM(sm_raw);  // float tile[taps][PW_T][PW_T + 1]
+    float* tile = reinterpret_cast<float*>(sm_raw);
+    const int n0 = blockIdx.y * PW_T, k0 = blockIdx.x * PW_T;
+    const int per = PW_T * taps;  // contiguous floats per outer index when s_tap == 1 and the inner stride == taps
+    const bool k_inner = s_k <= s_n;
+    for (int i = threadIdx.x; i < PW_T * per; i += blockDim.x) {
+        const int outer = i / per, rem = i - outer * per;
+        const int inner = rem / taps, tap = rem - inner * taps;
+        const int nl = k_inner ? outer : inner, kl = k_inner ? inner : outer;
+        const int n = n0 + nl, k = k0 + kl;
+        tile[(tap * PW_T + nl) * (PW_T + 1) + kl] = (n < N && k < K) ? w[n * s_n + k * s_k + tap * s_tap] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < taps * PW_T * PW_T; i += blockDim.x) {
+        const int kl = i % PW_T, t = i / PW_T;
+        const int nl = t % PW_T, tap = t / PW_T;
+        const int n = n0 + nl, k = k0 + kl;
+        if (n < N && k < pitch_k) cnb_st(wp + ((long)tap * N + n) * pitch_k + k, tile[(tap * PW_T + nl) * (PW_T + 1) + kl]);
+    }
+    if (wd) {
+        for (int i = threadIdx.x; i < taps * PW_T * PW_T; i += blockDim.x) {
+            const int nl = i % PW_T, t = i / PW_T;
+            const int kl = t % PW_T, tap = t / PW_T;
+            const int n = n0 + nl, k = k0 + kl;
+            if (k < K && n < pitch_n) cnb_st(wd + ((long)tap * K + k) * pitch_n + n, tile[(tap * PW_T + nl) * (PW_T + 1) + kl]);
+        }
+    }
+}
+
+// g[n*s_n + k*s_k + tap*s_tap] (+)= dwp[tap][n][k], written in the parameter's memory order
+__global__ void __launch_bounds__(256) unpack_wgrad_tiled_kernel(const float* __restrict__ dwp, float* __restrict__ g, int taps, int N, int K,
+                                                                long s_n, long s_k, long s_tap, int accumulate) {
+    CNB_DYN_SMEM(sm_raw);
+    float* tile = reinterpret_cast<float*>(sm_raw);
+    const int n0 = blockIdx.y * PW_T, k0 = blockIdx.x * PW_T;
+    for (int i = threadIdx.x; i < taps * PW_T * PW_T; i += blockDim.x) {
+        const int kl = i % PW_T, t = i / PW_T;
+        const int nl = t % PW_T, tap = t / PW_T;
+        const int n = n0 + nl, k = k0 + kl;
+        tile[(tap * PW_T + nl) * (PW_T + 1) + kl] = (n < N && k < K) ? dwp[((long)tap * N + n) * K + k] : 0.f;
+    }
+    __syncthreads();
+    const int per = PW_T * taps;
+    const bool k_inner = s_k <= s_n;
+    for (int i = threadIdx.x; i < PW_T * per; i += blockDim.x) {
+        const int outer = i / per, rem = i - outer * per;
+        const int inner = rem / taps, tap = rem - inner * taps;
+        const int nl = k_inner ? outer : inner, kl = k_inner ? inner : outer;
+        const int n = n0 + nl, k = k0 + kl;
+        if (n < N && k < K) {
+            const long o = n * s_n + k * s_k + tap * s_tap;
+            const float v = tile[(tap * PW_T + nl) * (PW_T + 1) + kl];
+            g[o] = accumulate ? g[o] + v : v;
+        }
+    }
+}
+
 // db[n] += sum_p dy[p][n]; grid = (ceil(N/32), pixel splits); 8 pixel lanes per channel column, one atomic per CTA column
 template <typename T>
 __global__ void __launch_bounds__(256) bias_grad_kernel(const T* __restrict__ dy, int dy_stride, long P, int N, float* __restrict__ db) {

@@ -218,6 +218,80 @@ __global__ void __launch_bounds__(THREADS, 2) bn_act_fwd_stream_kernel(const bf1
     }
 }
 
+// Training-mode forward with the statistics finalisation folded in (one launch instead of bn_finalize + apply): every thread
+// derives scale/shift of ITS eight channels from the batch sums; CTA 0 also publishes mean / rstd / scale / shift for the backward
+// pass and updates the running statistics (it is the only CTA that touches them).
+template <bool RES>
+__global__ void __launch_bounds__(THREADS, 2) bn_train_fwd_stream_kernel(const bf16_t* __restrict__ x, const float* __restrict__ sums,
+                                                                        long count, const float* __restrict__ gamma,
+                                                                        const float* __restrict__ beta, float eps, float momentum,
+                                                                        float* running_mean, float* running_var, float* __restrict__ save_mean,
+                                                                        float* __restrict__ save_rstd, float* __restrict__ scale,
+                                                                        float* __restrict__ shift, const bf16_t* __restrict__ residual,
+                                                                        bf16_t* __restrict__ y, long total_v, int CV, int C, int ch_div,
+                                                                        int act) {
+    CNB_DYN_SMEM(smem);
+    const float inv = 1.0f / (float)count;
+    if (blockIdx.x == 0) {
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            const float mean = sums[c] * inv;
+            const float var = fmaxf(sums[C + c] * inv - mean * mean, 0.f);
+            if (running_mean) {
+                const float unbiased = count > 1 ? var * ((float)count / (float)(count - 1)) : var;
+                running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+                running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+            }
+            const float rstd = rsqrtf(var + eps);
+            const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+            save_mean[c] = mean;
+            save_rstd[c] = rstd;
+            scale[c] = g * rstd;
+            shift[c] = b - mean * g * rstd;
+        }
+    }
+    int chn[8];
+    s_channels(CV, C, ch_div, chn);
+    float sc[8], sf[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if (chn[j] >= 0) {
+            const int c = chn[j];
+            const float mean = sums[c] * inv;
+            const float var = fmaxf(sums[C + c] * inv - mean * mean, 0.f);
+            const float rstd = rsqrtf(var + eps);
+            const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+            sc[j] = g * rstd;
+            sf[j] = b - mean * g * rstd;
+        } else {
+            sc[j] = 0.f, sf[j] = 0.f;
+        }
+    }
+    auto body = [&](long v0, auto& r, int n) {
+        constexpr int LAST = RES ? 1 : 0;
+#pragma unroll
+        for (int u = 0; u < VPT; ++u)
+            if (u < n) {
+                float v[8], w[8];
+                s_unpack(r[0][u], v);
+                if (RES) s_unpack(r[LAST][u], w);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float z = fmaf(v[j], sc[j], sf[j]);
+                    z = act ? cnb_silu_t<bf16_t>(z) : z;
+                    v[j] = RES ? z + w[j] : z;
+                }
+                *reinterpret_cast<uint4*>(y + (v0 + (long)u * THREADS) * 8) = s_pack(v);
+            }
+    };
+    if constexpr (RES) {
+        const void* const src[2] = {x, residual};
+        stream_tiles<2, S2>(src, total_v, smem, body);
+    } else {
+        const void* const src[1] = {x};
+        stream_tiles<1, S1>(src, total_v, smem, body);
+    }
+}
+
 // dsums[0..C) += sum dz, dsums[C..2C) += sum dz*xhat, dz = dy * act'(x*A + Bc)
 __global__ void __launch_bounds__(THREADS, 2) bn_act_bwd_reduce_stream_kernel(const bf16_t* __restrict__ x, const bf16_t* __restrict__ dy,
                                                                              const float* __restrict__ mean, const float* __restrict__ rstd,

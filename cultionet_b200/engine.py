@@ -1,13 +1,26 @@
 """Minimal training / prediction loops for ``CultionetLitModel`` when Lightning is not installed: what Lightning's ``Trainer``
 does around ``training_step`` on the hot path (``src/cultionet/model.py:168-186``: DDP, gradient clipping 1.0, optimizer +
-per-step OneCycle schedule), nothing else."""
+per-step OneCycle schedule), nothing else.
+
+``TrainStep(..., cuda_graph=True)`` captures the whole step (zero-grad, forward, loss, backward, gradient all-reduce, AdamW: ~1200
+kernel launches at BASELINE config 2) into ONE CUDA graph after a few eager warm-up steps and replays it afterwards.  Measured on
+a B200 the eager step needs 64 ms of host time to enqueue 68 ms of device work, so any further kernel speed-up would be hidden behind
+Python; a replay costs the host a few hundred microseconds.  Everything the graph needs is already static: parameters, gradients
+and optimizer state live in flat buffers, the learning rate and step count are read from a device buffer, the C ABI allocates
+nothing and only enqueues work on the stream it is given (``include/cultionet_b200.h``).
+"""
 from __future__ import annotations
 
+import warnings
 from typing import Optional
 
 import torch
+import torch.distributed as dist
 
+from . import _lib
+from . import functional as F
 from .data import Data
+from .nn.modules.convolution import deferred_batch_counters
 from .parallel import BucketedGradSync
 
 
@@ -18,22 +31,93 @@ def batch_to_device(batch: Data, device, non_blocking: bool = True) -> Data:
     return Data(**out)
 
 
-class TrainStep:
-    """One data-parallel optimisation step: forward + loss + backward (+ overlapped gradient all-reduce) + AdamW."""
+def _signature(batch: Data) -> tuple:
+    return tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(batch.__dict__.items()) if isinstance(v, torch.Tensor))
 
-    def __init__(self, lit_model, total_steps: Optional[int] = None, bucket_mb: float = 32.0):
+
+class TrainStep:
+    """One data-parallel optimisation step: forward + loss + backward (+ gradient all-reduce) + AdamW.
+
+    Eager mode overlaps the bucketed all-reduce with backward (``parallel.BucketedGradSync``).  Graph mode replays a captured
+    step; its gradient exchange is a single all-reduce of the flat gradient buffer after backward on the capture stream (169 MB
+    over NVLink: ~0.4 ms, nothing worth overlapping against the host time the graph removes)."""
+
+    def __init__(self, lit_model, total_steps: Optional[int] = None, bucket_mb: float = 32.0, cuda_graph: bool = False,
+                 graph_warmup: int = 3):
         self.model = lit_model
         self.optimizer = lit_model.configure_optimizers(total_steps=total_steps)
-        self.sync = BucketedGradSync(self.optimizer, bucket_mb=bucket_mb)
+        self.cuda_graph = bool(cuda_graph) and self.optimizer.flat_param.is_cuda and not _lib.is_emulator()
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        # graph mode exchanges gradients itself (see _device_step); eager mode uses the overlapped bucketed exchange
+        self.sync = None if self.cuda_graph else BucketedGradSync(self.optimizer, bucket_mb=bucket_mb)
+        self.graph_warmup = graph_warmup
+        self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self._static: Optional[Data] = None
+        self._static_loss: Optional[torch.Tensor] = None
+        self._sig = None
+        self._calls = 0
+        self.launches_per_step: Optional[int] = None  # C-ABI kernel launches recorded while capturing (replays repeat them)
         self.model.train()
 
-    def __call__(self, batch: Data) -> torch.Tensor:
+    # ---- the device work of one step (what a graph captures) ----
+    def _device_step(self, batch: Data) -> torch.Tensor:
         self.optimizer.zero_grad()
-        loss = self.model.training_step(batch, 0)
+        with deferred_batch_counters():  # one multi-tensor launch for the 52 BatchNorm step counters
+            loss = self.model.training_step(batch, 0)
         loss.backward()
-        self.sync.finish()
-        self.optimizer.step()
+        if self.sync is not None:
+            self.sync.finish()
+        elif self.world > 1:
+            dist.all_reduce(self.optimizer.flat_grad, op=dist.ReduceOp.SUM)
+            self.optimizer.grad_scale = 1.0 / self.world
+        self.optimizer.launch_device()
         return loss.detach()
+
+    def eager(self, batch: Data) -> torch.Tensor:
+        self.optimizer.advance_host()
+        return self._device_step(batch)
+
+    def _capture(self, batch: Data) -> None:
+        dev = self.optimizer.flat_param.device
+        self._static = Data(**{k: (v.to(dev).clone() if isinstance(v, torch.Tensor) else v) for k, v in batch.__dict__.items()})
+        self._sig = _signature(batch)
+        if self.world > 1:
+            self.optimizer.grad_scale = 1.0 / self.world  # a kernel argument: must hold its final value while capturing
+        F.invalidate_packed_weights()
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        l0 = _lib.launch_count()
+        with torch.cuda.graph(graph):
+            self._static_loss = self._device_step(self._static)
+        self.launches_per_step = _lib.launch_count() - l0
+        self._graph = graph
+        F.invalidate_packed_weights()
+
+    def __call__(self, batch: Data) -> torch.Tensor:
+        if not self.cuda_graph or _lib.TIMER is not None:
+            return self.eager(batch)
+        if self._graph is None:
+            if self._calls < self.graph_warmup:  # lazy initialisation (kernel attributes, NCCL communicators) happens eagerly
+                self._calls += 1
+                return self.eager(batch)
+            try:
+                self._capture(batch)
+            except Exception as e:  # noqa: BLE001 - a step that cannot be captured still trains, eagerly
+                warnings.warn(f"cultionet_b200: CUDA graph capture of the training step failed ({e!r}); running eagerly")
+                self.cuda_graph = False
+                self._graph = None
+                torch.cuda.synchronize()
+                self.sync = BucketedGradSync(self.optimizer)
+                return self.eager(batch)
+        if _signature(batch) != self._sig:
+            return self.eager(batch)  # a ragged last batch: same arithmetic, no graph
+        for k, v in batch.__dict__.items():
+            if isinstance(v, torch.Tensor):
+                getattr(self._static, k).copy_(v, non_blocking=True)
+        self.optimizer.advance_host()
+        self._graph.replay()
+        F.invalidate_packed_weights()  # the packed weights inside the graph's pool describe the parameters BEFORE this step
+        return self._static_loss
 
 
 @torch.no_grad()

@@ -7,6 +7,7 @@ kernels.  Nothing here computes with torch ops: torch only owns memory, streams 
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from typing import Optional, Sequence
 
 import torch
@@ -46,6 +47,42 @@ def pack_weight(weight: torch.Tensor, kind: str, N: int, K: int, taps: int, dtyp
     out = torch.empty((taps, rows, pitch), dtype=dtype, device=w.device)
     call("cnb_pack_weight", ptr(w), ptr(out), dtype_code(dtype), taps, rows, cols, pitch, s_n, s_k, s_tap, stream_ptr(w))
     return out
+
+
+# Packed copies of nn.Parameters, valid until the parameter changes: torch in-place updates bump `_version`; the flat AdamW kernel
+# writes through raw pointers and calls invalidate_packed_weights() instead.  Inference therefore packs each weight once, and a
+# training step reads each parameter once (forward and data-gradient layouts come out of one launch).
+_PACK_CACHE: dict = {}
+_PACK_CACHE_MAX = 4096
+
+
+def invalidate_packed_weights() -> None:
+    _PACK_CACHE.clear()
+
+
+def packed_weights(weight: torch.Tensor, kind: str, N: int, K: int, taps: int, dtype: torch.dtype, need_dgrad: bool):
+    """(wp, wd): forward layout [taps][N][K-pitch] and, if ``need_dgrad``, the data-gradient layout [taps][K][N-pitch] (else None)."""
+    key = None
+    if isinstance(weight, torch.nn.Parameter):
+        # keyed by the Parameter OBJECT (a weak reference guards against id / address reuse after a model is freed)
+        key = (id(weight), kind, dtype)
+        stamp = (weight.data_ptr(), weight._version, tuple(weight.shape))
+        hit = _PACK_CACHE.get(key)
+        if hit is not None and hit[0]() is weight and hit[1] == stamp and (hit[3] is not None or not need_dgrad):
+            return hit[2], hit[3]
+    _, _, s_n, s_k, s_tap = _weight_strides(kind, N, K, taps, False)
+    w = _contig(weight.detach())
+    bf = dtype == torch.bfloat16
+    pitch_k = (K + 7) // 8 * 8 if bf else K
+    pitch_n = (N + 7) // 8 * 8 if bf else N
+    wp = torch.empty((taps, N, pitch_k), dtype=dtype, device=w.device)
+    wd = torch.empty((taps, K, pitch_n), dtype=dtype, device=w.device) if need_dgrad else None
+    call("cnb_pack_weight2", ptr(w), ptr(wp), ptr(wd), dtype_code(dtype), taps, N, K, pitch_k, pitch_n, s_n, s_k, s_tap, stream_ptr(w))
+    if key is not None:
+        if len(_PACK_CACHE) >= _PACK_CACHE_MAX:
+            _PACK_CACHE.clear()
+        _PACK_CACHE[key] = (weakref.ref(weight), stamp, wp, wd)
+    return wp, wd
 
 
 def _conv_out_size(n: int, k: int, stride: int, pad: int, dil: int) -> int:
@@ -131,7 +168,8 @@ class _Conv2dFn(torch.autograd.Function):
             Hout, Wout = _conv_out_size(Hin, KH, stride, pad, dil), _conv_out_size(Win, KW, stride, pad, dil)
         if out_hw is not None:
             assert tuple(out_hw) == (Hout, Wout), (out_hw, Hout, Wout)
-        wp = pack_weight(weight, kind, N, Ctot, taps, dtype, for_dgrad=False)
+        need_dgrad = any(ctx.needs_input_grad[11 + i] for i in range(len(sources)))
+        wp, ctx.wd = packed_weights(weight, kind, N, Ctot, taps, dtype, need_dgrad)
         out = torch.empty((B, Hout, Wout, N), dtype=dtype, device=x0.device)
         geom = (B, Hin, Win, Hout, Wout, KH, KW, stride, pad, dil)
         bias_c = _contig(bias) if bias is not None else None
@@ -169,7 +207,7 @@ class _Conv2dFn(torch.autograd.Function):
 
         if any(need_src):
             # dgrad: the adjoint gather with the per-tap transposed weights [taps][Ctot][N]; one launch per source slice
-            wd = pack_weight(weight, kind, N, Ctot, taps, dtype, for_dgrad=True)
+            wd = ctx.wd if ctx.wd is not None else pack_weight(weight, kind, N, Ctot, taps, dtype, for_dgrad=True)
             dgeom = (B, Hout, Wout, Hin, Win, KH, KW, stride, pad, dil)
             coff = 0
             for i, (s, c) in enumerate(zip(sources, src_channels)):
@@ -241,21 +279,22 @@ class _BatchNormActFn(torch.autograd.Function):
         st = stream_ptr(x)
         stats = torch.empty((6, Cn), dtype=torch.float32, device=dev)  # sum, sumsq, mean, rstd, scale, shift
         count = P * ch_div  # elements per channel: ch_div columns of every row
+        y = torch.empty_like(x)
+        res = _contig(residual) if residual is not None else None
         if training:
             if sums is not None and sums.numel() == 2 * Cn:
                 sums_ptr = ptr(_contig(sums))  # batch statistics came out of the convolution epilogue
             else:
                 sums_ptr = ptr(stats[0])
                 call("cnb_bn_stats", ptr(x), P, L, Cn, ch_div, sums_ptr, dtype_code(dtype), st)
-            call("cnb_bn_finalize", sums_ptr, count, Cn, ptr(gamma), ptr(beta), eps, momentum, ptr(running_mean),
-                 ptr(running_var), ptr(stats[2]), ptr(stats[3]), ptr(stats[4]), ptr(stats[5]), st)
+            call("cnb_bn_train_fwd", ptr(x), sums_ptr, count, ptr(gamma), ptr(beta), eps, momentum, ptr(running_mean), ptr(running_var),
+                 ptr(stats[2]), ptr(stats[3]), ptr(stats[4]), ptr(stats[5]), ptr(res), ptr(y), P, L, Cn, ch_div, int(act),
+                 dtype_code(dtype), st)
         else:
             call("cnb_bn_finalize", None, count, Cn, ptr(gamma), ptr(beta), eps, momentum, ptr(running_mean),
                  ptr(running_var), ptr(stats[2]), ptr(stats[3]), ptr(stats[4]), ptr(stats[5]), st)
-        y = torch.empty_like(x)
-        res = _contig(residual) if residual is not None else None
-        call("cnb_bn_act_fwd", ptr(x), ptr(stats[4]), ptr(stats[5]), ptr(res), ptr(y), P, L, Cn, ch_div, int(act),
-             dtype_code(dtype), st)
+            call("cnb_bn_act_fwd", ptr(x), ptr(stats[4]), ptr(stats[5]), ptr(res), ptr(y), P, L, Cn, ch_div, int(act),
+                 dtype_code(dtype), st)
         ctx.save_for_backward(x, gamma, beta, stats)
         ctx.meta = (P, L, Cn, ch_div, int(act), bool(training), count, residual is not None)
         return y

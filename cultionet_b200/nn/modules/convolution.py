@@ -30,12 +30,35 @@ def _require_silu(activation_type: str) -> None:
         )
 
 
+# `num_batches_tracked += 1` is one tiny kernel per BatchNorm layer (52 per TowerUNet step).  A training loop may collect the counters
+# of a step and bump them with ONE multi-tensor launch instead: `with deferred_batch_counters(): forward(...)`.
+_PENDING_COUNTERS: T.Optional[T.List[torch.Tensor]] = None
+
+
+class deferred_batch_counters:
+    def __enter__(self):
+        global _PENDING_COUNTERS
+        self.prev = _PENDING_COUNTERS
+        _PENDING_COUNTERS = []
+        return self
+
+    def __exit__(self, *exc):
+        global _PENDING_COUNTERS
+        pending, _PENDING_COUNTERS = _PENDING_COUNTERS, self.prev
+        if pending:
+            torch._foreach_add_(pending, 1)
+        return False
+
+
 def batchnorm_act(bn: nn.modules.batchnorm._BatchNorm, x: torch.Tensor, act: bool, ch_div: int = 1,
                   sums: T.Optional[torch.Tensor] = None) -> torch.Tensor:
     """BatchNorm2d/3d (+SiLU) with the module's parameters; batch statistics iff the module is in training mode."""
     training = bn.training
     if training and bn.track_running_stats and bn.num_batches_tracked is not None:
-        bn.num_batches_tracked.add_(1)
+        if _PENDING_COUNTERS is not None:
+            _PENDING_COUNTERS.append(bn.num_batches_tracked)
+        else:
+            bn.num_batches_tracked.add_(1)
     return F.batchnorm_act(
         x, bn.weight, bn.bias, bn.running_mean, bn.running_var, training,
         momentum=bn.momentum if bn.momentum is not None else 0.1, eps=bn.eps, act=act, ch_div=ch_div, sums=sums,

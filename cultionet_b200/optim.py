@@ -60,7 +60,12 @@ class FlatAdamW:
         self.total_steps = total_steps
         self.step_count = 0
         self.hyper = torch.zeros(2, dtype=torch.float32, device=dev)
-        self._hyper_host = torch.zeros(2, dtype=torch.float32).pin_memory() if dev.type == "cuda" else torch.zeros(2)
+        # (lr, step) travel through a small RING of pinned host buffers: the host runs ahead of the device (and of a replaying CUDA
+        # graph), so a single staging buffer could be overwritten before its copy has executed
+        self._ring_n = 16
+        self._ring = [torch.zeros(2, dtype=torch.float32).pin_memory() if dev.type == "cuda" else torch.zeros(2) for _ in range(self._ring_n)]
+        self._ring_events: list = [None] * self._ring_n
+        self._ring_i = 0
         self.norm_ws = torch.zeros(1, dtype=torch.float32, device=dev)
         self.grad_scale = 1.0
 
@@ -76,18 +81,40 @@ class FlatAdamW:
             return one_cycle_lr(min(self.step_count, self.total_steps - 1), self.total_steps, self.lr)
         return self.lr
 
-    def step(self) -> None:
+    def advance_host(self) -> None:
+        """Host half of a step: next (lr, step count) staged in pinned memory and copied to the device on the current stream."""
         lr = self.current_lr()
         self.step_count += 1
-        self._hyper_host[0] = lr
-        self._hyper_host[1] = float(self.step_count)
-        self.hyper.copy_(self._hyper_host, non_blocking=True)
+        slot = self._ring_i % self._ring_n
+        self._ring_i += 1
+        ev = self._ring_events[slot]
+        if ev is not None:
+            ev.synchronize()  # the copy that last used this slot has executed (normally long ago)
+        buf = self._ring[slot]
+        buf[0] = lr
+        buf[1] = float(self.step_count)
+        self.hyper.copy_(buf, non_blocking=True)
+        if self.hyper.is_cuda:
+            ev = torch.cuda.Event()
+            ev.record()
+            self._ring_events[slot] = ev
+
+    def launch_device(self) -> None:
+        """Device half of a step (capturable in a CUDA graph): |g|^2 for the clip, then AdamW reading (lr, step) from ``hyper``."""
         st = stream_ptr(self.flat_param)
         if self.clip_norm and self.clip_norm > 0:
             call("cnb_grad_sqnorm", ptr(self.flat_grad), self.numel, ptr(self.norm_ws), st)
         call("cnb_adamw_step", ptr(self.flat_param), ptr(self.flat_grad), ptr(self.exp_avg), ptr(self.exp_avg_sq), self.numel,
              ptr(self.hyper), self.betas[0], self.betas[1], self.eps, self.weight_decay, self.grad_scale,
              float(self.clip_norm or 0.0), ptr(self.norm_ws), st)
+        # the kernel wrote the parameters through raw pointers (no torch version bump): drop their packed bf16 copies
+        from . import functional as F
+
+        F.invalidate_packed_weights()
+
+    def step(self) -> None:
+        self.advance_host()
+        self.launch_device()
 
     def state_dict(self) -> dict:
         return {"step": self.step_count, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq}

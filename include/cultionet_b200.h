@@ -110,6 +110,11 @@ int cnb_repitch(const void* src, int src_stride, void* dst, int dst_stride, int6
  * nn.ConvTranspose2d weight [Cin,Cout,kh,kw]: forward (n=Cout,k=Cin) s_n=taps,s_k=Cout*taps; dgrad s_n=Cout*taps,s_k=taps. */
 int cnb_pack_weight(const float* w, void* wp, int dtype, int taps, int N, int K, int wp_pitch,
                     int64_t s_n, int64_t s_k, int64_t s_tap, void* stream);
+/* Both packed layouts of one parameter from ONE read of it (tiled through shared memory, every access coalesced):
+ *   wp[tap][n][k] (pitch_k >= K) as cnb_pack_weight, and, when wd != NULL, the data-gradient layout wd[tap][k][n] (pitch_n >= N);
+ * s_n/s_k/s_tap are the parameter's element strides for the FORWARD roles of n (output channel) and k (input channel). */
+int cnb_pack_weight2(const float* w, void* wp, void* wd, int dtype, int taps, int N, int K, int pitch_k, int pitch_n,
+                     int64_t s_n, int64_t s_k, int64_t s_tap, void* stream);
 /* inverse scatter of a packed fp32 gradient into the parameter layout: g[...] (+)= dwp[tap][n][k] */
 int cnb_unpack_wgrad(const float* dwp, float* g, int taps, int N, int K,
                      int64_t s_n, int64_t s_k, int64_t s_tap, int accumulate, void* stream);
@@ -131,6 +136,11 @@ int cnb_bn_finalize(const float* sums, int64_t count, int C, const float* gamma,
 /* y = act(x*scale[ch] + shift[ch]) (+ residual) ; act: 0 none, 1 SiLU */
 int cnb_bn_act_fwd(const void* x, const float* scale, const float* shift, const void* residual, void* y,
                    int64_t P, int L, int C, int ch_div, int act, int dtype, void* stream);
+/* training-mode cnb_bn_finalize + cnb_bn_act_fwd as one call (one launch on the bulk-copy path: the apply kernel derives scale/shift
+ * from the batch sums itself and its first CTA publishes mean/rstd/scale/shift and updates the running statistics) */
+int cnb_bn_train_fwd(const void* x, const float* sums, int64_t count, const float* gamma, const float* beta, float eps, float momentum,
+                     float* running_mean, float* running_var, float* save_mean, float* save_rstd, float* scale, float* shift,
+                     const void* residual, void* y, int64_t P, int L, int C, int ch_div, int act, int dtype, void* stream);
 /* backward pass 1: dsums[0..C) = sum dz, dsums[C..2C) = sum dz*xhat, dz = dy * act'(z) */
 int cnb_bn_act_bwd_reduce(const void* x, const void* dy, const float* save_mean, const float* save_rstd, const float* gamma,
                           const float* beta, int64_t P, int L, int C, int ch_div, int act, float* dsums, int dtype, void* stream);

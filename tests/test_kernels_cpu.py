@@ -84,6 +84,13 @@ def test_resize_bilinear(dev, sizes):
     cases.resize_case(dev, F32, 2, *sizes, 3)
 
 
+@pytest.mark.parametrize("sizes", [(7, 7, 8, 8), (13, 13, 25, 25), (5, 9, 12, 10), (10, 10, 7, 7), (1, 1, 4, 4), (31, 17, 32, 33)])
+def test_resize_bilinear_vector_kernels(dev, sizes):
+    # channel counts that are whole 16-byte vectors: the row-per-CTA forward and the table-form / gather-form backward kernels
+    cases.resize_case(dev, F32, 2, *sizes, 8)
+    cases.resize_case(dev, BF16, 1, *sizes, 16)
+
+
 @pytest.mark.parametrize("k", [3, 5])
 def test_pretime_conv(dev, k):
     cases.pretime_case(dev, F32, 2, 3, 12, 5, 6, k)
@@ -148,3 +155,31 @@ def test_tiny_channel_convs(dev):
     cases.conv_case(dev, BF16, 2, 9, 11, [1, 1, 1], 3, 3, 1, 1, 1)
     cases.conv_case(dev, F32, 1, 9, 11, [4], 2, 3, 2, 1, 1)
     cases.convT_case(dev, F32, 1, 5, 6, 3, 2, 2)
+
+
+def test_packed_weight_cache_tracks_parameter_updates(dev):
+    """Packed bf16/fp32 copies of nn.Parameters are cached between calls: torch in-place updates, the flat AdamW kernel and a freed
+    and re-created parameter must all miss the cache."""
+    from cultionet_b200 import functional as F
+    from cultionet_b200.optim import FlatAdamW
+
+    torch.manual_seed(0)
+    x = torch.randn(1, 6, 5, 8, device=dev)
+    w = torch.nn.Parameter(torch.randn(4, 8, 3, 3, device=dev))
+    y1 = F.conv2d([x], w, None, 3, 1, 1, 1)
+    assert F.packed_weights(w, F.W_CONV, 4, 8, 9, torch.float32, False)[0] is F.packed_weights(w, F.W_CONV, 4, 8, 9, torch.float32, False)[0]
+    with torch.no_grad():
+        w.mul_(2.0)
+    y2 = F.conv2d([x], w, None, 3, 1, 1, 1)
+    assert torch.allclose(y2, 2 * y1, rtol=1e-5, atol=1e-6)
+    opt = FlatAdamW([w], lr=0.1, clip_norm=0.0)
+    opt.zero_grad()
+    F.conv2d([x], w, None, 3, 1, 1, 1).sum().backward()
+    opt.step()
+    y3 = F.conv2d([x], w, None, 3, 1, 1, 1)
+    ref = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2), w.detach(), padding=1).permute(0, 2, 3, 1)
+    assert torch.allclose(y3, ref, rtol=1e-4, atol=1e-5) and not torch.allclose(y3, y2)
+    del w
+    w2 = torch.nn.Parameter(torch.randn(4, 8, 3, 3, device=dev))
+    ref2 = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2), w2.detach(), padding=1).permute(0, 2, 3, 1)
+    assert torch.allclose(F.conv2d([x], w2, None, 3, 1, 1, 1), ref2, rtol=1e-4, atol=1e-5)
