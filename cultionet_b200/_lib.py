@@ -48,6 +48,15 @@ class ConvDesc(C.Structure):
     ]
 
 
+class PackDesc(C.Structure):
+    _fields_ = [
+        ("w", C.c_void_p), ("wp", C.c_void_p), ("wd", C.c_void_p),
+        ("taps", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("pitch_k", C.c_int32), ("pitch_n", C.c_int32),
+        ("tile0", C.c_int32), ("tiles_x", C.c_int32), ("reserved", C.c_int32),
+        ("s_n", C.c_int64), ("s_k", C.c_int64), ("s_tap", C.c_int64),
+    ]
+
+
 class WgradDesc(C.Structure):
     _fields_ = [
         ("src", C.c_void_p), ("src_c", C.c_int32), ("src_stride", C.c_int32),
@@ -86,6 +95,7 @@ _PROTOS = {
     "cnb_repitch": [_vp, _i, _vp, _i, _i64, _i, _i, _vp],
     "cnb_pack_weight": [_vp, _vp, _i, _i, _i, _i, _i, _i64, _i64, _i64, _vp],
     "cnb_pack_weight2": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i64, _i64, _i64, _vp],
+    "cnb_pack_weights_batched": [_vp, _i, _i, _i, _i, _vp],
     "cnb_unpack_wgrad": [_vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i, _vp],
     "cnb_bias_grad": [_vp, _i, _i64, _i, _vp, _i, _i, _vp],
     "cnb_bn_stats": [_vp, _i64, _i, _i, _i, _vp, _i, _vp],

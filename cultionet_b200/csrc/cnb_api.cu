@@ -265,6 +265,17 @@ int cnb_pack_weight2(const float* w, void* wp, void* wd, int dtype, int taps, in
     return CNB_OK;
 }
 
+int cnb_pack_weights_batched(const cnb_pack_desc* table, int ndesc, int total_tiles, int max_taps, int dtype, void* stream) {
+    CNB_REQUIRE(table && ndesc > 0 && total_tiles > 0 && max_taps > 0 && max_taps <= 32, "pack_weights_batched: bad arguments");
+    const size_t smem = (size_t)max_taps * PW_T * (PW_T + 1) * sizeof(float);
+    CNB_DISPATCH_DTYPE(dtype, {
+        CNB_SET_SMEM((pack_weight_batched_kernel<T>), smem);
+        CNB_LAUNCH((pack_weight_batched_kernel<T>), dim3(total_tiles), dim3(256), smem, (cudaStream_t)stream, table, ndesc);
+    });
+    CNB_CHECK_LAUNCH("pack_weight_batched_kernel");
+    return CNB_OK;
+}
+
 int cnb_unpack_wgrad(const float* dwp, float* g, int taps, int N, int K, int64_t s_n, int64_t s_k, int64_t s_tap, int accumulate, void* stream) {
     CNB_REQUIRE(dwp && g && taps > 0 && N > 0 && K > 0, "unpack_wgrad: bad arguments");
     if (taps <= 32) {

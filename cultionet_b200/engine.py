@@ -31,6 +31,56 @@ def batch_to_device(batch: Data, device, non_blocking: bool = True) -> Data:
     return Data(**out)
 
 
+class DevicePrefetcher:
+    """Iterates over HOST batches (pinned ``Data`` objects) and yields device copies, issuing each batch's host-to-device copies on
+    a side stream ``depth - 1`` steps ahead so that they overlap the previous step's kernels (what ``DataLoader(pin_memory=True)``
+    + non-blocking copies do in the reference's Lightning loop).  The device buffers are reused round-robin; a buffer is refilled
+    only after the work the consumer enqueued while holding it has finished (event on the consumer's stream)."""
+
+    def __init__(self, batches, device, depth: int = 2):
+        self.it = iter(batches)
+        self.device = torch.device(device)
+        self.depth = max(1, depth)
+        self.stream = torch.cuda.Stream(self.device)
+        self.slots = [None] * self.depth
+        self.free = [None] * self.depth
+        self.ready: list = []
+
+    def _issue(self, slot: int) -> bool:
+        try:
+            host = next(self.it)
+        except StopIteration:
+            return False
+        with torch.cuda.stream(self.stream):
+            if self.free[slot] is not None:
+                self.stream.wait_event(self.free[slot])
+            buf = self.slots[slot]
+            if buf is None or _signature(buf) != _signature(host):
+                buf = Data(**{k: (torch.empty(v.shape, dtype=v.dtype, device=self.device) if isinstance(v, torch.Tensor) else v)
+                              for k, v in host.__dict__.items()})
+                self.slots[slot] = buf
+            for k, v in host.__dict__.items():
+                if isinstance(v, torch.Tensor):
+                    getattr(buf, k).copy_(v, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self.ready.append((slot, ev))
+        return True
+
+    def __iter__(self):
+        for slot in range(self.depth):
+            if not self._issue(slot):
+                break
+        while self.ready:
+            slot, ev = self.ready.pop(0)
+            torch.cuda.current_stream(self.device).wait_event(ev)
+            yield self.slots[slot]
+            done = torch.cuda.Event()
+            done.record(torch.cuda.current_stream(self.device))
+            self.free[slot] = done
+            self._issue(slot)
+
+
 def _signature(batch: Data) -> tuple:
     return tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(batch.__dict__.items()) if isinstance(v, torch.Tensor))
 
@@ -62,6 +112,7 @@ class TrainStep:
     # ---- the device work of one step (what a graph captures) ----
     def _device_step(self, batch: Data) -> torch.Tensor:
         self.optimizer.zero_grad()
+        F.prepack_parameters()  # every convolution weight seen so far: one packing launch instead of one per layer
         with deferred_batch_counters():  # one multi-tensor launch for the 52 BatchNorm step counters
             loss = self.model.training_step(batch, 0)
         loss.backward()

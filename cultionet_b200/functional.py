@@ -60,6 +60,19 @@ def invalidate_packed_weights() -> None:
     _PACK_CACHE.clear()
 
 
+def _pack_geometry(kind: str, N: int, K: int, taps: int, dtype: torch.dtype):
+    _, _, s_n, s_k, s_tap = _weight_strides(kind, N, K, taps, False)
+    bf = dtype == torch.bfloat16
+    return s_n, s_k, s_tap, ((K + 7) // 8 * 8 if bf else K), ((N + 7) // 8 * 8 if bf else N)
+
+
+# Every Parameter that went through packed_weights() is remembered here ("the plan"), so that a training loop can pack ALL of them
+# with one launch at the top of a step (prepack_parameters) instead of one launch per layer as the forward reaches it.
+_PACK_PLAN: dict = {}       # key -> [weakref, kind, N, K, taps, dtype, need_dgrad]
+_PACK_BATCH: dict = {}      # dtype -> persistent state of the batched launch (buffers + device descriptor table)
+_PACK_PLAN_DIRTY = [True]
+
+
 def packed_weights(weight: torch.Tensor, kind: str, N: int, K: int, taps: int, dtype: torch.dtype, need_dgrad: bool):
     """(wp, wd): forward layout [taps][N][K-pitch] and, if ``need_dgrad``, the data-gradient layout [taps][K][N-pitch] (else None)."""
     key = None
@@ -70,11 +83,12 @@ def packed_weights(weight: torch.Tensor, kind: str, N: int, K: int, taps: int, d
         hit = _PACK_CACHE.get(key)
         if hit is not None and hit[0]() is weight and hit[1] == stamp and (hit[3] is not None or not need_dgrad):
             return hit[2], hit[3]
-    _, _, s_n, s_k, s_tap = _weight_strides(kind, N, K, taps, False)
+        plan = _PACK_PLAN.get(key)
+        if plan is None or plan[0]() is not weight or (need_dgrad and not plan[6]):
+            _PACK_PLAN[key] = [weakref.ref(weight), kind, N, K, taps, dtype, bool(need_dgrad or (plan is not None and plan[0]() is weight and plan[6]))]
+            _PACK_PLAN_DIRTY[0] = True
+    s_n, s_k, s_tap, pitch_k, pitch_n = _pack_geometry(kind, N, K, taps, dtype)
     w = _contig(weight.detach())
-    bf = dtype == torch.bfloat16
-    pitch_k = (K + 7) // 8 * 8 if bf else K
-    pitch_n = (N + 7) // 8 * 8 if bf else N
     wp = torch.empty((taps, N, pitch_k), dtype=dtype, device=w.device)
     wd = torch.empty((taps, K, pitch_n), dtype=dtype, device=w.device) if need_dgrad else None
     call("cnb_pack_weight2", ptr(w), ptr(wp), ptr(wd), dtype_code(dtype), taps, N, K, pitch_k, pitch_n, s_n, s_k, s_tap, stream_ptr(w))
@@ -83,6 +97,54 @@ def packed_weights(weight: torch.Tensor, kind: str, N: int, K: int, taps: int, d
             _PACK_CACHE.clear()
         _PACK_CACHE[key] = (weakref.ref(weight), stamp, wp, wd)
     return wp, wd
+
+
+def prepack_parameters() -> int:
+    """Packs every planned Parameter with ONE launch per compute dtype and refreshes the cache; returns the number packed.  Call at
+    the top of a training step (after the optimizer has changed the parameters).  The packed buffers and the device-resident
+    descriptor table persist between calls, so under CUDA-graph capture this is a single kernel node."""
+    if _PACK_PLAN_DIRTY[0]:
+        for k in [k for k, e in _PACK_PLAN.items() if e[0]() is None]:
+            del _PACK_PLAN[k]
+        _PACK_BATCH.clear()
+        by_dtype: dict = {}
+        for key, e in _PACK_PLAN.items():
+            w = e[0]()
+            if w.is_contiguous():
+                by_dtype.setdefault((e[5], w.device), []).append((key, e))
+        for (dtype, dev), entries in by_dtype.items():
+            table = (_lib.PackDesc * len(entries))()
+            bufs, tile0, max_taps = [], 0, 1
+            for i, (key, (ref, kind, N, K, taps, _, need_dgrad)) in enumerate(entries):
+                w = ref()
+                s_n, s_k, s_tap, pitch_k, pitch_n = _pack_geometry(kind, N, K, taps, dtype)
+                wp = torch.empty((taps, N, pitch_k), dtype=dtype, device=dev)
+                wd = torch.empty((taps, K, pitch_n), dtype=dtype, device=dev) if need_dgrad else None
+                d = table[i]
+                d.w, d.wp, d.wd = w.data_ptr(), wp.data_ptr(), (wd.data_ptr() if wd is not None else None)
+                d.taps, d.N, d.K, d.pitch_k, d.pitch_n = taps, N, K, pitch_k, pitch_n
+                d.s_n, d.s_k, d.s_tap = s_n, s_k, s_tap
+                tiles_x = (max(K, pitch_k) + 31) // 32
+                tiles_y = (max(N, pitch_n if need_dgrad else N) + 31) // 32
+                d.tile0, d.tiles_x = tile0, tiles_x
+                tile0 += tiles_x * tiles_y
+                max_taps = max(max_taps, taps)
+                bufs.append((key, ref, w.data_ptr(), wp, wd))
+            raw = torch.frombuffer(bytearray(bytes(table)), dtype=torch.uint8).clone()
+            _PACK_BATCH[(dtype, dev)] = (raw.to(dev), len(entries), tile0, max_taps, bufs)
+        _PACK_PLAN_DIRTY[0] = False
+    n = 0
+    for (dtype, dev), (table_dev, ndesc, total_tiles, max_taps, bufs) in _PACK_BATCH.items():
+        # a parameter whose storage moved since the table was built (e.g. FlatAdamW re-homed it) invalidates the table
+        if any(ref() is None or ref().data_ptr() != p0 for _, ref, p0, _, _ in bufs):
+            _PACK_PLAN_DIRTY[0] = True
+            return prepack_parameters()
+        call("cnb_pack_weights_batched", ptr(table_dev), ndesc, total_tiles, max_taps, dtype_code(dtype), stream_ptr(table_dev))
+        for key, ref, _, wp, wd in bufs:
+            w = ref()
+            _PACK_CACHE[key] = (ref, (w.data_ptr(), w._version, tuple(w.shape)), wp, wd)
+        n += ndesc
+    return n
 
 
 def _conv_out_size(n: int, k: int, stride: int, pad: int, dil: int) -> int:

@@ -115,6 +115,19 @@ int cnb_pack_weight(const float* w, void* wp, int dtype, int taps, int N, int K,
  * s_n/s_k/s_tap are the parameter's element strides for the FORWARD roles of n (output channel) and k (input channel). */
 int cnb_pack_weight2(const float* w, void* wp, void* wd, int dtype, int taps, int N, int K, int pitch_k, int pitch_n,
                      int64_t s_n, int64_t s_k, int64_t s_tap, void* stream);
+/* cnb_pack_weight2 for MANY parameters in one launch.  `table` is a DEVICE array of `ndesc` descriptors sorted by tile0; descriptor
+ * i owns tiles [tile0, tile0 + tiles_x * tiles_y) of the launch, tiles_x = ceil(max(K, pitch_k) / 32),
+ * tiles_y = ceil(max(N, wd ? pitch_n : N) / 32); total_tiles = sum over descriptors; max_taps = largest taps in the table (<= 32). */
+typedef struct cnb_pack_desc {
+    const float* w;
+    void* wp;
+    void* wd; /* may be NULL */
+    int32_t taps, N, K, pitch_k, pitch_n;
+    int32_t tile0, tiles_x;
+    int32_t reserved;
+    int64_t s_n, s_k, s_tap;
+} cnb_pack_desc;
+int cnb_pack_weights_batched(const cnb_pack_desc* table, int ndesc, int total_tiles, int max_taps, int dtype, void* stream);
 /* inverse scatter of a packed fp32 gradient into the parameter layout: g[...] (+)= dwp[tap][n][k] */
 int cnb_unpack_wgrad(const float* dwp, float* g, int taps, int N, int K,
                      int64_t s_n, int64_t s_k, int64_t s_tap, int accumulate, void* stream);

@@ -220,3 +220,22 @@ def test_cuda_graph_train_step_matches_eager(dev):
     # running statistics and step counters advanced inside the replays as well
     bn = [m for m in s_graph.model.modules() if isinstance(m, torch.nn.BatchNorm2d)][0]
     assert int(bn.num_batches_tracked) == 8
+
+
+def test_device_prefetcher_feeds_identical_batches(dev):
+    """engine.DevicePrefetcher: pinned host batches copied on a side stream one step ahead; the consumer sees every batch intact and
+    in order even though the two device buffers are recycled."""
+    import cultionet_b200 as cb
+    from cultionet_b200.engine import DevicePrefetcher
+
+    g = torch.Generator().manual_seed(3)
+    host = [cb.Data(x=torch.rand(2, 3, 4, 16, 16, generator=g).pin_memory(), y=torch.randint(0, 3, (2, 16, 16), generator=g).pin_memory(),
+                    bdist=torch.rand(2, 16, 16, generator=g).pin_memory()) for _ in range(7)]
+    seen = 0
+    for want, got in zip(host, DevicePrefetcher(iter(host), dev)):
+        # some device work between batches, as a training step would enqueue
+        acc = (got.x.sum() + got.bdist.sum()).item()
+        assert got.x.is_cuda and torch.equal(got.x.cpu(), want.x) and torch.equal(got.y.cpu(), want.y) and torch.equal(got.bdist.cpu(), want.bdist)
+        assert abs(acc - float(want.x.sum() + want.bdist.sum())) < 1e-2
+        seen += 1
+    assert seen == 7
