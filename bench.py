@@ -353,9 +353,12 @@ def main() -> None:
             "final_loss": float(losses[-1]),
         }
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    # Leave without tearing the process group down: every collective of this run has completed (the timed regions end in barriers),
+    # and destroying the NCCL communicators while captured CUDA graphs still reference them blocked for minutes on a 2-GPU box.
+    sys.stdout.flush()
+    sys.stderr.flush()
+    torch.cuda.synchronize()
+    os._exit(0)
 
 
 if __name__ == "__main__":
