@@ -147,6 +147,20 @@ int cnb_conv2d_fwd_tiny(const cnb_conv_desc* d, int dtype, void* stream) {
     int ctot = 0;
     for (int s = 0; s < d->nsrc; ++s) ctot += d->src_c[s];
     const long M = (long)d->B * d->Hout * d->Wout;
+    if (d->nsrc == 1 && ((d->N == 3 && (ctot == 9 || ctot == 3)) || (d->N == 9 && ctot == 3))) {
+        // the Psi-Net head shapes: compile-time channel counts (see conv_tiny_fixed_kernel)
+        const dim3 grid(stream_grid(M, 256, 8));
+        CNB_DISPATCH_DTYPE(dtype, {
+            if (d->N == 3 && ctot == 9)
+                CNB_LAUNCH((conv_tiny_fixed_kernel<T, 3, 9>), grid, dim3(256), 0, (cudaStream_t)stream, *d);
+            else if (d->N == 3)
+                CNB_LAUNCH((conv_tiny_fixed_kernel<T, 3, 3>), grid, dim3(256), 0, (cudaStream_t)stream, *d);
+            else
+                CNB_LAUNCH((conv_tiny_fixed_kernel<T, 9, 3>), grid, dim3(256), 0, (cudaStream_t)stream, *d);
+        });
+        CNB_CHECK_LAUNCH("conv_tiny_fixed_kernel");
+        return CNB_OK;
+    }
     CNB_DISPATCH_DTYPE(dtype, { CNB_LAUNCH((conv_tiny_kernel<T>), dim3(stream_grid(M, 256, 4)), dim3(256), 0, (cudaStream_t)stream, *d, ctot); });
     CNB_CHECK_LAUNCH("conv_tiny_kernel");
     return CNB_OK;

@@ -176,15 +176,25 @@ class ResidualAConv(nn.Module):
 
     def forward(self, x: Sources) -> torch.Tensor:
         sources = _as_sources(x)
+        nres = len(self.res_modules)
+        attention = self.attention_weights is not None
+        # every source feeds the skip path and each dilation branch; F.fanout hands each consumer its own reference so that the
+        # backward sums their gradients in one n-ary add instead of autograd's pairwise accumulation
         if isinstance(self.skip, nn.Identity):
             assert len(sources) == 1
-            skip = sources[0]
+            refs = F.fanout(sources[0], nres + 1 + (1 if attention else 0))
+            skip, att_in = refs[0], refs[-1]
+            branch_in = [[refs[1 + i]] for i in range(nres)]
         else:
-            skip = F.conv2d(sources, self.skip.weight, self.skip.bias, ksize=1, stride=1, pad=0)
-        terms = [skip] + [layer(sources) for layer in self.res_modules]
-        if self.attention_weights is not None:
+            refs = [F.fanout(s, nres + 1) for s in sources]
+            skip = F.conv2d([r[0] for r in refs], self.skip.weight, self.skip.bias, ksize=1, stride=1, pad=0)
+            branch_in = [[r[1 + i] for r in refs] for i in range(nres)]
+            if attention:
+                skip, att_in = F.fanout(skip, 2)
+        terms = [skip] + [layer(branch_in[i]) for i, layer in enumerate(self.res_modules)]
+        if attention:
             ln1, na, ln2 = self.attention_conv[1], self.attention_conv[2], self.attention_conv[3]
-            a = F.layernorm(skip, ln1.weight, ln1.bias, ln1.eps)
+            a = F.layernorm(att_in, ln1.weight, ln1.bias, ln1.eps)
             a = na(a)
             terms.append(F.layernorm(a, ln2.weight, ln2.bias, ln2.eps))
         out = F.add_n(*terms[:4])
