@@ -41,6 +41,13 @@ WORKLOADS = {
     "cfg2": dict(B=32, C=5, T=24, H=128, W=128, hidden=64, dilations=[1, 2], dtype="bf16", fwd_gflop_per_chip=423.0),
     # BASELINE.json configs[0]: fp32, x=[4,3,12,100,100], hidden 32 (the reference's CPU-runnable case)
     "cfg1": dict(B=4, C=3, T=12, H=100, W=100, hidden=32, dilations=[1, 2], dtype="f32", fwd_gflop_per_chip=64.9),
+    # BASELINE.json configs[3]: long time series T=36, neighbourhood attention kernel 7 dilation 2, batch 16 of 256x256 chips
+    "cfg4": dict(B=16, C=5, T=36, H=256, W=256, hidden=64, dilations=[1, 2], dtype="bf16", fwd_gflop_per_chip=1697.0,
+                 natten=dict(natten_kernel_size=7, natten_dilation=2)),
+    # BASELINE.json configs[4] on ONE GPU: eval-mode sliding-window prediction, windows of 100 px + 20 px halo = 140x140 chips
+    # (C=5, T=12); a step = one batch of 32 windows through predict_step; metric = useful (un-padded) Mpx/s
+    "cfg5": dict(B=32, C=5, T=12, H=140, W=140, hidden=64, dilations=[1, 2], dtype="bf16", fwd_gflop_per_chip=505.0, predict=True,
+                 useful_px_per_chip=100 * 100),
     "tiny": dict(B=2, C=3, T=8, H=32, W=32, hidden=16, dilations=[1, 2], dtype="bf16", fwd_gflop_per_chip=0.0),
 }
 
@@ -169,6 +176,104 @@ def run_reference_arm(args, w: dict) -> None:
     print(json.dumps(line), flush=True)
 
 
+def run_predict(args, w: dict) -> None:
+    """Secondary metric of BASELINE.json (inference Mpx/s): predict_step over batches of sliding-window chips, weak-scaled over ranks
+    (windows are independent: no collective on the data path).  Not the driver's default line (that is the training metric)."""
+    import torch.distributed as dist
+
+    import cultionet_b200 as cb
+    from cultionet_b200 import _lib
+    from cultionet_b200.engine import DevicePrefetcher, PredictStep
+    from cultionet_b200.models.lightning import CultionetLitModel
+    from cultionet_b200.parallel import init_distributed
+
+    rank, local, world = init_distributed()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    B = w["B"]
+    torch.manual_seed(1234)
+    model = CultionetLitModel(in_channels=w["C"], in_time=w["T"], hidden_channels=w["hidden"], dilations=w["dilations"], dropout=0.0,
+                              compute_dtype=torch.bfloat16).to(dev)
+    step = PredictStep(model, cuda_graph=not args.no_graph)
+    g = torch.Generator().manual_seed(100 + rank)
+    hx = torch.rand(B, w["C"], w["T"], w["H"], w["W"], generator=g).pin_memory()
+    dbatch = cb.Data(x=hx.to(dev))
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    host_out = torch.empty((B, 3, w["H"], w["W"]), dtype=torch.float32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce_max(ms: float) -> float:
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    for _ in range(max(args.warmup, 3) + 3):
+        step(dbatch)
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step(dbatch)
+        flush.zero_()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    torch.cuda.synchronize()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        flush.zero_()
+    f1.record()
+    torch.cuda.synchronize()
+    fl = f0.elapsed_time(f1)
+    ms_res = reduce_max(e0.elapsed_time(e1)) - fl
+
+    # end to end: windows from pinned host memory (prefetched on a side stream), the three output planes copied back to the host
+    def e2e(n):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for bt in DevicePrefetcher((cb.Data(x=hx) for _ in range(n)), dev):
+            out = step(bt)
+            for i, k in enumerate(("distance", "edge", "crop")):
+                host_out[:, i].copy_(out[k][:, 0], non_blocking=True)
+            flush.zero_()
+        b.record()
+        barrier()
+        return reduce_max(a.elapsed_time(b))
+
+    e2e(2)
+    ms_e2e = e2e(args.steps) - fl
+    if rank == 0:
+        px = B * world * args.steps * w["useful_px_per_chip"]
+        line = {
+            "metric": "inference Mpx/s", "value": px / 1e6 / (ms_res / 1e3), "unit": "Mpx/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: predict_step (eval-mode BatchNorm) over batches of {B} sliding-window chips "
+                                   f"x=[{B},{w['C']},{w['T']},{w['H']},{w['W']}] per GPU (100 px window + 20 px halo), hidden {w['hidden']}; "
+                                   "value counts the un-padded 100x100 pixels of every window",
+                       "windows_per_s": B * world * args.steps / (ms_res / 1e3), "parallelism": f"dp{world} (windows round-robin, no collective)",
+                       "l2": "256 MB flush buffer written between timed steps (its time subtracted)",
+                       "execution": "one CUDA graph per batch, replayed" if step.cuda_graph else "eager launches through the C ABI"},
+            "e2e": {"value": px / 1e6 / (ms_e2e / 1e3), "unit": "Mpx/s", "h2d_bytes_per_step": hx.numel() * 4,
+                    "d2h_bytes_per_step": host_out.numel() * 4, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(step.launches_per_step or 0), "clocks": clocks,
+            "model_tflops": w["fwd_gflop_per_chip"] * 1e9 * B * world * args.steps / (ms_res / 1e3) / 1e12,
+        }
+        print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    torch.cuda.synchronize()
+    os._exit(0)
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 def main() -> None:
     args = parse_args()
@@ -177,6 +282,10 @@ def main() -> None:
         w["B"] = args.batch
     if args.impl == "reference":
         run_reference_arm(args, w)
+        return
+
+    if w.get("predict"):
+        run_predict(args, w)
         return
 
     import torch.distributed as dist
@@ -195,6 +304,11 @@ def main() -> None:
     dtype = torch.bfloat16 if w["dtype"] == "bf16" else torch.float32
     B = w["B"]
 
+    if w.get("natten"):  # the reference configures natten through this module-level dict too (unet_parts.py:19-40)
+        from cultionet_b200.nn.modules import unet_parts
+
+        for lvl in ("a", "b", "c"):
+            unet_parts.NATTEN_PARAMS[lvl].update(w["natten"])
     torch.manual_seed(1234)  # identical replicas
     model = CultionetLitModel(in_channels=w["C"], in_time=w["T"], hidden_channels=w["hidden"], dilations=w["dilations"], dropout=0.0,
                               compute_dtype=dtype).to(dev)

@@ -175,3 +175,58 @@ class TrainStep:
 def predict(lit_model, batch: Data):
     lit_model.eval()
     return lit_model.predict_step(batch, 0)
+
+
+class PredictStep:
+    """``predict_step`` over fixed-shape window batches (the sliding-window inference of ``cultionet predict``): eval-mode BatchNorm,
+    no autograd, packed weights cached across calls; with ``cuda_graph=True`` the forward is captured once and replayed, the
+    returned dict holds STATIC output tensors that the next call overwrites (copy or consume them first)."""
+
+    def __init__(self, lit_model, cuda_graph: bool = False, graph_warmup: int = 2):
+        self.model = lit_model
+        self.model.eval()
+        p = next(lit_model.parameters())
+        self.cuda_graph = bool(cuda_graph) and p.is_cuda and not _lib.is_emulator()
+        self.graph_warmup = graph_warmup
+        self._graph = None
+        self._static = None
+        self._out = None
+        self._sig = None
+        self._calls = 0
+        self.launches_per_step: Optional[int] = None
+
+    @torch.no_grad()
+    def eager(self, batch: Data):
+        return self.model.predict_step(batch, 0)
+
+    @torch.no_grad()
+    def __call__(self, batch: Data):
+        if not self.cuda_graph or _lib.TIMER is not None:
+            return self.eager(batch)
+        if self._graph is None:
+            if self._calls < self.graph_warmup:
+                self._calls += 1
+                return self.eager(batch)
+            try:
+                self._static = Data(**{k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in batch.__dict__.items()})
+                self._sig = _signature(batch)
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                l0 = _lib.launch_count()
+                with torch.cuda.graph(graph):
+                    self._out = self.model.predict_step(self._static, 0)
+                self.launches_per_step = _lib.launch_count() - l0
+                self._graph = graph
+            except Exception as e:  # noqa: BLE001
+                warnings.warn(f"cultionet_b200: CUDA graph capture of predict_step failed ({e!r}); running eagerly")
+                self.cuda_graph = False
+                self._graph = None
+                torch.cuda.synchronize()
+                return self.eager(batch)
+        if _signature(batch) != self._sig:
+            return self.eager(batch)
+        for k, v in batch.__dict__.items():
+            if isinstance(v, torch.Tensor):
+                getattr(self._static, k).copy_(v, non_blocking=True)
+        self._graph.replay()
+        return self._out

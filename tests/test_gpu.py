@@ -239,3 +239,22 @@ def test_device_prefetcher_feeds_identical_batches(dev):
         assert abs(acc - float(want.x.sum() + want.bdist.sum())) < 1e-2
         seen += 1
     assert seen == 7
+
+
+def test_predict_step_cuda_graph_matches_eager(dev):
+    """engine.PredictStep: eval-mode forward captured once and replayed on fresh window batches == the eager predict_step."""
+    import cultionet_b200 as cb
+    from cultionet_b200.engine import PredictStep
+    from cultionet_b200.models.lightning import CultionetLitModel
+
+    torch.manual_seed(0)
+    model = CultionetLitModel(in_channels=3, in_time=6, hidden_channels=16, dropout=0.0, compute_dtype=BF16).to(dev)
+    graphed, eager = PredictStep(model, cuda_graph=True), PredictStep(model, cuda_graph=False)
+    g = torch.Generator().manual_seed(5)
+    for i in range(5):
+        b = cb.Data(x=torch.rand(2, 3, 6, 40, 40, generator=g).to(dev))
+        want = {k: v.clone() for k, v in eager(b).items() if v is not None}
+        got = graphed(b)
+        for k, v in want.items():
+            assert got[k].shape == (2, 1, 40, 40) and torch.allclose(got[k], v, rtol=1e-5, atol=1e-6), (i, k)
+    assert graphed._graph is not None and graphed.launches_per_step > 50
