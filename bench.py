@@ -441,7 +441,17 @@ def main() -> None:
                              "tflops": round(v["flops"] / (v["ms"] / 1e3) / 1e12, 1) if v["ms"] > 0 else None}
                             for k, v in sorted(shapes.items(), key=lambda kv: -kv[1]["ms"]) if k.startswith("conv")][:40],
                         "other_ms_per_step": {k: v["ms"] / nprof for k, v in sorted(summ.items(), key=lambda kv: -kv[1]["ms"])
-                                              if not k.startswith("conv")}}
+                                              if not k.startswith("conv")},
+                        # the bandwidth-bound kernels against the measured HBM copy rate: algorithmic bytes of all
+                        # launches of an entry point / their summed launch time (eager instrumented pass: small launches include
+                        # host gaps, so these are lower bounds; tools/bench_bw.py times the level-a shapes alone)
+                        "hbm_kernels": {"peak_GBps": peaks["hbm_gbs"],
+                                        "by_entry_point": {k: {"ms_per_step": round(v["ms"] / nprof, 4),
+                                                               "GB_per_step": round(v["bytes"] / nprof / 1e9, 3),
+                                                               "GBps": round(v["bytes"] / 1e9 / (v["ms"] / 1e3), 0),
+                                                               "frac": round(v["bytes"] / 1e9 / (v["ms"] / 1e3) / peaks["hbm_gbs"], 3)}
+                                                           for k, v in sorted(summ.items(), key=lambda kv: -kv[1]["ms"])
+                                                           if v["bytes"] > 0 and v["ms"] > 0}}}
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -220,6 +220,38 @@ class KernelTimer:
 TIMER: "KernelTimer | None" = None
 
 
+def _es(code: int) -> int:
+    return 2 if code == CNB_BF16 else 4
+
+
+def _nn(*ptrs) -> int:
+    return sum(1 for p in ptrs if p)
+
+
+# Algorithmic HBM bytes of the bandwidth-bound entry points, from the C-ABI arguments by position; evaluated only while
+# a KernelTimer is recording (bench.py's roofline pass).
+ALG_BYTES = {
+    "cnb_bn_stats": lambda a: a[1] * a[2] * _es(a[6]),
+    "cnb_bn_train_fwd": lambda a: (2 + _nn(a[13])) * a[15] * a[16] * _es(a[20]),
+    "cnb_bn_act_fwd": lambda a: (2 + _nn(a[3])) * a[5] * a[6] * _es(a[10]),
+    "cnb_bn_act_bwd_reduce": lambda a: 2 * a[6] * a[7] * _es(a[12]),
+    "cnb_bn_act_bwd_apply": lambda a: 3 * a[9] * a[10] * _es(a[15]),
+    "cnb_add_n": lambda a: (_nn(a[0], a[1], a[2], a[3]) + 1) * a[5] * _es(a[6]),
+    "cnb_layernorm_fwd": lambda a: 2 * a[7] * a[8] * _es(a[9]),
+    "cnb_layernorm_bwd": lambda a: 3 * a[8] * a[9] * _es(a[10]),
+    "cnb_na2d_fwd": lambda a: 4 * a[3] * a[4] * a[5] * a[6] * a[7] * _es(a[11]),
+    "cnb_na2d_bwd": lambda a: 8 * a[8] * a[9] * a[10] * a[11] * a[12] * _es(a[16]),
+    "cnb_resize_bilinear_fwd": lambda a: a[2] * a[7] * _es(a[8]) * (a[3] * a[4] + a[5] * a[6]),
+    "cnb_resize_bilinear_bwd": lambda a: a[2] * a[7] * _es(a[8]) * (a[3] * a[4] + a[5] * a[6]),
+    "cnb_time_to_pixel_major": lambda a: a[2] * a[4] * (a[3] * 4 + a[5] * _es(a[6])),
+    "cnb_bias_grad": lambda a: a[2] * a[3] * _es(a[6]),
+    "cnb_adamw_step": lambda a: 28 * a[4],
+    "cnb_grad_sqnorm": lambda a: 4 * a[1],
+    "cnb_tanimoto_fwd": lambda a: 24 * a[2] * a[3],
+    "cnb_tanimoto_bwd": lambda a: 36 * a[2] * a[3],
+}
+
+
 def launch_count() -> int:
     return int(lib().cnb_launch_count())
 
@@ -231,6 +263,11 @@ def call(name: str, *args, flops: float = None, nbytes: float = None, tag: str =
         e0.record()
         rc = fn(*args)
         e1.record()
+        if nbytes is None and name in ALG_BYTES:
+            try:
+                nbytes = float(ALG_BYTES[name](args))
+            except Exception:  # noqa: BLE001 - accounting must never break a launch
+                nbytes = None
         TIMER.records.append((tag or name, flops, nbytes, e0, e1, detail))
     else:
         rc = fn(*args)
