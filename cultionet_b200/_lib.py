@@ -118,6 +118,8 @@ _PROTOS = {
     "cnb_time_to_pixel_major": [_vp, _vp, _i, _i, _i64, _i, _i, _vp],
     "cnb_toeplitz_expand": [_vp, _vp, _i, _i, _i, _i, _vp],
     "cnb_toeplitz_fold": [_vp, _vp, _i, _i, _i, _vp],
+    "cnb_tap_shift_add": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "cnb_tap_shift_gather": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "cnb_final_combine_fwd": [_vp, _vp, _vp, _vp, _f, _i, _vp, _vp, _vp, _i64, _i, _vp],
     "cnb_final_combine_bwd": [_vp, _vp, _vp, _vp, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _vp],
     "cnb_tanimoto_fwd": [C.POINTER(TanimotoTerm), _i, _i, _i64, _f, _i, _vp, _vp, _vp, _vp],

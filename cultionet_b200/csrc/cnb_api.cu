@@ -895,6 +895,34 @@ int cnb_toeplitz_fold(const float* dwt, float* dw1, int C, int T_, int k, void* 
     return CNB_OK;
 }
 
+int cnb_tap_shift_add(const void* t, void* out, int B, int H, int W, int N, int KH, int KW, int pad, int dil, int t_pitch, int out_pitch,
+                      int dtype, void* stream) {
+    CNB_REQUIRE(t && out && B > 0 && H > 0 && W > 0 && N > 0 && N <= 16 && KH > 0 && KW > 0 && dil > 0 && pad >= 0 && t_pitch >= KH * KW * N &&
+                    out_pitch >= N,
+                "tap_shift_add: bad arguments (N <= 16)");
+    const long P = (long)B * H * W;
+    CNB_DISPATCH_DTYPE(dtype, {
+        CNB_LAUNCH((tap_shift_add_kernel<T>), dim3(stream_grid(P, 256, 16)), dim3(256), 0, (cudaStream_t)stream, (const T*)t, (T*)out, B, H, W, N,
+                   KH, KW, pad, dil, t_pitch, out_pitch);
+    });
+    CNB_CHECK_LAUNCH("tap_shift_add_kernel");
+    return CNB_OK;
+}
+
+int cnb_tap_shift_gather(const void* dout, void* dt, int B, int H, int W, int N, int KH, int KW, int pad, int dil, int t_pitch, int out_pitch,
+                         int dtype, void* stream) {
+    CNB_REQUIRE(dout && dt && B > 0 && H > 0 && W > 0 && N > 0 && KH > 0 && KW > 0 && dil > 0 && pad >= 0 && t_pitch >= KH * KW * N &&
+                    out_pitch >= N,
+                "tap_shift_gather: bad arguments");
+    const long total = (long)B * H * W * t_pitch;
+    CNB_DISPATCH_DTYPE(dtype, {
+        CNB_LAUNCH((tap_shift_gather_kernel<T>), dim3(stream_grid(total, 256, 16)), dim3(256), 0, (cudaStream_t)stream, (const T*)dout, (T*)dt,
+                   B, H, W, N, KH, KW, pad, dil, t_pitch, out_pitch);
+    });
+    CNB_CHECK_LAUNCH("tap_shift_gather_kernel");
+    return CNB_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 int cnb_final_combine_fwd(const void* ha, const void* hb, const void* hc, const float* params, float smooth, int flags, float* distance,
                           float* edge, float* crop, int64_t P, int dtype, void* stream) {

@@ -313,6 +313,63 @@ __global__ void __launch_bounds__(256) toeplitz_fold_kernel(const float* __restr
 }
 
 // ---------------------------------------------------------------------------------------------
+// Skinny 3x3 convolutions (the Psi-Net stream heads, 256 -> 9): out[p][n] = sum_tap sum_c x[p + off(tap)][c] w[n][c][tap].
+// As an implicit GEMM with N = 9 the tensor-core kernel re-reads the 256-channel input once per tap from L2 (2.4 GB per call, 0.29 ms,
+// L2-bound).  Instead: t[p][(tap, n)] = sum_c x[p][c] w[n][c][tap] is ONE 1x1 GEMM with N = taps*n (81 -> 88) that reads x once, and
+// the kernels below do the remaining shift-and-add over the narrow t tensor / its adjoint gather (which is also exactly the im2col
+// of dy that the data- and weight-gradient GEMMs of the 1x1 form need).  unit stride, zero padding.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) tap_shift_add_kernel(const T* __restrict__ t, T* __restrict__ out, int B, int H, int W, int N, int KH,
+                                                           int KW, int pad, int dil, int t_pitch, int out_pitch) {
+    const long P = (long)B * H * W;
+    for (long p = (long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long)gridDim.x * blockDim.x) {
+        const int x = (int)(p % W);
+        const int y = (int)((p / W) % H);
+        float acc[16];
+#pragma unroll
+        for (int n = 0; n < 16; ++n) acc[n] = 0.f;
+        for (int ky = 0; ky < KH; ++ky) {
+            const int iy = y + ky * dil - pad;
+            if (iy < 0 || iy >= H) continue;
+            for (int kx = 0; kx < KW; ++kx) {
+                const int ix = x + kx * dil - pad;
+                if (ix < 0 || ix >= W) continue;
+                const T* src = t + (p + (long)(iy - y) * W + (ix - x)) * t_pitch + (ky * KW + kx) * N;
+#pragma unroll
+                for (int n = 0; n < 16; ++n)
+                    if (n < N) acc[n] += cnb_ld(src + n);
+            }
+        }
+#pragma unroll
+        for (int n = 0; n < 16; ++n)
+            if (n < N) cnb_st(out + p * out_pitch + n, acc[n]);
+    }
+}
+
+// adjoint: dt[q][(tap, n)] = dout[q - off(tap)][n] (zero outside the image; columns >= taps*N zero)
+template <typename T>
+__global__ void __launch_bounds__(256) tap_shift_gather_kernel(const T* __restrict__ dout, T* __restrict__ dt, int B, int H, int W, int N,
+                                                              int KH, int KW, int pad, int dil, int t_pitch, int out_pitch) {
+    const long total = (long)B * H * W * t_pitch;
+    const int taps = KH * KW;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int col = (int)(i % t_pitch);
+        const long q = i / t_pitch;
+        float v = 0.f;
+        if (col < taps * N) {
+            const int tap = col / N, n = col - tap * N;
+            const int ky = tap / KW, kx = tap - ky * KW;
+            const int x = (int)(q % W);
+            const int y = (int)((q / W) % H);
+            const int oy = y - (ky * dil - pad), ox = x - (kx * dil - pad);
+            if (oy >= 0 && oy < H && ox >= 0 && ox < W) v = cnb_ld(dout + (q + (long)(oy - y) * W + (ox - x)) * out_pitch + n);
+        }
+        cnb_st(dt + i, v);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // TowerUNetFinalCombine (+ SigmoidCrisp).  params: g[3][3], w[3], b[3], crisp_gamma
 // ---------------------------------------------------------------------------------------------
 template <typename T>

@@ -321,6 +321,46 @@ def conv_transpose2d(x: torch.Tensor, weight, bias=None, ksize=3, stride=2, pad=
     return _Conv2dFn.apply(weight, bias, W_CONVT, ksize, stride, pad, dil, True, None, False, None, x)
 
 
+class _TapShiftAddFn(torch.autograd.Function):
+    """out[p][n] = sum_tap t[p + off(tap)][tap*N + n]; backward = the gather dt[q][tap*N + n] = dout[q - off(tap)][n]."""
+
+    @staticmethod
+    def forward(ctx, t, N, ksize, pad, dil):
+        check_device(t)
+        t = _contig(t)
+        B, H, W, pitch = t.shape
+        out = torch.empty((B, H, W, N), dtype=t.dtype, device=t.device)
+        call("cnb_tap_shift_add", ptr(t), ptr(out), B, H, W, N, ksize, ksize, pad, dil, pitch, N, dtype_code(t.dtype), stream_ptr(t))
+        ctx.meta = (B, H, W, pitch, N, ksize, pad, dil)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, H, W, pitch, N, ksize, pad, dil = ctx.meta
+        dout = _contig(dout)
+        dt = torch.empty((B, H, W, pitch), dtype=dout.dtype, device=dout.device)
+        call("cnb_tap_shift_gather", ptr(dout), ptr(dt), B, H, W, N, ksize, ksize, pad, dil, pitch, N, dtype_code(dout.dtype), stream_ptr(dout))
+        return dt, None, None, None, None
+
+
+SKINNY_MAX_COLS = 128  # taps * N of the intermediate tensor
+
+
+def conv2d_skinny(x: torch.Tensor, weight: torch.Tensor, ksize: int = 3, pad: int = 1, dil: int = 1) -> torch.Tensor:
+    """Unit-stride ``nn.Conv2d(C -> N, k, bias=False)`` with a handful of output channels (taps*N <= 128) as a 1x1 GEMM with
+    taps*N outputs followed by a shift-and-add: the wide input is read once instead of once per tap (see csrc/k_misc.cuh).  The
+    per-tap partial sums pass through the activation dtype before they are added."""
+    N, Cin = weight.shape[0], weight.shape[1]
+    taps = ksize * ksize
+    assert taps * N <= SKINNY_MAX_COLS and N <= 16
+    w2 = weight.permute(2, 3, 0, 1).reshape(taps * N, Cin)  # rows (tap, n)
+    rows = (taps * N + 7) // 8 * 8
+    if rows > taps * N:
+        w2 = torch.nn.functional.pad(w2, (0, 0, 0, rows - taps * N))
+    t = linear(x, w2, None, in_features=Cin)
+    return _TapShiftAddFn.apply(t, N, ksize, pad, dil)
+
+
 def linear(x: torch.Tensor, weight, bias=None, in_features: Optional[int] = None) -> torch.Tensor:
     """nn.Linear over the channel axis of a pixel-major tensor (``in_features`` < last dim: the rest is row padding)."""
     return _Conv2dFn.apply(weight, bias, W_LINEAR, 1, 1, 0, 1, False, None, False, None if in_features is None else (in_features,), x)

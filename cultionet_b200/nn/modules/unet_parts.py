@@ -125,10 +125,14 @@ class TowerUNetFinal(nn.Module):
         w1 = torch.cat([b.seq[0].weight for b in blocks], dim=0)  # [9, C, 3, 3]
         bns = [b.seq[1] for b in blocks]
         training = bns[0].training
-        h = F.conv2d([x], w1, None, ksize=3, stride=1, pad=1, want_stats=training)
         sums = None
-        if training:
-            h, sums = h
+        if x.dtype == torch.bfloat16:
+            # throughput mode: C -> 9 as a 1x1 GEMM (C -> 81) + shift-and-add, so the wide tower tensor is read once, not once per tap
+            h = F.conv2d_skinny(x, w1, ksize=3, pad=1, dil=1)
+        else:
+            h = F.conv2d([x], w1, None, ksize=3, stride=1, pad=1, want_stats=training)
+            if training:
+                h, sums = h
         rm = torch.cat([bn.running_mean for bn in bns])
         rv = torch.cat([bn.running_var for bn in bns])
         h = F.batchnorm_act(h, torch.cat([bn.weight for bn in bns]), torch.cat([bn.bias for bn in bns]), rm, rv, training,

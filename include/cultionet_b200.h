@@ -221,6 +221,17 @@ int cnb_toeplitz_expand(const float* w1, float* wt, int C, int T, int k, int row
 int cnb_toeplitz_fold(const float* dwt, float* dw1, int C, int T, int k, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Skinny-N unit-stride convolution split into a 1x1 GEMM and a shift-and-add (StreamConv2d's first convolution, C -> 3 per stream,
+ * nn/modules/unet_parts.py:205-221): t[p][(tap, n)] = sum_c x[p][c] w[n][c][tap] comes from cnb_conv2d_fwd with a 1x1 kernel;
+ *   cnb_tap_shift_add:    out[p][n] = sum_tap t[p + off(tap)][tap*N + n]   (zero padding, off = (ky*dil - pad, kx*dil - pad))
+ *   cnb_tap_shift_gather: dt[q][tap*N + n] = dout[q - off(tap)][n]          (its adjoint = the im2col of dout; padding columns zero)
+ * ------------------------------------------------------------------------------------------------ */
+int cnb_tap_shift_add(const void* t, void* out, int B, int H, int W, int N, int KH, int KW, int pad, int dil, int t_pitch, int out_pitch,
+                      int dtype, void* stream);
+int cnb_tap_shift_gather(const void* dout, void* dt, int B, int H, int W, int N, int KH, int KW, int pad, int dil, int t_pitch,
+                         int out_pitch, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * TowerUNetFinalCombine + SigmoidCrisp (nn/modules/unet_parts.py:86-98, :148-193)
  *   z_t = w_t * (ha[p][t]/g[t][0] + hb[p][t]/g[t][1] + hc[p][t]/g[t][2]) + b_t,  t in {0 distance, 1 edge, 2 crop}
  *   distance = sigmoid(z_0); edge = sigmoid(z_1 / (smooth + sigmoid(crisp_gamma))); crop = sigmoid(z_2)

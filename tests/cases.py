@@ -183,6 +183,22 @@ def pretime_case(dev, dtype, B, C, T, H, W, k, seed=0):
     _check("pretime wgrad", torch.autograd.grad(u, w1, gp.to(dtype))[0], torch.autograd.grad(ur, w1, g.to(dtype).float())[0], tol)
 
 
+def conv_skinny_case(dev, dtype, B, H, W, cin, cout, k=3, pad=1, dil=1, seed=0):
+    """1x1 GEMM + shift-and-add form of a skinny convolution against torch's conv2d (forward, data and weight gradients)."""
+    torch.manual_seed(seed)
+    x = _mk((B, H, W, cin), dev, dtype)
+    w = (torch.randn(cout, cin, k, k, device=dev) / (cin * k * k) ** 0.5).requires_grad_(True)
+    y = F.conv2d_skinny(x, w, ksize=k, pad=pad, dil=dil)
+    xr = _f(x)
+    yr = TF.conv2d(xr.permute(0, 3, 1, 2), w, None, stride=1, padding=pad, dilation=dil).permute(0, 2, 3, 1)
+    tol = _tol(dtype)
+    assert y.shape == yr.shape
+    _check("skinny conv fwd", y, yr, tol)
+    g = torch.randn_like(yr)
+    for i, (a, c) in enumerate(zip(torch.autograd.grad(y, [x, w], g.to(dtype)), torch.autograd.grad(yr, [xr, w], g.to(dtype).float()))):
+        _check(f"skinny conv grad {i}", a, c, tol * 2)
+
+
 def pretime_gemm_case(dev, dtype, B, C, T, H, W, k, seed=0):
     """The banded-GEMM form of the temporal convolution (throughput mode) against torch's conv3d."""
     torch.manual_seed(seed)

@@ -42,6 +42,14 @@ def test_conv_tensor_core_shapes(dev):
         F.CONV_BACKEND = "auto"
 
 
+def test_conv_skinny_gemm_plus_shift_add(dev):
+    """Psi-Net stream heads (C -> 9, 3x3): 1x1 tcgen05 GEMM to 81 partial-product columns + shift-and-add, and its autograd."""
+    cases.conv_skinny_case(dev, BF16, 2, 64, 64, 256, 9)
+    cases.conv_skinny_case(dev, BF16, 2, 25, 31, 128, 9)
+    cases.conv_skinny_case(dev, BF16, 1, 33, 20, 64, 3, k=3, pad=2, dil=2)
+    cases.conv_skinny_case(dev, F32, 2, 20, 20, 32, 9)
+
+
 @pytest.mark.parametrize("dtype", [F32, BF16])
 @pytest.mark.parametrize("stride", [2, 4])
 def test_conv_transpose(dev, dtype, stride):

@@ -91,6 +91,12 @@ def test_resize_bilinear_vector_kernels(dev, sizes):
     cases.resize_case(dev, BF16, 1, *sizes, 16)
 
 
+def test_conv_skinny_gemm_plus_shift_add(dev):
+    cases.conv_skinny_case(dev, F32, 2, 9, 11, 16, 9)
+    cases.conv_skinny_case(dev, F32, 1, 7, 6, 8, 3, k=3, pad=2, dil=2)
+    cases.conv_skinny_case(dev, BF16, 1, 10, 12, 32, 9)
+
+
 @pytest.mark.parametrize("k", [3, 5])
 def test_pretime_conv(dev, k):
     cases.pretime_case(dev, F32, 2, 3, 12, 5, 6, k)

@@ -63,4 +63,29 @@ for k, v in sorted(summ.items(), key=lambda kv: -kv[1]["ms"]):
         e["GBps"] = round(ALG[k] * unit / 1e9 / (ms / 1e3), 0)
     out[k] = e
     print(k, e)
+# pure-read reference points (library reductions, not ours): is ~4.2 TB/s a property of read-only streams on this part?
+def ev_time(fn, n=5):
+    fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    best = 1e9
+    for _ in range(n):
+        flush.zero_()
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        best = min(best, a.elapsed_time(b))
+    return best
+
+
+xd = x.detach()
+big = torch.empty(1 << 30, dtype=torch.bfloat16, device=dev).normal_()
+for name, fn, nbytes in (("torch.sum bf16 268MB", lambda: xd.sum(dtype=torch.float32), xd.numel() * 2),
+                         ("torch.sum bf16 2GB", lambda: big.sum(dtype=torch.float32), big.numel() * 2),
+                         ("torch.amax bf16 2GB", lambda: big.amax(), big.numel() * 2),
+                         ("torch copy bf16 2GB->2GB", lambda: big[: 1 << 29].copy_(big[1 << 29:]), big.numel() * 2)):
+    ms = ev_time(fn)
+    out[name] = {"ms": round(ms, 4), "GBps": round(nbytes / 1e9 / (ms / 1e3), 0)}
+    print(name, out[name])
 print(json.dumps(out))
