@@ -29,6 +29,7 @@ constexpr int CG_BM = 64, CG_BN = 64, CG_BK = 16, CG_PAD = 4;
 
 template <typename T>
 __global__ void __launch_bounds__(256) conv_fwd_generic_kernel(cnb_conv_desc d) {
+    CNB_PDL_SYNC();
     __shared__ float As[CG_BK][CG_BM + CG_PAD];
     __shared__ float Bs[CG_BK][CG_BN + CG_PAD];
     const int tid = threadIdx.x;
@@ -120,6 +121,7 @@ __global__ void __launch_bounds__(256) conv_fwd_generic_kernel(cnb_conv_desc d) 
 // dWp[tap][n][k_off + c] += sum over a slice of the pixels.  grid = (ceil(Cs/64), ceil(N/64), taps*splits)
 template <typename T>
 __global__ void __launch_bounds__(256) conv_wgrad_generic_kernel(cnb_wgrad_desc d, int splits, long m_per_split) {
+    CNB_PDL_SYNC();
     __shared__ float As[CG_BK][CG_BM + CG_PAD];  // [pixel in chunk][source channel]
     __shared__ float Bs[CG_BK][CG_BN + CG_PAD];  // [pixel in chunk][output channel]
     const int tid = threadIdx.x;
@@ -202,6 +204,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_generic_kernel(cnb_wgrad_desc 
 template <typename T>
 __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ wp, int taps, int N, int K, int pitch, long s_n, long s_k,
                                    long s_tap) {
+    CNB_PDL_SYNC();
     const long total = (long)taps * N * pitch;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         const int k = (int)(i % pitch);
@@ -214,6 +217,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
 
 __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ g, int taps, int N, int K, long s_n, long s_k,
                                     long s_tap, int accumulate) {
+    CNB_PDL_SYNC();
     const long total = (long)taps * N * K;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         const int k = (int)(i % K);
@@ -266,6 +270,7 @@ __device__ __forceinline__ void pack_weight_tile(float* tile, const float* __res
 template <typename T>
 __global__ void __launch_bounds__(256) pack_weight_tiled_kernel(const float* __restrict__ w, T* __restrict__ wp, T* __restrict__ wd, int taps,
                                                                int N, int K, int pitch_k, int pitch_n, long s_n, long s_k, long s_tap) {
+    CNB_PDL_SYNC();
     CNB_DYN_SMEM(sm_raw);  // float tile[taps][PW_T][PW_T + 1]
     pack_weight_tile<T>(reinterpret_cast<float*>(sm_raw), w, wp, wd, taps, N, K, pitch_k, pitch_n, s_n, s_k, s_tap, blockIdx.y * PW_T,
                         blockIdx.x * PW_T);
@@ -275,6 +280,7 @@ __global__ void __launch_bounds__(256) pack_weight_tiled_kernel(const float* __r
 // one CTA per 32 x 32 tile of any of them.  96 separate launches of 64-320 CTAs each cost 2.1 ms per step (ncu), the work is ~0.1 ms.
 template <typename T>
 __global__ void __launch_bounds__(256) pack_weight_batched_kernel(const cnb_pack_desc* __restrict__ table, int ndesc) {
+    CNB_PDL_SYNC();
     CNB_DYN_SMEM(sm_raw);
     int lo = 0, hi = ndesc - 1;  // last descriptor whose tile0 <= blockIdx.x
     while (lo < hi) {
@@ -293,6 +299,7 @@ __global__ void __launch_bounds__(256) pack_weight_batched_kernel(const cnb_pack
 // g[n*s_n + k*s_k + tap*s_tap] (+)= dwp[tap][n][k], written in the parameter's memory order
 __global__ void __launch_bounds__(256) unpack_wgrad_tiled_kernel(const float* __restrict__ dwp, float* __restrict__ g, int taps, int N, int K,
                                                                 long s_n, long s_k, long s_tap, int accumulate) {
+    CNB_PDL_SYNC();
     CNB_DYN_SMEM(sm_raw);
     float* tile = reinterpret_cast<float*>(sm_raw);
     const int n0 = blockIdx.y * PW_T, k0 = blockIdx.x * PW_T;
@@ -323,6 +330,7 @@ __global__ void __launch_bounds__(256) unpack_wgrad_tiled_kernel(const float* __
 // db[n] += sum_p dy[p][n]; grid = (ceil(N/32), pixel splits); 8 pixel lanes per channel column, one atomic per CTA column
 template <typename T>
 __global__ void __launch_bounds__(256) bias_grad_kernel(const T* __restrict__ dy, int dy_stride, long P, int N, float* __restrict__ db) {
+    CNB_PDL_SYNC();
     __shared__ float red[8][33];
     const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
     const int n = blockIdx.x * 32 + cx;

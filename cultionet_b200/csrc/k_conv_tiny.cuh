@@ -26,6 +26,7 @@ inline bool wgrad_tiny_eligible(const cnb_wgrad_desc* d) {
 
 template <typename T>
 __global__ void __launch_bounds__(256) conv_tiny_kernel(cnb_conv_desc d, int ctot) {
+    CNB_PDL_SYNC();
     __shared__ float ws[TINY_MAX_TAPS * TINY_MAX_N * TINY_MAX_C];
     __shared__ float bs[TINY_MAX_N];
     const int taps = d.KH * d.KW;
@@ -81,6 +82,7 @@ __global__ void __launch_bounds__(256) conv_tiny_kernel(cnb_conv_desc d, int cto
 // on predicated-off FMAs of a 16-wide accumulator and one LDS per FMA (ncu: 70-150 us per launch for 9.4 MB of input).
 template <typename T, int N, int C>
 __global__ void __launch_bounds__(256) conv_tiny_fixed_kernel(cnb_conv_desc d) {
+    CNB_PDL_SYNC();
     constexpr int NP = (N + 3) / 4 * 4;  // weights of one (tap, c) padded to whole float4
     __shared__ __align__(16) float ws[TINY_MAX_TAPS * C * NP];
     __shared__ float bs[NP];
@@ -136,6 +138,7 @@ __global__ void __launch_bounds__(256) conv_tiny_fixed_kernel(cnb_conv_desc d) {
 // dWp[tap][n][k_off + c] += sum_p dY[p][n] * X[gather(p, tap)][c]; grid = (pixel blocks, taps, 4-channel chunks of the source)
 template <typename T>
 __global__ void __launch_bounds__(256) conv_tiny_wgrad_kernel(cnb_wgrad_desc d) {
+    CNB_PDL_SYNC();
     __shared__ float red[TINY_WG_MAX_N * TINY_WG_MAX_C];
     const int tap = blockIdx.y;
     const int cbase = blockIdx.z * TINY_WG_MAX_C;
@@ -191,6 +194,7 @@ __global__ void __launch_bounds__(256) conv_tiny_wgrad_kernel(cnb_wgrad_desc d) 
 // dst[p][0..C) = src[p][0..C), dst[p][C..dst_stride) = 0: gives a skinny tensor the 16-byte pixel pitch TMA needs
 template <typename T>
 __global__ void repitch_kernel(const T* __restrict__ src, int src_stride, T* __restrict__ dst, int dst_stride, long P, int C) {
+    CNB_PDL_SYNC();
     const long total = P * dst_stride;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         const int c = (int)(i % dst_stride);

@@ -44,6 +44,7 @@ __device__ __forceinline__ void tanimoto_elem(const cnb_tanimoto_term& tm, long 
 
 // grid = (chunks, B, nterms); sums[(term*B + b)*4 + {P, S, St, Sp}] in fp64
 __global__ void __launch_bounds__(256) tanimoto_sums_kernel(TanimotoTerms terms, int B, long HW, double* __restrict__ sums) {
+    CNB_PDL_SYNC();
     __shared__ double sh[4];
     if (threadIdx.x < 4) sh[threadIdx.x] = 0.0;
     __syncthreads();
@@ -93,6 +94,7 @@ __device__ __forceinline__ void tanimoto_T(double P, double S, double eps, int d
 __global__ void __launch_bounds__(256) tanimoto_finalize_kernel(TanimotoTerms terms, int nterms, int B, long HW, float smooth, int depth,
                                                                const double* __restrict__ sums, float* __restrict__ coef,
                                                                float* __restrict__ loss) {
+    CNB_PDL_SYNC();
     __shared__ double lsum[TN_MAX_TERMS];
     if (threadIdx.x < TN_MAX_TERMS) lsum[threadIdx.x] = 0.0;
     __syncthreads();
@@ -126,6 +128,7 @@ __global__ void __launch_bounds__(256) tanimoto_finalize_kernel(TanimotoTerms te
 // dpred = g * mask * (c0 t' + c1 p' + c2 (1-t') + c3 (1-p'))
 __global__ void __launch_bounds__(256) tanimoto_bwd_kernel(TanimotoTerms terms, int B, long HW, const float* __restrict__ coef,
                                                           const float* __restrict__ gscale) {
+    CNB_PDL_SYNC();
     const int term = blockIdx.z;
     const long b = blockIdx.y;
     const cnb_tanimoto_term& tm = terms.t[term];
@@ -144,6 +147,7 @@ __global__ void __launch_bounds__(256) tanimoto_bwd_kernel(TanimotoTerms terms, 
 // optimiser
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) grad_sqnorm_kernel(const float* __restrict__ g, long n, float* __restrict__ out) {
+    CNB_PDL_SYNC();
     __shared__ float sh;
     if (threadIdx.x == 0) sh = 0.f;
     __syncthreads();
@@ -160,6 +164,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
                                                    float* __restrict__ v, long n, const float* __restrict__ hyper, float beta1,
                                                    float beta2, float eps, float wd, float grad_scale, float clip_norm,
                                                    const float* __restrict__ norm_ws) {
+    CNB_PDL_SYNC();
     const float lr = hyper[0], step = hyper[1];
     float gs = grad_scale;
     if (clip_norm > 0.f) {

@@ -20,6 +20,7 @@ __device__ __forceinline__ void bilinear_src(int o, float rscale, int in_len, in
 template <typename T>
 __global__ void __launch_bounds__(256) resize_bilinear_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int Hin, int Win,
                                                                  int Hout, int Wout, int C, float rh, float rw) {
+    CNB_PDL_SYNC();
     const long total = (long)B * Hout * Wout * C;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         const int c = (int)(i % C);
@@ -68,6 +69,7 @@ __device__ __forceinline__ void bilinear_candidates(int i, float rscale, int out
 template <typename T>
 __global__ void __launch_bounds__(256) resize_bilinear_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int B, int Hin, int Win,
                                                                  int Hout, int Wout, int C, float rh, float rw) {
+    CNB_PDL_SYNC();
     const long total = (long)B * Hin * Win * C;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         const int c = (int)(i % C);
@@ -114,6 +116,7 @@ constexpr int PT_MAX_K = 8;
 template <typename T>
 __global__ void __launch_bounds__(PT_THREADS) pretime_conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w1,
                                                                      T* __restrict__ u, int B, int C, int Tn, int H, int W, int k, int up) {
+    CNB_PDL_SYNC();
     CNB_DYN_SMEM(sm_raw);
     const int Tp = Tn - k + 1;
     const int CT = C * Tn;
@@ -173,6 +176,7 @@ template <typename T>
 __global__ void __launch_bounds__(PT_THREADS) pretime_conv_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ du,
                                                                        float* __restrict__ dw1, int B, int C, int Tn, int H, int W, int k,
                                                                        int up) {
+    CNB_PDL_SYNC();
     CNB_DYN_SMEM(sm_raw);
     const int Tp = Tn - k + 1;
     const int CT = C * Tn;
@@ -246,6 +250,7 @@ constexpr int TP_XPITCH = TP_PIX + 1;
 template <typename T>
 __global__ void __launch_bounds__(256) time_to_pixel_major_kernel(const float* __restrict__ x, T* __restrict__ xp, int B, int CT, long HW,
                                                                  int pitch) {
+    CNB_PDL_SYNC();
     constexpr int V = cnb_vec<T>::N;
     CNB_DYN_SMEM(sm_raw);
     float* xs = reinterpret_cast<float*>(sm_raw);
@@ -288,6 +293,7 @@ __global__ void __launch_bounds__(256) time_to_pixel_major_kernel(const float* _
 // Wt[n][c*T + t] (n < rows; rows past C*T' are zero)
 __global__ void __launch_bounds__(256) toeplitz_expand_kernel(const float* __restrict__ w1, float* __restrict__ wt, int C, int Tn, int k,
                                                              int rows) {
+    CNB_PDL_SYNC();
     const int Tp = Tn - k + 1, CT = C * Tn;
     const int total = rows * CT;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -301,6 +307,7 @@ __global__ void __launch_bounds__(256) toeplitz_expand_kernel(const float* __res
 
 // dw1[c2][c][dt] = sum_t' dWt[c2*T' + t'][c*T + t' + dt]
 __global__ void __launch_bounds__(256) toeplitz_fold_kernel(const float* __restrict__ dwt, float* __restrict__ dw1, int C, int Tn, int k) {
+    CNB_PDL_SYNC();
     const int Tp = Tn - k + 1, CT = C * Tn;
     const int total = C * C * k;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -322,6 +329,7 @@ __global__ void __launch_bounds__(256) toeplitz_fold_kernel(const float* __restr
 template <typename T>
 __global__ void __launch_bounds__(256) tap_shift_add_kernel(const T* __restrict__ t, T* __restrict__ out, int B, int H, int W, int N, int KH,
                                                            int KW, int pad, int dil, int t_pitch, int out_pitch) {
+    CNB_PDL_SYNC();
     const long P = (long)B * H * W;
     for (long p = (long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long)gridDim.x * blockDim.x) {
         const int x = (int)(p % W);
@@ -351,6 +359,7 @@ __global__ void __launch_bounds__(256) tap_shift_add_kernel(const T* __restrict_
 template <typename T>
 __global__ void __launch_bounds__(256) tap_shift_gather_kernel(const T* __restrict__ dout, T* __restrict__ dt, int B, int H, int W, int N,
                                                               int KH, int KW, int pad, int dil, int t_pitch, int out_pitch) {
+    CNB_PDL_SYNC();
     const long total = (long)B * H * W * t_pitch;
     const int taps = KH * KW;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -377,6 +386,7 @@ __global__ void __launch_bounds__(256) final_combine_fwd_kernel(const T* __restr
                                                                const T* __restrict__ hc, const float* __restrict__ prm, float smooth,
                                                                int flags, float* __restrict__ dist, float* __restrict__ edge,
                                                                float* __restrict__ crop, long P) {
+    CNB_PDL_SYNC();
     float ig[9], w[3], bb[3];
 #pragma unroll
     for (int i = 0; i < 9; ++i) ig[i] = 1.0f / prm[i];
@@ -408,6 +418,7 @@ __global__ void __launch_bounds__(256) final_combine_bwd_kernel(const T* __restr
                                                                const float* __restrict__ d_edge, const float* __restrict__ d_crop,
                                                                T* __restrict__ dha, T* __restrict__ dhb, T* __restrict__ dhc,
                                                                float* __restrict__ red, long P) {
+    CNB_PDL_SYNC();
     __shared__ float sh[13];
     if (threadIdx.x < 13) sh[threadIdx.x] = 0.f;
     __syncthreads();
@@ -472,6 +483,7 @@ __global__ void __launch_bounds__(256) final_combine_bwd_kernel(const T* __restr
 
 __global__ void final_combine_param_grad_kernel(const float* __restrict__ prm, const float* __restrict__ red, float smooth, int flags,
                                                 float* __restrict__ dprm) {
+    CNB_PDL_SYNC();
     const int i = threadIdx.x;
     if (i < 9) {
         const int t = i / 3;

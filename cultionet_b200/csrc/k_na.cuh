@@ -23,6 +23,7 @@ __device__ __forceinline__ int na_window_start(int index, int length, int ksize,
 template <typename T>
 __global__ void __launch_bounds__(256) na2d_fwd_kernel(const T* __restrict__ qkv, T* __restrict__ out, int B, int H, int W, int heads,
                                                       int hd, int ksize, int dil, float scale) {
+    CNB_PDL_SYNC();
     const int lane = threadIdx.x & 31;
     const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
@@ -94,6 +95,7 @@ __global__ void __launch_bounds__(256) na2d_fwd_kernel(const T* __restrict__ qkv
 template <typename T>
 __global__ void __launch_bounds__(256) na2d_bwd_kernel(const T* __restrict__ qkv, const T* __restrict__ dout, float* __restrict__ dacc,
                                                       int B, int H, int W, int heads, int hd, int ksize, int dil, float scale) {
+    CNB_PDL_SYNC();
     const int lane = threadIdx.x & 31;
     const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
@@ -180,6 +182,7 @@ __global__ void __launch_bounds__(256) na2d_bwd_kernel(const T* __restrict__ qkv
 
 template <typename T>
 __global__ void __launch_bounds__(256) cast_from_f32_kernel(const float* __restrict__ src, T* __restrict__ dst, long n) {
+    CNB_PDL_SYNC();
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) cnb_st(dst + i, src[i]);
 }
 
@@ -259,6 +262,7 @@ __device__ __forceinline__ void na_kv_ptr(const T* sm, const T* qkv, const NaTil
 template <typename T, int LPH>
 __global__ void __launch_bounds__(NA_TILE_THREADS) na2d_fwd_tile_kernel(const T* __restrict__ qkv, T* __restrict__ out,
                                                                        float* __restrict__ lse, NaTile g) {
+    CNB_PDL_SYNC();
     constexpr int V = cnb_vec<T>::N;
     CNB_DYN_SMEM(sm_raw);
     T* sm = reinterpret_cast<T*>(sm_raw);
@@ -329,6 +333,7 @@ template <typename T, int LPH>
 __global__ void __launch_bounds__(NA_TILE_THREADS) na2d_bwd_dq_tile_kernel(const T* __restrict__ qkv, const T* __restrict__ dout,
                                                                           const T* __restrict__ out, const float* __restrict__ lse,
                                                                           float* __restrict__ dvec, T* __restrict__ dqkv, NaTile g) {
+    CNB_PDL_SYNC();
     constexpr int V = cnb_vec<T>::N;
     CNB_DYN_SMEM(sm_raw);
     T* sm = reinterpret_cast<T*>(sm_raw);
@@ -419,6 +424,7 @@ template <typename T, int LPH>
 __global__ void __launch_bounds__(NA_TILE_THREADS) na2d_bwd_dkv_tile_kernel(const T* __restrict__ qkv, const T* __restrict__ dout,
                                                                            const float* __restrict__ lse, const float* __restrict__ dvec,
                                                                            T* __restrict__ dqkv, NaTile g) {
+    CNB_PDL_SYNC();
     constexpr int V = cnb_vec<T>::N;
     CNB_DYN_SMEM(sm_raw);
     T* sm = reinterpret_cast<T*>(sm_raw);

@@ -84,6 +84,7 @@ __device__ __forceinline__ TilePos tile_pos(const NaTile& g) {
 template <int KS, int DIL, int LPH>
 __global__ void __launch_bounds__(NA_TILE_THREADS) na2d_fwd_fast_kernel(const bf16_t* __restrict__ qkv, bf16_t* __restrict__ out,
                                                                        float* __restrict__ lse, NaTile g) {
+    CNB_PDL_SYNC();
     constexpr int HD = LPH * 8, K2 = KS * KS;
     CNB_DYN_SMEM(sm_raw);
     bf16_t* sm = reinterpret_cast<bf16_t*>(sm_raw);
@@ -147,6 +148,7 @@ template <int KS, int DIL, int LPH>
 __global__ void __launch_bounds__(NA_TILE_THREADS) na2d_bwd_dq_fast_kernel(const bf16_t* __restrict__ qkv, const bf16_t* __restrict__ dout,
                                                                           const bf16_t* __restrict__ out, const float* __restrict__ lse,
                                                                           float2* __restrict__ pds, bf16_t* __restrict__ dqkv, NaTile g) {
+    CNB_PDL_SYNC();
     constexpr int HD = LPH * 8, K2 = KS * KS;
     CNB_DYN_SMEM(sm_raw);
     bf16_t* sm = reinterpret_cast<bf16_t*>(sm_raw);
@@ -222,6 +224,7 @@ template <int KS, int DIL, int LPH>
 __global__ void __launch_bounds__(NA_TILE_THREADS) na2d_bwd_dkv_fast_kernel(const bf16_t* __restrict__ qkv, const bf16_t* __restrict__ dout,
                                                                            const float2* __restrict__ pds, bf16_t* __restrict__ dqkv,
                                                                            NaTile g) {
+    CNB_PDL_SYNC();
     constexpr int HD = LPH * 8, K2 = KS * KS;
     CNB_DYN_SMEM(sm_raw);
     bf16_t* sm = reinterpret_cast<bf16_t*>(sm_raw);

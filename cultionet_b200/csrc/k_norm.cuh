@@ -12,6 +12,7 @@ constexpr int BN_SMEM_C = 512;  // channels reduced through shared memory; above
 template <typename T>
 __global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ x, long total, int L, int C, int ch_div, long stride,
                                                       float* __restrict__ sums) {
+    CNB_PDL_SYNC();
     __shared__ float sh[2 * BN_SMEM_C];
     const bool use_sh = C <= BN_SMEM_C;
     if (use_sh) {
@@ -48,6 +49,7 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ x, 
 __global__ void bn_finalize_kernel(const float* __restrict__ sums, long count, int C, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float eps, float momentum, float* running_mean, float* running_var,
                                    float* save_mean, float* save_rstd, float* scale, float* shift) {
+    CNB_PDL_SYNC();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     float mean, var;
@@ -77,6 +79,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const T* __restrict__ x, const float* __restrict__ scale,
                                                         const float* __restrict__ shift, const T* __restrict__ residual,
                                                         T* __restrict__ y, long total, int L, int C, int ch_div, int act) {
+    CNB_PDL_SYNC();
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         const int col = (int)(i % L);
         const int ch = col / ch_div;
@@ -97,6 +100,7 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(const T* __restr
                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                long total, int L, int C, int ch_div, int act, long stride,
                                                                float* __restrict__ dsums) {
+    CNB_PDL_SYNC();
     __shared__ float sh[2 * BN_SMEM_C];
     const bool use_sh = C <= BN_SMEM_C;
     if (use_sh) {
@@ -140,6 +144,7 @@ __global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(const T* __restri
                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
                                                               const float* __restrict__ dsums, float inv_count, T* __restrict__ dx,
                                                               long total, int L, int C, int ch_div, int act, int train_stats) {
+    CNB_PDL_SYNC();
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         const int col = (int)(i % L);
         const int ch = col / ch_div;
@@ -164,6 +169,7 @@ __global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(const T* __restri
 template <typename T>
 __global__ void __launch_bounds__(256) add_n_kernel(const T* __restrict__ a, const T* __restrict__ b, const T* __restrict__ c,
                                                    const T* __restrict__ d, T* __restrict__ out, long n) {
+    CNB_PDL_SYNC();
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
         float v = cnb_ld(a + i) + cnb_ld(b + i);
         if (c) v += cnb_ld(c + i);
@@ -179,6 +185,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, float eps, T* __restrict__ y,
                                                            float* __restrict__ save_mean, float* __restrict__ save_rstd, long P, int C) {
+    CNB_PDL_SYNC();
     const int lane = threadIdx.x & 31;
     const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
@@ -208,6 +215,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict_
                                                            const float* __restrict__ gamma, const float* __restrict__ save_mean,
                                                            const float* __restrict__ save_rstd, T* __restrict__ dx,
                                                            float* __restrict__ dgamma, float* __restrict__ dbeta, long P, int C) {
+    CNB_PDL_SYNC();
     const int lane = threadIdx.x & 31;
     const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;

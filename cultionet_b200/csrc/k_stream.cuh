@@ -152,6 +152,7 @@ __device__ __forceinline__ void s_flush_sums(float* sh, int C, const int (&chn)[
 // sums[0..C) += sum x, sums[C..2C) += sum x^2
 __global__ void __launch_bounds__(THREADS, 2) bn_stats_stream_kernel(const bf16_t* __restrict__ x, long total_v, int CV, int C, int ch_div,
                                                                     float* __restrict__ sums) {
+    CNB_PDL_SYNC();
     CNB_DYN_SMEM(smem);
     float* sh = reinterpret_cast<float*>(smem + smem_bytes<1, S1>());
     for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
@@ -183,6 +184,7 @@ __global__ void __launch_bounds__(THREADS, 2) bn_act_fwd_stream_kernel(const bf1
                                                                       const float* __restrict__ shift, const bf16_t* __restrict__ residual,
                                                                       bf16_t* __restrict__ y, long total_v, int CV, int C, int ch_div,
                                                                       int act) {
+    CNB_PDL_SYNC();
     CNB_DYN_SMEM(smem);
     int chn[8];
     s_channels(CV, C, ch_div, chn);
@@ -230,6 +232,7 @@ __global__ void __launch_bounds__(THREADS, 2) bn_train_fwd_stream_kernel(const b
                                                                         float* __restrict__ shift, const bf16_t* __restrict__ residual,
                                                                         bf16_t* __restrict__ y, long total_v, int CV, int C, int ch_div,
                                                                         int act) {
+    CNB_PDL_SYNC();
     CNB_DYN_SMEM(smem);
     const float inv = 1.0f / (float)count;
     if (blockIdx.x == 0) {
@@ -298,6 +301,7 @@ __global__ void __launch_bounds__(THREADS, 2) bn_act_bwd_reduce_stream_kernel(co
                                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                              long total_v, int CV, int C, int ch_div, int act,
                                                                              float* __restrict__ dsums) {
+    CNB_PDL_SYNC();
     CNB_DYN_SMEM(smem);
     float* sh = reinterpret_cast<float*>(smem + smem_bytes<2, S2>());
     for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
@@ -342,6 +346,7 @@ __global__ void __launch_bounds__(THREADS, 2) bn_act_bwd_apply_stream_kernel(con
                                                                             const float* __restrict__ dsums, float inv_count,
                                                                             bf16_t* __restrict__ dx, long total_v, int CV, int C, int ch_div,
                                                                             int act, int train_stats) {
+    CNB_PDL_SYNC();
     CNB_DYN_SMEM(smem);
     int chn[8];
     s_channels(CV, C, ch_div, chn);

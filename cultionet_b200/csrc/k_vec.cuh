@@ -17,6 +17,7 @@ namespace cnb {
 template <typename T>
 __global__ void __launch_bounds__(256) bn_stats_vec_kernel(const T* __restrict__ x, long total_v, int CV, long stride_v, int C,
                                                           int ch_div, float* __restrict__ sums) {
+    CNB_PDL_SYNC();
     constexpr int V = cnb_vec<T>::N;
     CNB_DYN_SMEM(sh_raw);  // 2*C floats
     float* sh_dyn = reinterpret_cast<float*>(sh_raw);
@@ -63,6 +64,7 @@ __global__ void __launch_bounds__(256) bn_act_fwd_vec_kernel(const T* __restrict
                                                             const float* __restrict__ shift, const T* __restrict__ residual,
                                                             T* __restrict__ y, long total_v, int CV, long stride_v, int C, int ch_div,
                                                             int act) {
+    CNB_PDL_SYNC();
     constexpr int V = cnb_vec<T>::N;
     const long gid = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= stride_v) return;
@@ -103,6 +105,7 @@ __global__ void __launch_bounds__(256, 3) bn_act_bwd_reduce_vec_kernel(const T* 
                                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                    long total_v, int CV, long stride_v, int C, int ch_div, int act,
                                                                    float* __restrict__ dsums) {
+    CNB_PDL_SYNC();
     constexpr int V = cnb_vec<T>::N;
     CNB_DYN_SMEM(sh_raw);
     float* sh_dyn = reinterpret_cast<float*>(sh_raw);
@@ -166,6 +169,7 @@ __global__ void __launch_bounds__(256, 3) bn_act_bwd_apply_vec_kernel(const T* _
                                                                   const float* __restrict__ dsums, float inv_count, T* __restrict__ dx,
                                                                   long total_v, int CV, long stride_v, int C, int ch_div, int act,
                                                                   int train_stats) {
+    CNB_PDL_SYNC();
     constexpr int V = cnb_vec<T>::N;
     const long gid = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= stride_v) return;
@@ -212,6 +216,7 @@ __global__ void __launch_bounds__(256, 3) bn_act_bwd_apply_vec_kernel(const T* _
 template <typename T>
 __global__ void __launch_bounds__(256) add_n_vec_kernel(const T* __restrict__ a, const T* __restrict__ b, const T* __restrict__ c,
                                                        const T* __restrict__ d, T* __restrict__ out, long n_v) {
+    CNB_PDL_SYNC();
     constexpr int V = cnb_vec<T>::N;
 #pragma unroll 2
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n_v; i += (long)gridDim.x * blockDim.x) {
@@ -238,6 +243,7 @@ __global__ void __launch_bounds__(256) add_n_vec_kernel(const T* __restrict__ a,
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ dy, long total_v, int CV, long stride_v, int N,
                                                         float* __restrict__ db) {
+    CNB_PDL_SYNC();
     constexpr int V = cnb_vec<T>::N;
     CNB_DYN_SMEM(sh_raw);
     float* sh_dyn = reinterpret_cast<float*>(sh_raw);
@@ -277,6 +283,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_vec_kernel(const T* __restr
                                                                const float* __restrict__ beta, float eps, T* __restrict__ y,
                                                                float* __restrict__ save_mean, float* __restrict__ save_rstd, long P,
                                                                int C) {
+    CNB_PDL_SYNC();
     constexpr int V = cnb_vec<T>::N;
     const int lane = threadIdx.x & 31;
     const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -339,6 +346,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_vec_kernel(const T* __restr
                                                                const float* __restrict__ gamma, const float* __restrict__ save_mean,
                                                                const float* __restrict__ save_rstd, T* __restrict__ dx,
                                                                float* __restrict__ dgamma, float* __restrict__ dbeta, long P, int C) {
+    CNB_PDL_SYNC();
     constexpr int V = cnb_vec<T>::N;
     CNB_DYN_SMEM(sh_raw);  // 2*C floats
     float* sh_dyn = reinterpret_cast<float*>(sh_raw);
@@ -421,6 +429,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_vec_kernel(const T* __restr
 template <typename T>
 __global__ void __launch_bounds__(256) resize_bilinear_fwd_vec_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int Hin, int Win,
                                                                      int Hout, int Wout, int C, float rh, float rw) {
+    CNB_PDL_SYNC();
     constexpr int V = cnb_vec<T>::N;
     const int CV = C / V;
     const int oy = blockIdx.x % Hout;
@@ -453,6 +462,7 @@ __global__ void __launch_bounds__(256) resize_bilinear_fwd_vec_kernel(const T* _
 template <typename T>
 __global__ void __launch_bounds__(256) resize_bilinear_bwd_vec_kernel(const T* __restrict__ dy, T* __restrict__ dx, int B, int Hin,
                                                                      int Win, int Hout, int Wout, int C, float rh, float rw) {
+    CNB_PDL_SYNC();
     constexpr int V = cnb_vec<T>::N;
     constexpr int MAXC = 6;  // candidate output rows / columns handled with per-axis weight tables
     const int CV = C / V;
@@ -539,6 +549,7 @@ __device__ __forceinline__ void bilinear_support(int i, float rscale, int in_len
 template <typename T>
 __global__ void __launch_bounds__(256) resize_bilinear_bwd_tab_kernel(const T* __restrict__ dy, T* __restrict__ dx, int B, int Hin, int Win,
                                                                      int Hout, int Wout, int C, float rh, float rw) {
+    CNB_PDL_SYNC();
     constexpr int V = cnb_vec<T>::N;
     CNB_DYN_SMEM(sm_raw);  // int xfirst[Win]; float wx[Win][RB_NC]; int yfirst; float wy[RB_NC]
     int* xfirst = reinterpret_cast<int*>(sm_raw);

@@ -50,6 +50,7 @@
 #define __align__(n) __attribute__((aligned(n)))
 
 #define CNB_MEMSET_ASYNC(ptr, val, bytes, stream) memset((ptr), (val), (bytes))
+#define CNB_PDL_SYNC() ((void)0)
 #define CNB_PEEK_ERROR() cudaSuccess
 #define CNB_CLEAR_ERROR() ((void)0)
 #define CNB_ERROR_STRING(e) "emu"
