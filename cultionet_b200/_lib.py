@@ -126,6 +126,20 @@ _PROTOS = {
     "cnb_tanimoto_bwd": [C.POINTER(TanimotoTerm), _i, _i, _i64, _vp, _vp, _vp],
     "cnb_grad_sqnorm": [_vp, _i64, _vp, _vp],
     "cnb_adamw_step": [_vp, _vp, _vp, _vp, _i64, _vp, _f, _f, _f, _f, _f, _f, _vp, _vp],
+    "cnb_adaptive_maxpool_fwd": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "cnb_adaptive_maxpool_bwd": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "cnb_silu_fwd": [_vp, _vp, _i64, _i, _vp],
+    "cnb_silu_bwd": [_vp, _vp, _vp, _i64, _i, _vp],
+    "cnb_sca_slices": [_i, _i, _i, _i],
+    "cnb_sca_pool_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "cnb_sca_pool_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "cnb_sca_apply_fwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "cnb_sca_apply_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "cnb_rng_advance": [_vp, _vp],
+    "cnb_na2d_dropout_fwd": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _i, _f, _i, _vp],
+    "cnb_na2d_dropout_bwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _i, _f, _i, _vp],
+    "cnb_dropout": [_vp, _vp, _i64, _vp, _i, _f, _i, _vp],
+    "cnb_dropout2d": [_vp, _vp, _i, _i, _i, _vp, _i, _f, _i, _vp],
 }
 
 # entry points that only exist in the nvcc build (tcgen05 / TMA kernels); filled in by later sections

@@ -12,6 +12,7 @@
 #include "k_norm.cuh"
 #include "k_vec.cuh"
 #include "k_stream.cuh"
+#include "k_pool_attn.cuh"
 
 using namespace cnb;
 
@@ -726,9 +727,47 @@ int cnb_na2d_fwd(const void* qkv, void* out, float* lse, int B, int H, int W, in
     const long items = (long)B * H * W * heads;
     CNB_DISPATCH_DTYPE(dtype, {
         CNB_LAUNCH((na2d_fwd_kernel<T>), dim3(stream_grid(items, 8)), dim3(256), 0, (cudaStream_t)stream, (const T*)qkv, (T*)out, B, H, W, heads,
-                   hd, ksize, dilation, scale);
+                   hd, ksize, dilation, scale, NaDrop{nullptr, 0, 0u, 1.0f});
     });
     CNB_CHECK_LAUNCH("na2d_fwd_kernel");
+    return CNB_OK;
+}
+
+static inline NaDrop na_drop(const void* rng_state, int site, float p) {
+    long t = lroundf(p * 65536.0f);
+    t = t < 0 ? 0 : (t > 65536 ? 65536 : t);
+    return NaDrop{(const int64_t*)rng_state, site, (uint32_t)t, 1.0f / (1.0f - p)};
+}
+
+// training-mode attention dropout (attn_drop > 0): the one-warp-per-(pixel, head) kernels with a keep mask on the probabilities
+int cnb_na2d_dropout_fwd(const void* qkv, void* out, int B, int H, int W, int heads, int hd, int ksize, int dilation, float scale,
+                         const void* rng_state, int site, float p, int dtype, void* stream) {
+    int rc = check_na(B, H, W, heads, hd, ksize, dilation);
+    if (rc) return rc;
+    CNB_REQUIRE(qkv && out && rng_state && p >= 0.f && p < 1.f, "na2d_dropout_fwd: bad arguments");
+    const long items = (long)B * H * W * heads;
+    CNB_DISPATCH_DTYPE(dtype, {
+        CNB_LAUNCH((na2d_fwd_kernel<T>), dim3(stream_grid(items, 8)), dim3(256), 0, (cudaStream_t)stream, (const T*)qkv, (T*)out, B, H, W, heads,
+                   hd, ksize, dilation, scale, na_drop(rng_state, site, p));
+    });
+    CNB_CHECK_LAUNCH("na2d_fwd_kernel");
+    return CNB_OK;
+}
+
+int cnb_na2d_dropout_bwd(const void* qkv, const void* dout, float* dqkv_acc, void* dqkv, int B, int H, int W, int heads, int hd, int ksize,
+                         int dilation, float scale, const void* rng_state, int site, float p, int dtype, void* stream) {
+    int rc = check_na(B, H, W, heads, hd, ksize, dilation);
+    if (rc) return rc;
+    CNB_REQUIRE(qkv && dout && dqkv && dqkv_acc && rng_state && p >= 0.f && p < 1.f, "na2d_dropout_bwd: bad arguments");
+    const long items = (long)B * H * W * heads;
+    const long n = (long)B * H * W * 3 * heads * hd;
+    CNB_MEMSET_ASYNC(dqkv_acc, 0, sizeof(float) * n, (cudaStream_t)stream);
+    CNB_DISPATCH_DTYPE(dtype, {
+        CNB_LAUNCH((na2d_bwd_kernel<T>), dim3(stream_grid(items, 8)), dim3(256), 0, (cudaStream_t)stream, (const T*)qkv, (const T*)dout,
+                   dqkv_acc, B, H, W, heads, hd, ksize, dilation, scale, na_drop(rng_state, site, p));
+        CNB_LAUNCH((cast_from_f32_kernel<T>), dim3(stream_grid(n)), dim3(256), 0, (cudaStream_t)stream, (const float*)dqkv_acc, (T*)dqkv, n);
+    });
+    CNB_CHECK_LAUNCH("na2d_bwd_kernel");
     return CNB_OK;
 }
 
@@ -763,7 +802,7 @@ int cnb_na2d_bwd(const void* qkv, const void* dout, const void* out, const float
     CNB_MEMSET_ASYNC(dqkv_acc, 0, sizeof(float) * n, (cudaStream_t)stream);
     CNB_DISPATCH_DTYPE(dtype, {
         CNB_LAUNCH((na2d_bwd_kernel<T>), dim3(stream_grid(items, 8)), dim3(256), 0, (cudaStream_t)stream, (const T*)qkv, (const T*)dout,
-                   dqkv_acc, B, H, W, heads, hd, ksize, dilation, scale);
+                   dqkv_acc, B, H, W, heads, hd, ksize, dilation, scale, NaDrop{nullptr, 0, 0u, 1.0f});
         CNB_LAUNCH((cast_from_f32_kernel<T>), dim3(stream_grid(n)), dim3(256), 0, (cudaStream_t)stream, (const float*)dqkv_acc, (T*)dqkv, n);
     });
     CNB_CHECK_LAUNCH("na2d_bwd_kernel");
@@ -1019,6 +1058,198 @@ int cnb_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, cons
     CNB_LAUNCH(adamw_kernel, dim3(stream_grid(n, 1024, 4)), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, (long)n, hyper, beta1, beta2, eps,
                weight_decay, grad_scale, clip_norm, norm_ws);
     CNB_CHECK_LAUNCH("adamw_kernel");
+    return CNB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// optional block variants: adaptive max pooling, spatial-channel attention, stand-alone SiLU, dropout (k_pool_attn.cuh)
+// ------------------------------------------------------------------------------------------------
+// VEC = whole 16-byte vectors when the channel count and the pointers allow it, else 1
+#define CNB_DISPATCH_VEC(dtype, vec_ok, ...)                    \
+    do {                                                        \
+        if ((dtype) == CNB_F32) {                               \
+            typedef float T;                                    \
+            if (vec_ok) {                                       \
+                constexpr int VEC = 4;                          \
+                __VA_ARGS__                                     \
+            } else {                                            \
+                constexpr int VEC = 1;                          \
+                __VA_ARGS__                                     \
+            }                                                   \
+        } else if ((dtype) == CNB_BF16) {                       \
+            typedef bf16_t T;                                   \
+            if (vec_ok) {                                       \
+                constexpr int VEC = 8;                          \
+                __VA_ARGS__                                     \
+            } else {                                            \
+                constexpr int VEC = 1;                          \
+                __VA_ARGS__                                     \
+            }                                                   \
+        } else {                                                \
+            CNB_FAIL(CNB_ERR_INVALID, "unsupported dtype %d", (int)(dtype)); \
+        }                                                       \
+    } while (0)
+
+int cnb_adaptive_maxpool_fwd(const void* x, void* y, void* idx, int B, int Hin, int Win, int Hout, int Wout, int C, int dtype, void* stream) {
+    CNB_REQUIRE(x && y && idx && B > 0 && Hin > 0 && Win > 0 && Hout > 0 && Wout > 0 && C > 0, "adaptive_maxpool_fwd: bad arguments");
+    CNB_REQUIRE(Hout <= Hin && Wout <= Win && cnb_div_up(Hin, Hout) + 1 <= 16 && cnb_div_up(Win, Wout) + 1 <= 16,
+                "adaptive_maxpool_fwd: windows larger than 16 x 16 are not supported");
+    const bool vec_ok = C % vec_width(dtype) == 0 && cnb_aligned16(x) && cnb_aligned16(y);
+    CNB_DISPATCH_VEC(dtype, vec_ok, {
+        const long total = (long)B * Hout * Wout * (C / VEC);
+        CNB_LAUNCH((adaptive_maxpool_fwd_kernel<T, VEC>), dim3(stream_grid(total)), dim3(256), 0, (cudaStream_t)stream, (const T*)x, (T*)y,
+                   (uint8_t*)idx, B, Hin, Win, Hout, Wout, C);
+    });
+    CNB_CHECK_LAUNCH("adaptive_maxpool_fwd_kernel");
+    return CNB_OK;
+}
+
+int cnb_adaptive_maxpool_bwd(const void* dy, const void* idx, void* dx, int B, int Hin, int Win, int Hout, int Wout, int C, int dtype,
+                             void* stream) {
+    CNB_REQUIRE(dy && dx && idx && B > 0 && Hin > 0 && Win > 0 && Hout > 0 && Wout > 0 && C > 0, "adaptive_maxpool_bwd: bad arguments");
+    CNB_REQUIRE(Hout <= Hin && Wout <= Win, "adaptive_maxpool_bwd: the output must not be larger than the input");
+    const bool vec_ok = C % vec_width(dtype) == 0 && cnb_aligned16(dy) && cnb_aligned16(dx);
+    CNB_DISPATCH_VEC(dtype, vec_ok, {
+        const long total = (long)B * Hin * Win * (C / VEC);
+        CNB_LAUNCH((adaptive_maxpool_bwd_kernel<T, VEC>), dim3(stream_grid(total)), dim3(256), 0, (cudaStream_t)stream, (const T*)dy,
+                   (const uint8_t*)idx, (T*)dx, B, Hin, Win, Hout, Wout, C);
+    });
+    CNB_CHECK_LAUNCH("adaptive_maxpool_bwd_kernel");
+    return CNB_OK;
+}
+
+int cnb_silu_fwd(const void* x, void* y, int64_t n, int dtype, void* stream) {
+    CNB_REQUIRE(x && y && n > 0, "silu_fwd: bad arguments");
+    CNB_DISPATCH_DTYPE(dtype, { CNB_LAUNCH((silu_fwd_kernel<T>), dim3(stream_grid(n)), dim3(256), 0, (cudaStream_t)stream, (const T*)x, (T*)y, (long)n); });
+    CNB_CHECK_LAUNCH("silu_fwd_kernel");
+    return CNB_OK;
+}
+
+int cnb_silu_bwd(const void* x, const void* dy, void* dx, int64_t n, int dtype, void* stream) {
+    CNB_REQUIRE(x && dy && dx && n > 0, "silu_bwd: bad arguments");
+    CNB_DISPATCH_DTYPE(dtype, {
+        CNB_LAUNCH((silu_bwd_kernel<T>), dim3(stream_grid(n)), dim3(256), 0, (cudaStream_t)stream, (const T*)x, (const T*)dy, (T*)dx, (long)n);
+    });
+    CNB_CHECK_LAUNCH("silu_bwd_kernel");
+    return CNB_OK;
+}
+
+// column tiles and pixel slices of the (slice, sample, column tile) grids of the attention pooling / apply-backward kernels
+static inline void sca_grid(int B, int HW, int C, int dtype, bool vec_ok, int* ztiles, int* slices) {
+    const int CV = C / (vec_ok ? vec_width(dtype) : 1);
+    const int cols = CV < SCA_THREADS ? CV : SCA_THREADS;
+    const int R = SCA_THREADS / cols;
+    *ztiles = cnb_div_up(CV, cols);
+    const long want = cnb_div_up(4L * CNB_NUM_SMS, (long)B * *ztiles);  // ~4 waves of CTAs
+    const long most = cnb_div_up(HW, 4L * R);                           // at least 4 pixels per thread
+    *slices = cnb_clamp_grid(want, most);
+}
+
+int cnb_sca_slices(int B, int HW, int C, int dtype) {
+    if (B <= 0 || HW <= 0 || C <= 0) return 0;
+    int zt, S;
+    sca_grid(B, HW, C, dtype, C % vec_width(dtype) == 0, &zt, &S);
+    int S1;
+    sca_grid(B, HW, C, dtype, false, &zt, &S1);  // the scalar path (unaligned pointers) must fit the same workspace
+    return S > S1 ? S : S1;
+}
+
+int cnb_sca_pool_fwd(const void* x, float* sp, float* ties, float* ch_avg, float* ch_max, int32_t* ch_arg, float* ws_sum, float* ws_max,
+                     int32_t* ws_arg, int B, int HW, int C, int dtype, void* stream) {
+    CNB_REQUIRE(x && sp && ties && ch_avg && ch_max && ch_arg && ws_sum && ws_max && ws_arg && B > 0 && HW > 0 && C > 0,
+                "sca_pool_fwd: bad arguments");
+    const bool vec_ok = C % vec_width(dtype) == 0 && cnb_aligned16(x);
+    int zt, S;
+    sca_grid(B, HW, C, dtype, vec_ok, &zt, &S);
+    const long P = (long)B * HW;
+    CNB_DISPATCH_VEC(dtype, vec_ok, {
+        CNB_LAUNCH((sca_spatial_pool_kernel<T, VEC>), dim3(stream_grid(P * 32)), dim3(256), 0, (cudaStream_t)stream, (const T*)x, sp, ties, P, C);
+        CNB_LAUNCH((sca_channel_pool_partial_kernel<T, VEC>), dim3(S, B, zt), dim3(SCA_THREADS), 0, (cudaStream_t)stream, (const T*)x, ws_sum,
+                   ws_max, (int*)ws_arg, HW, C, S);
+    });
+    CNB_CHECK_LAUNCH("sca_pool kernels");
+    CNB_LAUNCH(sca_channel_pool_final_kernel, dim3(stream_grid((long)B * C)), dim3(256), 0, (cudaStream_t)stream, (const float*)ws_sum,
+               (const float*)ws_max, (const int*)ws_arg, ch_avg, ch_max, (int*)ch_arg, B, C, S, HW);
+    CNB_CHECK_LAUNCH("sca_channel_pool_final_kernel");
+    return CNB_OK;
+}
+
+int cnb_sca_pool_bwd(const void* x, const float* sp, const float* ties, const float* dsp, const float* dch_avg, const float* dch_max,
+                     const int32_t* ch_arg, void* dx, int B, int HW, int C, int dtype, void* stream) {
+    CNB_REQUIRE(x && sp && ties && dsp && dch_avg && dch_max && ch_arg && dx && B > 0 && HW > 0 && C > 0, "sca_pool_bwd: bad arguments");
+    const bool vec_ok = C % vec_width(dtype) == 0 && cnb_aligned16(x) && cnb_aligned16(dx);
+    CNB_DISPATCH_VEC(dtype, vec_ok, {
+        const long total = (long)B * HW * (C / VEC);
+        CNB_LAUNCH((sca_pool_bwd_kernel<T, VEC>), dim3(stream_grid(total)), dim3(256), 0, (cudaStream_t)stream, (const T*)x, sp, ties, dsp,
+                   dch_avg, dch_max, (const int*)ch_arg, (T*)dx, B, HW, C);
+    });
+    CNB_CHECK_LAUNCH("sca_pool_bwd_kernel");
+    return CNB_OK;
+}
+
+int cnb_sca_apply_fwd(const void* y, const float* cl, const float* sl, const float* gamma, void* out, int B, int HW, int C, int dtype,
+                      void* stream) {
+    CNB_REQUIRE(y && cl && sl && gamma && out && B > 0 && HW > 0 && C > 0, "sca_apply_fwd: bad arguments");
+    const bool vec_ok = C % vec_width(dtype) == 0 && cnb_aligned16(y) && cnb_aligned16(out);
+    CNB_DISPATCH_VEC(dtype, vec_ok, {
+        const long total = (long)B * HW * (C / VEC);
+        CNB_LAUNCH((sca_apply_fwd_kernel<T, VEC>), dim3(stream_grid(total)), dim3(256), 0, (cudaStream_t)stream, (const T*)y, cl, sl, gamma,
+                   (T*)out, B, HW, C);
+    });
+    CNB_CHECK_LAUNCH("sca_apply_fwd_kernel");
+    return CNB_OK;
+}
+
+int cnb_sca_apply_bwd(const void* y, const void* dout, const float* cl, const float* sl, const float* gamma, void* dy, float* dcl,
+                      float* dsl, float* dgamma, int B, int HW, int C, int dtype, void* stream) {
+    CNB_REQUIRE(y && dout && cl && sl && gamma && dy && dcl && dsl && dgamma && B > 0 && HW > 0 && C > 0, "sca_apply_bwd: bad arguments");
+    const bool vec_ok = C % vec_width(dtype) == 0 && cnb_aligned16(y) && cnb_aligned16(dout) && cnb_aligned16(dy);
+    int zt, S;
+    sca_grid(B, HW, C, dtype, vec_ok, &zt, &S);
+    CNB_MEMSET_ASYNC(dcl, 0, sizeof(float) * (size_t)B * C, (cudaStream_t)stream);
+    CNB_MEMSET_ASYNC(dsl, 0, sizeof(float) * (size_t)B * HW, (cudaStream_t)stream);
+    CNB_MEMSET_ASYNC(dgamma, 0, sizeof(float), (cudaStream_t)stream);
+    CNB_DISPATCH_VEC(dtype, vec_ok, {
+        CNB_LAUNCH((sca_apply_bwd_kernel<T, VEC>), dim3(S, B, zt), dim3(SCA_THREADS), 0, (cudaStream_t)stream, (const T*)y, (const T*)dout, cl,
+                   sl, gamma, (T*)dy, dcl, dsl, dgamma, HW, C, S);
+    });
+    CNB_CHECK_LAUNCH("sca_apply_bwd_kernel");
+    return CNB_OK;
+}
+
+int cnb_rng_advance(void* rng_state, void* stream) {
+    CNB_REQUIRE(rng_state, "rng_advance: null state");
+    CNB_LAUNCH(rng_advance_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, (int64_t*)rng_state);
+    CNB_CHECK_LAUNCH("rng_advance_kernel");
+    return CNB_OK;
+}
+
+static inline uint32_t dropout_threshold(float p) {
+    long t = lroundf(p * 65536.0f);
+    return (uint32_t)(t < 0 ? 0 : (t > 65536 ? 65536 : t));
+}
+
+int cnb_dropout(const void* x, void* out, int64_t n, const void* rng_state, int site, float p, int dtype, void* stream) {
+    CNB_REQUIRE(x && out && rng_state && n > 0 && p >= 0.f && p < 1.f, "dropout: bad arguments");
+    const bool vec_ok = n % vec_width(dtype) == 0 && cnb_aligned16(x) && cnb_aligned16(out);
+    CNB_DISPATCH_VEC(dtype, vec_ok, {
+        const long n_v = n / VEC;
+        CNB_LAUNCH((dropout_kernel<T, VEC>), dim3(stream_grid(n_v)), dim3(256), 0, (cudaStream_t)stream, (const T*)x, (T*)out, n_v,
+                   (const int64_t*)rng_state, site, dropout_threshold(p), 1.0f / (1.0f - p));
+    });
+    CNB_CHECK_LAUNCH("dropout_kernel");
+    return CNB_OK;
+}
+
+int cnb_dropout2d(const void* x, void* out, int B, int HW, int C, const void* rng_state, int site, float p, int dtype, void* stream) {
+    CNB_REQUIRE(x && out && rng_state && B > 0 && HW > 0 && C > 0 && p >= 0.f && p < 1.f, "dropout2d: bad arguments");
+    const bool vec_ok = C % vec_width(dtype) == 0 && cnb_aligned16(x) && cnb_aligned16(out);
+    CNB_DISPATCH_VEC(dtype, vec_ok, {
+        const long total = (long)B * HW * (C / VEC);
+        CNB_LAUNCH((dropout2d_kernel<T, VEC>), dim3(stream_grid(total)), dim3(256), 0, (cudaStream_t)stream, (const T*)x, (T*)out, B, HW, C,
+                   (const int64_t*)rng_state, site, dropout_threshold(p), 1.0f / (1.0f - p));
+    });
+    CNB_CHECK_LAUNCH("dropout2d_kernel");
     return CNB_OK;
 }
 

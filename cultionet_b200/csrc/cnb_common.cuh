@@ -222,6 +222,21 @@ __device__ __forceinline__ float cnb_warp_max(float v) {
     return v;
 }
 
+// counter-based random bits for the dropout kernels (k_pool_attn.cuh, k_na.cuh): state = device int64[2] {seed, step counter}
+__device__ __forceinline__ uint64_t cnb_mix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ uint64_t cnb_rng_key(const int64_t* state, int site) {
+    return cnb_mix64((uint64_t)state[0] ^ cnb_mix64((uint64_t)state[1] * 0x9e3779b97f4a7c15ULL + (uint64_t)(uint32_t)site));
+}
+// 16 random bits of element `e` of the stream `key`
+__device__ __forceinline__ uint32_t cnb_rng_bits16(uint64_t key, uint64_t e) {
+    const uint64_t h = cnb_mix64(key + (e >> 2) * 0x9e3779b97f4a7c15ULL);
+    return (uint32_t)(h >> (16 * (e & 3))) & 0xffffu;
+}
+
 static inline int cnb_div_up(long a, long b) { return (int)((a + b - 1) / b); }
 static inline int cnb_clamp_grid(long blocks, long cap) { return (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks)); }
 

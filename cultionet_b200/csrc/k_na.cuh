@@ -20,10 +20,20 @@ __device__ __forceinline__ int na_window_start(int index, int length, int ksize,
     return g + dilation * s;
 }
 
+// Attention dropout (natten attn_drop, reference convolution.py:341-350): `rng` = device {seed, step counter} or null; probability n of
+// item (pixel, head) is kept iff its 16 random bits >= drop_thr and then scaled by drop_scale = 1 / (1 - p).
+struct NaDrop {
+    const int64_t* rng;
+    int site;
+    uint32_t thr;
+    float scale;
+};
+
 template <typename T>
 __global__ void __launch_bounds__(256) na2d_fwd_kernel(const T* __restrict__ qkv, T* __restrict__ out, int B, int H, int W, int heads,
-                                                      int hd, int ksize, int dil, float scale) {
+                                                      int hd, int ksize, int dil, float scale, NaDrop drop) {
     CNB_PDL_SYNC();
+    const uint64_t drop_key = drop.rng ? cnb_rng_key(drop.rng, drop.site) : 0;
     const int lane = threadIdx.x & 31;
     const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
@@ -75,7 +85,8 @@ __global__ void __launch_bounds__(256) na2d_fwd_kernel(const T* __restrict__ qkv
             const int a = n / ksize, b = n - a * ksize;
             const long np = (img * H + (sy + a * dil)) * W + (sx + b * dil);
             const T* vp = qkv + np * 3 * C + 2 * C + head * hd;
-            const float p = logit[n] * inv;
+            float p = logit[n] * inv;
+            if (drop.rng) p = cnb_rng_bits16(drop_key, (uint64_t)item * k2 + n) >= drop.thr ? p * drop.scale : 0.f;
 #pragma unroll
             for (int j = 0; j < NA_MAX_DPL; ++j) {
                 const int dd = lane + 32 * j;
@@ -94,8 +105,9 @@ __global__ void __launch_bounds__(256) na2d_fwd_kernel(const T* __restrict__ qkv
 // Recomputes the attention probabilities; dq is written, dk/dv are scattered with fp32 atomics into dacc.
 template <typename T>
 __global__ void __launch_bounds__(256) na2d_bwd_kernel(const T* __restrict__ qkv, const T* __restrict__ dout, float* __restrict__ dacc,
-                                                      int B, int H, int W, int heads, int hd, int ksize, int dil, float scale) {
+                                                      int B, int H, int W, int heads, int hd, int ksize, int dil, float scale, NaDrop drop) {
     CNB_PDL_SYNC();
+    const uint64_t drop_key = drop.rng ? cnb_rng_key(drop.rng, drop.site) : 0;
     const int lane = threadIdx.x & 31;
     const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
@@ -151,6 +163,8 @@ __global__ void __launch_bounds__(256) na2d_bwd_kernel(const T* __restrict__ qkv
         float dot = 0.f;
         for (int n = 0; n < k2; ++n) {
             prob[n] *= inv;
+            // with dropout out = sum_n m_n p_n v_n (m_n = keep / (1 - p_drop)): d out / d p_n carries the same factor
+            if (drop.rng) dprob[n] *= cnb_rng_bits16(drop_key, (uint64_t)item * k2 + n) >= drop.thr ? drop.scale : 0.f;
             dot = fmaf(prob[n], dprob[n], dot);
         }
         for (int n = 0; n < k2; ++n) {
@@ -161,13 +175,15 @@ __global__ void __launch_bounds__(256) na2d_bwd_kernel(const T* __restrict__ qkv
             float* dvp = dkp + C;
             const float p = prob[n];
             const float ds = p * (dprob[n] - dot);
+            float pv = p;  // the (dropped, rescaled) probability that multiplied v_n in the forward
+            if (drop.rng) pv = cnb_rng_bits16(drop_key, (uint64_t)item * k2 + n) >= drop.thr ? p * drop.scale : 0.f;
 #pragma unroll
             for (int j = 0; j < NA_MAX_DPL; ++j) {
                 const int dd = lane + 32 * j;
                 if (dd < hd) {
                     dq[j] = fmaf(ds, cnb_ld(kp + dd), dq[j]);
                     atomicAdd(dkp + dd, ds * q[j]);
-                    atomicAdd(dvp + dd, p * go[j]);
+                    atomicAdd(dvp + dd, pv * go[j]);
                 }
             }
         }

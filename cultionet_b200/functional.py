@@ -551,8 +551,41 @@ class _NA2DFn(torch.autograd.Function):
         return dqkv, None, None, None, None
 
 
-def na2d(qkv: torch.Tensor, heads: int, ksize: int, dilation: int, scale: float) -> torch.Tensor:
-    """Neighbourhood attention core over a packed ``[B,H,W,3*heads*hd]`` qkv tensor."""
+class _NA2DDropoutFn(torch.autograd.Function):
+    """Neighbourhood attention with dropout on the attention probabilities (natten ``attn_drop`` in training mode)."""
+
+    @staticmethod
+    def forward(ctx, qkv, heads, ksize, dilation, scale, p, site):
+        check_device(qkv)
+        qkv = _contig(qkv)
+        B, H, W, C3 = qkv.shape
+        Cn = C3 // 3
+        st = rng_state(qkv.device)
+        out = torch.empty((B, H, W, Cn), dtype=qkv.dtype, device=qkv.device)
+        call("cnb_na2d_dropout_fwd", ptr(qkv), ptr(out), B, H, W, heads, Cn // heads, ksize, dilation, scale, ptr(st), site, p,
+             dtype_code(qkv.dtype), stream_ptr(qkv))
+        ctx.save_for_backward(qkv)
+        ctx.meta = (heads, ksize, dilation, scale, p, site, st)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (qkv,) = ctx.saved_tensors
+        heads, ksize, dilation, scale, p, site, st = ctx.meta
+        dout = _contig(dout)
+        B, H, W, C3 = qkv.shape
+        acc = torch.empty(qkv.shape, dtype=torch.float32, device=qkv.device)
+        dqkv = torch.empty_like(qkv)
+        call("cnb_na2d_dropout_bwd", ptr(qkv), ptr(dout), ptr(acc), ptr(dqkv), B, H, W, heads, C3 // 3 // heads, ksize, dilation, scale,
+             ptr(st), site, p, dtype_code(qkv.dtype), stream_ptr(qkv))
+        return dqkv, None, None, None, None, None, None
+
+
+def na2d(qkv: torch.Tensor, heads: int, ksize: int, dilation: int, scale: float, attn_drop: float = 0.0, site: int = 0) -> torch.Tensor:
+    """Neighbourhood attention core over a packed ``[B,H,W,3*heads*hd]`` qkv tensor (``attn_drop`` > 0: training-mode dropout on the
+    attention probabilities, drawn from the device generator state at call site ``site``)."""
+    if attn_drop > 0:
+        return _NA2DDropoutFn.apply(qkv, heads, ksize, dilation, scale, float(attn_drop), int(site))
     return _NA2DFn.apply(qkv, heads, ksize, dilation, scale)
 
 
@@ -793,3 +826,198 @@ class _TanimotoFn(torch.autograd.Function):
 def tanimoto_complement(preds: Sequence[torch.Tensor], specs: Sequence[TanimotoTermSpec], smooth: float = 1e-5, depth: int = 5):
     """Returns (sum_t weight_t * loss_t, tensor[1 + nterms] of total and per-term losses)."""
     return _TanimotoFn.apply(smooth, depth, list(specs), *preds)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# optional ResUNet-a block variants (SURVEY.md 8f N4): adaptive max pooling, spatial-channel attention, dropout
+# ----------------------------------------------------------------------------------------------------------------
+class _AdaptiveMaxPoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, Hout, Wout):
+        check_device(x)
+        x = _contig(x)
+        B, Hin, Win, Cn = x.shape
+        y = torch.empty((B, Hout, Wout, Cn), dtype=x.dtype, device=x.device)
+        idx = torch.empty((B, Hout, Wout, Cn), dtype=torch.uint8, device=x.device)
+        call("cnb_adaptive_maxpool_fwd", ptr(x), ptr(y), ptr(idx), B, Hin, Win, Hout, Wout, Cn, dtype_code(x.dtype), stream_ptr(x))
+        ctx.save_for_backward(idx)
+        ctx.meta = (B, Hin, Win, Hout, Wout, Cn)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (idx,) = ctx.saved_tensors
+        B, Hin, Win, Hout, Wout, Cn = ctx.meta
+        dy = _contig(dy)
+        dx = torch.empty((B, Hin, Win, Cn), dtype=dy.dtype, device=dy.device)
+        call("cnb_adaptive_maxpool_bwd", ptr(dy), ptr(idx), ptr(dx), B, Hin, Win, Hout, Wout, Cn, dtype_code(dy.dtype), stream_ptr(dy))
+        return dx, None, None
+
+
+def adaptive_max_pool2d(x: torch.Tensor, size) -> torch.Tensor:
+    """``F.adaptive_max_pool2d`` over a pixel-major ``[B,H,W,C]`` tensor."""
+    return _AdaptiveMaxPoolFn.apply(x, int(size[0]), int(size[1]))
+
+
+class _SiLUFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        check_device(x)
+        x = _contig(x)
+        y = torch.empty_like(x)
+        call("cnb_silu_fwd", ptr(x), ptr(y), x.numel(), dtype_code(x.dtype), stream_ptr(x))
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dy = _contig(dy)
+        dx = torch.empty_like(x)
+        call("cnb_silu_bwd", ptr(x), ptr(dy), ptr(dx), x.numel(), dtype_code(x.dtype), stream_ptr(x))
+        return dx
+
+
+def silu(x: torch.Tensor) -> torch.Tensor:
+    return _SiLUFn.apply(x)
+
+
+class _ScaPoolFn(torch.autograd.Function):
+    """x[B,H,W,C] -> sp[B,H,W,2] (per-pixel mean, max over channels), ch_avg[B,1,1,C], ch_max[B,1,1,C] (per-channel mean / max over
+    pixels); all three fp32."""
+
+    @staticmethod
+    def forward(ctx, x):
+        check_device(x)
+        x = _contig(x)
+        B, H, W, Cn = x.shape
+        HW = H * W
+        dev = x.device
+        sp = torch.empty((B, H, W, 2), dtype=torch.float32, device=dev)
+        ties = torch.empty((B, HW), dtype=torch.float32, device=dev)
+        ch = torch.empty((2, B, 1, 1, Cn), dtype=torch.float32, device=dev)
+        arg = torch.empty((B, Cn), dtype=torch.int32, device=dev)
+        S = int(_lib.lib().cnb_sca_slices(B, HW, Cn, dtype_code(x.dtype)))
+        ws = torch.empty((3, B, S, Cn), dtype=torch.float32, device=dev)  # the third plane holds int32 indices
+        call("cnb_sca_pool_fwd", ptr(x), ptr(sp), ptr(ties), ptr(ch[0]), ptr(ch[1]), ptr(arg), ptr(ws[0]), ptr(ws[1]), ptr(ws[2]), B, HW, Cn,
+             dtype_code(x.dtype), stream_ptr(x))
+        ctx.save_for_backward(x, sp, ties, arg)
+        return sp, ch[0], ch[1]
+
+    @staticmethod
+    def backward(ctx, dsp, davg, dmax):
+        x, sp, ties, arg = ctx.saved_tensors
+        B, H, W, Cn = x.shape
+        dev = x.device
+
+        def g(t, shape):
+            return _contig(t.float()) if t is not None else torch.zeros(shape, dtype=torch.float32, device=dev)
+
+        dsp, davg, dmax = g(dsp, sp.shape), g(davg, (B, Cn)), g(dmax, (B, Cn))
+        dx = torch.empty_like(x)
+        call("cnb_sca_pool_bwd", ptr(x), ptr(sp), ptr(ties), ptr(dsp), ptr(davg), ptr(dmax), ptr(arg), ptr(dx), B, H * W, Cn,
+             dtype_code(x.dtype), stream_ptr(x))
+        return dx
+
+
+def sca_pool(x: torch.Tensor):
+    return _ScaPoolFn.apply(x)
+
+
+class _ScaApplyFn(torch.autograd.Function):
+    """out = y * (1 + gamma * 0.5 * (sigmoid(cl[b,c]) + sigmoid(sl[b,h,w])))."""
+
+    @staticmethod
+    def forward(ctx, y, cl, sl, gamma):
+        check_device(y, cl, sl, gamma)
+        y, cl, sl = _contig(y), _contig(cl.float()), _contig(sl.float())
+        gamma_c = _contig(gamma.float())
+        B, H, W, Cn = y.shape
+        assert cl.numel() == B * Cn and sl.numel() == B * H * W and gamma_c.numel() == 1
+        out = torch.empty_like(y)
+        call("cnb_sca_apply_fwd", ptr(y), ptr(cl), ptr(sl), ptr(gamma_c), ptr(out), B, H * W, Cn, dtype_code(y.dtype), stream_ptr(y))
+        ctx.save_for_backward(y, cl, sl, gamma_c)
+        ctx.shapes = (cl.shape, sl.shape, gamma.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        y, cl, sl, gamma_c = ctx.saved_tensors
+        B, H, W, Cn = y.shape
+        dout = _contig(dout)
+        dy = torch.empty_like(y)
+        dcl = torch.empty(ctx.shapes[0], dtype=torch.float32, device=y.device)
+        dsl = torch.empty(ctx.shapes[1], dtype=torch.float32, device=y.device)
+        dgamma = torch.empty(ctx.shapes[2], dtype=torch.float32, device=y.device)
+        call("cnb_sca_apply_bwd", ptr(y), ptr(dout), ptr(cl), ptr(sl), ptr(gamma_c), ptr(dy), ptr(dcl), ptr(dsl), ptr(dgamma), B, H * W, Cn,
+             dtype_code(y.dtype), stream_ptr(y))
+        return dy, dcl, dsl, dgamma
+
+
+def sca_apply(y: torch.Tensor, cl: torch.Tensor, sl: torch.Tensor, gamma: torch.Tensor) -> torch.Tensor:
+    return _ScaApplyFn.apply(y, cl, sl, gamma)
+
+
+# dropout: one device-resident generator state {seed, step counter} per device; the seed comes from torch's default CPU generator, so
+# torch.manual_seed() makes a run repeatable.  rng_advance() is called once per training forward (TowerUNet.forward).
+_RNG_STATE: dict = {}
+_RNG_SITES = [0]
+
+
+def new_rng_site() -> int:
+    """A unique id per dropout module instance (separates the random streams of the call sites of one step)."""
+    _RNG_SITES[0] += 1
+    return _RNG_SITES[0]
+
+
+def rng_state(device: torch.device) -> torch.Tensor:
+    key = (device.type, device.index)
+    st = _RNG_STATE.get(key)
+    if st is None:
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        st = torch.tensor([seed, 0], dtype=torch.int64).to(device)
+        _RNG_STATE[key] = st
+    return st
+
+
+def rng_advance(device: torch.device) -> None:
+    st = rng_state(device)
+    call("cnb_rng_advance", ptr(st), stream_ptr(st))
+
+
+class _DropoutFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, p, site, channelwise):
+        check_device(x)
+        x = _contig(x)
+        st = rng_state(x.device)
+        out = torch.empty_like(x)
+        ctx.meta = (p, site, channelwise, st)
+        _DropoutFn._launch(x, out, ctx.meta)
+        return out
+
+    @staticmethod
+    def _launch(x, out, meta):
+        p, site, channelwise, st = meta
+        if channelwise:
+            B, Cn = x.shape[0], x.shape[-1]
+            call("cnb_dropout2d", ptr(x), ptr(out), B, x.numel() // (B * Cn), Cn, ptr(st), site, p, dtype_code(x.dtype), stream_ptr(x))
+        else:
+            call("cnb_dropout", ptr(x), ptr(out), x.numel(), ptr(st), site, p, dtype_code(x.dtype), stream_ptr(x))
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _contig(dy)
+        dx = torch.empty_like(dy)
+        _DropoutFn._launch(dy, dx, ctx.meta)  # same state, same site => the same mask
+        return dx, None, None, None
+
+
+def dropout(x: torch.Tensor, p: float, site: int) -> torch.Tensor:
+    """nn.Dropout in training mode (elementwise)."""
+    return x if p <= 0 else _DropoutFn.apply(x, float(p), int(site), False)
+
+
+def dropout2d(x: torch.Tensor, p: float, site: int) -> torch.Tensor:
+    """nn.Dropout2d in training mode over a pixel-major tensor: whole channels of a sample are zeroed."""
+    return x if p <= 0 else _DropoutFn.apply(x, float(p), int(site), True)

@@ -97,6 +97,7 @@ class TowerUNet(nn.Module):
         up_channels = int(hidden_channels * len(channels))
         self.in_channels, self.in_time = in_channels, in_time
         self.compute_dtype = compute_dtype
+        self.dropout = float(dropout)
 
         self.pre_unet = PreTimeReduction(in_channels, in_time, channels[0], activation_type)
         self.encoder = cunn.TowerUNetEncoder(channels=channels, dilations=dilations, activation_type=activation_type, dropout=dropout,
@@ -134,6 +135,8 @@ class TowerUNet(nn.Module):
         if x.dim() != 5 or x.shape[1] != self.in_channels or x.shape[2] != self.in_time:
             raise ValueError(f"TowerUNet expects x[B,{self.in_channels},{self.in_time},H,W], got {tuple(x.shape)}")
         dtype = self.compute_dtype
+        if self.training and self.dropout > 0:
+            F.rng_advance(x.device)  # one new set of dropout masks per forward (a kernel, so CUDA-graph replays advance too)
         embeddings = self.pre_unet(x.float(), dtype)
         encoded = self.encoder(embeddings)
         decoded = self.decoder(encoded)

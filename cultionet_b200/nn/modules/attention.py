@@ -24,11 +24,14 @@ class NeighborhoodAttention2D(nn.Module):
         self.attn_drop = nn.Dropout(attn_drop)
         self.proj = nn.Linear(dim, dim)
         self.proj_drop = nn.Dropout(proj_drop)
+        self._rng_sites = (F.new_rng_site(), F.new_rng_site())
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """x: [B, H, W, C] (already pixel-major, as natten expects)."""
-        if self.training and (self.attn_drop.p > 0 or self.proj_drop.p > 0):
-            raise NotImplementedError("cultionet_b200: attention dropout in training mode is not built yet; construct with dropout=0.0")
+        drop = self.attn_drop.p if self.training else 0.0
         qkv = F.linear(x, self.qkv.weight, self.qkv.bias)
-        o = F.na2d(qkv, self.num_heads, self.kernel_size, self.dilation, float(self.scale))
-        return F.linear(o, self.proj.weight, self.proj.bias)
+        o = F.na2d(qkv, self.num_heads, self.kernel_size, self.dilation, float(self.scale), attn_drop=drop, site=self._rng_sites[0])
+        o = F.linear(o, self.proj.weight, self.proj.bias)
+        if self.training and self.proj_drop.p > 0:
+            o = F.dropout(o, self.proj_drop.p, self._rng_sites[1])
+        return o

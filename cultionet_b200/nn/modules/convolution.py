@@ -80,24 +80,33 @@ class ConvTranspose2d(nn.Module):
 
 
 class ConvBlock2d(nn.Module):
-    """Conv2d(bias=False) -> BatchNorm2d -> [SiLU]  (reference ``convolution.py:71-120``, default ordering)."""
+    """Conv2d(bias=False) -> BatchNorm2d -> [SiLU], or with ``batchnorm_first``: BatchNorm2d -> SiLU -> Conv2d(bias=True)
+    (reference ``convolution.py:71-120``)."""
 
     def __init__(self, in_channels: int, out_channels: int, kernel_size: int, padding: int = 0, dilation: int = 1,
                  stride: int = 1, add_activation: bool = True, activation_type: str = "SiLU", batchnorm_first: bool = False):
         super().__init__()
-        if batchnorm_first:
-            raise NotImplementedError("cultionet_b200: batchnorm_first=True is outside the built hot path (SURVEY.md 8f N4)")
         _require_silu(activation_type)
-        layers = [
-            nn.Conv2d(in_channels, out_channels, kernel_size=kernel_size, padding=padding, dilation=dilation, stride=stride, bias=False),
-            nn.BatchNorm2d(out_channels),
-        ]
-        if add_activation:
-            layers.append(nn.SiLU())
+        self.batchnorm_first = batchnorm_first
+        if batchnorm_first:
+            layers = [
+                nn.BatchNorm2d(in_channels),
+                nn.SiLU(),
+                nn.Conv2d(in_channels, out_channels, kernel_size=kernel_size, padding=padding, dilation=dilation, stride=stride),
+            ]
+        else:
+            layers = [
+                nn.Conv2d(in_channels, out_channels, kernel_size=kernel_size, padding=padding, dilation=dilation, stride=stride, bias=False),
+                nn.BatchNorm2d(out_channels),
+            ]
+            if add_activation:
+                layers.append(nn.SiLU())
         self.add_activation = add_activation
         self.seq = nn.Sequential(*layers)
 
     def forward(self, x: Sources) -> torch.Tensor:
+        if self.batchnorm_first:
+            return self._forward_bn_first(_as_sources(x))
         conv, bn = self.seq[0], self.seq[1]
         # in training mode the tcgen05 convolution epilogue also produces BatchNorm's per-channel sums (no separate statistics pass)
         y = F.conv2d(_as_sources(x), conv.weight, None, ksize=conv.kernel_size[0], stride=conv.stride[0], pad=conv.padding[0],
@@ -106,6 +115,26 @@ class ConvBlock2d(nn.Module):
         if bn.training:
             y, sums = y
         return batchnorm_act(bn, y, act=self.add_activation, sums=sums)
+
+    def _forward_bn_first(self, sources: T.List[torch.Tensor]) -> torch.Tensor:
+        """BatchNorm over the (virtual) channel concatenation = BatchNorm of every source with its slice of the parameters."""
+        bn, conv = self.seq[0], self.seq[2]
+        if len(sources) == 1:
+            normed = [batchnorm_act(bn, sources[0], act=True)]
+        else:
+            if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
+                if _PENDING_COUNTERS is not None:
+                    _PENDING_COUNTERS.append(bn.num_batches_tracked)
+                else:
+                    bn.num_batches_tracked.add_(1)
+            normed, c0 = [], 0
+            for s in sources:
+                c1 = c0 + s.shape[-1]
+                normed.append(F.batchnorm_act(s, bn.weight[c0:c1], bn.bias[c0:c1], bn.running_mean[c0:c1], bn.running_var[c0:c1],
+                                              bn.training, momentum=bn.momentum if bn.momentum is not None else 0.1, eps=bn.eps, act=True))
+                c0 = c1
+        return F.conv2d(normed, conv.weight, conv.bias, ksize=conv.kernel_size[0], stride=conv.stride[0], pad=conv.padding[0],
+                        dil=conv.dilation[0])
 
 
 class ResConvBlock2d(nn.Module):
@@ -134,10 +163,87 @@ class ResConvBlock2d(nn.Module):
         return x
 
 
-class ResidualConv(nn.Module):
-    def __init__(self, *args, **kwargs):
+class ChannelAttention(nn.Module):
+    """Holds the two channel MLPs (1x1 convs without bias) of the reference ``attention.py:12-63``."""
+
+    def __init__(self, in_channels: int, activation_type: str):
         super().__init__()
-        raise NotImplementedError("cultionet_b200: res_block_type='res' is outside the built hot path (SURVEY.md 8f N4)")
+        _require_silu(activation_type)
+
+        def mlp():
+            return nn.Sequential(nn.Conv2d(in_channels, in_channels // 2, kernel_size=1, padding=0, bias=False), nn.SiLU(),
+                                 nn.Conv2d(in_channels // 2, in_channels, kernel_size=1, padding=0, bias=False))
+
+        self.fc1 = mlp()
+        self.fc2 = mlp()
+
+    @staticmethod
+    def _mlp(seq: nn.Sequential, v: torch.Tensor) -> torch.Tensor:
+        h = F.silu(F.conv2d([v], seq[0].weight, None, ksize=1, stride=1, pad=0))
+        return F.conv2d([h], seq[2].weight, None, ksize=1, stride=1, pad=0)
+
+    def logits(self, ch_avg: torch.Tensor, ch_max: torch.Tensor) -> torch.Tensor:
+        """fc1(avg-pooled) + fc2(max-pooled): ``[B,1,1,C]`` fp32 (the sigmoid is taken by the apply kernel)."""
+        return F.add_n(self._mlp(self.fc1, ch_avg), self._mlp(self.fc2, ch_max))
+
+
+class SpatialAttention(nn.Module):
+    """Holds the 3x3 (2 -> 1) convolution of the reference ``attention.py:66-88``."""
+
+    def __init__(self):
+        super().__init__()
+        self.conv = nn.Conv2d(2, 1, kernel_size=3, padding=1, bias=False)
+
+    def logits(self, sp: torch.Tensor) -> torch.Tensor:
+        return F.conv2d([sp], self.conv.weight, None, ksize=3, stride=1, pad=1)
+
+
+class SpatialChannelAttention(nn.Module):
+    """``1 + gamma * 0.5 * (channel_attention + spatial_attention)`` (reference ``attention.py:91-125``), applied to a second
+    tensor by ``scale``: the pooled statistics and both logit maps are small fp32 tensors, the two passes over the activations
+    (pooling, apply) are single kernels."""
+
+    def __init__(self, in_channels: int, activation_type: str):
+        super().__init__()
+        self.channel_attention = ChannelAttention(in_channels=in_channels, activation_type=activation_type)
+        self.spatial_attention = SpatialAttention()
+        self.gamma = nn.Parameter(torch.zeros(1))
+
+    def scale(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        """``y * attention(x)``."""
+        sp, ch_avg, ch_max = F.sca_pool(x)
+        cl = self.channel_attention.logits(ch_avg, ch_max)
+        sl = self.spatial_attention.logits(sp)
+        return F.sca_apply(y, cl, sl, self.gamma)
+
+
+class ResidualConv(nn.Module):
+    """``skip(x) + ResConvBlock2d(x)`` (reference ``convolution.py:179-247``)."""
+
+    def __init__(self, in_channels: int, out_channels: int, kernel_size: int = 3, num_blocks: int = 2,
+                 attention_weights: T.Optional[str] = None, activation_type: str = "SiLU", batchnorm_first: bool = False):
+        super().__init__()
+        self.attention_weights = attention_weights
+        if attention_weights is not None:
+            assert attention_weights in [AttentionTypes.SPATIAL_CHANNEL], "The attention method is not supported."
+            # the reference constructs SpatialChannelAttention(out_channels=...) here (convolution.py:203-205), a keyword that class
+            # does not take: ResidualConv with attention cannot be built there either
+            raise TypeError("SpatialChannelAttention.__init__() got an unexpected keyword argument 'out_channels'")
+        self.seq = ResConvBlock2d(in_channels, out_channels, kernel_size=kernel_size, num_blocks=num_blocks,
+                                  activation_type=activation_type, batchnorm_first=batchnorm_first)
+        self.skip = None
+        if in_channels != out_channels:
+            self.skip = nn.Conv2d(in_channels, out_channels, kernel_size=1, padding=0)
+
+    def forward(self, x: Sources) -> torch.Tensor:
+        sources = _as_sources(x)
+        if self.skip is None:
+            assert len(sources) == 1
+            a, b = F.fanout(sources[0], 2)
+            return F.add_n(a, self.seq(b))
+        refs = [F.fanout(s, 2) for s in sources]
+        skip = F.conv2d([r[0] for r in refs], self.skip.weight, self.skip.bias, ksize=1, stride=1, pad=0)
+        return F.add_n(skip, self.seq([r[1] for r in refs]))
 
 
 class ResidualAConv(nn.Module):
@@ -157,17 +263,18 @@ class ResidualAConv(nn.Module):
             self.skip = nn.Identity()
         if attention_weights is not None:
             assert attention_weights in [AttentionTypes.NATTEN, AttentionTypes.SPATIAL_CHANNEL], "The attention method is not supported."
-            if attention_weights != AttentionTypes.NATTEN:
-                raise NotImplementedError("cultionet_b200: attention_weights='spatial_channel' is outside the built hot path (SURVEY.md 8f N4)")
-            # indices 1..3 carry the parameters (the reference has einops Rearrange layers at 0 and 4)
-            self.attention_conv = nn.Sequential(
-                nn.Identity(),
-                nn.LayerNorm(out_channels),
-                NeighborhoodAttention2D(out_channels, num_heads=natten_num_heads, kernel_size=natten_kernel_size, dilation=natten_dilation,
-                                        attn_drop=natten_attn_drop, proj_drop=natten_proj_drop),
-                nn.LayerNorm(out_channels),
-                nn.Identity(),
-            )
+            if attention_weights == AttentionTypes.NATTEN:
+                # indices 1..3 carry the parameters (the reference has einops Rearrange layers at 0 and 4)
+                self.attention_conv = nn.Sequential(
+                    nn.Identity(),
+                    nn.LayerNorm(out_channels),
+                    NeighborhoodAttention2D(out_channels, num_heads=natten_num_heads, kernel_size=natten_kernel_size,
+                                            dilation=natten_dilation, attn_drop=natten_attn_drop, proj_drop=natten_proj_drop),
+                    nn.LayerNorm(out_channels),
+                    nn.Identity(),
+                )
+            else:
+                self.attention_conv = SpatialChannelAttention(in_channels=out_channels, activation_type=activation_type)
         self.res_modules = nn.ModuleList([
             ResConvBlock2d(in_channels, out_channels, kernel_size=kernel_size, dilation=d, activation_type=activation_type,
                            num_blocks=num_blocks, batchnorm_first=batchnorm_first)
@@ -192,7 +299,8 @@ class ResidualAConv(nn.Module):
             if attention:
                 skip, att_in = F.fanout(skip, 2)
         terms = [skip] + [layer(branch_in[i]) for i, layer in enumerate(self.res_modules)]
-        if attention:
+        natten = attention and self.attention_weights == AttentionTypes.NATTEN
+        if natten:
             ln1, na, ln2 = self.attention_conv[1], self.attention_conv[2], self.attention_conv[3]
             a = F.layernorm(att_in, ln1.weight, ln1.bias, ln1.eps)
             a = na(a)
@@ -200,11 +308,14 @@ class ResidualAConv(nn.Module):
         out = F.add_n(*terms[:4])
         for i in range(4, len(terms), 3):
             out = F.add_n(out, *terms[i:i + 3])
+        if attention and not natten:
+            out = self.attention_conv.scale(att_in, out)  # out * (1 + gamma * attention(skip)), convolution.py:392-393
         return out
 
 
 class PoolResidualConv(nn.Module):
-    """[3x3 stride-2 conv + BN] -> ResidualAConv -> Dropout2d (reference ``convolution.py:398-513``)."""
+    """[3x3 stride-2 conv (+ BN), or adaptive max pooling to (H//2, W//2)] -> ResidualAConv / ResidualConv -> Dropout2d
+    (reference ``convolution.py:398-513``)."""
 
     def __init__(self, in_channels: int, out_channels: int, dropout: float = 0.0, kernel_size: int = 3, num_blocks: int = 2,
                  attention_weights: T.Optional[str] = None, activation_type: str = "SiLU", res_block_type: str = ResBlockTypes.RESA,
@@ -213,26 +324,37 @@ class PoolResidualConv(nn.Module):
                  natten_proj_drop: float = 0.0):
         super().__init__()
         assert res_block_type in (ResBlockTypes.RES, ResBlockTypes.RESA)
-        if res_block_type != ResBlockTypes.RESA:
-            raise NotImplementedError("cultionet_b200: res_block_type='res' is outside the built hot path (SURVEY.md 8f N4)")
-        if pool_by_max:
-            raise NotImplementedError("cultionet_b200: pool_by_max=True is outside the built hot path (SURVEY.md 8f N4)")
         self.pool_first = pool_first
         self.pool_by_max = pool_by_max
-        if pool_first:
-            self.pool_conv = ConvBlock2d(in_channels, out_channels, kernel_size=3, padding=1, stride=2, add_activation=False,
-                                         batchnorm_first=False)
+        if pool_first and not pool_by_max:
+            if batchnorm_first:
+                self.pool_conv = nn.Conv2d(in_channels, out_channels, kernel_size=3, padding=1, stride=2)
+            else:
+                self.pool_conv = ConvBlock2d(in_channels, out_channels, kernel_size=3, padding=1, stride=2, add_activation=False,
+                                             batchnorm_first=False)
             in_channels = out_channels
-        self.res_conv = ResidualAConv(in_channels, out_channels, kernel_size=kernel_size, dilations=dilations, num_blocks=num_blocks,
-                                      attention_weights=attention_weights, activation_type=activation_type, batchnorm_first=batchnorm_first,
-                                      natten_num_heads=natten_num_heads, natten_kernel_size=natten_kernel_size,
-                                      natten_dilation=natten_dilation, natten_attn_drop=natten_attn_drop, natten_proj_drop=natten_proj_drop)
+        if res_block_type == ResBlockTypes.RES:
+            self.res_conv = ResidualConv(in_channels, out_channels, kernel_size=kernel_size, attention_weights=attention_weights,
+                                         num_blocks=num_blocks, activation_type=activation_type, batchnorm_first=batchnorm_first)
+        else:
+            self.res_conv = ResidualAConv(in_channels, out_channels, kernel_size=kernel_size, dilations=dilations, num_blocks=num_blocks,
+                                          attention_weights=attention_weights, activation_type=activation_type,
+                                          batchnorm_first=batchnorm_first, natten_num_heads=natten_num_heads,
+                                          natten_kernel_size=natten_kernel_size, natten_dilation=natten_dilation,
+                                          natten_attn_drop=natten_attn_drop, natten_proj_drop=natten_proj_drop)
         self.dropout_layer = nn.Dropout2d(p=dropout)
+        self._rng_site = F.new_rng_site()
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if self.pool_first:
-            x = self.pool_conv(x)
+            if self.pool_by_max:
+                x = F.adaptive_max_pool2d(x, (x.shape[1] // 2, x.shape[2] // 2))
+            elif isinstance(self.pool_conv, nn.Conv2d):
+                c = self.pool_conv
+                x = F.conv2d([x], c.weight, c.bias, ksize=3, stride=2, pad=1)
+            else:
+                x = self.pool_conv(x)
         x = self.res_conv(x)
         if self.training and self.dropout_layer.p > 0:
-            raise NotImplementedError("cultionet_b200: Dropout2d in training mode is not built yet; construct with dropout=0.0")
+            x = F.dropout2d(x, self.dropout_layer.p, self._rng_site)
         return x

@@ -16,7 +16,7 @@ import torch.nn as nn
 
 from ... import functional as F
 from ...enums import AttentionTypes, ResBlockTypes
-from .convolution import ConvBlock2d, ConvTranspose2d, PoolResidualConv, ResidualAConv, batchnorm_act
+from .convolution import ConvBlock2d, ConvTranspose2d, PoolResidualConv, ResidualAConv, ResidualConv, batchnorm_act
 
 # natten settings per resolution level (reference ``unet_parts.py:19-40``); a mutable module-level dict there too
 NATTEN_PARAMS = {
@@ -27,10 +27,17 @@ NATTEN_PARAMS = {
 }
 
 
-def _require_resa(res_block_type: str) -> None:
+def _res_block(res_block_type: str, in_channels: int, out_channels: int, kernel_size: int, num_blocks: T.Optional[int], dilations,
+               attention_weights, activation_type: str, batchnorm_first: bool, natten_kw: dict) -> nn.Module:
+    """ResidualConv for ``res``, ResidualAConv for ``resa`` (reference ``unet_parts.py:340-368``, ``:683-710``)."""
     assert res_block_type in (ResBlockTypes.RES, ResBlockTypes.RESA)
-    if res_block_type != ResBlockTypes.RESA:
-        raise NotImplementedError("cultionet_b200: res_block_type='res' is outside the built hot path (SURVEY.md 8f N4)")
+    if res_block_type == ResBlockTypes.RES:
+        return ResidualConv(in_channels=in_channels, out_channels=out_channels, kernel_size=kernel_size,
+                            num_blocks=2 if num_blocks is None else num_blocks, attention_weights=attention_weights,
+                            activation_type=activation_type, batchnorm_first=batchnorm_first)
+    kw = {} if num_blocks is None else {"num_blocks": num_blocks}
+    return ResidualAConv(in_channels, out_channels, kernel_size=kernel_size, dilations=dilations, attention_weights=attention_weights,
+                         activation_type=activation_type, batchnorm_first=batchnorm_first, **kw, **natten_kw)
 
 
 class SigmoidCrisp(nn.Module):
@@ -157,14 +164,14 @@ class UNetUpBlock(nn.Module):
                  dilations: T.Sequence[int] = None, batchnorm_first: bool = False, resample_up: bool = True, natten_num_heads: int = 8,
                  natten_kernel_size: int = 3, natten_dilation: int = 1, natten_attn_drop: float = 0.0, natten_proj_drop: float = 0.0):
         super().__init__()
-        _require_resa(res_block_type)
         if resample_up:
             self.up_conv = ConvTranspose2d(in_channels, in_channels)
-        # like the reference (unet_parts.py:355-368) the RESA branch does not forward ``num_blocks``
-        self.res_conv = ResidualAConv(in_channels, out_channels, kernel_size=kernel_size, dilations=dilations,
-                                      attention_weights=attention_weights, activation_type=activation_type, batchnorm_first=batchnorm_first,
-                                      natten_num_heads=natten_num_heads, natten_kernel_size=natten_kernel_size,
-                                      natten_dilation=natten_dilation, natten_attn_drop=natten_attn_drop, natten_proj_drop=natten_proj_drop)
+        natten_kw = dict(natten_num_heads=natten_num_heads, natten_kernel_size=natten_kernel_size, natten_dilation=natten_dilation,
+                         natten_attn_drop=natten_attn_drop, natten_proj_drop=natten_proj_drop)
+        # like the reference (unet_parts.py:355-368) the RESA branch does not forward ``num_blocks``; the RES branch does (:342-350)
+        self.res_conv = _res_block(res_block_type, in_channels, out_channels, kernel_size,
+                                   num_blocks if res_block_type == ResBlockTypes.RES else None, dilations, attention_weights,
+                                   activation_type, batchnorm_first, natten_kw)
 
     def forward(self, x: torch.Tensor, size) -> torch.Tensor:
         if tuple(x.shape[1:3]) != tuple(size):
@@ -230,7 +237,6 @@ class TowerUNetBlock(nn.Module):
                  batchnorm_first: bool = False, natten_num_heads: int = 8, natten_kernel_size: int = 3, natten_dilation: int = 1,
                  natten_attn_drop: float = 0.0, natten_proj_drop: float = 0.0, use_latlon: bool = False):
         super().__init__()
-        _require_resa(res_block_type)
         if use_latlon:
             raise NotImplementedError("cultionet_b200: use_latlon=True (GeoEmbeddings) is off in CultionetLitModel and not built")
         self.use_latlon = use_latlon
@@ -240,10 +246,10 @@ class TowerUNetBlock(nn.Module):
         if tower:
             self.tower_conv = ConvTranspose2d(up_channels, up_channels, kernel_size=3, stride=2, padding=1)
             in_channels += up_channels
-        self.res_conv = ResidualAConv(in_channels, out_channels, kernel_size=kernel_size, num_blocks=num_blocks, dilations=dilations,
-                                      attention_weights=attention_weights, activation_type=activation_type, batchnorm_first=batchnorm_first,
-                                      natten_num_heads=natten_num_heads, natten_kernel_size=natten_kernel_size,
-                                      natten_dilation=natten_dilation, natten_attn_drop=natten_attn_drop, natten_proj_drop=natten_proj_drop)
+        natten_kw = dict(natten_num_heads=natten_num_heads, natten_kernel_size=natten_kernel_size, natten_dilation=natten_dilation,
+                         natten_attn_drop=natten_attn_drop, natten_proj_drop=natten_proj_drop)
+        self.res_conv = _res_block(res_block_type, in_channels, out_channels, kernel_size, num_blocks, dilations, attention_weights,
+                                   activation_type, batchnorm_first, natten_kw)
 
     def forward(self, backbone_side, backbone_down, decode_side, decode_down, tower_down=None, latlon_coords=None) -> torch.Tensor:
         size = tuple(decode_side.shape[1:3])

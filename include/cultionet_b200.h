@@ -283,6 +283,54 @@ int cnb_grad_sqnorm(const float* g, int64_t n, float* norm_ws, void* stream);
 int cnb_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper, float beta1, float beta2, float eps,
                    float weight_decay, float grad_scale, float clip_norm, const float* norm_ws, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Optional ResUNet-a block variants (constructor arguments of TowerUNet the reference's own tests use,
+ * tests/test_cultionet.py:67-78: attention_weights="spatial_channel", pool_by_max=True, dropout > 0).
+ * ------------------------------------------------------------------------------------------------ */
+/* F.adaptive_max_pool2d(x, (Hout, Wout)) of PoolResidualConv.forward (nn/modules/convolution.py:499-503), pixel-major.
+ * idx: uint8 [B,Hout,Wout,C], position of the (first) maximum inside its window as row*16 + column (windows up to 16 x 16). */
+int cnb_adaptive_maxpool_fwd(const void* x, void* y, void* idx, int B, int Hin, int Win, int Hout, int Wout, int C, int dtype, void* stream);
+int cnb_adaptive_maxpool_bwd(const void* dy, const void* idx, void* dx, int B, int Hin, int Win, int Hout, int Wout, int C, int dtype,
+                             void* stream);
+
+/* SetActivation("SiLU") as a stand-alone operator (the channel MLP of ChannelAttention, nn/modules/attention.py:19-52) */
+int cnb_silu_fwd(const void* x, void* y, int64_t n, int dtype, void* stream);
+int cnb_silu_bwd(const void* x, const void* dy, void* dx, int64_t n, int dtype, void* stream);
+
+/* SpatialChannelAttention, pooling side (nn/modules/attention.py:54-63, :78-86) over x[B][HW][C]:
+ *   sp[B*HW][2]  = per-pixel (mean, max) over channels; ties[B*HW] = number of channels equal to that max (torch.amax shares the
+ *                  gradient between ties);
+ *   ch_avg/ch_max[B][C] = per-channel mean / max over the pixels, ch_arg[B][C] = pixel index of the first maximum
+ *                  (nn.AdaptiveAvgPool2d(1) / nn.AdaptiveMaxPool2d(1)).
+ * ws_sum/ws_max/ws_arg: scratch [B][S][C] with S = cnb_sca_slices(B, HW, C, dtype). */
+int cnb_sca_slices(int B, int HW, int C, int dtype);
+int cnb_sca_pool_fwd(const void* x, float* sp, float* ties, float* ch_avg, float* ch_max, int32_t* ch_arg, float* ws_sum, float* ws_max,
+                     int32_t* ws_arg, int B, int HW, int C, int dtype, void* stream);
+/* dx (overwritten) from the gradients of the four pooled tensors */
+int cnb_sca_pool_bwd(const void* x, const float* sp, const float* ties, const float* dsp, const float* dch_avg, const float* dch_max,
+                     const int32_t* ch_arg, void* dx, int B, int HW, int C, int dtype, void* stream);
+/* apply side (attention.py:118-123 + convolution.py:392-393): out = y * (1 + gamma * 0.5 * (sigmoid(cl[b][c]) + sigmoid(sl[b][p])));
+ * cl fp32 [B][C] = channel logits (fc1(avg) + fc2(max)), sl fp32 [B][HW] = spatial logits (3x3 conv of sp), gamma fp32[1].
+ * Backward: dy overwritten; dcl [B][C], dsl [B][HW], dgamma [1] are zeroed inside and accumulated with fp32 atomics. */
+int cnb_sca_apply_fwd(const void* y, const float* cl, const float* sl, const float* gamma, void* out, int B, int HW, int C, int dtype,
+                      void* stream);
+int cnb_sca_apply_bwd(const void* y, const void* dout, const float* cl, const float* sl, const float* gamma, void* dy, float* dcl,
+                      float* dsl, float* dgamma, int B, int HW, int C, int dtype, void* stream);
+
+/* Dropout with a counter-based generator: rng_state = device int64[2] {seed, step counter}; cnb_rng_advance bumps the counter (once
+ * per forward, also inside a captured CUDA graph), `site` separates the call sites of one step, the backward is the same call on the
+ * gradient (same state and site => same mask).  cnb_dropout = nn.Dropout (natten proj_drop, convolution.py:341-350);
+ * cnb_dropout2d = nn.Dropout2d, one draw per (sample, channel) (PoolResidualConv.dropout_layer, convolution.py:487, :509). */
+int cnb_rng_advance(void* rng_state, void* stream);
+/* natten attn_drop in training mode: neighbourhood attention whose probabilities are dropped (and rescaled by 1/(1-p)) before they
+ * weight the values; one-warp-per-(pixel, head) kernels for any shape.  dqkv_acc: fp32 scratch [B,H,W,3*heads*hd] (zeroed inside). */
+int cnb_na2d_dropout_fwd(const void* qkv, void* out, int B, int H, int W, int heads, int hd, int ksize, int dilation, float scale,
+                         const void* rng_state, int site, float p, int dtype, void* stream);
+int cnb_na2d_dropout_bwd(const void* qkv, const void* dout, float* dqkv_acc, void* dqkv, int B, int H, int W, int heads, int hd, int ksize,
+                         int dilation, float scale, const void* rng_state, int site, float p, int dtype, void* stream);
+int cnb_dropout(const void* x, void* out, int64_t n, const void* rng_state, int site, float p, int dtype, void* stream);
+int cnb_dropout2d(const void* x, void* out, int B, int HW, int C, const void* rng_state, int site, float p, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,6 +21,11 @@ from oracle import towerunet_port as port  # noqa: E402
 CASES = {
     "small_masked": dict(B=2, C=3, T=7, H=24, W=24, hidden=8, dilations=[1, 2], seed=11, y_low=-1),
     "odd_dil3": dict(B=1, C=2, T=6, H=25, W=25, hidden=8, dilations=[1, 2, 3], seed=23, y_low=0),
+    # constructor-argument variants (the reference's tests/test_cultionet.py:67-78 builds spatial_channel + pool_by_max)
+    "sca_maxpool": dict(B=2, C=3, T=6, H=24, W=24, hidden=8, dilations=[1, 2], seed=31, y_low=-1, attention=1, pool_by_max=1),
+    "res_bnfirst": dict(B=2, C=2, T=6, H=20, W=20, hidden=8, dilations=[1, 2], seed=37, y_low=0, attention=2, res=1, batchnorm_first=1),
+    "bnfirst_maxpool_odd": dict(B=1, C=2, T=6, H=25, W=25, hidden=8, dilations=[1, 2], seed=41, y_low=-1, batchnorm_first=1,
+                                pool_by_max=1),
 }
 FULL_GRADS = [
     "pre_unet.conv3.seq.0.weight",
@@ -29,12 +34,33 @@ FULL_GRADS = [
     "decoder.up_cu.res_conv.attention_conv.2.qkv.bias",
     "final_a.fuse_conv.seq.0.weight",
     "encoder.down_b.pool_conv.seq.1.weight",
+    # variants
+    "decoder.up_au.res_conv.attention_conv.gamma",
+    "decoder.up_bu.res_conv.attention_conv.channel_attention.fc2.0.weight",
+    "decoder.up_cu.res_conv.attention_conv.spatial_attention.conv.weight",
+    "encoder.down_b.res_conv.skip.weight",
+    "encoder.down_c.pool_conv.bias",
+    "tower_fusion.tower_a.res_conv.seq.block.0.seq.0.weight",
+    "tower_fusion.tower_b.res_conv.res_modules.1.block.0.seq.0.bias",
 ]
+ATTENTION = {0: "natten", 1: "spatial_channel", 2: None}
 
 
-def golden_case(cfg: dict):
-    """Seeded weights and inputs of a case (shared by the generator and the tests)."""
-    spec = port.param_spec(cfg["C"], cfg["T"], cfg["hidden"], cfg["dilations"])
+def variant_kwargs(cfg: dict) -> dict:
+    """TowerUNet constructor arguments of a case beyond the defaults (shared by the generator and the tests)."""
+    return dict(attention_weights=ATTENTION[cfg.get("attention", 0)], pool_by_max=bool(cfg.get("pool_by_max", 0)),
+                batchnorm_first=bool(cfg.get("batchnorm_first", 0)), res_block_type="res" if cfg.get("res", 0) else "resa")
+
+
+def is_variant(cfg: dict) -> bool:
+    return any(cfg.get(k, 0) for k in ("attention", "pool_by_max", "batchnorm_first", "res"))
+
+
+def golden_case(cfg: dict, spec=None):
+    """Seeded weights and inputs of a case (shared by the generator and the tests).  Default-architecture cases take the parameter
+    inventory from the port; variant cases pass the inventory stored in their fixture."""
+    if spec is None:
+        spec = port.param_spec(cfg["C"], cfg["T"], cfg["hidden"], cfg["dilations"])
     sd = port.synth_state_dict(spec, seed=cfg["seed"])
     rng = np.random.default_rng(cfg["seed"] + 1000)
     x = torch.from_numpy(rng.random((cfg["B"], cfg["C"], cfg["T"], cfg["H"], cfg["W"]), dtype=np.float32))
@@ -47,8 +73,12 @@ def run_reference(cfg: dict):
     from oracle.ref_loader import load_reference
 
     ref = load_reference()
-    spec, sd, x, y, bdist = golden_case(cfg)
-    model = ref.TowerUNet(in_channels=cfg["C"], in_time=cfg["T"], hidden_channels=cfg["hidden"], dilations=cfg["dilations"])
+    model = ref.TowerUNet(in_channels=cfg["C"], in_time=cfg["T"], hidden_channels=cfg["hidden"], dilations=cfg["dilations"],
+                          **variant_kwargs(cfg))
+    spec = None
+    if is_variant(cfg):  # the parameter inventory of a variant comes from the reference model itself
+        spec = [(k, tuple(v.shape)) for k, v in model.state_dict().items()]
+    spec, sd, x, y, bdist = golden_case(cfg, spec)
     model.load_state_dict(sd, strict=True)
     model.train()
     out = model(x)
@@ -62,14 +92,17 @@ def run_reference(cfg: dict):
     loss.backward()
     grads = {n: p.grad.detach().clone() for n, p in model.named_parameters()}
     buffers = {n: b.detach().clone() for n, b in model.named_buffers()}
-    return out, (loss, d, e, c), grads, buffers
+    return out, (loss, d, e, c), grads, buffers, spec
 
 
 def main() -> None:
     out_dir = ROOT / "tests" / "golden"
     out_dir.mkdir(parents=True, exist_ok=True)
+    only = set(sys.argv[1:])
     for name, cfg in CASES.items():
-        out, losses, grads, buffers = run_reference(cfg)
+        if only and name not in only:
+            continue
+        out, losses, grads, buffers, spec = run_reference(cfg)
         names = sorted(grads)
         arrays = {
             "grad_names": np.array(names),
@@ -79,7 +112,11 @@ def main() -> None:
         for k in ("distance", "edge", "crop"):
             arrays["out_" + k] = out[k].detach().numpy()[:, :, ::3, ::3].astype(np.float32)
         for n in FULL_GRADS:
-            arrays["grad::" + n] = grads[n].numpy().astype(np.float32)
+            if n in grads:
+                arrays["grad::" + n] = grads[n].numpy().astype(np.float32)
+        if is_variant(cfg):
+            arrays["spec_names"] = np.array([k for k, _ in spec])
+            arrays["spec_shapes"] = np.array([",".join(map(str, shp)) for _, shp in spec])
         rm = sorted(n for n in buffers if n.endswith("running_mean"))
         arrays["bn_names"] = np.array(rm)
         arrays["bn_mean_norms"] = np.array([float(buffers[n].double().norm()) for n in rm])

@@ -329,3 +329,22 @@ def training_loss(pred: Dict[str, torch.Tensor], y: torch.Tensor, bdist: torch.T
     e = tanimoto_complement_loss(pred["edge"], true_edge, mask)
     c = tanimoto_complement_loss(pred["crop"], true_crop, mask)
     return (d + e + c) / 3.0, {"dloss": d, "eloss": e, "closs": c}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# optional block variants (constructor arguments the reference's own tests use, tests/test_cultionet.py:67-78)
+# ---------------------------------------------------------------------------------------------------------------------
+def spatial_channel_attention(x: torch.Tensor, fc1_0, fc1_2, fc2_0, fc2_2, sp_conv, gamma) -> torch.Tensor:
+    """SpatialChannelAttention.forward over NCHW ``x`` (nn/modules/attention.py:54-63, :78-88, :118-125): returns the
+    ``1 + gamma * attention`` map that ResidualAConv multiplies its output with (nn/modules/convolution.py:392-393)."""
+    avg = F.conv2d(F.silu(F.conv2d(F.adaptive_avg_pool2d(x, 1), fc1_0)), fc1_2)  # attention.py:56
+    mx = F.conv2d(F.silu(F.conv2d(F.adaptive_max_pool2d(x, 1), fc2_0)), fc2_2)  # attention.py:57
+    channel = torch.sigmoid(avg + mx)  # attention.py:58-61
+    sp = torch.cat([x.mean(dim=1, keepdim=True), x.amax(dim=1, keepdim=True)], dim=1)  # attention.py:81-83 (einops reduce -> amax)
+    spatial = torch.sigmoid(F.conv2d(sp, sp_conv, padding=1))  # attention.py:84-85
+    return 1.0 + gamma * ((channel + spatial) * 0.5)  # attention.py:121-123
+
+
+def adaptive_max_pool_half(x: torch.Tensor) -> torch.Tensor:
+    """PoolResidualConv's ``pool_by_max`` down-sampling over NCHW ``x`` (nn/modules/convolution.py:499-503)."""
+    return F.adaptive_max_pool2d(x, output_size=(x.shape[-2] // 2, x.shape[-1] // 2))

@@ -143,12 +143,12 @@ def test_adamw_and_clipping(dev):
     cases.adamw_case(dev, n=1_000_003)
 
 
-@pytest.mark.parametrize("name", ["small_masked", "odd_dil3"])
+@pytest.mark.parametrize("name", ["small_masked", "odd_dil3", "sca_maxpool", "res_bnfirst", "bnfirst_maxpool_odd"])
 def test_model_reproduces_reference_golden_fp32(dev, name):
     cases.model_vs_golden(dev, name, F32)
 
 
-@pytest.mark.parametrize("name", ["small_masked", "odd_dil3"])
+@pytest.mark.parametrize("name", ["small_masked", "odd_dil3", "sca_maxpool", "res_bnfirst", "bnfirst_maxpool_odd"])
 def test_model_reproduces_reference_golden_bf16(dev, name):
     cases.model_vs_golden(dev, name, BF16)
 
@@ -266,3 +266,68 @@ def test_predict_step_cuda_graph_matches_eager(dev):
         for k, v in want.items():
             assert got[k].shape == (2, 1, 40, 40) and torch.allclose(got[k], v, rtol=1e-5, atol=1e-6), (i, k)
     assert graphed._graph is not None and graphed.launches_per_step > 50
+
+
+# --- optional block variants and dropout ------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [F32, BF16])
+@pytest.mark.parametrize("shape", [(2, 64, 64, 128), (1, 25, 25, 5), (3, 50, 50, 64), (2, 13, 13, 256)])
+def test_adaptive_max_pool(dev, dtype, shape):
+    cases.maxpool_case(dev, dtype, *shape)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [F32, BF16])
+@pytest.mark.parametrize("shape", [(2, 32, 32, 128), (1, 5, 4, 6), (2, 25, 25, 32), (2, 16, 16, 512), (3, 9, 8, 24)])
+def test_spatial_channel_attention(dev, dtype, shape):
+    cases.sca_case(dev, dtype, *shape)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [F32, BF16])
+def test_silu_and_dropout(dev, dtype):
+    cases.silu_case(dev, dtype, n=100_003)
+    cases.dropout_case(dev, dtype, B=4, H=32, W=32, C=64)
+    cases.dropout_case(dev, dtype, B=3, H=7, W=5, C=6, p=0.5)
+
+
+@pytest.mark.gpu
+def test_attention_dropout(dev):
+    cases.na_dropout_case(dev, 2, 16, 16, 4, 16, 3, 2)
+    cases.na_dropout_case(dev, 1, 14, 15, 2, 8, 7, 2, p=0.1)
+
+
+@pytest.mark.gpu
+def test_train_step_with_default_dropout_under_cuda_graph(dev):
+    """dropout=0.2 (the LightningModule default): masks come from the device-resident generator state, so the captured step draws a
+    new mask at every replay; the loss still goes down on a fixed batch."""
+    import cultionet_b200 as cb
+    from cultionet_b200 import functional as Fn
+    from cultionet_b200.engine import TrainStep
+    from cultionet_b200.models.lightning import CultionetLitModel
+
+    torch.manual_seed(0)
+    model = CultionetLitModel(in_channels=3, in_time=8, hidden_channels=16, dropout=0.2, compute_dtype=BF16).to(dev)
+    step = TrainStep(model, total_steps=100, cuda_graph=True)
+    batch = cb.Data(x=torch.rand(2, 3, 8, 48, 48, device=dev), y=torch.randint(0, 3, (2, 48, 48), device=dev),
+                    bdist=torch.rand(2, 48, 48, device=dev))
+    c0 = int(Fn.rng_state(torch.device(dev, torch.cuda.current_device()))[1])
+    losses = [float(step(batch)) for _ in range(12)]
+    c1 = int(Fn.rng_state(torch.device(dev, torch.cuda.current_device()))[1])
+    assert c1 - c0 == 12, (c0, c1)  # the counter advanced inside the replayed graph too
+    assert all(l == l for l in losses) and min(losses[6:]) < losses[0], losses
+
+
+@pytest.mark.gpu
+def test_reference_test_cultionet_configuration_bf16(dev):
+    import cultionet_b200 as cb
+
+    torch.manual_seed(0)
+    model = cb.CultioNet(in_channels=5, in_time=13, hidden_channels=32, model_type="TowerUNet", dilations=[1, 2], dropout=0.2,
+                         res_block_type="resa", attention_weights="spatial_channel", pool_by_max=True, compute_dtype=BF16).to(dev)
+    batch = cb.Data(x=torch.rand(2, 5, 13, 100, 100, device=dev), lon=torch.zeros(2, device=dev), lat=torch.zeros(2, device=dev))
+    out = model(batch)
+    for k in ("distance", "edge", "crop"):
+        assert out[k].shape == (2, 1, 100, 100) and bool(torch.isfinite(out[k]).all())
+    (out["distance"].mean() + out["edge"].mean() + out["crop"].mean()).backward()
+    assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in model.parameters() if p.requires_grad)

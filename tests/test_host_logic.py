@@ -35,15 +35,59 @@ def test_data_container_contract():
         cb.Data(x=torch.zeros(1), bad="string")
 
 
-def test_unbuilt_options_fail_loudly():
-    with pytest.raises(NotImplementedError):
-        cb.TowerUNet(in_channels=2, in_time=6, hidden_channels=8, res_block_type="res")
-    with pytest.raises(NotImplementedError):
-        cb.TowerUNet(in_channels=2, in_time=6, hidden_channels=8, pool_by_max=True)
-    with pytest.raises(NotImplementedError):
-        cb.TowerUNet(in_channels=2, in_time=6, hidden_channels=8, attention_weights="spatial_channel")
+def test_option_errors_mirror_the_reference():
     with pytest.raises(AssertionError):
         cb.CultioNet(in_channels=2, in_time=6, model_type="UNet3")
+    with pytest.raises(AssertionError):  # ResidualConv only knows spatial_channel (convolution.py:197-200)
+        cb.TowerUNet(in_channels=2, in_time=6, hidden_channels=8, res_block_type="res", attention_weights="natten")
+    with pytest.raises(TypeError):  # ... and cannot build it either (SpatialChannelAttention(out_channels=...), convolution.py:203-205)
+        cb.TowerUNet(in_channels=2, in_time=6, hidden_channels=8, res_block_type="res", attention_weights="spatial_channel")
+    with pytest.raises(AssertionError):
+        cb.TowerUNet(in_channels=2, in_time=6, hidden_channels=8, res_block_type="resx")
+    with pytest.raises(NotImplementedError):
+        cb.TowerUNet(in_channels=2, in_time=6, hidden_channels=8, use_latlon=True)
+
+
+def test_variant_state_dict_keys_match_the_reference_inventory():
+    # inventories recorded from the real reference models by oracle/make_golden.py
+    from tests.util import golden_spec, load_golden, mine_from_state_dict
+    from oracle.make_golden import golden_case
+
+    for name in ("sca_maxpool", "res_bnfirst", "bnfirst_maxpool_odd"):
+        cfg, z = load_golden(name)
+        spec, sd, *_ = golden_case(cfg, golden_spec(z))
+        m = mine_from_state_dict(cfg, sd, "cpu")
+        mine = m.state_dict()
+        assert sorted(mine) == sorted(dict(spec)), name
+        assert all(tuple(mine[k].shape) == tuple(dict(spec)[k]) for k in mine), name
+
+
+def test_reference_test_cultionet_configuration(dev):
+    """tests/test_cultionet.py:58-120 of the reference: spatial_channel attention, pool_by_max, dropout 0.2, train mode, shapes only."""
+    torch.manual_seed(0)
+    model = cb.CultioNet(in_channels=5, in_time=13, hidden_channels=8, model_type="TowerUNet", activation_type="SiLU", dilations=[1, 2],
+                         dropout=0.2, res_block_type="resa", attention_weights="spatial_channel", pool_by_max=True)
+    batch = cb.Data(x=torch.rand(2, 5, 13, 20, 20), lon=torch.zeros(2), lat=torch.zeros(2))
+    out = model(batch)
+    for k in (InferenceNames.DISTANCE, InferenceNames.EDGE, InferenceNames.CROP):
+        assert out[k].shape == (2, 1, 20, 20)
+    (out[InferenceNames.DISTANCE].mean() + out[InferenceNames.CROP].mean()).backward()
+    assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in model.parameters() if p.requires_grad)
+
+
+def test_default_dropout_trains_and_eval_ignores_it(dev):
+    """CultionetLitModel defaults to dropout=0.2 (lightning.py:828): Dropout2d in the encoder, attn_drop / proj_drop in natten."""
+    torch.manual_seed(1)
+    m = cb.TowerUNet(in_channels=2, in_time=6, hidden_channels=8, dropout=0.2)
+    m0 = cb.TowerUNet(in_channels=2, in_time=6, hidden_channels=8, dropout=0.0)
+    m0.load_state_dict(m.state_dict())
+    x = torch.rand(1, 2, 6, 16, 16)
+    assert torch.equal(m.eval()(x)["crop"], m0.eval()(x)["crop"])
+    a = m.train()(x)["crop"]
+    b = m.train()(x)["crop"]
+    assert not torch.equal(a, b)  # a new mask every forward
+    a.mean().backward()
+    assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in m.parameters())
 
 
 def test_cultionet_forward_adds_reference_keys(dev):

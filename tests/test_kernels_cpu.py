@@ -122,7 +122,7 @@ def test_adamw_and_clipping(dev):
     cases.adamw_case(dev)
 
 
-@pytest.mark.parametrize("name", ["small_masked", "odd_dil3"])
+@pytest.mark.parametrize("name", ["small_masked", "odd_dil3", "sca_maxpool", "res_bnfirst", "bnfirst_maxpool_odd"])
 def test_model_reproduces_reference_golden(dev, name):
     cases.model_vs_golden(dev, name)
 
@@ -189,3 +189,30 @@ def test_packed_weight_cache_tracks_parameter_updates(dev):
     w2 = torch.nn.Parameter(torch.randn(4, 8, 3, 3, device=dev))
     ref2 = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2), w2.detach(), padding=1).permute(0, 2, 3, 1)
     assert torch.allclose(F.conv2d([x], w2, None, 3, 1, 1, 1), ref2, rtol=1e-4, atol=1e-5)
+
+
+# --- optional block variants -----------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [F32, BF16])
+@pytest.mark.parametrize("shape", [(2, 12, 10, 8), (1, 25, 25, 5), (2, 7, 9, 16)])
+def test_adaptive_max_pool(dev, dtype, shape):
+    cases.maxpool_case(dev, dtype, *shape)
+
+
+@pytest.mark.parametrize("dtype", [F32, BF16])
+@pytest.mark.parametrize("shape", [(2, 6, 7, 16), (1, 5, 4, 6), (2, 9, 8, 64)])
+def test_spatial_channel_attention(dev, dtype, shape):
+    cases.sca_case(dev, dtype, *shape)
+
+
+@pytest.mark.parametrize("dtype", [F32, BF16])
+def test_silu(dev, dtype):
+    cases.silu_case(dev, dtype)
+
+
+@pytest.mark.parametrize("dtype", [F32, BF16])
+def test_dropout(dev, dtype):
+    cases.dropout_case(dev, dtype)
+
+
+def test_attention_dropout(dev):
+    cases.na_dropout_case(dev, 1, 9, 8, 2, 8, 3, 1)

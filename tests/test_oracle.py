@@ -6,7 +6,7 @@ import torch
 
 from oracle import natten_ref
 from oracle import towerunet_port as port
-from oracle.make_golden import CASES, FULL_GRADS, golden_case
+from oracle.make_golden import CASES, FULL_GRADS, golden_case, is_variant
 from oracle.ref_loader import reference_available
 from tests.util import load_golden, rel_err
 
@@ -56,7 +56,7 @@ def test_kernel_loss_reproduces_reference_known_answers(dev):
     assert round(float(TanimotoComplementLoss(one_hot_targets=False)(dist, dist_targets)), 3) == 0.704
 
 
-@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("name", [n for n, c in CASES.items() if not is_variant(c)])
 def test_port_reproduces_golden(name):
     cfg, z = load_golden(name)
     assert {k: v for k, v in CASES[name].items()} == cfg
@@ -73,7 +73,8 @@ def test_port_reproduces_golden(name):
     norms = np.array([float(sd[n].grad.double().norm()) for n in names])
     assert np.allclose(norms, z["grad_norms"], rtol=2e-3, atol=1e-7)
     for n in FULL_GRADS:
-        assert rel_err(sd[n].grad, torch.from_numpy(z["grad::" + n])) < 2e-4
+        if "grad::" + n in z:
+            assert rel_err(sd[n].grad, torch.from_numpy(z["grad::" + n])) < 2e-4
 
 
 @pytest.mark.skipif(not reference_available(), reason="/root/reference is only present in the authoring container")
@@ -96,3 +97,27 @@ def test_port_matches_reference_module():
         want = model(x)
         for k in ("distance", "edge", "crop"):
             assert rel_err(got[k], want[k]) < 1e-5
+
+
+@pytest.mark.skipif(not reference_available(), reason="/root/reference is only present in the authoring container")
+def test_variant_restatements_match_reference_modules():
+    """The oracle's SpatialChannelAttention / pool_by_max restatements against the real reference modules."""
+    import importlib
+
+    from oracle.ref_loader import load_reference
+
+    load_reference()
+    att = importlib.import_module("cultionet.nn.modules.attention")
+    torch.manual_seed(5)
+    m = att.SpatialChannelAttention(in_channels=12, activation_type="SiLU")
+    with torch.no_grad():
+        m.gamma.fill_(0.6)
+    x = torch.randn(2, 12, 9, 7)
+    ca, sa = m.channel_attention, m.spatial_attention
+    got = port.spatial_channel_attention(x, ca.fc1[0].weight, ca.fc1[2].weight, ca.fc2[0].weight, ca.fc2[2].weight, sa.conv.weight, m.gamma)
+    assert rel_err(got, m(x)) < 1e-6
+    conv = importlib.import_module("cultionet.nn.modules.convolution")
+    blk = conv.PoolResidualConv(4, 8, pool_by_max=True, dilations=[1]).eval()
+    x = torch.randn(1, 4, 11, 9)
+    pooled = port.adaptive_max_pool_half(x)
+    assert rel_err(blk.res_conv(pooled), blk(x)) < 1e-6

@@ -28,9 +28,18 @@ def load_golden(name: str):
     return cfg, z
 
 
+def golden_spec(z):
+    """Parameter inventory stored in a variant fixture (None for the default architecture: the port's inventory applies)."""
+    if "spec_names" not in z:
+        return None
+    return [(str(n), tuple(int(v) for v in str(s).split(",")) if str(s) else ()) for n, s in zip(z["spec_names"], z["spec_shapes"])]
+
+
 def mine_from_state_dict(cfg: dict, sd: dict, device: str, dtype=torch.float32):
     import cultionet_b200 as cb
+    from oracle.make_golden import variant_kwargs
 
-    m = cb.TowerUNet(in_channels=cfg["C"], in_time=cfg["T"], hidden_channels=cfg["hidden"], dilations=cfg["dilations"], compute_dtype=dtype)
+    m = cb.TowerUNet(in_channels=cfg["C"], in_time=cfg["T"], hidden_channels=cfg["hidden"], dilations=cfg["dilations"], compute_dtype=dtype,
+                     **variant_kwargs(cfg))
     m.load_state_dict(sd, strict=True)
     return m.to(device)
