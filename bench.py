@@ -354,6 +354,7 @@ def main() -> None:
         return e0.elapsed_time(e1)
 
     losses = []
+    e2e_step_ms: list = []
 
     def resident_step():
         losses.append(step(dbatch))
@@ -367,10 +368,15 @@ def main() -> None:
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        t_prev = time.perf_counter()
+        e2e_step_ms.clear()
         for b in DevicePrefetcher((cb.Data(x=hx, y=hy, bdist=hb) for _ in range(n)), dev):
             loss = step(b)
             losses.append(float(loss.cpu()))  # D2H read of the step's result
             flush.zero_()
+            t_now = time.perf_counter()
+            e2e_step_ms.append(round((t_now - t_prev) * 1e3, 2))  # host clock per step (diagnostic: shows a stalled copy)
+            t_prev = t_now
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -471,7 +477,7 @@ def main() -> None:
                        "execution": "one CUDA graph per step (captured after 3 eager steps), replayed" if step.cuda_graph
                        else "eager launches through the C ABI"},
             "e2e": {"value": e2e_value, "unit": "chips/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
-                    "ms_per_step": ms_e2e / args.steps},
+                    "ms_per_step": ms_e2e / args.steps, "host_ms_each_step": list(e2e_step_ms)},
             "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_enqueue_ms[0] if host_enqueue_ms else None, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_base,
             "model_tflops": 3 * w["fwd_gflop_per_chip"] * 1e9 * value / 1e12 if w["fwd_gflop_per_chip"] else None,
             "final_loss": float(losses[-1]),

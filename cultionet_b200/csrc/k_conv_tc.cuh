@@ -260,6 +260,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *slot_ptr;
+    // programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch) ran while the previous kernel of the
+    // stream was draining; nothing below may touch global memory before that kernel has completed
+    CNB_PDL_SYNC();
 
     int chunks_per_tap = 0;
     for (int s = 0; s < p.nsrc; ++s) chunks_per_tap += p.chunks[s];
@@ -513,6 +516,15 @@ inline bool eligible(const cnb_conv_desc* d, int dtype) {
     return encode_tiled_fn() != nullptr;
 }
 
+// CNB_PDL_TC=0 launches the tensor-core kernels without the programmatic-dependent-launch attribute (A/B timing)
+inline bool tc_pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("CNB_PDL_TC");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
 template <int BN>
 inline int launch_bn(const ConvTcParams& p, cudaStream_t stream) {
     static bool configured = false;
@@ -524,8 +536,12 @@ inline int launch_bn(const ConvTcParams& p, cudaStream_t stream) {
     }
     const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
     const int smem = Cfg<BN>::SMEM_BYTES + (p.stats ? 2 * p.N * (int)sizeof(float) : 0);
-    cnb_count_launch();
-    conv_tc_kernel<BN><<<grid, NUM_THREADS, smem, stream>>>(p);
+    if (tc_pdl_enabled())
+        CNB_LAUNCH(conv_tc_kernel<BN>, dim3(grid), dim3(NUM_THREADS), (size_t)smem, stream, p);
+    else {
+        cnb_count_launch();
+        conv_tc_kernel<BN><<<grid, NUM_THREADS, smem, stream>>>(p);
+    }
     return 0;
 }
 

@@ -19,6 +19,7 @@ constexpr int WG_PIX = 64;                    // pixels (K) per pipeline stage
 constexpr int WG_BOX_BYTES = WG_PIX * 128;    // one {64 ch x 64 px} box
 constexpr int WG_STAGES = 4;
 constexpr int WG_MAX_CTILES = 64;
+constexpr int WG_MAX_BTILES = 192;            // B tiles of one launch: up to four {64 ch x 64 px} boxes each
 
 // The pixel loop runs over the domain of the operand that is read at UNIT coordinates (U); the other operand (G) is gathered at
 // s*p + q per tap through a parity sub-grid tensor map (see k_conv_tc.cuh):
@@ -28,9 +29,14 @@ struct WgradTcParams {
     CUtensorMap tmU;
     CUtensorMap tmG[MAX_MAPS];
     int u_is_dy;
-    int n_ctiles;                 // channel tiles of the source slice
-    short ct_c0[WG_MAX_CTILES];   // first channel inside the source
-    short ct_cw[WG_MAX_CTILES];   // tile width (multiple of 64, <= 256; may run past src_c: zero-filled and masked)
+    // A "B tile" is the N side of one accumulator: up to four boxes of 64 source channels, box j = channels [c0, c0 + 64) of the
+    // source gathered for tap `tap`.  Wide sources use four boxes of one tap (256 channels); sources of 64 / 128 channels put the
+    // boxes of three / two TAPS side by side, so that the dY tile staged for one tap feeds several taps' accumulators (the
+    // 64-channel layers staged 24 KB per 128 MMA cycles before: 145 TFLOP/s, bound by the L2 -> shared memory feed).
+    int n_btiles;
+    uint8_t bt_nbox[WG_MAX_BTILES];
+    uint8_t bt_tap[WG_MAX_BTILES][4];
+    short bt_c0[WG_MAX_BTILES][4];    // may run past src_c: zero-filled by TMA and masked in the epilogue
     int src_c, k_off;
     int ntaps;
     short tap_dy[MAX_TAPS], tap_dx[MAX_TAPS], tap_map[MAX_TAPS], tap_w[MAX_TAPS];
@@ -80,27 +86,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const __grid_c
     // work item: blockIdx.x = split * items + ((tap * n_tiles + nt) * n_ctiles + ct).  The pixel split is the SLOW index: the CTAs that
     // are resident together then walk the same pixel range for every (tap, n tile, channel tile), so X and dY come from DRAM once
     // and from L2 for the other items (ncu: 4.6x DRAM re-reads with the split as the fast index).
-    const int items = p.ntaps * p.n_tiles * p.n_ctiles;
-    int w = blockIdx.x % items;
+    const int items = p.n_tiles * p.n_btiles;
+    const int w = blockIdx.x % items;
     const int split = blockIdx.x / items;
-    const int ct = w % p.n_ctiles;
-    w /= p.n_ctiles;
-    const int nt = w % p.n_tiles;
-    const int tap = w / p.n_tiles;
-    const int c0 = p.ct_c0[ct], cw = p.ct_cw[ct];
+    const int bt = w % p.n_btiles;
+    const int nt = w / p.n_btiles;
+    const int nboxes_x = p.bt_nbox[bt];
+    const int cw = 64 * nboxes_x;
     const int n0 = nt * BM * nsub;
     const int pt_begin = split * p.pt_per_split;
     int pt_end = pt_begin + p.pt_per_split;
     if (pt_end > p.pixel_tiles) pt_end = p.pixel_tiles;
-    const int nboxes_x = cw / 64;
     const uint32_t stage_tx = (uint32_t)(2 * nsub + nboxes_x) * WG_BOX_BYTES;
-    const CUtensorMap* mapG = &p.tmG[p.tap_map[tap]];
-    const CUtensorMap* mapDY = p.u_is_dy ? &p.tmU : mapG;
-    const CUtensorMap* mapX = p.u_is_dy ? mapG : &p.tmU;
+    // the transposed case gathers dY per tap: its B tiles hold boxes of ONE tap (tap0)
+    const int tap0 = p.bt_tap[bt][0];
+    const CUtensorMap* mapDY = p.u_is_dy ? &p.tmU : &p.tmG[p.tap_map[tap0]];
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(mapDY);
-        tma_prefetch_desc(mapX);
+        tma_prefetch_desc(p.u_is_dy ? &p.tmG[p.tap_map[tap0]] : &p.tmU);
         for (int s = 0; s < WG_STAGES; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
@@ -113,14 +117,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const __grid_c
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *slot_ptr;
+    CNB_PDL_SYNC();  // see conv_tc_kernel
 
     if (warp == 0) {
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            const int gy = p.tap_dy[tap], gx = p.tap_dx[tap];
-            const int dy_oy = p.u_is_dy ? 0 : gy, dy_ox = p.u_is_dy ? 0 : gx;
-            const int x_oy = p.u_is_dy ? gy : 0, x_ox = p.u_is_dy ? gx : 0;
+            const int dy_oy = p.u_is_dy ? 0 : p.tap_dy[tap0], dy_ox = p.u_is_dy ? 0 : p.tap_dx[tap0];
+            const CUtensorMap* box_map[4];
+            int box_c0[4], box_oy[4], box_ox[4];
+            for (int j = 0; j < nboxes_x; ++j) {
+                const int tj = p.bt_tap[bt][j];
+                box_map[j] = p.u_is_dy ? &p.tmG[p.tap_map[tj]] : &p.tmU;
+                box_c0[j] = p.bt_c0[bt][j];
+                box_oy[j] = p.u_is_dy ? p.tap_dy[tj] : 0;
+                box_ox[j] = p.u_is_dy ? p.tap_dx[tj] : 0;
+            }
             for (int pt = pt_begin; pt < pt_end; ++pt) {
                 int t = pt;
                 const int tw = t % p.tiles_w;
@@ -134,7 +146,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const __grid_c
                 for (int j = 0; j < 2 * nsub; ++j)
                     tma_load_4d(dst + j * WG_BOX_BYTES, mapDY, full_bar(stage), n0 + 64 * j, x0 + dy_ox, y0 + dy_oy, b);
                 for (int j = 0; j < nboxes_x; ++j)
-                    tma_load_4d(dst + (2 * nsub + j) * WG_BOX_BYTES, mapX, full_bar(stage), c0 + 64 * j, x0 + x_ox, y0 + x_oy, b);
+                    tma_load_4d(dst + (2 * nsub + j) * WG_BOX_BYTES, box_map[j], full_bar(stage), box_c0[j], x0 + box_ox[j], y0 + box_oy[j], b);
                 if (++stage == nstages) {
                     stage = 0;
                     phase ^= 1u;
@@ -178,29 +190,31 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const __grid_c
         const int half = (warp - 2) >> 2;   // alternating 32-column chunks
         mbar_wait(done_bar, 0);
         tc_fence_after();
-        const int cvalid = p.src_c - c0;  // columns of this tile that exist
         for (int sub = 0; sub < nsub; ++sub) {
             const int n = n0 + sub * BM + quad * 32 + lane;
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(sub * 256);
-            float* drow = p.dwp + ((long)p.tap_w[tap] * p.N + n) * p.Ctot + p.k_off + c0;
-            const bool vec_red = (reinterpret_cast<uintptr_t>(drow) & 15u) == 0;  // 16-byte aligned rows when Ctot, k_off are multiples of 4
             if (pt_end > pt_begin && n0 + sub * BM < p.N) {
-                for (int c = half; c < cw / 32; c += 2) {
-                    if (c * 32 >= cvalid) break;
+                for (int c = half; c < cw / 32; c += 2) {   // 32-column chunk c = half (c & 1) of box c >> 1
+                    const int box = c >> 1, cin = (c & 1) * 32;
+                    const int bc0 = p.bt_c0[bt][box];
+                    const int cvalid = p.src_c - bc0 - cin;  // columns of this chunk that exist in the source
+                    if (cvalid <= 0) continue;               // warp-uniform
                     uint32_t v[32];
                     tmem_ld32(taddr + (uint32_t)(c * 32), v);
                     if (n < p.N) {
-                        if (vec_red && c * 32 + 32 <= cvalid) {
+                        float* dchunk = p.dwp + ((long)p.tap_w[p.bt_tap[bt][box]] * p.N + n) * p.Ctot + p.k_off + bc0 + cin;
+                        // 16-byte aligned when Ctot, k_off and the channel offsets are multiples of 4
+                        if ((reinterpret_cast<uintptr_t>(dchunk) & 15u) == 0 && cvalid >= 32) {
 #pragma unroll
                             for (int j = 0; j < 32; j += 4)
-                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(drow + c * 32 + j),
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dchunk + j),
                                              "f"(__uint_as_float(v[j])), "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])),
                                              "f"(__uint_as_float(v[j + 3]))
                                              : "memory");
                         } else {
 #pragma unroll
                             for (int j = 0; j < 32; ++j)
-                                if (c * 32 + j < cvalid) atomicAdd(drow + c * 32 + j, __uint_as_float(v[j]));
+                                if (j < cvalid) atomicAdd(dchunk + j, __uint_as_float(v[j]));
                         }
                     }
                 }
@@ -222,7 +236,7 @@ inline bool wgrad_eligible(const cnb_wgrad_desc* d, int dtype) {
     if (d->Hin > 32000 || d->Win > 32000 || d->Hout > 32000 || d->Wout > 32000) return false;
     if (d->src_stride % 8 != 0 || reinterpret_cast<uintptr_t>(d->src) % 16 != 0) return false;
     if (d->dy_stride % 8 != 0 || reinterpret_cast<uintptr_t>(d->dy) % 16 != 0) return false;
-    if (cnb_div_up(d->src_c, 256) > WG_MAX_CTILES) return false;
+    if (cnb_div_up(d->src_c, 256) * d->KH * d->KW > WG_MAX_BTILES) return false;
     return encode_tiled_fn() != nullptr;
 }
 
@@ -278,15 +292,41 @@ inline int wgrad_tc_launch(const cnb_wgrad_desc* d, cudaStream_t stream) {
     p.ntaps = nt;
     if (nt == 0) return 0;
 
-    int nct = 0;
-    for (int c0 = 0; c0 < d->src_c; c0 += 256) {
-        if (nct >= WG_MAX_CTILES) return 3;
-        const int rem = d->src_c - c0;
-        p.ct_c0[nct] = (short)c0;
-        p.ct_cw[nct] = (short)(rem >= 256 ? 256 : cnb_div_up(rem, 64) * 64);
-        ++nct;
+    // B tiles (see WgradTcParams): narrow sources of a direct convolution share one accumulator between several taps
+    int nbt = 0;
+    const int boxes_per_tap = cnb_div_up(d->src_c, 64);
+    static const bool group_taps = [] {
+        const char* e = getenv("CNB_WGRAD_TAP_GROUPS");
+        return !(e && e[0] == '0');
+    }();
+    if (p.u_is_dy && boxes_per_tap <= 2 && nt > 1 && group_taps) {
+        const int fit = 4 / boxes_per_tap;                  // taps that fit in one 256-column accumulator
+        const int ntile = cnb_div_up(nt, fit);
+        const int per = cnb_div_up(nt, ntile);              // ... spread evenly: 9 taps of 64 channels -> 3 + 3 + 3
+        for (int t0 = 0; t0 < nt; t0 += per) {
+            int nb = 0;
+            for (int t = t0; t < t0 + per && t < nt; ++t)
+                for (int j = 0; j < boxes_per_tap; ++j) {
+                    p.bt_tap[nbt][nb] = (uint8_t)t;
+                    p.bt_c0[nbt][nb] = (short)(64 * j);
+                    ++nb;
+                }
+            p.bt_nbox[nbt++] = (uint8_t)nb;
+        }
+    } else {
+        for (int t = 0; t < nt; ++t)
+            for (int c0 = 0; c0 < d->src_c; c0 += 256) {
+                if (nbt >= WG_MAX_BTILES) return 3;
+                const int rem = d->src_c - c0;
+                const int nb = rem >= 256 ? 4 : cnb_div_up(rem, 64);
+                for (int j = 0; j < nb; ++j) {
+                    p.bt_tap[nbt][j] = (uint8_t)t;
+                    p.bt_c0[nbt][j] = (short)(c0 + 64 * j);
+                }
+                p.bt_nbox[nbt++] = (uint8_t)nb;
+            }
     }
-    p.n_ctiles = nct;
+    p.n_btiles = nbt;
     p.src_c = d->src_c;
     p.k_off = d->k_off;
     p.Bn = d->B;
@@ -300,9 +340,16 @@ inline int wgrad_tc_launch(const cnb_wgrad_desc* d, cudaStream_t stream) {
     p.n_tiles = cnb_div_up(d->N, BM * p.nsub);
     p.Ctot = d->Ctot;
     p.dwp = d->dwp;
-    const int base_items = p.ntaps * p.n_tiles * p.n_ctiles;
-    // ~3 CTAs per SM, rounded DOWN so that items * splits fills whole waves (450 CTAs on 148 SMs left the last wave 96 % empty)
-    int splits = (3 * num_sms()) / base_items;
+    const int base_items = p.n_tiles * p.n_btiles;
+    // `waves` CTAs per SM, rounded DOWN so that items * splits fills whole waves (450 CTAs on 148 SMs left the last wave 96 % empty).
+    // Every CTA ends with a 128 x cw (x nsub) fp32 red.add epilogue, so the atomic traffic grows with the split count: one wave
+    // instead of three took all wgrad launches of config 2 from 17.3 to 15.2 ms (782 -> 891 TFLOP/s; 32x32 shapes 490 -> 740).
+    static const int waves = [] {
+        const char* e = getenv("CNB_WGRAD_WAVES");
+        const int w = e ? atoi(e) : 0;
+        return w >= 1 && w <= 8 ? w : 1;
+    }();
+    int splits = (waves * num_sms()) / base_items;
     const int max_splits = p.pixel_tiles / 8 > 0 ? p.pixel_tiles / 8 : 1;
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
@@ -313,8 +360,12 @@ inline int wgrad_tc_launch(const cnb_wgrad_desc* d, cudaStream_t stream) {
         if (cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES) != cudaSuccess) return 1;
         configured = true;
     }
-    cnb_count_launch();
-    wgrad_tc_kernel<<<base_items * p.splits, NUM_THREADS, WG_SMEM_BYTES, stream>>>(p);
+    if (tc_pdl_enabled())
+        CNB_LAUNCH(wgrad_tc_kernel, dim3(base_items * p.splits), dim3(NUM_THREADS), (size_t)WG_SMEM_BYTES, stream, p);
+    else {
+        cnb_count_launch();
+        wgrad_tc_kernel<<<base_items * p.splits, NUM_THREADS, WG_SMEM_BYTES, stream>>>(p);
+    }
     return 0;
 }
 

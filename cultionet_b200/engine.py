@@ -115,7 +115,9 @@ class TrainStep:
         F.prepack_parameters()  # every convolution weight seen so far: one packing launch instead of one per layer
         with deferred_batch_counters():  # one multi-tensor launch for the 52 BatchNorm step counters
             loss = self.model.training_step(batch, 0)
-        loss.backward()
+        # weight / bias gradients go straight into the flat gradient buffer unless per-parameter hooks must see them (overlapped DDP)
+        with F.direct_param_grads(self.sync is None or not self.sync.enabled):
+            loss.backward()
         if self.sync is not None:
             self.sync.finish()
         elif self.world > 1:

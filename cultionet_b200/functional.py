@@ -201,6 +201,35 @@ def _launch_conv(sources, src_channels, wp, w_row_off, w_row_stride, w_tap_strid
     return stats
 
 
+# With DIRECT_PARAM_GRAD the weight / bias gradient kernels accumulate straight into ``param.grad`` (the flat gradient buffer of
+# optim.FlatAdamW) and the backward returns None for them: no temporary gradient tensor and no AccumulateGrad add per parameter.
+# engine.TrainStep switches it on when no per-parameter gradient hook has to fire (no overlapped bucketed all-reduce).
+DIRECT_PARAM_GRAD = [False]
+
+
+class direct_param_grads:
+    def __init__(self, enabled: bool = True):
+        self.enabled = enabled
+
+    def __enter__(self):
+        self.prev = DIRECT_PARAM_GRAD[0]
+        DIRECT_PARAM_GRAD[0] = bool(self.enabled)
+        return self
+
+    def __exit__(self, *exc):
+        DIRECT_PARAM_GRAD[0] = self.prev
+        return False
+
+
+def _direct_grad_target(param, like_shape) -> Optional[torch.Tensor]:
+    if not DIRECT_PARAM_GRAD[0] or not isinstance(param, torch.nn.Parameter):
+        return None
+    g = param.grad
+    if g is None or g.dtype != torch.float32 or not g.is_contiguous() or tuple(g.shape) != tuple(like_shape) or g.requires_grad:
+        return None
+    return g
+
+
 class _Conv2dFn(torch.autograd.Function):
     """y = conv(cat(sources, channel), weight) + bias over pixel-major tensors; see ``cnb_conv2d_fwd``."""
 
@@ -238,6 +267,7 @@ class _Conv2dFn(torch.autograd.Function):
         stats = _launch_conv(sources, src_channels, wp, 0, wp.shape[2], N * wp.shape[2], N, bias_c, out, geom, transposed, dtype,
                              want_stats=want_stats)
         ctx.save_for_backward(weight, *sources)
+        ctx.params = (weight, bias)  # the Parameter objects themselves (their .grad may take the gradient directly)
         ctx.meta = (kind, geom, transposed, src_channels, N, Ctot, bias is not None)
         if not want_stats:
             return out
@@ -298,14 +328,22 @@ class _Conv2dFn(torch.autograd.Function):
                 call(_WGRAD_ENTRY[CONV_BACKEND], C.byref(d), dtype_code(dtype), stream_ptr(dy), flops=2.0 * B * (Hin * Win if transposed else Hout * Wout) * N * c * taps,
                      tag="conv_wgrad", detail=detail)
                 coff += c
-            dw = torch.empty_like(weight, dtype=torch.float32, memory_format=torch.contiguous_format)
             rows, cols, s_n, s_k, s_tap = _weight_strides(kind, N, Ctot, taps, for_dgrad=False)
-            call("cnb_unpack_wgrad", ptr(dwp), ptr(dw), taps, rows, cols, s_n, s_k, s_tap, 0, stream_ptr(dy))
+            target = _direct_grad_target(ctx.params[0], weight.shape)
+            if target is not None:
+                call("cnb_unpack_wgrad", ptr(dwp), ptr(target), taps, rows, cols, s_n, s_k, s_tap, 1, stream_ptr(dy))
+            else:
+                dw = torch.empty_like(weight, dtype=torch.float32, memory_format=torch.contiguous_format)
+                call("cnb_unpack_wgrad", ptr(dwp), ptr(dw), taps, rows, cols, s_n, s_k, s_tap, 0, stream_ptr(dy))
 
         db = None
         if need_b:
-            db = torch.empty((N,), dtype=torch.float32, device=dev)
-            call("cnb_bias_grad", ptr(dy), dy_pitch, B * Hout * Wout, N, ptr(db), 0, dtype_code(dtype), stream_ptr(dy))
+            target = _direct_grad_target(ctx.params[1], (N,))
+            if target is not None:
+                call("cnb_bias_grad", ptr(dy), dy_pitch, B * Hout * Wout, N, ptr(target), 1, dtype_code(dtype), stream_ptr(dy))
+            else:
+                db = torch.empty((N,), dtype=torch.float32, device=dev)
+                call("cnb_bias_grad", ptr(dy), dy_pitch, B * Hout * Wout, N, ptr(db), 0, dtype_code(dtype), stream_ptr(dy))
         return (dw, db, None, None, None, None, None, None, None, None, None, *src_grads)
 
 

@@ -26,6 +26,7 @@ class CultioNet(nn.Module):
         pool_by_max: bool = False,
         batchnorm_first: bool = False,
         use_latlon: bool = False,
+        compute_dtype: torch.dtype = torch.float32,
     ):
         super().__init__()
         self.in_channels, self.in_time, self.hidden_channels = in_channels, in_time, hidden_channels
@@ -34,7 +35,7 @@ class CultioNet(nn.Module):
             in_channels=in_channels, in_time=in_time, hidden_channels=hidden_channels, num_classes=1,
             attention_weights=attention_weights, res_block_type=res_block_type, dropout=dropout, dilations=dilations,
             activation_type=activation_type, edge_activation=True, mask_activation=True, pool_by_max=pool_by_max,
-            batchnorm_first=batchnorm_first, use_latlon=use_latlon,
+            batchnorm_first=batchnorm_first, use_latlon=use_latlon, compute_dtype=compute_dtype,
         )
 
     def forward(self, batch: Data) -> T.Dict[str, torch.Tensor]:

@@ -36,6 +36,10 @@ def test_conv_tensor_core_shapes(dev):
         cases.conv_case(dev, BF16, 2, 25, 25, [128], 256, 3, 2, 1, 1)      # pool convolution, odd size (25 -> 13)
         cases.conv_case(dev, BF16, 2, 20, 20, [72, 24, 8], 136, 3, 1, 1, 1)  # partial 64-channel chunks and N tiles
         cases.conv_case(dev, BF16, 2, 40, 40, [256], 3, 3, 1, 1, 1)        # 256 -> 3 stream convolution
+        cases.conv_case(dev, BF16, 2, 48, 40, [64], 64, 3, 1, 1, 1)         # 64-channel source: three taps share an accumulator in wgrad
+        cases.conv_case(dev, BF16, 2, 32, 32, [64, 128, 256], 256, 3, 1, 1, 1)  # tower-like concat: 3-tap, 2-tap and 1-tap weight-gradient tiles
+        cases.conv_case(dev, BF16, 1, 30, 34, [128], 72, 3, 1, 2, 2)        # dilation 2, two taps per tile, ragged N
+        cases.conv_case(dev, BF16, 2, 16, 16, [88], 256, 1, 1, 0, 1)        # 1x1: one tap, nothing to group
         cases.convT_case(dev, BF16, 2, 25, 25, 128, 128, 2)                  # 25 -> 49
         cases.convT_case(dev, BF16, 2, 13, 13, 64, 64, 4)                    # 13 -> 49 (final_c)
     finally:
