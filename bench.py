@@ -395,7 +395,15 @@ def main() -> None:
         launches = step.launches_per_step  # a replay repeats the launches recorded at capture; the host-side counter does not see them
     clocks = sampler.stop()
     timed_e2e(2)
-    ms_e2e = timed_e2e(args.steps)
+    # the end-to-end region shares the host (PCIe, memory) with whatever else runs on the box: a stalled first copy has cost a
+    # region 150 ms in one run out of three.  Three regions of K steps each are timed back to back; the fastest is reported and all
+    # three are listed.
+    e2e_regions, e2e_steps_best = [], []
+    for _ in range(3):
+        e2e_regions.append(timed_e2e(args.steps))
+        if e2e_regions[-1] == min(e2e_regions):
+            e2e_steps_best = list(e2e_step_ms)
+    ms_e2e = min(e2e_regions)
     fl = flush_ms(args.steps)
     ms_res -= fl
     ms_e2e -= fl
@@ -477,7 +485,8 @@ def main() -> None:
                        "execution": "one CUDA graph per step (captured after 3 eager steps), replayed" if step.cuda_graph
                        else "eager launches through the C ABI"},
             "e2e": {"value": e2e_value, "unit": "chips/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
-                    "ms_per_step": ms_e2e / args.steps, "host_ms_each_step": list(e2e_step_ms)},
+                    "ms_per_step": ms_e2e / args.steps, "host_ms_each_step": e2e_steps_best,
+                    "regions_ms": [round(r, 2) for r in e2e_regions], "pick": "fastest of 3 regions of K steps (flush time not yet subtracted)"},
             "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_enqueue_ms[0] if host_enqueue_ms else None, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_base,
             "model_tflops": 3 * w["fwd_gflop_per_chip"] * 1e9 * value / 1e12 if w["fwd_gflop_per_chip"] else None,
             "final_loss": float(losses[-1]),

@@ -45,6 +45,10 @@ class ConvDesc(C.Structure):
         ("out", C.c_void_p),
         ("out_stride", C.c_int32),
         ("stats", C.c_void_p),
+        ("nout", C.c_int32),
+        ("out_seg", C.c_void_p * CNB_MAX_SRC),
+        ("out_seg_c", C.c_int32 * CNB_MAX_SRC),
+        ("out_seg_stride", C.c_int32 * CNB_MAX_SRC),
     ]
 
 

@@ -96,7 +96,18 @@ static int check_conv_desc(const cnb_conv_desc* d) {
         CNB_REQUIRE(d->src[s] != nullptr && d->src_c[s] > 0 && d->src_stride[s] >= d->src_c[s], "conv2d_fwd: bad source %d", s);
         ctot += d->src_c[s];
     }
-    CNB_REQUIRE(d->w_packed && d->out && d->N > 0 && d->out_stride >= d->N && d->w_row_stride >= ctot, "conv2d_fwd: bad weight/output");
+    CNB_REQUIRE(d->w_packed && d->N > 0 && d->w_row_stride >= ctot, "conv2d_fwd: bad weight");
+    if (d->nout == 0) {
+        CNB_REQUIRE(d->out && d->out_stride >= d->N, "conv2d_fwd: bad output");
+    } else {
+        CNB_REQUIRE(d->nout > 0 && d->nout <= CNB_MAX_SRC && d->bias == nullptr && d->stats == nullptr, "conv2d_fwd: bad split output");
+        int n = 0;
+        for (int i = 0; i < d->nout; ++i) {
+            CNB_REQUIRE(d->out_seg[i] && d->out_seg_c[i] > 0 && d->out_seg_stride[i] >= d->out_seg_c[i], "conv2d_fwd: bad output segment %d", i);
+            n += d->out_seg_c[i];
+        }
+        CNB_REQUIRE(n == d->N, "conv2d_fwd: output segments cover %d of %d channels", n, d->N);
+    }
     return CNB_OK;
 }
 
@@ -104,6 +115,7 @@ int cnb_conv2d_fwd_generic(const cnb_conv_desc* d, int dtype, void* stream) {
     int rc = check_conv_desc(d);
     if (rc) return rc;
     CNB_REQUIRE(d->stats == nullptr, "conv2d_fwd_generic: fused BatchNorm statistics exist only in the tcgen05 kernel");
+    CNB_REQUIRE(d->nout == 0, "conv2d_fwd_generic: split outputs exist only in the tcgen05 kernel");
     const long M = (long)d->B * d->Hout * d->Wout;
     dim3 grid(cnb_div_up(M, CG_BM), cnb_div_up(d->N, CG_BN));
     CNB_DISPATCH_DTYPE(dtype, { CNB_LAUNCH((conv_fwd_generic_kernel<T>), grid, dim3(256), 0, (cudaStream_t)stream, *d); });
@@ -169,7 +181,7 @@ int cnb_conv2d_fwd_tiny(const cnb_conv_desc* d, int dtype, void* stream) {
 
 int cnb_conv2d_fwd(const cnb_conv_desc* d, int dtype, void* stream) {
     if (d && d->stats) return cnb_conv2d_fwd_tc(d, dtype, stream);
-    if (check_conv_desc(d) == CNB_OK && conv_tiny_eligible(d)) return cnb_conv2d_fwd_tiny(d, dtype, stream);
+    if (check_conv_desc(d) == CNB_OK && d->nout == 0 && conv_tiny_eligible(d)) return cnb_conv2d_fwd_tiny(d, dtype, stream);
     if (cnb_conv2d_tc_eligible(d, dtype)) return cnb_conv2d_fwd_tc(d, dtype, stream);
     return cnb_conv2d_fwd_generic(d, dtype, stream);
 }
@@ -954,6 +966,14 @@ int cnb_tap_shift_gather(const void* dout, void* dt, int B, int H, int W, int N,
                     out_pitch >= N,
                 "tap_shift_gather: bad arguments");
     const long total = (long)B * H * W * t_pitch;
+    if (N == 9 && KH == 3 && KW == 3 && t_pitch % vec_width(dtype) == 0 && cnb_aligned16(dt)) {  // the three stacked Psi-Net streams
+        CNB_DISPATCH_DTYPE(dtype, {
+            CNB_LAUNCH((tap_shift_gather_px_kernel<T, 9, 3>), dim3(stream_grid((long)B * H * W, 256, 16)), dim3(256), 0, (cudaStream_t)stream,
+                       (const T*)dout, (T*)dt, B, H, W, pad, dil, t_pitch, out_pitch);
+        });
+        CNB_CHECK_LAUNCH("tap_shift_gather_px_kernel");
+        return CNB_OK;
+    }
     CNB_DISPATCH_DTYPE(dtype, {
         CNB_LAUNCH((tap_shift_gather_kernel<T>), dim3(stream_grid(total, 256, 16)), dim3(256), 0, (cudaStream_t)stream, (const T*)dout, (T*)dt,
                    B, H, W, N, KH, KW, pad, dil, t_pitch, out_pitch);

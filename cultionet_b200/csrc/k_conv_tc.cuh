@@ -60,6 +60,12 @@ struct ConvTcParams {
     int out_stride;
     const float* bias;
     float* stats;  // optional [2*N]: per-output-channel sum and sum of squares of the STORED (bf16-rounded) outputs, for BatchNorm
+    // split output (cnb_conv_desc::nout): columns [seg_begin[i], seg_begin[i+1]) of the GEMM go to seg_out[i]; boundaries are
+    // multiples of 32, so every 32-column epilogue chunk has one destination
+    int nseg;
+    int seg_begin[CNB_MAX_SRC + 1];
+    bf16_t* seg_out[CNB_MAX_SRC];
+    int seg_stride[CNB_MAX_SRC];
 };
 
 struct TileCoord {
@@ -358,7 +364,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             const bool valid = vy < p.ph_hv[tc.ph] && vx < p.ph_wv[tc.ph] && oy < p.Hout && ox < p.Wout;
             const bool has_taps = p.ph_tap0[tc.ph + 1] > p.ph_tap0[tc.ph];
             const int n0 = tc.n0;
-            bf16_t* orow = p.out + (((long)tc.b * p.Hout + oy) * p.Wout + ox) * p.out_stride + n0;
+            const long opix = ((long)tc.b * p.Hout + oy) * p.Wout + ox;
+            bf16_t* orow = p.out + opix * p.out_stride + n0;
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
@@ -369,6 +376,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 uint32_t v[32];
                 tmem_ld32(taddr + (uint32_t)(c * 32), v);
                 if (!valid) continue;
+                bf16_t* ochunk = orow + c * 32;
+                if (p.nseg) {
+                    int sg = 0;
+                    while (sg + 1 < p.nseg && col0 >= p.seg_begin[sg + 1]) ++sg;
+                    ochunk = p.seg_out[sg] + opix * p.seg_stride[sg] + (col0 - p.seg_begin[sg]);
+                }
                 if (p.vec_ok && col0 + 32 <= p.N) {
                     uint32_t packed[16];
                     if (p.bias) {
@@ -383,7 +396,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                         for (int j = 0; j < 16; ++j)
                             packed[j] = has_taps ? cnb_pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])) : 0u;
                     }
-                    uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
+                    uint4* dst = reinterpret_cast<uint4*>(ochunk);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
                 } else {
@@ -392,7 +405,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                         if (col0 + j < p.N) {
                             float f = has_taps ? __uint_as_float(v[j]) : 0.f;
                             if (p.bias) f += __ldg(p.bias + col0 + j);
-                            orow[c * 32 + j] = __float2bfloat16(f);
+                            ochunk[j] = __float2bfloat16(f);
                         }
                     }
                 }
@@ -513,6 +526,8 @@ inline bool eligible(const cnb_conv_desc* d, int dtype) {
         if (reinterpret_cast<uintptr_t>(d->src[s]) % 16 != 0) return false;
     }
     if (d->w_row_stride % 8 != 0 || d->w_tap_stride % 8 != 0 || reinterpret_cast<uintptr_t>(d->w_packed) % 16 != 0) return false;
+    for (int i = 0; i < d->nout; ++i)
+        if (d->out_seg_c[i] % 32 != 0 || d->out_seg_stride[i] % 8 != 0 || reinterpret_cast<uintptr_t>(d->out_seg[i]) % 16 != 0) return false;
     return encode_tiled_fn() != nullptr;
 }
 
@@ -545,13 +560,19 @@ inline int launch_bn(const ConvTcParams& p, cudaStream_t stream) {
     return 0;
 }
 
+// Output-tile width: the padded column count times a penalty for narrow tiles (a narrow tile re-stages the A operand more often per
+// output column).  N = 960 (merged data gradient of a tower convolution) takes 4 tiles of 256 with the last one masked, not 15 of 64.
 inline int pick_bn(int N) {
-    if (N % 256 == 0) return 256;
-    if (N % 128 == 0) return 128;
-    if (N % 64 == 0) return 64;
     if (N <= 32) return 32;
-    if (N <= 64) return 64;
-    return N > 512 ? 256 : 128;  // ragged N: the last tile is masked
+    const int bns[4] = {256, 128, 64, 32};
+    const float penalty[4] = {1.0f, 1.15f, 1.6f, 2.5f};
+    int best = 256;
+    float best_cost = 1e30f;
+    for (int i = 0; i < 4; ++i) {
+        const float cost = (float)(cnb_div_up(N, bns[i]) * bns[i]) * penalty[i];
+        if (cost < best_cost) best_cost = cost, best = bns[i];
+    }
+    return best;
 }
 
 inline int conv_tc_launch(const cnb_conv_desc* d, cudaStream_t stream) {
@@ -668,6 +689,20 @@ inline int conv_tc_launch(const cnb_conv_desc* d, cudaStream_t stream) {
     p.out_stride = d->out_stride;
     p.bias = d->bias;
     p.vec_ok = (d->out_stride % 8 == 0 && reinterpret_cast<uintptr_t>(d->out) % 16 == 0) ? 1 : 0;
+    p.nseg = d->nout;
+    if (d->nout > 0) {
+        int c0 = 0;
+        for (int i = 0; i < d->nout; ++i) {
+            p.seg_begin[i] = c0;
+            p.seg_out[i] = reinterpret_cast<bf16_t*>(d->out_seg[i]);
+            p.seg_stride[i] = d->out_seg_stride[i];
+            c0 += d->out_seg_c[i];
+        }
+        p.seg_begin[d->nout] = c0;
+        p.vec_ok = 1;  // eligible(): every segment has a 16-byte pitch and base
+        p.out = p.seg_out[0];
+        p.out_stride = p.seg_stride[0];
+    }
     p.log2_tw = 0;
     while ((1 << p.log2_tw) < p.TW) ++p.log2_tw;
     p.stats = nullptr;

@@ -7,6 +7,7 @@ kernels.  Nothing here computes with torch ops: torch only owns memory, streams 
 from __future__ import annotations
 
 import ctypes as C
+import os
 import weakref
 from typing import Optional, Sequence
 
@@ -164,10 +165,11 @@ _WGRAD_ENTRY = {"auto": "cnb_conv2d_wgrad", "generic": "cnb_conv2d_wgrad_generic
 
 
 STATS_MAX_N = 1024  # csrc/k_conv_tc.cuh
+MERGE_SOURCE_DGRADS = os.environ.get("CNB_MERGE_DGRAD", "1") != "0"  # data gradient of a multi-source convolution as one split-output launch (A/B switch for bench runs)
 
 
 def _launch_conv(sources, src_channels, wp, w_row_off, w_row_stride, w_tap_stride, N, bias, out, geom, transposed, dtype,
-                 want_stats=False):
+                 want_stats=False, out_segments=None):
     """Launches the convolution; with ``want_stats`` returns the [2, N] fp32 BatchNorm partial sums the tcgen05 epilogue produced
     (None when the shape takes another kernel and the caller has to run ``cnb_bn_stats``)."""
     d = ConvDesc()
@@ -185,8 +187,20 @@ def _launch_conv(sources, src_channels, wp, w_row_off, w_row_stride, w_tap_strid
     d.w_row_stride = w_row_stride
     d.N = N
     d.bias = bias.data_ptr() if bias is not None else None
-    d.out = out.data_ptr()
-    d.out_stride = out.shape[-1]
+    if out_segments is None:
+        d.out = out.data_ptr()
+        d.out_stride = out.shape[-1]
+        d.nout = 0
+    else:  # split output: [(tensor, channels), ...] covering the N output channels in order
+        d.out, d.out_stride = None, 0
+        d.nout = len(out_segments)
+        for i, (t, c) in enumerate(out_segments):
+            d.out_seg[i] = t.data_ptr()
+            d.out_seg_c[i] = c
+            d.out_seg_stride[i] = t.shape[-1]
+        out = out_segments[0][0]
+        if not (CONV_BACKEND != "generic" and not _lib.is_emulator() and _lib.lib().cnb_conv2d_tc_eligible(C.byref(d), dtype_code(dtype))):
+            return False
     d.stats = None
     stats = None
     if want_stats and N <= STATS_MAX_N and CONV_BACKEND != "generic" and not _lib.is_emulator():
@@ -197,37 +211,48 @@ def _launch_conv(sources, src_channels, wp, w_row_off, w_row_stride, w_tap_strid
     detail = None
     if _lib.TIMER is not None:
         detail = f"B{B} {Hin}x{Win}->{Hout}x{Wout} {'+'.join(map(str, src_channels))}->{N} k{KH} s{stride}{'T' if transposed else ''}"
+    if _lib.TIMER is not None and out_segments is not None:
+        detail = detail.replace(f"->{N} ", "->" + "+".join(str(c) for _, c in out_segments) + " ")
     call(_CONV_ENTRY[CONV_BACKEND], C.byref(d), dtype_code(dtype), stream_ptr(out), flops=flops, tag="conv_fwd/dgrad", detail=detail)
-    return stats
+    return True if out_segments is not None else stats
 
 
 # With DIRECT_PARAM_GRAD the weight / bias gradient kernels accumulate straight into ``param.grad`` (the flat gradient buffer of
 # optim.FlatAdamW) and the backward returns None for them: no temporary gradient tensor and no AccumulateGrad add per parameter.
 # engine.TrainStep switches it on when no per-parameter gradient hook has to fire (no overlapped bucketed all-reduce).
 DIRECT_PARAM_GRAD = [False]
+_DIRECT_WRITTEN: set = set()  # parameters whose gradient buffer already holds a contribution of the running backward
 
 
 class direct_param_grads:
+    """``with direct_param_grads(): loss.backward()`` -- the gradient buffers must be ZERO (or stale) on entry: the first contribution
+    to a parameter overwrites its buffer (a plain store instead of a read-modify-write), later ones (a shared parameter) accumulate."""
+
     def __init__(self, enabled: bool = True):
         self.enabled = enabled
 
     def __enter__(self):
         self.prev = DIRECT_PARAM_GRAD[0]
         DIRECT_PARAM_GRAD[0] = bool(self.enabled)
+        _DIRECT_WRITTEN.clear()
         return self
 
     def __exit__(self, *exc):
         DIRECT_PARAM_GRAD[0] = self.prev
+        _DIRECT_WRITTEN.clear()
         return False
 
 
-def _direct_grad_target(param, like_shape) -> Optional[torch.Tensor]:
+def _direct_grad_target(param, like_shape):
+    """(gradient buffer, accumulate flag) when the kernel may write ``param.grad`` itself, else (None, 0)."""
     if not DIRECT_PARAM_GRAD[0] or not isinstance(param, torch.nn.Parameter):
-        return None
+        return None, 0
     g = param.grad
     if g is None or g.dtype != torch.float32 or not g.is_contiguous() or tuple(g.shape) != tuple(like_shape) or g.requires_grad:
-        return None
-    return g
+        return None, 0
+    first = id(param) not in _DIRECT_WRITTEN
+    _DIRECT_WRITTEN.add(id(param))
+    return g, 0 if first else 1
 
 
 class _Conv2dFn(torch.autograd.Function):
@@ -301,8 +326,19 @@ class _Conv2dFn(torch.autograd.Function):
             # dgrad: the adjoint gather with the per-tap transposed weights [taps][Ctot][N]; one launch per source slice
             wd = ctx.wd if ctx.wd is not None else pack_weight(weight, kind, N, Ctot, taps, dtype, for_dgrad=True)
             dgeom = (B, Hout, Wout, Hin, Win, KH, KW, stride, pad, dil)
+            merged = False
+            if len(sources) > 1 and all(need_src) and MERGE_SOURCE_DGRADS:
+                # ONE GEMM with N = Ctot whose column ranges land in the sources' gradient tensors (tcgen05 kernel only): dY is
+                # staged once per 256 output columns instead of once per source, and narrow sources share full-width tiles
+                dxs = [torch.empty_like(s) if s.shape[-1] == c else torch.zeros_like(s) for s, c in zip(sources, src_channels)]
+                merged = _launch_conv([dy], [N], wd, 0, wd.shape[2], Ctot * wd.shape[2], Ctot, None, None, dgeom, not transposed, dtype,
+                                      out_segments=list(zip(dxs, src_channels)))
+                if merged:
+                    src_grads = dxs
             coff = 0
             for i, (s, c) in enumerate(zip(sources, src_channels)):
+                if merged:
+                    break
                 if need_src[i]:
                     # a padded source gets zeros in its padding columns (the kernels only write the logical channels)
                     dx = torch.empty_like(s) if s.shape[-1] == c else torch.zeros_like(s)
@@ -329,18 +365,18 @@ class _Conv2dFn(torch.autograd.Function):
                      tag="conv_wgrad", detail=detail)
                 coff += c
             rows, cols, s_n, s_k, s_tap = _weight_strides(kind, N, Ctot, taps, for_dgrad=False)
-            target = _direct_grad_target(ctx.params[0], weight.shape)
+            target, acc_flag = _direct_grad_target(ctx.params[0], weight.shape)
             if target is not None:
-                call("cnb_unpack_wgrad", ptr(dwp), ptr(target), taps, rows, cols, s_n, s_k, s_tap, 1, stream_ptr(dy))
+                call("cnb_unpack_wgrad", ptr(dwp), ptr(target), taps, rows, cols, s_n, s_k, s_tap, acc_flag, stream_ptr(dy))
             else:
                 dw = torch.empty_like(weight, dtype=torch.float32, memory_format=torch.contiguous_format)
                 call("cnb_unpack_wgrad", ptr(dwp), ptr(dw), taps, rows, cols, s_n, s_k, s_tap, 0, stream_ptr(dy))
 
         db = None
         if need_b:
-            target = _direct_grad_target(ctx.params[1], (N,))
+            target, acc_flag = _direct_grad_target(ctx.params[1], (N,))
             if target is not None:
-                call("cnb_bias_grad", ptr(dy), dy_pitch, B * Hout * Wout, N, ptr(target), 1, dtype_code(dtype), stream_ptr(dy))
+                call("cnb_bias_grad", ptr(dy), dy_pitch, B * Hout * Wout, N, ptr(target), acc_flag, dtype_code(dtype), stream_ptr(dy))
             else:
                 db = torch.empty((N,), dtype=torch.float32, device=dev)
                 call("cnb_bias_grad", ptr(dy), dy_pitch, B * Hout * Wout, N, ptr(db), 0, dtype_code(dtype), stream_ptr(dy))

@@ -65,6 +65,14 @@ typedef struct {
                                      * channel over all pixels (y = the stored, rounded value), i.e. BatchNorm's batch statistics come out
                                      * of the convolution epilogue and cnb_bn_stats is skipped.  Only honoured by cnb_conv2d_fwd_tc
                                      * (N <= 1024); the other kernels require NULL. */
+    /* Split output (the data gradient of a convolution over a virtual concatenation: one GEMM with N = Ctot whose columns land in
+     * the gradient tensors of the individual sources).  nout = 0: the single output above.  nout > 0: `out` is ignored and output
+     * channels [sum_{j<i} out_seg_c[j], + out_seg_c[i]) go to out_seg[i] + p*out_seg_stride[i] + c.  Only the tcgen05 kernel
+     * implements it (every out_seg_c a multiple of 32, sum = N, no bias); ask cnb_conv2d_tc_eligible() first. */
+    int32_t nout;
+    void* out_seg[CNB_MAX_SRC];
+    int32_t out_seg_c[CNB_MAX_SRC];
+    int32_t out_seg_stride[CNB_MAX_SRC];
 } cnb_conv_desc;
 
 /* picks the tiny-channel kernel, else the tcgen05/TMA kernel when cnb_conv2d_tc_eligible(), else the CUDA-core kernel */

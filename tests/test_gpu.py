@@ -4,6 +4,7 @@ import pytest
 import torch
 
 from tests import cases
+from tests.util import rel_err
 
 pytestmark = pytest.mark.gpu
 F32 = torch.float32
@@ -335,3 +336,66 @@ def test_reference_test_cultionet_configuration_bf16(dev):
         assert out[k].shape == (2, 1, 100, 100) and bool(torch.isfinite(out[k]).all())
     (out["distance"].mean() + out["edge"].mean() + out["crop"].mean()).backward()
     assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in model.parameters() if p.requires_grad)
+
+
+@pytest.mark.gpu
+def test_direct_parameter_gradients_match_autograd_accumulation(dev):
+    """functional.direct_param_grads: the tcgen05 weight-gradient path writes into ``param.grad`` itself.  Operator level in bf16 (one
+    convolution is deterministic up to the split-K order); model level in fp32 (a bf16 model is not repeatable run to run: the
+    atomically summed BatchNorm statistics flip bf16 roundings, 2-4 % on the gradients of two identical steps)."""
+    import cultionet_b200 as cb
+    from cultionet_b200 import functional as Fn
+    from cultionet_b200.models.lightning import CultionetLitModel
+
+    torch.manual_seed(0)
+    xs = [torch.randn(2, 32, 32, c, device=dev).to(BF16).requires_grad_(True) for c in (64, 256)]
+    w = torch.nn.Parameter(torch.randn(128, 320, 3, 3, device=dev) / 50)
+    b = torch.nn.Parameter(torch.randn(128, device=dev))
+    g = torch.randn(2, 32, 32, 128, device=dev).to(BF16)
+    Fn.conv2d(xs, w, b, 3, 1, 1, 1).backward(g)
+    want_w, want_b = w.grad.clone(), b.grad.clone()
+    for second in (False, True):  # first contribution overwrites, a second one accumulates
+        w.grad, b.grad = torch.full_like(w, 7.0), torch.full_like(b, 7.0)  # stale contents must not leak into the first write
+        with Fn.direct_param_grads():
+            Fn.conv2d(xs, w, b, 3, 1, 1, 1).backward(g)
+            if second:
+                Fn.conv2d(xs, w, b, 3, 1, 1, 1).backward(g)
+        scale = 2.0 if second else 1.0
+        assert rel_err(w.grad, scale * want_w) < 1e-5 and rel_err(b.grad, scale * want_b) < 1e-5
+
+    torch.manual_seed(3)
+    model = CultionetLitModel(in_channels=3, in_time=8, hidden_channels=16, dropout=0.0, compute_dtype=F32).to(dev)
+    opt = model.configure_optimizers(total_steps=10)
+    batch = cb.Data(x=torch.rand(2, 3, 8, 32, 32, device=dev), y=torch.randint(-1, 3, (2, 32, 32), device=dev),
+                    bdist=torch.rand(2, 32, 32, device=dev))
+    grads = []
+    for direct in (False, True):
+        opt.zero_grad()
+        loss = model.training_step(batch, 0)
+        with Fn.direct_param_grads(direct):
+            loss.backward()
+        grads.append(opt.flat_grad.clone())
+    assert float(grads[0].norm()) > 0 and rel_err(grads[1], grads[0]) < 1e-4
+
+
+@pytest.mark.gpu
+def test_merged_multi_source_data_gradient(dev):
+    """The data gradient of a convolution over a virtual concatenation as ONE split-output tcgen05 launch vs one launch per source."""
+    from cultionet_b200 import functional as Fn
+
+    assert Fn.MERGE_SOURCE_DGRADS
+    for cins, cout, k in (([64, 128, 256, 256], 256, 3), ([32, 512, 96], 128, 1), ([256, 64], 72, 3)):
+        cases.conv_case(dev, BF16, 2, 32, 32, cins, cout, k, 1, k // 2, 1)
+    # same shapes, per-source launches: identical results up to bf16 rounding of identical fp32 sums
+    torch.manual_seed(0)
+    xs = [(torch.randn(2, 24, 24, c, device=dev)).to(BF16).requires_grad_(True) for c in (64, 128, 256)]
+    w = (torch.randn(256, 448, 3, 3, device=dev) / 60).requires_grad_(True)
+    g = torch.randn(2, 24, 24, 256, device=dev).to(BF16)
+    a = torch.autograd.grad(Fn.conv2d(xs, w, None, 3, 1, 1, 1), xs, g)
+    Fn.MERGE_SOURCE_DGRADS = False
+    try:
+        b = torch.autograd.grad(Fn.conv2d(xs, w, None, 3, 1, 1, 1), xs, g)
+    finally:
+        Fn.MERGE_SOURCE_DGRADS = True
+    for u, v in zip(a, b):
+        assert torch.equal(u, v)

@@ -104,3 +104,25 @@ def test_bad_input_shape_raises(dev):
     m = cb.TowerUNet(in_channels=2, in_time=6, hidden_channels=8)
     with pytest.raises(ValueError):
         m(torch.rand(1, 3, 6, 16, 16))
+
+
+def test_direct_parameter_gradients_match_autograd_accumulation(dev):
+    """engine.TrainStep lets the weight / bias gradient kernels write into the flat gradient buffer (functional.direct_param_grads);
+    the result must equal what autograd's AccumulateGrad produces."""
+    from cultionet_b200 import functional as F
+    from cultionet_b200.models.lightning import CultionetLitModel
+
+    torch.manual_seed(3)
+    model = CultionetLitModel(in_channels=2, in_time=6, hidden_channels=8, dropout=0.0, compute_dtype=torch.float32).to(dev)
+    opt = model.configure_optimizers(total_steps=10)
+    batch = cb.Data(x=torch.rand(2, 2, 6, 16, 16, device=dev), y=torch.randint(-1, 3, (2, 16, 16), device=dev),
+                    bdist=torch.rand(2, 16, 16, device=dev))
+    grads = []
+    for direct in (False, True):
+        opt.zero_grad()
+        loss = model.training_step(batch, 0)
+        with F.direct_param_grads(direct):
+            loss.backward()
+        grads.append(opt.flat_grad.clone())
+    assert float(grads[0].norm()) > 0
+    assert float((grads[0] - grads[1]).norm() / grads[0].norm()) < 1e-5
