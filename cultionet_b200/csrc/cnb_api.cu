@@ -705,7 +705,7 @@ int64_t cnb_na2d_bwd_workspace_floats(int B, int H, int W, int heads, int hd, in
     size_t smem;
     if (!naf::eligible(hd, ksize, dilation, dtype) || !na_tile_setup(B, H, W, heads, hd, ksize, dilation, 1.f, dtype, false, &g, &lph, &smem))
         return 0;
-    return (int64_t)B * H * W * heads * ksize * ksize * 2;
+    return (int64_t)B * H * W * heads * ksize * ksize;  // one bf16 pair (4 bytes) per (pixel, head, neighbour)
 }
 
 int cnb_na2d_tiled_eligible(int B, int H, int W, int heads, int hd, int ksize, int dilation, int dtype) {
@@ -797,9 +797,9 @@ int cnb_na2d_bwd(const void* qkv, const void* dout, const void* out, const float
         if (pds_ws && naf::eligible(hd, ksize, dilation, dtype)) {
             // the staged rows are k|v (query pass) or q|dout (key pass); no per-pixel statistics ride along
             smem = (size_t)g.RH * g.RW * 2 * hd * 2;
-            CNB_NAF_LAUNCH(naf::na2d_bwd_dq_fast_kernel, (const bf16_t*)qkv, (const bf16_t*)dout, (const bf16_t*)out, lse, (float2*)pds_ws,
+            CNB_NAF_LAUNCH(naf::na2d_bwd_dq_fast_kernel, (const bf16_t*)qkv, (const bf16_t*)dout, (const bf16_t*)out, lse, (uint32_t*)pds_ws,
                            (bf16_t*)dqkv, g);
-            CNB_NAF_LAUNCH(naf::na2d_bwd_dkv_fast_kernel, (const bf16_t*)qkv, (const bf16_t*)dout, (const float2*)pds_ws, (bf16_t*)dqkv, g);
+            CNB_NAF_LAUNCH(naf::na2d_bwd_dkv_fast_kernel, (const bf16_t*)qkv, (const bf16_t*)dout, (const uint32_t*)pds_ws, (bf16_t*)dqkv, g);
             CNB_CHECK_LAUNCH("na2d_bwd_fast_kernels");
             return CNB_OK;
         }

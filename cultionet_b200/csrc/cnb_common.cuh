@@ -206,6 +206,45 @@ __device__ __forceinline__ float cnb_silu_grad(float x) {
     return s * (1.0f + x * (1.0f - s));
 }
 
+// ---------------------------------------------------------------------------------------------
+// Mixed-precision FMA (sm_100: fma.rn.f32.bf16 -> SASS FHFMA.BF16): fp32 accumulator, bf16 operands read as the halves of packed
+// 32-bit words.  A bf16 operand is never unpacked: the (shift, mask) pair per element of the usual bf16 -> fp32 path runs on the
+// half-rate integer pipe and was half of the instructions of the neighbourhood-attention kernels (ncu: 70-75 % issue-slot busy).
+// ---------------------------------------------------------------------------------------------
+// acc + a.lo * b.lo + a.hi * b.hi
+__device__ __forceinline__ float cnb_fma2_bf16(uint32_t a, uint32_t b, float acc) {
+#ifdef CNB_EMU
+    acc = fmaf(cnb_bits2f(a << 16), cnb_bits2f(b << 16), acc);
+    return fmaf(cnb_bits2f(a & 0xffff0000u), cnb_bits2f(b & 0xffff0000u), acc);
+#else
+    asm("{\n\t.reg .b16 al, ah, bl, bh;\n\tmov.b32 {al, ah}, %1;\n\tmov.b32 {bl, bh}, %2;\n\t"
+        "fma.rn.f32.bf16 %0, al, bl, %0;\n\tfma.rn.f32.bf16 %0, ah, bh, %0;\n\t}"
+        : "+f"(acc)
+        : "r"(a), "r"(b));
+    return acc;
+#endif
+}
+// (acc_lo, acc_hi) += w * (b.lo, b.hi) with w = the LOW (HI = false) or HIGH (HI = true) half of wp
+template <bool HI>
+__device__ __forceinline__ void cnb_axpy2_bf16(uint32_t wp, uint32_t b, float& acc_lo, float& acc_hi) {
+#ifdef CNB_EMU
+    const float w = HI ? cnb_bits2f(wp & 0xffff0000u) : cnb_bits2f(wp << 16);
+    acc_lo = fmaf(w, cnb_bits2f(b << 16), acc_lo);
+    acc_hi = fmaf(w, cnb_bits2f(b & 0xffff0000u), acc_hi);
+#else
+    if (HI)
+        asm("{\n\t.reg .b16 wl, wh, bl, bh;\n\tmov.b32 {wl, wh}, %2;\n\tmov.b32 {bl, bh}, %3;\n\t"
+            "fma.rn.f32.bf16 %0, wh, bl, %0;\n\tfma.rn.f32.bf16 %1, wh, bh, %1;\n\t}"
+            : "+f"(acc_lo), "+f"(acc_hi)
+            : "r"(wp), "r"(b));
+    else
+        asm("{\n\t.reg .b16 wl, wh, bl, bh;\n\tmov.b32 {wl, wh}, %2;\n\tmov.b32 {bl, bh}, %3;\n\t"
+            "fma.rn.f32.bf16 %0, wl, bl, %0;\n\tfma.rn.f32.bf16 %1, wl, bh, %1;\n\t}"
+            : "+f"(acc_lo), "+f"(acc_hi)
+            : "r"(wp), "r"(b));
+#endif
+}
+
 __device__ __forceinline__ float cnb_warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -8,8 +8,11 @@
 //     TILE >= dilation, see na2d_fwd_tile_kernel) and the lanes of a (pixel, head) group reduce with full-warp xor shuffles --
 //     ncu/SASS of the generic kernel showed ~110 instructions per neighbour, half of them generic-address LD, 64-bit address
 //     arithmetic and MATCH/VOTE sequences guarding partial-mask shuffles;
+//   * every multiply-add takes its bf16 operands as the halves of packed words (fma.rn.f32.bf16 = FHFMA.BF16 on sm_100, fp32
+//     accumulate): no bf16 -> fp32 unpacking, whose shift/mask pairs were half of the issued instructions; softmax probabilities
+//     and logit gradients enter those products rounded to bf16 (as the P operand of a tensor-core attention kernel does);
 //   * the backward no longer recomputes q.k and dout.v in the key-side pass: the query-side pass stores p_in and
-//     scale * p_in (dp_in - D_i) (72 bytes per (pixel, head) for k = 3), and the key-side pass is a pure gather
+//     scale * p_in (dp_in - D_i) as one bf16 pair (36 bytes per (pixel, head) for k = 3), and the key-side pass is a pure gather
 //         dk_j = sum_i ds_ij q_i,   dv_j = sum_i p_ij dout_i
 //     with no dot products, no exponentials and no shuffles.
 #pragma once
@@ -59,6 +62,22 @@ __device__ __forceinline__ void axpy8(float w, const uint4& r, float* acc) {
     for (int j = 0; j < 8; ++j) acc[j] = fmaf(w, b[j], acc[j]);
 }
 
+// the same on packed operands (FHFMA.BF16, cnb_common.cuh): no unpacking, one instruction per element
+__device__ __forceinline__ float dot8p(const uint4& a, const uint4& b) {
+    float s = cnb_fma2_bf16(a.x, b.x, 0.f);
+    s = cnb_fma2_bf16(a.y, b.y, s);
+    s = cnb_fma2_bf16(a.z, b.z, s);
+    return cnb_fma2_bf16(a.w, b.w, s);
+}
+// acc[0..8) += w * b, w = the low (HI = false) / high (HI = true) bf16 half of wp
+template <bool HI>
+__device__ __forceinline__ void axpy8p(uint32_t wp, const uint4& b, float* acc) {
+    cnb_axpy2_bf16<HI>(wp, b.x, acc[0], acc[1]);
+    cnb_axpy2_bf16<HI>(wp, b.y, acc[2], acc[3]);
+    cnb_axpy2_bf16<HI>(wp, b.z, acc[4], acc[5]);
+    cnb_axpy2_bf16<HI>(wp, b.w, acc[6], acc[7]);
+}
+
 struct TilePos {
     int head, b, y0, x0, ry0, rx0;
     long img_pix0;
@@ -95,17 +114,17 @@ __global__ void __launch_bounds__(NA_TILE_THREADS) na2d_fwd_fast_kernel(const bf
     const int dil = DIL > 0 ? DIL : g.dil;
     const int col_step = dil * 2 * HD, row_step = col_step * g.RW;  // elements between window columns / rows in the staged region
 
-    for (int it = threadIdx.x; it < NA_TH * NA_TW * LPH; it += NA_TILE_THREADS) {
+    static_assert((NA_TH * NA_TW * LPH) % NA_TILE_THREADS == 0, "whole rounds: the warps stay converged for the shuffles");
+#pragma unroll 1
+    for (int round = 0; round < (NA_TH * NA_TW * LPH) / NA_TILE_THREADS; ++round) {  // compile-time trip count: provably uniform
+        const int it = round * NA_TILE_THREADS + threadIdx.x;
         const int sub = it % LPH, pl = it / LPH;
         const int lx = pl % NA_TW, ly = pl / NA_TW;
         const bool valid = (t.y0 + ly) < g.H && (t.x0 + lx) < g.W;
         // out-of-image lanes shadow the last pixel of the image (it lies in this tile): control flow and shuffles stay uniform
         const int y = (t.y0 + ly) < g.H ? t.y0 + ly : g.H - 1, x = (t.x0 + lx) < g.W ? t.x0 + lx : g.W - 1;
         const long pix = t.img_pix0 + (long)y * g.W + x;
-        float q[8];
-        unpack8(*reinterpret_cast<const uint4*>(qkv + pix * 3 * C + t.head * HD + sub * 8), q);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) q[j] *= g.scale;
+        const uint4 qraw = *reinterpret_cast<const uint4*>(qkv + pix * 3 * C + t.head * HD + sub * 8);
         const int sy = wstart<DIL>(y, g.H, KS, g.dil), sx = wstart<DIL>(x, g.W, KS, g.dil);
         const bf16_t* kb = sm + ((sy - t.ry0) * g.RW + (sx - t.rx0)) * 2 * HD + sub * 8;
         float lg[K2];
@@ -114,7 +133,7 @@ __global__ void __launch_bounds__(NA_TILE_THREADS) na2d_fwd_fast_kernel(const bf
         for (int a = 0; a < KS; ++a)
 #pragma unroll
             for (int b = 0; b < KS; ++b) {
-                const float s = gsum<LPH>(dot8(q, *reinterpret_cast<const uint4*>(kb + a * row_step + b * col_step)));
+                const float s = g.scale * gsum<LPH>(dot8p(qraw, *reinterpret_cast<const uint4*>(kb + a * row_step + b * col_step)));
                 lg[a * KS + b] = s;
                 m = fmaxf(m, s);
             }
@@ -127,10 +146,12 @@ __global__ void __launch_bounds__(NA_TILE_THREADS) na2d_fwd_fast_kernel(const bf
         float o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = 0.f;
+        // the un-normalised probabilities (in (0, 1]) weight v as bf16, like the P operand of a tensor-core attention kernel
 #pragma unroll
         for (int a = 0; a < KS; ++a)
 #pragma unroll
-            for (int b = 0; b < KS; ++b) axpy8(lg[a * KS + b], *reinterpret_cast<const uint4*>(kb + a * row_step + b * col_step + HD), o);
+            for (int b = 0; b < KS; ++b)
+                axpy8p<false>(cnb_pack_bf16x2(lg[a * KS + b], 0.f), *reinterpret_cast<const uint4*>(kb + a * row_step + b * col_step + HD), o);
         if (valid) {
             const float inv = 1.0f / l;
 #pragma unroll
@@ -147,7 +168,7 @@ __global__ void __launch_bounds__(NA_TILE_THREADS) na2d_fwd_fast_kernel(const bf
 template <int KS, int DIL, int LPH>
 __global__ void __launch_bounds__(NA_TILE_THREADS) na2d_bwd_dq_fast_kernel(const bf16_t* __restrict__ qkv, const bf16_t* __restrict__ dout,
                                                                           const bf16_t* __restrict__ out, const float* __restrict__ lse,
-                                                                          float2* __restrict__ pds, bf16_t* __restrict__ dqkv, NaTile g) {
+                                                                          uint32_t* __restrict__ pds, bf16_t* __restrict__ dqkv, NaTile g) {
     CNB_PDL_SYNC();
     constexpr int HD = LPH * 8, K2 = KS * KS;
     CNB_DYN_SMEM(sm_raw);
@@ -159,44 +180,41 @@ __global__ void __launch_bounds__(NA_TILE_THREADS) na2d_bwd_dq_fast_kernel(const
     const int dil = DIL > 0 ? DIL : g.dil;
     const int col_step = dil * 2 * HD, row_step = col_step * g.RW;
 
-    for (int it = threadIdx.x; it < NA_TH * NA_TW * LPH; it += NA_TILE_THREADS) {
+    static_assert((NA_TH * NA_TW * LPH) % NA_TILE_THREADS == 0, "whole rounds: the warps stay converged for the shuffles");
+#pragma unroll 1
+    for (int round = 0; round < (NA_TH * NA_TW * LPH) / NA_TILE_THREADS; ++round) {  // compile-time trip count: provably uniform
+        const int it = round * NA_TILE_THREADS + threadIdx.x;
         const int sub = it % LPH, pl = it / LPH;
         const int lx = pl % NA_TW, ly = pl / NA_TW;
         const bool valid = (t.y0 + ly) < g.H && (t.x0 + lx) < g.W;
         const int y = (t.y0 + ly) < g.H ? t.y0 + ly : g.H - 1, x = (t.x0 + lx) < g.W ? t.x0 + lx : g.W - 1;
         const long pix = t.img_pix0 + (long)y * g.W + x;
-        float q[8], go[8];
-        unpack8(*reinterpret_cast<const uint4*>(qkv + pix * 3 * C + t.head * HD + sub * 8), q);
+        const uint4 qraw = *reinterpret_cast<const uint4*>(qkv + pix * 3 * C + t.head * HD + sub * 8);
         const uint4 graw = *reinterpret_cast<const uint4*>(dout + pix * C + t.head * HD + sub * 8);
-        unpack8(graw, go);
-        const float D = gsum<LPH>(dot8(go, *reinterpret_cast<const uint4*>(out + pix * C + t.head * HD + sub * 8)));
+        const float D = gsum<LPH>(dot8p(graw, *reinterpret_cast<const uint4*>(out + pix * C + t.head * HD + sub * 8)));
         const float L = lse[pix * g.heads + t.head];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) q[j] *= g.scale;
         const int sy = wstart<DIL>(y, g.H, KS, g.dil), sx = wstart<DIL>(x, g.W, KS, g.dil);
         const bf16_t* kb = sm + ((sy - t.ry0) * g.RW + (sx - t.rx0)) * 2 * HD + sub * 8;
         float dq[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) dq[j] = 0.f;
-        float2* rec = pds + (pix * g.heads + t.head) * K2;
+        uint32_t* rec = pds + (pix * g.heads + t.head) * K2;
 #pragma unroll
         for (int a = 0; a < KS; ++a)
 #pragma unroll
             for (int b = 0; b < KS; ++b) {
                 const uint4 kraw = *reinterpret_cast<const uint4*>(kb + a * row_step + b * col_step);
                 const uint4 vraw = *reinterpret_cast<const uint4*>(kb + a * row_step + b * col_step + HD);
-                const float s = gsum<LPH>(dot8(q, kraw)), dp = gsum<LPH>(dot8(go, vraw));
+                const float s = g.scale * gsum<LPH>(dot8p(qraw, kraw)), dp = gsum<LPH>(dot8p(graw, vraw));
                 const float p = cnb_exp(s - L);
-                const float ds = p * (dp - D);
-                axpy8(ds, kraw, dq);
-                // the lanes of the group share p and ds: lane (n mod LPH) writes record n (72 contiguous bytes per group for k = 3)
-                if (valid && sub == (a * KS + b) % LPH) rec[a * KS + b] = make_float2(p, ds * g.scale);
+                const float ds = p * (dp - D) * g.scale;
+                // record = (p, scale * ds) as one bf16 pair: the weights of this pass (ds, high half) and of the key-side pass
+                const uint32_t w = cnb_pack_bf16x2(p, ds);
+                axpy8p<true>(w, kraw, dq);
+                // the lanes of the group share the record: lane (n mod LPH) writes record n (36 contiguous bytes per group for k = 3)
+                if (valid && sub == (a * KS + b) % LPH) rec[a * KS + b] = w;
             }
-        if (valid) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) dq[j] *= g.scale;
-            cnb_stv(dqkv + pix * 3 * C + t.head * HD + sub * 8, dq);
-        }
+        if (valid) cnb_stv(dqkv + pix * 3 * C + t.head * HD + sub * 8, dq);  // ds already carries the scale
     }
 }
 
@@ -222,7 +240,7 @@ __device__ __forceinline__ uint32_t inverse_mask(int j, int len, int dil_rt) {
 // ---------------------------------------------------------------------------------------------------------------------
 template <int KS, int DIL, int LPH>
 __global__ void __launch_bounds__(NA_TILE_THREADS) na2d_bwd_dkv_fast_kernel(const bf16_t* __restrict__ qkv, const bf16_t* __restrict__ dout,
-                                                                           const float2* __restrict__ pds, bf16_t* __restrict__ dqkv,
+                                                                           const uint32_t* __restrict__ pds, bf16_t* __restrict__ dqkv,
                                                                            NaTile g) {
     CNB_PDL_SYNC();
     constexpr int HD = LPH * 8, K2 = KS * KS;
@@ -255,6 +273,30 @@ __global__ void __launch_bounds__(NA_TILE_THREADS) na2d_bwd_dkv_fast_kernel(cons
         float dk[8], dv[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) dk[j] = 0.f, dv[j] = 0.f;
+        // Interior keys (most of the image): no window that holds the key is clamped, so the queries are exactly the k x k pixels
+        // (y + my*d, x + mx*d), |my|, |mx| <= k/2, the key sits at window position (k/2 - my, k/2 - mx) of each, and all of them lie
+        // in the staged region: compile-time offsets, no window arithmetic (the generic path below spends ~60 integer instructions
+        // per candidate on it, 5 x 5 candidates for k = 3).  A clamped window reaches at most (k - 1)*d + d - 1 from its border.
+        constexpr int HK = KS / 2;
+        const int lim = (2 * HK + 1) * dil;
+        if (y >= lim && y + lim < g.H && x >= lim && x + lim < g.W) {
+            const bf16_t* qb = sm + ((y - t.ry0) * g.RW + (x - t.rx0)) * 2 * HD + sub * 8;
+            const uint32_t* rb = pds + (pix * g.heads + t.head) * K2;
+            const long rec_row = (long)dil * g.W * g.heads * K2, rec_col = (long)dil * g.heads * K2;
+            const int sm_row = dil * g.RW * 2 * HD, sm_col = dil * 2 * HD;
+#pragma unroll
+            for (int my = -HK; my <= HK; ++my)
+#pragma unroll
+                for (int mx = -HK; mx <= HK; ++mx) {
+                    const uint32_t w = rb[my * rec_row + mx * rec_col + (HK - my) * KS + (HK - mx)];
+                    const bf16_t* qp = qb + my * sm_row + mx * sm_col;
+                    axpy8p<true>(w, *reinterpret_cast<const uint4*>(qp), dk);
+                    axpy8p<false>(w, *reinterpret_cast<const uint4*>(qp + HD), dv);
+                }
+            cnb_stv(dqkv + pix * 3 * C + C + t.head * HD + sub * 8, dk);
+            cnb_stv(dqkv + pix * 3 * C + 2 * C + t.head * HD + sub * 8, dv);
+            continue;
+        }
         const uint32_t ymask = inverse_mask<KS, DIL>(y, g.H, g.dil), xmask = inverse_mask<KS, DIL>(x, g.W, g.dil);
         // column index of x inside the window of each candidate query column (hoisted out of the row loop)
         int bcol[2 * KS - 1];
@@ -275,7 +317,7 @@ __global__ void __launch_bounds__(NA_TILE_THREADS) na2d_bwd_dkv_fast_kernel(cons
                 const int ix = x + (mx - (KS - 1)) * dil;
                 const int rx = ix - t.rx0;
                 const long ipix = t.img_pix0 + (long)iy * g.W + ix;
-                const float2 w = pds[(ipix * g.heads + t.head) * K2 + arow * KS + bcol[mx]];
+                const uint32_t w = pds[(ipix * g.heads + t.head) * K2 + arow * KS + bcol[mx]];  // bf16 pair (p, scale * ds)
                 uint4 qraw, graw;
                 if (ry >= 0 && ry < g.RH && rx >= 0 && rx < g.RW) {
                     const bf16_t* qp = sm + (ry * g.RW + rx) * 2 * HD + sub * 8;
@@ -285,8 +327,8 @@ __global__ void __launch_bounds__(NA_TILE_THREADS) na2d_bwd_dkv_fast_kernel(cons
                     qraw = *reinterpret_cast<const uint4*>(qkv + ipix * 3 * C + t.head * HD + sub * 8);
                     graw = *reinterpret_cast<const uint4*>(dout + ipix * C + t.head * HD + sub * 8);
                 }
-                axpy8(w.y, qraw, dk);
-                axpy8(w.x, graw, dv);
+                axpy8p<true>(w, qraw, dk);
+                axpy8p<false>(w, graw, dv);
             }
         }
         cnb_stv(dqkv + pix * 3 * C + C + t.head * HD + sub * 8, dk);

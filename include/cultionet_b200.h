@@ -202,7 +202,8 @@ int cnb_na2d_bwd(const void* qkv, const void* dout, const void* out, const float
                  void* dqkv, int B, int H, int W, int heads, int hd, int ksize, int dilation, float scale, int dtype, void* stream);
 /* Specialised backward (bf16, kernel 3 or 7, dilation 1 or 2, head_dim 32 or 64): the query-side pass stores the attention
  * probabilities and their scaled logit gradients so that the key-side pass is a pure gather.  Returns the number of fp32 elements
- * of that scratch (pds_ws: [B,H,W,heads,k*k,2]) or 0 when the shape takes the generic kernels (pds_ws may then be NULL). */
+ * of that scratch (pds_ws: [B,H,W,heads,k*k] bf16 pairs (p, scale*ds), 4 bytes each) or 0 when the shape takes the generic kernels
+ * (pds_ws may then be NULL). */
 int64_t cnb_na2d_bwd_workspace_floats(int B, int H, int W, int heads, int hd, int ksize, int dilation, int dtype);
 
 /* ------------------------------------------------------------------------------------------------
