@@ -303,19 +303,19 @@ int cnb_pack_weights_batched(const cnb_pack_desc* table, int ndesc, int total_ti
     return CNB_OK;
 }
 
-int cnb_unpack_wgrad(const float* dwp, float* g, int taps, int N, int K, int64_t s_n, int64_t s_k, int64_t s_tap, int accumulate, void* stream) {
+int cnb_unpack_wgrad(float* dwp, float* g, int taps, int N, int K, int64_t s_n, int64_t s_k, int64_t s_tap, int mode, void* stream) {
     CNB_REQUIRE(dwp && g && taps > 0 && N > 0 && K > 0, "unpack_wgrad: bad arguments");
     if (taps <= 32) {
         const size_t smem = (size_t)taps * PW_T * (PW_T + 1) * sizeof(float);
         CNB_SET_SMEM(unpack_wgrad_tiled_kernel, smem);
         CNB_LAUNCH(unpack_wgrad_tiled_kernel, dim3(cnb_div_up(K, PW_T), cnb_div_up(N, PW_T)), dim3(256), smem, (cudaStream_t)stream, dwp, g, taps,
-                   N, K, (long)s_n, (long)s_k, (long)s_tap, accumulate);
+                   N, K, (long)s_n, (long)s_k, (long)s_tap, mode);
         CNB_CHECK_LAUNCH("unpack_wgrad_tiled_kernel");
         return CNB_OK;
     }
     const long total = (long)taps * N * K;
     CNB_LAUNCH(unpack_wgrad_kernel, dim3(stream_grid(total)), dim3(256), 0, (cudaStream_t)stream, dwp, g, taps, N, K, (long)s_n, (long)s_k,
-               (long)s_tap, accumulate);
+               (long)s_tap, mode);
     CNB_CHECK_LAUNCH("unpack_wgrad_kernel");
     return CNB_OK;
 }

@@ -215,8 +215,8 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
     }
 }
 
-__global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ g, int taps, int N, int K, long s_n, long s_k,
-                                    long s_tap, int accumulate) {
+__global__ void unpack_wgrad_kernel(float* __restrict__ dwp, float* __restrict__ g, int taps, int N, int K, long s_n, long s_k,
+                                    long s_tap, int mode) {
     CNB_PDL_SYNC();
     const long total = (long)taps * N * K;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -225,7 +225,9 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, float* __rest
         const int n = (int)(t % N);
         const int tap = (int)(t / N);
         const long o = n * s_n + k * s_k + tap * s_tap;
-        g[o] = accumulate ? g[o] + dwp[i] : dwp[i];
+        const float v = dwp[i];
+        if (mode & 2) dwp[i] = 0.f;
+        g[o] = (mode & 1) ? g[o] + v : v;
     }
 }
 
@@ -296,33 +298,50 @@ __global__ void __launch_bounds__(256) pack_weight_batched_kernel(const cnb_pack
                         d.pitch_k, d.pitch_n, (long)d.s_n, (long)d.s_k, (long)d.s_tap, (t / d.tiles_x) * PW_T, (t % d.tiles_x) * PW_T);
 }
 
-// g[n*s_n + k*s_k + tap*s_tap] (+)= dwp[tap][n][k], written in the parameter's memory order
-__global__ void __launch_bounds__(256) unpack_wgrad_tiled_kernel(const float* __restrict__ dwp, float* __restrict__ g, int taps, int N, int K,
-                                                                long s_n, long s_k, long s_tap, int accumulate) {
+// g[n*s_n + k*s_k + tap*s_tap] (+)= dwp[tap][n][k], written in the parameter's memory order.  mode bit 0: accumulate into g; bit 1:
+// clear dwp after reading it (a persistent per-parameter accumulator is then zero again for the next step: no fill kernel).
+__global__ void __launch_bounds__(256) unpack_wgrad_tiled_kernel(float* __restrict__ dwp, float* __restrict__ g, int taps, int N, int K,
+                                                                long s_n, long s_k, long s_tap, int mode) {
     CNB_PDL_SYNC();
     CNB_DYN_SMEM(sm_raw);
     float* tile = reinterpret_cast<float*>(sm_raw);
     const int n0 = blockIdx.y * PW_T, k0 = blockIdx.x * PW_T;
-#pragma unroll 4
-    for (int i = threadIdx.x; i < taps * PW_T * PW_T; i += blockDim.x) {
-        const int kl = i % PW_T, t = i / PW_T;
-        const int nl = t % PW_T, tap = t / PW_T;
-        const int n = n0 + nl, k = k0 + kl;
-        tile[(tap * PW_T + nl) * (PW_T + 1) + kl] = (n < N && k < K) ? dwp[((long)tap * N + n) * K + k] : 0.f;
+    const bool accumulate = mode & 1, clear = mode & 2;
+    // read phase: thread (nl = t / 32, kl = t % 32) walks the taps and every fourth... row: no divisions inside the loop
+    {
+        const int kl = threadIdx.x % PW_T, nl0 = threadIdx.x / PW_T;  // PW_T = 32, 256 threads: 8 rows per pass
+        const int k = k0 + kl;
+        for (int tap = 0; tap < taps; ++tap)
+            for (int nl = nl0; nl < PW_T; nl += 256 / PW_T) {
+                const int n = n0 + nl;
+                float v = 0.f;
+                if (n < N && k < K) {
+                    float* src = dwp + ((long)tap * N + n) * K + k;
+                    v = *src;
+                    if (clear) *src = 0.f;
+                }
+                tile[(tap * PW_T + nl) * (PW_T + 1) + kl] = v;
+            }
     }
     __syncthreads();
     const int per = PW_T * taps;
     const bool k_inner = s_k <= s_n;
-#pragma unroll 4
-    for (int i = threadIdx.x; i < PW_T * per; i += blockDim.x) {
-        const int outer = i / per, rem = i - outer * per;
-        const int inner = rem / taps, tap = rem - inner * taps;
-        const int nl = k_inner ? outer : inner, kl = k_inner ? inner : outer;
-        const int n = n0 + nl, k = k0 + kl;
-        if (n < N && k < K) {
-            const long o = n * s_n + k * s_k + tap * s_tap;
-            const float v = tile[(tap * PW_T + nl) * (PW_T + 1) + kl];
-            g[o] = accumulate ? g[o] + v : v;
+    // write phase: position p = (inner, tap) inside a run of `per` consecutive outputs; p advances by 256 per step, (inner, tap) follow
+    // incrementally
+    const int step_inner = 256 / taps, step_tap = 256 % taps;
+    for (int outer = 0; outer < PW_T; ++outer) {
+        int inner = threadIdx.x / taps, tap = threadIdx.x % taps;
+        for (int pp = threadIdx.x; pp < per; pp += 256) {
+            const int nl = k_inner ? outer : inner, kl = k_inner ? inner : outer;
+            const int n = n0 + nl, k = k0 + kl;
+            if (n < N && k < K) {
+                const long o = n * s_n + k * s_k + tap * s_tap;
+                const float v = tile[(tap * PW_T + nl) * (PW_T + 1) + kl];
+                g[o] = accumulate ? g[o] + v : v;
+            }
+            inner += step_inner;
+            tap += step_tap;
+            if (tap >= taps) tap -= taps, ++inner;
         }
     }
 }

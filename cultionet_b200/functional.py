@@ -255,6 +255,21 @@ def _direct_grad_target(param, like_shape):
     return g, 0 if first else 1
 
 
+# Persistent fp32 accumulators [taps][N][Ctot] of the split-K weight-gradient kernels, one per Parameter taking its gradient
+# directly: ``cnb_unpack_wgrad`` (mode bit 1) clears the accumulator while reading it, so a step needs no fill launch per weight.
+_DWP_ACC: dict = {}
+
+
+def _wgrad_accumulator(param, taps, N, Ctot, dev):
+    key = id(param)
+    hit = _DWP_ACC.get(key)
+    if hit is not None and hit[0]() is param and hit[1].shape == (taps, N, Ctot) and hit[1].device == dev:
+        return hit[1]
+    buf = torch.zeros((taps, N, Ctot), dtype=torch.float32, device=dev)
+    _DWP_ACC[key] = (weakref.ref(param, lambda _r, k=key: _DWP_ACC.pop(k, None)), buf)
+    return buf
+
+
 class _Conv2dFn(torch.autograd.Function):
     """y = conv(cat(sources, channel), weight) + bias over pixel-major tensors; see ``cnb_conv2d_fwd``."""
 
@@ -348,7 +363,11 @@ class _Conv2dFn(torch.autograd.Function):
 
         dw = None
         if need_w:
-            dwp = torch.zeros((taps, N, Ctot), dtype=torch.float32, device=dev)
+            target, acc_flag = _direct_grad_target(ctx.params[0], weight.shape)
+            if target is not None:
+                dwp = _wgrad_accumulator(ctx.params[0], taps, N, Ctot, dev)  # zero on entry: cleared by the previous unpack
+            else:
+                dwp = torch.zeros((taps, N, Ctot), dtype=torch.float32, device=dev)
             coff = 0
             for s, c in zip(sources, src_channels):
                 d = WgradDesc()
@@ -365,9 +384,8 @@ class _Conv2dFn(torch.autograd.Function):
                      tag="conv_wgrad", detail=detail)
                 coff += c
             rows, cols, s_n, s_k, s_tap = _weight_strides(kind, N, Ctot, taps, for_dgrad=False)
-            target, acc_flag = _direct_grad_target(ctx.params[0], weight.shape)
             if target is not None:
-                call("cnb_unpack_wgrad", ptr(dwp), ptr(target), taps, rows, cols, s_n, s_k, s_tap, acc_flag, stream_ptr(dy))
+                call("cnb_unpack_wgrad", ptr(dwp), ptr(target), taps, rows, cols, s_n, s_k, s_tap, acc_flag | 2, stream_ptr(dy))
             else:
                 dw = torch.empty_like(weight, dtype=torch.float32, memory_format=torch.contiguous_format)
                 call("cnb_unpack_wgrad", ptr(dwp), ptr(dw), taps, rows, cols, s_n, s_k, s_tap, 0, stream_ptr(dy))

@@ -136,9 +136,10 @@ typedef struct cnb_pack_desc {
     int64_t s_n, s_k, s_tap;
 } cnb_pack_desc;
 int cnb_pack_weights_batched(const cnb_pack_desc* table, int ndesc, int total_tiles, int max_taps, int dtype, void* stream);
-/* inverse scatter of a packed fp32 gradient into the parameter layout: g[...] (+)= dwp[tap][n][k] */
-int cnb_unpack_wgrad(const float* dwp, float* g, int taps, int N, int K,
-                     int64_t s_n, int64_t s_k, int64_t s_tap, int accumulate, void* stream);
+/* inverse scatter of a packed fp32 gradient into the parameter layout: g[...] (+)= dwp[tap][n][k].
+ * mode bit 0: accumulate into g (else overwrite); bit 1: clear dwp while reading it (persistent split-K accumulator). */
+int cnb_unpack_wgrad(float* dwp, float* g, int taps, int N, int K,
+                     int64_t s_n, int64_t s_k, int64_t s_tap, int mode, void* stream);
 /* db[n] (+)= sum_p dy[p][n] (bias gradient) */
 int cnb_bias_grad(const void* dy, int dy_stride, int64_t P, int N, float* db, int accumulate, int dtype, void* stream);
 

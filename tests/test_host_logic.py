@@ -118,7 +118,7 @@ def test_direct_parameter_gradients_match_autograd_accumulation(dev):
     batch = cb.Data(x=torch.rand(2, 2, 6, 16, 16, device=dev), y=torch.randint(-1, 3, (2, 16, 16), device=dev),
                     bdist=torch.rand(2, 16, 16, device=dev))
     grads = []
-    for direct in (False, True):
+    for direct in (False, True, True):  # twice direct: the persistent split-K accumulators must come back cleared
         opt.zero_grad()
         loss = model.training_step(batch, 0)
         with F.direct_param_grads(direct):
@@ -126,3 +126,4 @@ def test_direct_parameter_gradients_match_autograd_accumulation(dev):
         grads.append(opt.flat_grad.clone())
     assert float(grads[0].norm()) > 0
     assert float((grads[0] - grads[1]).norm() / grads[0].norm()) < 1e-5
+    assert float((grads[0] - grads[2]).norm() / grads[0].norm()) < 1e-5
