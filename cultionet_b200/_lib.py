@@ -144,6 +144,8 @@ _PROTOS = {
     "cnb_na2d_dropout_bwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _i, _f, _i, _vp],
     "cnb_dropout": [_vp, _vp, _i64, _vp, _i, _f, _i, _vp],
     "cnb_dropout2d": [_vp, _vp, _i, _i, _i, _vp, _i, _f, _i, _vp],
+    "cnb_window_load": [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp, _vp],
+    "cnb_predict_pack": [_vp, _vp, _vp, _i64, _i, _i, _i, _vp, _i, _i, _f, _vp, _i, _i, _i, _vp],
 }
 
 # entry points that only exist in the nvcc build (tcgen05 / TMA kernels); filled in by later sections
@@ -251,6 +253,9 @@ def _nn(*ptrs) -> int:
 # Algorithmic HBM bytes of the bandwidth-bound entry points, from the C-ABI arguments by position; evaluated only while
 # a KernelTimer is recording (bench.py's roofline pass).
 ALG_BYTES = {
+    # int16 in + fp32 out per element of the window batch; fp32 in + uint16 out per kept pixel of three bands
+    "cnb_window_load": lambda a: 6 * a[7] * a[2] * a[1] * (a[8] + 2 * a[9]) ** 2,
+    "cnb_predict_pack": lambda a: 6 * 3 * a[8] * a[9] * a[9],
     "cnb_bn_stats": lambda a: a[1] * a[2] * _es(a[6]),
     "cnb_bn_train_fwd": lambda a: (2 + _nn(a[13])) * a[15] * a[16] * _es(a[20]),
     "cnb_bn_act_fwd": lambda a: (2 + _nn(a[3])) * a[5] * a[6] * _es(a[10]),

@@ -13,6 +13,7 @@
 #include "k_vec.cuh"
 #include "k_stream.cuh"
 #include "k_pool_attn.cuh"
+#include "k_tile.cuh"
 
 using namespace cnb;
 
@@ -1270,6 +1271,33 @@ int cnb_dropout2d(const void* x, void* out, int B, int HW, int C, const void* rn
                    (const int64_t*)rng_state, site, dropout_threshold(p), 1.0f / (1.0f - p));
     });
     CNB_CHECK_LAUNCH("dropout2d_kernel");
+    return CNB_OK;
+}
+
+int cnb_window_load(const int16_t* tile, int T, int C, int Ht, int Wt, const int32_t* win, int win_stride, int B, int window_size, int pad,
+                    float scale, float lo, float hi, const float* mean, const float* stdv, float* out, void* stream) {
+    CNB_REQUIRE(tile && win && out && win_stride >= 2 && T > 0 && C > 0 && Ht > 0 && Wt > 0 && B > 0 && window_size > 0 && pad >= 0 && scale != 0.f,
+                "window_load: bad arguments");
+    const int Hw = window_size + 2 * pad;
+    CNB_REQUIRE(Hw % 4 == 0, "window_load: window_size + 2 * padding must be a multiple of 4 (16-byte stores)");
+    CNB_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "window_load: out must be 16-byte aligned");
+    const long total = (long)B * C * T * Hw * (Hw / 4);
+    CNB_LAUNCH(window_load_kernel, dim3(stream_grid(total)), dim3(256), 0, (cudaStream_t)stream, tile, T, C, Ht, Wt, win, win_stride, B, Hw, Hw, pad,
+               scale, lo, hi, mean, stdv, out);
+    CNB_CHECK_LAUNCH("window_load_kernel");
+    return CNB_OK;
+}
+
+int cnb_predict_pack(const float* dist, const float* edge, const float* crop, int64_t batch_stride, int Hs, int Ws, int pad,
+                     const int32_t* win, int B, int window_size, float scale, uint16_t* mosaic, int Ht, int Wt, int mosaic_pitch, void* stream) {
+    CNB_REQUIRE(dist && edge && crop && win && mosaic && B > 0 && Hs > 0 && Ws > 0 && pad >= 0 && window_size > 0 && Ht > 0 && Wt > 0 &&
+                    mosaic_pitch >= Wt,
+                "predict_pack: bad arguments");
+    CNB_REQUIRE(batch_stride >= (int64_t)Hs * Ws, "predict_pack: batch stride smaller than one prediction");
+    const long total = (long)B * 3 * window_size * window_size;
+    CNB_LAUNCH(predict_pack_kernel, dim3(stream_grid(total)), dim3(256), 0, (cudaStream_t)stream, dist, edge, crop, (long)batch_stride, Hs, Ws,
+               pad, win, B, window_size, scale, mosaic, Ht, Wt, mosaic_pitch);
+    CNB_CHECK_LAUNCH("predict_pack_kernel");
     return CNB_OK;
 }
 

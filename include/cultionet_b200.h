@@ -341,6 +341,23 @@ int cnb_na2d_dropout_bwd(const void* qkv, const void* dout, float* dqkv_acc, voi
 int cnb_dropout(const void* x, void* out, int64_t n, const void* rng_state, int site, float p, int dtype, void* stream);
 int cnb_dropout2d(const void* x, void* out, int B, int HW, int C, const void* rng_state, int site, float p, int dtype, void* stream);
 
+/* ---- Prediction over a resident tile: the steps either side of predict_step ----
+ * cnb_window_load replaces, for prediction, create_predict_dataset's windowing (data/create.py:201-214: chunks of window_size,
+ * map_overlap(depth = padding, boundary = 0); data/store.py:68-90: ragged end chunks zero-padded) together with EdgeDataset.get's
+ * load arithmetic (data/datasets.py:443: x / 10000 clipped to [1e-9, 1]; utils/normalize.py:78-80: (x - mean_c) / std_c):
+ *   out[b][c][t][y][x] = (clip(raw / scale, lo, hi) - mean[c]) / std[c],  raw = tile[t][c][row_off_b - pad + y][col_off_b - pad + x]
+ * or 0 outside the tile.  tile: device int16 [T][C][Ht][Wt]; win: device int32 [B][win_stride], row b starts with (row_off, col_off); out: device fp32
+ * [B][C][T][window_size + 2 pad][window_size + 2 pad] (the x field of the reference's Data); mean / stdv: device fp32 [C] or NULL. */
+int cnb_window_load(const int16_t* tile, int T, int C, int Ht, int Wt, const int32_t* win, int win_stride, int B, int window_size, int pad,
+                    float scale, float lo, float hi, const float* mean, const float* stdv, float* out, void* stream);
+/* cnb_predict_pack replaces LightningGTiffWriter.write_on_batch_end's per-window work (callbacks.py:176-227): halo slice
+ * (get_batch_slice, :136-146), band stack (distance, edge, crop), (v * scale).clip(0, scale) -> uint16 (truncation), placed at the
+ * window's offset of the 3-band mosaic (device uint16 [3][Ht][mosaic_pitch >= Wt]).  dist / edge / crop: device fp32, element (b, y, x) at
+ * ptr[b * batch_stride + y * Ws + x]; win: device int32 [B][4] = (row_off, col_off, height, width), clipped to the mosaic as
+ * :182-185; height 0 = filler window. */
+int cnb_predict_pack(const float* dist, const float* edge, const float* crop, int64_t batch_stride, int Hs, int Ws, int pad,
+                     const int32_t* win, int B, int window_size, float scale, uint16_t* mosaic, int Ht, int Wt, int mosaic_pitch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -493,3 +493,115 @@ def na_dropout_case(dev, B, H, W, heads, hd, k, d, p=0.3, seed=0):
             F.rng_advance(qkv.device)
             acc += F.na2d(qkv, heads, k, d, hd ** -0.5, attn_drop=p, site=site)
     assert rel_err(acc / n_masks, plain) < 0.2
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# prediction over a resident tile (cultionet_b200/tile.py; oracle/tile_port.py)
+def _random_tile(T, C, H, W, seed):
+    rng = np.random.default_rng(seed)
+    tile = rng.integers(-200, 12000, size=(T, C, H, W), dtype=np.int64).astype(np.int16)  # below 0 and above 10000: both clips fire
+    tile[:, :, : H // 3, : W // 4] = 0  # a no-data corner
+    return tile
+
+
+def window_load_case(dev, T, C, H, W, ws, pad, norm=True, seed=0):
+    """cnb_window_load == reference windowing + load arithmetic, bit for bit."""
+    from cultionet_b200.tile import WindowLoader, predict_windows
+    from oracle import tile_port
+
+    tile = _random_tile(T, C, H, W, seed)
+    g = torch.Generator().manual_seed(seed)
+    mean = torch.rand(C, generator=g) * 0.3 if norm else None
+    std = torch.rand(C, generator=g) * 0.2 + 0.05 if norm else None
+    want = tile_port.create_predict_windows(tile, ws, pad)
+    win = predict_windows(H, W, ws, pad)
+    assert len(win) == len(want)
+    for row, wd in zip(win, want):
+        assert tuple(row) == (wd["window_row_off"], wd["window_col_off"], wd["window_height"], wd["window_width"])
+    loader = WindowLoader(torch.from_numpy(tile).to(dev), ws, pad, (mean.reshape(1, C, 1, 1, 1), std) if norm else None)
+    batch = loader.load(torch.from_numpy(win))
+    assert batch.x.shape == (len(win), C, T, ws + 2 * pad, ws + 2 * pad) and batch.x.dtype == torch.float32
+    ref = torch.cat([tile_port.load_window(wd["x"], mean, std) for wd in want], dim=0)
+    assert torch.equal(batch.x.cpu(), ref), float((batch.x.cpu() - ref).abs().max())
+    assert batch.window_row_off.tolist() == [wd["window_row_off"] for wd in want]
+    return batch
+
+
+def predict_pack_case(dev, H, W, ws, pad, crop_channels=1, seed=0):
+    """cnb_predict_pack == LightningGTiffWriter's slice / scale / clip / uint16 / windowed write, bit for bit."""
+    from cultionet_b200.data import Data
+    from cultionet_b200.tile import MosaicWriter, predict_windows
+
+    from oracle import tile_port
+
+    win = predict_windows(H, W, ws, pad)
+    B, s = len(win), ws + 2 * pad
+    g = torch.Generator().manual_seed(seed)
+    pred = {k: torch.rand(B, 1, s, s, generator=g) * 1.2 - 0.1 for k in ("distance", "edge")}  # outside [0, 1]: the clip fires
+    pred["crop"] = torch.rand(B, crop_channels, s, s, generator=g) * 1.2 - 0.1
+    pred["distance"][0, 0, pad, pad] = 0.99999  # truncation, not rounding
+    windows = [dict(window_row_off=r, window_col_off=c, window_height=h, window_width=w, padding=pad) for r, c, h, w in win.tolist()]
+    want = np.zeros((3, H, W), dtype=np.uint16)
+    tile_port.write_windows(want, pred, windows)
+    writer = MosaicWriter(H, W, dev, ws)
+    dev_pred = {k: v.to(dev) for k, v in pred.items()}
+    half = B // 2  # two batches through the reference-shaped entry point
+    for lo, hi in ((0, half), (half, B)):
+        if hi > lo:
+            batch = Data(x=torch.empty(hi - lo, 1, 1, s, s), padding=[pad] * (hi - lo),
+                         window_row_off=torch.from_numpy(win[lo:hi, 0]), window_col_off=torch.from_numpy(win[lo:hi, 1]),
+                         window_height=torch.from_numpy(win[lo:hi, 2]), window_width=torch.from_numpy(win[lo:hi, 3]))
+            writer.write_on_batch_end({k: v[lo:hi] for k, v in dev_pred.items()}, batch)
+    got = writer.mosaic.cpu().numpy()
+    assert got.shape == want.shape and np.array_equal(got, want), int((got.astype(np.int32) != want.astype(np.int32)).sum())
+    assert int(want[0, 0, 0]) == 9999 or win[0][2] == 0
+
+
+def tile_predictor_case(dev, H=37, W=50, ws=12, pad=4, batch_windows=5, rank=0, world_size=1, cuda_graph=False, seed=0,
+                        dtype=torch.float32, hidden=8, streaming=False):
+    """TilePredictor (load -> predict_step -> pack per window batch, windows rank::world) == the reference pipeline run window by
+    window on the oracle's windows with the same model: identical uint16 mosaic on this rank's windows, zeros elsewhere."""
+    from cultionet_b200.data import Data
+    from cultionet_b200.models.lightning import CultionetLitModel
+    from cultionet_b200.tile import TilePredictor
+
+    from oracle import tile_port
+
+    T, C = 6, 2
+    tile = _random_tile(T, C, H, W, seed)
+    torch.manual_seed(seed)
+    model = CultionetLitModel(in_channels=C, in_time=T, hidden_channels=hidden, dropout=0.0, compute_dtype=dtype).to(dev)
+    model.eval()
+    mean, std = torch.tensor([0.1, 0.2]), torch.tensor([0.07, 0.11])
+    resident = torch.zeros(tile.shape, dtype=torch.int16, device=dev) if streaming else torch.from_numpy(tile).to(dev)
+    tp = TilePredictor(model, resident, (mean, std), ws, pad, batch_windows, cuda_graph=cuda_graph, rank=rank, world_size=world_size)
+    if streaming:  # the tile starts in host memory; rows are copied in ahead of the batches, finished mosaic rows copied back
+        host_tile = torch.from_numpy(tile)
+        host_tile = host_tile.pin_memory() if dev != "cpu" else host_tile
+        host_mosaic = tp.run_streaming(host_tile)
+        if dev != "cpu":
+            torch.cuda.synchronize()
+        assert torch.equal(tp.loader.tile.cpu(), torch.from_numpy(tile))
+        got = host_mosaic[:, :, :W].numpy().copy()
+        assert np.array_equal(got, tp.writer.mosaic.cpu().numpy())
+    else:
+        got = tp.run().cpu().numpy().copy()  # (a CPU mosaic would alias the writer's storage)
+    windows = tile_port.create_predict_windows(tile, ws, pad)[rank::world_size]
+    assert tp.num_windows == len(windows)
+    want = np.zeros((3, H, W), dtype=np.uint16)
+    with torch.no_grad():
+        for lo in range(0, len(windows), batch_windows):
+            chunk = windows[lo:lo + batch_windows]
+            fill = batch_windows - len(chunk)  # the predictor fills a ragged last batch with (0, 0, 0, 0) windows
+            x = torch.cat([tile_port.load_window(wd["x"], mean, std) for wd in chunk], dim=0).to(dev)
+            if fill:
+                origin = tile_port.create_predict_windows(tile, ws, pad)[0]["x"]
+                x = torch.cat([x, tile_port.load_window(origin, mean, std).to(dev).expand(fill, -1, -1, -1, -1)], dim=0)
+            out = model.predict_step(Data(x=x.contiguous()), 0)
+            tile_port.write_windows(want, {k: v[: len(chunk)].float().cpu() for k, v in out.items() if v is not None}, chunk)
+    diff = np.abs(got.astype(np.int32) - want.astype(np.int32))
+    # eval-mode results are per-sample; the same kernels ran on the same values, so the mosaics agree exactly in fp32
+    tol = 0 if dtype == torch.float32 else 200
+    assert diff.max() <= tol, (int(diff.max()), int((diff > 0).sum()))
+    assert got.any()
+    return got

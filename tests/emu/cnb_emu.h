@@ -314,6 +314,9 @@ inline T __ldg(const T* p) {
     return *p;
 }
 inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+inline float __fdiv_rn(float a, float b) { return a / b; }
+inline float __fmul_rn(float a, float b) { return a * b; }
+inline float __fsub_rn(float a, float b) { return a - b; }
 inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 
 inline void cnb_count_launch();

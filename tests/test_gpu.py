@@ -399,3 +399,25 @@ def test_merged_multi_source_data_gradient(dev):
         Fn.MERGE_SOURCE_DGRADS = True
     for u, v in zip(a, b):
         assert torch.equal(u, v)
+
+
+@pytest.mark.parametrize("geom", [(12, 5, 340, 450, 100, 20, True), (3, 2, 37, 50, 12, 4, False), (2, 1, 100, 100, 100, 20, True)])
+def test_window_load_matches_reference_windowing(dev, geom):
+    """cfg5 geometry (100 px windows, 20 px halo, ragged right / bottom windows): bit-identical to create_predict_dataset's windowing +
+    EdgeDataset.get's scaling / clipping + NormValues z-score (oracle/tile_port.py)."""
+    cases.window_load_case(dev, *geom)
+
+
+@pytest.mark.parametrize("geom", [(340, 451, 100, 20, 1), (37, 50, 12, 4, 2)])
+def test_predict_pack_matches_reference_writer(dev, geom):
+    cases.predict_pack_case(dev, *geom)
+
+
+@pytest.mark.parametrize("mode", ["eager", "graph", "streaming"])
+def test_tile_predictor_fp32(dev, mode):
+    cases.tile_predictor_case(dev, H=70, W=90, ws=24, pad=4, batch_windows=5, cuda_graph=mode != "eager", streaming=mode == "streaming")
+
+
+def test_tile_predictor_bf16_graph_streaming(dev):
+    """bf16 storage: the mosaic (values 0..10000) stays within 2e-2 of the window-by-window pipeline on the same bf16 model."""
+    cases.tile_predictor_case(dev, H=128, W=160, ws=32, pad=8, batch_windows=8, cuda_graph=True, streaming=True, dtype=BF16, hidden=16)

@@ -216,3 +216,18 @@ def test_dropout(dev, dtype):
 
 def test_attention_dropout(dev):
     cases.na_dropout_case(dev, 1, 9, 8, 2, 8, 3, 1)
+
+
+@pytest.mark.parametrize("geom", [(3, 2, 37, 50, 12, 4, True), (2, 3, 24, 24, 12, 2, False), (1, 1, 5, 9, 8, 2, True)])
+def test_window_load_matches_reference_windowing(dev, geom):
+    cases.window_load_case(dev, *geom)
+
+
+@pytest.mark.parametrize("geom", [(37, 50, 12, 4, 1), (24, 24, 12, 2, 2), (5, 9, 8, 2, 1)])
+def test_predict_pack_matches_reference_writer(dev, geom):
+    cases.predict_pack_case(dev, *geom)
+
+
+@pytest.mark.parametrize("streaming", [False, True])
+def test_tile_predictor_matches_window_by_window_reference_pipeline(dev, streaming):
+    cases.tile_predictor_case(dev, streaming=streaming)

@@ -105,3 +105,46 @@ def test_bucket_layout_covers_the_flat_gradient(dev):
     assert spans[0][0] == 0 and spans[-1][1] == step.optimizer.numel
     assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
     assert sum(n for _, _, n in step.sync.buckets) == len(step.optimizer.params)
+
+
+def _tile_worker(rank: int, world: int, port: int, out_dir: str):
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.set_num_threads(1)
+    _bind_emulator()
+    from cultionet_b200.parallel import init_distributed
+    from tests import cases
+
+    init_distributed(backend="gloo")
+    import cultionet_b200.tile as tile_mod
+
+    kept = {}
+    orig_run = tile_mod.TilePredictor.run
+
+    def run(self, batches=None):  # keep the predictor of the case to call its writer's gather afterwards
+        kept["tp"] = self
+        return orig_run(self, batches)
+
+    tile_mod.TilePredictor.run = run
+    mine = cases.tile_predictor_case("cpu", rank=rank, world_size=world)  # checks this rank's windows against the reference pipeline
+    full = kept["tp"].writer.gather(dst=0)
+    assert (full is None) == (rank != 0)
+    torch.save({"mine": torch.from_numpy(mine.astype("int32")), "full": None if full is None else full.to(torch.int32).clone()},
+               os.path.join(out_dir, f"tile{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_two_rank_tile_prediction_shards_windows_and_gathers_mosaic(tmp_path, dev):
+    """Windows i mod 2 go to rank i (no data-path collective); the writer rank's gathered mosaic equals the single-process one."""
+    from tests import cases
+
+    world = 2
+    mp.spawn(_tile_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    r0, r1 = (torch.load(tmp_path / f"tile{r}.pt") for r in range(world))
+    single = torch.from_numpy(cases.tile_predictor_case(dev).astype("int32"))
+    assert r1["full"] is None
+    assert not torch.equal(r0["mine"], r1["mine"])
+    assert int(((r0["mine"] != 0) & (r1["mine"] != 0)).sum()) == 0  # disjoint windows
+    assert torch.equal(r0["full"], single)
