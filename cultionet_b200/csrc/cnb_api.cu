@@ -1281,8 +1281,8 @@ int cnb_window_load(const int16_t* tile, int T, int C, int Ht, int Wt, const int
     const int Hw = window_size + 2 * pad;
     CNB_REQUIRE(Hw % 4 == 0, "window_load: window_size + 2 * padding must be a multiple of 4 (16-byte stores)");
     CNB_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "window_load: out must be 16-byte aligned");
-    const long total = (long)B * C * T * Hw * (Hw / 4);
-    CNB_LAUNCH(window_load_kernel, dim3(stream_grid(total)), dim3(256), 0, (cudaStream_t)stream, tile, T, C, Ht, Wt, win, win_stride, B, Hw, Hw, pad,
+    CNB_REQUIRE((long)B * C * T < (1L << 31), "window_load: too many planes for one launch");
+    CNB_LAUNCH(window_load_kernel, dim3((unsigned)((long)B * C * T)), dim3(256), 0, (cudaStream_t)stream, tile, T, C, Ht, Wt, win, win_stride, B, Hw, Hw, pad,
                scale, lo, hi, mean, stdv, out);
     CNB_CHECK_LAUNCH("window_load_kernel");
     return CNB_OK;
@@ -1294,8 +1294,7 @@ int cnb_predict_pack(const float* dist, const float* edge, const float* crop, in
                     mosaic_pitch >= Wt,
                 "predict_pack: bad arguments");
     CNB_REQUIRE(batch_stride >= (int64_t)Hs * Ws, "predict_pack: batch stride smaller than one prediction");
-    const long total = (long)B * 3 * window_size * window_size;
-    CNB_LAUNCH(predict_pack_kernel, dim3(stream_grid(total)), dim3(256), 0, (cudaStream_t)stream, dist, edge, crop, (long)batch_stride, Hs, Ws,
+    CNB_LAUNCH(predict_pack_kernel, dim3((unsigned)((long)B * 3 * window_size)), dim3(128), 0, (cudaStream_t)stream, dist, edge, crop, (long)batch_stride, Hs, Ws,
                pad, win, B, window_size, scale, mosaic, Ht, Wt, mosaic_pitch);
     CNB_CHECK_LAUNCH("predict_pack_kernel");
     return CNB_OK;

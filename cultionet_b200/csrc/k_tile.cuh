@@ -14,44 +14,68 @@
 
 namespace cnb {
 
+// Correctly rounded a / b from y = RN(1 / b) in five instructions instead of the ~12 + range check of div.rn.f32: q0 = RN(a y) is
+// within 1.5 ulp of a / b, one residual step makes it faithful, and by Markstein's theorem a second residual step from a faithful
+// quotient with a correctly rounded reciprocal gives RN(a / b) -- for divisors whose significand is not all ones and operands far
+// from the overflow / underflow thresholds, which `markstein_ok` checks once per CTA (otherwise __fdiv_rn).
+__device__ __forceinline__ bool markstein_ok(float b) {
+    const float ab = fabsf(b);
+    return ab > 1e-18f && ab < 1e18f && (__float_as_uint(b) & 0x7fffffu) != 0x7fffffu;
+}
+__device__ __forceinline__ float div_rn_markstein(float a, float b, float y) {
+    float q = __fmul_rn(a, y);
+    float r = __fmaf_rn(-q, b, a);
+    q = __fmaf_rn(r, y, q);
+    r = __fmaf_rn(-q, b, a);
+    return __fmaf_rn(r, y, q);
+}
+
 // tile  int16 [T][C][Ht][Wt]  (reference order: time, band, y, x -- data/create.py:70-79)
 // win   int32 [B][win_stride]  row b starts with (row_off, col_off), the window's un-padded origin in the tile
 // out   fp32  [B][C][T][Hw][Ww], Hw = Ww = window_size + 2 * pad; (y, x) of the window is tile pixel (row_off - pad + y, col_off - pad + x)
-// One thread = four consecutive x of one row (Ww % 4 == 0): a 16-byte store, four 2-byte loads that share sectors with the neighbours.
+// One CTA = one (b, c, t) plane of a window (grid = B*C*T, a multiple of waves at cfg 5: 1920 planes); one thread = four consecutive
+// x of one row (Ww % 4 == 0): a 16-byte store, four 2-byte loads that share sectors with the neighbours.  The (row, quad) position
+// advances incrementally -- no division inside the loop; band constants and the window origin are per-CTA values.
 __global__ void __launch_bounds__(256) window_load_kernel(const int16_t* __restrict__ tile, int T, int C, int Ht, int Wt,
                                                           const int32_t* __restrict__ win, int win_stride, int B, int Hw, int Ww, int pad,
                                                           float scale, float lo, float hi, const float* __restrict__ mean, const float* __restrict__ stdv,
                                                           float* __restrict__ out) {
     CNB_PDL_SYNC();
     const int quads = Ww >> 2;
-    const long total = (long)B * C * T * Hw * quads;
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        const int xq = (int)(i % quads);
-        long r = i / quads;
-        const int y = (int)(r % Hw);
-        r /= Hw;
-        const int t = (int)(r % T);
-        r /= T;
-        const int c = (int)(r % C);
-        const int b = (int)(r / C);
-        const int row = win[win_stride * b] - pad + y;
-        const int col0 = win[win_stride * b + 1] - pad + 4 * xq;
-        const float m = mean ? mean[c] : 0.f;
-        const float s = stdv ? stdv[c] : 1.f;
+    const int plane = blockIdx.x;  // ((b * C) + c) * T + t
+    const int t = plane % T;
+    const int c = (plane / T) % C;
+    const int b = plane / (T * C);
+    const int row0 = win[win_stride * b] - pad, col00 = win[win_stride * b + 1] - pad;
+    const float m = mean ? mean[c] : 0.f;
+    const float s = stdv ? stdv[c] : 1.f;
+    const int16_t* src_plane = tile + ((long)t * C + c) * Ht * Wt;
+    float* dst_plane = out + (long)plane * Hw * Ww;
+    const int step_y = (int)blockDim.x / quads, step_x = (int)blockDim.x % quads;
+    int y = (int)threadIdx.x / quads, xq = (int)threadIdx.x % quads;
+    const bool interior_cols = col00 >= 0 && col00 + Ww <= Wt;
+    // |raw| <= 32768 and the clipped reflectances are far inside the normal range: only the divisors decide
+    const bool fast_div = markstein_ok(scale) && markstein_ok(s) && fabsf(m) < 1e18f && fabsf(lo) < 1e18f && fabsf(hi) < 1e18f;
+    const float y_scale = __frcp_rn(scale), y_s = __frcp_rn(s);
+    for (; y < Hw; y += step_y) {
+        const int row = row0 + y;
         const bool row_ok = row >= 0 && row < Ht;
-        const int16_t* src = tile + (((long)t * C + c) * Ht + (row_ok ? row : 0)) * Wt;
+        const int col0 = col00 + 4 * xq;
+        const int16_t* src = src_plane + (long)(row_ok ? row : 0) * Wt + col0;
         float v[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int col = col0 + j;
-            const float raw = (row_ok && col >= 0 && col < Wt) ? (float)src[col] : 0.f;
-            float q = __fdiv_rn(raw, scale);
+            const bool ok = row_ok && (interior_cols || (col0 + j >= 0 && col0 + j < Wt));
+            const float raw = ok ? (float)src[j] : 0.f;
+            float q = fast_div ? div_rn_markstein(raw, scale, y_scale) : __fdiv_rn(raw, scale);
             q = fminf(fmaxf(q, lo), hi);
             if (mean) q = __fsub_rn(q, m);
-            if (stdv) q = __fdiv_rn(q, s);
+            if (stdv) q = fast_div ? div_rn_markstein(q, s, y_s) : __fdiv_rn(q, s);
             v[j] = q;
         }
-        *reinterpret_cast<float4*>(out + i * 4) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(dst_plane + (long)y * Ww + 4 * xq) = make_float4(v[0], v[1], v[2], v[3]);
+        xq += step_x;
+        if (xq >= quads) xq -= quads, ++y;
     }
 }
 
@@ -60,29 +84,27 @@ __global__ void __launch_bounds__(256) window_load_kernel(const int16_t* __restr
 // win   int32 [B][4]  (row_off, col_off, height, width); height/width are clipped to the mosaic here as callbacks.py:182-185 does;
 //                     height = 0 marks a filler window of a ragged last batch
 // mosaic uint16 [3][Ht][pitch >= Wt]
-__global__ void __launch_bounds__(256) predict_pack_kernel(const float* __restrict__ dist, const float* __restrict__ edge,
+// One CTA = one output row of one band of one window (grid = B * 3 * win_size).
+__global__ void __launch_bounds__(128) predict_pack_kernel(const float* __restrict__ dist, const float* __restrict__ edge,
                                                            const float* __restrict__ crop, long batch_stride, int Hs, int Ws, int pad,
                                                            const int32_t* __restrict__ win, int B, int win_size, float scale,
                                                            uint16_t* __restrict__ mosaic, int Ht, int Wt, int pitch) {
     CNB_PDL_SYNC();
-    const long per_b = 3L * win_size * win_size;
-    const long total = (long)B * per_b;
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        const int x = (int)(i % win_size);
-        long r = i / win_size;
-        const int y = (int)(r % win_size);
-        r /= win_size;
-        const int band = (int)(r % 3);
-        const int b = (int)(r / 3);
-        const int row_off = win[4 * b], col_off = win[4 * b + 1];
-        int h = win[4 * b + 2], w = win[4 * b + 3];
-        if (row_off + h > Ht) h = Ht - row_off;
-        if (col_off + w > Wt) w = Wt - col_off;
-        if (y >= h || x >= w || pad + y >= Hs || pad + x >= Ws) continue;
-        const float* src = band == 0 ? dist : (band == 1 ? edge : crop);
-        float v = __fmul_rn(src[b * batch_stride + (long)(pad + y) * Ws + (pad + x)], scale);
+    const int y = blockIdx.x % win_size;
+    const int pl = blockIdx.x / win_size;
+    const int band = pl % 3, b = pl / 3;
+    const int row_off = win[4 * b], col_off = win[4 * b + 1];
+    int h = win[4 * b + 2], w = win[4 * b + 3];
+    if (row_off + h > Ht) h = Ht - row_off;
+    if (col_off + w > Wt) w = Wt - col_off;
+    if (y >= h || pad + y >= Hs) return;
+    if (w > Ws - pad) w = Ws - pad;
+    const float* src = (band == 0 ? dist : (band == 1 ? edge : crop)) + b * batch_stride + (long)(pad + y) * Ws + pad;
+    uint16_t* dst = mosaic + ((long)band * Ht + row_off + y) * pitch + col_off;
+    for (int x = threadIdx.x; x < w; x += blockDim.x) {
+        float v = __fmul_rn(src[x], scale);
         v = fminf(fmaxf(v, 0.f), scale);  // NaN -> 0 (fmaxf returns the non-NaN operand)
-        mosaic[((long)band * Ht + row_off + y) * pitch + col_off + x] = (uint16_t)(int)v;  // C truncation = numpy's astype
+        dst[x] = (uint16_t)(int)v;        // C truncation = numpy's astype
     }
 }
 

@@ -135,6 +135,8 @@ class CultionetLitModel(LightningModuleMixin):
         compute_dtype: torch.dtype = torch.bfloat16,
     ):
         super().__init__()
+        # what Lightning's save_hyperparameters() records (lightning.py:850) and writes into checkpoints as 'hyper_parameters'
+        self.hyper_parameters = {k: v for k, v in locals().items() if k not in ("self", "__class__")}
         if loss_name != LossTypes.TANIMOTO_COMPLEMENT:
             raise NotImplementedError("cultionet_b200 builds the reference's default loss only (TanimotoComplementLoss)")
         if HAVE_LIGHTNING:  # pragma: no cover
@@ -157,3 +159,18 @@ class CultionetLitModel(LightningModuleMixin):
     @property
     def is_transfer_model(self) -> bool:
         return False
+
+    @classmethod
+    def load_from_checkpoint(cls, checkpoint_path, map_location="cpu", strict: bool = True, **kwargs) -> "CultionetLitModel":
+        """Lightning's classmethod as the reference calls it (``model.py:398-400``, ``:458-460``)."""
+        from ..model import load_from_checkpoint
+
+        return load_from_checkpoint(checkpoint_path, map_location=map_location, strict=strict, **kwargs)
+
+    if not HAVE_LIGHTNING:
+
+        def freeze(self) -> None:
+            """``LightningModule.freeze`` (``model.py:402``): no gradients, eval mode."""
+            for p in self.parameters():
+                p.requires_grad_(False)
+            self.eval()

@@ -527,6 +527,27 @@ def window_load_case(dev, T, C, H, W, ws, pad, norm=True, seed=0):
     return batch
 
 
+def window_load_all_values_case(dev, seed=0):
+    """Every int16 value through cnb_window_load with three (mean, std) pairs: the correctly rounded two-step division of the kernel
+    is bit-identical to torch's fp32 division for all 65536 raw values (incl. negative no-data and > 10000 saturated values)."""
+    from cultionet_b200.tile import WindowLoader
+    from oracle import tile_port
+
+    C = 3
+    plane = np.arange(-32768, 32768, dtype=np.int64).astype(np.int16).reshape(256, 256)
+    tile = np.broadcast_to(plane, (1, C, 256, 256)).copy()
+    g = torch.Generator().manual_seed(seed)
+    for trial in range(4):
+        mean = torch.rand(C, generator=g) * 0.6
+        std = torch.rand(C, generator=g) * 0.5 + 1e-3
+        if trial == 3:
+            std[0] = float(np.float32(np.nextafter(np.float32(0.25), np.float32(0))))  # all-ones significand: the guarded divisor
+        loader = WindowLoader(torch.from_numpy(tile).to(dev), 248, 4, (mean, std))
+        x = loader.load(torch.tensor([[4, 4, 248, 248]], dtype=torch.int32)).x.cpu()  # origin (4,4), halo 4: covers the tile exactly
+        want = tile_port.load_window(torch.from_numpy(tile.astype("int32")).permute(1, 0, 2, 3)[None], mean, std)
+        assert torch.equal(x, want), (trial, int((x != want).sum()))
+
+
 def predict_pack_case(dev, H, W, ws, pad, crop_channels=1, seed=0):
     """cnb_predict_pack == LightningGTiffWriter's slice / scale / clip / uint16 / windowed write, bit for bit."""
     from cultionet_b200.data import Data

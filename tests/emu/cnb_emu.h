@@ -317,6 +317,13 @@ inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 inline float __fdiv_rn(float a, float b) { return a / b; }
 inline float __fmul_rn(float a, float b) { return a * b; }
 inline float __fsub_rn(float a, float b) { return a - b; }
+inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
+inline float __frcp_rn(float a) { return 1.0f / a; }
+inline unsigned __float_as_uint(float a) {
+    unsigned u;
+    memcpy(&u, &a, 4);
+    return u;
+}
 inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 
 inline void cnb_count_launch();

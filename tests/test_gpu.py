@@ -421,3 +421,7 @@ def test_tile_predictor_fp32(dev, mode):
 def test_tile_predictor_bf16_graph_streaming(dev):
     """bf16 storage: the mosaic (values 0..10000) stays within 2e-2 of the window-by-window pipeline on the same bf16 model."""
     cases.tile_predictor_case(dev, H=128, W=160, ws=32, pad=8, batch_windows=8, cuda_graph=True, streaming=True, dtype=BF16, hidden=16)
+
+
+def test_window_load_division_is_correctly_rounded_for_every_int16_value(dev):
+    cases.window_load_all_values_case(dev)

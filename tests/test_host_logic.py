@@ -127,3 +127,68 @@ def test_direct_parameter_gradients_match_autograd_accumulation(dev):
     assert float(grads[0].norm()) > 0
     assert float((grads[0] - grads[1]).norm() / grads[0].norm()) < 1e-5
     assert float((grads[0] - grads[2]).norm() / grads[0].norm()) < 1e-5
+
+
+def test_fit_checkpoint_roundtrip_and_resume(dev, tmp_path):
+    """model.fit writes a Lightning-layout checkpoint (best val_score), load_from_checkpoint rebuilds an identical module from its
+    hyper_parameters + state_dict, and a second fit() call resumes from the file (model.py:308-314, callbacks.py:238-249)."""
+    from cultionet_b200 import model as M
+    from cultionet_b200.models.lightning import CultionetLitModel
+
+    torch.manual_seed(5)
+    lit = CultionetLitModel(in_channels=2, in_time=6, hidden_channels=8, dropout=0.0, compute_dtype=torch.float32).to(dev)
+    g = torch.Generator().manual_seed(1)
+    batches = [cb.Data(x=torch.rand(2, 2, 6, 16, 16, generator=g), y=torch.randint(-1, 3, (2, 16, 16), generator=g),
+                       bdist=torch.rand(2, 16, 16, generator=g)) for _ in range(2)]
+    ckpt = tmp_path / "ckpt" / "last.ckpt"
+    hist = M.fit(lit, batches, val_batches=batches[:1], epochs=2, ckpt_file=ckpt, device=dev, cuda_graph=False)
+    assert len(hist["loss"]) == 2 and ckpt.is_file() and hist["checkpoint"] == str(ckpt)
+    raw = torch.load(ckpt, weights_only=False)
+    assert {"state_dict", "hyper_parameters", "epoch", "global_step", "optimizer_states", "pytorch-lightning_version"} <= set(raw)
+    assert all(k.startswith("cultionet_TowerUNet.") for k in raw["state_dict"])  # the reference's attribute prefix (lightning.py:874)
+    assert raw["hyper_parameters"]["in_time"] == 6 and raw["hyper_parameters"]["hidden_channels"] == 8
+
+    again = CultionetLitModel.load_from_checkpoint(ckpt, map_location=dev)
+    again.freeze()
+    want = raw["state_dict"]
+    for k, v in again.state_dict().items():
+        assert torch.equal(v.cpu(), want[k]), k
+    assert not any(p.requires_grad for p in again.parameters()) and not again.training
+
+    # resume: the saved epoch was the best of {0, 1}; a 3-epoch fit continues after it with the saved AdamW moments
+    saved_epoch, saved_step = raw["epoch"], raw["optimizer_states"][0]["step"]
+    lit2 = CultionetLitModel(**{k: v for k, v in raw["hyper_parameters"].items()}).to(dev)
+    hist2 = M.fit(lit2, batches, val_batches=batches[:1], epochs=3, ckpt_file=ckpt, device=dev, cuda_graph=False)
+    assert len(hist2["loss"]) == 3 - (saved_epoch + 1)
+    assert saved_step == 2 * (saved_epoch + 1)
+
+
+def test_reference_layout_checkpoint_loads_and_reproduces_golden_outputs(dev, tmp_path):
+    """A checkpoint laid out as the reference's Lightning run writes it -- ``state_dict`` keys ``cultionet_TowerUNet.mask_model.<TowerUNet key>``
+    (lightning.py:874, cultionet.py:70-78) with the ``pre_unet._orig_mod.`` infix of torch.compile (nunet.py:141) and the reference's
+    hyper-parameter names -- loads through ``CultionetLitModel.load_from_checkpoint`` and reproduces the golden outputs the real
+    reference produced from the same weights."""
+    from cultionet_b200.models.lightning import CultionetLitModel
+    from oracle.make_golden import golden_case
+    from tests.util import TOL_OUT_FP32, golden_spec, load_golden, rel_err
+
+    cfg, z = load_golden("small_masked")
+    _, sd, x, _, _ = golden_case(cfg, golden_spec(z))
+    ref_sd = {}
+    for k, v in sd.items():
+        k = k.replace("pre_unet.", "pre_unet._orig_mod.", 1) if k.startswith("pre_unet.") and "_orig_mod" not in k else k
+        ref_sd["cultionet_TowerUNet.mask_model." + k] = v
+    hp = dict(in_channels=cfg["C"], in_time=cfg["T"], hidden_channels=cfg["hidden"], model_type="TowerUNet", dropout=0.0,
+              activation_type="SiLU", dilations=cfg["dilations"], res_block_type="resa", attention_weights="natten", optimizer="AdamW",
+              loss_name="TanimotoComplementLoss", learning_rate=0.01, lr_scheduler="OneCycleLR", steplr_step_size=5, weight_decay=1e-3,
+              eps=1e-4, ckpt_name="last", model_name="cultionet", pool_by_max=False, batchnorm_first=False, class_counts=None,
+              edge_class=2, scale_pos_weight=False, save_batch_val_metrics=False)
+    path = tmp_path / "last.ckpt"
+    torch.save({"epoch": 3, "global_step": 40, "pytorch-lightning_version": "2.1.0", "state_dict": ref_sd, "hyper_parameters": hp,
+                "optimizer_states": [], "lr_schedulers": []}, path)
+    lit = CultionetLitModel.load_from_checkpoint(path, map_location=dev, compute_dtype=torch.float32)
+    assert lit.loaded_checkpoint["epoch"] == 3
+    lit.train()  # the golden vectors are train-mode (batch statistics) outputs
+    out = lit.cultionet_model.mask_model(x.to(dev))
+    for k in ("distance", "edge", "crop"):
+        assert rel_err(out[k][:, :, ::3, ::3], torch.from_numpy(z["out_" + k])) < TOL_OUT_FP32, k

@@ -231,3 +231,7 @@ def test_predict_pack_matches_reference_writer(dev, geom):
 @pytest.mark.parametrize("streaming", [False, True])
 def test_tile_predictor_matches_window_by_window_reference_pipeline(dev, streaming):
     cases.tile_predictor_case(dev, streaming=streaming)
+
+
+def test_window_load_division_is_correctly_rounded_for_every_int16_value(dev):
+    cases.window_load_all_values_case(dev)
