@@ -101,6 +101,7 @@ _PROTOS = {
     "cnb_pack_weight2": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i64, _i64, _i64, _vp],
     "cnb_pack_weights_batched": [_vp, _i, _i, _i, _i, _vp],
     "cnb_unpack_wgrad": [_vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i, _vp],
+    "cnb_unpack_wgrads_batched": [_vp, _i, _i, _i, _vp],
     "cnb_bias_grad": [_vp, _i, _i64, _i, _vp, _i, _i, _vp],
     "cnb_bn_stats": [_vp, _i64, _i, _i, _i, _vp, _i, _vp],
     "cnb_bn_finalize": [_vp, _i64, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp],

@@ -321,6 +321,15 @@ int cnb_unpack_wgrad(float* dwp, float* g, int taps, int N, int K, int64_t s_n, 
     return CNB_OK;
 }
 
+int cnb_unpack_wgrads_batched(const cnb_pack_desc* table, int ndesc, int total_tiles, int max_taps, void* stream) {
+    CNB_REQUIRE(table && ndesc > 0 && total_tiles > 0 && max_taps > 0 && max_taps <= 32, "unpack_wgrads_batched: bad arguments");
+    const size_t smem = (size_t)max_taps * PW_T * (PW_T + 1) * sizeof(float);
+    CNB_SET_SMEM(unpack_wgrad_batched_kernel, smem);
+    CNB_LAUNCH(unpack_wgrad_batched_kernel, dim3(total_tiles), dim3(256), smem, (cudaStream_t)stream, table, ndesc);
+    CNB_CHECK_LAUNCH("unpack_wgrad_batched_kernel");
+    return CNB_OK;
+}
+
 int cnb_bias_grad(const void* dy, int dy_stride, int64_t P, int N, float* db, int accumulate, int dtype, void* stream) {
     CNB_REQUIRE(dy && db && P > 0 && N > 0 && dy_stride >= N, "bias_grad: bad arguments");
     if (!accumulate) CNB_MEMSET_ASYNC(db, 0, sizeof(float) * N, (cudaStream_t)stream);
@@ -1282,8 +1291,10 @@ int cnb_window_load(const int16_t* tile, int T, int C, int Ht, int Wt, const int
     CNB_REQUIRE(Hw % 4 == 0, "window_load: window_size + 2 * padding must be a multiple of 4 (16-byte stores)");
     CNB_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "window_load: out must be 16-byte aligned");
     CNB_REQUIRE((long)B * C * T < (1L << 31), "window_load: too many planes for one launch");
-    CNB_LAUNCH(window_load_kernel, dim3((unsigned)((long)B * C * T)), dim3(256), 0, (cudaStream_t)stream, tile, T, C, Ht, Wt, win, win_stride, B, Hw, Hw, pad,
-               scale, lo, hi, mean, stdv, out);
+    // a quad of four int16 is one aligned 8-byte load when rows and the base pointer are; the kernel adds the per-window column test
+    const int vec_ok = Wt % 4 == 0 && (reinterpret_cast<uintptr_t>(tile) & 7) == 0;
+    CNB_LAUNCH(window_load_kernel, dim3((unsigned)((long)B * C * T)), dim3(256), 0, (cudaStream_t)stream, tile, T, C, Ht, Wt, win, win_stride, B,
+               Hw, Hw, pad, scale, lo, hi, mean, stdv, out, vec_ok);
     CNB_CHECK_LAUNCH("window_load_kernel");
     return CNB_OK;
 }

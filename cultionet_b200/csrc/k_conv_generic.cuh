@@ -300,28 +300,34 @@ __global__ void __launch_bounds__(256) pack_weight_batched_kernel(const cnb_pack
 
 // g[n*s_n + k*s_k + tap*s_tap] (+)= dwp[tap][n][k], written in the parameter's memory order.  mode bit 0: accumulate into g; bit 1:
 // clear dwp after reading it (a persistent per-parameter accumulator is then zero again for the next step: no fill kernel).
-__global__ void __launch_bounds__(256) unpack_wgrad_tiled_kernel(float* __restrict__ dwp, float* __restrict__ g, int taps, int N, int K,
-                                                                long s_n, long s_k, long s_tap, int mode) {
-    CNB_PDL_SYNC();
-    CNB_DYN_SMEM(sm_raw);
-    float* tile = reinterpret_cast<float*>(sm_raw);
-    const int n0 = blockIdx.y * PW_T, k0 = blockIdx.x * PW_T;
+__device__ __forceinline__ void unpack_wgrad_tile(float* tile, float* __restrict__ dwp, float* __restrict__ g, int taps, int N, int K, long s_n,
+                                                  long s_k, long s_tap, int mode, int n0, int k0) {
     const bool accumulate = mode & 1, clear = mode & 2;
-    // read phase: thread (nl = t / 32, kl = t % 32) walks the taps and every fourth... row: no divisions inside the loop
+    // read phase: thread (kl = t % 32, nl0 = t / 32) owns column k of rows nl0, nl0 + 8, .. of every tap: no divisions; the four row
+    // loads of a tap are issued together, and the accumulator is cleared only after them (a store between the loads would serialise
+    // them on the load latency: the compiler cannot prove that the stores do not alias the next loads)
     {
         const int kl = threadIdx.x % PW_T, nl0 = threadIdx.x / PW_T;  // PW_T = 32, 256 threads: 8 rows per pass
         const int k = k0 + kl;
-        for (int tap = 0; tap < taps; ++tap)
-            for (int nl = nl0; nl < PW_T; nl += 256 / PW_T) {
-                const int n = n0 + nl;
-                float v = 0.f;
-                if (n < N && k < K) {
-                    float* src = dwp + ((long)tap * N + n) * K + k;
-                    v = *src;
-                    if (clear) *src = 0.f;
-                }
-                tile[(tap * PW_T + nl) * (PW_T + 1) + kl] = v;
+        constexpr int ROWS = PW_T / (256 / PW_T);  // 4
+#pragma unroll 2
+        for (int tap = 0; tap < taps; ++tap) {
+            float v[ROWS];
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) {
+                const int n = n0 + nl0 + r * (256 / PW_T);
+                v[r] = (n < N && k < K) ? dwp[((long)tap * N + n) * K + k] : 0.f;
             }
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) tile[(tap * PW_T + nl0 + r * (256 / PW_T)) * (PW_T + 1) + kl] = v[r];
+        }
+        if (clear)
+            for (int tap = 0; tap < taps; ++tap)
+#pragma unroll
+                for (int r = 0; r < ROWS; ++r) {
+                    const int n = n0 + nl0 + r * (256 / PW_T);
+                    if (n < N && k < K) dwp[((long)tap * N + n) * K + k] = 0.f;
+                }
     }
     __syncthreads();
     const int per = PW_T * taps;
@@ -344,6 +350,33 @@ __global__ void __launch_bounds__(256) unpack_wgrad_tiled_kernel(float* __restri
             if (tap >= taps) tap -= taps, ++inner;
         }
     }
+}
+
+__global__ void __launch_bounds__(256) unpack_wgrad_tiled_kernel(float* __restrict__ dwp, float* __restrict__ g, int taps, int N, int K,
+                                                                long s_n, long s_k, long s_tap, int mode) {
+    CNB_PDL_SYNC();
+    CNB_DYN_SMEM(sm_raw);
+    unpack_wgrad_tile(reinterpret_cast<float*>(sm_raw), dwp, g, taps, N, K, s_n, s_k, s_tap, mode, blockIdx.y * PW_T, blockIdx.x * PW_T);
+}
+
+// Every weight gradient of a backward pass in ONE launch (the inverse of pack_weight_batched_kernel, same descriptor table layout:
+// w = gradient destination, wp = fp32 accumulator [taps][N][K], reserved = mode).  103 separate launches of 4-320 CTAs cost 1.1 ms per
+// step; the work is 0.5 GB of traffic.
+__global__ void __launch_bounds__(256) unpack_wgrad_batched_kernel(const cnb_pack_desc* __restrict__ table, int ndesc) {
+    CNB_PDL_SYNC();
+    CNB_DYN_SMEM(sm_raw);
+    int lo = 0, hi = ndesc - 1;  // last descriptor whose tile0 <= blockIdx.x
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (table[mid].tile0 <= (int)blockIdx.x)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    const cnb_pack_desc d = table[lo];
+    const int t = (int)blockIdx.x - d.tile0;
+    unpack_wgrad_tile(reinterpret_cast<float*>(sm_raw), reinterpret_cast<float*>(d.wp), const_cast<float*>(d.w), d.taps, d.N, d.K, (long)d.s_n,
+                      (long)d.s_k, (long)d.s_tap, d.reserved, (t / d.tiles_x) * PW_T, (t % d.tiles_x) * PW_T);
 }
 
 // db[n] += sum_p dy[p][n]; grid = (ceil(N/32), pixel splits); 8 pixel lanes per channel column, one atomic per CTA column

@@ -36,12 +36,68 @@ __device__ __forceinline__ float div_rn_markstein(float a, float b, float y) {
 // One CTA = one (b, c, t) plane of a window (grid = B*C*T, a multiple of waves at cfg 5: 1920 planes); one thread = four consecutive
 // x of one row (Ww % 4 == 0): a 16-byte store, four 2-byte loads that share sectors with the neighbours.  The (row, quad) position
 // advances incrementally -- no division inside the loop; band constants and the window origin are per-CTA values.
+// VEC: the four int16 of a quad are one aligned 8-byte load (tile width, window column origin and base pointer multiples of 4
+// elements -- true for 100 px windows with a 20 px halo on a 10980 px tile); otherwise four 2-byte loads.  Each thread first issues
+// the loads of WL_UNROLL quads, then does the arithmetic: a 2-byte-per-element stream needs that many bytes in flight per thread
+// to cover the HBM latency (the first version, one quad at a time, stopped at 3.2 TB/s).
+#define WL_UNROLL 4
+template <bool VEC>
+__device__ __forceinline__ void window_plane(const int16_t* __restrict__ src_plane, float* __restrict__ dst_plane, int Ht, int Wt, int Hw,
+                                             int Ww, int row0, int col00, float scale, float lo, float hi, bool mean, float m, bool stdv,
+                                             float s) {
+    const int quads = Ww >> 2;
+    const int step_y = (int)blockDim.x / quads, step_x = (int)blockDim.x % quads;
+    int y = (int)threadIdx.x / quads, xq = (int)threadIdx.x % quads;
+    // |raw| <= 32768 and the clipped reflectances are far inside the normal range: only the divisors decide
+    const bool fast_div = markstein_ok(scale) && markstein_ok(s) && fabsf(m) < 1e18f && fabsf(lo) < 1e18f && fabsf(hi) < 1e18f;
+    const float y_scale = __frcp_rn(scale), y_s = __frcp_rn(s);
+    while (y < Hw) {
+        int ys[WL_UNROLL], xs[WL_UNROLL];
+        short4 raw[WL_UNROLL];
+#pragma unroll
+        for (int u = 0; u < WL_UNROLL; ++u) {
+            ys[u] = y, xs[u] = xq;
+            y += step_y, xq += step_x;
+            if (xq >= quads) xq -= quads, ++y;
+        }
+#pragma unroll
+        for (int u = 0; u < WL_UNROLL; ++u) {
+            raw[u] = make_short4(0, 0, 0, 0);
+            const int row = row0 + ys[u], col0 = col00 + 4 * xs[u];
+            if (ys[u] < Hw && row >= 0 && row < Ht) {
+                const int16_t* src = src_plane + (long)row * Wt + col0;
+                if (VEC) {
+                    if (col0 >= 0 && col0 < Wt) raw[u] = *reinterpret_cast<const short4*>(src);  // quads are entirely in or out
+                } else {
+                    if (col0 >= 0 && col0 < Wt) raw[u].x = src[0];
+                    if (col0 + 1 >= 0 && col0 + 1 < Wt) raw[u].y = src[1];
+                    if (col0 + 2 >= 0 && col0 + 2 < Wt) raw[u].z = src[2];
+                    if (col0 + 3 >= 0 && col0 + 3 < Wt) raw[u].w = src[3];
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < WL_UNROLL; ++u) {
+            if (ys[u] >= Hw) break;
+            float v[4] = {(float)raw[u].x, (float)raw[u].y, (float)raw[u].z, (float)raw[u].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float q = fast_div ? div_rn_markstein(v[j], scale, y_scale) : __fdiv_rn(v[j], scale);
+                q = fminf(fmaxf(q, lo), hi);
+                if (mean) q = __fsub_rn(q, m);
+                if (stdv) q = fast_div ? div_rn_markstein(q, s, y_s) : __fdiv_rn(q, s);
+                v[j] = q;
+            }
+            *reinterpret_cast<float4*>(dst_plane + (long)ys[u] * Ww + 4 * xs[u]) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) window_load_kernel(const int16_t* __restrict__ tile, int T, int C, int Ht, int Wt,
                                                           const int32_t* __restrict__ win, int win_stride, int B, int Hw, int Ww, int pad,
                                                           float scale, float lo, float hi, const float* __restrict__ mean, const float* __restrict__ stdv,
-                                                          float* __restrict__ out) {
+                                                          float* __restrict__ out, int vec_ok) {
     CNB_PDL_SYNC();
-    const int quads = Ww >> 2;
     const int plane = blockIdx.x;  // ((b * C) + c) * T + t
     const int t = plane % T;
     const int c = (plane / T) % C;
@@ -51,32 +107,10 @@ __global__ void __launch_bounds__(256) window_load_kernel(const int16_t* __restr
     const float s = stdv ? stdv[c] : 1.f;
     const int16_t* src_plane = tile + ((long)t * C + c) * Ht * Wt;
     float* dst_plane = out + (long)plane * Hw * Ww;
-    const int step_y = (int)blockDim.x / quads, step_x = (int)blockDim.x % quads;
-    int y = (int)threadIdx.x / quads, xq = (int)threadIdx.x % quads;
-    const bool interior_cols = col00 >= 0 && col00 + Ww <= Wt;
-    // |raw| <= 32768 and the clipped reflectances are far inside the normal range: only the divisors decide
-    const bool fast_div = markstein_ok(scale) && markstein_ok(s) && fabsf(m) < 1e18f && fabsf(lo) < 1e18f && fabsf(hi) < 1e18f;
-    const float y_scale = __frcp_rn(scale), y_s = __frcp_rn(s);
-    for (; y < Hw; y += step_y) {
-        const int row = row0 + y;
-        const bool row_ok = row >= 0 && row < Ht;
-        const int col0 = col00 + 4 * xq;
-        const int16_t* src = src_plane + (long)(row_ok ? row : 0) * Wt + col0;
-        float v[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const bool ok = row_ok && (interior_cols || (col0 + j >= 0 && col0 + j < Wt));
-            const float raw = ok ? (float)src[j] : 0.f;
-            float q = fast_div ? div_rn_markstein(raw, scale, y_scale) : __fdiv_rn(raw, scale);
-            q = fminf(fmaxf(q, lo), hi);
-            if (mean) q = __fsub_rn(q, m);
-            if (stdv) q = fast_div ? div_rn_markstein(q, s, y_s) : __fdiv_rn(q, s);
-            v[j] = q;
-        }
-        *reinterpret_cast<float4*>(dst_plane + (long)y * Ww + 4 * xq) = make_float4(v[0], v[1], v[2], v[3]);
-        xq += step_x;
-        if (xq >= quads) xq -= quads, ++y;
-    }
+    if (vec_ok && (col00 & 3) == 0)  // uniform over the CTA
+        window_plane<true>(src_plane, dst_plane, Ht, Wt, Hw, Ww, row0, col00, scale, lo, hi, mean != nullptr, m, stdv != nullptr, s);
+    else
+        window_plane<false>(src_plane, dst_plane, Ht, Wt, Hw, Ww, row0, col00, scale, lo, hi, mean != nullptr, m, stdv != nullptr, s);
 }
 
 // dist / edge / crop: fp32, element (b, y, x) at ptr[b * batch_stride + y * Ws + x] (the [B,1,Hs,Ws] outputs of predict_step; a

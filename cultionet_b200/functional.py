@@ -240,6 +240,12 @@ class direct_param_grads:
     def __exit__(self, *exc):
         DIRECT_PARAM_GRAD[0] = self.prev
         _DIRECT_WRITTEN.clear()
+        if exc and exc[0] is not None:  # a failed backward: drop the deferred work, leave the accumulators clean
+            for _, dwp, *_ in _PENDING_UNPACK.values():
+                dwp.zero_()
+            _PENDING_UNPACK.clear()
+        else:
+            flush_weight_gradients()
         return False
 
 
@@ -268,6 +274,56 @@ def _wgrad_accumulator(param, taps, N, Ctot, dev):
     buf = torch.zeros((taps, N, Ctot), dtype=torch.float32, device=dev)
     _DWP_ACC[key] = (weakref.ref(param, lambda _r, k=key: _DWP_ACC.pop(k, None)), buf)
     return buf
+
+
+# Weight gradients taken directly are unpacked from their accumulators into ``param.grad`` by ONE launch when the backward pass
+# ends (``direct_param_grads.__exit__``): id(param) -> (param ref, accumulator, gradient buffer, taps, rows, cols, strides, mode).
+_PENDING_UNPACK: dict = {}
+_UNPACK_TABLES: dict = {}  # signature of a pending set -> (device table, ndesc, total_tiles, max_taps)
+BATCH_UNPACK = os.environ.get("CNB_BATCH_UNPACK", "1") != "0"
+
+
+def _defer_unpack(param, dwp, target, taps, rows, cols, s_n, s_k, s_tap, acc_flag) -> bool:
+    if not BATCH_UNPACK or taps > 32:
+        return False
+    key = id(param)
+    if key not in _PENDING_UNPACK:  # a shared weight: its launches accumulate in the same accumulator, one unpack serves them all
+        _PENDING_UNPACK[key] = (param, dwp, target, taps, rows, cols, s_n, s_k, s_tap, acc_flag | 2)
+    return True
+
+
+def flush_weight_gradients() -> int:
+    """Unpack every deferred weight-gradient accumulator into its gradient buffer (and clear it) with one launch; returns how many."""
+    if not _PENDING_UNPACK:
+        return 0
+    entries = list(_PENDING_UNPACK.values())
+    _PENDING_UNPACK.clear()
+    sig = tuple((e[1].data_ptr(), e[2].data_ptr(), e[3], e[4], e[5], e[9]) for e in entries)
+    plan = _UNPACK_TABLES.get(sig)
+    dev = entries[0][1].device
+    if plan is None:
+        capturing = dev.type == "cuda" and torch.cuda.is_current_stream_capturing()
+        if capturing:  # the table upload is a host-to-device copy: build it in an eager step; here fall back to single launches
+            for _, dwp, target, taps, rows, cols, s_n, s_k, s_tap, mode in entries:
+                call("cnb_unpack_wgrad", ptr(dwp), ptr(target), taps, rows, cols, s_n, s_k, s_tap, mode, stream_ptr(dwp))
+            return len(entries)
+        table = (_lib.PackDesc * len(entries))()
+        tile0, max_taps = 0, 1
+        for d, (_, dwp, target, taps, rows, cols, s_n, s_k, s_tap, mode) in zip(table, entries):
+            d.w, d.wp, d.wd = target.data_ptr(), dwp.data_ptr(), None
+            d.taps, d.N, d.K, d.pitch_k, d.pitch_n = taps, rows, cols, cols, rows
+            d.s_n, d.s_k, d.s_tap, d.reserved = s_n, s_k, s_tap, mode
+            d.tiles_x = (cols + 31) // 32
+            d.tile0 = tile0
+            tile0 += d.tiles_x * ((rows + 31) // 32)
+            max_taps = max(max_taps, taps)
+        raw = torch.frombuffer(bytearray(bytes(table)), dtype=torch.uint8).clone().to(dev)
+        if len(_UNPACK_TABLES) > 8:
+            _UNPACK_TABLES.clear()
+        plan = _UNPACK_TABLES[sig] = (raw, len(entries), tile0, max_taps)
+    raw, ndesc, total_tiles, max_taps = plan
+    call("cnb_unpack_wgrads_batched", ptr(raw), ndesc, total_tiles, max_taps, stream_ptr(raw))
+    return ndesc
 
 
 class _Conv2dFn(torch.autograd.Function):
@@ -385,7 +441,8 @@ class _Conv2dFn(torch.autograd.Function):
                 coff += c
             rows, cols, s_n, s_k, s_tap = _weight_strides(kind, N, Ctot, taps, for_dgrad=False)
             if target is not None:
-                call("cnb_unpack_wgrad", ptr(dwp), ptr(target), taps, rows, cols, s_n, s_k, s_tap, acc_flag | 2, stream_ptr(dy))
+                if not _defer_unpack(ctx.params[0], dwp, target, taps, rows, cols, s_n, s_k, s_tap, acc_flag):
+                    call("cnb_unpack_wgrad", ptr(dwp), ptr(target), taps, rows, cols, s_n, s_k, s_tap, acc_flag | 2, stream_ptr(dy))
             else:
                 dw = torch.empty_like(weight, dtype=torch.float32, memory_format=torch.contiguous_format)
                 call("cnb_unpack_wgrad", ptr(dwp), ptr(dw), taps, rows, cols, s_n, s_k, s_tap, 0, stream_ptr(dy))

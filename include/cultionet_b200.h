@@ -140,6 +140,10 @@ int cnb_pack_weights_batched(const cnb_pack_desc* table, int ndesc, int total_ti
  * mode bit 0: accumulate into g (else overwrite); bit 1: clear dwp while reading it (persistent split-K accumulator). */
 int cnb_unpack_wgrad(float* dwp, float* g, int taps, int N, int K,
                      int64_t s_n, int64_t s_k, int64_t s_tap, int mode, void* stream);
+/* cnb_unpack_wgrad for MANY parameters in one launch (taps <= 32 each).  Same device table layout as cnb_pack_weights_batched with the
+ * roles: w = gradient destination g (written), wp = fp32 accumulator dwp[taps][N][K], reserved = mode, tiles_x = ceil(K / 32),
+ * tiles_y = ceil(N / 32), descriptors sorted by tile0. */
+int cnb_unpack_wgrads_batched(const cnb_pack_desc* table, int ndesc, int total_tiles, int max_taps, void* stream);
 /* db[n] (+)= sum_p dy[p][n] (bias gradient) */
 int cnb_bias_grad(const void* dy, int dy_stride, int64_t P, int N, float* db, int accumulate, int dtype, void* stream);
 

@@ -401,7 +401,7 @@ def test_merged_multi_source_data_gradient(dev):
         assert torch.equal(u, v)
 
 
-@pytest.mark.parametrize("geom", [(12, 5, 340, 450, 100, 20, True), (3, 2, 37, 50, 12, 4, False), (2, 1, 100, 100, 100, 20, True)])
+@pytest.mark.parametrize("geom", [(12, 5, 340, 450, 100, 20, True), (12, 5, 340, 440, 100, 20, True), (3, 2, 37, 50, 12, 4, False), (2, 1, 100, 100, 100, 20, True)])
 def test_window_load_matches_reference_windowing(dev, geom):
     """cfg5 geometry (100 px windows, 20 px halo, ragged right / bottom windows): bit-identical to create_predict_dataset's windowing +
     EdgeDataset.get's scaling / clipping + NormValues z-score (oracle/tile_port.py)."""

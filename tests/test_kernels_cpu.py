@@ -218,7 +218,7 @@ def test_attention_dropout(dev):
     cases.na_dropout_case(dev, 1, 9, 8, 2, 8, 3, 1)
 
 
-@pytest.mark.parametrize("geom", [(3, 2, 37, 50, 12, 4, True), (2, 3, 24, 24, 12, 2, False), (1, 1, 5, 9, 8, 2, True)])
+@pytest.mark.parametrize("geom", [(3, 2, 37, 50, 12, 4, True), (2, 3, 24, 24, 12, 2, False), (1, 1, 5, 9, 8, 2, True), (2, 2, 45, 64, 16, 4, True)])
 def test_window_load_matches_reference_windowing(dev, geom):
     cases.window_load_case(dev, *geom)
 
