@@ -654,6 +654,7 @@ static bool na_tile_setup(int B, int H, int W, int heads, int hd, int ksize, int
     if (dil > NA_TH) return false;  // the halo bound needs TILE >= dilation
     const int span = (ksize - 1) * dil;
     g->B = B, g->H = H, g->W = W, g->heads = heads, g->hd = hd, g->ksize = ksize, g->dil = dil, g->scale = scale;
+    g->groups = 1;
     g->RH = H < NA_TH + span ? H : NA_TH + span;
     g->RW = W < NA_TW + span ? W : NA_TW + span;
     g->tiles_y = cnb_div_up(H, NA_TH);
@@ -662,6 +663,28 @@ static bool na_tile_setup(int B, int H, int W, int heads, int hd, int ksize, int
     if (*smem > (size_t)NA_MAX_SMEM) return false;
     if ((long)B * g->tiles_y * g->tiles_x > 2147483647L || heads > 65535) return false;
     *lph = l;
+    return true;
+}
+
+// Geometry of the specialised kernels (k_na_fast.cuh): dilation d = d*d independent dilation-1 sub-images of at most
+// ceil(H/d) x ceil(W/d) pixels; tiles, halo (k/2 sub-image pixels) and the staged region are those of the largest sub-image.
+static bool naf_tile_setup(int B, int H, int W, int heads, int hd, int ksize, int dil, float scale, NaTile* g, int* lph, size_t* smem,
+                           dim3* grid) {
+    if (hd % 8 != 0) return false;
+    const int Hs = cnb_div_up(H, dil), Ws = cnb_div_up(W, dil);
+    const int span = ksize - 1;
+    g->B = B, g->H = H, g->W = W, g->heads = heads, g->hd = hd, g->ksize = ksize, g->dil = 1, g->scale = scale;
+    g->groups = dil;
+    g->RH = Hs < NA_TH + span ? Hs : NA_TH + span;
+    g->RW = Ws < NA_TW + span ? Ws : NA_TW + span;
+    g->tiles_y = cnb_div_up(Hs, NA_TH);
+    g->tiles_x = cnb_div_up(Ws, NA_TW);
+    *smem = (size_t)g->RH * g->RW * 2 * hd * 2;
+    if (*smem > (size_t)NA_MAX_SMEM) return false;
+    const long ctas = (long)B * dil * dil * g->tiles_y * g->tiles_x;
+    if (ctas > 2147483647L || heads > 65535) return false;
+    *lph = hd / 8;
+    *grid = dim3((unsigned)ctas, heads);
     return true;
 }
 
@@ -698,14 +721,10 @@ static bool na_tile_setup(int B, int H, int W, int heads, int hd, int ksize, int
     } while (0)
 #define CNB_NAF_LAUNCH(KERNEL, ...)                                                 \
     do {                                                                            \
-        if (ksize == 3 && dilation == 1)                                            \
+        if (ksize == 3)                                                             \
             CNB_NAF_LAUNCH_KD(KERNEL, 3, 1, __VA_ARGS__);                           \
-        else if (ksize == 3)                                                        \
-            CNB_NAF_LAUNCH_KD(KERNEL, 3, 2, __VA_ARGS__);                           \
-        else if (dilation == 1)                                                     \
-            CNB_NAF_LAUNCH_KD(KERNEL, 7, 1, __VA_ARGS__);                           \
         else                                                                        \
-            CNB_NAF_LAUNCH_KD(KERNEL, 7, 2, __VA_ARGS__);                           \
+            CNB_NAF_LAUNCH_KD(KERNEL, 7, 1, __VA_ARGS__);                           \
     } while (0)
 
 int64_t cnb_na2d_bwd_workspace_floats(int B, int H, int W, int heads, int hd, int ksize, int dilation, int dtype) {
@@ -713,8 +732,8 @@ int64_t cnb_na2d_bwd_workspace_floats(int B, int H, int W, int heads, int hd, in
     NaTile g;
     int lph;
     size_t smem;
-    if (!naf::eligible(hd, ksize, dilation, dtype) || !na_tile_setup(B, H, W, heads, hd, ksize, dilation, 1.f, dtype, false, &g, &lph, &smem))
-        return 0;
+    dim3 grid;
+    if (!naf::eligible(hd, ksize, dilation, dtype) || !naf_tile_setup(B, H, W, heads, hd, ksize, dilation, 1.f, &g, &lph, &smem, &grid)) return 0;
     return (int64_t)B * H * W * heads * ksize * ksize;  // one bf16 pair (4 bytes) per (pixel, head, neighbour)
 }
 
@@ -723,6 +742,8 @@ int cnb_na2d_tiled_eligible(int B, int H, int W, int heads, int hd, int ksize, i
     NaTile g;
     int lph;
     size_t smem;
+    dim3 grid;
+    if (naf::eligible(hd, ksize, dilation, dtype) && naf_tile_setup(B, H, W, heads, hd, ksize, dilation, 1.f, &g, &lph, &smem, &grid)) return 1;
     return na_tile_setup(B, H, W, heads, hd, ksize, dilation, 1.f, dtype, true, &g, &lph, &smem) ? 1 : 0;
 }
 
@@ -734,14 +755,17 @@ int cnb_na2d_fwd(const void* qkv, void* out, float* lse, int B, int H, int W, in
     NaTile g;
     int lph;
     size_t smem;
-    if (lse && cnb_aligned16(qkv) && cnb_aligned16(out) &&
-        na_tile_setup(B, H, W, heads, hd, ksize, dilation, scale, dtype, false, &g, &lph, &smem)) {
-        const dim3 grid(B * g.tiles_y * g.tiles_x, heads);
-        if (naf::eligible(hd, ksize, dilation, dtype)) {
+    if (lse && cnb_aligned16(qkv) && cnb_aligned16(out) && naf::eligible(hd, ksize, dilation, dtype)) {
+        dim3 grid;
+        if (naf_tile_setup(B, H, W, heads, hd, ksize, dilation, scale, &g, &lph, &smem, &grid)) {
             CNB_NAF_LAUNCH(naf::na2d_fwd_fast_kernel, (const bf16_t*)qkv, (bf16_t*)out, lse, g);
             CNB_CHECK_LAUNCH("na2d_fwd_fast_kernel");
             return CNB_OK;
         }
+    }
+    if (lse && cnb_aligned16(qkv) && cnb_aligned16(out) &&
+        na_tile_setup(B, H, W, heads, hd, ksize, dilation, scale, dtype, false, &g, &lph, &smem)) {
+        const dim3 grid(B * g.tiles_y * g.tiles_x, heads);
         CNB_NA_LAUNCH(na2d_fwd_tile_kernel, (const T*)qkv, (T*)out, lse, g);
         CNB_CHECK_LAUNCH("na2d_fwd_tile_kernel");
         return CNB_OK;
@@ -801,18 +825,21 @@ int cnb_na2d_bwd(const void* qkv, const void* dout, const void* out, const float
     NaTile g;
     int lph;
     size_t smem;
-    if (out && lse && dvec && cnb_aligned16(qkv) && cnb_aligned16(dout) && cnb_aligned16(out) && cnb_aligned16(dqkv) &&
-        na_tile_setup(B, H, W, heads, hd, ksize, dilation, scale, dtype, true, &g, &lph, &smem)) {
-        const dim3 grid(B * g.tiles_y * g.tiles_x, heads);
-        if (pds_ws && naf::eligible(hd, ksize, dilation, dtype)) {
-            // the staged rows are k|v (query pass) or q|dout (key pass); no per-pixel statistics ride along
-            smem = (size_t)g.RH * g.RW * 2 * hd * 2;
+    if (out && lse && pds_ws && cnb_aligned16(qkv) && cnb_aligned16(dout) && cnb_aligned16(out) && cnb_aligned16(dqkv) &&
+        naf::eligible(hd, ksize, dilation, dtype)) {
+        dim3 grid;
+        if (naf_tile_setup(B, H, W, heads, hd, ksize, dilation, scale, &g, &lph, &smem, &grid)) {
+            // the staged rows are k|v (query pass) or q|dout (key pass)
             CNB_NAF_LAUNCH(naf::na2d_bwd_dq_fast_kernel, (const bf16_t*)qkv, (const bf16_t*)dout, (const bf16_t*)out, lse, (uint32_t*)pds_ws,
                            (bf16_t*)dqkv, g);
             CNB_NAF_LAUNCH(naf::na2d_bwd_dkv_fast_kernel, (const bf16_t*)qkv, (const bf16_t*)dout, (const uint32_t*)pds_ws, (bf16_t*)dqkv, g);
             CNB_CHECK_LAUNCH("na2d_bwd_fast_kernels");
             return CNB_OK;
         }
+    }
+    if (out && lse && dvec && cnb_aligned16(qkv) && cnb_aligned16(dout) && cnb_aligned16(out) && cnb_aligned16(dqkv) &&
+        na_tile_setup(B, H, W, heads, hd, ksize, dilation, scale, dtype, true, &g, &lph, &smem)) {
+        const dim3 grid(B * g.tiles_y * g.tiles_x, heads);
         CNB_NA_LAUNCH(na2d_bwd_dq_tile_kernel, (const T*)qkv, (const T*)dout, (const T*)out, lse, dvec, (T*)dqkv, g);
         CNB_NA_LAUNCH(na2d_bwd_dkv_tile_kernel, (const T*)qkv, (const T*)dout, lse, (const float*)dvec, (T*)dqkv, g);
         CNB_CHECK_LAUNCH("na2d_bwd_tile_kernels");

@@ -223,6 +223,8 @@ struct NaTile {
     int B, H, W, heads, hd, ksize, dil;
     int tiles_x, tiles_y, RH, RW;  // region = tile + halo, clipped to the image
     float scale;
+    int groups;  // k_na_fast.cuh: dilation d handled as d*d independent dilation-1 sub-images (groups = d; H/W/tiles/RH/RW as set up
+                 // by naf_tile_setup describe the LARGEST sub-image); 0 or 1 elsewhere
 };
 
 __device__ __forceinline__ int na_region_origin(int t0, int halo, int len, int rlen) {

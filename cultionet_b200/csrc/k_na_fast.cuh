@@ -78,23 +78,54 @@ __device__ __forceinline__ void axpy8p(uint32_t wp, const uint4& b, float* acc) 
     cnb_axpy2_bf16<HI>(wp, b.w, acc[6], acc[7]);
 }
 
+// Dilation groups.  A pixel only ever attends to pixels of its own residue class (y mod d, x mod d), and natten clamps a window
+// inside that class (oracle/natten_ref.py): neighbourhood attention with dilation d IS plain dilation-1 attention on each of the d*d
+// sub-images x[gy::d, gx::d].  A CTA therefore works on a tile of ONE sub-image: the staged halo is k/2 sub-image pixels wide
+// instead of (k/2)*d image pixels, i.e. the staged region of a k = 7, d = 2 tile shrinks from 20 x 28 (143 KB, one CTA per SM) to
+// 14 x 22 pixels (79 KB, two CTAs per SM), and every kernel below is written for dilation 1 in sub-image coordinates
+// (ys, xs) <-> image pixel (gy + d ys, gx + d xs) = img_pix0 + ys * rs + xs * cs.
 struct TilePos {
-    int head, b, y0, x0, ry0, rx0;
-    long img_pix0;
+    int head, y0, x0, ry0, rx0;
+    int H, W, RH, RW;  // this sub-image, and its staged region
+    long img_pix0, rs, cs;
+    bool empty;  // the tile lies outside a (smaller) sub-image
 };
 __device__ __forceinline__ TilePos tile_pos(const NaTile& g) {
     TilePos t;
     t.head = blockIdx.y;
+    const int d = g.groups > 1 ? g.groups : 1;
     int i = blockIdx.x;
     const int tx = i % g.tiles_x;
     i /= g.tiles_x;
     const int ty = i % g.tiles_y;
-    t.b = i / g.tiles_y;
-    const int halo = (g.ksize / 2) * g.dil;
+    i /= g.tiles_y;
+    const int par = i % (d * d), b = i / (d * d);
+    const int gy = par / d, gx = par % d;
+    t.H = (g.H - gy + d - 1) / d, t.W = (g.W - gx + d - 1) / d;
+    t.RH = g.RH < t.H ? g.RH : t.H, t.RW = g.RW < t.W ? g.RW : t.W;
+    const int halo = g.ksize / 2;
     t.y0 = ty * NA_TH, t.x0 = tx * NA_TW;
-    t.ry0 = na_region_origin(t.y0, halo, g.H, g.RH), t.rx0 = na_region_origin(t.x0, halo, g.W, g.RW);
-    t.img_pix0 = (long)t.b * g.H * g.W;
+    t.ry0 = na_region_origin(t.y0, halo, t.H, t.RH), t.rx0 = na_region_origin(t.x0, halo, t.W, t.RW);
+    t.img_pix0 = (long)b * g.H * g.W + (long)gy * g.W + gx;
+    t.rs = (long)d * g.W, t.cs = d;
+    t.empty = t.y0 >= t.H || t.x0 >= t.W;
     return t;
+}
+// stage two HD-wide row segments per region pixel: smem[(ry*RW + rx)][0..HD) = a, [HD..2HD) = b
+template <int HD>
+__device__ __forceinline__ void stage_region(bf16_t* sm, const bf16_t* a_base, long a_stride, const bf16_t* b_base, long b_stride,
+                                             const TilePos& t) {
+    constexpr int parts = HD / 8;
+    const int total = t.RH * t.RW * 2 * parts;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int part = i % (2 * parts);
+        const int r = i / (2 * parts);
+        const int rx = r % t.RW, ry = r / t.RW;
+        const long pix = t.img_pix0 + (t.ry0 + ry) * t.rs + (t.rx0 + rx) * t.cs;
+        const bf16_t* src = part < parts ? a_base + pix * a_stride + part * 8 : b_base + pix * b_stride + (part - parts) * 8;
+        cnb_cp_async16(sm + (long)r * 2 * HD + part * 8, src);
+    }
+    cnb_cp_async_wait_all();
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -107,12 +138,13 @@ __global__ void __launch_bounds__(NA_TILE_THREADS) na2d_fwd_fast_kernel(const bf
     constexpr int HD = LPH * 8, K2 = KS * KS;
     CNB_DYN_SMEM(sm_raw);
     bf16_t* sm = reinterpret_cast<bf16_t*>(sm_raw);
+    static_assert(DIL == 1, "dilation is handled by the sub-image decomposition (tile_pos)");
     const TilePos t = tile_pos(g);
+    if (t.empty) return;
     const int C = g.heads * HD;
-    na_stage_region(sm, qkv + C + t.head * HD, qkv + 2 * C + t.head * HD, 3L * C, g, t.img_pix0, t.ry0, t.rx0);
+    stage_region<HD>(sm, qkv + C + t.head * HD, 3L * C, qkv + 2 * C + t.head * HD, 3L * C, t);
     __syncthreads();
-    const int dil = DIL > 0 ? DIL : g.dil;
-    const int col_step = dil * 2 * HD, row_step = col_step * g.RW;  // elements between window columns / rows in the staged region
+    const int col_step = 2 * HD, row_step = col_step * t.RW;  // elements between window columns / rows in the staged region
 
     static_assert((NA_TH * NA_TW * LPH) % NA_TILE_THREADS == 0, "whole rounds: the warps stay converged for the shuffles");
 #pragma unroll 1
@@ -120,13 +152,13 @@ __global__ void __launch_bounds__(NA_TILE_THREADS) na2d_fwd_fast_kernel(const bf
         const int it = round * NA_TILE_THREADS + threadIdx.x;
         const int sub = it % LPH, pl = it / LPH;
         const int lx = pl % NA_TW, ly = pl / NA_TW;
-        const bool valid = (t.y0 + ly) < g.H && (t.x0 + lx) < g.W;
-        // out-of-image lanes shadow the last pixel of the image (it lies in this tile): control flow and shuffles stay uniform
-        const int y = (t.y0 + ly) < g.H ? t.y0 + ly : g.H - 1, x = (t.x0 + lx) < g.W ? t.x0 + lx : g.W - 1;
-        const long pix = t.img_pix0 + (long)y * g.W + x;
+        const bool valid = (t.y0 + ly) < t.H && (t.x0 + lx) < t.W;
+        // out-of-image lanes shadow the last pixel of the sub-image (it lies in this tile): control flow and shuffles stay uniform
+        const int y = (t.y0 + ly) < t.H ? t.y0 + ly : t.H - 1, x = (t.x0 + lx) < t.W ? t.x0 + lx : t.W - 1;
+        const long pix = t.img_pix0 + y * t.rs + x * t.cs;
         const uint4 qraw = *reinterpret_cast<const uint4*>(qkv + pix * 3 * C + t.head * HD + sub * 8);
-        const int sy = wstart<DIL>(y, g.H, KS, g.dil), sx = wstart<DIL>(x, g.W, KS, g.dil);
-        const bf16_t* kb = sm + ((sy - t.ry0) * g.RW + (sx - t.rx0)) * 2 * HD + sub * 8;
+        const int sy = wstart<1>(y, t.H, KS, 1), sx = wstart<1>(x, t.W, KS, 1);
+        const bf16_t* kb = sm + ((sy - t.ry0) * t.RW + (sx - t.rx0)) * 2 * HD + sub * 8;
         float lg[K2];
         float m = -INFINITY;
 #pragma unroll
@@ -173,12 +205,13 @@ __global__ void __launch_bounds__(NA_TILE_THREADS) na2d_bwd_dq_fast_kernel(const
     constexpr int HD = LPH * 8, K2 = KS * KS;
     CNB_DYN_SMEM(sm_raw);
     bf16_t* sm = reinterpret_cast<bf16_t*>(sm_raw);
+    static_assert(DIL == 1, "dilation is handled by the sub-image decomposition (tile_pos)");
     const TilePos t = tile_pos(g);
+    if (t.empty) return;
     const int C = g.heads * HD;
-    na_stage_region(sm, qkv + C + t.head * HD, qkv + 2 * C + t.head * HD, 3L * C, g, t.img_pix0, t.ry0, t.rx0);
+    stage_region<HD>(sm, qkv + C + t.head * HD, 3L * C, qkv + 2 * C + t.head * HD, 3L * C, t);
     __syncthreads();
-    const int dil = DIL > 0 ? DIL : g.dil;
-    const int col_step = dil * 2 * HD, row_step = col_step * g.RW;
+    const int col_step = 2 * HD, row_step = col_step * t.RW;
 
     static_assert((NA_TH * NA_TW * LPH) % NA_TILE_THREADS == 0, "whole rounds: the warps stay converged for the shuffles");
 #pragma unroll 1
@@ -186,15 +219,15 @@ __global__ void __launch_bounds__(NA_TILE_THREADS) na2d_bwd_dq_fast_kernel(const
         const int it = round * NA_TILE_THREADS + threadIdx.x;
         const int sub = it % LPH, pl = it / LPH;
         const int lx = pl % NA_TW, ly = pl / NA_TW;
-        const bool valid = (t.y0 + ly) < g.H && (t.x0 + lx) < g.W;
-        const int y = (t.y0 + ly) < g.H ? t.y0 + ly : g.H - 1, x = (t.x0 + lx) < g.W ? t.x0 + lx : g.W - 1;
-        const long pix = t.img_pix0 + (long)y * g.W + x;
+        const bool valid = (t.y0 + ly) < t.H && (t.x0 + lx) < t.W;
+        const int y = (t.y0 + ly) < t.H ? t.y0 + ly : t.H - 1, x = (t.x0 + lx) < t.W ? t.x0 + lx : t.W - 1;
+        const long pix = t.img_pix0 + y * t.rs + x * t.cs;
         const uint4 qraw = *reinterpret_cast<const uint4*>(qkv + pix * 3 * C + t.head * HD + sub * 8);
         const uint4 graw = *reinterpret_cast<const uint4*>(dout + pix * C + t.head * HD + sub * 8);
         const float D = gsum<LPH>(dot8p(graw, *reinterpret_cast<const uint4*>(out + pix * C + t.head * HD + sub * 8)));
         const float L = lse[pix * g.heads + t.head];
-        const int sy = wstart<DIL>(y, g.H, KS, g.dil), sx = wstart<DIL>(x, g.W, KS, g.dil);
-        const bf16_t* kb = sm + ((sy - t.ry0) * g.RW + (sx - t.rx0)) * 2 * HD + sub * 8;
+        const int sy = wstart<1>(y, t.H, KS, 1), sx = wstart<1>(x, t.W, KS, 1);
+        const bf16_t* kb = sm + ((sy - t.ry0) * t.RW + (sx - t.rx0)) * 2 * HD + sub * 8;
         float dq[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) dq[j] = 0.f;
@@ -246,30 +279,20 @@ __global__ void __launch_bounds__(NA_TILE_THREADS) na2d_bwd_dkv_fast_kernel(cons
     constexpr int HD = LPH * 8, K2 = KS * KS;
     CNB_DYN_SMEM(sm_raw);
     bf16_t* sm = reinterpret_cast<bf16_t*>(sm_raw);
+    static_assert(DIL == 1, "dilation is handled by the sub-image decomposition (tile_pos)");
     const TilePos t = tile_pos(g);
+    if (t.empty) return;
     const int C = g.heads * HD;
-    {
-        constexpr int parts = HD / 8;
-        const int total = g.RH * g.RW * 2 * parts;
-        for (int i = threadIdx.x; i < total; i += blockDim.x) {
-            const int part = i % (2 * parts);
-            const int r = i / (2 * parts);
-            const int rx = r % g.RW, ry = r / g.RW;
-            const long pix = t.img_pix0 + (long)(t.ry0 + ry) * g.W + (t.rx0 + rx);
-            const bf16_t* src = part < parts ? qkv + pix * 3 * C + t.head * HD + part * 8 : dout + pix * C + t.head * HD + (part - parts) * 8;
-            cnb_cp_async16(sm + (long)r * 2 * HD + part * 8, src);
-        }
-        cnb_cp_async_wait_all();
-    }
+    stage_region<HD>(sm, qkv + t.head * HD, 3L * C, dout + t.head * HD, (long)C, t);
     __syncthreads();
-    const int dil = DIL > 0 ? DIL : g.dil;
+    constexpr int dil = 1;
 
     for (int it = threadIdx.x; it < NA_TH * NA_TW * LPH; it += NA_TILE_THREADS) {
         const int sub = it % LPH, pl = it / LPH;
         const int lx = pl % NA_TW, ly = pl / NA_TW;
         const int y = t.y0 + ly, x = t.x0 + lx;
-        if (y >= g.H || x >= g.W) continue;  // no shuffles below: lanes may drop out
-        const long pix = t.img_pix0 + (long)y * g.W + x;
+        if (y >= t.H || x >= t.W) continue;  // no shuffles below: lanes may drop out
+        const long pix = t.img_pix0 + y * t.rs + x * t.cs;
         float dk[8], dv[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) dk[j] = 0.f, dv[j] = 0.f;
@@ -279,11 +302,11 @@ __global__ void __launch_bounds__(NA_TILE_THREADS) na2d_bwd_dkv_fast_kernel(cons
         // per candidate on it, 5 x 5 candidates for k = 3).  A clamped window reaches at most (k - 1)*d + d - 1 from its border.
         constexpr int HK = KS / 2;
         const int lim = (2 * HK + 1) * dil;
-        if (y >= lim && y + lim < g.H && x >= lim && x + lim < g.W) {
-            const bf16_t* qb = sm + ((y - t.ry0) * g.RW + (x - t.rx0)) * 2 * HD + sub * 8;
+        if (y >= lim && y + lim < t.H && x >= lim && x + lim < t.W) {
+            const bf16_t* qb = sm + ((y - t.ry0) * t.RW + (x - t.rx0)) * 2 * HD + sub * 8;
             const uint32_t* rb = pds + (pix * g.heads + t.head) * K2;
-            const long rec_row = (long)dil * g.W * g.heads * K2, rec_col = (long)dil * g.heads * K2;
-            const int sm_row = dil * g.RW * 2 * HD, sm_col = dil * 2 * HD;
+            const long rec_row = t.rs * g.heads * K2, rec_col = t.cs * g.heads * K2;
+            const int sm_row = t.RW * 2 * HD, sm_col = 2 * HD;
 #pragma unroll
             for (int my = -HK; my <= HK; ++my)
 #pragma unroll
@@ -297,30 +320,30 @@ __global__ void __launch_bounds__(NA_TILE_THREADS) na2d_bwd_dkv_fast_kernel(cons
             cnb_stv(dqkv + pix * 3 * C + 2 * C + t.head * HD + sub * 8, dv);
             continue;
         }
-        const uint32_t ymask = inverse_mask<KS, DIL>(y, g.H, g.dil), xmask = inverse_mask<KS, DIL>(x, g.W, g.dil);
+        const uint32_t ymask = inverse_mask<KS, 1>(y, t.H, 1), xmask = inverse_mask<KS, 1>(x, t.W, 1);
         // column index of x inside the window of each candidate query column (hoisted out of the row loop)
         int bcol[2 * KS - 1];
 #pragma unroll
         for (int mx = 0; mx < 2 * KS - 1; ++mx) {
             const int ix = x + (mx - (KS - 1)) * dil;
-            bcol[mx] = ((xmask >> mx) & 1u) ? (x - wstart<DIL>(ix, g.W, KS, g.dil)) / dil : 0;
+            bcol[mx] = ((xmask >> mx) & 1u) ? (x - wstart<1>(ix, t.W, KS, 1)) : 0;
         }
 #pragma unroll
         for (int my = 0; my < 2 * KS - 1; ++my) {
             if (!((ymask >> my) & 1u)) continue;
             const int iy = y + (my - (KS - 1)) * dil;
-            const int arow = (y - wstart<DIL>(iy, g.H, KS, g.dil)) / dil;
+            const int arow = y - wstart<1>(iy, t.H, KS, 1);
             const int ry = iy - t.ry0;
 #pragma unroll
             for (int mx = 0; mx < 2 * KS - 1; ++mx) {
                 if (!((xmask >> mx) & 1u)) continue;
                 const int ix = x + (mx - (KS - 1)) * dil;
                 const int rx = ix - t.rx0;
-                const long ipix = t.img_pix0 + (long)iy * g.W + ix;
+                const long ipix = t.img_pix0 + iy * t.rs + ix * t.cs;
                 const uint32_t w = pds[(ipix * g.heads + t.head) * K2 + arow * KS + bcol[mx]];  // bf16 pair (p, scale * ds)
                 uint4 qraw, graw;
-                if (ry >= 0 && ry < g.RH && rx >= 0 && rx < g.RW) {
-                    const bf16_t* qp = sm + (ry * g.RW + rx) * 2 * HD + sub * 8;
+                if (ry >= 0 && ry < t.RH && rx >= 0 && rx < t.RW) {
+                    const bf16_t* qp = sm + (ry * t.RW + rx) * 2 * HD + sub * 8;
                     qraw = *reinterpret_cast<const uint4*>(qp);
                     graw = *reinterpret_cast<const uint4*>(qp + HD);
                 } else {

@@ -107,7 +107,7 @@ def test_neighborhood_attention(dev, dtype, cfg):
 
 
 @pytest.mark.parametrize("cfg", [(8, 32, 3, 1, 32, 32), (4, 64, 3, 1, 64, 64), (4, 64, 3, 2, 128, 128), (4, 64, 7, 2, 100, 100), (2, 32, 7, 1, 25, 29),
-                                 (2, 64, 3, 2, 21, 37), (1, 32, 3, 2, 6, 7)])
+                                 (2, 64, 3, 2, 21, 37), (1, 32, 3, 2, 6, 7), (1, 32, 3, 2, 33, 21), (1, 32, 7, 2, 33, 35)])
 def test_neighborhood_attention_specialised_bf16(dev, cfg):
     """k_na_fast.cuh: the cfg 2 shapes (levels c, b, a), cfg 4's kernel 7 / dilation 2, and odd sizes with clamped windows."""
     heads, hd, k, d, H, W = cfg
