@@ -688,6 +688,16 @@ static bool naf_tile_setup(int B, int H, int W, int heads, int hd, int ksize, in
     return true;
 }
 
+// which tiling the key-side backward pass of the specialised kernels uses (see k_na_fast.cuh); measured per shape on B200
+static bool na_dkv_image_tiles(int ksize, int dilation) {
+    static const int forced = [] {
+        const char* e = getenv("CNB_NA_DKV");
+        return !e ? 0 : (e[0] == 'i' ? 1 : (e[0] == 'g' ? 2 : 0));
+    }();
+    if (forced) return forced == 1;
+    return dilation > 1;  // B200: image tiles win the key-side pass at every dilated shape (k3 d2 128^2: 1.20 vs 1.46 ms bwd; k7 d2 256^2: 12.9 vs 16.1)
+}
+
 // launch a `template <typename T, int LPH>` tiled NA kernel
 #define CNB_NA_LAUNCH_LPH(KERNEL, LPHV, ...)                                                                       \
     CNB_DISPATCH_DTYPE(dtype, {                                                                                    \
@@ -832,7 +842,27 @@ int cnb_na2d_bwd(const void* qkv, const void* dout, const void* out, const float
             // the staged rows are k|v (query pass) or q|dout (key pass)
             CNB_NAF_LAUNCH(naf::na2d_bwd_dq_fast_kernel, (const bf16_t*)qkv, (const bf16_t*)dout, (const bf16_t*)out, lse, (uint32_t*)pds_ws,
                            (bf16_t*)dqkv, g);
-            CNB_NAF_LAUNCH(naf::na2d_bwd_dkv_fast_kernel, (const bf16_t*)qkv, (const bf16_t*)dout, (const uint32_t*)pds_ws, (bf16_t*)dqkv, g);
+            // key side: sub-image tiles, or image-space tiles (the query records are indexed by image pixel: the two passes may tile
+            // differently); CNB_NA_DKV=img|group overrides the default
+            NaTile gi;
+            int lph_i;
+            size_t smem_i;
+            const bool img_ok = na_tile_setup(B, H, W, heads, hd, ksize, dilation, scale, dtype, false, &gi, &lph_i, &smem_i);
+            if (img_ok && na_dkv_image_tiles(ksize, dilation)) {
+                const dim3 grid_g = grid;
+                (void)grid_g;
+                grid = dim3(B * gi.tiles_y * gi.tiles_x, heads);
+                smem = smem_i;
+                if (dilation == 1) {
+                    if (ksize == 3) CNB_NAF_LAUNCH_KD(naf::na2d_bwd_dkv_img_kernel, 3, 1, (const bf16_t*)qkv, (const bf16_t*)dout, (const uint32_t*)pds_ws, (bf16_t*)dqkv, gi);
+                    else CNB_NAF_LAUNCH_KD(naf::na2d_bwd_dkv_img_kernel, 7, 1, (const bf16_t*)qkv, (const bf16_t*)dout, (const uint32_t*)pds_ws, (bf16_t*)dqkv, gi);
+                } else {
+                    if (ksize == 3) CNB_NAF_LAUNCH_KD(naf::na2d_bwd_dkv_img_kernel, 3, 2, (const bf16_t*)qkv, (const bf16_t*)dout, (const uint32_t*)pds_ws, (bf16_t*)dqkv, gi);
+                    else CNB_NAF_LAUNCH_KD(naf::na2d_bwd_dkv_img_kernel, 7, 2, (const bf16_t*)qkv, (const bf16_t*)dout, (const uint32_t*)pds_ws, (bf16_t*)dqkv, gi);
+                }
+            } else {
+                CNB_NAF_LAUNCH(naf::na2d_bwd_dkv_fast_kernel, (const bf16_t*)qkv, (const bf16_t*)dout, (const uint32_t*)pds_ws, (bf16_t*)dqkv, g);
+            }
             CNB_CHECK_LAUNCH("na2d_bwd_fast_kernels");
             return CNB_OK;
         }

@@ -359,6 +359,131 @@ __global__ void __launch_bounds__(NA_TILE_THREADS) na2d_bwd_dkv_fast_kernel(cons
     }
 }
 
+struct TilePosImg {
+    int head, b, y0, x0, ry0, rx0;
+    long img_pix0;
+};
+__device__ __forceinline__ TilePosImg tile_pos_img(const NaTile& g) {
+    TilePosImg t;
+    t.head = blockIdx.y;
+    int i = blockIdx.x;
+    const int tx = i % g.tiles_x;
+    i /= g.tiles_x;
+    const int ty = i % g.tiles_y;
+    t.b = i / g.tiles_y;
+    const int halo = (g.ksize / 2) * g.dil;
+    t.y0 = ty * NA_TH, t.x0 = tx * NA_TW;
+    t.ry0 = na_region_origin(t.y0, halo, g.H, g.RH), t.rx0 = na_region_origin(t.x0, halo, g.W, g.RW);
+    t.img_pix0 = (long)t.b * g.H * g.W;
+    return t;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// backward, key side, IMAGE-SPACE tiles (the version before the sub-image decomposition; NaTile from na_tile_setup, dilation as a
+// template parameter).  Kept selectable (CNB_NA_DKV=img) because the key-side gather of the query records behaves differently in L1
+// under the two tilings.
+// backward, key side: dk_j = sum_i ds_ij q_i, dv_j = sum_i p_ij dout_i over the queries i whose window holds j (a gather: no
+// atomics, deterministic).  Region rows: q_i | dout_i.  A query clamped at the image border can sit up to (k-1)*d from its key,
+// i.e. outside the staged region of an interior-side tile: those few candidates are read from global memory.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int KS, int DIL, int LPH>
+__global__ void __launch_bounds__(NA_TILE_THREADS) na2d_bwd_dkv_img_kernel(const bf16_t* __restrict__ qkv, const bf16_t* __restrict__ dout,
+                                                                           const uint32_t* __restrict__ pds, bf16_t* __restrict__ dqkv,
+                                                                           NaTile g) {
+    CNB_PDL_SYNC();
+    constexpr int HD = LPH * 8, K2 = KS * KS;
+    CNB_DYN_SMEM(sm_raw);
+    bf16_t* sm = reinterpret_cast<bf16_t*>(sm_raw);
+    const TilePosImg t = tile_pos_img(g);
+    const int C = g.heads * HD;
+    {
+        constexpr int parts = HD / 8;
+        const int total = g.RH * g.RW * 2 * parts;
+        for (int i = threadIdx.x; i < total; i += blockDim.x) {
+            const int part = i % (2 * parts);
+            const int r = i / (2 * parts);
+            const int rx = r % g.RW, ry = r / g.RW;
+            const long pix = t.img_pix0 + (long)(t.ry0 + ry) * g.W + (t.rx0 + rx);
+            const bf16_t* src = part < parts ? qkv + pix * 3 * C + t.head * HD + part * 8 : dout + pix * C + t.head * HD + (part - parts) * 8;
+            cnb_cp_async16(sm + (long)r * 2 * HD + part * 8, src);
+        }
+        cnb_cp_async_wait_all();
+    }
+    __syncthreads();
+    const int dil = DIL > 0 ? DIL : g.dil;
+
+    for (int it = threadIdx.x; it < NA_TH * NA_TW * LPH; it += NA_TILE_THREADS) {
+        const int sub = it % LPH, pl = it / LPH;
+        const int lx = pl % NA_TW, ly = pl / NA_TW;
+        const int y = t.y0 + ly, x = t.x0 + lx;
+        if (y >= g.H || x >= g.W) continue;  // no shuffles below: lanes may drop out
+        const long pix = t.img_pix0 + (long)y * g.W + x;
+        float dk[8], dv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dk[j] = 0.f, dv[j] = 0.f;
+        // Interior keys (most of the image): no window that holds the key is clamped, so the queries are exactly the k x k pixels
+        // (y + my*d, x + mx*d), |my|, |mx| <= k/2, the key sits at window position (k/2 - my, k/2 - mx) of each, and all of them lie
+        // in the staged region: compile-time offsets, no window arithmetic (the generic path below spends ~60 integer instructions
+        // per candidate on it, 5 x 5 candidates for k = 3).  A clamped window reaches at most (k - 1)*d + d - 1 from its border.
+        constexpr int HK = KS / 2;
+        const int lim = (2 * HK + 1) * dil;
+        if (y >= lim && y + lim < g.H && x >= lim && x + lim < g.W) {
+            const bf16_t* qb = sm + ((y - t.ry0) * g.RW + (x - t.rx0)) * 2 * HD + sub * 8;
+            const uint32_t* rb = pds + (pix * g.heads + t.head) * K2;
+            const long rec_row = (long)dil * g.W * g.heads * K2, rec_col = (long)dil * g.heads * K2;
+            const int sm_row = dil * g.RW * 2 * HD, sm_col = dil * 2 * HD;
+#pragma unroll
+            for (int my = -HK; my <= HK; ++my)
+#pragma unroll
+                for (int mx = -HK; mx <= HK; ++mx) {
+                    const uint32_t w = rb[my * rec_row + mx * rec_col + (HK - my) * KS + (HK - mx)];
+                    const bf16_t* qp = qb + my * sm_row + mx * sm_col;
+                    axpy8p<true>(w, *reinterpret_cast<const uint4*>(qp), dk);
+                    axpy8p<false>(w, *reinterpret_cast<const uint4*>(qp + HD), dv);
+                }
+            cnb_stv(dqkv + pix * 3 * C + C + t.head * HD + sub * 8, dk);
+            cnb_stv(dqkv + pix * 3 * C + 2 * C + t.head * HD + sub * 8, dv);
+            continue;
+        }
+        const uint32_t ymask = inverse_mask<KS, DIL>(y, g.H, g.dil), xmask = inverse_mask<KS, DIL>(x, g.W, g.dil);
+        // column index of x inside the window of each candidate query column (hoisted out of the row loop)
+        int bcol[2 * KS - 1];
+#pragma unroll
+        for (int mx = 0; mx < 2 * KS - 1; ++mx) {
+            const int ix = x + (mx - (KS - 1)) * dil;
+            bcol[mx] = ((xmask >> mx) & 1u) ? (x - wstart<DIL>(ix, g.W, KS, g.dil)) / dil : 0;
+        }
+#pragma unroll
+        for (int my = 0; my < 2 * KS - 1; ++my) {
+            if (!((ymask >> my) & 1u)) continue;
+            const int iy = y + (my - (KS - 1)) * dil;
+            const int arow = (y - wstart<DIL>(iy, g.H, KS, g.dil)) / dil;
+            const int ry = iy - t.ry0;
+#pragma unroll
+            for (int mx = 0; mx < 2 * KS - 1; ++mx) {
+                if (!((xmask >> mx) & 1u)) continue;
+                const int ix = x + (mx - (KS - 1)) * dil;
+                const int rx = ix - t.rx0;
+                const long ipix = t.img_pix0 + (long)iy * g.W + ix;
+                const uint32_t w = pds[(ipix * g.heads + t.head) * K2 + arow * KS + bcol[mx]];  // bf16 pair (p, scale * ds)
+                uint4 qraw, graw;
+                if (ry >= 0 && ry < g.RH && rx >= 0 && rx < g.RW) {
+                    const bf16_t* qp = sm + (ry * g.RW + rx) * 2 * HD + sub * 8;
+                    qraw = *reinterpret_cast<const uint4*>(qp);
+                    graw = *reinterpret_cast<const uint4*>(qp + HD);
+                } else {
+                    qraw = *reinterpret_cast<const uint4*>(qkv + ipix * 3 * C + t.head * HD + sub * 8);
+                    graw = *reinterpret_cast<const uint4*>(dout + ipix * C + t.head * HD + sub * 8);
+                }
+                axpy8p<true>(w, qraw, dk);
+                axpy8p<false>(w, graw, dv);
+            }
+        }
+        cnb_stv(dqkv + pix * 3 * C + C + t.head * HD + sub * 8, dk);
+        cnb_stv(dqkv + pix * 3 * C + 2 * C + t.head * HD + sub * 8, dv);
+    }
+}
+
 // shapes with a specialised instantiation: bf16, k in {3, 7}, dilation in {1, 2}, head_dim in {32, 64}
 static inline bool eligible(int hd, int ksize, int dil, int dtype) {
     return dtype == CNB_BF16 && (ksize == 3 || ksize == 7) && (dil == 1 || dil == 2) && (hd == 32 || hd == 64);

@@ -235,3 +235,27 @@ def test_tile_predictor_matches_window_by_window_reference_pipeline(dev, streami
 
 def test_window_load_division_is_correctly_rounded_for_every_int16_value(dev):
     cases.window_load_all_values_case(dev)
+
+
+def test_neighborhood_attention_key_side_pass_both_tilings(dev):
+    """The key-side backward pass has an image-tile and a sub-image-tile kernel (CNB_NA_DKV=img|group, read once per process); the
+    default picks per shape, so the other one is exercised here in a child process."""
+    import os
+    import subprocess
+    import sys
+
+    code = (
+        "import sys, torch; sys.path.insert(0, %r)\n"
+        "from cultionet_b200 import _lib\n"
+        "from tests.emu.build_emu import build\n"
+        "_lib.use_library(build())\n"
+        "from tests import cases\n"
+        "for cfg in [(1, 64, 3, 2, 21, 37), (1, 32, 7, 2, 33, 35), (2, 32, 3, 1, 19, 35)]:\n"
+        "    heads, hd, k, d, H, W = cfg\n"
+        "    cases.na_case('cpu', torch.bfloat16, 1, H, W, heads, hd, k, d)\n"
+        "print('ok')\n" % str(cases.__file__.rsplit('/tests/', 1)[0])
+    )
+    for variant in ("group", "img"):
+        env = dict(os.environ, CNB_NA_DKV=variant)
+        res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        assert res.returncode == 0 and "ok" in res.stdout, (variant, res.stderr[-2000:])
