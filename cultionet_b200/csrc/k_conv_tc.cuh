@@ -209,8 +209,12 @@ __device__ __forceinline__ float warp_transpose_sum32(float (&vals)[32]) {
 }
 
 __device__ __forceinline__ void decode_tile(const ConvTcParams& p, int tile, int bn, TileCoord& t) {
-    const int nt = tile / p.m_tiles;
-    int mt = tile - nt * p.m_tiles;
+    // the output-column tile is the FAST index: the CTAs that run side by side share one pixel tile, so its A operand comes from DRAM
+    // once and from L2 for the other column tiles (ncu, column tile slow: the 268 MB dY of the 256 -> 960 data gradient was read
+    // 4 x from DRAM, 1.08 GB)
+    const int n_tiles = p.num_tiles / p.m_tiles;
+    const int nt = tile % n_tiles;
+    int mt = tile / n_tiles;
     int ph = 0;
     while (ph + 1 < p.nphases && mt >= p.ph_tile0[ph + 1]) ++ph;
     mt -= p.ph_tile0[ph];
