@@ -695,7 +695,10 @@ static bool na_dkv_image_tiles(int ksize, int dilation) {
         return !e ? 0 : (e[0] == 'i' ? 1 : (e[0] == 'g' ? 2 : 0));
     }();
     if (forced) return forced == 1;
-    return dilation > 1;  // B200: image tiles win the key-side pass at every dilated shape (k3 d2 128^2: 1.20 vs 1.46 ms bwd; k7 d2 256^2: 12.9 vs 16.1)
+    (void)ksize, (void)dilation;
+    // B200: image tiles win the key-side pass at every shape measured (k3 d2 128^2: 1.20 vs 1.46 ms bwd; k7 d2 256^2: 12.9 vs 16.1;
+    // k3 d1 64^2: 0.36 vs 0.38) -- the sub-image kernel's run-time strides cost it registers (k7: 254 vs 128)
+    return true;
 }
 
 // launch a `template <typename T, int LPH>` tiled NA kernel
@@ -716,7 +719,25 @@ static bool na_dkv_image_tiles(int ksize, int dilation) {
         }                                                            \
     } while (0)
 
-// launch a `template <int KS, int DIL, int LPH>` specialised NA kernel (naf::eligible shapes only)
+// launch a specialised NA kernel (naf::eligible shapes only).  Query-side kernels (`template <int KS, int DIL, int LPH, int VPL>`): head_dim
+// 64 runs 4 lanes x 2 vectors, head_dim 32 runs 4 lanes x 1 vector.  Key-side kernels (`template <int KS, int DIL, int LPH>`): hd / 8 lanes.
+#define CNB_NAQ_LAUNCH_K(KERNEL, KSV, ...)                                                                               \
+    do {                                                                                                                 \
+        if (hd == 64) {                                                                                                  \
+            CNB_SET_SMEM((KERNEL<KSV, 1, 4, 2>), smem);                                                                  \
+            CNB_LAUNCH((KERNEL<KSV, 1, 4, 2>), grid, dim3(NA_TILE_THREADS), smem, (cudaStream_t)stream, __VA_ARGS__);    \
+        } else {                                                                                                         \
+            CNB_SET_SMEM((KERNEL<KSV, 1, 4, 1>), smem);                                                                  \
+            CNB_LAUNCH((KERNEL<KSV, 1, 4, 1>), grid, dim3(NA_TILE_THREADS), smem, (cudaStream_t)stream, __VA_ARGS__);    \
+        }                                                                                                                \
+    } while (0)
+#define CNB_NAQ_LAUNCH(KERNEL, ...)                          \
+    do {                                                     \
+        if (ksize == 3)                                      \
+            CNB_NAQ_LAUNCH_K(KERNEL, 3, __VA_ARGS__);        \
+        else                                                 \
+            CNB_NAQ_LAUNCH_K(KERNEL, 7, __VA_ARGS__);        \
+    } while (0)
 #define CNB_NAF_LAUNCH_KDL(KERNEL, KSV, DILV, LPHV, ...)                                                             \
     do {                                                                                                             \
         CNB_SET_SMEM((KERNEL<KSV, DILV, LPHV>), smem);                                                               \
@@ -768,7 +789,7 @@ int cnb_na2d_fwd(const void* qkv, void* out, float* lse, int B, int H, int W, in
     if (lse && cnb_aligned16(qkv) && cnb_aligned16(out) && naf::eligible(hd, ksize, dilation, dtype)) {
         dim3 grid;
         if (naf_tile_setup(B, H, W, heads, hd, ksize, dilation, scale, &g, &lph, &smem, &grid)) {
-            CNB_NAF_LAUNCH(naf::na2d_fwd_fast_kernel, (const bf16_t*)qkv, (bf16_t*)out, lse, g);
+            CNB_NAQ_LAUNCH(naf::na2d_fwd_fast_kernel, (const bf16_t*)qkv, (bf16_t*)out, lse, g);
             CNB_CHECK_LAUNCH("na2d_fwd_fast_kernel");
             return CNB_OK;
         }
@@ -840,7 +861,7 @@ int cnb_na2d_bwd(const void* qkv, const void* dout, const void* out, const float
         dim3 grid;
         if (naf_tile_setup(B, H, W, heads, hd, ksize, dilation, scale, &g, &lph, &smem, &grid)) {
             // the staged rows are k|v (query pass) or q|dout (key pass)
-            CNB_NAF_LAUNCH(naf::na2d_bwd_dq_fast_kernel, (const bf16_t*)qkv, (const bf16_t*)dout, (const bf16_t*)out, lse, (uint32_t*)pds_ws,
+            CNB_NAQ_LAUNCH(naf::na2d_bwd_dq_fast_kernel, (const bf16_t*)qkv, (const bf16_t*)dout, (const bf16_t*)out, lse, (uint32_t*)pds_ws,
                            (bf16_t*)dqkv, g);
             // key side: sub-image tiles, or image-space tiles (the query records are indexed by image pixel: the two passes may tile
             // differently); CNB_NA_DKV=img|group overrides the default

@@ -131,11 +131,22 @@ __device__ __forceinline__ void stage_region(bf16_t* sm, const bf16_t* a_base, l
 // ---------------------------------------------------------------------------------------------------------------------
 // forward: out_i = softmax_n(scale q_i . k_n) v_n, lse_i
 // ---------------------------------------------------------------------------------------------------------------------
-template <int KS, int DIL, int LPH>
+// VPL = 16-byte vectors per lane: a (pixel, head) is shared by LPH = HD / (8 VPL) lanes.  VPL = 2 for head_dim 64 halves the lanes per
+// group: one shuffle step and half of the redundant exponentials / logit arithmetic per neighbour disappear (the kernels are
+// issue-bound: ~27 instructions per lane and neighbour at VPL = 1, of which 3 shuffles + 3 adds + the exponential are per-lane
+// overhead).  Lane `sub` of an even pixel holds channel chunks {sub, LPH + sub}, of an odd pixel {LPH + sub, sub}: the two groups of a
+// quarter-warp then read different 64-byte halves of their 128-byte rows -- conflict-free 16-byte shared-memory loads.
+template <int LPH, int VPL>
+__device__ __forceinline__ void lane_chunks(int sub, int pl, int (&off)[VPL]) {
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) off[v] = (((VPL > 1 ? (v ^ (pl & 1)) : v) * LPH) + sub) * 8;
+}
+
+template <int KS, int DIL, int LPH, int VPL>
 __global__ void __launch_bounds__(NA_TILE_THREADS) na2d_fwd_fast_kernel(const bf16_t* __restrict__ qkv, bf16_t* __restrict__ out,
                                                                        float* __restrict__ lse, NaTile g) {
     CNB_PDL_SYNC();
-    constexpr int HD = LPH * 8, K2 = KS * KS;
+    constexpr int HD = LPH * 8 * VPL, K2 = KS * KS;
     CNB_DYN_SMEM(sm_raw);
     bf16_t* sm = reinterpret_cast<bf16_t*>(sm_raw);
     static_assert(DIL == 1, "dilation is handled by the sub-image decomposition (tile_pos)");
@@ -156,16 +167,24 @@ __global__ void __launch_bounds__(NA_TILE_THREADS) na2d_fwd_fast_kernel(const bf
         // out-of-image lanes shadow the last pixel of the sub-image (it lies in this tile): control flow and shuffles stay uniform
         const int y = (t.y0 + ly) < t.H ? t.y0 + ly : t.H - 1, x = (t.x0 + lx) < t.W ? t.x0 + lx : t.W - 1;
         const long pix = t.img_pix0 + y * t.rs + x * t.cs;
-        const uint4 qraw = *reinterpret_cast<const uint4*>(qkv + pix * 3 * C + t.head * HD + sub * 8);
+        int off[VPL];
+        lane_chunks<LPH, VPL>(sub, pl, off);
+        uint4 qraw[VPL];
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) qraw[v] = *reinterpret_cast<const uint4*>(qkv + pix * 3 * C + t.head * HD + off[v]);
         const int sy = wstart<1>(y, t.H, KS, 1), sx = wstart<1>(x, t.W, KS, 1);
-        const bf16_t* kb = sm + ((sy - t.ry0) * t.RW + (sx - t.rx0)) * 2 * HD + sub * 8;
+        const bf16_t* kb = sm + ((sy - t.ry0) * t.RW + (sx - t.rx0)) * 2 * HD;
         float lg[K2];
         float m = -INFINITY;
 #pragma unroll
         for (int a = 0; a < KS; ++a)
 #pragma unroll
             for (int b = 0; b < KS; ++b) {
-                const float s = g.scale * gsum<LPH>(dot8p(qraw, *reinterpret_cast<const uint4*>(kb + a * row_step + b * col_step)));
+                float part = 0.f;
+#pragma unroll
+                for (int v = 0; v < VPL; ++v)
+                    part += dot8p(qraw[v], *reinterpret_cast<const uint4*>(kb + a * row_step + b * col_step + off[v]));
+                const float s = g.scale * gsum<LPH>(part);
                 lg[a * KS + b] = s;
                 m = fmaxf(m, s);
             }
@@ -175,20 +194,29 @@ __global__ void __launch_bounds__(NA_TILE_THREADS) na2d_fwd_fast_kernel(const bf
             lg[n] = cnb_exp(lg[n] - m);
             l += lg[n];
         }
-        float o[8];
+        float o[VPL][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = 0.f;
+        for (int v = 0; v < VPL; ++v)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[v][j] = 0.f;
         // the un-normalised probabilities (in (0, 1]) weight v as bf16, like the P operand of a tensor-core attention kernel
 #pragma unroll
         for (int a = 0; a < KS; ++a)
 #pragma unroll
-            for (int b = 0; b < KS; ++b)
-                axpy8p<false>(cnb_pack_bf16x2(lg[a * KS + b], 0.f), *reinterpret_cast<const uint4*>(kb + a * row_step + b * col_step + HD), o);
+            for (int b = 0; b < KS; ++b) {
+                const uint32_t w = cnb_pack_bf16x2(lg[a * KS + b], 0.f);
+#pragma unroll
+                for (int v = 0; v < VPL; ++v)
+                    axpy8p<false>(w, *reinterpret_cast<const uint4*>(kb + a * row_step + b * col_step + HD + off[v]), o[v]);
+            }
         if (valid) {
             const float inv = 1.0f / l;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] *= inv;
-            cnb_stv(out + pix * C + t.head * HD + sub * 8, o);
+            for (int v = 0; v < VPL; ++v) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[v][j] *= inv;
+                cnb_stv(out + pix * C + t.head * HD + off[v], o[v]);
+            }
             if (sub == 0) lse[pix * g.heads + t.head] = m + logf(l);
         }
     }
@@ -197,12 +225,12 @@ __global__ void __launch_bounds__(NA_TILE_THREADS) na2d_fwd_fast_kernel(const bf
 // ---------------------------------------------------------------------------------------------------------------------
 // backward, query side: dq_i (into the q third of dqkv) and pds[(pix*heads + head)*K2 + n] = (p_in, scale p_in (dp_in - D_i))
 // ---------------------------------------------------------------------------------------------------------------------
-template <int KS, int DIL, int LPH>
+template <int KS, int DIL, int LPH, int VPL>
 __global__ void __launch_bounds__(NA_TILE_THREADS) na2d_bwd_dq_fast_kernel(const bf16_t* __restrict__ qkv, const bf16_t* __restrict__ dout,
                                                                           const bf16_t* __restrict__ out, const float* __restrict__ lse,
                                                                           uint32_t* __restrict__ pds, bf16_t* __restrict__ dqkv, NaTile g) {
     CNB_PDL_SYNC();
-    constexpr int HD = LPH * 8, K2 = KS * KS;
+    constexpr int HD = LPH * 8 * VPL, K2 = KS * KS;
     CNB_DYN_SMEM(sm_raw);
     bf16_t* sm = reinterpret_cast<bf16_t*>(sm_raw);
     static_assert(DIL == 1, "dilation is handled by the sub-image decomposition (tile_pos)");
@@ -222,32 +250,53 @@ __global__ void __launch_bounds__(NA_TILE_THREADS) na2d_bwd_dq_fast_kernel(const
         const bool valid = (t.y0 + ly) < t.H && (t.x0 + lx) < t.W;
         const int y = (t.y0 + ly) < t.H ? t.y0 + ly : t.H - 1, x = (t.x0 + lx) < t.W ? t.x0 + lx : t.W - 1;
         const long pix = t.img_pix0 + y * t.rs + x * t.cs;
-        const uint4 qraw = *reinterpret_cast<const uint4*>(qkv + pix * 3 * C + t.head * HD + sub * 8);
-        const uint4 graw = *reinterpret_cast<const uint4*>(dout + pix * C + t.head * HD + sub * 8);
-        const float D = gsum<LPH>(dot8p(graw, *reinterpret_cast<const uint4*>(out + pix * C + t.head * HD + sub * 8)));
+        int off[VPL];
+        lane_chunks<LPH, VPL>(sub, pl, off);
+        uint4 qraw[VPL], graw[VPL];
+        float dpart = 0.f;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            qraw[v] = *reinterpret_cast<const uint4*>(qkv + pix * 3 * C + t.head * HD + off[v]);
+            graw[v] = *reinterpret_cast<const uint4*>(dout + pix * C + t.head * HD + off[v]);
+            dpart += dot8p(graw[v], *reinterpret_cast<const uint4*>(out + pix * C + t.head * HD + off[v]));
+        }
+        const float D = gsum<LPH>(dpart);
         const float L = lse[pix * g.heads + t.head];
         const int sy = wstart<1>(y, t.H, KS, 1), sx = wstart<1>(x, t.W, KS, 1);
-        const bf16_t* kb = sm + ((sy - t.ry0) * t.RW + (sx - t.rx0)) * 2 * HD + sub * 8;
-        float dq[8];
+        const bf16_t* kb = sm + ((sy - t.ry0) * t.RW + (sx - t.rx0)) * 2 * HD;
+        float dq[VPL][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) dq[j] = 0.f;
+        for (int v = 0; v < VPL; ++v)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dq[v][j] = 0.f;
         uint32_t* rec = pds + (pix * g.heads + t.head) * K2;
 #pragma unroll
         for (int a = 0; a < KS; ++a)
 #pragma unroll
             for (int b = 0; b < KS; ++b) {
-                const uint4 kraw = *reinterpret_cast<const uint4*>(kb + a * row_step + b * col_step);
-                const uint4 vraw = *reinterpret_cast<const uint4*>(kb + a * row_step + b * col_step + HD);
-                const float s = g.scale * gsum<LPH>(dot8p(qraw, kraw)), dp = gsum<LPH>(dot8p(graw, vraw));
+                uint4 kraw[VPL];
+                float sp = 0.f, dpp = 0.f;
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) {
+                    kraw[v] = *reinterpret_cast<const uint4*>(kb + a * row_step + b * col_step + off[v]);
+                    const uint4 vraw = *reinterpret_cast<const uint4*>(kb + a * row_step + b * col_step + HD + off[v]);
+                    sp += dot8p(qraw[v], kraw[v]);
+                    dpp += dot8p(graw[v], vraw);
+                }
+                const float s = g.scale * gsum<LPH>(sp), dp = gsum<LPH>(dpp);
                 const float p = cnb_exp(s - L);
                 const float ds = p * (dp - D) * g.scale;
                 // record = (p, scale * ds) as one bf16 pair: the weights of this pass (ds, high half) and of the key-side pass
                 const uint32_t w = cnb_pack_bf16x2(p, ds);
-                axpy8p<true>(w, kraw, dq);
-                // the lanes of the group share the record: lane (n mod LPH) writes record n (36 contiguous bytes per group for k = 3)
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) axpy8p<true>(w, kraw[v], dq[v]);
+                // the lanes of the group share the record: lane (n mod LPH) writes record n (contiguous bytes per group)
                 if (valid && sub == (a * KS + b) % LPH) rec[a * KS + b] = w;
             }
-        if (valid) cnb_stv(dqkv + pix * 3 * C + t.head * HD + sub * 8, dq);  // ds already carries the scale
+        if (valid) {
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) cnb_stv(dqkv + pix * 3 * C + t.head * HD + off[v], dq[v]);  // ds already carries the scale
+        }
     }
 }
 

@@ -425,3 +425,39 @@ def test_tile_predictor_bf16_graph_streaming(dev):
 
 def test_window_load_division_is_correctly_rounded_for_every_int16_value(dev):
     cases.window_load_all_values_case(dev)
+
+
+def test_model_cfg1_exact_baseline_size_fp32(dev):
+    """BASELINE configs[0] at its exact size -- x=[4,3,12,100,100], hidden 32, fp32 forward + loss + backward -- against the oracle port:
+    outputs / loss 1e-3, every parameter gradient 5e-3, crop mask >= 99.9 % (north_star tolerances, tests/util.py)."""
+    cfg = dict(B=4, C=3, T=12, H=100, W=100, hidden=32, dilations=[1, 2], y_low=-1)
+    print("cfg1 exact fp32", cases.model_vs_port(dev, cfg, F32))
+
+
+def test_model_cfg2_geometry_bf16(dev):
+    """BASELINE configs[1] geometry (C=5, T=24, 128x128, hidden 64: every tcgen05 / TMA shape of the bench, levels 128 / 64 / 32 / 16) at
+    batch 4 in bf16 against the fp32 oracle port: outputs and loss within 2e-2."""
+    cfg = dict(B=4, C=5, T=24, H=128, W=128, hidden=64, dilations=[1, 2])
+    print("cfg2 geometry bf16", cases.model_vs_port(dev, cfg, BF16))
+
+
+def test_cfg2_full_size_eval_is_batch_split_invariant(dev):
+    """Size-independent property at BASELINE configs[1]'s FULL size (x=[32,5,24,128,128], hidden 64, bf16): in eval mode every sample is
+    independent, so predicting the batch of 32 equals predicting its quarters -- across different tile counts, wave shapes and
+    split factors of every kernel."""
+    import cultionet_b200 as cb
+
+    torch.manual_seed(11)
+    m = cb.TowerUNet(in_channels=5, in_time=24, hidden_channels=64, dilations=[1, 2], compute_dtype=BF16).to(dev).eval()
+    x = torch.rand(32, 5, 24, 128, 128, device=dev)
+    with torch.no_grad():
+        full = m(x)
+        for lo in (0, 8, 24):
+            part = m(x[lo:lo + 8].contiguous())
+            for k in ("distance", "edge", "crop"):
+                assert rel_err(part[k], full[k][lo:lo + 8]) < 2e-2, (k, lo)
+            agree = ((part["crop"] > 0.5) == (full["crop"][lo:lo + 8] > 0.5)).float().mean()
+            assert float(agree) >= 0.999
+    for k in ("distance", "edge", "crop"):
+        assert full[k].shape == (32, 1, 128, 128) and bool(torch.isfinite(full[k]).all())
+        assert float(full[k].min()) >= 0.0 and float(full[k].max()) <= 1.0
