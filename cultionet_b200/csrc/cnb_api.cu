@@ -874,13 +874,26 @@ int cnb_na2d_bwd(const void* qkv, const void* dout, const void* out, const float
                 (void)grid_g;
                 grid = dim3(B * gi.tiles_y * gi.tiles_x, heads);
                 smem = smem_i;
+#define CNB_NAK_IMG(KSV, DILV)                                                                                                          \
+    do {                                                                                                                                \
+        if (hd == 64) {                                                                                                                 \
+            CNB_SET_SMEM((naf::na2d_bwd_dkv_img_kernel<KSV, DILV, 4, 2>), smem);                                                        \
+            CNB_LAUNCH((naf::na2d_bwd_dkv_img_kernel<KSV, DILV, 4, 2>), grid, dim3(NA_TILE_THREADS), smem, (cudaStream_t)stream,        \
+                       (const bf16_t*)qkv, (const bf16_t*)dout, (const uint32_t*)pds_ws, (bf16_t*)dqkv, gi);                            \
+        } else {                                                                                                                        \
+            CNB_SET_SMEM((naf::na2d_bwd_dkv_img_kernel<KSV, DILV, 4, 1>), smem);                                                        \
+            CNB_LAUNCH((naf::na2d_bwd_dkv_img_kernel<KSV, DILV, 4, 1>), grid, dim3(NA_TILE_THREADS), smem, (cudaStream_t)stream,        \
+                       (const bf16_t*)qkv, (const bf16_t*)dout, (const uint32_t*)pds_ws, (bf16_t*)dqkv, gi);                            \
+        }                                                                                                                               \
+    } while (0)
                 if (dilation == 1) {
-                    if (ksize == 3) CNB_NAF_LAUNCH_KD(naf::na2d_bwd_dkv_img_kernel, 3, 1, (const bf16_t*)qkv, (const bf16_t*)dout, (const uint32_t*)pds_ws, (bf16_t*)dqkv, gi);
-                    else CNB_NAF_LAUNCH_KD(naf::na2d_bwd_dkv_img_kernel, 7, 1, (const bf16_t*)qkv, (const bf16_t*)dout, (const uint32_t*)pds_ws, (bf16_t*)dqkv, gi);
+                    if (ksize == 3) CNB_NAK_IMG(3, 1);
+                    else CNB_NAK_IMG(7, 1);
                 } else {
-                    if (ksize == 3) CNB_NAF_LAUNCH_KD(naf::na2d_bwd_dkv_img_kernel, 3, 2, (const bf16_t*)qkv, (const bf16_t*)dout, (const uint32_t*)pds_ws, (bf16_t*)dqkv, gi);
-                    else CNB_NAF_LAUNCH_KD(naf::na2d_bwd_dkv_img_kernel, 7, 2, (const bf16_t*)qkv, (const bf16_t*)dout, (const uint32_t*)pds_ws, (bf16_t*)dqkv, gi);
+                    if (ksize == 3) CNB_NAK_IMG(3, 2);
+                    else CNB_NAK_IMG(7, 2);
                 }
+#undef CNB_NAK_IMG
             } else {
                 CNB_NAF_LAUNCH(naf::na2d_bwd_dkv_fast_kernel, (const bf16_t*)qkv, (const bf16_t*)dout, (const uint32_t*)pds_ws, (bf16_t*)dqkv, g);
             }

@@ -435,12 +435,12 @@ __device__ __forceinline__ TilePosImg tile_pos_img(const NaTile& g) {
 // atomics, deterministic).  Region rows: q_i | dout_i.  A query clamped at the image border can sit up to (k-1)*d from its key,
 // i.e. outside the staged region of an interior-side tile: those few candidates are read from global memory.
 // ---------------------------------------------------------------------------------------------------------------------
-template <int KS, int DIL, int LPH>
+template <int KS, int DIL, int LPH, int VPL>
 __global__ void __launch_bounds__(NA_TILE_THREADS) na2d_bwd_dkv_img_kernel(const bf16_t* __restrict__ qkv, const bf16_t* __restrict__ dout,
                                                                            const uint32_t* __restrict__ pds, bf16_t* __restrict__ dqkv,
                                                                            NaTile g) {
     CNB_PDL_SYNC();
-    constexpr int HD = LPH * 8, K2 = KS * KS;
+    constexpr int HD = LPH * 8 * VPL, K2 = KS * KS;
     CNB_DYN_SMEM(sm_raw);
     bf16_t* sm = reinterpret_cast<bf16_t*>(sm_raw);
     const TilePosImg t = tile_pos_img(g);
@@ -467,9 +467,13 @@ __global__ void __launch_bounds__(NA_TILE_THREADS) na2d_bwd_dkv_img_kernel(const
         const int y = t.y0 + ly, x = t.x0 + lx;
         if (y >= g.H || x >= g.W) continue;  // no shuffles below: lanes may drop out
         const long pix = t.img_pix0 + (long)y * g.W + x;
-        float dk[8], dv[8];
+        int off[VPL];
+        lane_chunks<LPH, VPL>(sub, pl, off);
+        float dk[VPL][8], dv[VPL][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) dk[j] = 0.f, dv[j] = 0.f;
+        for (int v = 0; v < VPL; ++v)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dk[v][j] = 0.f, dv[v][j] = 0.f;
         // Interior keys (most of the image): no window that holds the key is clamped, so the queries are exactly the k x k pixels
         // (y + my*d, x + mx*d), |my|, |mx| <= k/2, the key sits at window position (k/2 - my, k/2 - mx) of each, and all of them lie
         // in the staged region: compile-time offsets, no window arithmetic (the generic path below spends ~60 integer instructions
@@ -477,7 +481,7 @@ __global__ void __launch_bounds__(NA_TILE_THREADS) na2d_bwd_dkv_img_kernel(const
         constexpr int HK = KS / 2;
         const int lim = (2 * HK + 1) * dil;
         if (y >= lim && y + lim < g.H && x >= lim && x + lim < g.W) {
-            const bf16_t* qb = sm + ((y - t.ry0) * g.RW + (x - t.rx0)) * 2 * HD + sub * 8;
+            const bf16_t* qb = sm + ((y - t.ry0) * g.RW + (x - t.rx0)) * 2 * HD;
             const uint32_t* rb = pds + (pix * g.heads + t.head) * K2;
             const long rec_row = (long)dil * g.W * g.heads * K2, rec_col = (long)dil * g.heads * K2;
             const int sm_row = dil * g.RW * 2 * HD, sm_col = dil * 2 * HD;
@@ -487,11 +491,17 @@ __global__ void __launch_bounds__(NA_TILE_THREADS) na2d_bwd_dkv_img_kernel(const
                 for (int mx = -HK; mx <= HK; ++mx) {
                     const uint32_t w = rb[my * rec_row + mx * rec_col + (HK - my) * KS + (HK - mx)];
                     const bf16_t* qp = qb + my * sm_row + mx * sm_col;
-                    axpy8p<true>(w, *reinterpret_cast<const uint4*>(qp), dk);
-                    axpy8p<false>(w, *reinterpret_cast<const uint4*>(qp + HD), dv);
+#pragma unroll
+                    for (int v = 0; v < VPL; ++v) {
+                        axpy8p<true>(w, *reinterpret_cast<const uint4*>(qp + off[v]), dk[v]);
+                        axpy8p<false>(w, *reinterpret_cast<const uint4*>(qp + HD + off[v]), dv[v]);
+                    }
                 }
-            cnb_stv(dqkv + pix * 3 * C + C + t.head * HD + sub * 8, dk);
-            cnb_stv(dqkv + pix * 3 * C + 2 * C + t.head * HD + sub * 8, dv);
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                cnb_stv(dqkv + pix * 3 * C + C + t.head * HD + off[v], dk[v]);
+                cnb_stv(dqkv + pix * 3 * C + 2 * C + t.head * HD + off[v], dv[v]);
+            }
             continue;
         }
         const uint32_t ymask = inverse_mask<KS, DIL>(y, g.H, g.dil), xmask = inverse_mask<KS, DIL>(x, g.W, g.dil);
@@ -515,21 +525,28 @@ __global__ void __launch_bounds__(NA_TILE_THREADS) na2d_bwd_dkv_img_kernel(const
                 const int rx = ix - t.rx0;
                 const long ipix = t.img_pix0 + (long)iy * g.W + ix;
                 const uint32_t w = pds[(ipix * g.heads + t.head) * K2 + arow * KS + bcol[mx]];  // bf16 pair (p, scale * ds)
-                uint4 qraw, graw;
-                if (ry >= 0 && ry < g.RH && rx >= 0 && rx < g.RW) {
-                    const bf16_t* qp = sm + (ry * g.RW + rx) * 2 * HD + sub * 8;
-                    qraw = *reinterpret_cast<const uint4*>(qp);
-                    graw = *reinterpret_cast<const uint4*>(qp + HD);
-                } else {
-                    qraw = *reinterpret_cast<const uint4*>(qkv + ipix * 3 * C + t.head * HD + sub * 8);
-                    graw = *reinterpret_cast<const uint4*>(dout + ipix * C + t.head * HD + sub * 8);
+                const bool staged = ry >= 0 && ry < g.RH && rx >= 0 && rx < g.RW;
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) {
+                    uint4 qraw, graw;
+                    if (staged) {
+                        const bf16_t* qp = sm + (ry * g.RW + rx) * 2 * HD + off[v];
+                        qraw = *reinterpret_cast<const uint4*>(qp);
+                        graw = *reinterpret_cast<const uint4*>(qp + HD);
+                    } else {
+                        qraw = *reinterpret_cast<const uint4*>(qkv + ipix * 3 * C + t.head * HD + off[v]);
+                        graw = *reinterpret_cast<const uint4*>(dout + ipix * C + t.head * HD + off[v]);
+                    }
+                    axpy8p<true>(w, qraw, dk[v]);
+                    axpy8p<false>(w, graw, dv[v]);
                 }
-                axpy8p<true>(w, qraw, dk);
-                axpy8p<false>(w, graw, dv);
             }
         }
-        cnb_stv(dqkv + pix * 3 * C + C + t.head * HD + sub * 8, dk);
-        cnb_stv(dqkv + pix * 3 * C + 2 * C + t.head * HD + sub * 8, dv);
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            cnb_stv(dqkv + pix * 3 * C + C + t.head * HD + off[v], dk[v]);
+            cnb_stv(dqkv + pix * 3 * C + 2 * C + t.head * HD + off[v], dv[v]);
+        }
     }
 }
 
