@@ -874,11 +874,13 @@ int cnb_na2d_bwd(const void* qkv, const void* dout, const void* out, const float
                 (void)grid_g;
                 grid = dim3(B * gi.tiles_y * gi.tiles_x, heads);
                 smem = smem_i;
+// (two vectors per lane were measured for this pass too: k7 d2 256^2 backward 10.5 -> 15.3 ms -- the scattered 4-byte record loads
+// are its latency-critical part and halving the lanes halves how many are in flight; it stays at one vector per lane)
 #define CNB_NAK_IMG(KSV, DILV)                                                                                                          \
     do {                                                                                                                                \
         if (hd == 64) {                                                                                                                 \
-            CNB_SET_SMEM((naf::na2d_bwd_dkv_img_kernel<KSV, DILV, 4, 2>), smem);                                                        \
-            CNB_LAUNCH((naf::na2d_bwd_dkv_img_kernel<KSV, DILV, 4, 2>), grid, dim3(NA_TILE_THREADS), smem, (cudaStream_t)stream,        \
+            CNB_SET_SMEM((naf::na2d_bwd_dkv_img_kernel<KSV, DILV, 8, 1>), smem);                                                        \
+            CNB_LAUNCH((naf::na2d_bwd_dkv_img_kernel<KSV, DILV, 8, 1>), grid, dim3(NA_TILE_THREADS), smem, (cudaStream_t)stream,        \
                        (const bf16_t*)qkv, (const bf16_t*)dout, (const uint32_t*)pds_ws, (bf16_t*)dqkv, gi);                            \
         } else {                                                                                                                        \
             CNB_SET_SMEM((naf::na2d_bwd_dkv_img_kernel<KSV, DILV, 4, 1>), smem);                                                        \
