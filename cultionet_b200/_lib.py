@@ -49,6 +49,7 @@ class ConvDesc(C.Structure):
         ("out_seg", C.c_void_p * CNB_MAX_SRC),
         ("out_seg_c", C.c_int32 * CNB_MAX_SRC),
         ("out_seg_stride", C.c_int32 * CNB_MAX_SRC),
+        ("ep_scale", C.c_void_p), ("ep_shift", C.c_void_p), ("ep_act", C.c_int32),
     ]
 
 

@@ -116,6 +116,7 @@ int cnb_conv2d_fwd_generic(const cnb_conv_desc* d, int dtype, void* stream) {
     int rc = check_conv_desc(d);
     if (rc) return rc;
     CNB_REQUIRE(d->stats == nullptr, "conv2d_fwd_generic: fused BatchNorm statistics exist only in the tcgen05 kernel");
+    if (d->ep_scale) CNB_FAIL(CNB_ERR_UNSUPPORTED, "conv2d_fwd_generic: the fused BatchNorm/activation epilogue exists only in the tcgen05 kernel");
     CNB_REQUIRE(d->nout == 0, "conv2d_fwd_generic: split outputs exist only in the tcgen05 kernel");
     const long M = (long)d->B * d->Hout * d->Wout;
     dim3 grid(cnb_div_up(M, CG_BM), cnb_div_up(d->N, CG_BN));
@@ -158,6 +159,7 @@ int cnb_conv2d_fwd_tiny(const cnb_conv_desc* d, int dtype, void* stream) {
     if (rc) return rc;
     if (!conv_tiny_eligible(d)) CNB_FAIL(CNB_ERR_UNSUPPORTED, "conv2d_fwd_tiny: needs N <= %d and at most %d input channels", TINY_MAX_N, TINY_MAX_C);
     CNB_REQUIRE(d->stats == nullptr, "conv2d_fwd_tiny: fused BatchNorm statistics exist only in the tcgen05 kernel");
+    if (d->ep_scale) CNB_FAIL(CNB_ERR_UNSUPPORTED, "conv2d_fwd_tiny: the fused BatchNorm/activation epilogue exists only in the tcgen05 kernel");
     int ctot = 0;
     for (int s = 0; s < d->nsrc; ++s) ctot += d->src_c[s];
     const long M = (long)d->B * d->Hout * d->Wout;
@@ -181,7 +183,7 @@ int cnb_conv2d_fwd_tiny(const cnb_conv_desc* d, int dtype, void* stream) {
 }
 
 int cnb_conv2d_fwd(const cnb_conv_desc* d, int dtype, void* stream) {
-    if (d && d->stats) return cnb_conv2d_fwd_tc(d, dtype, stream);
+    if (d && (d->stats || d->ep_scale)) return cnb_conv2d_fwd_tc(d, dtype, stream);
     if (check_conv_desc(d) == CNB_OK && d->nout == 0 && conv_tiny_eligible(d)) return cnb_conv2d_fwd_tiny(d, dtype, stream);
     if (cnb_conv2d_tc_eligible(d, dtype)) return cnb_conv2d_fwd_tc(d, dtype, stream);
     return cnb_conv2d_fwd_generic(d, dtype, stream);

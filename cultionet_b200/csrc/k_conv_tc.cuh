@@ -59,6 +59,9 @@ struct ConvTcParams {
     bf16_t* out;
     int out_stride;
     const float* bias;
+    const float* ep_scale;  // fused inference epilogue (cnb_conv_desc::ep_scale / ep_shift / ep_act), or NULL
+    const float* ep_shift;
+    int ep_act;
     float* stats;  // optional [2*N]: per-output-channel sum and sum of squares of the STORED (bf16-rounded) outputs, for BatchNorm
     // split output (cnb_conv_desc::nout): columns [seg_begin[i], seg_begin[i+1]) of the GEMM go to seg_out[i]; boundaries are
     // multiples of 32, so every 32-column epilogue chunk has one destination
@@ -386,7 +389,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                     while (sg + 1 < p.nseg && col0 >= p.seg_begin[sg + 1]) ++sg;
                     ochunk = p.seg_out[sg] + opix * p.seg_stride[sg] + (col0 - p.seg_begin[sg]);
                 }
-                if (p.vec_ok && col0 + 32 <= p.N) {
+                if (p.ep_scale && p.vec_ok && col0 + 32 <= p.N) {
+                    // eval-mode BatchNorm (+ SiLU) on the fp32 accumulator: the convolution output never exists un-normalised
+                    uint32_t packed[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float f0 = fmaf(has_taps ? __uint_as_float(v[2 * j]) : 0.f, __ldg(p.ep_scale + col0 + 2 * j), __ldg(p.ep_shift + col0 + 2 * j));
+                        float f1 = fmaf(has_taps ? __uint_as_float(v[2 * j + 1]) : 0.f, __ldg(p.ep_scale + col0 + 2 * j + 1),
+                                        __ldg(p.ep_shift + col0 + 2 * j + 1));
+                        if (p.ep_act) f0 = cnb_silu_t<bf16_t>(f0), f1 = cnb_silu_t<bf16_t>(f1);
+                        packed[j] = cnb_pack_bf16x2(f0, f1);
+                    }
+                    uint4* dst = reinterpret_cast<uint4*>(ochunk);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                } else if (p.vec_ok && col0 + 32 <= p.N) {
                     uint32_t packed[16];
                     if (p.bias) {
 #pragma unroll
@@ -409,6 +426,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                         if (col0 + j < p.N) {
                             float f = has_taps ? __uint_as_float(v[j]) : 0.f;
                             if (p.bias) f += __ldg(p.bias + col0 + j);
+                            if (p.ep_scale) {
+                                f = fmaf(f, __ldg(p.ep_scale + col0 + j), __ldg(p.ep_shift + col0 + j));
+                                if (p.ep_act) f = cnb_silu_t<bf16_t>(f);
+                            }
                             ochunk[j] = __float2bfloat16(f);
                         }
                     }
@@ -692,6 +713,8 @@ inline int conv_tc_launch(const cnb_conv_desc* d, cudaStream_t stream) {
     p.out = reinterpret_cast<bf16_t*>(d->out);
     p.out_stride = d->out_stride;
     p.bias = d->bias;
+    p.ep_scale = d->ep_scale, p.ep_shift = d->ep_shift, p.ep_act = d->ep_act;
+    if (d->ep_scale && (!d->ep_shift || d->bias || d->nout > 0 || d->stats)) return 3;
     p.vec_ok = (d->out_stride % 8 == 0 && reinterpret_cast<uintptr_t>(d->out) % 16 == 0) ? 1 : 0;
     p.nseg = d->nout;
     if (d->nout > 0) {

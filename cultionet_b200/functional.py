@@ -169,7 +169,7 @@ MERGE_SOURCE_DGRADS = os.environ.get("CNB_MERGE_DGRAD", "1") != "0"  # data grad
 
 
 def _launch_conv(sources, src_channels, wp, w_row_off, w_row_stride, w_tap_stride, N, bias, out, geom, transposed, dtype,
-                 want_stats=False, out_segments=None):
+                 want_stats=False, out_segments=None, epilogue=None):
     """Launches the convolution; with ``want_stats`` returns the [2, N] fp32 BatchNorm partial sums the tcgen05 epilogue produced
     (None when the shape takes another kernel and the caller has to run ``cnb_bn_stats``)."""
     d = ConvDesc()
@@ -201,6 +201,13 @@ def _launch_conv(sources, src_channels, wp, w_row_off, w_row_stride, w_tap_strid
         out = out_segments[0][0]
         if not (CONV_BACKEND != "generic" and not _lib.is_emulator() and _lib.lib().cnb_conv2d_tc_eligible(C.byref(d), dtype_code(dtype))):
             return False
+    if epilogue is not None:  # (scale, shift, act): eval-mode BatchNorm + activation in the tcgen05 epilogue; False when not available
+        if CONV_BACKEND == "generic" or _lib.is_emulator() or bias is not None or out_segments is not None:
+            return False
+        d.ep_scale, d.ep_shift, d.ep_act = epilogue[0].data_ptr(), epilogue[1].data_ptr(), int(epilogue[2])
+        d.stats = None
+        if not _lib.lib().cnb_conv2d_tc_eligible(C.byref(d), dtype_code(dtype)):
+            return False
     d.stats = None
     stats = None
     if want_stats and N <= STATS_MAX_N and CONV_BACKEND != "generic" and not _lib.is_emulator():
@@ -214,7 +221,7 @@ def _launch_conv(sources, src_channels, wp, w_row_off, w_row_stride, w_tap_strid
     if _lib.TIMER is not None and out_segments is not None:
         detail = detail.replace(f"->{N} ", "->" + "+".join(str(c) for _, c in out_segments) + " ")
     call(_CONV_ENTRY[CONV_BACKEND], C.byref(d), dtype_code(dtype), stream_ptr(out), flops=flops, tag="conv_fwd/dgrad", detail=detail)
-    return True if out_segments is not None else stats
+    return True if (out_segments is not None or epilogue is not None) else stats
 
 
 # With DIRECT_PARAM_GRAD the weight / bias gradient kernels accumulate straight into ``param.grad`` (the flat gradient buffer of
@@ -463,6 +470,43 @@ def conv2d(sources: Sequence[torch.Tensor], weight, bias=None, ksize=3, stride=1
     ``(y, sums)`` where ``sums`` is the ``[2, N]`` per-channel (sum, sum of squares) of ``y`` computed in the convolution epilogue,
     or an empty tensor when the shape took a kernel without that epilogue."""
     return _Conv2dFn.apply(weight, bias, W_CONV, ksize, stride, pad, dil, False, None, want_stats, None, *sources)
+
+
+FUSE_EVAL_EPILOGUE = os.environ.get("CNB_FUSE_EVAL", "1") != "0"
+_EVAL_FUSE_REJECTED: set = set()
+
+
+def conv2d_bn_act_eval(sources: Sequence[torch.Tensor], weight, gamma, beta, running_mean, running_var, eps: float, act: bool, ksize=3,
+                       stride=1, pad=1, dil=1) -> Optional[torch.Tensor]:
+    """Inference form of ``Conv2d(bias=False) -> BatchNorm2d(running statistics) -> [SiLU]`` (reference ``convolution.py:88-116``) as ONE
+    launch: the tcgen05 epilogue applies ``y = act(acc * scale + shift)`` to the fp32 accumulator.  No autograd (call under
+    ``torch.no_grad()``).  Returns ``None`` when the shape does not take the tcgen05 kernel (the caller runs the two-launch path)."""
+    if not FUSE_EVAL_EPILOGUE or torch.is_grad_enabled() or _lib.is_emulator():
+        return None
+    sources = [_contig(s) for s in sources]
+    x0 = sources[0]
+    if x0.dtype != torch.bfloat16:
+        return None
+    check_device(weight, *sources)
+    B, Hin, Win = x0.shape[0], x0.shape[1], x0.shape[2]
+    src_channels = [s.shape[-1] for s in sources]
+    Ctot, N, taps = sum(src_channels), weight.shape[0], ksize * ksize
+    Hout, Wout = _conv_out_size(Hin, ksize, stride, pad, dil), _conv_out_size(Win, ksize, stride, pad, dil)
+    shape_key = (B, Hin, Win, tuple(s.shape[-1] for s in sources), N, ksize, stride, pad, dil)
+    if shape_key in _EVAL_FUSE_REJECTED:
+        return None
+    wp, _ = packed_weights(weight, W_CONV, N, Ctot, taps, x0.dtype, False)
+    stats = torch.empty((6, N), dtype=torch.float32, device=x0.device)
+    call("cnb_bn_finalize", None, 1, N, ptr(gamma), ptr(beta), eps, 0.0, ptr(running_mean), ptr(running_var), ptr(stats[2]),
+         ptr(stats[3]), ptr(stats[4]), ptr(stats[5]), stream_ptr(x0))
+    out = torch.empty((B, Hout, Wout, N), dtype=x0.dtype, device=x0.device)
+    geom = (B, Hin, Win, Hout, Wout, ksize, ksize, stride, pad, dil)
+    ok = _launch_conv(sources, src_channels, wp, 0, wp.shape[2], N * wp.shape[2], N, None, out, geom, False, x0.dtype,
+                      epilogue=(stats[4], stats[5], act))
+    if not ok:
+        _EVAL_FUSE_REJECTED.add(shape_key)  # this shape takes another kernel: do not try again
+        return None
+    return out
 
 
 def conv_transpose2d(x: torch.Tensor, weight, bias=None, ksize=3, stride=2, pad=1, dil=1) -> torch.Tensor:

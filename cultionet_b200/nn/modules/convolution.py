@@ -108,6 +108,13 @@ class ConvBlock2d(nn.Module):
         if self.batchnorm_first:
             return self._forward_bn_first(_as_sources(x))
         conv, bn = self.seq[0], self.seq[1]
+        if not bn.training and not torch.is_grad_enabled():
+            # inference: BatchNorm (running statistics) and SiLU ride in the convolution epilogue -- one launch, one write
+            y = F.conv2d_bn_act_eval(_as_sources(x), conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps,
+                                     self.add_activation, ksize=conv.kernel_size[0], stride=conv.stride[0], pad=conv.padding[0],
+                                     dil=conv.dilation[0])
+            if y is not None:
+                return y
         # in training mode the tcgen05 convolution epilogue also produces BatchNorm's per-channel sums (no separate statistics pass)
         y = F.conv2d(_as_sources(x), conv.weight, None, ksize=conv.kernel_size[0], stride=conv.stride[0], pad=conv.padding[0],
                      dil=conv.dilation[0], want_stats=bn.training)

@@ -73,6 +73,14 @@ typedef struct {
     void* out_seg[CNB_MAX_SRC];
     int32_t out_seg_c[CNB_MAX_SRC];
     int32_t out_seg_stride[CNB_MAX_SRC];
+    /* Fused epilogue for inference (ConvBlock2d in eval mode, convolution.py:88-116: Conv2d -> BatchNorm2d(running statistics) -> [SiLU]):
+     *   y[n] = act(acc[n] * ep_scale[n] + ep_shift[n]),  ep_scale = gamma * rsqrt(var + eps), ep_shift = beta - mean * ep_scale
+     * (fp32 [N] each, as cnb_bn_finalize produces them), ep_act: 0 = identity, 1 = SiLU.  ep_scale == NULL: off.  The normalised
+     * activation is written once instead of conv out -> read -> write.  Only the tcgen05 kernel implements it (bias must be NULL,
+     * single output); the other kernels return CNB_ERR_UNSUPPORTED. */
+    const float* ep_scale;
+    const float* ep_shift;
+    int32_t ep_act;
 } cnb_conv_desc;
 
 /* picks the tiny-channel kernel, else the tcgen05/TMA kernel when cnb_conv2d_tc_eligible(), else the CUDA-core kernel */

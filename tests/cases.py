@@ -626,3 +626,26 @@ def tile_predictor_case(dev, H=37, W=50, ws=12, pad=4, batch_windows=5, rank=0, 
     assert diff.max() <= tol, (int(diff.max()), int((diff > 0).sum()))
     assert got.any()
     return got
+
+
+def conv_bn_act_eval_case(dev, B, H, W, cins, cout, k, stride=1, act=True, seed=0):
+    """Inference epilogue fusion (cnb_conv_desc::ep_scale/ep_shift/ep_act): ONE tcgen05 launch == Conv2d -> BatchNorm2d(eval) -> [SiLU] of
+    torch in fp32 (bf16 tolerance), and == the two-launch path of this library."""
+    torch.manual_seed(seed)
+    dtype = torch.bfloat16
+    xs = [_mk((B, H, W, c), dev, dtype, grad=False) for c in cins]
+    w = torch.nn.Parameter(torch.randn(cout, sum(cins), k, k, device=dev) / (sum(cins) * k * k) ** 0.5)
+    gamma, beta = torch.rand(cout, device=dev) + 0.5, torch.randn(cout, device=dev) * 0.2
+    mean, var = torch.randn(cout, device=dev) * 0.3, torch.rand(cout, device=dev) + 0.3
+    pad = k // 2
+    with torch.no_grad():
+        fused = F.conv2d_bn_act_eval(xs, w, gamma, beta, mean, var, 1e-5, act, ksize=k, stride=stride, pad=pad, dil=1)
+        assert fused is not None, "the shape was expected to take the tcgen05 kernel"
+        y = F.conv2d(xs, w, None, ksize=k, stride=stride, pad=pad, dil=1)
+        two = F.batchnorm_act(y, gamma, beta, mean, var, False, eps=1e-5, act=act)
+        xr = torch.cat([_f(x) for x in xs], dim=-1).permute(0, 3, 1, 2)
+        ref = TF.batch_norm(TF.conv2d(xr, w, None, stride=stride, padding=pad), mean, var, gamma, beta, False, 0.0, 1e-5)
+        ref = (TF.silu(ref) if act else ref).permute(0, 2, 3, 1)
+    tol = _tol(dtype)
+    _check("fused eval epilogue vs torch", fused, ref, tol)
+    _check("fused eval epilogue vs two launches", fused, two, tol)

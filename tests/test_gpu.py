@@ -461,3 +461,16 @@ def test_cfg2_full_size_eval_is_batch_split_invariant(dev):
     for k in ("distance", "edge", "crop"):
         assert full[k].shape == (32, 1, 128, 128) and bool(torch.isfinite(full[k]).all())
         assert float(full[k].min()) >= 0.0 and float(full[k].max()) <= 1.0
+
+
+@pytest.mark.parametrize("cfg", [(2, 40, 40, [256], 256, 3, 1, True), (2, 33, 47, [64, 128, 256], 256, 3, 1, True), (2, 32, 32, [512], 256, 1, 1, False),
+                                 (2, 64, 64, [64], 128, 3, 2, False), (1, 20, 20, [96], 72, 3, 1, True)])
+def test_conv_batchnorm_activation_fused_eval_epilogue(dev, cfg):
+    cases.conv_bn_act_eval_case(dev, *cfg)
+
+
+def test_model_eval_mode_bf16_fused_epilogue(dev):
+    """Eval-mode bf16 model (every ConvBlock2d runs conv + BatchNorm + SiLU as one tcgen05 launch) against the fp32 oracle port."""
+    cfg = dict(B=2, C=5, T=12, H=140, W=140, hidden=32, dilations=[1, 2])
+    with torch.no_grad():
+        print("eval bf16", cases.model_vs_port(dev, cfg, BF16, training=False))
