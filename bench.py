@@ -173,7 +173,7 @@ def run_reference_arm(args, w: dict) -> None:
         "e2e": {"value": base["value"], "unit": "chips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_predict(args, w: dict) -> None:
@@ -301,14 +301,34 @@ def run_predict(args, w: dict) -> None:
                          "cnb_predict_pack": {"avg_launch_ms": ms_pack, "GBps": by_pack / 1e9 / (ms_pack / 1e3),
                                               "algorithmic_bytes": by_pack}},
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     sys.stdout.flush()
     torch.cuda.synchronize()
     os._exit(0)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def claim_stdout() -> None:
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to stdout when NCCL_DEBUG is
+    set): keep a private duplicate of fd 1 for the result line and point fd 1 at stderr for everything else."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main() -> None:
+    claim_stdout()
     args = parse_args()
     w = dict(WORKLOADS[args.workload])
     if args.batch:
@@ -524,7 +544,7 @@ def main() -> None:
             "model_tflops": 3 * w["fwd_gflop_per_chip"] * 1e9 * value / 1e12 if w["fwd_gflop_per_chip"] else None,
             "final_loss": float(losses[-1]),
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     # Leave without tearing the process group down: every collective of this run has completed (the timed regions end in barriers),
     # and destroying the NCCL communicators while captured CUDA graphs still reference them blocked for minutes on a 2-GPU box.
     sys.stdout.flush()
