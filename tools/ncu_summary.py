@@ -18,6 +18,8 @@ KEEP = {
     "launch__block_size": "block",
     "sm__warps_active.avg.pct_of_peak_sustained_active": "achieved_occupancy_pct",
     "smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_slots_busy_pct",
+    "dram__bytes.sum.per_second": "dram_bytes_per_second",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum": "smem_bank_conflicts",
 }
 UNIT = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6, "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 out = {}
