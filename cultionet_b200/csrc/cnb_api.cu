@@ -1144,8 +1144,9 @@ int cnb_tanimoto_fwd(const cnb_tanimoto_term* terms, int nterms, int B, int64_t 
     CNB_MEMSET_ASYNC(sums, 0, sizeof(double) * 4 * nterms * B, (cudaStream_t)stream);
     const int chunks = cnb_clamp_grid(cnb_div_up((long)cmax * HW, 256 * 8), cnb_div_up(4L * CNB_NUM_SMS, (long)B * nterms));
     CNB_LAUNCH(tanimoto_sums_kernel, dim3(chunks, B, nterms), dim3(256), 0, (cudaStream_t)stream, pack, B, (long)HW, sums);
-    CNB_LAUNCH(tanimoto_finalize_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, pack, nterms, B, (long)HW, smooth, depth,
-               (const double*)sums, coef, loss);
+    CNB_MEMSET_ASYNC(loss, 0, sizeof(float) * (1 + nterms), (cudaStream_t)stream);
+    CNB_LAUNCH(tanimoto_finalize_kernel, dim3(cnb_div_up((long)nterms * B, 256)), dim3(256), 0, (cudaStream_t)stream, pack, nterms, B, (long)HW,
+               smooth, depth, (const double*)sums, coef, loss);
     CNB_CHECK_LAUNCH("tanimoto_fwd");
     return CNB_OK;
 }

@@ -155,7 +155,8 @@ __device__ __forceinline__ void tanimoto_T(double P, double S, double eps, int d
     dS = -sc * (P + eps) * sum_a;
 }
 
-// one CTA; coef[(term*B+b)*4] = dloss/d{P, S, P', S'} folded with weight/(2B); loss[0] total, loss[1+term] per term
+// coef[(term*B+b)*4] = dloss/d{P, S, P', S'} folded with weight/(2B); loss[0] total, loss[1+term] per term (zeroed by the caller: one
+// CTA per 256 (term, sample) pairs adds its share -- a single CTA for B <= 85 with three terms, i.e. a fixed summation order there)
 __global__ void __launch_bounds__(256) tanimoto_finalize_kernel(TanimotoTerms terms, int nterms, int B, long HW, float smooth, int depth,
                                                                const double* __restrict__ sums, float* __restrict__ coef,
                                                                float* __restrict__ loss) {
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(256) tanimoto_finalize_kernel(TanimotoTerms te
     __shared__ double lsum[TN_MAX_TERMS];
     if (threadIdx.x < TN_MAX_TERMS) lsum[threadIdx.x] = 0.0;
     __syncthreads();
-    for (int i = threadIdx.x; i < nterms * B; i += blockDim.x) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nterms * B; i += gridDim.x * blockDim.x) {
         const int term = i / B;
         const double N = (double)terms.t[term].C * (double)HW;
         const double P = sums[i * 4 + 0], S = sums[i * 4 + 1], St = sums[i * 4 + 2], Sp = sums[i * 4 + 3];
@@ -183,10 +184,10 @@ __global__ void __launch_bounds__(256) tanimoto_finalize_kernel(TanimotoTerms te
     if (threadIdx.x == 0) {
         double tot = 0.0;
         for (int t = 0; t < nterms; ++t) {
-            loss[1 + t] = (float)lsum[t];
+            atomicAdd(&loss[1 + t], (float)lsum[t]);
             tot += (double)terms.t[t].weight * lsum[t];
         }
-        loss[0] = (float)tot;
+        atomicAdd(&loss[0], (float)tot);
     }
 }
 
