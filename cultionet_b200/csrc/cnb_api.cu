@@ -953,12 +953,21 @@ int cnb_resize_bilinear_bwd(const void* dy, void* dx, int B, int Hin, int Win, i
     const long total = (long)B * Hin * Win * C;
     const float rh_ = align_corners_scale(Hin, Hout), rw_ = align_corners_scale(Win, Wout);
     if (C % vec_width(dtype) == 0 && cnb_aligned16(dy) && cnb_aligned16(dx) && rh_ >= 0.5f && rw_ >= 0.5f && Win <= 4096) {
-        // scale >= 0.5: at most RB_NC outputs read an input index per axis (support of length 2/scale <= 4)
-        const size_t smem = (size_t)Win * (1 + RB_NC) * 4 + (1 + RB_NC) * 4;
+        // scale >= 0.5: at most RB_NC = 5 outputs read an input index per axis (support of length 2/scale <= 4); scale >= 0.7 (the
+        // ConvTranspose fix-up, scale ~ 1): at most 3
+        const bool near1 = rh_ >= 0.7f && rw_ >= 0.7f;
+        const int nc = near1 ? RB_NC_NEAR1 : RB_NC;
+        const size_t smem = (size_t)Win * (1 + nc) * 4 + (1 + nc) * 4;
         CNB_DISPATCH_DTYPE(dtype, {
-            CNB_SET_SMEM((resize_bilinear_bwd_tab_kernel<T>), smem);
-            CNB_LAUNCH((resize_bilinear_bwd_tab_kernel<T>), dim3(B * Hin), dim3(256), smem, (cudaStream_t)stream, (const T*)dy, (T*)dx, B, Hin,
-                       Win, Hout, Wout, C, rh_, rw_);
+            if (near1) {
+                CNB_SET_SMEM((resize_bilinear_bwd_tab_kernel<T, RB_NC_NEAR1>), smem);
+                CNB_LAUNCH((resize_bilinear_bwd_tab_kernel<T, RB_NC_NEAR1>), dim3(B * Hin), dim3(256), smem, (cudaStream_t)stream, (const T*)dy,
+                           (T*)dx, B, Hin, Win, Hout, Wout, C, rh_, rw_);
+            } else {
+                CNB_SET_SMEM((resize_bilinear_bwd_tab_kernel<T, RB_NC>), smem);
+                CNB_LAUNCH((resize_bilinear_bwd_tab_kernel<T, RB_NC>), dim3(B * Hin), dim3(256), smem, (cudaStream_t)stream, (const T*)dy, (T*)dx, B,
+                           Hin, Win, Hout, Wout, C, rh_, rw_);
+            }
         });
         CNB_CHECK_LAUNCH("resize_bilinear_bwd_tab_kernel");
         return CNB_OK;

@@ -259,15 +259,27 @@ __global__ void __launch_bounds__(256) time_to_pixel_major_kernel(const float* _
     const int groups = pitch / V;
     for (long p0 = (long)blockIdx.x * TP_PIX; p0 < total; p0 += (long)gridDim.x * TP_PIX) {
         __syncthreads();  // the previous tile has left shared memory
-        for (int i = threadIdx.x; i < CT * TP_PIX; i += blockDim.x) {
-            const int pp = i % TP_PIX, ct = i / TP_PIX;
-            const long p = p0 + pp;
-            float v = 0.f;
-            if (p < total) {
-                const long b = p / HW, hw = p - b * HW;
-                v = x[(b * CT + ct) * HW + hw];
+        if (HW % TP_PIX == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+            // the tile lies inside one image: one division per tile, 16-byte loads (four pixels of one (channel, time) plane)
+            const long b = p0 / HW, hw0 = p0 - b * HW;
+            const float* xb = x + b * CT * HW + hw0;
+            for (int i = threadIdx.x; i < CT * (TP_PIX / 4); i += blockDim.x) {
+                const int q = i % (TP_PIX / 4), ct = i / (TP_PIX / 4);
+                const float4 v = *reinterpret_cast<const float4*>(xb + (long)ct * HW + q * 4);
+                float* d = xs + ct * TP_XPITCH + q * 4;
+                d[0] = v.x, d[1] = v.y, d[2] = v.z, d[3] = v.w;
             }
-            xs[ct * TP_XPITCH + pp] = v;
+        } else {
+            for (int i = threadIdx.x; i < CT * TP_PIX; i += blockDim.x) {
+                const int pp = i % TP_PIX, ct = i / TP_PIX;
+                const long p = p0 + pp;
+                float v = 0.f;
+                if (p < total) {
+                    const long b = p / HW, hw = p - b * HW;
+                    v = x[(b * CT + ct) * HW + hw];
+                }
+                xs[ct * TP_XPITCH + pp] = v;
+            }
         }
         __syncthreads();
         // thread = (pixel, column group): lanes walk pixels, so the xs reads are conflict-free

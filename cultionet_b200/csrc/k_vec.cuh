@@ -527,59 +527,62 @@ __global__ void __launch_bounds__(256) resize_bilinear_bwd_vec_kernel(const T* _
 // column) are computed once per CTA into shared memory, the y-axis support is CTA-uniform, and the streaming loop is
 // `table lookup + at most RB_NC^2 guarded 16-byte loads` (ncu on the generic gather kernel: 74 % issue-slot use, 2.0 TB/s, most of
 // it weight arithmetic for candidates whose weight is zero).
-constexpr int RB_NC = 5;
+constexpr int RB_NC = 5;       // scale >= 0.5
+constexpr int RB_NC_NEAR1 = 3; // scale >= 0.7: an input index is read by at most 3 outputs (support of length 2/scale < 3): the
+                               // ConvTranspose fix-up (2H-1 -> 2H) walks 9 candidates per vector instead of 25
 // tight support of input index i along one axis: first output index with a non-zero weight, and RB_NC weights from there
+template <int NC>
 __device__ __forceinline__ void bilinear_support(int i, float rscale, int in_len, int out_len, int& first, float* w) {
     int lo, hi;
     bilinear_candidates(i, rscale, out_len, lo, hi);
     first = lo;
     bool found = false;
 #pragma unroll
-    for (int a = 0; a < RB_NC; ++a) w[a] = 0.f;
+    for (int a = 0; a < NC; ++a) w[a] = 0.f;
     for (int o = lo; o <= hi; ++o) {
         const float wo = bilinear_weight(o, i, rscale, in_len);
         if (!found && wo != 0.f) {
             found = true;
             first = o;
         }
-        if (found && o - first < RB_NC) w[o - first] = wo;
+        if (found && o - first < NC) w[o - first] = wo;
     }
 }
 
-template <typename T>
+template <typename T, int NC>
 __global__ void __launch_bounds__(256) resize_bilinear_bwd_tab_kernel(const T* __restrict__ dy, T* __restrict__ dx, int B, int Hin, int Win,
                                                                      int Hout, int Wout, int C, float rh, float rw) {
     CNB_PDL_SYNC();
     constexpr int V = cnb_vec<T>::N;
-    CNB_DYN_SMEM(sm_raw);  // int xfirst[Win]; float wx[Win][RB_NC]; int yfirst; float wy[RB_NC]
+    CNB_DYN_SMEM(sm_raw);  // int xfirst[Win]; float wx[Win][NC]; int yfirst; float wy[NC]
     int* xfirst = reinterpret_cast<int*>(sm_raw);
     float* wxs = reinterpret_cast<float*>(xfirst + Win);
-    int* yfirst_s = reinterpret_cast<int*>(wxs + Win * RB_NC);
+    int* yfirst_s = reinterpret_cast<int*>(wxs + Win * NC);
     float* wys = reinterpret_cast<float*>(yfirst_s + 1);
     const int CV = C / V;
     const int iy = blockIdx.x % Hin;
     const int b = blockIdx.x / Hin;
     for (int ix = threadIdx.x; ix < Win; ix += blockDim.x) {
-        float w[RB_NC];
+        float w[NC];
         int f;
-        bilinear_support(ix, rw, Win, Wout, f, w);
+        bilinear_support<NC>(ix, rw, Win, Wout, f, w);
         xfirst[ix] = f;
 #pragma unroll
-        for (int a = 0; a < RB_NC; ++a) wxs[ix * RB_NC + a] = w[a];
+        for (int a = 0; a < NC; ++a) wxs[ix * NC + a] = w[a];
     }
     if (threadIdx.x == 0) {
-        float w[RB_NC];
+        float w[NC];
         int f;
-        bilinear_support(iy, rh, Hin, Hout, f, w);
+        bilinear_support<NC>(iy, rh, Hin, Hout, f, w);
         *yfirst_s = f;
 #pragma unroll
-        for (int a = 0; a < RB_NC; ++a) wys[a] = w[a];
+        for (int a = 0; a < NC; ++a) wys[a] = w[a];
     }
     __syncthreads();
     const int yfirst = *yfirst_s;
-    float wy[RB_NC];
+    float wy[NC];
 #pragma unroll
-    for (int a = 0; a < RB_NC; ++a) wy[a] = wys[a];
+    for (int a = 0; a < NC; ++a) wy[a] = wys[a];
     const T* base = dy + ((long)b * Hout + yfirst) * Wout * C;
     T* orow = dx + ((long)b * Hin + iy) * Win * C;
     const int n = Win * CV;
@@ -587,17 +590,17 @@ __global__ void __launch_bounds__(256) resize_bilinear_bwd_tab_kernel(const T* _
         const int ix = i / CV;
         const int c = (i - ix * CV) * V;
         const T* col = base + (long)xfirst[ix] * C + c;
-        float wx[RB_NC];
+        float wx[NC];
 #pragma unroll
-        for (int a = 0; a < RB_NC; ++a) wx[a] = wxs[ix * RB_NC + a];
+        for (int a = 0; a < NC; ++a) wx[a] = wxs[ix * NC + a];
         float acc[V];
 #pragma unroll
         for (int j = 0; j < V; ++j) acc[j] = 0.f;
 #pragma unroll
-        for (int a = 0; a < RB_NC; ++a) {
+        for (int a = 0; a < NC; ++a) {
             if (wy[a] == 0.f) continue;  // CTA-uniform
 #pragma unroll
-            for (int bb = 0; bb < RB_NC; ++bb) {
+            for (int bb = 0; bb < NC; ++bb) {
                 const float w = wy[a] * wx[bb];
                 if (w != 0.f) {
                     float v[V];

@@ -84,7 +84,7 @@ def test_resize_bilinear(dev, sizes):
     cases.resize_case(dev, F32, 2, *sizes, 3)
 
 
-@pytest.mark.parametrize("sizes", [(7, 7, 8, 8), (13, 13, 25, 25), (5, 9, 12, 10), (10, 10, 7, 7), (1, 1, 4, 4), (31, 17, 32, 33)])
+@pytest.mark.parametrize("sizes", [(7, 7, 8, 8), (13, 13, 25, 25), (5, 9, 12, 10), (10, 10, 7, 7), (1, 1, 4, 4), (31, 17, 32, 33), (8, 8, 11, 11), (15, 15, 21, 22)])
 def test_resize_bilinear_vector_kernels(dev, sizes):
     # channel counts that are whole 16-byte vectors: the row-per-CTA forward and the table-form / gather-form backward kernels
     cases.resize_case(dev, F32, 2, *sizes, 8)
@@ -106,6 +106,7 @@ def test_pretime_conv(dev, k):
 def test_pretime_conv_as_banded_gemm(dev, k):
     cases.pretime_gemm_case(dev, F32, 2, 3, 12, 5, 6, k)
     cases.pretime_gemm_case(dev, torch.bfloat16, 1, 5, 10, 9, 8, k)  # K = 50 -> pitch 56; 72 pixels = one full + one ragged tile
+    cases.pretime_gemm_case(dev, torch.bfloat16, 2, 3, 8, 8, 16, k)  # 128 pixels per image = whole 64-pixel tiles: the 16-byte load path
 
 
 @pytest.mark.parametrize("flags", [(True, True), (False, False)])
