@@ -192,3 +192,35 @@ def test_reference_layout_checkpoint_loads_and_reproduces_golden_outputs(dev, tm
     out = lit.cultionet_model.mask_model(x.to(dev))
     for k in ("distance", "edge", "crop"):
         assert rel_err(out[k][:, :, ::3, ::3], torch.from_numpy(z["out_" + k])) < TOL_OUT_FP32, k
+
+
+def test_predict_windows_geometry_of_a_sentinel2_tile():
+    """BASELINE configs[4]: a 10980 x 10980 tile in 100 px windows = 110 x 110 = 12 100 windows, the last row / column 80 px."""
+    from cultionet_b200.tile import predict_windows
+
+    win = predict_windows(10980, 10980, 100, 20)
+    assert win.shape == (12100, 4) and win.dtype.name == "int32"
+    assert tuple(win[0]) == (0, 0, 100, 100) and tuple(win[1]) == (0, 100, 100, 100)  # chunk order: x fastest
+    assert tuple(win[109]) == (0, 10900, 100, 80) and tuple(win[-1]) == (10900, 10900, 80, 80)
+    assert int((win[:, 2].astype("int64") * win[:, 3]).sum()) == 10980 * 10980  # the windows tile the image exactly
+    with pytest.raises(ValueError):
+        predict_windows(100, 100, 0, 20)
+
+
+def test_tile_and_checkpoint_argument_errors(dev, tmp_path):
+    from cultionet_b200 import model as M
+    from cultionet_b200.tile import WindowLoader
+
+    with pytest.raises(TypeError):
+        WindowLoader(torch.zeros(2, 2, 8, 8, dtype=torch.int32, device=dev), 4, 2)  # the tile is int16 (data/create.py:70-79)
+    with pytest.raises(ValueError):
+        WindowLoader(torch.zeros(2, 2, 8, 8, dtype=torch.int16, device=dev), 5, 2)  # window + halo must be whole 16-byte rows
+    with pytest.raises(ValueError):
+        WindowLoader(torch.zeros(2, 2, 8, 8, dtype=torch.int16, device=dev), 4, 2, (torch.zeros(3), torch.ones(3)))  # one mean / std per band
+    bad = tmp_path / "not_a_checkpoint.ckpt"
+    torch.save({"weights": {}}, bad)
+    with pytest.raises(KeyError):
+        M.load_from_checkpoint(bad)
+    torch.save({"state_dict": {}, "hyper_parameters": {}}, bad)
+    with pytest.raises(KeyError):
+        M.load_from_checkpoint(bad)  # no in_channels / in_time: must be passed as keyword arguments
