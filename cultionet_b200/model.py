@@ -16,6 +16,7 @@ from pathlib import Path
 from typing import Iterable, Optional, Union
 
 import torch
+import torch.distributed as dist
 
 from .data import Data
 from .engine import TrainStep, batch_to_device
@@ -75,6 +76,7 @@ def fit(lit_model: CultionetLitModel, train_batches, val_batches=None, epochs: i
     ``ckpt_file``.  An existing ``ckpt_file`` is resumed (weights, AdamW moments, step count, epoch).  Returns the history."""
     device = torch.device(device) if device is not None else next(lit_model.parameters()).device
     lit_model.to(device)
+    distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
     def iterate(src) -> Iterable[Data]:
         return src() if callable(src) else iter(src)
@@ -119,10 +121,18 @@ def fit(lit_model: CultionetLitModel, train_batches, val_batches=None, epochs: i
         history["val_score"].append(score)
         if log is not None:
             log(f"epoch {epoch}: loss {epoch_loss:.5f} val_score {score:.5f} lr {step.optimizer.current_lr():.5g}")
+        if distributed:  # every rank must take the same save decision: use the mean score of the ranks' validation shards
+            t = torch.tensor([score], dtype=torch.float64, device=device if device.type == "cuda" else "cpu")
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            score = float(t) / dist.get_world_size()
+            history["val_score"][-1] = score
         if ckpt_file is not None and score <= history["best_val_score"]:
             history["best_val_score"] = score
-            history["checkpoint"] = str(save_checkpoint(lit_model, ckpt_file, step.optimizer, epoch, global_step,
-                                                        best_val_score=score))
+            if not distributed or dist.get_rank() == 0:  # replicas are identical: one writer (Lightning's rank-zero-only checkpointing)
+                history["checkpoint"] = str(save_checkpoint(lit_model, ckpt_file, step.optimizer, epoch, global_step,
+                                                            best_val_score=score))
+            if distributed:
+                dist.barrier()
     return history
 
 
