@@ -148,3 +148,36 @@ def test_two_rank_tile_prediction_shards_windows_and_gathers_mosaic(tmp_path, de
     assert not torch.equal(r0["mine"], r1["mine"])
     assert int(((r0["mine"] != 0) & (r1["mine"] != 0)).sum()) == 0  # disjoint windows
     assert torch.equal(r0["full"], single)
+
+
+def _fit_worker(rank: int, world: int, port: int, out_dir: str):
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.set_num_threads(1)
+    _bind_emulator()
+    from cultionet_b200 import model as M
+    from cultionet_b200.parallel import init_distributed
+
+    init_distributed(backend="gloo")
+    lit = _model()
+    ckpt = Path(out_dir) / "ckpt" / "last.ckpt"
+    hist = M.fit(lit, [_batch(rank), _batch(rank + 10)], val_batches=[_batch(rank + 20)], epochs=1, ckpt_file=ckpt, device="cpu",
+                 cuda_graph=False)
+    flat = torch.cat([p.detach().reshape(-1) for p in lit.parameters()])
+    torch.save({"val_score": hist["val_score"], "checkpoint": hist["checkpoint"], "param": flat}, os.path.join(out_dir, f"fit{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_two_rank_fit_writes_one_checkpoint_with_a_common_score(tmp_path, dev):
+    """model.fit under a process group: replicas stay identical, the validation score is the mean over the ranks' shards (every rank
+    takes the same save decision) and only rank 0 writes the checkpoint (Lightning's rank-zero-only ModelCheckpoint)."""
+    world = 2
+    mp.spawn(_fit_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    r0, r1 = (torch.load(tmp_path / f"fit{r}.pt") for r in range(world))
+    assert torch.equal(r0["param"], r1["param"])
+    assert r0["val_score"] == r1["val_score"]
+    assert r0["checkpoint"] is not None and r1["checkpoint"] is None
+    ck = torch.load(r0["checkpoint"], weights_only=False)
+    assert ck["epoch"] == 0 and ck["optimizer_states"][0]["step"] == 2
