@@ -12,11 +12,14 @@ data-parallel gradient all-reduce + AdamW, through the reference-facing API (``C
   roofline  the dominant kernel class (implicit-GEMM convolution: fwd/dgrad/wgrad launches) timed per launch with CUDA events
             on the launching stream in a separate instrumented pass: algorithmic FLOPs / summed launch time vs the measured
             bf16 peak in MEASURED_PEAKS.json
-  cpu_baseline  the oracle port (oracle/towerunet_port.py: the reference's arithmetic in plain PyTorch fp32) on the host cores,
-            rank 0, N=1 only, on a bounded sample (batch 1 of the same chip shape)
+  cpu_baseline  the UNMODIFIED reference modules (``baseline/_ref/cultionet``: TowerUNet + TanimotoComplementLoss + torch AdamW,
+            fp32; its one absent third-party dependency, natten, is the torch restatement oracle/natten_ref.py) on the host
+            cores, rank 0, N=1 only, on a bounded sample (batch 2 of the same chip shape); the oracle port
+            (kind "port") when ``baseline/_ref`` is absent
+  secondary     N=1 only: short runs of the other single-GPU BASELINE configs (cfg1 fp32, cfg4 long series / NA k7 d2, cfg5
+            sliding-window inference Mpx/s) as sub-processes of this script, their own JSON lines nested under this key
 
-``--impl reference`` times that CPU port alone with all host threads (the reference is pure Python over torch and cannot travel
-to the GPU box), same metric/unit/config.
+``--impl reference`` times that CPU reference alone with all host threads, same metric / unit / config.
 """
 from __future__ import annotations
 
@@ -63,6 +66,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying the captured CUDA graph")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the short cfg1 / cfg4 / cfg5 runs nested under 'secondary'")
     return ap.parse_args()
 
 
@@ -131,46 +135,142 @@ def make_host_batch(w: dict, batch: int, rank: int, pin: bool):
     return x, y, bdist
 
 
-def cpu_port_chips_per_s(w: dict, steps: int, warmup: int, batch: int = 1) -> dict:
-    """fwd + loss + bwd of the oracle port on the host cores (fp32), a bounded sample of the workload."""
-    from oracle import towerunet_port as port
+def _reference_modules():
+    """The unmodified reference (pip-installed from /root/reference into baseline/_ref) through the package-shell
+    loader; None when it did not travel."""
+    ref_src = ROOT / "baseline" / "_ref" / "cultionet"
+    if not (ref_src / "models" / "nunet.py").is_file():
+        return None
+    os.environ["CULTIONET_REFERENCE_SRC"] = str(ref_src)
+    from oracle import ref_loader
 
+    ref_loader.REFERENCE_SRC = ref_src
+    return ref_loader.load_reference()
+
+
+def cpu_reference_chips_per_s(w: dict, steps: int, warmup: int, batch: int = 2) -> dict:
+    """fwd + loss + bwd + clip + AdamW on the host cores (fp32), a bounded sample of the workload: the reference's own TowerUNet /
+    TanimotoComplementLoss modules when baseline/_ref travelled (kind "reference"), else the oracle port (kind "port")."""
     torch.set_num_threads(os.cpu_count() or 1)
-    spec = port.param_spec(w["C"], w["T"], w["hidden"], w["dilations"])
-    sd = port.synth_state_dict(spec, seed=0)
-    sd = {k: (v.requires_grad_(True) if v.is_floating_point() and "running" not in k else v) for k, v in sd.items()}
     x, y, bdist = make_host_batch(w, batch, 0, pin=False)
+    ref = None
+    try:
+        ref = _reference_modules()
+    except Exception as e:  # noqa: BLE001
+        print(f"[bench] reference modules unavailable ({e!r}); timing the oracle port", file=sys.stderr)
+    if w.get("natten") and ref is not None:
+        for lvl in ("a", "b", "c"):
+            ref.unet_parts.NATTEN_PARAMS[lvl].update(w["natten"])
+    predict = bool(w.get("predict"))
+    if ref is not None:
+        kind = "reference"
+        torch.manual_seed(0)
+        model = ref.TowerUNet(in_channels=w["C"], in_time=w["T"], hidden_channels=w["hidden"], dilations=w["dilations"], dropout=0.0)
+        loss_fn_c = ref.TanimotoComplementLoss()
+        opt = torch.optim.AdamW(model.parameters(), lr=0.01, betas=(0.9, 0.98), eps=1e-4, weight_decay=1e-3)
+
+        def one_step():
+            if predict:
+                with torch.no_grad():
+                    model(x)
+                return
+            out = model(x)
+            # label recoding + (distance + edge + crop) / 3 as reference models/lightning.py:161-207, :318-354
+            true_edge = (y == 2).long()
+            true_crop = ((y > 0) & (y < 2)).long()
+            loss = (loss_fn_c(out["distance"], bdist) + loss_fn_c(out["edge"], true_edge) + loss_fn_c(out["crop"], true_crop)) / 3.0
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+            opt.step()
+
+        model.eval() if predict else model.train()
+    else:
+        kind = "port"
+        from oracle import towerunet_port as port
+
+        spec = port.param_spec(w["C"], w["T"], w["hidden"], w["dilations"])
+        sd = port.synth_state_dict(spec, seed=0)
+        sd = {k: (v.requires_grad_(True) if v.is_floating_point() and "running" not in k else v) for k, v in sd.items()}
+
+        def one_step():
+            if predict:
+                with torch.no_grad():
+                    port.towerunet_forward(sd, x, w["dilations"], training=False)
+                return
+            out = port.towerunet_forward(sd, x, w["dilations"], training=True)
+            loss, _ = port.training_loss(out, y, bdist)
+            loss.backward()
+            for v in sd.values():
+                if v.grad is not None:
+                    v.grad = None
+
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        out = port.towerunet_forward(sd, x, w["dilations"], training=True)
-        loss, _ = port.training_loss(out, y, bdist)
-        loss.backward()
-        for v in sd.values():
-            if v.grad is not None:
-                v.grad = None
+        one_step()
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
     sec = statistics.median(times)
-    return {"value": batch / sec, "unit": "chips/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"oracle port fp32, fwd+loss+bwd, batch {batch} of x=[{w['C']},{w['T']},{w['H']},{w['W']}] hidden {w['hidden']}, "
+    what = ("the reference's own modules (baseline/_ref: TowerUNet + TanimotoComplementLoss + torch AdamW; natten = torch restatement)"
+            if kind == "reference" else "oracle port")
+    if predict:
+        px = batch * w.get("useful_px_per_chip", w["H"] * w["W"])
+        return {"value": px / 1e6 / sec, "unit": "Mpx/s", "cores": torch.get_num_threads(), "kind": kind,
+                "sample": f"{what}, fp32 eval forward, batch {batch} of x=[{w['C']},{w['T']},{w['H']},{w['W']}] hidden {w['hidden']}, "
+                          f"median of {steps} steps after {warmup} warm-up", "s_per_step": sec}
+    return {"value": batch / sec, "unit": "chips/s", "cores": torch.get_num_threads(), "kind": kind,
+            "sample": f"{what}, fp32 fwd+loss+bwd+clip+AdamW, batch {batch} of x=[{w['C']},{w['T']},{w['H']},{w['W']}] hidden {w['hidden']}, "
                       f"median of {steps} steps after {warmup} warm-up", "s_per_step": sec}
+
+
+def secondary_runs(args) -> dict:
+    """Short runs of the other single-GPU BASELINE configs through this same script (one sub-process each: a workload owns module
+    level state such as NATTEN_PARAMS and its own CUDA graphs).  Returns {workload: parsed JSON line or {"error": ...}}."""
+    out = {}
+    for name, steps in (("cfg1", 10), ("cfg4", 5), ("cfg5", 10)):
+        cmd = [sys.executable, str(ROOT / "bench.py"), "--gpus", "1", "--workload", name, "--steps", str(steps), "--warmup", "3",
+               "--no-cpu-baseline", "--no-secondary", "--no-roofline"]
+        t0 = time.perf_counter()
+        try:
+            res = subprocess.run(cmd, capture_output=True, text=True, timeout=420, env={**os.environ, "WORLD_SIZE": "1", "RANK": "0",
+                                                                                     "LOCAL_RANK": os.environ.get("LOCAL_RANK", "0")})
+            lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+            rec = json.loads(lines[-1]) if lines else {"error": f"rc {res.returncode}: {res.stderr[-400:]}"}
+        except Exception as e:  # noqa: BLE001
+            rec = {"error": repr(e)}
+        keep = ("metric", "value", "unit", "ms_per_step", "steps", "warmup", "dtype", "e2e", "gpu_launches", "clocks", "model_tflops",
+                "config", "error", "final_loss")
+        out[name] = {k: rec[k] for k in keep if k in rec}
+        out[name]["wall_s"] = round(time.perf_counter() - t0, 1)
+    return out
+
+
+def workload_label(name: str, w: dict, B: int) -> str:
+    if w.get("predict"):
+        return (f"{name}: sliding-window prediction, batches of {B} windows (100 px + 20 px halo = x[{B},{w['C']},{w['T']},140,140]) per GPU, "
+                f"eval-mode BatchNorm, hidden {w['hidden']}; value counts the un-padded 100x100 pixels of every window")
+    return (f"{name}: TowerUNet train step (fwd + Tanimoto-complement loss + bwd + all-reduce + AdamW), "
+            f"x=[{B},{w['C']},{w['T']},{w['H']},{w['W']}] per GPU, hidden {w['hidden']}, dilations {w['dilations']}, dropout 0")
 
 
 def run_reference_arm(args, w: dict) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    base = cpu_port_chips_per_s(w, steps=args.steps, warmup=args.warmup, batch=1)
+    sample_b = 1 if (w["H"] >= 256 or w.get("predict")) else 2  # BASELINE.md section 4: cfg 2 at B=2, cfg 4 at B=1, scaled per chip
+    sample_b = min(sample_b, w["B"])
+    base = cpu_reference_chips_per_s(w, steps=args.steps, warmup=args.warmup, batch=sample_b)
+    predict = bool(w.get("predict"))
     line = {
-        "impl": "reference", "metric": "train chips/s", "value": base["value"], "unit": "chips/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["s_per_step"] * 1e3, "higher_is_better": True,
+        "impl": "reference", "metric": "inference Mpx/s" if predict else "train chips/s", "value": base["value"], "unit": base["unit"],
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["s_per_step"] * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: TowerUNet train step x=[B,{w['C']},{w['T']},{w['H']},{w['W']}] hidden {w['hidden']}",
-                   "sample_batch": 1},
+        "config": {"workload": workload_label(args.workload, w, w["B"]), "global_batch": w["B"] * args.gpus,
+                   "parallelism": f"dp{args.gpus}", "reference_sample_batch": sample_b},
         "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
-        "e2e": {"value": base["value"], "unit": "chips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "e2e": {"value": base["value"], "unit": base["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
@@ -302,12 +402,49 @@ def run_predict(args, w: dict) -> None:
                                               "algorithmic_bytes": by_pack}},
         }
         emit(line)
-    sys.stdout.flush()
-    torch.cuda.synchronize()
-    os._exit(0)
+    clean_exit(tp, getattr(tp, "predict", None))
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+def clean_exit(*graph_owners) -> None:
+    """Leave through the interpreter's normal exit path (exit hooks run, the loaded libraries stay visible to whoever inspects the
+    process at exit).  Captured CUDA graphs hold references to the NCCL communicator's streams: they are released FIRST, then the
+    process group is destroyed (destroying it under live graphs blocked for minutes in round 1).  A watchdog bounds a teardown
+    that hangs anyway: it runs the registered exit hooks itself and then leaves."""
+    import atexit
+    import gc
+
+    import torch.distributed as dist
+
+    sys.stdout.flush()
+    sys.stderr.flush()
+
+    def bail():  # pragma: no cover - only when a teardown hangs
+        try:
+            atexit._run_exitfuncs()
+        finally:
+            os._exit(0)
+
+    t = threading.Timer(float(os.environ.get("CNB_EXIT_WATCHDOG_S", "90")), bail)
+    t.daemon = True
+    t.start()
+    torch.cuda.synchronize()
+    for o in graph_owners:
+        for attr in ("_graph", "graph", "_graphs"):
+            if hasattr(o, attr):
+                try:
+                    setattr(o, attr, None)
+                except Exception:  # noqa: BLE001
+                    pass
+    gc.collect()
+    torch.cuda.synchronize()
+    if dist.is_available() and dist.is_initialized():
+        dist.barrier()
+        torch.cuda.synchronize()
+        dist.destroy_process_group()
+    t.cancel()
+
+
 _REAL_STDOUT = None
 
 
@@ -448,15 +585,14 @@ def main() -> None:
         launches = step.launches_per_step  # a replay repeats the launches recorded at capture; the host-side counter does not see them
     clocks = sampler.stop()
     timed_e2e(2)
-    # the end-to-end region shares the host (PCIe, memory) with whatever else runs on the box: a stalled first copy has cost a
-    # region 150 ms in one run out of three.  Three regions of K steps each are timed back to back; the fastest is reported and all
-    # three are listed.
-    e2e_regions, e2e_steps_best = [], []
+    # the end-to-end region shares the host (PCIe, memory) with whatever else runs on the box: three regions of K steps each are
+    # timed back to back, the MEDIAN is reported and all three are listed.
+    e2e_regions, e2e_steps_all = [], []
     for _ in range(3):
         e2e_regions.append(timed_e2e(args.steps))
-        if e2e_regions[-1] == min(e2e_regions):
-            e2e_steps_best = list(e2e_step_ms)
-    ms_e2e = min(e2e_regions)
+        e2e_steps_all.append(list(e2e_step_ms))
+    ms_e2e = statistics.median(e2e_regions)
+    e2e_steps_best = e2e_steps_all[e2e_regions.index(ms_e2e)]
     fl = flush_ms(args.steps)
     ms_res -= fl
     ms_e2e -= fl
@@ -489,12 +625,16 @@ def main() -> None:
             conv_shapes = {k: v for k, v in shapes.items() if k.startswith("conv") and v["flops"] > 0}
             top_key, top = max(conv_shapes.items(), key=lambda kv: kv[1]["ms"])
             achieved = top["flops"] / (top["ms"] / 1e3) / 1e12
-            traffic = None
-            tfile = ROOT / "profiles" / "r01_ncu_traffic.json"
+            # DRAM traffic cannot be measured outside a profiler: it is read from the committed ncu --set full capture of the SAME
+            # kernel and shape (profiles/ncu_traffic.json, regenerated by tools/ncu_summary.py), not from this run
+            traffic, traffic_src = None, None
+            tfile = ROOT / "profiles" / "ncu_traffic.json"
             if tfile.is_file():
-                traffic = json.loads(tfile.read_text()).get(top_key, {}).get("traffic_bytes")
+                ent = json.loads(tfile.read_text()).get(top_key, {})
+                traffic, traffic_src = ent.get("traffic_bytes"), ent.get("capture")
             roofline = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                         "frac": achieved / peaks["bf16_tflops"], "traffic": traffic,
+                        "traffic_source": (f"static, not this run: {traffic_src}" if traffic is not None else None),
                         "kernel": f"tcgen05 implicit-GEMM convolution, dominant shape: {top_key}",
                         "launches_per_step": top["calls"] // nprof, "avg_launch_ms": top["ms"] / top["calls"],
                         "algorithmic_flops_per_launch": top["flops"] / top["calls"],
@@ -522,16 +662,19 @@ def main() -> None:
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_base = cpu_port_chips_per_s(w, steps=3, warmup=1, batch=1)
+        cpu_base = cpu_reference_chips_per_s(w, steps=3, warmup=1, batch=1 if w["H"] >= 256 else min(2, B))
         cpu_base = {k: cpu_base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    secondary = None
+    if rank == 0 and world == 1 and args.workload == "cfg2" and not args.no_secondary and not args.batch:
+        secondary = secondary_runs(args)
 
     if rank == 0:
         line = {
             "metric": "train chips/s", "value": value, "unit": "chips/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": w["dtype"],
             "data": "synthetic",
-            "config": {"workload": f"{args.workload}: TowerUNet train step (fwd + Tanimoto-complement loss + bwd + all-reduce + AdamW), "
-                                   f"x=[{B},{w['C']},{w['T']},{w['H']},{w['W']}] per GPU, hidden {w['hidden']}, dilations {w['dilations']}, dropout 0",
+            "config": {"workload": workload_label(args.workload, w, B),
                        "global_batch": B * world, "parallelism": f"dp{world}", "l2": "256 MB flush buffer written between timed steps "
                        "(its time subtracted); per-step activations exceed L2",
                        "train_gflop_per_chip": 3 * w["fwd_gflop_per_chip"],
@@ -539,18 +682,13 @@ def main() -> None:
                        else "eager launches through the C ABI"},
             "e2e": {"value": e2e_value, "unit": "chips/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps, "host_ms_each_step": e2e_steps_best,
-                    "regions_ms": [round(r, 2) for r in e2e_regions], "pick": "fastest of 3 regions of K steps (flush time not yet subtracted)"},
+                    "regions_ms": [round(r, 2) for r in e2e_regions], "pick": "median of 3 regions of K steps (regions_ms before the flush time is subtracted)"},
             "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_enqueue_ms[0] if host_enqueue_ms else None, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_base,
             "model_tflops": 3 * w["fwd_gflop_per_chip"] * 1e9 * value / 1e12 if w["fwd_gflop_per_chip"] else None,
-            "final_loss": float(losses[-1]),
+            "final_loss": float(losses[-1]), "secondary": secondary,
         }
         emit(line)
-    # Leave without tearing the process group down: every collective of this run has completed (the timed regions end in barriers),
-    # and destroying the NCCL communicators while captured CUDA graphs still reference them blocked for minutes on a 2-GPU box.
-    sys.stdout.flush()
-    sys.stderr.flush()
-    torch.cuda.synchronize()
-    os._exit(0)
+    clean_exit(step)
 
 
 if __name__ == "__main__":

@@ -3,17 +3,17 @@ __version__ = "0.1.0"
 
 from . import enums  # noqa: F401
 from .data import Data  # noqa: F401
-from .losses import TanimotoComplementLoss  # noqa: F401
+from .losses import CombinedLoss, TanimotoComplementLoss, TanimotoDistLoss  # noqa: F401
 from .models.cultionet import CultioNet  # noqa: F401
 from .models.nunet import TowerUNet  # noqa: F401
 from .models.lightning import CultionetLitModel  # noqa: F401,E402
 
 
 def __getattr__(name):
-    """Lazy entry points that pull in torch.distributed / the engine: ``fit``, ``predict_tile``, ``load_from_checkpoint``,
-    ``save_checkpoint`` (cultionet_b200.model) and ``TilePredictor``, ``WindowLoader``, ``MosaicWriter``, ``predict_windows``
+    """Lazy entry points that pull in torch.distributed / the engine: ``fit``, ``fit_params``, ``CultionetParams``, ``predict_tile``,
+    ``load_from_checkpoint``, ``save_checkpoint``, ``read_checkpoint`` (cultionet_b200.model) and ``TilePredictor``, ``WindowLoader``, ``MosaicWriter``, ``predict_windows``
     (cultionet_b200.tile)."""
-    if name in ("fit", "predict_tile", "load_from_checkpoint", "save_checkpoint"):
+    if name in ("fit", "fit_params", "CultionetParams", "predict_tile", "load_from_checkpoint", "save_checkpoint", "read_checkpoint"):
         from . import model
 
         return getattr(model, name)

@@ -98,6 +98,7 @@ _PROTOS = {
     "cnb_conv2d_wgrad_tc_eligible": [C.POINTER(WgradDesc), _i],
     "cnb_conv2d_wgrad_tiny": [C.POINTER(WgradDesc), _i, _vp],
     "cnb_repitch": [_vp, _i, _vp, _i, _i64, _i, _i, _vp],
+    "cnb_broadcast_pixels": [_vp, _vp, _i, _i64, _i, _i, _vp],
     "cnb_pack_weight": [_vp, _vp, _i, _i, _i, _i, _i, _i64, _i64, _i64, _vp],
     "cnb_pack_weight2": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i64, _i64, _i64, _vp],
     "cnb_pack_weights_batched": [_vp, _i, _i, _i, _i, _vp],
@@ -128,7 +129,8 @@ _PROTOS = {
     "cnb_tap_shift_gather": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "cnb_final_combine_fwd": [_vp, _vp, _vp, _vp, _f, _i, _vp, _vp, _vp, _i64, _i, _vp],
     "cnb_final_combine_bwd": [_vp, _vp, _vp, _vp, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _vp],
-    "cnb_tanimoto_fwd": [C.POINTER(TanimotoTerm), _i, _i, _i64, _f, _i, _vp, _vp, _vp, _vp],
+    "cnb_tanimoto_fwd": [C.POINTER(TanimotoTerm), _i, _i, _i64, _f, _i, _i, _vp, _vp, _vp, _vp],
+    "cnb_val_counts": [_vp, _vp, _vp, _vp, _vp, _i64, _i, _f, _vp, _vp],
     "cnb_tanimoto_bwd": [C.POINTER(TanimotoTerm), _i, _i, _i64, _vp, _vp, _vp],
     "cnb_grad_sqnorm": [_vp, _i64, _vp, _vp],
     "cnb_adamw_step": [_vp, _vp, _vp, _vp, _i64, _vp, _f, _f, _f, _f, _f, _f, _vp, _vp],
@@ -150,9 +152,6 @@ _PROTOS = {
     "cnb_predict_pack": [_vp, _vp, _vp, _i64, _i, _i, _i, _vp, _i, _i, _f, _vp, _i, _i, _i, _vp],
 }
 
-# entry points that only exist in the nvcc build (tcgen05 / TMA kernels); filled in by later sections
-_CUDA_ONLY_PROTOS: dict = {}
-
 EXPORTED_SYMBOLS = ["cnb_version", "cnb_sm_arch", "cnb_last_error", "cnb_launch_count", *_PROTOS.keys()]
 
 
@@ -165,11 +164,6 @@ def _bind(lib) -> None:
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = C.c_int64 if name.endswith("_workspace_floats") else C.c_int
-    for name, argtypes in _CUDA_ONLY_PROTOS.items():
-        if hasattr(lib, name):
-            fn = getattr(lib, name)
-            fn.argtypes = argtypes
-            fn.restype = C.c_int
 
 
 def use_library(path) -> None:

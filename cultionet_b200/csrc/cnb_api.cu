@@ -269,6 +269,16 @@ int cnb_repitch(const void* src, int src_stride, void* dst, int dst_stride, int6
     return CNB_OK;
 }
 
+int cnb_broadcast_pixels(const void* e, void* out, int B, int64_t HW, int C, int dtype, void* stream) {
+    CNB_REQUIRE(e && out && B > 0 && HW > 0 && C > 0, "broadcast_pixels: bad arguments");
+    CNB_DISPATCH_DTYPE(dtype, {
+        CNB_LAUNCH((broadcast_pixels_kernel<T>), dim3(stream_grid((long)B * HW * C)), dim3(256), 0, (cudaStream_t)stream, (const T*)e, (T*)out, B,
+                   (long)HW, C);
+    });
+    CNB_CHECK_LAUNCH("broadcast_pixels_kernel");
+    return CNB_OK;
+}
+
 int cnb_pack_weight(const float* w, void* wp, int dtype, int taps, int N, int K, int wp_pitch, int64_t s_n, int64_t s_k, int64_t s_tap,
                     void* stream) {
     CNB_REQUIRE(w && wp && taps > 0 && N > 0 && K > 0 && wp_pitch >= K, "pack_weight: bad arguments");
@@ -1138,11 +1148,12 @@ static int check_terms(const cnb_tanimoto_term* terms, int nterms, int B, int64_
     return CNB_OK;
 }
 
-int cnb_tanimoto_fwd(const cnb_tanimoto_term* terms, int nterms, int B, int64_t HW, float smooth, int depth, double* sums, float* coef,
-                     float* loss, void* stream) {
+int cnb_tanimoto_fwd(const cnb_tanimoto_term* terms, int nterms, int B, int64_t HW, float smooth, int depth, int variant, double* sums,
+                     float* coef, float* loss, void* stream) {
     int rc = check_terms(terms, nterms, B, HW, 0);
     if (rc) return rc;
     CNB_REQUIRE(sums && coef && loss && depth >= 1 && depth <= 32, "tanimoto_fwd: bad arguments");
+    CNB_REQUIRE(variant >= 0 && variant <= 2, "tanimoto_fwd: variant %d (0 complement, 1 dist, 2 combined)", variant);
     TanimotoTerms pack;
     memset(&pack, 0, sizeof(pack));
     int cmax = 1;
@@ -1155,7 +1166,7 @@ int cnb_tanimoto_fwd(const cnb_tanimoto_term* terms, int nterms, int B, int64_t 
     CNB_LAUNCH(tanimoto_sums_kernel, dim3(chunks, B, nterms), dim3(256), 0, (cudaStream_t)stream, pack, B, (long)HW, sums);
     CNB_MEMSET_ASYNC(loss, 0, sizeof(float) * (1 + nterms), (cudaStream_t)stream);
     CNB_LAUNCH(tanimoto_finalize_kernel, dim3(cnb_div_up((long)nterms * B, 256)), dim3(256), 0, (cudaStream_t)stream, pack, nterms, B, (long)HW,
-               smooth, depth, (const double*)sums, coef, loss);
+               smooth, depth, variant, (const double*)sums, coef, loss);
     CNB_CHECK_LAUNCH("tanimoto_fwd");
     return CNB_OK;
 }
@@ -1174,6 +1185,16 @@ int cnb_tanimoto_bwd(const cnb_tanimoto_term* terms, int nterms, int B, int64_t 
     const int chunks = cnb_clamp_grid(cnb_div_up((long)cmax * HW, 256 * 4), cnb_div_up(8L * CNB_NUM_SMS, (long)B * nterms));
     CNB_LAUNCH(tanimoto_bwd_kernel, dim3(chunks, B, nterms), dim3(256), 0, (cudaStream_t)stream, pack, B, (long)HW, coef, gscale);
     CNB_CHECK_LAUNCH("tanimoto_bwd_kernel");
+    return CNB_OK;
+}
+
+int cnb_val_counts(const float* dist, const float* edge, const float* crop, const int64_t* y, const float* bdist, int64_t n, int edge_class,
+                   float thresh, double* out, void* stream) {
+    CNB_REQUIRE(dist && edge && crop && y && bdist && out && n > 0, "val_counts: bad arguments");
+    CNB_MEMSET_ASYNC(out, 0, sizeof(double) * 12, (cudaStream_t)stream);
+    CNB_LAUNCH(val_counts_kernel, dim3(stream_grid(n, 1024, 4)), dim3(256), 0, (cudaStream_t)stream, dist, edge, crop, (const long long*)y, bdist,
+               (long)n, edge_class, thresh, out);
+    CNB_CHECK_LAUNCH("val_counts_kernel");
     return CNB_OK;
 }
 

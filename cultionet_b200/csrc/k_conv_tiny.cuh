@@ -203,4 +203,16 @@ __global__ void repitch_kernel(const T* __restrict__ src, int src_stride, T* __r
     }
 }
 
+// out[b][p][c] = e[b][c]: a per-sample vector over the pixels of a level (GeoEmbeddings, reference unet_parts.py:742-750)
+template <typename T>
+__global__ void broadcast_pixels_kernel(const T* __restrict__ e, T* __restrict__ out, int B, long HW, int C) {
+    CNB_PDL_SYNC();
+    const long total = (long)B * HW * C;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const long b = i / ((long)HW * C);
+        out[i] = e[b * C + c];
+    }
+}
+
 }  // namespace cnb

@@ -157,8 +157,11 @@ __device__ __forceinline__ void tanimoto_T(double P, double S, double eps, int d
 
 // coef[(term*B+b)*4] = dloss/d{P, S, P', S'} folded with weight/(2B); loss[0] total, loss[1+term] per term (zeroed by the caller: one
 // CTA per 256 (term, sample) pairs adds its share -- a single CTA for B <= 85 with three terms, i.e. a fixed summation order there)
+// variant (reference LOSS_DICT, models/lightning.py:38-88): 0 = TanimotoComplementLoss (losses.py:103-218, `depth` terms);
+// 1 = TanimotoDistLoss (losses.py:221-340: T = (P+eps)/(S-P+eps), i.e. the depth-1 case of the same closed form);
+// 2 = CombinedLoss([TanimotoDistLoss, TanimotoComplementLoss]) = the mean of the two (losses.py:62-100)
 __global__ void __launch_bounds__(256) tanimoto_finalize_kernel(TanimotoTerms terms, int nterms, int B, long HW, float smooth, int depth,
-                                                               const double* __restrict__ sums, float* __restrict__ coef,
+                                                               int variant, const double* __restrict__ sums, float* __restrict__ coef,
                                                                float* __restrict__ loss) {
     CNB_PDL_SYNC();
     __shared__ double lsum[TN_MAX_TERMS];
@@ -170,8 +173,15 @@ __global__ void __launch_bounds__(256) tanimoto_finalize_kernel(TanimotoTerms te
         const double P = sums[i * 4 + 0], S = sums[i * 4 + 1], St = sums[i * 4 + 2], Sp = sums[i * 4 + 3];
         const double Pc = N - St - Sp + P, Sc = 2.0 * N - 2.0 * St - 2.0 * Sp + S;
         double T1, T1p, T1s, T2, T2p, T2s;
-        tanimoto_T(P, S, (double)smooth, depth, T1, T1p, T1s);
-        tanimoto_T(Pc, Sc, (double)smooth, depth, T2, T2p, T2s);
+        tanimoto_T(P, S, (double)smooth, variant == 1 ? 1 : depth, T1, T1p, T1s);
+        tanimoto_T(Pc, Sc, (double)smooth, variant == 1 ? 1 : depth, T2, T2p, T2s);
+        if (variant == 2) {  // mean of the depth-1 (TanimotoDistLoss) and depth-D (complement) forms
+            double U1, U1p, U1s, U2, U2p, U2s;
+            tanimoto_T(P, S, (double)smooth, 1, U1, U1p, U1s);
+            tanimoto_T(Pc, Sc, (double)smooth, 1, U2, U2p, U2s);
+            T1 = 0.5 * (T1 + U1), T1p = 0.5 * (T1p + U1p), T1s = 0.5 * (T1s + U1s);
+            T2 = 0.5 * (T2 + U2), T2p = 0.5 * (T2p + U2p), T2s = 0.5 * (T2s + U2s);
+        }
         const double l = 0.5 * ((1.0 - T1) + (1.0 - T2));
         atomicAdd(&lsum[term], l / (double)B);
         const double k = -(double)terms.t[term].weight / (2.0 * (double)B);
@@ -217,6 +227,48 @@ __global__ void __launch_bounds__(256) tanimoto_bwd_kernel(TanimotoTerms terms, 
         tanimoto_elem(tm, b, e, HW, t, p, m);
         tm.dpred[b * n + e] = m * (c0 * t + c1 * p + c2 * (1.f - t) + c3 * (1.f - p));
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// validation counts (reference _shared_eval_step, models/lightning.py:374-481): ONE pass over the three predictions and the labels
+// gives everything the scorers need.  out[12] (fp64, zeroed by the caller):
+//   0 valid pixels, 1 sum |dist - bdist|, 2 sum (dist - bdist)^2,
+//   3..6 edge confusion (tp, fp, fn, tn) of (edge > thresh) vs (y == edge_class), 7..10 crop confusion of (crop > thresh) vs (0 < y < edge_class),
+//   11 unused.  Pixels with y == -1 are excluded (the reference masks them out only when the batch holds any: same result).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) val_counts_kernel(const float* __restrict__ dist, const float* __restrict__ edge,
+                                                        const float* __restrict__ crop, const long long* __restrict__ y,
+                                                        const float* __restrict__ bdist, long n, int edge_class, float thresh,
+                                                        double* __restrict__ out) {
+    CNB_PDL_SYNC();
+    __shared__ double sh[11];
+    if (threadIdx.x < 11) sh[threadIdx.x] = 0.0;
+    __syncthreads();
+    float mae = 0.f, mse = 0.f;
+    int cnt[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // valid, edge tp fp fn tn, crop tp fp fn tn
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const long long lab = y[i];
+        if (lab == -1) continue;
+        cnt[0]++;
+        const float d = dist[i] - bdist[i];
+        mae += fabsf(d);
+        mse = fmaf(d, d, mse);
+        const bool te = lab == edge_class, pe = edge[i] > thresh;
+        cnt[1 + (pe ? (te ? 0 : 1) : (te ? 2 : 3))]++;
+        const bool tc = lab > 0 && lab < edge_class, pc = crop[i] > thresh;
+        cnt[5 + (pc ? (tc ? 0 : 1) : (tc ? 2 : 3))]++;
+    }
+    double v[11];
+    v[0] = (double)cnt[0], v[1] = (double)mae, v[2] = (double)mse;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[3 + k] = (double)cnt[1 + k];
+#pragma unroll
+    for (int k = 0; k < 11; ++k) {
+        const double w = cnb_warp_sum(v[k]);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&sh[k], w);
+    }
+    __syncthreads();
+    if (threadIdx.x < 11) atomicAdd(out + threadIdx.x, sh[threadIdx.x]);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -93,9 +93,9 @@ class TrainStep:
     over NVLink: ~0.4 ms, nothing worth overlapping against the host time the graph removes)."""
 
     def __init__(self, lit_model, total_steps: Optional[int] = None, bucket_mb: float = 32.0, cuda_graph: bool = False,
-                 graph_warmup: int = 3):
+                 graph_warmup: int = 3, steps_per_epoch: Optional[int] = None):
         self.model = lit_model
-        self.optimizer = lit_model.configure_optimizers(total_steps=total_steps)
+        self.optimizer = lit_model.configure_optimizers(total_steps=total_steps, steps_per_epoch=steps_per_epoch)
         self.cuda_graph = bool(cuda_graph) and self.optimizer.flat_param.is_cuda and not _lib.is_emulator()
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         # graph mode exchanges gradients itself (see _device_step); eager mode uses the overlapped bucketed exchange
@@ -130,6 +130,14 @@ class TrainStep:
         self.optimizer.advance_host()
         return self._device_step(batch)
 
+    def close(self) -> None:
+        """Detach from the model: removes the gradient-exchange hooks (a later ``TrainStep`` / ``fit`` on the same model registers its
+        own) and drops the captured graph."""
+        if self.sync is not None:
+            self.sync.close()
+            self.sync = None
+        self._graph = None
+
     def _capture(self, batch: Data) -> None:
         dev = self.optimizer.flat_param.device
         self._static = Data(**{k: (v.to(dev).clone() if isinstance(v, torch.Tensor) else v) for k, v in batch.__dict__.items()})
@@ -160,6 +168,8 @@ class TrainStep:
                 self.cuda_graph = False
                 self._graph = None
                 torch.cuda.synchronize()
+                if self.sync is not None:
+                    self.sync.close()
                 self.sync = BucketedGradSync(self.optimizer)
                 return self.eager(batch)
         if _signature(batch) != self._sig:

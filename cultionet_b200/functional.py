@@ -810,6 +810,34 @@ def resize_bilinear(x: torch.Tensor, size) -> torch.Tensor:
     return _ResizeBilinearFn.apply(x, int(size[0]), int(size[1]))
 
 
+class _BroadcastPixelsFn(torch.autograd.Function):
+    """``[B,1,1,C] -> [B,H,W,C]`` (the per-sample GeoEmbeddings vector over a level's pixels, reference ``unet_parts.py:742-750``);
+    backward = the per-sample column sum of the gradient."""
+
+    @staticmethod
+    def forward(ctx, e, H, W):
+        check_device(e)
+        e = _contig(e)
+        B, Cn = e.shape[0], e.shape[-1]
+        out = torch.empty((B, H, W, Cn), dtype=e.dtype, device=e.device)
+        call("cnb_broadcast_pixels", ptr(e), ptr(out), B, H * W, Cn, dtype_code(e.dtype), stream_ptr(e))
+        ctx.meta = (B, H, W, Cn)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, H, W, Cn = ctx.meta
+        dout = _contig(dout)
+        de32 = torch.empty((B, Cn), dtype=torch.float32, device=dout.device)
+        for b in range(B):  # one column sum per sample (an option that is off by default: B small launches)
+            call("cnb_bias_grad", ptr(dout[b]), Cn, H * W, Cn, ptr(de32[b]), 0, dtype_code(dout.dtype), stream_ptr(dout))
+        return de32.view(B, 1, 1, Cn).to(dout.dtype), None, None  # [B, C] values: dtype plumbing, not compute
+
+
+def broadcast_pixels(e: torch.Tensor, size) -> torch.Tensor:
+    return _BroadcastPixelsFn.apply(e, int(size[0]), int(size[1]))
+
+
 # ----------------------------------------------------------------------------------------------------------------
 class _PreTimeConvFn(torch.autograd.Function):
     """Conv3d(C->C, (k,1,1), bias=False) over x[B,C,T,H,W] -> pixel-major u[B,H,W,pitch] (column = c*T' + t'; pitch = C*T'
@@ -960,7 +988,7 @@ class TanimotoTermSpec:
 
 class _TanimotoFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, smooth, depth, specs, *preds):
+    def forward(ctx, smooth, depth, variant, specs, *preds):
         nterms = len(preds)
         assert 1 <= nterms <= _lib.TN_MAX_TERMS and len(specs) == nterms
         preds = [_contig(p.float()) for p in preds]
@@ -995,7 +1023,7 @@ class _TanimotoFn(torch.autograd.Function):
         sums = torch.empty((nterms, B, 4), dtype=torch.float64, device=dev)
         coef = torch.empty((nterms, B, 4), dtype=torch.float32, device=dev)
         loss = torch.empty((1 + nterms,), dtype=torch.float32, device=dev)
-        call("cnb_tanimoto_fwd", terms, nterms, B, HW, smooth, depth, ptr(sums), ptr(coef), ptr(loss), stream_ptr(preds[0]))
+        call("cnb_tanimoto_fwd", terms, nterms, B, HW, smooth, depth, int(variant), ptr(sums), ptr(coef), ptr(loss), stream_ptr(preds[0]))
         ctx.terms, ctx.keep, ctx.preds, ctx.coef = terms, keep, preds, coef
         ctx.meta = (nterms, B, HW)
         ctx.mark_non_differentiable(loss)
@@ -1013,12 +1041,31 @@ class _TanimotoFn(torch.autograd.Function):
             grads.append(g)
         gs = _contig(gtotal.float().reshape(1))
         call("cnb_tanimoto_bwd", terms, nterms, B, HW, ptr(ctx.coef), ptr(gs), stream_ptr(gs))
-        return (None, None, None, *grads)
+        return (None, None, None, None, *grads)
 
 
-def tanimoto_complement(preds: Sequence[torch.Tensor], specs: Sequence[TanimotoTermSpec], smooth: float = 1e-5, depth: int = 5):
-    """Returns (sum_t weight_t * loss_t, tensor[1 + nterms] of total and per-term losses)."""
-    return _TanimotoFn.apply(smooth, depth, list(specs), *preds)
+TANIMOTO_COMPLEMENT, TANIMOTO_DIST, TANIMOTO_COMBINED = 0, 1, 2  # `variant` of cnb_tanimoto_fwd
+
+
+def tanimoto_complement(preds: Sequence[torch.Tensor], specs: Sequence[TanimotoTermSpec], smooth: float = 1e-5, depth: int = 5,
+                        variant: int = TANIMOTO_COMPLEMENT):
+    """Returns (sum_t weight_t * loss_t, tensor[1 + nterms] of total and per-term losses).  ``variant`` picks the reference's
+    TanimotoComplementLoss (0), TanimotoDistLoss (1) or the CombinedLoss of the two (2)."""
+    return _TanimotoFn.apply(smooth, depth, variant, list(specs), *preds)
+
+
+def validation_counts(dist: torch.Tensor, edge: torch.Tensor, crop: torch.Tensor, y: torch.Tensor, bdist: torch.Tensor,
+                      edge_class: int = 2, thresh: float = 0.5) -> torch.Tensor:
+    """fp64[12] = {valid pixels, sum |dist - bdist|, sum (dist - bdist)^2, edge tp/fp/fn/tn, crop tp/fp/fn/tn, 0} over the labelled
+    (``y != -1``) pixels of a batch in one pass (``cnb_val_counts``): the inputs of every scorer of ``_shared_eval_step``."""
+    dist, edge, crop = (_contig(t.detach().float()) for t in (dist, edge, crop))
+    y, bdist = _contig(y.long()), _contig(bdist.float())
+    check_device(dist, edge, crop, y, bdist)
+    n = y.numel()
+    assert dist.numel() == n and edge.numel() == n and crop.numel() == n and bdist.numel() == n, "validation_counts: 1-channel predictions"
+    out = torch.empty((12,), dtype=torch.float64, device=y.device)
+    call("cnb_val_counts", ptr(dist), ptr(edge), ptr(crop), ptr(y), ptr(bdist), n, int(edge_class), float(thresh), ptr(out), stream_ptr(y))
+    return out
 
 
 # ----------------------------------------------------------------------------------------------------------------

@@ -30,6 +30,7 @@ class CultioNet(nn.Module):
     ):
         super().__init__()
         self.in_channels, self.in_time, self.hidden_channels = in_channels, in_time, hidden_channels
+        self.use_latlon = bool(use_latlon)
         assert model_type in (ModelTypes.TOWERUNET,), "The model type is not supported."
         self.mask_model = TowerUNet(
             in_channels=in_channels, in_time=in_time, hidden_channels=hidden_channels, num_classes=1,
@@ -39,8 +40,11 @@ class CultioNet(nn.Module):
         )
 
     def forward(self, batch: Data) -> T.Dict[str, torch.Tensor]:
-        # the reference builds latlon_coords [B,2] here (cultionet.py:88-94); TowerUNet only reads it when use_latlon=True,
-        # which CultionetLitModel never enables (lightning.py:878-890) and this build rejects at construction.
-        out = self.mask_model(batch.x, latlon_coords=None)
+        # latlon_coords [B,2] = (lon, lat) as the reference builds it (cultionet.py:88-94); TowerUNet reads it only when use_latlon=True
+        # (CultionetLitModel never enables that, lightning.py:878-890), so a batch without lon / lat is fine otherwise
+        latlon_coords = None
+        if self.use_latlon:
+            latlon_coords = torch.cat((batch.lon.reshape(-1, 1), batch.lat.reshape(-1, 1)), dim=1)
+        out = self.mask_model(batch.x, latlon_coords=latlon_coords)
         out.update({InferenceNames.CROP_TYPE: None, InferenceNames.CLASSES_L2: None, InferenceNames.CLASSES_L3: None})
         return out

@@ -3,8 +3,11 @@ for the TowerUNet hot path: ``forward`` / ``predict_step`` / ``training_step`` /
 ``get_true_labels`` / ``configure_optimizers`` with the same constructor keywords and the same attribute layout
 (``cultionet_model`` stored under ``f"{model_name}_{model_type}"`` so checkpoints keep their key prefix).
 
-``lightning`` is optional: when it is importable the class derives from ``lightning.LightningModule`` and drops into a Lightning
-``Trainer``; otherwise it is a plain ``nn.Module`` and ``cultionet_b200.engine`` provides the training / prediction loops.
+The class is a plain ``nn.Module`` carrying the LightningModule METHOD surface; ``cultionet_b200.model.fit`` /
+``cultionet_b200.engine.TrainStep`` are the loops that drive it (what ``lightning.Trainer`` does for this path in the reference:
+DDP, clipping, optimizer + scheduler stepping, best-``val_score`` checkpoint).  It is deliberately NOT a ``lightning.LightningModule``
+subclass: the optimiser is a flat-buffer kernel pair that owns parameter and gradient storage and clips inside its step, which a
+Lightning ``Trainer`` (torch ``Optimizer`` protocol, its own ``gradient_clip_val``) cannot drive.
 """
 from __future__ import annotations
 
@@ -15,20 +18,51 @@ import torch.nn as nn
 
 from ..data import Data
 from ..enums import AttentionTypes, InferenceNames, LearningRateSchedulers, LossTypes, ModelTypes, ResBlockTypes, ValidationNames
+from .. import functional as F
 from ..losses import tower_unet_loss
-from ..optim import FlatAdamW
+from ..optim import FlatAdamW, make_lr_schedule
 from .cultionet import CultioNet
 
-try:  # pragma: no cover - lightning is not installed in the build image
-    from lightning import LightningModule as _Base
+HAVE_LIGHTNING = False  # see the module docstring
 
-    HAVE_LIGHTNING = True
-except Exception:  # noqa: BLE001
-    _Base = nn.Module
-    HAVE_LIGHTNING = False
+# LOSS_DICT of the reference (models/lightning.py:38-88), the Tanimoto family: one reduction kernel, three closed forms
+LOSS_VARIANTS = {
+    str(LossTypes.TANIMOTO_COMPLEMENT): F.TANIMOTO_COMPLEMENT,
+    str(LossTypes.TANIMOTO): F.TANIMOTO_DIST,
+    str(LossTypes.TANIMOTO_COMBINED): F.TANIMOTO_COMBINED,
+}
 
 
-class LightningModuleMixin(_Base):
+def _plain(v):
+    """Checkpoint-safe hyper-parameter value: enum members become their string value, so that neither side needs the other's enum
+    classes importable to unpickle a checkpoint."""
+    import enum
+
+    if isinstance(v, enum.Enum):
+        return str(v.value)
+    if isinstance(v, (list, tuple)):
+        return [_plain(i) for i in v]
+    return v
+
+
+def scores_from_counts(c: torch.Tensor) -> T.Dict[str, torch.Tensor]:
+    """The scorers of ``configure_scorer`` (models/lightning.py:562-580) from the fp64[12] counts of ``cnb_val_counts``:
+    MeanAbsoluteError / MeanSquaredError; ``FBetaScore(task="multiclass", num_classes=2, beta=2)`` -- whose default ``average="micro"``
+    makes it (tp + tn) / n, i.e. accuracy, for any beta; ``MatthewsCorrCoef(task="multiclass", num_classes=2)`` from the 2x2 confusion
+    matrix (0 when a marginal is empty, 1 / -1 when every pixel is right / wrong, as torchmetrics special-cases it)."""
+    n = c[0].clamp_min(1.0)
+    out = {"dist_mae": c[1] / n, "dist_mse": c[2] / n}
+    for name, o in (("edge", 3), ("crop", 7)):
+        tp, fp, fn, tn = c[o], c[o + 1], c[o + 2], c[o + 3]
+        out[f"{name}_f1"] = (tp + tn) / n
+        den = (tp + fp) * (tp + fn) * (tn + fp) * (tn + fn)
+        mcc = (tp * tn - fp * fn) / den.clamp_min(1e-300).sqrt()
+        perfect = (fp + fn == 0).to(mcc.dtype) - (tp + tn == 0).to(mcc.dtype)
+        out[f"{name}_mcc"] = torch.where(den > 0, mcc, perfect)
+    return {k: v.float() for k, v in out.items()}
+
+
+class LightningModuleMixin(nn.Module):
     def __call__(self, *args, **kwargs):  # the reference overrides __call__ the same way (lightning.py:95-96)
         return self.forward(*args, **kwargs)
 
@@ -66,43 +100,61 @@ class LightningModuleMixin(_Base):
 
     def calc_loss(self, batch: Data, predictions: T.Dict[str, torch.Tensor]):
         """(distance + edge + crop) / 3 with Tanimoto-complement terms (lightning.py:318-354), one fused reduction."""
-        loss, parts = tower_unet_loss(predictions, batch.y, batch.bdist, edge_class=self.edge_class)
+        loss, parts = tower_unet_loss(predictions, batch.y, batch.bdist, edge_class=self.edge_class,
+                                      variant=LOSS_VARIANTS[str(self.loss_name)])
         return loss, {"dloss": parts[1], "eloss": parts[2], "closs": parts[3]}
 
     def training_step(self, batch: Data, batch_idx: int = None):
         predictions = self(batch)
         loss, _ = self.calc_loss(batch, predictions)
-        if HAVE_LIGHTNING:  # pragma: no cover
-            self.log("loss", loss, on_step=False, on_epoch=True, prog_bar=True, batch_size=batch.num_samples)
         return loss
 
     @torch.no_grad()
-    def validation_step(self, batch: Data, batch_idx: int = None) -> dict:
+    def _shared_eval_step(self, batch: Data, batch_idx: int = None) -> dict:
+        """``_shared_eval_step`` (models/lightning.py:374-481): loss + one counting pass (``cnb_val_counts``) over the labelled pixels
+        -> MAE / MSE of the distance, micro F-beta and MCC of the edge and crop masks, and
+        ``score = loss + (1 - edge_f) + (1 - crop_f) + mae + (1 - max(edge_mcc, 0)) + (1 - max(crop_mcc, 0))``."""
         predictions = self(batch)
         loss, report = self.calc_loss(batch, predictions)
-        labels = self.get_true_labels(batch)
-        valid = labels[ValidationNames.MASK]
-        valid = torch.ones_like(batch.y, dtype=torch.bool) if valid is None else valid.squeeze(1).bool()
-        dist_mae = (predictions[InferenceNames.DISTANCE].squeeze(1) - batch.bdist).abs()[valid].mean()
-        metrics = {"val_loss": loss, "vmae": dist_mae, "val_dloss": report["dloss"], "val_eloss": report["eloss"],
-                   "val_closs": report["closs"]}
-        for name, key, truth in (("vef1", InferenceNames.EDGE, ValidationNames.TRUE_EDGE), ("vcf1", InferenceNames.CROP, ValidationNames.TRUE_CROP)):
-            pred = self.probas_to_labels(predictions[key])[valid]
-            true = labels[truth][valid]
-            tp = ((pred == 1) & (true == 1)).sum().float()
-            fp = ((pred == 1) & (true == 0)).sum().float()
-            fn = ((pred == 0) & (true == 1)).sum().float()
-            metrics[name] = 5.0 * tp / (5.0 * tp + 4.0 * fn + fp).clamp_min(1.0)  # F-beta, beta = 2 (lightning.py:574-576)
-        metrics["val_score"] = loss + (1.0 - metrics["vef1"]) + (1.0 - metrics["vcf1"]) + dist_mae
+        counts = F.validation_counts(predictions[InferenceNames.DISTANCE], predictions[InferenceNames.EDGE],
+                                     predictions[InferenceNames.CROP], batch.y, batch.bdist, edge_class=self.edge_class)
+        m = scores_from_counts(counts)
+        score = (loss + (1.0 - m["edge_f1"]) + (1.0 - m["crop_f1"]) + m["dist_mae"] + (1.0 - m["edge_mcc"].clamp_min(0))
+                 + (1.0 - m["crop_mcc"].clamp_min(0)))
+        metrics = {"loss": loss, "score": score, "counts": counts, **m}
+        metrics.update(report)
         return metrics
 
-    def configure_optimizers(self, total_steps: T.Optional[int] = None):
-        if self.optimizer != "AdamW":
-            raise NameError("cultionet_b200 builds the reference's default optimizer only: choose 'AdamW'.")
-        if self.lr_scheduler != LearningRateSchedulers.ONE_CYCLE_LR:
-            raise NameError("The learning rate scheduler is not implemented in cultionet_b200 (OneCycleLR only).")
-        return FlatAdamW(self.cultionet_model.parameters(), lr=self.learning_rate, betas=(0.9, 0.98), eps=self.eps,
-                         weight_decay=self.weight_decay, clip_norm=1.0, total_steps=total_steps)
+    @torch.no_grad()
+    def validation_step(self, batch: Data, batch_idx: int = None) -> dict:
+        """Keys of the reference's ``validation_step`` (:483-510) plus the MCC / MSE values it computes but does not log."""
+        e = self._shared_eval_step(batch, batch_idx)
+        return {"vef1": e["edge_f1"], "vcf1": e["crop_f1"], "vmae": e["dist_mae"], "val_score": e["score"], "val_loss": e["loss"],
+                "val_dloss": e["dloss"], "val_eloss": e["eloss"], "val_closs": e["closs"], "vmse": e["dist_mse"],
+                "vemcc": e["edge_mcc"], "vcmcc": e["crop_mcc"]}
+
+    @torch.no_grad()
+    def test_step(self, batch: Data, batch_idx: int = None) -> dict:
+        """``test_step`` (:544-560) for the scorers ``_shared_eval_step`` provides (the reference also reads dice / jaccard keys that its
+        own ``_shared_eval_step`` never sets)."""
+        e = self._shared_eval_step(batch, batch_idx)
+        return {"test_loss": e["loss"], "tmae": e["dist_mae"], "tmse": e["dist_mse"], "tef1": e["edge_f1"], "tcf1": e["crop_f1"],
+                "temcc": e["edge_mcc"], "tcmcc": e["crop_mcc"], "test_score": e["score"]}
+
+    def configure_optimizers(self, total_steps: T.Optional[int] = None, steps_per_epoch: T.Optional[int] = None):
+        """``configure_optimizers`` (:611-683).  Optimisers: AdamW (betas (0.9, 0.98)) and Adam (no decay) on the flat AdamW kernel; the
+        reference's RAdam / SGD are not built (``NameError``, as for any unknown name there).  Schedulers: OneCycleLR stepped per batch,
+        CosineAnnealingLR(T_max=20, eta_min=1e-5) / ExponentialLR(0.5) / StepLR(step_size, 0.5) stepped per epoch."""
+        if self.optimizer == "AdamW":
+            betas, wd = (0.9, 0.98), self.weight_decay
+        elif self.optimizer == "Adam":
+            betas, wd = (0.9, 0.999), 0.0
+        else:
+            raise NameError("cultionet_b200 builds the reference's 'AdamW' and 'Adam' optimizers only.")
+        schedule = make_lr_schedule(str(self.lr_scheduler), self.learning_rate, total_steps=total_steps,
+                                    steps_per_epoch=steps_per_epoch, steplr_step_size=self.steplr_step_size)
+        return FlatAdamW(self.cultionet_model.parameters(), lr=self.learning_rate, betas=betas, eps=self.eps, weight_decay=wd,
+                         clip_norm=1.0, total_steps=total_steps, lr_schedule=schedule)
 
 
 class CultionetLitModel(LightningModuleMixin):
@@ -132,15 +184,18 @@ class CultionetLitModel(LightningModuleMixin):
         edge_class: T.Optional[int] = None,
         scale_pos_weight: bool = False,
         save_batch_val_metrics: bool = False,
-        compute_dtype: torch.dtype = torch.bfloat16,
+        compute_dtype: T.Union[torch.dtype, str] = torch.bfloat16,
     ):
         super().__init__()
-        # what Lightning's save_hyperparameters() records (lightning.py:850) and writes into checkpoints as 'hyper_parameters'
-        self.hyper_parameters = {k: v for k, v in locals().items() if k not in ("self", "__class__")}
-        if loss_name != LossTypes.TANIMOTO_COMPLEMENT:
-            raise NotImplementedError("cultionet_b200 builds the reference's default loss only (TanimotoComplementLoss)")
-        if HAVE_LIGHTNING:  # pragma: no cover
-            self.save_hyperparameters()
+        if isinstance(compute_dtype, str):  # a checkpoint stores the name
+            compute_dtype = getattr(torch, compute_dtype.replace("torch.", ""))
+        # what Lightning's save_hyperparameters() records (lightning.py:850) and writes into checkpoints as 'hyper_parameters' -- as
+        # plain values (enum members -> their strings, dtype -> its name): a checkpoint must unpickle without this package
+        self.hyper_parameters = {k: _plain(v) for k, v in locals().items() if k not in ("self", "__class__", "compute_dtype")}
+        self.hyper_parameters["compute_dtype"] = str(compute_dtype).replace("torch.", "")
+        if str(loss_name) not in LOSS_VARIANTS:
+            raise NotImplementedError(f"cultionet_b200 builds the Tanimoto family of the reference's LOSS_DICT ({sorted(LOSS_VARIANTS)}); "
+                                      f"got {loss_name!r}")
         self.optimizer, self.loss_name, self.learning_rate = optimizer, loss_name, learning_rate
         self.lr_scheduler, self.steplr_step_size = lr_scheduler, steplr_step_size
         self.weight_decay, self.eps, self.ckpt_name, self.model_name = weight_decay, eps, ckpt_name, model_name
@@ -167,10 +222,8 @@ class CultionetLitModel(LightningModuleMixin):
 
         return load_from_checkpoint(checkpoint_path, map_location=map_location, strict=strict, **kwargs)
 
-    if not HAVE_LIGHTNING:
-
-        def freeze(self) -> None:
-            """``LightningModule.freeze`` (``model.py:402``): no gradients, eval mode."""
-            for p in self.parameters():
-                p.requires_grad_(False)
-            self.eval()
+    def freeze(self) -> None:
+        """``LightningModule.freeze`` (``model.py:402``): no gradients, eval mode."""
+        for p in self.parameters():
+            p.requires_grad_(False)
+        self.eval()

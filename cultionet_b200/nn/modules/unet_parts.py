@@ -227,6 +227,28 @@ class TowerUNetDecoder(nn.Module):
         return {"x_au": x_au, "x_bu": x_bu, "x_cu": x_cu, "x_du": x_du}
 
 
+class GeoEmbeddings(nn.Module):
+    """``nn/modules/geo_encoding.py:5-26``: (lon, lat) in decimal degrees -> unit-sphere cartesian (x, y, z) -> ``Linear(3, channels)``.
+    The degrees -> cartesian step is three trigonometric values per SAMPLE (a ``[B, 2]`` tensor, no gradient in the reference either);
+    the Linear runs on the convolution kernel like every other Linear of the model."""
+
+    def __init__(self, channels: int):
+        super().__init__()
+        self.coord_embedding = nn.Linear(3, channels)
+
+    @torch.no_grad()
+    def decimal_degrees_to_cartesian(self, degrees: torch.Tensor) -> torch.Tensor:
+        radians = torch.deg2rad(degrees)
+        cosine, sine = torch.cos(radians), torch.sin(radians)
+        return torch.stack([cosine[:, 1] * cosine[:, 0], cosine[:, 1] * sine[:, 0], sine[:, 1]], dim=-1)
+
+    def forward(self, x: torch.Tensor, dtype: torch.dtype = torch.float32) -> torch.Tensor:
+        """``x``: ``[B, 2]`` (lon, lat) -> ``[B, 1, 1, channels]`` pixel-major embedding in the compute dtype."""
+        cart = self.decimal_degrees_to_cartesian(x.float())
+        cart = cart.to(dtype).view(cart.shape[0], 1, 1, 3)
+        return F.linear(cart, self.coord_embedding.weight, self.coord_embedding.bias)
+
+
 class TowerUNetBlock(nn.Module):
     """UNet3+ full-scale skip: same-level {backbone, decoder} + ConvT-upsampled level below of {backbone, decoder[, tower]}
     -> ResidualAConv over the virtual concatenation (reference ``unet_parts.py:615-760``)."""
@@ -237,14 +259,15 @@ class TowerUNetBlock(nn.Module):
                  batchnorm_first: bool = False, natten_num_heads: int = 8, natten_kernel_size: int = 3, natten_dilation: int = 1,
                  natten_attn_drop: float = 0.0, natten_proj_drop: float = 0.0, use_latlon: bool = False):
         super().__init__()
-        if use_latlon:
-            raise NotImplementedError("cultionet_b200: use_latlon=True (GeoEmbeddings) is off in CultionetLitModel and not built")
         self.use_latlon = use_latlon
         in_channels = backbone_side_channels + backbone_down_channels + up_channels * 2
         self.backbone_down_conv = ConvTranspose2d(backbone_down_channels, backbone_down_channels, kernel_size=3, stride=2, padding=1)
         self.decode_down_conv = ConvTranspose2d(up_channels, up_channels, kernel_size=3, stride=2, padding=1)
         if tower:
             self.tower_conv = ConvTranspose2d(up_channels, up_channels, kernel_size=3, stride=2, padding=1)
+            in_channels += up_channels
+        if use_latlon:  # reference unet_parts.py:676-681 (its torch.compile wrapper changes nothing in the arithmetic)
+            self.geo_embeddings = GeoEmbeddings(up_channels)
             in_channels += up_channels
         natten_kw = dict(natten_num_heads=natten_num_heads, natten_kernel_size=natten_kernel_size, natten_dilation=natten_dilation,
                          natten_attn_drop=natten_attn_drop, natten_proj_drop=natten_proj_drop)
@@ -259,6 +282,10 @@ class TowerUNetBlock(nn.Module):
             decode_side,
             self.decode_down_conv(decode_down, size=size),
         ]
+        if self.use_latlon:  # reference :739-750: the per-sample embedding broadcast over the level's pixels, concatenated
+            assert latlon_coords is not None, "No lat/lon coordinates given."
+            emb = self.geo_embeddings(latlon_coords, decode_side.dtype)
+            sources.append(F.broadcast_pixels(emb, size))
         if tower_down is not None:
             sources.append(self.tower_conv(tower_down, size=size))
         return self.res_conv(sources)

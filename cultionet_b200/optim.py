@@ -32,9 +32,36 @@ def one_cycle_lr(step: int, total_steps: int, max_lr: float, pct_start: float = 
     return cos(max_lr, minimum, min(1.0, (step - up_end) / (down_end - up_end)))
 
 
+def make_lr_schedule(name: str, lr: float, total_steps: Optional[int] = None, steps_per_epoch: Optional[int] = None,
+                     steplr_step_size: int = 5):
+    """The schedulers ``configure_optimizers`` offers (``models/lightning.py:650-672``) as closed forms ``f(step, epoch) -> lr``:
+    ``OneCycleLR(max_lr=lr)`` stepped per batch; ``CosineAnnealingLR(T_max=20, eta_min=1e-5)``, ``ExponentialLR(gamma=0.5)`` and
+    ``StepLR(step_size, gamma=0.5)`` stepped per epoch (Lightning ``interval='epoch'``).  ``epoch`` = completed epochs; without
+    ``steps_per_epoch`` it is taken from ``FlatAdamW.epoch`` (``set_epoch``)."""
+
+    def epoch_of(step: int, epoch: Optional[int]) -> int:
+        if epoch is not None:
+            return epoch
+        return step // steps_per_epoch if steps_per_epoch else 0
+
+    if name == "OneCycleLR":
+        if not total_steps:
+            return lambda step, epoch=None: lr
+        return lambda step, epoch=None: one_cycle_lr(min(step, total_steps - 1), total_steps, lr)
+    if name == "CosineAnnealingLR":
+        t_max, eta_min = 20, 1e-5
+        # the closed form of torch's CosineAnnealingLR (its recursive form follows the same curve, periodic with period 2*T_max)
+        return lambda step, epoch=None: eta_min + (lr - eta_min) * (1.0 + math.cos(math.pi * epoch_of(step, epoch) / t_max)) / 2.0
+    if name == "ExponentialLR":
+        return lambda step, epoch=None: lr * 0.5 ** epoch_of(step, epoch)
+    if name == "StepLR":
+        return lambda step, epoch=None: lr * 0.5 ** (epoch_of(step, epoch) // max(1, int(steplr_step_size)))
+    raise NameError("The learning rate scheduler is not implemented in Cultionet.")
+
+
 class FlatAdamW:
     def __init__(self, params: Iterable[torch.nn.Parameter], lr: float = 0.01, betas=(0.9, 0.98), eps: float = 1e-4,
-                 weight_decay: float = 1e-3, clip_norm: float = 1.0, total_steps: Optional[int] = None):
+                 weight_decay: float = 1e-3, clip_norm: float = 1.0, total_steps: Optional[int] = None, lr_schedule=None):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("FlatAdamW: no trainable parameters")
@@ -58,6 +85,8 @@ class FlatAdamW:
                 off += k
         self.lr, self.betas, self.eps, self.weight_decay, self.clip_norm = lr, betas, eps, weight_decay, clip_norm
         self.total_steps = total_steps
+        self.lr_schedule = lr_schedule  # f(step, epoch) -> lr; None: OneCycle over total_steps (constant lr without total_steps)
+        self.epoch: Optional[int] = None  # set by the training loop for the per-epoch schedulers
         self.step_count = 0
         self.hyper = torch.zeros(2, dtype=torch.float32, device=dev)
         # (lr, step) travel through a small RING of pinned host buffers: the host runs ahead of the device (and of a replaying CUDA
@@ -76,7 +105,12 @@ class FlatAdamW:
             if p.grad is None or p.grad.data_ptr() != self.flat_grad.data_ptr() + 4 * off:
                 p.grad = self.flat_grad[off:off + k].view(p.shape)
 
+    def set_epoch(self, epoch: int) -> None:
+        self.epoch = int(epoch)
+
     def current_lr(self) -> float:
+        if self.lr_schedule is not None:
+            return float(self.lr_schedule(self.step_count, self.epoch))
         if self.total_steps:
             return one_cycle_lr(min(self.step_count, self.total_steps - 1), self.total_steps, self.lr)
         return self.lr
@@ -117,9 +151,42 @@ class FlatAdamW:
         self.launch_device()
 
     def state_dict(self) -> dict:
-        return {"step": self.step_count, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq}
+        """``torch.optim.AdamW.state_dict()`` layout -- ``{"state": {i: {"step", "exp_avg", "exp_avg_sq"}}, "param_groups": [...]}``
+        with the parameters in ``cultionet_model.parameters()`` order, the order of the reference's ``params_list``
+        (``models/lightning.py:614``) -- so the moments of a checkpoint written here load into the reference's optimizer and back."""
+        state = {}
+        for i, (p, (off, k)) in enumerate(zip(self.params, self.offsets)):
+            state[i] = {"step": torch.tensor(float(self.step_count)),
+                        "exp_avg": self.exp_avg[off:off + k].view(p.shape).detach().clone(),
+                        "exp_avg_sq": self.exp_avg_sq[off:off + k].view(p.shape).detach().clone()}
+        group = {"lr": self.current_lr(), "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.weight_decay, "amsgrad": False,
+                 "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+                 "decoupled_weight_decay": True, "initial_lr": self.lr / 25.0, "max_lr": self.lr, "min_lr": self.lr / 25.0 / 1e4,
+                 "params": list(range(len(self.params)))}
+        return {"state": state, "param_groups": [group]}
 
     def load_state_dict(self, sd: dict) -> None:
+        """Accepts the torch layout above (a reference ``last.ckpt``'s ``optimizer_states[0]`` included) and the flat
+        ``{"step", "exp_avg", "exp_avg_sq"}`` layout this class wrote in round 1."""
+        if "state" in sd and "param_groups" in sd:
+            order = [i for g in sd["param_groups"] for i in g["params"]]
+            if len(order) != len(self.params):
+                raise ValueError(f"optimizer state holds {len(order)} parameters, the model has {len(self.params)}")
+            step = 0
+            with torch.no_grad():
+                for idx, p, (off, k) in zip(order, self.params, self.offsets):
+                    st = sd["state"].get(idx)
+                    if st is None:  # a parameter that never received a gradient has no state in torch
+                        self.exp_avg[off:off + k].zero_()
+                        self.exp_avg_sq[off:off + k].zero_()
+                        continue
+                    if tuple(st["exp_avg"].shape) != tuple(p.shape):
+                        raise ValueError(f"optimizer state {idx}: shape {tuple(st['exp_avg'].shape)} vs parameter {tuple(p.shape)}")
+                    self.exp_avg[off:off + k].copy_(st["exp_avg"].reshape(-1))
+                    self.exp_avg_sq[off:off + k].copy_(st["exp_avg_sq"].reshape(-1))
+                    step = max(step, int(float(st["step"])))
+            self.step_count = step
+            return
         self.step_count = int(sd["step"])
         self.exp_avg.copy_(sd["exp_avg"])
         self.exp_avg_sq.copy_(sd["exp_avg_sq"])

@@ -61,10 +61,19 @@ class BucketedGradSync:
         self.pending = [0] * len(self.buckets)
         self.handles: list = []
         self.enabled = self.world > 1
+        self._hooks: list = []  # RemovableHandles of the per-parameter hooks (close() removes them)
         if self.enabled:
             for i, p in enumerate(optimizer.params):
-                p.register_post_accumulate_grad_hook(self._make_hook(i))
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(i)))
         self.reset()
+
+    def close(self) -> None:
+        """Remove the parameter hooks: a later exchange object on the same parameters must be the only one issuing all-reduces."""
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+        self.enabled = False
+        self.handles = []
 
     def reset(self) -> None:
         self.pending = [n for (_, _, n) in self.buckets]

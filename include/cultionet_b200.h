@@ -119,6 +119,9 @@ int cnb_conv2d_wgrad_tiny(const cnb_wgrad_desc* d, int dtype, void* stream);
 /* dst[p][c] = src[p][c] for c < C, 0 for C <= c < dst_stride: gives a skinny tensor (e.g. the 3-channel gradient of a Psi-Net
  * stream) the 16-byte pixel pitch the TMA-fed kernels need */
 int cnb_repitch(const void* src, int src_stride, void* dst, int dst_stride, int64_t P, int C, int dtype, void* stream);
+/* out[b][p][c] = e[b][c] for p < HW: the per-sample GeoEmbeddings vector broadcast over a level's pixels before it joins the
+ * full-scale-skip concatenation (nn/modules/unet_parts.py:739-750, geo_encoding.py:5-26) */
+int cnb_broadcast_pixels(const void* e, void* out, int B, int64_t HW, int C, int dtype, void* stream);
 
 /* fp32 parameter (any strided [n][k][tap] view) -> packed [tap][N][wp_pitch] in `dtype` (wp_pitch >= K; padding columns zeroed):
  *   wp[tap][n][k] = w[n*s_n + k*s_k + tap*s_tap]
@@ -289,11 +292,19 @@ typedef struct {
 
 /* sums: fp64 [nterms][B][4] scratch {P,S,sum t,sum p} (zeroed inside); coef: fp32 [nterms][B][4] (d loss / d{P,S,P',S'} already scaled by
  * weight/(2B)); loss: fp32[1 + nterms] = total, then each term's unweighted loss */
-int cnb_tanimoto_fwd(const cnb_tanimoto_term* terms, int nterms, int B, int64_t HW, float smooth, int depth,
+/* variant selects the reference's LOSS_DICT entry (models/lightning.py:38-88): 0 TanimotoComplementLoss (losses/losses.py:103-218),
+ * 1 TanimotoDistLoss (:221-340; `depth` ignored), 2 CombinedLoss of the two (:62-100) */
+int cnb_tanimoto_fwd(const cnb_tanimoto_term* terms, int nterms, int B, int64_t HW, float smooth, int depth, int variant,
                      double* sums, float* coef, float* loss, void* stream);
 /* dpred = gscale[0] * dloss/dpred */
 int cnb_tanimoto_bwd(const cnb_tanimoto_term* terms, int nterms, int B, int64_t HW, const float* coef, const float* gscale,
                      void* stream);
+
+/* Validation counts of LightningModuleMixin._shared_eval_step (models/lightning.py:374-481) in one pass: out = fp64[12] (zeroed inside)
+ * {valid pixels, sum|dist-bdist|, sum (dist-bdist)^2, edge tp/fp/fn/tn, crop tp/fp/fn/tn, unused}; predictions fp32 [n], labels int64 [n]
+ * (-1 = unlabelled, excluded), a prediction is positive when > thresh (probas_to_labels, :126-136) */
+int cnb_val_counts(const float* dist, const float* edge, const float* crop, const int64_t* y, const float* bdist, int64_t n,
+                   int edge_class, float thresh, double* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Optimiser step over flat fp32 buffers (LightningModuleMixin.configure_optimizers, models/lightning.py:611-683; gradient

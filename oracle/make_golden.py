@@ -26,6 +26,8 @@ CASES = {
     "res_bnfirst": dict(B=2, C=2, T=6, H=20, W=20, hidden=8, dilations=[1, 2], seed=37, y_low=0, attention=2, res=1, batchnorm_first=1),
     "bnfirst_maxpool_odd": dict(B=1, C=2, T=6, H=25, W=25, hidden=8, dilations=[1, 2], seed=41, y_low=-1, batchnorm_first=1,
                                 pool_by_max=1),
+    # GeoEmbeddings broadcast channel block in the towers (use_latlon=True, nn/modules/unet_parts.py:739-750, geo_encoding.py:5-26)
+    "latlon": dict(B=2, C=2, T=6, H=20, W=20, hidden=8, dilations=[1, 2], seed=43, y_low=0, use_latlon=1),
 }
 FULL_GRADS = [
     "pre_unet.conv3.seq.0.weight",
@@ -42,6 +44,8 @@ FULL_GRADS = [
     "encoder.down_c.pool_conv.bias",
     "tower_fusion.tower_a.res_conv.seq.block.0.seq.0.weight",
     "tower_fusion.tower_b.res_conv.res_modules.1.block.0.seq.0.bias",
+    "tower_fusion.tower_a.geo_embeddings.coord_embedding.weight",
+    "tower_fusion.tower_c.geo_embeddings.coord_embedding.bias",
 ]
 ATTENTION = {0: "natten", 1: "spatial_channel", 2: None}
 
@@ -49,11 +53,22 @@ ATTENTION = {0: "natten", 1: "spatial_channel", 2: None}
 def variant_kwargs(cfg: dict) -> dict:
     """TowerUNet constructor arguments of a case beyond the defaults (shared by the generator and the tests)."""
     return dict(attention_weights=ATTENTION[cfg.get("attention", 0)], pool_by_max=bool(cfg.get("pool_by_max", 0)),
-                batchnorm_first=bool(cfg.get("batchnorm_first", 0)), res_block_type="res" if cfg.get("res", 0) else "resa")
+                batchnorm_first=bool(cfg.get("batchnorm_first", 0)), res_block_type="res" if cfg.get("res", 0) else "resa",
+                use_latlon=bool(cfg.get("use_latlon", 0)))
 
 
 def is_variant(cfg: dict) -> bool:
-    return any(cfg.get(k, 0) for k in ("attention", "pool_by_max", "batchnorm_first", "res"))
+    return any(cfg.get(k, 0) for k in ("attention", "pool_by_max", "batchnorm_first", "res", "use_latlon"))
+
+
+def golden_latlon(cfg: dict):
+    """(lon, lat) in decimal degrees per sample for the use_latlon cases, else None."""
+    if not cfg.get("use_latlon", 0):
+        return None
+    rng = np.random.default_rng(cfg["seed"] + 2000)
+    lon = rng.uniform(-180.0, 180.0, size=(cfg["B"], 1))
+    lat = rng.uniform(-90.0, 90.0, size=(cfg["B"], 1))
+    return torch.from_numpy(np.concatenate([lon, lat], axis=1).astype(np.float32))
 
 
 def golden_case(cfg: dict, spec=None):
@@ -77,11 +92,12 @@ def run_reference(cfg: dict):
                           **variant_kwargs(cfg))
     spec = None
     if is_variant(cfg):  # the parameter inventory of a variant comes from the reference model itself
-        spec = [(k, tuple(v.shape)) for k, v in model.state_dict().items()]
+        spec = [(k.replace("._orig_mod.", "."), tuple(v.shape)) for k, v in model.state_dict().items()]
     spec, sd, x, y, bdist = golden_case(cfg, spec)
-    model.load_state_dict(sd, strict=True)
+    compiled = {k.replace("._orig_mod.", "."): k for k in model.state_dict()}  # torch.compile wrappers prefix their keys
+    model.load_state_dict({compiled[k]: v for k, v in sd.items()}, strict=True)
     model.train()
-    out = model(x)
+    out = model(x, latlon_coords=golden_latlon(cfg))
     cls = ref.TanimotoComplementLoss()
     reg = ref.TanimotoComplementLoss(transform_logits=False, one_hot_targets=False)
     mask = (y != -1).long().unsqueeze(1) if int(y.min()) == -1 else None
@@ -90,8 +106,8 @@ def run_reference(cfg: dict):
     c = cls(out["crop"], ((y > 0) & (y < 2)).long(), mask=mask)
     loss = (d + e + c) / 3.0
     loss.backward()
-    grads = {n: p.grad.detach().clone() for n, p in model.named_parameters()}
-    buffers = {n: b.detach().clone() for n, b in model.named_buffers()}
+    grads = {n.replace("._orig_mod.", "."): p.grad.detach().clone() for n, p in model.named_parameters()}
+    buffers = {n.replace("._orig_mod.", "."): b.detach().clone() for n, b in model.named_buffers()}
     return out, (loss, d, e, c), grads, buffers, spec
 
 

@@ -63,6 +63,9 @@ def natten_get_window_start(index: int, length: int, kernel_size: int, dilation:
     return ni
 
 
+_GATHER_BYTES = 6 << 30  # the gathered neighbour tensor [B, heads, H, k, W, k, hd] is materialised: process sample by sample above this
+
+
 def neighbor_index(length: int, kernel_size: int, dilation: int) -> torch.Tensor:
     """[length, k] long tensor: neighbour coordinates along one axis."""
     assert kernel_size * dilation <= length, "natten requires kernel_size * dilation <= min(H, W)"
@@ -77,6 +80,8 @@ def neighbor_index(length: int, kernel_size: int, dilation: int) -> torch.Tensor
 def na2d_qk(q: torch.Tensor, k: torch.Tensor, kernel_size: int, dilation: int) -> torch.Tensor:
     """q, k: [B, heads, H, W, hd] -> logits [B, heads, H, W, k*k]."""
     B, nh, H, W, hd = q.shape
+    if B > 1 and B * nh * H * W * kernel_size * kernel_size * hd * 4 > _GATHER_BYTES:  # samples are independent: bound the gather
+        return torch.cat([na2d_qk(q[b:b + 1], k[b:b + 1], kernel_size, dilation) for b in range(B)], dim=0)
     iy = neighbor_index(H, kernel_size, dilation).to(q.device)  # [H, k]
     ix = neighbor_index(W, kernel_size, dilation).to(q.device)  # [W, k]
     # gather neighbours: [B, nh, H, k, W, k, hd]
@@ -89,6 +94,8 @@ def na2d_qk(q: torch.Tensor, k: torch.Tensor, kernel_size: int, dilation: int) -
 def na2d_av(attn: torch.Tensor, v: torch.Tensor, kernel_size: int, dilation: int) -> torch.Tensor:
     """attn: [B, heads, H, W, k*k], v: [B, heads, H, W, hd] -> [B, heads, H, W, hd]."""
     B, nh, H, W, hd = v.shape
+    if B > 1 and B * nh * H * W * kernel_size * kernel_size * hd * 4 > _GATHER_BYTES:
+        return torch.cat([na2d_av(attn[b:b + 1], v[b:b + 1], kernel_size, dilation) for b in range(B)], dim=0)
     iy = neighbor_index(H, kernel_size, dilation).to(v.device)
     ix = neighbor_index(W, kernel_size, dilation).to(v.device)
     vv = v[:, :, iy][:, :, :, :, ix].permute(0, 1, 2, 4, 3, 5, 6)

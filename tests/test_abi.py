@@ -20,7 +20,7 @@ def test_header_declares_the_bound_functions():
     from cultionet_b200 import _lib
 
     declared = set(declared_symbols())
-    bound = set(_lib.EXPORTED_SYMBOLS) | set(_lib._CUDA_ONLY_PROTOS)
+    bound = set(_lib.EXPORTED_SYMBOLS)
     assert bound <= declared, sorted(bound - declared)
     assert declared <= bound, sorted(declared - bound)
 

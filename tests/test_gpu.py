@@ -148,12 +148,12 @@ def test_adamw_and_clipping(dev):
     cases.adamw_case(dev, n=1_000_003)
 
 
-@pytest.mark.parametrize("name", ["small_masked", "odd_dil3", "sca_maxpool", "res_bnfirst", "bnfirst_maxpool_odd"])
+@pytest.mark.parametrize("name", ["small_masked", "odd_dil3", "sca_maxpool", "res_bnfirst", "bnfirst_maxpool_odd", "latlon"])
 def test_model_reproduces_reference_golden_fp32(dev, name):
     cases.model_vs_golden(dev, name, F32)
 
 
-@pytest.mark.parametrize("name", ["small_masked", "odd_dil3", "sca_maxpool", "res_bnfirst", "bnfirst_maxpool_odd"])
+@pytest.mark.parametrize("name", ["small_masked", "odd_dil3", "sca_maxpool", "res_bnfirst", "bnfirst_maxpool_odd", "latlon"])
 def test_model_reproduces_reference_golden_bf16(dev, name):
     cases.model_vs_golden(dev, name, BF16)
 
@@ -469,14 +469,16 @@ def test_conv_batchnorm_activation_fused_eval_epilogue(dev, cfg):
     cases.conv_bn_act_eval_case(dev, *cfg)
 
 
-def test_model_eval_mode_bf16_fused_epilogue(dev):
+@pytest.mark.parametrize("hidden,batch", [(32, 2), (64, 8)])
+def test_model_eval_mode_bf16_fused_epilogue(dev, hidden, batch):
     """Eval-mode bf16 model (every ConvBlock2d runs conv + BatchNorm + SiLU as one tcgen05 launch) against the fp32 oracle port, with
     running statistics that describe the data (one fp32 training-mode pass with momentum 1 calibrates them: random running statistics
-    let the activations drift layer by layer and bf16 rounding is amplified to 7 % with or without the fusion)."""
+    let the activations drift layer by layer and bf16 rounding is amplified to 7 % with or without the fusion).  (64, 8) is BASELINE
+    configs[4]'s window shape x=[b,5,12,140,140] at its hidden size."""
     from oracle import towerunet_port as port
-    from tests.util import TOL_OUT_BF16, mine_from_state_dict
+    from tests.util import MASK_AGREEMENT_BF16_RANDOM_INIT, TOL_OUT_BF16, mine_from_state_dict
 
-    cfg = dict(B=2, C=5, T=12, H=140, W=140, hidden=32, dilations=[1, 2])
+    cfg = dict(B=batch, C=5, T=12, H=140, W=140, hidden=hidden, dilations=[1, 2])
     spec = port.param_spec(cfg["C"], cfg["T"], cfg["hidden"], cfg["dilations"])
     sd = port.synth_state_dict(spec, seed=3)
     g = torch.Generator().manual_seed(3)
@@ -495,3 +497,54 @@ def test_model_eval_mode_bf16_fused_epilogue(dev):
         agree = float(((out["crop"] > 0.5) == (want["crop"] > 0.5)).float().mean())
     print("eval bf16 (calibrated running statistics)", errs, agree)
     assert all(e < TOL_OUT_BF16 for e in errs.values()), errs
+    assert agree >= MASK_AGREEMENT_BF16_RANDOM_INIT, agree
+
+
+def test_model_cfg2_full_size_train_bf16(dev):
+    """BASELINE configs[1] at its FULL size -- x=[32,5,24,128,128], hidden 64, bf16, training-mode BatchNorm, forward + loss + backward
+    -- against the fp32 oracle port on the same GPU (TF32 off): outputs / loss 2e-2, all-parameter gradient error 5e-2, worst single
+    parameter 2e-1, random-init mask bar (tests/util.py)."""
+    cfg = dict(B=32, C=5, T=24, H=128, W=128, hidden=64, dilations=[1, 2])
+    rep = cases.model_vs_port(dev, cfg, BF16)
+    print("cfg2 FULL size bf16 train", rep)
+    torch.cuda.empty_cache()
+
+
+def _cfg4_natten():
+    from cultionet_b200.nn.modules import unet_parts
+
+    saved = {k: dict(v) for k, v in unet_parts.NATTEN_PARAMS.items()}
+    for lvl in ("a", "b", "c"):
+        unet_parts.NATTEN_PARAMS[lvl].update(natten_kernel_size=7, natten_dilation=2)
+    nat = {lvl: dict(heads=saved[lvl]["natten_num_heads"], k=7, d=2) for lvl in ("a", "b", "c")}
+    return saved, nat
+
+
+def test_model_cfg4_full_size_forward_bf16(dev):
+    """BASELINE configs[3] at its FULL size -- x=[16,5,36,256,256], hidden 64, neighbourhood attention kernel 7 dilation 2, bf16 --
+    forward + loss against the fp32 oracle port (no autograd graph on either side: the fp32 port's saved activations at this size
+    would not fit next to the model)."""
+    from cultionet_b200.nn.modules import unet_parts
+
+    saved, nat = _cfg4_natten()
+    try:
+        cfg = dict(B=16, C=5, T=36, H=256, W=256, hidden=64, dilations=[1, 2], natten=nat)
+        rep = cases.model_vs_port(dev, cfg, BF16, check_grads=False)
+        print("cfg4 FULL size bf16 forward", rep)
+    finally:
+        unet_parts.NATTEN_PARAMS.update(saved)
+        torch.cuda.empty_cache()
+
+
+def test_model_cfg4_geometry_train_bf16(dev):
+    """configs[3]'s geometry (T=36, 256x256, hidden 64, NA k7 d2) at batch 2 WITH gradients, bf16 vs the fp32 oracle port."""
+    from cultionet_b200.nn.modules import unet_parts
+
+    saved, nat = _cfg4_natten()
+    try:
+        cfg = dict(B=2, C=5, T=36, H=256, W=256, hidden=64, dilations=[1, 2], natten=nat)
+        rep = cases.model_vs_port(dev, cfg, BF16)
+        print("cfg4 geometry bf16 train", rep)
+    finally:
+        unet_parts.NATTEN_PARAMS.update(saved)
+        torch.cuda.empty_cache()

@@ -44,8 +44,8 @@ def test_option_errors_mirror_the_reference():
         cb.TowerUNet(in_channels=2, in_time=6, hidden_channels=8, res_block_type="res", attention_weights="spatial_channel")
     with pytest.raises(AssertionError):
         cb.TowerUNet(in_channels=2, in_time=6, hidden_channels=8, res_block_type="resx")
-    with pytest.raises(NotImplementedError):
-        cb.TowerUNet(in_channels=2, in_time=6, hidden_channels=8, use_latlon=True)
+    with pytest.raises(NotImplementedError):  # the Tanimoto family of LOSS_DICT is built, the rest is not
+        cb.CultionetLitModel(in_channels=2, in_time=6, hidden_channels=8, loss_name="TverskyLoss")
 
 
 def test_variant_state_dict_keys_match_the_reference_inventory():
@@ -53,7 +53,7 @@ def test_variant_state_dict_keys_match_the_reference_inventory():
     from tests.util import golden_spec, load_golden, mine_from_state_dict
     from oracle.make_golden import golden_case
 
-    for name in ("sca_maxpool", "res_bnfirst", "bnfirst_maxpool_odd"):
+    for name in ("sca_maxpool", "res_bnfirst", "bnfirst_maxpool_odd", "latlon"):
         cfg, z = load_golden(name)
         spec, sd, *_ = golden_case(cfg, golden_spec(z))
         m = mine_from_state_dict(cfg, sd, "cpu")

@@ -123,7 +123,7 @@ def test_adamw_and_clipping(dev):
     cases.adamw_case(dev)
 
 
-@pytest.mark.parametrize("name", ["small_masked", "odd_dil3", "sca_maxpool", "res_bnfirst", "bnfirst_maxpool_odd"])
+@pytest.mark.parametrize("name", ["small_masked", "odd_dil3", "sca_maxpool", "res_bnfirst", "bnfirst_maxpool_odd", "latlon"])
 def test_model_reproduces_reference_golden(dev, name):
     cases.model_vs_golden(dev, name)
 
