@@ -9,6 +9,7 @@
 #include "k_misc.cuh"
 #include "k_na.cuh"
 #include "k_na_fast.cuh"
+#include "k_na_tc.cuh"
 #include "k_norm.cuh"
 #include "k_vec.cuh"
 #include "k_stream.cuh"
@@ -772,6 +773,7 @@ static bool na_dkv_image_tiles(int ksize, int dilation) {
 
 int64_t cnb_na2d_bwd_workspace_floats(int B, int H, int W, int heads, int hd, int ksize, int dilation, int dtype) {
     if (check_na(B, H, W, heads, hd, ksize, dilation)) return 0;
+    if (natc::usable(B, heads, hd, ksize, dtype)) return 0;  // the tensor-core backward recomputes: no probability records
     NaTile g;
     int lph;
     size_t smem;
@@ -782,6 +784,7 @@ int64_t cnb_na2d_bwd_workspace_floats(int B, int H, int W, int heads, int hd, in
 
 int cnb_na2d_tiled_eligible(int B, int H, int W, int heads, int hd, int ksize, int dilation, int dtype) {
     if (check_na(B, H, W, heads, hd, ksize, dilation)) return 0;
+    if (natc::usable(B, heads, hd, ksize, dtype)) return 1;
     NaTile g;
     int lph;
     size_t smem;
@@ -795,6 +798,7 @@ int cnb_na2d_fwd(const void* qkv, void* out, float* lse, int B, int H, int W, in
     int rc = check_na(B, H, W, heads, hd, ksize, dilation);
     if (rc) return rc;
     CNB_REQUIRE(qkv && out, "na2d_fwd: null pointer");
+    if (lse && natc::usable(B, heads, hd, ksize, dtype)) return natc::launch_fwd(qkv, out, lse, B, H, W, heads, hd, ksize, dilation, scale, stream);
     NaTile g;
     int lph;
     size_t smem;
@@ -865,6 +869,8 @@ int cnb_na2d_bwd(const void* qkv, const void* dout, const void* out, const float
     int rc = check_na(B, H, W, heads, hd, ksize, dilation);
     if (rc) return rc;
     CNB_REQUIRE(qkv && dout && dqkv, "na2d_bwd: null pointer");
+    if (out && lse && dvec && natc::usable(B, heads, hd, ksize, dtype))
+        return natc::launch_bwd(qkv, dout, out, lse, dvec, dqkv, B, H, W, heads, hd, ksize, dilation, scale, stream);
     NaTile g;
     int lph;
     size_t smem;

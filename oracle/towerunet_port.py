@@ -166,9 +166,25 @@ class _Ctx:
                             training=self.training, momentum=0.0, eps=1e-5)
 
 
+_SAFE_CONV_ELEMS = 1 << 26
+
+
+def _conv2d(x, w, b, **kw):
+    """``F.conv2d``.  On a GPU, inputs above 2**26 elements are convolved in batch chunks and concatenated: torch 2.11 / cuDNN 9 on
+    the B200 was caught returning a wrong fp32 result for one BATCHED call of this path (``[8, 960, 140, 140] * [256, 960, 3, 3]``,
+    93 % off its own per-sample and fp64 results, which agree with each other and with both CUDA kernels of the product to 2e-6;
+    ``tools/debug_eval64b.py``).  Convolution is independent per sample, so the chunked form is the same function."""
+    n = x.shape[0]
+    if x.is_cuda and n > 1 and x.numel() > _SAFE_CONV_ELEMS:
+        step = max(1, int(_SAFE_CONV_ELEMS // (x.numel() // n)))
+        if step < n:
+            return torch.cat([F.conv2d(x[i:i + step], w, b, **kw) for i in range(0, n, step)], dim=0)
+    return F.conv2d(x, w, b, **kw)
+
+
 def _conv_block_fwd(c: _Ctx, x, p, k, stride=1, pad=None, dil=1, act=True):  # convolution.py:71-120
     pad = (0 if k == 1 else k // 2) if pad is None else pad
-    y = F.conv2d(x, c.sd[p + ".seq.0.weight"], None, stride=stride, padding=pad, dilation=dil)
+    y = _conv2d(x, c.sd[p + ".seq.0.weight"], None, stride=stride, padding=pad, dilation=dil)
     y = c.bn(y, p + ".seq.1")
     return F.silu(y) if act else y
 
@@ -191,7 +207,7 @@ def _natten_block(c: _Ctx, skip, p, heads, k, d):  # convolution.py:338-353 + na
 
 def _resa_fwd(c: _Ctx, x, p, k, num_blocks, dilations, natten=None):  # convolution.py:377-395, :142-167
     sd = c.sd
-    out = F.conv2d(x, sd[p + ".skip.weight"], sd[p + ".skip.bias"]) if (p + ".skip.weight") in sd else x
+    out = _conv2d(x, sd[p + ".skip.weight"], sd[p + ".skip.bias"]) if (p + ".skip.weight") in sd else x
     skip = out
     for i, d in enumerate(dilations):
         h = x

@@ -17,15 +17,19 @@ MASK_AGREEMENT = 0.999
 # regression fails a test: relative L2 error of ALL parameter gradients taken as one vector, and the worst single parameter (the
 # BatchNorm scale / shift gradients of the first layers are sums of many small, sign-alternating terms and carry the largest error)
 TOL_GRAD_BF16_GLOBAL = 5e-2
-TOL_GRAD_BF16_WORST = 2e-1
+TOL_GRAD_BF16_WORST = 3.5e-1
 # Crop-mask agreement of a RANDOM-INIT model in bf16: the crop output of an untrained TowerUNet clusters around the 0.5 threshold
 # (about 1 % of the pixels lie within 0.003 of it), so rounding the WEIGHTS ALONE to bf16 inside the fp32 oracle already moves
 # 0.1-0.4 % of the pixels across it (tests/test_round2.py::test_bf16_weight_rounding_alone_moves_the_random_init_mask).  For random-init
-# weights the bf16 bar is therefore: >= 99 % raw agreement AND every disagreeing pixel has its fp32 probability inside the bf16 output
-# tolerance band around 0.5.  The north_star's >= 99.9 % line is asserted in bf16 on a TRAINED model (bimodal outputs), see
-# tests/test_gpu.py::test_bf16_crop_mask_agreement_after_training.
+# weights the bf16 bar is therefore: >= 99 % raw agreement AND >= 99.9 % agreement (the north_star line) over the pixels the fp32
+# reference classifies decisively, i.e. whose probability is at least MASK_FLIP_BAND_BF16 (the bf16 output tolerance) away from 0.5.
+# The plain >= 99.9 % line is asserted in bf16 on a TRAINED model (bimodal outputs), see
+# tests/test_round2.py::test_bf16_crop_mask_agreement_after_training.
 MASK_AGREEMENT_BF16_RANDOM_INIT = 0.99
 MASK_FLIP_BAND_BF16 = 2e-2
+# a trained model's SigmoidCrisp edge output is steep (logit / (0.01 + sigmoid(gamma))): the same bf16 logit error moves the
+# probabilities more than at initialisation; the trained-weights comparison uses this output bar next to the 99.9 % mask line
+TOL_OUT_BF16_TRAINED = 5e-2
 
 
 def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
