@@ -74,6 +74,10 @@ class WgradDesc(C.Structure):
     ]
 
 
+class MultiCopyEntry(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("n", C.c_int32), ("mode", C.c_int32)]
+
+
 class TanimotoTerm(C.Structure):
     _fields_ = [
         ("pred", C.c_void_p), ("target", C.c_void_p), ("mask", C.c_void_p), ("dpred", C.c_void_p),
@@ -98,6 +102,7 @@ _PROTOS = {
     "cnb_conv2d_wgrad_tc_eligible": [C.POINTER(WgradDesc), _i],
     "cnb_conv2d_wgrad_tiny": [C.POINTER(WgradDesc), _i, _vp],
     "cnb_repitch": [_vp, _i, _vp, _i, _i64, _i, _i, _vp],
+    "cnb_multi_copy": [C.POINTER(MultiCopyEntry), _i, _i, _vp],
     "cnb_broadcast_pixels": [_vp, _vp, _i, _i64, _i, _i, _vp],
     "cnb_pack_weight": [_vp, _vp, _i, _i, _i, _i, _i, _i64, _i64, _i64, _vp],
     "cnb_pack_weight2": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i64, _i64, _i64, _vp],

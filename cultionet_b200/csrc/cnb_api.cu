@@ -134,7 +134,7 @@ int cnb_conv2d_tc_eligible(const cnb_conv_desc* d, int dtype) {
 #else
     if (check_conv_desc(d)) return 0;
     if (!tc::eligible(d, dtype)) return 0;
-    return 1;  // (2 would announce BatchNorm sums from the epilogue; no kernel offers that at present)
+    return tc::stats_ok(d) ? 2 : 1;  // 2: the epilogue can also produce BatchNorm's per-channel sums (cnb_conv_desc::stats)
 #endif
 }
 
@@ -267,6 +267,20 @@ int cnb_repitch(const void* src, int src_stride, void* dst, int dst_stride, int6
                    (T*)dst, dst_stride, (long)P, C);
     });
     CNB_CHECK_LAUNCH("repitch_kernel");
+    return CNB_OK;
+}
+
+int cnb_multi_copy(const void* table, int n_entries, int max_len, void* stream) {
+    CNB_REQUIRE(table && n_entries > 0 && max_len > 0, "multi_copy: bad arguments");
+    const MultiCopyEntry* e = (const MultiCopyEntry*)table;  // HOST memory: copied into the launch arguments below
+    const int bx = cnb_clamp_grid(cnb_div_up(max_len, 256), 64);
+    for (int i = 0; i < n_entries; i += MULTI_COPY_BATCH) {
+        const int n = n_entries - i < MULTI_COPY_BATCH ? n_entries - i : MULTI_COPY_BATCH;
+        MultiCopyBatch batch;
+        memcpy(batch.e, e + i, sizeof(MultiCopyEntry) * n);
+        CNB_LAUNCH(multi_copy_kernel, dim3(bx, n), dim3(256), 0, (cudaStream_t)stream, batch);
+    }
+    CNB_CHECK_LAUNCH("multi_copy_kernel");
     return CNB_OK;
 }
 

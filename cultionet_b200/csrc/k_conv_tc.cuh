@@ -382,6 +382,30 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 if (col0 >= p.N) break;
                 uint32_t v[32];
                 tmem_ld32(taddr + (uint32_t)(c * 32), v);
+                if (p.stats) {
+                    // BatchNorm batch statistics of this chunk (training-mode ConvBlock2d: no bias, no fused epilogue, N % 32 == 0):
+                    // per-channel sum and sum of squares of the STORED (bf16-rounded) values over the warp's 32 pixel rows -- one
+                    // transposing reduction per quantity (31 shuffles), then a shared-memory atomic per lane; the CTA flushes its
+                    // [2, N] partials to global memory once, at the end.  The separate statistics pass (a full read of the output) goes.
+                    uint32_t packed[16];
+                    float vals[32], sq[32];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        packed[j] = (has_taps && valid) ? cnb_pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])) : 0u;
+                        const float f0 = cnb_bits2f(packed[j] << 16), f1 = cnb_bits2f(packed[j] & 0xffff0000u);
+                        vals[2 * j] = f0, vals[2 * j + 1] = f1;
+                        sq[2 * j] = f0 * f0, sq[2 * j + 1] = f1 * f1;
+                    }
+                    const float s1 = warp_transpose_sum32(vals), s2 = warp_transpose_sum32(sq);
+                    atomicAdd(&sm_stats[col0 + lane], s1);
+                    atomicAdd(&sm_stats[p.N + col0 + lane], s2);
+                    if (valid) {
+                        uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                    }
+                    continue;
+                }
                 if (!valid) continue;
                 bf16_t* ochunk = orow + c * 32;
                 if (p.nseg) {
@@ -554,6 +578,17 @@ inline bool eligible(const cnb_conv_desc* d, int dtype) {
     for (int i = 0; i < d->nout; ++i)
         if (d->out_seg_c[i] % 32 != 0 || d->out_seg_stride[i] % 8 != 0 || reinterpret_cast<uintptr_t>(d->out_seg[i]) % 16 != 0) return false;
     return encode_tiled_fn() != nullptr;
+}
+
+// BatchNorm statistics from the epilogue (cnb_conv_desc::stats): plain single-destination convolution without bias / fused epilogue whose
+// column count is a whole number of 32-column chunks (every ConvBlock2d of the TowerUNet); CNB_CONV_STATS=0 switches it off (A/B)
+inline bool stats_ok(const cnb_conv_desc* d) {
+    static const bool on = [] {
+        const char* e = getenv("CNB_CONV_STATS");
+        return !(e && e[0] == '0');
+    }();
+    return on && d->N % 32 == 0 && d->N <= STATS_MAX_N && !d->bias && !d->ep_scale && d->nout == 0 && d->out && d->out_stride % 8 == 0 &&
+           reinterpret_cast<uintptr_t>(d->out) % 16 == 0;
 }
 
 // CNB_PDL_TC=0 launches the tensor-core kernels without the programmatic-dependent-launch attribute (A/B timing)
@@ -733,7 +768,10 @@ inline int conv_tc_launch(const cnb_conv_desc* d, cudaStream_t stream) {
     p.log2_tw = 0;
     while ((1 << p.log2_tw) < p.TW) ++p.log2_tw;
     p.stats = nullptr;
-    if (d->stats) return 3;  // statistics in the epilogue: measured slower than the separate pass (see the epilogue note above)
+    if (d->stats) {
+        if (!stats_ok(d) || !p.vec_ok) return 3;
+        p.stats = reinterpret_cast<float*>(d->stats);
+    }
     p.num_tiles = cnb_div_up(d->N, BN) * p.m_tiles;
     switch (BN) {
         case 256: return launch_bn<256>(p, stream);

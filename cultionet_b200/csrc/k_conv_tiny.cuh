@@ -203,6 +203,27 @@ __global__ void repitch_kernel(const T* __restrict__ src, int src_stride, T* __r
     }
 }
 
+// Multi-tensor copy / accumulate of small fp32 segments: one launch for what would otherwise be one tiny torch kernel per segment
+// (stacking the Psi-Net stream parameters, scattering BatchNorm / LayerNorm / scalar parameter gradients into the flat gradient
+// buffer, writing stacked running statistics back).  grid = (blocks per segment, segments).
+struct MultiCopyEntry {
+    const float* src;
+    float* dst;
+    int n;
+    int mode;  // 0: dst = src, 1: dst += src
+};
+// the segment table travels BY VALUE in the kernel arguments (160 x 24 bytes, inside the 4 KB argument space): nothing to upload, and a
+// captured CUDA graph keeps its own copy
+constexpr int MULTI_COPY_BATCH = 160;
+struct MultiCopyBatch {
+    MultiCopyEntry e[MULTI_COPY_BATCH];
+};
+__global__ void multi_copy_kernel(const __grid_constant__ MultiCopyBatch batch) {
+    CNB_PDL_SYNC();
+    const MultiCopyEntry& e = batch.e[blockIdx.y];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < e.n; i += gridDim.x * blockDim.x) e.dst[i] = e.mode ? e.dst[i] + e.src[i] : e.src[i];
+}
+
 // out[b][p][c] = e[b][c]: a per-sample vector over the pixels of a level (GeoEmbeddings, reference unet_parts.py:742-750)
 template <typename T>
 __global__ void broadcast_pixels_kernel(const T* __restrict__ e, T* __restrict__ out, int B, long HW, int C) {

@@ -701,7 +701,11 @@ inline int launch_bwd(const void* qkv, const void* dout, const void* out, const 
         }));
     }
     // key side: 16-row tiles (16 warps) where one 8-row CTA per SM would be all that fits (k 7, head_dim 64), 8-row tiles otherwise
-    if (ksize == 7 && hd == 64) {
+    static const int dkv_th = [] {  // CNB_NA_DKV_TH=8 forces the 8-row key tiles everywhere (A/B timing)
+        const char* e = getenv("CNB_NA_DKV_TH");
+        return (e && e[0] == '8') ? 8 : 16;
+    }();
+    if (ksize == 7 && hd == 64 && dkv_th == 16) {
         constexpr int TH = 16;
         dim3 grid;
         const Geom g = make_geom<TH>(B, H, W, heads, dilation, scale, &grid);

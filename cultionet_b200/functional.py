@@ -168,6 +168,36 @@ STATS_MAX_N = 1024  # csrc/k_conv_tc.cuh
 MERGE_SOURCE_DGRADS = os.environ.get("CNB_MERGE_DGRAD", "1") != "0"  # data gradient of a multi-source convolution as one split-output launch (A/B switch for bench runs)
 
 
+# Zero-initialised [2, N] slices for the BatchNorm sums the tcgen05 epilogue accumulates: one arena per device, cleared by ONE fill at the
+# top of a forward (reset_stats_arena, called by TowerUNet.forward in training mode) instead of one torch.zeros per convolution.  Slices
+# are only handed out once between two resets, so a slice is always clean; when the arena runs out the caller gets a fresh tensor.
+_STATS_ARENA: dict = {}
+_STATS_ARENA_FLOATS = 1 << 17
+
+
+def reset_stats_arena(dev) -> None:
+    dev = torch.device(dev)
+    if dev.type != "cuda":
+        return
+    ent = _STATS_ARENA.get(dev)
+    if ent is None:
+        _STATS_ARENA[dev] = [torch.zeros(_STATS_ARENA_FLOATS, dtype=torch.float32, device=dev), 0]
+        return
+    if ent[1] > 0:
+        ent[0][:ent[1]].zero_()
+        ent[1] = 0
+
+
+def _stats_slice(N: int, dev) -> torch.Tensor:
+    ent = _STATS_ARENA.get(torch.device(dev))
+    n = 2 * N
+    if ent is None or ent[1] + n > _STATS_ARENA_FLOATS:
+        return torch.zeros((2, N), dtype=torch.float32, device=dev)
+    off = ent[1]
+    ent[1] = off + (n + 31) // 32 * 32
+    return ent[0][off:off + n].view(2, N)
+
+
 def _launch_conv(sources, src_channels, wp, w_row_off, w_row_stride, w_tap_stride, N, bias, out, geom, transposed, dtype,
                  want_stats=False, out_segments=None, epilogue=None):
     """Launches the convolution; with ``want_stats`` returns the [2, N] fp32 BatchNorm partial sums the tcgen05 epilogue produced
@@ -212,7 +242,7 @@ def _launch_conv(sources, src_channels, wp, w_row_off, w_row_stride, w_tap_strid
     stats = None
     if want_stats and N <= STATS_MAX_N and CONV_BACKEND != "generic" and not _lib.is_emulator():
         if _lib.lib().cnb_conv2d_tc_eligible(C.byref(d), dtype_code(dtype)) == 2:
-            stats = torch.zeros((2, N), dtype=torch.float32, device=out.device)
+            stats = _stats_slice(N, out.device)
             d.stats = stats.data_ptr()
     flops = 2.0 * B * (Hin * Win if transposed else Hout * Wout) * N * sum(src_channels) * KH * KW  # algorithmic
     detail = None
@@ -242,6 +272,7 @@ class direct_param_grads:
         self.prev = DIRECT_PARAM_GRAD[0]
         DIRECT_PARAM_GRAD[0] = bool(self.enabled)
         _DIRECT_WRITTEN.clear()
+        _PENDING_SMALL.clear()
         return self
 
     def __exit__(self, *exc):
@@ -251,6 +282,7 @@ class direct_param_grads:
             for _, dwp, *_ in _PENDING_UNPACK.values():
                 dwp.zero_()
             _PENDING_UNPACK.clear()
+            _PENDING_SMALL.clear()
         else:
             flush_weight_gradients()
         return False
@@ -283,6 +315,19 @@ def _wgrad_accumulator(param, taps, N, Ctot, dev):
     return buf
 
 
+_DERIVED_ACC: dict = {}
+
+
+def _derived_accumulator(key, taps, N, Ctot, dev):
+    hit = _DERIVED_ACC.get(key)
+    if hit is not None and hit.shape == (taps, N, Ctot) and hit.device == dev:
+        return hit
+    if len(_DERIVED_ACC) > 256:
+        _DERIVED_ACC.clear()
+    buf = _DERIVED_ACC[key] = torch.zeros((taps, N, Ctot), dtype=torch.float32, device=dev)
+    return buf
+
+
 # Weight gradients taken directly are unpacked from their accumulators into ``param.grad`` by ONE launch when the backward pass
 # ends (``direct_param_grads.__exit__``): id(param) -> (param ref, accumulator, gradient buffer, taps, rows, cols, strides, mode).
 _PENDING_UNPACK: dict = {}
@@ -299,8 +344,21 @@ def _defer_unpack(param, dwp, target, taps, rows, cols, s_n, s_k, s_tap, acc_fla
     return True
 
 
+def flush_small_gradients() -> int:
+    if not _PENDING_SMALL:
+        return 0
+    entries = [(src.data_ptr(), dst.data_ptr(), src.numel(), mode) for src, dst, mode in _PENDING_SMALL]
+    ref = _PENDING_SMALL[0][1]
+    keep = list(_PENDING_SMALL)  # the sources stay referenced until the launch is enqueued
+    _PENDING_SMALL.clear()
+    multi_copy(entries, ref)
+    del keep
+    return len(entries)
+
+
 def flush_weight_gradients() -> int:
     """Unpack every deferred weight-gradient accumulator into its gradient buffer (and clear it) with one launch; returns how many."""
+    flush_small_gradients()
     if not _PENDING_UNPACK:
         return 0
     entries = list(_PENDING_UNPACK.values())
@@ -331,6 +389,107 @@ def flush_weight_gradients() -> int:
     raw, ndesc, total_tiles, max_taps = plan
     call("cnb_unpack_wgrads_batched", ptr(raw), ndesc, total_tiles, max_taps, stream_ptr(raw))
     return ndesc
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Multi-tensor copies of small fp32 segments (``cnb_multi_copy``): ONE launch for parameter plumbing that would otherwise be one tiny
+# torch kernel per tensor -- stacking the Psi-Net stream parameters, scattering the BatchNorm / LayerNorm / scalar parameter gradients
+# of a backward pass into the flat gradient buffer.
+# ----------------------------------------------------------------------------------------------------------------
+def multi_copy(entries, ref: torch.Tensor) -> None:
+    """``entries``: ``[(src data_ptr, dst data_ptr, n, mode)]`` over fp32 memory on ``ref``'s device (mode 0 copies, 1 accumulates).  The
+    table is a host array handed to ``cnb_multi_copy``, which passes it to the kernel by value."""
+    if not entries:
+        return
+    table = (_lib.MultiCopyEntry * len(entries))()
+    max_len = 1
+    for e, (src, dst, n, mode) in zip(table, entries):
+        e.src, e.dst, e.n, e.mode = src, dst, n, mode
+        max_len = max(max_len, n)
+    call("cnb_multi_copy", table, len(entries), max_len, stream_ptr(ref))
+
+
+# Small parameter gradients (BatchNorm / LayerNorm scale and shift, the final-combine scalars, stacked Psi-Net parameters) taken
+# directly: (source tensor, gradient buffer, mode) collected during backward, scattered by ONE launch in flush_weight_gradients().
+_PENDING_SMALL: list = []
+
+
+def _defer_small_grad(param, src: torch.Tensor) -> bool:
+    """True when ``src`` (fp32, contiguous, ``param.numel()`` elements) will be written into ``param.grad`` at the end of backward; the
+    backward then returns None for that parameter."""
+    if src.dtype != torch.float32 or not src.is_contiguous():
+        return False
+    target, acc = _direct_grad_target(param, param.shape)
+    if target is None:
+        return False
+    _PENDING_SMALL.append((src, target, acc))
+    return True
+
+
+def _small_grad(param, src: torch.Tensor):
+    """``None`` when the gradient was taken directly, else ``src`` shaped like the parameter (autograd accumulates it)."""
+    return None if _defer_small_grad(param, src) else src.view(param.shape)
+
+
+def _zeros_like_cached(n: int, dev) -> torch.Tensor:
+    z = _ZEROS.get(dev)
+    if z is None or z.numel() < n:
+        z = _ZEROS[dev] = torch.zeros(max(n, 4096), dtype=torch.float32, device=dev)
+    return z
+
+
+_ZEROS: dict = {}
+
+
+class _StackParamsFn(torch.autograd.Function):
+    """``total`` fp32 elements holding parameter ``i`` at ``offsets[i]`` and zeros elsewhere -- ``torch.cat`` / ``F.pad`` of small
+    parameters as ONE launch; the backward hands each parameter its slice (directly into its gradient buffer when possible)."""
+
+    @staticmethod
+    def forward(ctx, total, offsets, *params):
+        check_device(*params)
+        ps = [_contig(p.detach()) for p in params]
+        out = torch.empty((total,), dtype=torch.float32, device=ps[0].device)
+        zeros = _zeros_like_cached(total, out.device)
+        entries, pos = [], 0
+        for p, off in sorted(zip(ps, offsets), key=lambda t: t[1]):
+            if off > pos:
+                entries.append((zeros.data_ptr(), out.data_ptr() + 4 * pos, off - pos, 0))
+            entries.append((p.data_ptr(), out.data_ptr() + 4 * off, p.numel(), 0))
+            pos = off + p.numel()
+        if pos < total:
+            entries.append((zeros.data_ptr(), out.data_ptr() + 4 * pos, total - pos, 0))
+        multi_copy(entries, out)
+        ctx.params, ctx.offsets = params, offsets
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _contig(g.float())
+        grads = []
+        for i, (p, off) in enumerate(zip(ctx.params, ctx.offsets)):
+            if not ctx.needs_input_grad[2 + i]:
+                grads.append(None)
+                continue
+            grads.append(_small_grad(p, g[off:off + p.numel()]))
+        ctx.keep = g
+        return (None, None, *grads)
+
+
+def stack_params(params: Sequence[torch.Tensor], offsets: Sequence[int], total: int) -> torch.Tensor:
+    out = _StackParamsFn.apply(int(total), tuple(int(o) for o in offsets), *params)
+    out._cnb_acc_key = ("stack",) + tuple(id(p) for p in params)
+    return out
+
+
+def tag_derived(t: torch.Tensor, like: torch.Tensor, *extra) -> torch.Tensor:
+    """Carry the accumulator key of a derived weight over a reshape / permute / pad of it."""
+    key = getattr(like, "_cnb_acc_key", None)
+    if key is None and isinstance(like, torch.nn.Parameter):
+        key = ("param", id(like))
+    if key is not None:
+        t._cnb_acc_key = key + tuple(extra)
+    return t
 
 
 class _Conv2dFn(torch.autograd.Function):
@@ -370,6 +529,7 @@ class _Conv2dFn(torch.autograd.Function):
         stats = _launch_conv(sources, src_channels, wp, 0, wp.shape[2], N * wp.shape[2], N, bias_c, out, geom, transposed, dtype,
                              want_stats=want_stats)
         ctx.save_for_backward(weight, *sources)
+        ctx.set_materialize_grads(False)  # the statistics output never has a gradient: no zero tensor (a fill launch) per convolution
         ctx.params = (weight, bias)  # the Parameter objects themselves (their .grad may take the gradient directly)
         ctx.meta = (kind, geom, transposed, src_channels, N, Ctot, bias is not None)
         if not want_stats:
@@ -427,10 +587,15 @@ class _Conv2dFn(torch.autograd.Function):
         dw = None
         if need_w:
             target, acc_flag = _direct_grad_target(ctx.params[0], weight.shape)
+            derived = None
             if target is not None:
                 dwp = _wgrad_accumulator(ctx.params[0], taps, N, Ctot, dev)  # zero on entry: cleared by the previous unpack
             else:
-                dwp = torch.zeros((taps, N, Ctot), dtype=torch.float32, device=dev)
+                # a weight DERIVED from parameters (stacked Psi-Net filters, the Toeplitz matrix, a view): its accumulator persists
+                # under the key the producer attached, and the unpack below clears it while reading -- no zero fill per step
+                derived = getattr(ctx.params[0], "_cnb_acc_key", None) if DIRECT_PARAM_GRAD[0] else None
+                dwp = _derived_accumulator(derived, taps, N, Ctot, dev) if derived is not None else torch.zeros(
+                    (taps, N, Ctot), dtype=torch.float32, device=dev)
             coff = 0
             for s, c in zip(sources, src_channels):
                 d = WgradDesc()
@@ -452,7 +617,7 @@ class _Conv2dFn(torch.autograd.Function):
                     call("cnb_unpack_wgrad", ptr(dwp), ptr(target), taps, rows, cols, s_n, s_k, s_tap, acc_flag | 2, stream_ptr(dy))
             else:
                 dw = torch.empty_like(weight, dtype=torch.float32, memory_format=torch.contiguous_format)
-                call("cnb_unpack_wgrad", ptr(dwp), ptr(dw), taps, rows, cols, s_n, s_k, s_tap, 0, stream_ptr(dy))
+                call("cnb_unpack_wgrad", ptr(dwp), ptr(dw), taps, rows, cols, s_n, s_k, s_tap, 2 if derived is not None else 0, stream_ptr(dy))
 
         db = None
         if need_b:
@@ -547,9 +712,11 @@ def conv2d_skinny(x: torch.Tensor, weight: torch.Tensor, ksize: int = 3, pad: in
     taps = ksize * ksize
     assert taps * N <= SKINNY_MAX_COLS and N <= 16
     w2 = weight.permute(2, 3, 0, 1).reshape(taps * N, Cin)  # rows (tap, n)
-    rows = (taps * N + 7) // 8 * 8
+    # a whole number of 32-column epilogue chunks (81 -> 96): every chunk takes the 128-bit store path of the tcgen05 epilogue
+    rows = (taps * N + 31) // 32 * 32
     if rows > taps * N:
         w2 = torch.nn.functional.pad(w2, (0, 0, 0, rows - taps * N))
+    tag_derived(w2, weight, "skinny")
     t = linear(x, w2, None, in_features=Cin)
     return _TapShiftAddFn.apply(t, N, ksize, pad, dil)
 
@@ -591,6 +758,7 @@ class _BatchNormActFn(torch.autograd.Function):
             call("cnb_bn_act_fwd", ptr(x), ptr(stats[4]), ptr(stats[5]), ptr(res), ptr(y), P, L, Cn, ch_div, int(act),
                  dtype_code(dtype), st)
         ctx.save_for_backward(x, gamma, beta, stats)
+        ctx.params = (gamma, beta)
         ctx.meta = (P, L, Cn, ch_div, int(act), bool(training), count, residual is not None)
         return y
 
@@ -608,7 +776,9 @@ class _BatchNormActFn(torch.autograd.Function):
         call("cnb_bn_act_bwd_apply", ptr(x), ptr(dy), ptr(stats[2]), ptr(stats[3]), ptr(gamma), ptr(beta), ptr(dsums), count, ptr(dx),
              P, L, Cn, ch_div, act, int(training), dtype_code(dtype), st)
         dres = dy if has_res else None
-        return dx, dsums[1], dsums[0], None, None, None, None, None, None, None, dres, None
+        dgamma = _small_grad(ctx.params[0], dsums[1]) if ctx.needs_input_grad[1] else None
+        dbeta = _small_grad(ctx.params[1], dsums[0]) if ctx.needs_input_grad[2] else None
+        return dx, dgamma, dbeta, None, None, None, None, None, None, None, dres, None
 
 
 def batchnorm_act(x, gamma, beta, running_mean, running_var, training: bool, momentum: float = 0.1, eps: float = 1e-5,
@@ -682,6 +852,7 @@ class _LayerNormFn(torch.autograd.Function):
         call("cnb_layernorm_fwd", ptr(x), ptr(gamma), ptr(beta), eps, ptr(y), ptr(ms[0]), ptr(ms[1]), P, Cn, dtype_code(x.dtype),
              stream_ptr(x))
         ctx.save_for_backward(x, gamma, ms)
+        ctx.params = (gamma, beta)
         return y
 
     @staticmethod
@@ -691,9 +862,20 @@ class _LayerNormFn(torch.autograd.Function):
         Cn = x.shape[-1]
         P = x.numel() // Cn
         dx = torch.empty_like(x)
+        # the kernel ACCUMULATES dgamma / dbeta atomically: when the parameters' gradient buffers may take them directly (zeroed at the
+        # top of the step) they are the target -- no zero-filled temporary, no accumulation kernel afterwards
+        tg, _ = _direct_grad_target(ctx.params[0], (Cn,))
+        tb, _ = _direct_grad_target(ctx.params[1], (Cn,)) if tg is not None else (None, 0)
+        if tg is not None and tb is not None:
+            call("cnb_layernorm_bwd", ptr(x), ptr(dy), ptr(gamma), ptr(ms[0]), ptr(ms[1]), ptr(dx), ptr(tg), ptr(tb), P, Cn,
+                 dtype_code(x.dtype), stream_ptr(x))
+            return dx, None, None, None
         dgb = torch.zeros((2, Cn), dtype=torch.float32, device=x.device)
         call("cnb_layernorm_bwd", ptr(x), ptr(dy), ptr(gamma), ptr(ms[0]), ptr(ms[1]), ptr(dx), ptr(dgb[0]), ptr(dgb[1]), P, Cn,
              dtype_code(x.dtype), stream_ptr(x))
+        if tg is not None:  # gamma's buffer was claimed above but beta's was not available: hand gamma's gradient over by the table
+            _PENDING_SMALL.append((dgb[0], tg, 1))
+            return dx, None, dgb[1], None
         return dx, dgb[0], dgb[1], None
 
 
@@ -917,43 +1099,38 @@ class _ToeplitzFn(torch.autograd.Function):
 def pretime_conv_gemm(xp: torch.Tensor, w1: torch.Tensor, in_time: int) -> torch.Tensor:
     """The temporal convolution of ``pretime_conv`` over the pixel-major copy ``xp`` of x, as a 1x1 GEMM on the tensor cores:
     returns u[B,H,W,rows] with the same column order and zero row padding as ``pretime_conv``."""
-    wt = _ToeplitzFn.apply(w1, in_time)
+    wt = tag_derived(_ToeplitzFn.apply(w1, in_time), w1, "toeplitz")
     return linear(xp, wt, None, in_features=w1.shape[0] * in_time)
 
 
 # ----------------------------------------------------------------------------------------------------------------
 class _FinalCombineFn(torch.autograd.Function):
-    """TowerUNetFinalCombine + SigmoidCrisp over the three towers' fused [B,H,W,3] streams; 16 scalar parameters."""
+    """TowerUNetFinalCombine + SigmoidCrisp over the three towers' fused [B,H,W,3] streams; ``prm`` = the 16 scalar parameters
+    stacked by ``stack_params`` (its backward scatters their gradients)."""
 
     @staticmethod
-    def forward(ctx, ha, hb, hc, smooth, flags, *params):
-        check_device(ha, hb, hc, *params)
+    def forward(ctx, ha, hb, hc, smooth, flags, prm):
+        check_device(ha, hb, hc, prm)
         ha, hb, hc = _contig(ha), _contig(hb), _contig(hc)
         B, H, W, _ = ha.shape
         P = B * H * W
-        prm = torch.cat([p.reshape(-1).float() for p in params])  # 16 scalars: plumbing, not compute
+        prm = _contig(prm.float())
         assert prm.numel() == 16
         out = [torch.empty((B, 1, H, W), dtype=torch.float32, device=ha.device) for _ in range(3)]
         call("cnb_final_combine_fwd", ptr(ha), ptr(hb), ptr(hc), ptr(prm), smooth, flags, ptr(out[0]), ptr(out[1]), ptr(out[2]), P,
              dtype_code(ha.dtype), stream_ptr(ha))
         ctx.save_for_backward(ha, hb, hc, prm)
-        ctx.meta = (smooth, flags, P, [p.shape for p in params])
+        ctx.meta = (smooth, flags, P)
         return out[0], out[1], out[2]
 
     @staticmethod
     def backward(ctx, d_dist, d_edge, d_crop):
         ha, hb, hc, prm = ctx.saved_tensors
-        smooth, flags, P, shapes = ctx.meta
+        smooth, flags, P = ctx.meta
         dev = ha.device
-        zeros = None
 
         def g(t):
-            nonlocal zeros
-            if t is None:
-                if zeros is None:
-                    zeros = torch.zeros((P,), dtype=torch.float32, device=dev)
-                return zeros
-            return _contig(t.float())
+            return _zeros_like_cached(P, dev) if t is None else _contig(t.float())
 
         d_dist, d_edge, d_crop = g(d_dist), g(d_edge), g(d_crop)
         dha, dhb, dhc = torch.empty_like(ha), torch.empty_like(hb), torch.empty_like(hc)
@@ -961,15 +1138,15 @@ class _FinalCombineFn(torch.autograd.Function):
         ws = torch.empty((32,), dtype=torch.float32, device=dev)
         call("cnb_final_combine_bwd", ptr(ha), ptr(hb), ptr(hc), ptr(prm), smooth, flags, ptr(d_dist), ptr(d_edge), ptr(d_crop),
              ptr(dha), ptr(dhb), ptr(dhc), ptr(dprm), ptr(ws), P, dtype_code(ha.dtype), stream_ptr(ha))
-        pgrads = [dprm[i:i + 1].view(s) for i, s in enumerate(shapes)]
-        return (dha, dhb, dhc, None, None, *pgrads)
+        return dha, dhb, dhc, None, None, dprm
 
 
 def final_combine(ha, hb, hc, params: Sequence[torch.Tensor], smooth: float = 1e-2, edge_activation: bool = True,
                   mask_activation: bool = True):
     """params: 9 gammas (dist 1-3, edge 1-3, crop 1-3), 3 conv weights, 3 conv biases, crisp gamma."""
     flags = (1 if edge_activation else 0) | (2 if mask_activation else 0)
-    return _FinalCombineFn.apply(ha, hb, hc, smooth, flags, *params)
+    prm = stack_params(list(params), list(range(16)), 16)  # one launch instead of a torch.cat of 16 scalars (+ 16 gradient adds back)
+    return _FinalCombineFn.apply(ha, hb, hc, smooth, flags, prm)
 
 
 # ----------------------------------------------------------------------------------------------------------------

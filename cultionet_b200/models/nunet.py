@@ -47,7 +47,7 @@ class Conv3d(nn.Module):
         else:
             u = F.pretime_conv(x, conv1.weight, dtype)
         a = batchnorm_act(bn1, u, act=True, ch_div=self.remaining_time)
-        w2 = conv2.weight.view(conv2.weight.shape[0], -1)
+        w2 = F.tag_derived(conv2.weight.view(conv2.weight.shape[0], -1), conv2.weight, "flat")
         v = F.linear(a, w2, None, in_features=w2.shape[1])
         return batchnorm_act(bn2, v, act=True)
 
@@ -135,6 +135,8 @@ class TowerUNet(nn.Module):
         if x.dim() != 5 or x.shape[1] != self.in_channels or x.shape[2] != self.in_time:
             raise ValueError(f"TowerUNet expects x[B,{self.in_channels},{self.in_time},H,W], got {tuple(x.shape)}")
         dtype = self.compute_dtype
+        if self.training:
+            F.reset_stats_arena(x.device)  # clean [2, N] slices for the BatchNorm sums the convolution epilogues produce
         if self.training and self.dropout > 0:
             F.rng_advance(x.device)  # one new set of dropout masks per forward (a kernel, so CUDA-graph replays advance too)
         embeddings = self.pre_unet(x.float(), dtype)

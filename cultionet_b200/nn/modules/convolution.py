@@ -50,18 +50,23 @@ class deferred_batch_counters:
         return False
 
 
-def batchnorm_act(bn: nn.modules.batchnorm._BatchNorm, x: torch.Tensor, act: bool, ch_div: int = 1,
-                  sums: T.Optional[torch.Tensor] = None) -> torch.Tensor:
-    """BatchNorm2d/3d (+SiLU) with the module's parameters; batch statistics iff the module is in training mode."""
-    training = bn.training
-    if training and bn.track_running_stats and bn.num_batches_tracked is not None:
+def bump_batch_counter(bn: nn.modules.batchnorm._BatchNorm) -> None:
+    if bn.track_running_stats and bn.num_batches_tracked is not None:
         if _PENDING_COUNTERS is not None:
             _PENDING_COUNTERS.append(bn.num_batches_tracked)
         else:
             bn.num_batches_tracked.add_(1)
+
+
+def batchnorm_act(bn: nn.modules.batchnorm._BatchNorm, x: torch.Tensor, act: bool, ch_div: int = 1,
+                  sums: T.Optional[torch.Tensor] = None, residual: T.Optional[torch.Tensor] = None) -> torch.Tensor:
+    """BatchNorm2d/3d (+SiLU) (+ residual) with the module's parameters; batch statistics iff the module is in training mode."""
+    training = bn.training
+    if training:
+        bump_batch_counter(bn)
     return F.batchnorm_act(
         x, bn.weight, bn.bias, bn.running_mean, bn.running_var, training,
-        momentum=bn.momentum if bn.momentum is not None else 0.1, eps=bn.eps, act=act, ch_div=ch_div, sums=sums,
+        momentum=bn.momentum if bn.momentum is not None else 0.1, eps=bn.eps, act=act, ch_div=ch_div, sums=sums, residual=residual,
     )
 
 
@@ -104,11 +109,13 @@ class ConvBlock2d(nn.Module):
         self.add_activation = add_activation
         self.seq = nn.Sequential(*layers)
 
-    def forward(self, x: Sources) -> torch.Tensor:
+    def forward(self, x: Sources, residual: T.Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``residual`` (training-mode, conv-first blocks only): added to the block's output inside the BatchNorm kernel."""
         if self.batchnorm_first:
+            assert residual is None
             return self._forward_bn_first(_as_sources(x))
         conv, bn = self.seq[0], self.seq[1]
-        if not bn.training and not torch.is_grad_enabled():
+        if not bn.training and not torch.is_grad_enabled() and residual is None:
             # inference: BatchNorm (running statistics) and SiLU ride in the convolution epilogue -- one launch, one write
             y = F.conv2d_bn_act_eval(_as_sources(x), conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps,
                                      self.add_activation, ksize=conv.kernel_size[0], stride=conv.stride[0], pad=conv.padding[0],
@@ -121,7 +128,7 @@ class ConvBlock2d(nn.Module):
         sums = None
         if bn.training:
             y, sums = y
-        return batchnorm_act(bn, y, act=self.add_activation, sums=sums)
+        return batchnorm_act(bn, y, act=self.add_activation, sums=sums, residual=residual)
 
     def _forward_bn_first(self, sources: T.List[torch.Tensor]) -> torch.Tensor:
         """BatchNorm over the (virtual) channel concatenation = BatchNorm of every source with its slice of the parameters."""
@@ -164,10 +171,17 @@ class ResConvBlock2d(nn.Module):
             )
         self.block = nn.ModuleList(blocks)
 
-    def forward(self, x: Sources) -> torch.Tensor:
-        for layer in self.block:
-            x = layer(x)
+    def forward(self, x: Sources, residual: T.Optional[torch.Tensor] = None) -> torch.Tensor:
+        last = len(self.block) - 1
+        for i, layer in enumerate(self.block):
+            x = layer(x, residual=residual) if (i == last and residual is not None) else layer(x)
         return x
+
+    @property
+    def takes_residual(self) -> bool:
+        """The last block can add a residual in its BatchNorm kernel: conv-first layout, training-mode statistics."""
+        blk = self.block[-1]
+        return (not blk.batchnorm_first) and blk.seq[1].training
 
 
 class ChannelAttention(nn.Module):
@@ -305,14 +319,22 @@ class ResidualAConv(nn.Module):
             branch_in = [[r[1 + i] for r in refs] for i in range(nres)]
             if attention:
                 skip, att_in = F.fanout(skip, 2)
-        terms = [skip] + [layer(branch_in[i]) for i, layer in enumerate(self.res_modules)]
+        if all(layer.takes_residual for layer in self.res_modules):
+            # training: skip + branch_1 + branch_2 ... accumulate inside the branches' last BatchNorm kernels (y = SiLU(BN(x)) + residual)
+            # instead of a separate n-ary add pass; the gradient of a residual is the incoming gradient itself (no kernel)
+            acc = skip
+            for i, layer in enumerate(self.res_modules):
+                acc = layer(branch_in[i], residual=acc)
+            terms = [acc]
+        else:
+            terms = [skip] + [layer(branch_in[i]) for i, layer in enumerate(self.res_modules)]
         natten = attention and self.attention_weights == AttentionTypes.NATTEN
         if natten:
             ln1, na, ln2 = self.attention_conv[1], self.attention_conv[2], self.attention_conv[3]
             a = F.layernorm(att_in, ln1.weight, ln1.bias, ln1.eps)
             a = na(a)
             terms.append(F.layernorm(a, ln2.weight, ln2.bias, ln2.eps))
-        out = F.add_n(*terms[:4])
+        out = terms[0] if len(terms) == 1 else F.add_n(*terms[:4])
         for i in range(4, len(terms), 3):
             out = F.add_n(out, *terms[i:i + 3])
         if attention and not natten:

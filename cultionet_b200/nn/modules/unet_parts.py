@@ -129,9 +129,16 @@ class TowerUNetFinal(nn.Module):
             x = self.up_conv(x, size=size)
         streams = (self.dist_conv, self.edge_conv, self.crop_conv)
         blocks = [s.conv[0] for s in streams]
-        w1 = torch.cat([b.seq[0].weight for b in blocks], dim=0)  # [9, C, 3, 3]
         bns = [b.seq[1] for b in blocks]
         training = bns[0].training
+        C = blocks[0].seq[0].weight.shape[1]
+        # the stacked filters / BatchNorm parameters come from ONE multi-tensor copy each (functional.stack_params: no torch.cat, no
+        # per-parameter gradient adds); the running statistics of the three BatchNorm2d(3) are views of one 9-element buffer
+        w1 = F.stack_params([b.seq[0].weight for b in blocks], [0, 27 * C, 54 * C], 81 * C)
+        w1 = F.tag_derived(w1.view(9, C, 3, 3), w1)
+        gamma = F.stack_params([bn.weight for bn in bns], [0, 3, 6], 9)
+        beta = F.stack_params([bn.bias for bn in bns], [0, 3, 6], 9)
+        rm, rv = self._stacked_running_stats(bns)
         sums = None
         if x.dtype == torch.bfloat16:
             # throughput mode: C -> 9 as a 1x1 GEMM (C -> 81) + shift-and-add, so the wide tower tensor is read once, not once per tap
@@ -140,22 +147,37 @@ class TowerUNetFinal(nn.Module):
             h = F.conv2d([x], w1, None, ksize=3, stride=1, pad=1, want_stats=training)
             if training:
                 h, sums = h
-        rm = torch.cat([bn.running_mean for bn in bns])
-        rv = torch.cat([bn.running_var for bn in bns])
-        h = F.batchnorm_act(h, torch.cat([bn.weight for bn in bns]), torch.cat([bn.bias for bn in bns]), rm, rv, training,
-                            momentum=bns[0].momentum if bns[0].momentum is not None else 0.1, eps=bns[0].eps, act=True, sums=sums)
         if training:
-            with torch.no_grad():
-                for i, bn in enumerate(bns):
-                    bn.running_mean.copy_(rm[3 * i:3 * i + 3])
-                    bn.running_var.copy_(rv[3 * i:3 * i + 3])
-                    if bn.num_batches_tracked is not None:
-                        bn.num_batches_tracked.add_(1)
-        # 3 x (3 -> 1) as one block-diagonal 9 -> 3 convolution
-        w2 = torch.cat([torch.nn.functional.pad(s.conv[1].weight, (0, 0, 0, 0, 3 * i, 6 - 3 * i)) for i, s in enumerate(streams)], dim=0)
-        b2 = torch.cat([s.conv[1].bias for s in streams])
+            from .convolution import bump_batch_counter
+
+            for bn in bns:
+                bump_batch_counter(bn)
+        h = F.batchnorm_act(h, gamma, beta, rm, rv, training, momentum=bns[0].momentum if bns[0].momentum is not None else 0.1,
+                            eps=bns[0].eps, act=True, sums=sums)
+        # 3 x (3 -> 1) as one block-diagonal 9 -> 3 convolution: stream i's [1,3,3,3] filter sits at input channels 3i..3i+2 of output i
+        w2 = F.stack_params([s.conv[1].weight for s in streams], [0, 108, 216], 243)
+        w2 = F.tag_derived(w2.view(3, 9, 3, 3), w2)
+        b2 = F.stack_params([s.conv[1].bias for s in streams], [0, 1, 2], 3)
         z = F.conv2d([h], w2, b2, ksize=3, stride=1, pad=1)
         return self.fuse_conv(z)
+
+    def _stacked_running_stats(self, bns):
+        """(running_mean[9], running_var[9]) whose thirds ARE the three modules' buffers: each ``bn.running_mean`` / ``running_var`` is
+        re-pointed at a view of one shared tensor (state_dict / load_state_dict see the same names, shapes and values), so the stacked
+        BatchNorm kernel updates them in place and nothing is copied per step.  Re-established when ``.to()`` re-homes the buffers."""
+        out = []
+        for name in ("running_mean", "running_var"):
+            bufs = [getattr(bn, name) for bn in bns]
+            base = getattr(self, "_stk_" + name, None)
+            ok = base is not None and base.device == bufs[0].device and all(
+                b.data_ptr() == base.data_ptr() + 12 * i and b.numel() == 3 for i, b in enumerate(bufs))
+            if not ok:
+                base = torch.cat([b.detach().reshape(-1).float() for b in bufs])
+                for i, bn in enumerate(bns):
+                    setattr(bn, name, base[3 * i:3 * i + 3])
+                object.__setattr__(self, "_stk_" + name, base)
+            out.append(base)
+        return out
 
 
 class UNetUpBlock(nn.Module):
@@ -195,11 +217,14 @@ class TowerUNetEncoder(nn.Module):
         self.down_d = PoolResidualConv(channels[2], channels[3], kernel_size=1, num_blocks=1, dilations=[1], attention_weights=None, **kw)
 
     def forward(self, x: torch.Tensor) -> T.Dict[str, torch.Tensor]:
-        x_a = self.down_a(x)
-        x_b = self.down_b(x_a)
-        x_c = self.down_c(x_b)
-        x_d = self.down_d(x_c)
-        return {"x_a": x_a, "x_b": x_b, "x_c": x_c, "x_d": x_d}
+        # every level feeds the next level AND one or two towers: F.fanout hands each consumer its own alias so that the backward sums
+        # their gradients with one n-ary add kernel (keys: "x_*" = the same-level tower / decoder input, "x_*_down" = the input of the
+        # tower one level up)
+        a_next, x_a = F.fanout(self.down_a(x), 2)
+        b_next, x_b, x_b_down = F.fanout(self.down_b(a_next), 3)
+        c_next, x_c, x_c_down = F.fanout(self.down_c(b_next), 3)
+        x_d, x_d_down = F.fanout(self.down_d(c_next), 2)
+        return {"x_a": x_a, "x_b": x_b, "x_c": x_c, "x_d": x_d, "x_b_down": x_b_down, "x_c_down": x_c_down, "x_d_down": x_d_down}
 
 
 class TowerUNetDecoder(nn.Module):
@@ -220,11 +245,11 @@ class TowerUNetDecoder(nn.Module):
 
     def forward(self, x: T.Dict[str, torch.Tensor]) -> T.Dict[str, torch.Tensor]:
         hw = lambda t: tuple(t.shape[1:3])  # noqa: E731
-        x_du = self.over_d(x["x_d"], size=hw(x["x_d"]))
-        x_cu = self.up_cu(x_du, size=hw(x["x_c"]))
-        x_bu = self.up_bu(x_cu, size=hw(x["x_b"]))
-        x_au = self.up_au(x_bu, size=hw(x["x_a"]))
-        return {"x_au": x_au, "x_bu": x_bu, "x_cu": x_cu, "x_du": x_du}
+        du_next, x_du = F.fanout(self.over_d(x["x_d"], size=hw(x["x_d"])), 2)
+        cu_next, x_cu, x_cu_down = F.fanout(self.up_cu(du_next, size=hw(x["x_c"])), 3)
+        bu_next, x_bu, x_bu_down = F.fanout(self.up_bu(cu_next, size=hw(x["x_b"])), 3)
+        x_au = self.up_au(bu_next, size=hw(x["x_a"]))
+        return {"x_au": x_au, "x_bu": x_bu, "x_cu": x_cu, "x_du": x_du, "x_cu_down": x_cu_down, "x_bu_down": x_bu_down}
 
 
 class GeoEmbeddings(nn.Module):
@@ -307,10 +332,12 @@ class TowerUNetFusion(nn.Module):
                                       dilations=dilations, **{**kw, **NATTEN_PARAMS["a"]})
 
     def forward(self, encoded, decoded, latlon_coords=None) -> T.Dict[str, torch.Tensor]:
-        t_c = self.tower_c(backbone_side=encoded["x_c"], backbone_down=encoded["x_d"], decode_side=decoded["x_cu"],
-                           decode_down=decoded["x_du"], latlon_coords=latlon_coords)
-        t_b = self.tower_b(backbone_side=encoded["x_b"], backbone_down=encoded["x_c"], decode_side=decoded["x_bu"],
-                           decode_down=decoded["x_cu"], tower_down=t_c, latlon_coords=latlon_coords)
-        t_a = self.tower_a(backbone_side=encoded["x_a"], backbone_down=encoded["x_b"], decode_side=decoded["x_au"],
-                           decode_down=decoded["x_bu"], tower_down=t_b, latlon_coords=latlon_coords)
+        enc = lambda k: encoded.get(k + "_down", encoded[k])  # noqa: E731 - plain dicts of tensors (no aliases) work too
+        dec = lambda k: decoded.get(k + "_down", decoded[k])  # noqa: E731
+        t_c_next, t_c = F.fanout(self.tower_c(backbone_side=encoded["x_c"], backbone_down=enc("x_d"), decode_side=decoded["x_cu"],
+                                              decode_down=decoded["x_du"], latlon_coords=latlon_coords), 2)
+        t_b_next, t_b = F.fanout(self.tower_b(backbone_side=encoded["x_b"], backbone_down=enc("x_c"), decode_side=decoded["x_bu"],
+                                              decode_down=dec("x_cu"), tower_down=t_c_next, latlon_coords=latlon_coords), 2)
+        t_a = self.tower_a(backbone_side=encoded["x_a"], backbone_down=enc("x_b"), decode_side=decoded["x_au"],
+                           decode_down=dec("x_bu"), tower_down=t_b_next, latlon_coords=latlon_coords)
         return {"x_tower_a": t_a, "x_tower_b": t_b, "x_tower_c": t_c}

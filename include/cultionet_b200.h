@@ -119,6 +119,13 @@ int cnb_conv2d_wgrad_tiny(const cnb_wgrad_desc* d, int dtype, void* stream);
 /* dst[p][c] = src[p][c] for c < C, 0 for C <= c < dst_stride: gives a skinny tensor (e.g. the 3-channel gradient of a Psi-Net
  * stream) the 16-byte pixel pitch the TMA-fed kernels need */
 int cnb_repitch(const void* src, int src_stride, void* dst, int dst_stride, int64_t P, int C, int dtype, void* stream);
+/* Multi-tensor copy / accumulate of small fp32 segments in one launch per 160 segments.  table: HOST array of n_entries records
+ * {const float* src; float* dst; int32 n; int32 mode (0: dst = src, 1: dst += src)} (24 bytes each, device pointers inside); it is
+ * copied into the kernel arguments before the call returns (no device table, nothing to upload; a captured graph keeps its copy).
+ * max_len = the largest n.
+ * Used for parameter plumbing that the reference leaves to torch.cat / autograd accumulation: stacking the three Psi-Net stream
+ * filters (nn/modules/unet_parts.py:281-309), scattering BatchNorm / LayerNorm / scalar gradients into the flat gradient buffer. */
+int cnb_multi_copy(const void* table, int n_entries, int max_len, void* stream);
 /* out[b][p][c] = e[b][c] for p < HW: the per-sample GeoEmbeddings vector broadcast over a level's pixels before it joins the
  * full-scale-skip concatenation (nn/modules/unet_parts.py:739-750, geo_encoding.py:5-26) */
 int cnb_broadcast_pixels(const void* e, void* out, int B, int64_t HW, int C, int dtype, void* stream);

@@ -48,6 +48,8 @@
 #define __launch_bounds__(...)
 #define __restrict__ __restrict
 #define __align__(n) __attribute__((aligned(n)))
+#undef __grid_constant__
+#define __grid_constant__
 
 #define CNB_MEMSET_ASYNC(ptr, val, bytes, stream) memset((ptr), (val), (bytes))
 #define CNB_PDL_SYNC() ((void)0)

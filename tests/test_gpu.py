@@ -553,3 +553,22 @@ def test_model_cfg4_geometry_train_bf16(dev):
     finally:
         unet_parts.NATTEN_PARAMS.update(saved)
         torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("shape", [(2, 40, 40, [256], 256, 3, 1), (3, 33, 47, [64, 128], 128, 3, 1), (2, 64, 64, [64], 64, 3, 2), (4, 16, 16, [512], 512, 1, 1)])
+def test_conv_epilogue_batchnorm_sums(dev, shape):
+    """The tcgen05 epilogue's BatchNorm sums (cnb_conv_desc::stats) = per-channel sum and sum of squares of the STORED bf16 outputs."""
+    from cultionet_b200 import functional as F
+
+    B, H, W, cins, cout, k, stride = shape
+    torch.manual_seed(0)
+    xs = [torch.randn(B, H, W, c, device=dev).bfloat16() for c in cins]
+    w = torch.randn(cout, sum(cins), k, k, device=dev) / (sum(cins) * k * k) ** 0.5
+    F.reset_stats_arena(dev)
+    y, sums = F.conv2d(xs, w, None, ksize=k, stride=stride, pad=k // 2, dil=1, want_stats=True)
+    assert sums.numel() == 2 * cout, "this shape must take the statistics epilogue"
+    yf = y.float().reshape(-1, cout)
+    assert rel_err(sums.view(2, cout)[0], yf.sum(0)) < 1e-4
+    assert rel_err(sums.view(2, cout)[1], (yf * yf).sum(0)) < 1e-4
+    y2 = F.conv2d(xs, w, None, ksize=k, stride=stride, pad=k // 2, dil=1)
+    assert torch.equal(y, y2)

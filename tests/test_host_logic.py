@@ -156,7 +156,8 @@ def test_fit_checkpoint_roundtrip_and_resume(dev, tmp_path):
     assert not any(p.requires_grad for p in again.parameters()) and not again.training
 
     # resume: the saved epoch was the best of {0, 1}; a 3-epoch fit continues after it with the saved AdamW moments
-    saved_epoch, saved_step = raw["epoch"], raw["optimizer_states"][0]["step"]
+    # optimizer_states[0] is laid out like torch.optim.AdamW.state_dict(): {"state": {i: {"step", "exp_avg", "exp_avg_sq"}}, "param_groups"}
+    saved_epoch, saved_step = raw["epoch"], int(raw["optimizer_states"][0]["state"][0]["step"])
     lit2 = CultionetLitModel(**{k: v for k, v in raw["hyper_parameters"].items()}).to(dev)
     hist2 = M.fit(lit2, batches, val_batches=batches[:1], epochs=3, ckpt_file=ckpt, device=dev, cuda_graph=False)
     assert len(hist2["loss"]) == 3 - (saved_epoch + 1)
