@@ -115,6 +115,7 @@ _PROTOS = {
     "cnb_bn_act_fwd": [_vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp],
     "cnb_bn_train_fwd": [_vp, _vp, _i64, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp],
     "cnb_bn_act_bwd_reduce": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _i, _vp],
+    "cnb_bn_act_bwd_reduce_acc": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _i, _vp],
     "cnb_bn_act_bwd_apply": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _i, _vp],
     "cnb_add_n": [_vp, _vp, _vp, _vp, _vp, _i64, _i, _vp],
     "cnb_layernorm_fwd": [_vp, _vp, _vp, _f, _vp, _vp, _vp, _i64, _i, _i, _vp],
@@ -125,6 +126,7 @@ _PROTOS = {
     "cnb_na2d_bwd_workspace_floats": [_i, _i, _i, _i, _i, _i, _i, _i],
     "cnb_resize_bilinear_fwd": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "cnb_resize_bilinear_bwd": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "cnb_resize_bilinear_bwd_colsum": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _vp],
     "cnb_pretime_conv_fwd": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "cnb_pretime_conv_wgrad": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "cnb_time_to_pixel_major": [_vp, _vp, _i, _i, _i64, _i, _i, _vp],
@@ -261,6 +263,7 @@ ALG_BYTES = {
     "cnb_bn_train_fwd": lambda a: (2 + _nn(a[13])) * a[15] * a[16] * _es(a[20]),
     "cnb_bn_act_fwd": lambda a: (2 + _nn(a[3])) * a[5] * a[6] * _es(a[10]),
     "cnb_bn_act_bwd_reduce": lambda a: 2 * a[6] * a[7] * _es(a[12]),
+    "cnb_bn_act_bwd_reduce_acc": lambda a: 2 * a[6] * a[7] * _es(a[12]),
     "cnb_bn_act_bwd_apply": lambda a: 3 * a[9] * a[10] * _es(a[15]),
     "cnb_add_n": lambda a: (_nn(a[0], a[1], a[2], a[3]) + 1) * a[5] * _es(a[6]),
     "cnb_layernorm_fwd": lambda a: 2 * a[7] * a[8] * _es(a[9]),
@@ -269,6 +272,7 @@ ALG_BYTES = {
     "cnb_na2d_bwd": lambda a: 8 * a[8] * a[9] * a[10] * a[11] * a[12] * _es(a[16]),
     "cnb_resize_bilinear_fwd": lambda a: a[2] * a[7] * _es(a[8]) * (a[3] * a[4] + a[5] * a[6]),
     "cnb_resize_bilinear_bwd": lambda a: a[2] * a[7] * _es(a[8]) * (a[3] * a[4] + a[5] * a[6]),
+    "cnb_resize_bilinear_bwd_colsum": lambda a: a[2] * a[7] * _es(a[10]) * (a[3] * a[4] + a[5] * a[6]),
     "cnb_time_to_pixel_major": lambda a: a[2] * a[4] * (a[3] * 4 + a[5] * _es(a[6])),
     "cnb_bias_grad": lambda a: a[2] * a[3] * _es(a[6]),
     "cnb_adamw_step": lambda a: 28 * a[4],

@@ -149,7 +149,7 @@ int cnb_conv2d_fwd_tc(const cnb_conv_desc* d, int dtype, void* stream) {
     if (rc) return rc;
     if (!tc::eligible(d, dtype)) CNB_FAIL(CNB_ERR_UNSUPPORTED, "conv2d_fwd_tc: shape/dtype not eligible for the tcgen05 kernel");
     rc = tc::conv_tc_launch(d, (cudaStream_t)stream);
-    if (rc) CNB_FAIL(CNB_ERR_CUDA, "conv2d_fwd_tc: tensor-map encode or launch configuration failed (%d)", rc);
+    if (rc) CNB_FAIL(CNB_ERR_CUDA, "conv2d_fwd_tc: tensor-map encode or launch configuration failed (%d) %s", rc, tc::encode_diag());
     CNB_CHECK_LAUNCH("conv_tc_kernel");
     return CNB_OK;
 #endif
@@ -248,6 +248,20 @@ int cnb_conv2d_wgrad_tiny(const cnb_wgrad_desc* d, int dtype, void* stream) {
     if (rc) return rc;
     if (!wgrad_tiny_eligible(d)) CNB_FAIL(CNB_ERR_UNSUPPORTED, "conv2d_wgrad_tiny: needs N <= %d and a source slice of at most %d channels", TINY_WG_MAX_N, TINY_MAX_C);
     const long M = (long)d->B * d->Hout * d->Wout;
+    if (d->N == 3 && (d->src_c == 9 || d->src_c == 3)) {
+        // the Psi-Net head shapes: TG taps' products in registers, taps / TG passes over the level (see conv_tiny_wgrad_fixed_kernel)
+        const int taps = d->KH * d->KW;
+        CNB_DISPATCH_DTYPE(dtype, {
+            if (d->src_c == 9)
+                CNB_LAUNCH((conv_tiny_wgrad_fixed_kernel<T, 3, 9, 3>), dim3(stream_grid(M, 256, 1), cnb_div_up(taps, 3)), dim3(256), 0,
+                           (cudaStream_t)stream, *d);
+            else
+                CNB_LAUNCH((conv_tiny_wgrad_fixed_kernel<T, 3, 3, 9>), dim3(stream_grid(M, 256, 2), cnb_div_up(taps, 9)), dim3(256), 0,
+                           (cudaStream_t)stream, *d);
+        });
+        CNB_CHECK_LAUNCH("conv_tiny_wgrad_fixed_kernel");
+        return CNB_OK;
+    }
     dim3 grid(stream_grid(M, 256, 1), d->KH * d->KW, cnb_div_up(d->src_c, TINY_WG_MAX_C));
     CNB_DISPATCH_DTYPE(dtype, { CNB_LAUNCH((conv_tiny_wgrad_kernel<T>), grid, dim3(256), 0, (cudaStream_t)stream, *d); });
     CNB_CHECK_LAUNCH("conv_tiny_wgrad_kernel");
@@ -504,10 +518,25 @@ int cnb_bn_train_fwd(const void* x, const float* sums, int64_t count, const floa
     return cnb_bn_act_fwd(x, scale, shift, residual, y, P, L, C, ch_div, act, dtype, stream);
 }
 
+static int bn_act_bwd_reduce_impl(const void* x, const void* dy, const float* save_mean, const float* save_rstd, const float* gamma,
+                                  const float* beta, int64_t P, int L, int C, int ch_div, int act, float* dsums, int dtype, void* stream,
+                                  bool clear);
+
 int cnb_bn_act_bwd_reduce(const void* x, const void* dy, const float* save_mean, const float* save_rstd, const float* gamma, const float* beta,
                           int64_t P, int L, int C, int ch_div, int act, float* dsums, int dtype, void* stream) {
+    return bn_act_bwd_reduce_impl(x, dy, save_mean, save_rstd, gamma, beta, P, L, C, ch_div, act, dsums, dtype, stream, true);
+}
+
+int cnb_bn_act_bwd_reduce_acc(const void* x, const void* dy, const float* save_mean, const float* save_rstd, const float* gamma,
+                              const float* beta, int64_t P, int L, int C, int ch_div, int act, float* dsums, int dtype, void* stream) {
+    return bn_act_bwd_reduce_impl(x, dy, save_mean, save_rstd, gamma, beta, P, L, C, ch_div, act, dsums, dtype, stream, false);
+}
+
+static int bn_act_bwd_reduce_impl(const void* x, const void* dy, const float* save_mean, const float* save_rstd, const float* gamma,
+                                  const float* beta, int64_t P, int L, int C, int ch_div, int act, float* dsums, int dtype, void* stream,
+                                  bool clear) {
     CNB_REQUIRE(x && dy && save_mean && save_rstd && dsums && P > 0 && L > 0 && C > 0 && ch_div > 0, "bn_act_bwd_reduce: bad arguments");
-    CNB_MEMSET_ASYNC(dsums, 0, sizeof(float) * 2 * C, (cudaStream_t)stream);
+    if (clear) CNB_MEMSET_ASYNC(dsums, 0, sizeof(float) * 2 * C, (cudaStream_t)stream);
     int blocks;
     const long total = (long)P * L;
 #ifndef CNB_EMU
@@ -606,7 +635,7 @@ int cnb_layernorm_fwd(const void* x, const float* gamma, const float* beta, floa
     CNB_REQUIRE(x && y && gamma && beta && save_mean && save_rstd && P > 0 && C > 0, "layernorm_fwd: bad arguments");
     if (C % vec_width(dtype) == 0 && C <= 128 * vec_width(dtype) && cnb_aligned16(x) && cnb_aligned16(y)) {
         const int K = cnb_div_up(C, 32 * vec_width(dtype));
-        const dim3 grid(stream_grid(P, 8, 4));
+        const dim3 grid(stream_grid(P, 8 * (K == 1 ? 4 : 2), 3));  // U pixels per warp and trip, 3 CTAs per SM (<= 85 registers)
 #define CNB_LN_FWD(KK)                                                                                                              \
     CNB_DISPATCH_DTYPE(dtype, {                                                                                                     \
         CNB_LAUNCH((layernorm_fwd_vec_kernel<T, KK>), grid, dim3(256), 0, (cudaStream_t)stream, (const T*)x, gamma, beta, eps, (T*)y, \
@@ -636,7 +665,7 @@ int cnb_layernorm_bwd(const void* x, const void* dy, const float* gamma, const f
     CNB_REQUIRE(C <= 32 * LN_MAX_CPL, "layernorm_bwd: C=%d exceeds %d", C, 32 * LN_MAX_CPL);
     if (C % vec_width(dtype) == 0 && C <= 128 * vec_width(dtype) && cnb_aligned16(x) && cnb_aligned16(dy) && cnb_aligned16(dx)) {
         const int K = cnb_div_up(C, 32 * vec_width(dtype));
-        const dim3 grid(stream_grid(P, 8, 2));
+        const dim3 grid(stream_grid(P, 8 * (K == 1 ? 2 : 1), 3));
 #define CNB_LN_BWD(KK)                                                                                                               \
     CNB_DISPATCH_DTYPE(dtype, {                                                                                                      \
         CNB_LAUNCH((layernorm_bwd_vec_kernel<T, KK>), grid, dim3(256), 2 * C * sizeof(float), (cudaStream_t)stream, (const T*)x,     \
@@ -978,28 +1007,68 @@ int cnb_resize_bilinear_fwd(const void* x, void* y, int B, int Hin, int Win, int
     return CNB_OK;
 }
 
+// rows per CTA of the persistent table kernel: the smallest whole number that keeps the grid within 8 CTAs per SM
+static inline int resize_bwd_grid(long rows) {
+    const long cap = 8L * CNB_NUM_SMS;
+    const long per = (rows + cap - 1) / cap;
+    return (int)((rows + per - 1) / per);
+}
+
 int cnb_resize_bilinear_bwd(const void* dy, void* dx, int B, int Hin, int Win, int Hout, int Wout, int C, int dtype, void* stream) {
+    return cnb_resize_bilinear_bwd_colsum(dy, dx, B, Hin, Win, Hout, Wout, C, nullptr, 0, dtype, stream);
+}
+
+int cnb_resize_bilinear_bwd_colsum(const void* dy, void* dx, int B, int Hin, int Win, int Hout, int Wout, int C, float* colsum, int accumulate,
+                                   int dtype, void* stream) {
     CNB_REQUIRE(dy && dx && B > 0 && Hin > 0 && Win > 0 && Hout > 0 && Wout > 0 && C > 0, "resize_bilinear_bwd: bad arguments");
     const long total = (long)B * Hin * Win * C;
     const float rh_ = align_corners_scale(Hin, Hout), rw_ = align_corners_scale(Win, Wout);
-    if (C % vec_width(dtype) == 0 && cnb_aligned16(dy) && cnb_aligned16(dx) && rh_ >= 0.5f && rw_ >= 0.5f && Win <= 4096) {
+    if (C % vec_width(dtype) == 0 && cnb_aligned16(dy) && cnb_aligned16(dx) && rh_ >= 0.5f && rw_ >= 0.5f && Win <= 4096 && Hin <= 4096) {
         // scale >= 0.5: at most RB_NC = 5 outputs read an input index per axis (support of length 2/scale <= 4); scale >= 0.7 (the
         // ConvTranspose fix-up, scale ~ 1): at most 3
         const bool near1 = rh_ >= 0.7f && rw_ >= 0.7f;
         const int nc = near1 ? RB_NC_NEAR1 : RB_NC;
-        const size_t smem = (size_t)Win * (1 + nc) * 4 + (1 + nc) * 4;
+        const int CV = C / vec_width(dtype);
+        // the fused column sum needs a thread to stay on one channel vector (256 % CV == 0) and the sums next to the tables
+        const bool fuse_sum = colsum && 256 % CV == 0 && C <= 4096;
+        float* cs = fuse_sum ? colsum : nullptr;
+        if (fuse_sum && !accumulate) CNB_MEMSET_ASYNC(colsum, 0, sizeof(float) * C, (cudaStream_t)stream);
+        static const bool persistent = [] {  // CNB_RESIZE_BWD=persistent: the row-looping variant (A/B)
+            const char* e = getenv("CNB_RESIZE_BWD");
+            return e && e[0] == 'p';
+        }();
+        if (!persistent) {
+            const size_t smem_row = (size_t)Win * (1 + nc) * 4 + (1 + nc) * 4 + (fuse_sum ? (size_t)C * 4 : 0);
+            CNB_DISPATCH_DTYPE(dtype, {
+                if (near1) {
+                    CNB_SET_SMEM((resize_bilinear_bwd_row_kernel<T, RB_NC_NEAR1>), smem_row);
+                    CNB_LAUNCH((resize_bilinear_bwd_row_kernel<T, RB_NC_NEAR1>), dim3(B * Hin), dim3(256), smem_row, (cudaStream_t)stream,
+                               (const T*)dy, (T*)dx, B, Hin, Win, Hout, Wout, C, rh_, rw_, cs);
+                } else {
+                    CNB_SET_SMEM((resize_bilinear_bwd_row_kernel<T, RB_NC>), smem_row);
+                    CNB_LAUNCH((resize_bilinear_bwd_row_kernel<T, RB_NC>), dim3(B * Hin), dim3(256), smem_row, (cudaStream_t)stream, (const T*)dy,
+                               (T*)dx, B, Hin, Win, Hout, Wout, C, rh_, rw_, cs);
+                }
+            });
+            CNB_CHECK_LAUNCH("resize_bilinear_bwd_row_kernel");
+            if (colsum && !fuse_sum) return cnb_bias_grad(dx, C, (int64_t)B * Hin * Win, C, colsum, accumulate, dtype, stream);
+            return CNB_OK;
+        }
+        const size_t smem = (size_t)(Win + Hin) * (1 + nc) * 4 + (fuse_sum ? (size_t)C * 4 : 0);
+        const dim3 grid(resize_bwd_grid((long)B * Hin));
         CNB_DISPATCH_DTYPE(dtype, {
             if (near1) {
                 CNB_SET_SMEM((resize_bilinear_bwd_tab_kernel<T, RB_NC_NEAR1>), smem);
-                CNB_LAUNCH((resize_bilinear_bwd_tab_kernel<T, RB_NC_NEAR1>), dim3(B * Hin), dim3(256), smem, (cudaStream_t)stream, (const T*)dy,
-                           (T*)dx, B, Hin, Win, Hout, Wout, C, rh_, rw_);
+                CNB_LAUNCH((resize_bilinear_bwd_tab_kernel<T, RB_NC_NEAR1>), grid, dim3(256), smem, (cudaStream_t)stream, (const T*)dy, (T*)dx, B,
+                           Hin, Win, Hout, Wout, C, rh_, rw_, cs);
             } else {
                 CNB_SET_SMEM((resize_bilinear_bwd_tab_kernel<T, RB_NC>), smem);
-                CNB_LAUNCH((resize_bilinear_bwd_tab_kernel<T, RB_NC>), dim3(B * Hin), dim3(256), smem, (cudaStream_t)stream, (const T*)dy, (T*)dx, B,
-                           Hin, Win, Hout, Wout, C, rh_, rw_);
+                CNB_LAUNCH((resize_bilinear_bwd_tab_kernel<T, RB_NC>), grid, dim3(256), smem, (cudaStream_t)stream, (const T*)dy, (T*)dx, B, Hin,
+                           Win, Hout, Wout, C, rh_, rw_, cs);
             }
         });
         CNB_CHECK_LAUNCH("resize_bilinear_bwd_tab_kernel");
+        if (colsum && !fuse_sum) return cnb_bias_grad(dx, C, (int64_t)B * Hin * Win, C, colsum, accumulate, dtype, stream);
         return CNB_OK;
     }
     if (C % vec_width(dtype) == 0 && cnb_aligned16(dy) && cnb_aligned16(dx)) {
@@ -1008,6 +1077,7 @@ int cnb_resize_bilinear_bwd(const void* dy, void* dx, int B, int Hin, int Win, i
                        (const T*)dy, (T*)dx, B, Hin, Win, Hout, Wout, C, align_corners_scale(Hin, Hout), align_corners_scale(Win, Wout));
         });
         CNB_CHECK_LAUNCH("resize_bilinear_bwd_vec_kernel");
+        if (colsum) return cnb_bias_grad(dx, C, (int64_t)B * Hin * Win, C, colsum, accumulate, dtype, stream);
         return CNB_OK;
     }
     CNB_DISPATCH_DTYPE(dtype, {
@@ -1015,6 +1085,7 @@ int cnb_resize_bilinear_bwd(const void* dy, void* dx, int B, int Hin, int Win, i
                    Win, Hout, Wout, C, align_corners_scale(Hin, Hout), align_corners_scale(Win, Wout));
     });
     CNB_CHECK_LAUNCH("resize_bilinear_bwd_kernel");
+    if (colsum) return cnb_bias_grad(dx, C, (int64_t)B * Hin * Win, C, colsum, accumulate, dtype, stream);
     return CNB_OK;
 }
 

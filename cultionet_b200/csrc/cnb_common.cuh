@@ -140,6 +140,20 @@ __device__ __forceinline__ void cnb_ldv(const bf16_t* p, float* v) {
     v[4] = cnb_bits2f(r.z << 16), v[5] = cnb_bits2f(r.z & 0xffff0000u);
     v[6] = cnb_bits2f(r.w << 16), v[7] = cnb_bits2f(r.w & 0xffff0000u);
 }
+// the same load split in two: the raw 16 bytes (what a thread keeps in flight: 4 registers for 8 bf16 values) and their expansion
+template <typename T>
+__device__ __forceinline__ uint4 cnb_ldraw(const T* p) {
+    return *reinterpret_cast<const uint4*>(p);
+}
+__device__ __forceinline__ void cnb_expand(const uint4& r, float* v, const float*) {
+    v[0] = cnb_bits2f(r.x), v[1] = cnb_bits2f(r.y), v[2] = cnb_bits2f(r.z), v[3] = cnb_bits2f(r.w);
+}
+__device__ __forceinline__ void cnb_expand(const uint4& r, float* v, const bf16_t*) {
+    v[0] = cnb_bits2f(r.x << 16), v[1] = cnb_bits2f(r.x & 0xffff0000u);
+    v[2] = cnb_bits2f(r.y << 16), v[3] = cnb_bits2f(r.y & 0xffff0000u);
+    v[4] = cnb_bits2f(r.z << 16), v[5] = cnb_bits2f(r.z & 0xffff0000u);
+    v[6] = cnb_bits2f(r.w << 16), v[7] = cnb_bits2f(r.w & 0xffff0000u);
+}
 __device__ __forceinline__ void cnb_stv(float* p, const float* v) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
 __device__ __forceinline__ uint32_t cnb_pack_bf16x2(float lo, float hi) {
     const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);

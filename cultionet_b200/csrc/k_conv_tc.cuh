@@ -29,8 +29,9 @@ constexpr int NUM_EPI_WARPS = 8;
 constexpr int MAX_TAPS = 16;    // taps summed over all phases
 constexpr int MAX_PHASES = 16;  // sub-pixel phases of a transposed convolution (stride^2)
 constexpr int MAX_MAPS = 9;     // A-operand tensor maps: one per source (unit stride) or one per tap (strided direct gather)
-constexpr int EPI_CHUNK_BYTES = 32 * 128;           // 32 rows x 64 bf16 columns staged per warp per chunk
-constexpr int EPI_STAGING_BYTES = 0;  // (no shared-memory staging in the epilogue)
+constexpr int EPI_CHUNK_BYTES = 32 * 64;            // 32 rows x 32 bf16 columns staged per warp per chunk
+constexpr int EPI_STAGING_BYTES = NUM_EPI_WARPS * EPI_CHUNK_BYTES;  // one staging tile per epilogue warp (row-contiguous stores)
+constexpr int MAX_STAGES = 12;  // barrier slots; the weights-resident mode runs up to 12 A-only stages
 
 // The iteration space is a list of PHASES.  A phase is a unit-stride gather over a (Hv x Wv) domain per image with its own taps;
 // domain pixel (vy, vx) produces output pixel (vy*osy + ooy, vx*osx + oox).
@@ -63,6 +64,13 @@ struct ConvTcParams {
     const float* ep_shift;
     int ep_act;
     float* stats;  // optional [2*N]: per-output-channel sum and sum of squares of the STORED (bf16-rounded) outputs, for BatchNorm
+    int par_smem;    // bias / ep_scale / ep_shift are copied to shared memory once per CTA (N <= STATS_MAX_N)
+    int staged;      // epilogue stores go through the warp's staging tile: a store instruction writes 8 rows x 64 contiguous bytes
+    // weights-resident mode (one N tile, all taps x chunks of B fit beside >= 4 A stages): B is loaded ONCE per CTA into the first
+    // res_bytes of the ring region and the pipeline stages carry the A operand only
+    int b_resident, res_bytes, nstages;
+    int prefetch;  // tiles (per CTA) the producer prefetches ahead into L2; 0 = off
+    int dbg;  // diagnostics only (CNB_EPI_DEBUG bit mask, timing experiments): 1 = epilogue skips its global stores, 2 = skips the BatchNorm sums
     // split output (cnb_conv_desc::nout): columns [seg_begin[i], seg_begin[i+1]) of the GEMM go to seg_out[i]; boundaries are
     // multiples of 32, so every 32-column epilogue chunk has one destination
     int nseg;
@@ -123,6 +131,14 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint
                  "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
                  : "memory");
 }
+// L2 prefetch of one box (no shared memory, no barrier): the producer runs it a few tiles ahead, so that the tile loads themselves are
+// L2 hits.  The 1x1 / short-K convolutions keep only 64 KB of the A operand in flight per SM (four stages); at DRAM latency that is
+// ~3 TB/s for the whole GPU, and any extra traffic (the epilogue's stores) stretched the latency and with it the step.
+__device__ __forceinline__ void tma_prefetch_4d(const void* tmap, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0),
+                 "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t src, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(reinterpret_cast<uint64_t>(tmap)),
                  "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
@@ -152,6 +168,26 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+// issue only: the registers are written asynchronously and must not be read before tmem_ld_wait(v)
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+// wait for every outstanding tcgen05.ld of this thread.  The empty volatile statements that follow make every register an in/out
+// operand of something ordered AFTER the wait (volatile asm statements keep their order), so no use of them can be scheduled above it.
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) asm volatile("" : "+r"(v[i]));
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
@@ -239,26 +275,32 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;          // SWIZZLE_128B atoms need 1024 B alignment
     uint8_t* base_ptr = smem_raw + (base - raw);
-    const uint32_t staging = base + C::RING_BYTES;                      // epilogue staging: [warp][2][32 rows x 64 B]
-    const uint32_t bars = staging + EPI_STAGING_BYTES;                  // full[S] empty[S] tmem_full[2] tmem_empty[2] slot
+    // layout: [resident B (res_bytes) | pipeline stages]  = C::RING_BYTES, [epilogue staging], [barriers 256 B], [2*N floats]
+    const uint32_t staging = base + C::RING_BYTES;
+    const uint32_t bars = staging + EPI_STAGING_BYTES;  // full[MAX_STAGES] empty[MAX_STAGES] tmem_full[2] tmem_empty[2] bres slot
     auto full_bar = [&](int s) { return bars + 8u * s; };
-    auto empty_bar = [&](int s) { return bars + 8u * (C::STAGES + s); };
-    auto tfull_bar = [&](int a) { return bars + 8u * (2 * C::STAGES + a); };
-    auto tempty_bar = [&](int a) { return bars + 8u * (2 * C::STAGES + 2 + a); };
-    const uint32_t slot = bars + 8u * (2 * C::STAGES + 4);
+    auto empty_bar = [&](int s) { return bars + 8u * (MAX_STAGES + s); };
+    auto tfull_bar = [&](int a) { return bars + 8u * (2 * MAX_STAGES + a); };
+    auto tempty_bar = [&](int a) { return bars + 8u * (2 * MAX_STAGES + 2 + a); };
+    const uint32_t bres_bar = bars + 8u * (2 * MAX_STAGES + 4);
+    const uint32_t slot = bars + 8u * (2 * MAX_STAGES + 5);
     volatile uint32_t* slot_ptr =
-        reinterpret_cast<volatile uint32_t*>(base_ptr + C::RING_BYTES + EPI_STAGING_BYTES + 8 * (2 * C::STAGES + 4));
+        reinterpret_cast<volatile uint32_t*>(base_ptr + C::RING_BYTES + EPI_STAGING_BYTES + 8 * (2 * MAX_STAGES + 5));
+    const int nstages = p.nstages;
+    const uint32_t stage_bytes = p.b_resident ? (uint32_t)A_BYTES : (uint32_t)C::STAGE_BYTES;
+    const uint32_t ring0 = base + (uint32_t)p.res_bytes;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* sm_stats = reinterpret_cast<float*>(base_ptr + C::RING_BYTES + EPI_STAGING_BYTES + 256);  // [2*N] when p.stats
+    // [2*N] floats: BatchNorm partial sums (p.stats), or bias / scale | shift of the fused epilogue (p.par_smem)
+    float* sm_par = reinterpret_cast<float*>(base_ptr + C::RING_BYTES + EPI_STAGING_BYTES + 256);
     if (p.stats)
-        for (int i = threadIdx.x; i < 2 * p.N; i += NUM_THREADS) sm_stats[i] = 0.f;
+        for (int i = threadIdx.x; i < 2 * p.N; i += NUM_THREADS) sm_par[i] = 0.f;
 
     if (warp == 0 && lane == 0) {
         const int nmaps = p.per_tap_map ? p.ph_tap0[p.nphases] : p.nsrc;
         for (int s = 0; s < nmaps; ++s) tma_prefetch_desc(&p.tmA[s]);
         tma_prefetch_desc(&p.tmB);
-        for (int s = 0; s < C::STAGES; ++s) {
+        for (int s = 0; s < nstages; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
         }
@@ -266,6 +308,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             mbar_init(tfull_bar(a), 1);
             mbar_init(tempty_bar(a), NUM_EPI_WARPS);  // one arrive per epilogue warp
         }
+        mbar_init(bres_bar, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(slot, C::TMEM_COLS);
@@ -283,22 +326,50 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
+            if (p.b_resident) {
+                // every (tap, source, chunk) tile of the packed weights, once per CTA, in the order the K loop walks them
+                mbar_arrive_expect_tx(bres_bar, (uint32_t)p.res_bytes);
+                uint32_t dst = base;
+                for (int t = 0; t < p.ph_tap0[p.nphases]; ++t)
+                    for (int s = 0; s < p.nsrc; ++s)
+                        for (int kc = 0; kc < p.chunks[s]; ++kc) {
+                            tma_load_3d(dst, &p.tmB, bres_bar, p.koff[s] + kc * BK, 0, p.tap_w[t]);
+                            dst += C::B_BYTES;
+                        }
+            }
             int stage = 0;
             uint32_t phase = 0;
             TileCoord tc;
+            // L2 prefetch of the un-shifted box of a pixel tile, per source chunk (the halo comes from the neighbouring tiles' boxes,
+            // which other CTAs prefetch at about the same time); only the first N tile of a pixel tile does it
+            auto prefetch_tile = [&](int tile) {
+                if (tile >= p.num_tiles || p.per_tap_map) return;
+                TileCoord pc;
+                decode_tile(p, tile, BN, pc);
+                if (pc.n0 != 0 || p.ph_tap0[pc.ph + 1] == p.ph_tap0[pc.ph]) return;
+                int t0 = p.ph_tap0[pc.ph];  // the tap with the smallest shift
+                for (int t = t0 + 1; t < p.ph_tap0[pc.ph + 1]; ++t)
+                    if (abs(p.tap_dy[t]) + abs(p.tap_dx[t]) < abs(p.tap_dy[t0]) + abs(p.tap_dx[t0])) t0 = t;
+                for (int s = 0; s < p.nsrc; ++s)
+                    for (int kc = 0; kc < p.chunks[s]; ++kc)
+                        tma_prefetch_4d(&p.tmA[s], kc * BK, pc.x0 + p.tap_dx[t0], pc.y0 + p.tap_dy[t0], pc.b);
+            };
+            if (p.prefetch)
+                for (int a = 1; a <= p.prefetch; ++a) prefetch_tile(blockIdx.x + a * (int)gridDim.x);
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 decode_tile(p, tile, BN, tc);
+                if (p.prefetch) prefetch_tile(tile + (p.prefetch + 1) * (int)gridDim.x);
                 for (int t = p.ph_tap0[tc.ph]; t < p.ph_tap0[tc.ph + 1]; ++t) {
                     const int cy = tc.y0 + p.tap_dy[t], cx = tc.x0 + p.tap_dx[t], wt = p.tap_w[t];
                     for (int s = 0; s < p.nsrc; ++s) {
                         const CUtensorMap* am = &p.tmA[p.per_tap_map ? p.tap_map[t] : s];
                         for (int kc = 0; kc < p.chunks[s]; ++kc) {
                             mbar_wait(empty_bar(stage), phase ^ 1u);
-                            mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
-                            const uint32_t a_dst = base + stage * C::STAGE_BYTES;
+                            mbar_arrive_expect_tx(full_bar(stage), stage_bytes);
+                            const uint32_t a_dst = ring0 + stage * stage_bytes;
                             tma_load_4d(a_dst, am, full_bar(stage), kc * BK, cx, cy, tc.b);
-                            tma_load_3d(a_dst + A_BYTES, &p.tmB, full_bar(stage), p.koff[s] + kc * BK, tc.n0, wt);
-                            if (++stage == C::STAGES) {
+                            if (!p.b_resident) tma_load_3d(a_dst + A_BYTES, &p.tmB, full_bar(stage), p.koff[s] + kc * BK, tc.n0, wt);
+                            if (++stage == nstages) {
                                 stage = 0;
                                 phase ^= 1u;
                             }
@@ -316,9 +387,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             uint32_t phase = 0;
             int it = 0;
             TileCoord tc;
+            if (p.b_resident) {
+                mbar_wait(bres_bar, 0u);
+                tc_fence_after();
+            }
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
                 decode_tile(p, tile, BN, tc);
                 const int total_chunks = (p.ph_tap0[tc.ph + 1] - p.ph_tap0[tc.ph]) * chunks_per_tap;
+                const uint32_t b_res0 = base + (uint32_t)(p.ph_tap0[tc.ph] * chunks_per_tap) * (uint32_t)C::B_BYTES;
                 const int acc = it & 1;
                 const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator
@@ -327,16 +403,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 for (int c = 0; c < total_chunks; ++c) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
-                    const uint32_t a_addr = base + stage * C::STAGE_BYTES;
+                    const uint32_t a_addr = ring0 + stage * stage_bytes;
                     const uint64_t adesc = umma_desc_sw128(a_addr);
-                    const uint64_t bdesc = umma_desc_sw128(a_addr + A_BYTES);
+                    const uint64_t bdesc = umma_desc_sw128(p.b_resident ? b_res0 + (uint32_t)c * (uint32_t)C::B_BYTES : a_addr + A_BYTES);
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
                         // +32 bytes per UMMA_K step inside the 128-byte swizzled row => +2 in the (addr >> 4) field
                         umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (c > 0 || k > 0) ? 1u : 0u);
                     }
                     umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs have read it
-                    if (++stage == C::STAGES) {
+                    if (++stage == nstages) {
                         stage = 0;
                         phase ^= 1u;
                     }
@@ -350,16 +426,32 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         __syncwarp();
     } else {
         // ===================== epilogue: TMEM -> registers -> bf16 -> global =====================
-        // A TMEM lane holds one pixel row; each lane converts and stores its own row, 64 bytes per 32-column chunk.  Measured
-        // alternatives (profiles/r01_epilogue_variants.md): staging through shared memory for whole-line stores and a TMA bulk
-        // store were both SLOWER -- the epilogue is bound by the instruction latency of a single warp, not by the store pattern --
-        // so the lean direct store stays and the work is split over EIGHT warps instead (two per TMEM lane quadrant, alternating
-        // 32-column chunks), which is what shortens the convolutions whose K loop is too short to hide it (1x1, transposed phases).
+        // A TMEM lane holds one pixel row: after tcgen05.ld a lane owns 32 columns (64 bytes) of ITS row.  Round 2 (ncu of the 1x1 and
+        // short-K convolutions, whose K loop cannot hide the epilogue: 5.5-6 us per 128 x 256 tile against 1.2 us of MMA):
+        //   * bias / scale / shift come from shared memory (copied once per CTA) -- the 32-64 uniform __ldg per chunk were the top
+        //     long-scoreboard and LSU-queue stalls;
+        //   * the next chunk's tcgen05.ld is in flight while the current one is converted and stored (two register sets);
+        //   * stores go through a 2 KB staging tile per warp so that an instruction writes 8 rows x 64 contiguous bytes (8 lines)
+        //     instead of 32 rows x 16 bytes (32 lines: 32 L1 tag cycles per instruction = 2.4 us per tile by itself).
+        // Eight warps, two per TMEM lane quadrant, alternate 32-column chunks.
         const int ew = warp - 2;
         const int quad = warp & 3;   // TMEM lane quadrant this warp may access (warp id % 4)
         const int half = ew >> 2;    // which of the two warps of that quadrant
         const int row = quad * 32 + lane;
         const int ly = row >> p.log2_tw, lx = row & (p.TW - 1);
+        uint8_t* stg = base_ptr + C::RING_BYTES + ew * EPI_CHUNK_BYTES;
+        const int sw_w = (lane >> 1) & 3;  // 16-byte chunk swizzle of this lane's own row (conflict-free 128-bit accesses both ways)
+        const int sw_r = (lane >> 3) & 3;  // ... of the rows (lane >> 2) + 8 k this lane stores (the same for every k)
+        const int rq = lane & 3;
+        if (p.par_smem) {
+            // epilogue threads only (named barrier 1): bias -> [0, N), or scale -> [0, N) and shift -> [N, 2N)
+            const float* a0 = p.ep_scale ? p.ep_scale : p.bias;
+            for (int i = (int)threadIdx.x - 64; i < p.N; i += NUM_EPI_WARPS * 32) {
+                sm_par[i] = a0[i];
+                if (p.ep_scale) sm_par[p.N + i] = p.ep_shift[i];
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory");
+        }
         int it = 0;
         TileCoord tc;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
@@ -372,79 +464,59 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             const bool has_taps = p.ph_tap0[tc.ph + 1] > p.ph_tap0[tc.ph];
             const int n0 = tc.n0;
             const long opix = ((long)tc.b * p.Hout + oy) * p.Wout + ox;
-            bf16_t* orow = p.out + opix * p.out_stride + n0;
+            // rows this lane stores in staged mode: (lane >> 2) + 8 k
+            long opix_k[4];
+            bool valid_k[4];
+            if (p.staged) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int src = (lane >> 2) + 8 * k;
+                    opix_k[k] = __shfl_sync(0xffffffffu, (long long)opix, src);
+                    valid_k[k] = __shfl_sync(0xffffffffu, (int)valid, src) != 0;
+                }
+            }
+            int nch = (p.N - n0 + 31) / 32;  // 32-column chunks of this tile that hold output channels
+            if (nch > BN / 32) nch = BN / 32;
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
-#pragma unroll 1
-            for (int c = half; c < BN / 32; c += 2) {
+
+            auto finish_chunk = [&](uint32_t(&v)[32], int c) {
                 const int col0 = n0 + c * 32;
-                if (col0 >= p.N) break;
-                uint32_t v[32];
-                tmem_ld32(taddr + (uint32_t)(c * 32), v);
+                const bool full = p.vec_ok && col0 + 32 <= p.N;
+                uint32_t packed[16];
                 if (p.stats) {
                     // BatchNorm batch statistics of this chunk (training-mode ConvBlock2d: no bias, no fused epilogue, N % 32 == 0):
                     // per-channel sum and sum of squares of the STORED (bf16-rounded) values over the warp's 32 pixel rows -- one
                     // transposing reduction per quantity (31 shuffles), then a shared-memory atomic per lane; the CTA flushes its
                     // [2, N] partials to global memory once, at the end.  The separate statistics pass (a full read of the output) goes.
-                    uint32_t packed[16];
-                    float vals[32], sq[32];
+                    float vals[32];  // one array, reduced twice (values, then squares): the two register sets of the pipelined
+                                     // tcgen05.ld leave no room for both at once
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         packed[j] = (has_taps && valid) ? cnb_pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])) : 0u;
-                        const float f0 = cnb_bits2f(packed[j] << 16), f1 = cnb_bits2f(packed[j] & 0xffff0000u);
-                        vals[2 * j] = f0, vals[2 * j + 1] = f1;
-                        sq[2 * j] = f0 * f0, sq[2 * j + 1] = f1 * f1;
+                        vals[2 * j] = cnb_bits2f(packed[j] << 16), vals[2 * j + 1] = cnb_bits2f(packed[j] & 0xffff0000u);
                     }
-                    const float s1 = warp_transpose_sum32(vals), s2 = warp_transpose_sum32(sq);
-                    atomicAdd(&sm_stats[col0 + lane], s1);
-                    atomicAdd(&sm_stats[p.N + col0 + lane], s2);
-                    if (valid) {
-                        uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-                    }
-                    continue;
-                }
-                if (!valid) continue;
-                bf16_t* ochunk = orow + c * 32;
-                if (p.nseg) {
-                    int sg = 0;
-                    while (sg + 1 < p.nseg && col0 >= p.seg_begin[sg + 1]) ++sg;
-                    ochunk = p.seg_out[sg] + opix * p.seg_stride[sg] + (col0 - p.seg_begin[sg]);
-                }
-                if (p.ep_scale && p.vec_ok && col0 + 32 <= p.N) {
-                    // eval-mode BatchNorm (+ SiLU) on the fp32 accumulator: the convolution output never exists un-normalised
-                    uint32_t packed[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        float f0 = fmaf(has_taps ? __uint_as_float(v[2 * j]) : 0.f, __ldg(p.ep_scale + col0 + 2 * j), __ldg(p.ep_shift + col0 + 2 * j));
-                        float f1 = fmaf(has_taps ? __uint_as_float(v[2 * j + 1]) : 0.f, __ldg(p.ep_scale + col0 + 2 * j + 1),
-                                        __ldg(p.ep_shift + col0 + 2 * j + 1));
-                        if (p.ep_act) f0 = cnb_silu_t<bf16_t>(f0), f1 = cnb_silu_t<bf16_t>(f1);
-                        packed[j] = cnb_pack_bf16x2(f0, f1);
-                    }
-                    uint4* dst = reinterpret_cast<uint4*>(ochunk);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-                } else if (p.vec_ok && col0 + 32 <= p.N) {
-                    uint32_t packed[16];
-                    if (p.bias) {
+                    if (!(p.dbg & 2)) {
+                        const float s1 = warp_transpose_sum32(vals);
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            const float f0 = (has_taps ? __uint_as_float(v[2 * j]) : 0.f) + __ldg(p.bias + col0 + 2 * j);
-                            const float f1 = (has_taps ? __uint_as_float(v[2 * j + 1]) : 0.f) + __ldg(p.bias + col0 + 2 * j + 1);
-                            packed[j] = cnb_pack_bf16x2(f0, f1);
+                            const float f0 = cnb_bits2f(packed[j] << 16), f1 = cnb_bits2f(packed[j] & 0xffff0000u);
+                            vals[2 * j] = f0 * f0, vals[2 * j + 1] = f1 * f1;
                         }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            packed[j] = has_taps ? cnb_pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])) : 0u;
+                        const float s2 = warp_transpose_sum32(vals);
+                        atomicAdd(&sm_par[col0 + lane], s1);
+                        atomicAdd(&sm_par[p.N + col0 + lane], s2);
                     }
-                    uint4* dst = reinterpret_cast<uint4*>(ochunk);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-                } else {
+                } else if (!full) {
+                    // ragged chunk (partial N tile or an unaligned pitch): scalar stores
+                    if (!valid) return;
+                    bf16_t* ochunk = p.out + opix * p.out_stride + col0;
+                    if (p.nseg) {
+                        int sg = 0;
+                        while (sg + 1 < p.nseg && col0 >= p.seg_begin[sg + 1]) ++sg;
+                        ochunk = p.seg_out[sg] + opix * p.seg_stride[sg] + (col0 - p.seg_begin[sg]);
+                    }
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         if (col0 + j < p.N) {
@@ -457,7 +529,97 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                             ochunk[j] = __float2bfloat16(f);
                         }
                     }
+                    return;
+                } else if (p.ep_scale) {
+                    // eval-mode BatchNorm (+ SiLU) on the fp32 accumulator: the convolution output never exists un-normalised
+                    if (p.par_smem) {
+                        const float4* sc4 = reinterpret_cast<const float4*>(sm_par + col0);
+                        const float4* sh4 = reinterpret_cast<const float4*>(sm_par + p.N + col0);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 sc = sc4[q], sh = sh4[q];
+                            float f0 = fmaf(has_taps ? __uint_as_float(v[4 * q]) : 0.f, sc.x, sh.x);
+                            float f1 = fmaf(has_taps ? __uint_as_float(v[4 * q + 1]) : 0.f, sc.y, sh.y);
+                            float f2 = fmaf(has_taps ? __uint_as_float(v[4 * q + 2]) : 0.f, sc.z, sh.z);
+                            float f3 = fmaf(has_taps ? __uint_as_float(v[4 * q + 3]) : 0.f, sc.w, sh.w);
+                            if (p.ep_act) f0 = cnb_silu_t<bf16_t>(f0), f1 = cnb_silu_t<bf16_t>(f1), f2 = cnb_silu_t<bf16_t>(f2), f3 = cnb_silu_t<bf16_t>(f3);
+                            packed[2 * q] = cnb_pack_bf16x2(f0, f1);
+                            packed[2 * q + 1] = cnb_pack_bf16x2(f2, f3);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            float f0 = fmaf(has_taps ? __uint_as_float(v[2 * j]) : 0.f, __ldg(p.ep_scale + col0 + 2 * j), __ldg(p.ep_shift + col0 + 2 * j));
+                            float f1 = fmaf(has_taps ? __uint_as_float(v[2 * j + 1]) : 0.f, __ldg(p.ep_scale + col0 + 2 * j + 1),
+                                            __ldg(p.ep_shift + col0 + 2 * j + 1));
+                            if (p.ep_act) f0 = cnb_silu_t<bf16_t>(f0), f1 = cnb_silu_t<bf16_t>(f1);
+                            packed[j] = cnb_pack_bf16x2(f0, f1);
+                        }
+                    }
+                } else if (p.bias) {
+                    if (p.par_smem) {
+                        const float4* b4 = reinterpret_cast<const float4*>(sm_par + col0);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 b = b4[q];
+                            packed[2 * q] = cnb_pack_bf16x2((has_taps ? __uint_as_float(v[4 * q]) : 0.f) + b.x,
+                                                            (has_taps ? __uint_as_float(v[4 * q + 1]) : 0.f) + b.y);
+                            packed[2 * q + 1] = cnb_pack_bf16x2((has_taps ? __uint_as_float(v[4 * q + 2]) : 0.f) + b.z,
+                                                                (has_taps ? __uint_as_float(v[4 * q + 3]) : 0.f) + b.w);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float f0 = (has_taps ? __uint_as_float(v[2 * j]) : 0.f) + __ldg(p.bias + col0 + 2 * j);
+                            const float f1 = (has_taps ? __uint_as_float(v[2 * j + 1]) : 0.f) + __ldg(p.bias + col0 + 2 * j + 1);
+                            packed[j] = cnb_pack_bf16x2(f0, f1);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        packed[j] = has_taps ? cnb_pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])) : 0u;
                 }
+                // ---- store the chunk: 64 bytes per pixel row ----
+                if (p.dbg & 1) return;
+                int sg = 0;
+                if (p.nseg)
+                    while (sg + 1 < p.nseg && col0 >= p.seg_begin[sg + 1]) ++sg;
+                bf16_t* const obase = p.nseg ? p.seg_out[sg] + (col0 - p.seg_begin[sg]) : p.out + col0;
+                const long opitch = p.nseg ? p.seg_stride[sg] : p.out_stride;
+                if (p.staged) {
+                    uint4* wrow = reinterpret_cast<uint4*>(stg + lane * 64);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) wrow[q ^ sw_w] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+                    __syncwarp();
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int rr = (lane >> 2) + 8 * k;
+                        const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 64 + ((rq ^ sw_r) << 4));
+                        if (valid_k[k]) *reinterpret_cast<uint4*>(obase + opix_k[k] * opitch + rq * 8) = val;
+                    }
+                    __syncwarp();
+                } else if (valid) {
+                    uint4* dst = reinterpret_cast<uint4*>(obase + opix * opitch);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) dst[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+                }
+            };
+
+            // two register sets: chunk c + 2 is on its way out of TMEM while chunk c is converted and stored
+            uint32_t va[32], vb[32];
+            int c = half;
+            if (c < nch) tmem_ld32_issue(taddr + (uint32_t)(c * 32), va);
+            while (c < nch) {
+                tmem_ld_wait(va);
+                if (c + 2 < nch) tmem_ld32_issue(taddr + (uint32_t)((c + 2) * 32), vb);
+                finish_chunk(va, c);
+                c += 2;
+                if (c >= nch) break;
+                tmem_ld_wait(vb);
+                if (c + 2 < nch) tmem_ld32_issue(taddr + (uint32_t)((c + 2) * 32), va);
+                finish_chunk(vb, c);
+                c += 2;
             }
             tc_fence_before();
             __syncwarp();
@@ -473,7 +635,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     }
     if (p.stats)
         for (int i = threadIdx.x; i < 2 * p.N; i += NUM_THREADS) {
-            const float t = sm_stats[i];
+            const float t = sm_par[i];
             if (t != 0.f) atomicAdd(p.stats + i, t);
         }
 }
@@ -494,6 +656,12 @@ inline EncodeTiledFn encode_tiled_fn() {
         return reinterpret_cast<EncodeTiledFn>(f);
     }();
     return fn;
+}
+
+// what the last failed tensor-map encode was asked for (appended to the C ABI's error message)
+inline char* encode_diag() {
+    static thread_local char buf[256] = {0};
+    return buf;
 }
 
 inline int num_sms() {
@@ -517,6 +685,16 @@ inline int make_grid_map(CUtensorMap* m, const void* ptr, int C, int W, int H, i
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_ERROR_INVALID_CONTEXT || r == CUDA_ERROR_NOT_INITIALIZED) {
+        // a driver-API call on a thread that has made no runtime call yet (autograd's backward thread when every allocation came out
+        // of torch's cache): bind the primary context of the current device to this thread and encode again
+        cudaFree(nullptr);
+        r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (r != CUDA_SUCCESS)
+        snprintf(encode_diag(), 256, "grid map: driver code %d, ptr %p, dims {%d,%d,%d,%d}, strides {%ld,%ld,%ld} elements, box {%d,%d,%d}", (int)r,
+                 ptr, C, W, H, B, sx, sy, sb, BK, TW, TH);
     return r == CUDA_SUCCESS ? 0 : 2;
 }
 
@@ -543,6 +721,14 @@ inline int make_weight_map(CUtensorMap* m, const void* ptr, int K, int rows, int
     cuuint32_t es[3] = {1, 1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_ERROR_INVALID_CONTEXT || r == CUDA_ERROR_NOT_INITIALIZED) {
+        cudaFree(nullptr);  // see make_grid_map
+        r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (r != CUDA_SUCCESS)
+        snprintf(encode_diag(), 256, "weight map: driver code %d, ptr %p, dims {%d,%d,%d}, strides {%ld,%ld} elements, box {%d,%d}", (int)r, ptr, K,
+                 rows, taps, row_stride, tap_stride, BK, BN);
     return r == CUDA_SUCCESS ? 0 : 2;
 }
 
@@ -600,8 +786,34 @@ inline bool tc_pdl_enabled() {
     return on;
 }
 
+// A/B switches of the round-2 epilogue and of the weights-resident mode (default on): CNB_EPI_STAGED=0, CNB_EPI_PARSMEM=0, CNB_B_RESIDENT=0
+inline bool env_on(const char* name) {
+    const char* e = getenv(name);
+    return !(e && e[0] == '0');
+}
+
+// pipeline depth / weights-resident decision (see ConvTcParams): resident when the launch has ONE N tile, every (tap, source, chunk)
+// tile of B fits beside at least four A-only stages, and a CTA runs enough pixel tiles to pay for loading all of B up front
 template <int BN>
-inline int launch_bn(const ConvTcParams& p, cudaStream_t stream) {
+inline void plan_ring(ConvTcParams& p, int total_b_tiles) {
+    static const bool allow = env_on("CNB_B_RESIDENT");
+    p.b_resident = 0, p.res_bytes = 0, p.nstages = Cfg<BN>::STAGES;
+    const long res = (long)total_b_tiles * Cfg<BN>::B_BYTES;
+    if (!allow || p.num_tiles != p.m_tiles || total_b_tiles <= 0 || res > Cfg<BN>::RING_BYTES) return;
+    const int stages = (int)((Cfg<BN>::RING_BYTES - res) / A_BYTES);
+    if (stages < 4 || p.m_tiles < 4 * num_sms()) return;
+    p.b_resident = 1;
+    p.res_bytes = (int)res;
+    p.nstages = stages < MAX_STAGES ? stages : MAX_STAGES;
+}
+
+template <int BN>
+inline int launch_bn(ConvTcParams& p, cudaStream_t stream) {
+    {
+        int cpt = 0;
+        for (int s = 0; s < p.nsrc; ++s) cpt += p.chunks[s];
+        plan_ring<BN>(p, p.ph_tap0[p.nphases] * cpt);
+    }
     static bool configured = false;
     if (!configured) {
         if (cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -610,7 +822,7 @@ inline int launch_bn(const ConvTcParams& p, cudaStream_t stream) {
         configured = true;
     }
     const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-    const int smem = Cfg<BN>::SMEM_BYTES + (p.stats ? 2 * p.N * (int)sizeof(float) : 0);
+    const int smem = Cfg<BN>::SMEM_BYTES + ((p.stats || p.par_smem) ? 2 * p.N * (int)sizeof(float) : 0);
     if (tc_pdl_enabled())
         CNB_LAUNCH(conv_tc_kernel<BN>, dim3(grid), dim3(NUM_THREADS), (size_t)smem, stream, p);
     else {
@@ -638,6 +850,7 @@ inline int pick_bn(int N) {
 inline int conv_tc_launch(const cnb_conv_desc* d, cudaStream_t stream) {
     ConvTcParams p;
     memset(&p, 0, sizeof(p));
+    encode_diag()[0] = 0;
     const int BN = pick_bn(d->N);
     const int s = d->stride;
     const int taps = d->KH * d->KW;
@@ -773,6 +986,21 @@ inline int conv_tc_launch(const cnb_conv_desc* d, cudaStream_t stream) {
         p.stats = reinterpret_cast<float*>(d->stats);
     }
     p.num_tiles = cnb_div_up(d->N, BN) * p.m_tiles;
+    {
+        static const bool staged = env_on("CNB_EPI_STAGED"), parsmem = env_on("CNB_EPI_PARSMEM");
+        static const int dbg = [] {
+            const char* e = getenv("CNB_EPI_DEBUG");
+            return e ? atoi(e) : 0;
+        }();
+        p.dbg = dbg;
+        static const int pf = [] {
+            const char* e = getenv("CNB_TC_PREFETCH");
+            return e ? atoi(e) : 0;  // measured slower (a64 +17 %, 960 -> 256 1x1 +38 %): off unless asked for
+        }();
+        p.prefetch = pf;
+        p.staged = (staged && p.vec_ok) ? 1 : 0;
+        p.par_smem = (parsmem && !p.stats && (p.bias || p.ep_scale) && d->N <= STATS_MAX_N) ? 1 : 0;
+    }
     switch (BN) {
         case 256: return launch_bn<256>(p, stream);
         case 128: return launch_bn<128>(p, stream);

@@ -191,6 +191,70 @@ __global__ void __launch_bounds__(256) conv_tiny_wgrad_kernel(cnb_wgrad_desc d) 
     }
 }
 
+// The Psi-Net head shapes again ((N, C) = (3, 9) and (3, 3)): the kernel above walks dY and X once per (tap, 4-channel chunk) = 27
+// passes over a 524 288-pixel level for the 9 -> 3 convolution (ncu: 85 us per launch for 13 MB of operands).  Here a thread keeps the
+// N x C products of TG taps in registers (N*C*TG <= 81), so the level is walked taps / TG times (3 for 9 -> 3, once for 3 -> 3), dY
+// is read once per pixel and pass, and the block reduces its TG*N*C partial sums once at the end.
+template <typename T, int N, int C, int TG>
+__global__ void __launch_bounds__(256) conv_tiny_wgrad_fixed_kernel(cnb_wgrad_desc d) {
+    CNB_PDL_SYNC();
+    __shared__ float red[TG * N * C];
+    const int taps = d.KH * d.KW;
+    const int tap0 = blockIdx.y * TG;
+    for (int i = threadIdx.x; i < TG * N * C; i += blockDim.x) red[i] = 0.f;
+    __syncthreads();
+    float acc[TG][N][C];
+#pragma unroll
+    for (int j = 0; j < TG; ++j)
+#pragma unroll
+        for (int n = 0; n < N; ++n)
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc[j][n][c] = 0.f;
+    const long M = (long)d.B * d.Hout * d.Wout;
+    const T* src = reinterpret_cast<const T*>(d.src);
+    const T* dy = reinterpret_cast<const T*>(d.dy);
+    for (long m = (long)blockIdx.x * blockDim.x + threadIdx.x; m < M; m += (long)gridDim.x * blockDim.x) {
+        const int ox = (int)(m % d.Wout);
+        const long t = m / d.Wout;
+        const int oy = (int)(t % d.Hout);
+        const int ob = (int)(t / d.Hout);
+        float g[N];
+#pragma unroll
+        for (int n = 0; n < N; ++n) g[n] = cnb_ld(dy + m * d.dy_stride + n);
+#pragma unroll
+        for (int j = 0; j < TG; ++j) {
+            const int tap = tap0 + j;
+            if (tap >= taps) continue;
+            const int ky = tap / d.KW, kx = tap - ky * d.KW;
+            int iy, ix;
+            if (!conv_src_coord(oy, ky, d.stride, d.pad, d.dil, d.transposed, d.Hin, iy)) continue;
+            if (!conv_src_coord(ox, kx, d.stride, d.pad, d.dil, d.transposed, d.Win, ix)) continue;
+            const T* sp = src + (((long)ob * d.Hin + iy) * d.Win + ix) * d.src_stride;
+            float xs[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) xs[c] = cnb_ld(sp + c);
+#pragma unroll
+            for (int n = 0; n < N; ++n)
+#pragma unroll
+                for (int c = 0; c < C; ++c) acc[j][n][c] = fmaf(g[n], xs[c], acc[j][n][c]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < TG; ++j)
+#pragma unroll
+        for (int n = 0; n < N; ++n)
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const float v = cnb_warp_sum(acc[j][n][c]);
+                if ((threadIdx.x & 31) == 0) atomicAdd(&red[(j * N + n) * C + c], v);
+            }
+    __syncthreads();
+    for (int i = threadIdx.x; i < TG * N * C; i += blockDim.x) {
+        const int c = i % C, n = (i / C) % N, tap = tap0 + i / (C * N);
+        if (tap < taps) atomicAdd(d.dwp + ((long)tap * N + n) * d.Ctot + d.k_off + c, red[i]);
+    }
+}
+
 // dst[p][0..C) = src[p][0..C), dst[p][C..dst_stride) = 0: gives a skinny tensor the 16-byte pixel pitch TMA needs
 template <typename T>
 __global__ void repitch_kernel(const T* __restrict__ src, int src_stride, T* __restrict__ dst, int dst_stride, long P, int C) {

@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ d
 // LayerNorm over channels: one warp per pixel, K vectors per lane (C <= 32*V*K), one read of x
 // ---------------------------------------------------------------------------------------------------------------------
 template <typename T, int K>
-__global__ void __launch_bounds__(256) layernorm_fwd_vec_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
+__global__ void __launch_bounds__(256, 3) layernorm_fwd_vec_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
                                                                const float* __restrict__ beta, float eps, T* __restrict__ y,
                                                                float* __restrict__ save_mean, float* __restrict__ save_rstd, long P,
                                                                int C) {
@@ -299,50 +299,66 @@ __global__ void __launch_bounds__(256) layernorm_fwd_vec_kernel(const T* __restr
             bt[k][j] = c < C ? beta[c + j] : 0.f;
         }
     }
-    for (long p = warp; p < P; p += nwarps) {
-        float v[K][V];
-        float s = 0.f;
+    // U pixels per warp and trip, all loads issued before the first reduction: a warp moves 512 bytes per pixel at C = 256, and with one
+    // pixel in flight per warp an SM had ~16 KB outstanding (ncu: 4.0 TB/s, issue slots 49 % busy, waiting on the loads)
+    constexpr int U = K == 1 ? 4 : 2;
+    for (long p0 = warp * U; p0 < P; p0 += nwarps * U) {
+        uint4 raw[U][K];  // in flight as raw 16-byte words: 4 registers per vector instead of 8 expanded floats
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const int c = (lane + 32 * k) * V;
-            if (c < C) {
-                cnb_ldv(x + p * C + c, v[k]);
+        for (int u = 0; u < U; ++u)
 #pragma unroll
-                for (int j = 0; j < V; ++j) s += v[k][j];
+            for (int k = 0; k < K; ++k) {
+                const int c = (lane + 32 * k) * V;
+                if (c < C && p0 + u < P) raw[u][k] = cnb_ldraw(x + (p0 + u) * C + c);
             }
-        }
-        const float mean = cnb_warp_sum(s) * invC;
-        float q = 0.f;
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const int c = (lane + 32 * k) * V;
-            if (c < C) {
+        for (int u = 0; u < U; ++u) {
+            const long p = p0 + u;
+            if (p >= P) break;  // warp-uniform
+            float v[1][K][V];
+            float s = 0.f;
 #pragma unroll
-                for (int j = 0; j < V; ++j) {
-                    const float d = v[k][j] - mean;
-                    q = fmaf(d, d, q);
+            for (int k = 0; k < K; ++k) {
+                const int c = (lane + 32 * k) * V;
+                if (c < C) {
+                    cnb_expand(raw[u][k], v[0][k], x);
+#pragma unroll
+                    for (int j = 0; j < V; ++j) s += v[0][k][j];
                 }
             }
-        }
-        const float rstd = rsqrtf(cnb_warp_sum(q) * invC + eps);
+            const float mean = cnb_warp_sum(s) * invC;
+            float q = 0.f;
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const int c = (lane + 32 * k) * V;
-            if (c < C) {
+            for (int k = 0; k < K; ++k) {
+                const int c = (lane + 32 * k) * V;
+                if (c < C) {
 #pragma unroll
-                for (int j = 0; j < V; ++j) v[k][j] = fmaf((v[k][j] - mean) * rstd, gm[k][j], bt[k][j]);
-                cnb_stv(y + p * C + c, v[k]);
+                    for (int j = 0; j < V; ++j) {
+                        const float d = v[0][k][j] - mean;
+                        q = fmaf(d, d, q);
+                    }
+                }
             }
-        }
-        if (lane == 0) {
-            save_mean[p] = mean;
-            save_rstd[p] = rstd;
+            const float rstd = rsqrtf(cnb_warp_sum(q) * invC + eps);
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int c = (lane + 32 * k) * V;
+                if (c < C) {
+#pragma unroll
+                    for (int j = 0; j < V; ++j) v[0][k][j] = fmaf((v[0][k][j] - mean) * rstd, gm[k][j], bt[k][j]);
+                    cnb_stv(y + p * C + c, v[0][k]);
+                }
+            }
+            if (lane == 0) {
+                save_mean[p] = mean;
+                save_rstd[p] = rstd;
+            }
         }
     }
 }
 
 template <typename T, int K>
-__global__ void __launch_bounds__(256) layernorm_bwd_vec_kernel(const T* __restrict__ x, const T* __restrict__ dy,
+__global__ void __launch_bounds__(256, 3) layernorm_bwd_vec_kernel(const T* __restrict__ x, const T* __restrict__ dy,
                                                                const float* __restrict__ gamma, const float* __restrict__ save_mean,
                                                                const float* __restrict__ save_rstd, T* __restrict__ dx,
                                                                float* __restrict__ dgamma, float* __restrict__ dbeta, long P, int C) {
@@ -367,39 +383,59 @@ __global__ void __launch_bounds__(256) layernorm_bwd_vec_kernel(const T* __restr
             db[k][j] = 0.f;
         }
     }
-    for (long p = warp; p < P; p += nwarps) {
-        const float mean = save_mean[p], rstd = save_rstd[p];
-        float xh[K][V], d[K][V];
-        float s1 = 0.f, s2 = 0.f;
+    constexpr int U = K == 1 ? 2 : 1;  // pixels per warp and trip (see the forward kernel)
+    for (long p0 = warp * U; p0 < P; p0 += nwarps * U) {
+        uint4 rx[U][K], rd[U][K];
+        float mean[U], rstd[U];
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const int c = (lane + 32 * k) * V;
-            if (c < C) {
-                cnb_ldv(x + p * C + c, xh[k]);
-                cnb_ldv(dy + p * C + c, d[k]);
+        for (int u = 0; u < U; ++u) {
+            const long p = p0 + u < P ? p0 + u : P - 1;
+            mean[u] = save_mean[p], rstd[u] = save_rstd[p];
 #pragma unroll
-                for (int j = 0; j < V; ++j) {
-                    xh[k][j] = (xh[k][j] - mean) * rstd;
-                    const float gd = d[k][j] * g[k][j];
-                    s1 += gd;
-                    s2 = fmaf(gd, xh[k][j], s2);
+            for (int k = 0; k < K; ++k) {
+                const int c = (lane + 32 * k) * V;
+                if (c < C && p0 + u < P) {
+                    rx[u][k] = cnb_ldraw(x + p * C + c);
+                    rd[u][k] = cnb_ldraw(dy + p * C + c);
                 }
             }
         }
-        s1 = cnb_warp_sum(s1) * invC;
-        s2 = cnb_warp_sum(s2) * invC;
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const int c = (lane + 32 * k) * V;
-            if (c < C) {
-                float o[V];
+        for (int u = 0; u < U; ++u) {
+            const long p = p0 + u;
+            if (p >= P) break;  // warp-uniform
+            float xh[1][K][V], d[1][K][V];
+            float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-                for (int j = 0; j < V; ++j) {
-                    o[j] = rstd * (d[k][j] * g[k][j] - s1 - xh[k][j] * s2);
-                    dg[k][j] = fmaf(d[k][j], xh[k][j], dg[k][j]);
-                    db[k][j] += d[k][j];
+            for (int k = 0; k < K; ++k) {
+                const int c = (lane + 32 * k) * V;
+                if (c < C) {
+                    cnb_expand(rx[u][k], xh[0][k], x);
+                    cnb_expand(rd[u][k], d[0][k], dy);
+#pragma unroll
+                    for (int j = 0; j < V; ++j) {
+                        xh[0][k][j] = (xh[0][k][j] - mean[u]) * rstd[u];
+                        const float gd = d[0][k][j] * g[k][j];
+                        s1 += gd;
+                        s2 = fmaf(gd, xh[0][k][j], s2);
+                    }
                 }
-                cnb_stv(dx + p * C + c, o);
+            }
+            s1 = cnb_warp_sum(s1) * invC;
+            s2 = cnb_warp_sum(s2) * invC;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int c = (lane + 32 * k) * V;
+                if (c < C) {
+                    float o[V];
+#pragma unroll
+                    for (int j = 0; j < V; ++j) {
+                        o[j] = rstd[u] * (d[0][k][j] * g[k][j] - s1 - xh[0][k][j] * s2);
+                        dg[k][j] = fmaf(d[0][k][j], xh[0][k][j], dg[k][j]);
+                        db[k][j] += d[0][k][j];
+                    }
+                    cnb_stv(dx + p * C + c, o);
+                }
             }
         }
     }
@@ -549,9 +585,13 @@ __device__ __forceinline__ void bilinear_support(int i, float rscale, int in_len
     }
 }
 
+// One CTA per input row (the x-axis table is rebuilt by every CTA, but 4064 short CTAs fill and drain the machine better than ~1000
+// persistent ones: 199 vs 218 us at level a).  With `colsum` the CTA also adds the per-channel sums of the row it wrote to colsum[C]
+// (the bias gradient of the ConvTranspose2d whose output was resized).
 template <typename T, int NC>
-__global__ void __launch_bounds__(256) resize_bilinear_bwd_tab_kernel(const T* __restrict__ dy, T* __restrict__ dx, int B, int Hin, int Win,
-                                                                     int Hout, int Wout, int C, float rh, float rw) {
+__global__ void __launch_bounds__(256) resize_bilinear_bwd_row_kernel(const T* __restrict__ dy, T* __restrict__ dx, int B, int Hin, int Win,
+                                                                     int Hout, int Wout, int C, float rh, float rw,
+                                                                     float* __restrict__ colsum) {
     CNB_PDL_SYNC();
     constexpr int V = cnb_vec<T>::N;
     CNB_DYN_SMEM(sm_raw);  // int xfirst[Win]; float wx[Win][NC]; int yfirst; float wy[NC]
@@ -559,6 +599,7 @@ __global__ void __launch_bounds__(256) resize_bilinear_bwd_tab_kernel(const T* _
     float* wxs = reinterpret_cast<float*>(xfirst + Win);
     int* yfirst_s = reinterpret_cast<int*>(wxs + Win * NC);
     float* wys = reinterpret_cast<float*>(yfirst_s + 1);
+    float* csum = wys + NC;  // [C] when colsum
     const int CV = C / V;
     const int iy = blockIdx.x % Hin;
     const int b = blockIdx.x / Hin;
@@ -570,6 +611,8 @@ __global__ void __launch_bounds__(256) resize_bilinear_bwd_tab_kernel(const T* _
 #pragma unroll
         for (int a = 0; a < NC; ++a) wxs[ix * NC + a] = w[a];
     }
+    if (colsum)
+        for (int i = threadIdx.x; i < C; i += blockDim.x) csum[i] = 0.f;
     if (threadIdx.x == 0) {
         float w[NC];
         int f;
@@ -586,6 +629,9 @@ __global__ void __launch_bounds__(256) resize_bilinear_bwd_tab_kernel(const T* _
     const T* base = dy + ((long)b * Hout + yfirst) * Wout * C;
     T* orow = dx + ((long)b * Hin + iy) * Win * C;
     const int n = Win * CV;
+    float cs[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) cs[j] = 0.f;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const int ix = i / CV;
         const int c = (i - ix * CV) * V;
@@ -611,6 +657,106 @@ __global__ void __launch_bounds__(256) resize_bilinear_bwd_tab_kernel(const T* _
             }
         }
         cnb_stv(orow + ix * C + c, acc);
+#pragma unroll
+        for (int j = 0; j < V; ++j) cs[j] += acc[j];
+    }
+    if (colsum) {  // uniform; blockDim % CV == 0: a thread stays on one channel vector
+        if ((int)threadIdx.x < n) {
+            const int c = ((int)threadIdx.x % CV) * V;
+#pragma unroll
+            for (int j = 0; j < V; ++j) atomicAdd(&csum[c + j], cs[j]);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&colsum[i], csum[i]);
+    }
+}
+
+
+// Persistent over input rows (row = blockIdx.x, += gridDim.x): the x- and y-axis support tables are built ONCE per CTA (the one-row
+// CTAs of the first version rebuilt the x table 4064 times per level-a launch), and with `colsum` the kernel also accumulates the
+// per-channel sum of the gradient it writes -- the bias gradient of the ConvTranspose2d whose output was resized -- so that tensor is
+// not read a second time by a column-sum launch (blockDim % (C / V) == 0: a thread stays on one channel vector).
+template <typename T, int NC>
+__global__ void __launch_bounds__(256) resize_bilinear_bwd_tab_kernel(const T* __restrict__ dy, T* __restrict__ dx, int B, int Hin, int Win,
+                                                                     int Hout, int Wout, int C, float rh, float rw,
+                                                                     float* __restrict__ colsum) {
+    CNB_PDL_SYNC();
+    constexpr int V = cnb_vec<T>::N;
+    CNB_DYN_SMEM(sm_raw);  // int xfirst[Win]; float wx[Win][NC]; int yfirst[Hin]; float wy[Hin][NC]; float csum[C]
+    int* xfirst = reinterpret_cast<int*>(sm_raw);
+    float* wxs = reinterpret_cast<float*>(xfirst + Win);
+    int* yfirst_s = reinterpret_cast<int*>(wxs + Win * NC);
+    float* wys = reinterpret_cast<float*>(yfirst_s + Hin);
+    float* csum = wys + Hin * NC;
+    const int CV = C / V;
+    for (int ix = threadIdx.x; ix < Win; ix += blockDim.x) {
+        float w[NC];
+        int f;
+        bilinear_support<NC>(ix, rw, Win, Wout, f, w);
+        xfirst[ix] = f;
+#pragma unroll
+        for (int a = 0; a < NC; ++a) wxs[ix * NC + a] = w[a];
+    }
+    for (int iy = threadIdx.x; iy < Hin; iy += blockDim.x) {
+        float w[NC];
+        int f;
+        bilinear_support<NC>(iy, rh, Hin, Hout, f, w);
+        yfirst_s[iy] = f;
+#pragma unroll
+        for (int a = 0; a < NC; ++a) wys[iy * NC + a] = w[a];
+    }
+    if (colsum)
+        for (int i = threadIdx.x; i < C; i += blockDim.x) csum[i] = 0.f;
+    __syncthreads();
+    float cs[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) cs[j] = 0.f;
+    const int n = Win * CV;
+    for (int row = blockIdx.x; row < B * Hin; row += gridDim.x) {
+        const int iy = row % Hin;
+        const int b = row / Hin;
+        float wy[NC];
+#pragma unroll
+        for (int a = 0; a < NC; ++a) wy[a] = wys[iy * NC + a];
+        const T* base = dy + ((long)b * Hout + yfirst_s[iy]) * Wout * C;
+        T* orow = dx + ((long)b * Hin + iy) * Win * C;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int ix = i / CV;
+            const int c = (i - ix * CV) * V;
+            const T* col = base + (long)xfirst[ix] * C + c;
+            float wx[NC];
+#pragma unroll
+            for (int a = 0; a < NC; ++a) wx[a] = wxs[ix * NC + a];
+            float acc[V];
+#pragma unroll
+            for (int j = 0; j < V; ++j) acc[j] = 0.f;
+#pragma unroll
+            for (int a = 0; a < NC; ++a) {
+                if (wy[a] == 0.f) continue;  // CTA-uniform
+#pragma unroll
+                for (int bb = 0; bb < NC; ++bb) {
+                    const float w = wy[a] * wx[bb];
+                    if (w != 0.f) {
+                        float v[V];
+                        cnb_ldv(col + ((long)a * Wout + bb) * C, v);
+#pragma unroll
+                        for (int j = 0; j < V; ++j) acc[j] = fmaf(w, v[j], acc[j]);
+                    }
+                }
+            }
+            cnb_stv(orow + ix * C + c, acc);
+#pragma unroll
+            for (int j = 0; j < V; ++j) cs[j] += acc[j];
+        }
+    }
+    if (colsum) {  // uniform
+        if ((int)threadIdx.x < n) {
+            const int c = ((int)threadIdx.x % CV) * V;
+#pragma unroll
+            for (int j = 0; j < V; ++j) atomicAdd(&csum[c + j], cs[j]);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&colsum[i], csum[i]);
     }
 }
 

@@ -116,7 +116,8 @@ class TrainStep:
         with deferred_batch_counters():  # one multi-tensor launch for the 52 BatchNorm step counters
             loss = self.model.training_step(batch, 0)
         # weight / bias gradients go straight into the flat gradient buffer unless per-parameter hooks must see them (overlapped DDP)
-        with F.direct_param_grads(self.sync is None or not self.sync.enabled):
+        # (zero_grad above has just cleared the flat gradient buffer: every gradient kernel accumulates, none clears its target first)
+        with F.direct_param_grads(self.sync is None or not self.sync.enabled, zeroed=True):
             loss.backward()
         if self.sync is not None:
             self.sync.finish()

@@ -258,6 +258,7 @@ def _launch_conv(sources, src_channels, wp, w_row_off, w_row_stride, w_tap_strid
 # optim.FlatAdamW) and the backward returns None for them: no temporary gradient tensor and no AccumulateGrad add per parameter.
 # engine.TrainStep switches it on when no per-parameter gradient hook has to fire (no overlapped bucketed all-reduce).
 DIRECT_PARAM_GRAD = [False]
+_DIRECT_ZEROED = [False]
 _DIRECT_WRITTEN: set = set()  # parameters whose gradient buffer already holds a contribution of the running backward
 
 
@@ -265,11 +266,14 @@ class direct_param_grads:
     """``with direct_param_grads(): loss.backward()`` -- the gradient buffers must be ZERO (or stale) on entry: the first contribution
     to a parameter overwrites its buffer (a plain store instead of a read-modify-write), later ones (a shared parameter) accumulate."""
 
-    def __init__(self, enabled: bool = True):
+    def __init__(self, enabled: bool = True, zeroed: bool = False):
         self.enabled = enabled
+        self.zeroed = zeroed  # the caller has just cleared every gradient buffer: every contribution accumulates, no kernel clears
 
     def __enter__(self):
         self.prev = DIRECT_PARAM_GRAD[0]
+        self.prev_zeroed = _DIRECT_ZEROED[0]
+        _DIRECT_ZEROED[0] = bool(self.zeroed)
         DIRECT_PARAM_GRAD[0] = bool(self.enabled)
         _DIRECT_WRITTEN.clear()
         _PENDING_SMALL.clear()
@@ -277,6 +281,7 @@ class direct_param_grads:
 
     def __exit__(self, *exc):
         DIRECT_PARAM_GRAD[0] = self.prev
+        _DIRECT_ZEROED[0] = self.prev_zeroed
         _DIRECT_WRITTEN.clear()
         if exc and exc[0] is not None:  # a failed backward: drop the deferred work, leave the accumulators clean
             for _, dwp, *_ in _PENDING_UNPACK.values():
@@ -295,7 +300,7 @@ def _direct_grad_target(param, like_shape):
     g = param.grad
     if g is None or g.dtype != torch.float32 or not g.is_contiguous() or tuple(g.shape) != tuple(like_shape) or g.requires_grad:
         return None, 0
-    first = id(param) not in _DIRECT_WRITTEN
+    first = id(param) not in _DIRECT_WRITTEN and not _DIRECT_ZEROED[0]
     _DIRECT_WRITTEN.add(id(param))
     return g, 0 if first else 1
 
@@ -769,8 +774,8 @@ class _BatchNormActFn(torch.autograd.Function):
         dy = _contig(dy)
         dtype = x.dtype
         st = stream_ptr(x)
-        dsums = torch.empty((2, Cn), dtype=torch.float32, device=x.device)
-        call("cnb_bn_act_bwd_reduce", ptr(x), ptr(dy), ptr(stats[2]), ptr(stats[3]), ptr(gamma), ptr(beta), P, L, Cn, ch_div, act,
+        dsums = _stats_slice(Cn, x.device)  # zero on entry (pre-cleared arena, or a fresh torch.zeros): no memset node per layer
+        call("cnb_bn_act_bwd_reduce_acc", ptr(x), ptr(dy), ptr(stats[2]), ptr(stats[3]), ptr(gamma), ptr(beta), P, L, Cn, ch_div, act,
              ptr(dsums), dtype_code(dtype), st)
         dx = torch.empty_like(x)
         call("cnb_bn_act_bwd_apply", ptr(x), ptr(dy), ptr(stats[2]), ptr(stats[3]), ptr(gamma), ptr(beta), ptr(dsums), count, ptr(dx),
@@ -966,14 +971,19 @@ def na2d(qkv: torch.Tensor, heads: int, ksize: int, dilation: int, scale: float,
 
 # ----------------------------------------------------------------------------------------------------------------
 class _ResizeBilinearFn(torch.autograd.Function):
+    """``bias`` (optional): the bias Parameter of the convolution that produced ``x``.  Its gradient is the per-channel sum of THIS
+    function's input gradient, which the backward kernel accumulates while it writes that gradient (``cnb_resize_bilinear_bwd_colsum``);
+    the convolution is then called with the bias detached, so it launches no column-sum pass of its own."""
+
     @staticmethod
-    def forward(ctx, x, Hout, Wout):
+    def forward(ctx, x, Hout, Wout, bias=None):
         check_device(x)
         x = _contig(x)
         B, Hin, Win, Cn = x.shape
         y = torch.empty((B, Hout, Wout, Cn), dtype=x.dtype, device=x.device)
         call("cnb_resize_bilinear_fwd", ptr(x), ptr(y), B, Hin, Win, Hout, Wout, Cn, dtype_code(x.dtype), stream_ptr(x))
         ctx.meta = (B, Hin, Win, Hout, Wout, Cn)
+        ctx.bias = bias
         return y
 
     @staticmethod
@@ -981,15 +991,28 @@ class _ResizeBilinearFn(torch.autograd.Function):
         B, Hin, Win, Hout, Wout, Cn = ctx.meta
         dy = _contig(dy)
         dx = torch.empty((B, Hin, Win, Cn), dtype=dy.dtype, device=dy.device)
-        call("cnb_resize_bilinear_bwd", ptr(dy), ptr(dx), B, Hin, Win, Hout, Wout, Cn, dtype_code(dy.dtype), stream_ptr(dy))
-        return dx, None, None
+        db = None
+        if ctx.bias is not None and ctx.needs_input_grad[3]:
+            target, acc_flag = _direct_grad_target(ctx.bias, (Cn,))
+            if target is None:
+                db = torch.empty((Cn,), dtype=torch.float32, device=dy.device)
+                target, acc_flag = db, 0
+            call("cnb_resize_bilinear_bwd_colsum", ptr(dy), ptr(dx), B, Hin, Win, Hout, Wout, Cn, ptr(target), acc_flag, dtype_code(dy.dtype),
+                 stream_ptr(dy))
+        else:
+            call("cnb_resize_bilinear_bwd", ptr(dy), ptr(dx), B, Hin, Win, Hout, Wout, Cn, dtype_code(dy.dtype), stream_ptr(dy))
+        return dx, None, None, db
 
 
-def resize_bilinear(x: torch.Tensor, size) -> torch.Tensor:
-    """``check_upsample``: bilinear, align_corners=True, only when the spatial size differs."""
+def resize_bilinear(x: torch.Tensor, size, producer_bias=None) -> torch.Tensor:
+    """``check_upsample``: bilinear, align_corners=True, only when the spatial size differs.  ``producer_bias``: see
+    ``_ResizeBilinearFn`` (the caller must have given the producing convolution ``producer_bias.detach()``)."""
     if tuple(x.shape[1:3]) == tuple(size):
+        assert producer_bias is None, "no resize: the producing convolution has to compute its own bias gradient"
         return x
-    return _ResizeBilinearFn.apply(x, int(size[0]), int(size[1]))
+    if producer_bias is not None and producer_bias.requires_grad and torch.is_grad_enabled():
+        return _ResizeBilinearFn.apply(x, int(size[0]), int(size[1]), producer_bias)
+    return _ResizeBilinearFn.apply(x, int(size[0]), int(size[1]), None)
 
 
 class _BroadcastPixelsFn(torch.autograd.Function):

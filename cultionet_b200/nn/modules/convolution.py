@@ -80,7 +80,13 @@ class ConvTranspose2d(nn.Module):
 
     def forward(self, x: torch.Tensor, size) -> torch.Tensor:
         m = self.up_conv
-        y = F.conv_transpose2d(x, m.weight, m.bias, ksize=m.kernel_size[0], stride=m.stride[0], pad=m.padding[0])
+        k, s, p = m.kernel_size[0], m.stride[0], m.padding[0]
+        out_hw = ((x.shape[1] - 1) * s - 2 * p + (k - 1) + 1, (x.shape[2] - 1) * s - 2 * p + (k - 1) + 1)
+        if m.bias is not None and out_hw != tuple(size) and m.bias.requires_grad and torch.is_grad_enabled():
+            # the resize backward writes the gradient the bias needs the column sums of: it accumulates them in the same pass
+            y = F.conv_transpose2d(x, m.weight, m.bias.detach(), ksize=k, stride=s, pad=p)
+            return F.resize_bilinear(y, size, producer_bias=m.bias)
+        y = F.conv_transpose2d(x, m.weight, m.bias, ksize=k, stride=s, pad=p)
         return F.resize_bilinear(y, size)
 
 

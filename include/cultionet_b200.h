@@ -188,6 +188,10 @@ int cnb_bn_train_fwd(const void* x, const float* sums, int64_t count, const floa
 /* backward pass 1: dsums[0..C) = sum dz, dsums[C..2C) = sum dz*xhat, dz = dy * act'(z) */
 int cnb_bn_act_bwd_reduce(const void* x, const void* dy, const float* save_mean, const float* save_rstd, const float* gamma,
                           const float* beta, int64_t P, int L, int C, int ch_div, int act, float* dsums, int dtype, void* stream);
+/* the same without the clearing memset: dsums must be ZERO on entry (a slice of a pre-cleared arena) -- one memset node less per
+ * BatchNorm in a captured step, and the kernel keeps its programmatic dependency on the kernel before it */
+int cnb_bn_act_bwd_reduce_acc(const void* x, const void* dy, const float* save_mean, const float* save_rstd, const float* gamma,
+                          const float* beta, int64_t P, int L, int C, int ch_div, int act, float* dsums, int dtype, void* stream);
 /* backward pass 2: dx = gamma*rstd*(dz - dsum/count - xhat*dsum_xhat/count); also writes dgamma = dsums[C..2C), dbeta = dsums[0..C)
  * when train_stats != 0; with train_stats == 0 (eval BN) dx = dz*gamma*rstd. */
 int cnb_bn_act_bwd_apply(const void* x, const void* dy, const float* save_mean, const float* save_rstd, const float* gamma,
@@ -234,6 +238,11 @@ int64_t cnb_na2d_bwd_workspace_floats(int B, int H, int W, int heads, int hd, in
  * ------------------------------------------------------------------------------------------------ */
 int cnb_resize_bilinear_fwd(const void* x, void* y, int B, int Hin, int Win, int Hout, int Wout, int C, int dtype, void* stream);
 int cnb_resize_bilinear_bwd(const void* dy, void* dx, int B, int Hin, int Win, int Hout, int Wout, int C, int dtype, void* stream);
+/* the same, also producing colsum[c] (+)= sum over pixels of dx[.., c] in the same pass: the bias gradient of the ConvTranspose2d whose
+ * output was resized (convolution.py:45-68 followed by nn/functional.py:72-81), so dx is not read again by cnb_bias_grad.  colsum may be
+ * NULL (plain backward); accumulate = 0 overwrites colsum. */
+int cnb_resize_bilinear_bwd_colsum(const void* dy, void* dx, int B, int Hin, int Win, int Hout, int Wout, int C, float* colsum, int accumulate,
+                                   int dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * PreTimeReduction first stage (models/nunet.py:31-39): Conv3d(C->C,(k,1,1), bias=False) over x[B,C,T,H,W] fp32.

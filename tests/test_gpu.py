@@ -22,9 +22,19 @@ def test_conv_ragged_channels(dev):
     cases.conv_case(dev, F32, 3, 25, 13, [70, 3, 1], 67, 3, 1, 1, 1)
 
 
+@pytest.mark.parametrize("direct", [False, True])
+def test_upconv_bias_gradient_from_resize_backward(dev, direct):
+    cases.upconv_case(dev, F32, 2, 13, 9, 8, direct)
+    cases.upconv_case(dev, BF16, 2, 32, 32, 256, direct)   # the persistent table kernel with the fused column sum
+    cases.upconv_case(dev, BF16, 1, 20, 12, 72, direct)    # 256 % (C / 8) != 0: separate column sum after the table kernel
+
+
 def test_conv_skinny_heads(dev):
     cases.conv_case(dev, F32, 2, 100, 100, [128], 3, 3, 1, 1, 1)
     cases.conv_case(dev, F32, 2, 100, 100, [1, 1, 1], 3, 3, 1, 1, 1)
+    for dtype in (F32, BF16):  # Psi-Net 9 -> 3 and 3 -> 3: fixed-shape forward / data-gradient / weight-gradient kernels
+        cases.conv_case(dev, dtype, 2, 100, 100, [9], 3, 3, 1, 1, 1)
+        cases.conv_case(dev, dtype, 3, 67, 41, [3], 3, 3, 1, 1, 1)
 
 
 def test_conv_tensor_core_shapes(dev):

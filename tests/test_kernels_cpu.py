@@ -24,6 +24,12 @@ def test_conv_transpose(dev, stride):
     cases.convT_case(dev, F32, 2, 7, 6, 5, 4, stride)
 
 
+@pytest.mark.parametrize("direct", [False, True])
+def test_upconv_bias_gradient_from_resize_backward(dev, direct):
+    cases.upconv_case(dev, F32, 2, 5, 6, 8, direct)
+    cases.upconv_case(dev, BF16, 1, 7, 5, 16, direct)
+
+
 def test_linear(dev):
     cases.linear_case(dev, F32, 2, 5, 7, 10, 21)
 
@@ -162,6 +168,10 @@ def test_tiny_channel_convs(dev):
     cases.conv_case(dev, BF16, 2, 9, 11, [1, 1, 1], 3, 3, 1, 1, 1)
     cases.conv_case(dev, F32, 1, 9, 11, [4], 2, 3, 2, 1, 1)
     cases.convT_case(dev, F32, 1, 5, 6, 3, 2, 2)
+    # the head shapes with compile-time channel counts (forward, data gradient and the register-blocked weight gradient)
+    for dtype in (F32, BF16):
+        cases.conv_case(dev, dtype, 2, 9, 11, [9], 3, 3, 1, 1, 1)
+        cases.conv_case(dev, dtype, 2, 9, 11, [3], 3, 3, 1, 1, 1)
 
 
 def test_packed_weight_cache_tracks_parameter_updates(dev):
