@@ -145,6 +145,8 @@ _PROTOS = {
     "cnb_adaptive_maxpool_bwd": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "cnb_silu_fwd": [_vp, _vp, _i64, _i, _vp],
     "cnb_silu_bwd": [_vp, _vp, _vp, _i64, _i, _vp],
+    "cnb_act_fwd": [_vp, _vp, _i64, _i, _i, _vp],
+    "cnb_act_bwd": [_vp, _vp, _vp, _i64, _i, _i, _vp],
     "cnb_sca_slices": [_i, _i, _i, _i],
     "cnb_sca_pool_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "cnb_sca_pool_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],

@@ -406,7 +406,7 @@ int cnb_bn_stats(const void* x, int64_t P, int L, int C, int ch_div, float* sums
         static bool cfg = false;
         const int smem = (st::smem_bytes<1, st::S1>()) + 2 * C * (int)sizeof(float);
         if (stream_smem(st::bn_stats_stream_kernel, (st::smem_bytes<1, st::S1>()) + 2 * 2048 * (int)sizeof(float), &cfg)) {
-            CNB_LAUNCH(st::bn_stats_stream_kernel, dim3(st::grid(total / 8)), dim3(st::THREADS), smem, (cudaStream_t)stream, (const bf16_t*)x,
+            CNB_LAUNCH(st::bn_stats_stream_kernel, dim3(st::grid_reduce(total / 8)), dim3(st::THREADS), smem, (cudaStream_t)stream, (const bf16_t*)x,
                        total / 8, L / 8, C, ch_div, sums);
             CNB_CHECK_LAUNCH("bn_stats_stream_kernel");
             return CNB_OK;
@@ -544,7 +544,7 @@ static int bn_act_bwd_reduce_impl(const void* x, const void* dy, const float* sa
         static bool cfg = false;
         const int smem = (st::smem_bytes<2, st::S2>()) + 2 * C * (int)sizeof(float);
         if (stream_smem(st::bn_act_bwd_reduce_stream_kernel, (st::smem_bytes<2, st::S2>()) + 2 * 2048 * (int)sizeof(float), &cfg)) {
-            CNB_LAUNCH(st::bn_act_bwd_reduce_stream_kernel, dim3(st::grid(total / 8)), dim3(st::THREADS), smem, (cudaStream_t)stream,
+            CNB_LAUNCH(st::bn_act_bwd_reduce_stream_kernel, dim3(st::grid_reduce(total / 8)), dim3(st::THREADS), smem, (cudaStream_t)stream,
                        (const bf16_t*)x, (const bf16_t*)dy, save_mean, save_rstd, gamma, beta, total / 8, L / 8, C, ch_div, act, dsums);
             CNB_CHECK_LAUNCH("bn_act_bwd_reduce_stream_kernel");
             return CNB_OK;
@@ -1365,20 +1365,30 @@ int cnb_adaptive_maxpool_bwd(const void* dy, const void* idx, void* dx, int B, i
     return CNB_OK;
 }
 
-int cnb_silu_fwd(const void* x, void* y, int64_t n, int dtype, void* stream) {
-    CNB_REQUIRE(x && y && n > 0, "silu_fwd: bad arguments");
-    CNB_DISPATCH_DTYPE(dtype, { CNB_LAUNCH((silu_fwd_kernel<T>), dim3(stream_grid(n)), dim3(256), 0, (cudaStream_t)stream, (const T*)x, (T*)y, (long)n); });
-    CNB_CHECK_LAUNCH("silu_fwd_kernel");
+static bool act_code_ok(int act) { return act >= CNB_ACT_NONE && act <= CNB_ACT_HARDSWISH; }
+
+int cnb_act_fwd(const void* x, void* y, int64_t n, int act, int dtype, void* stream) {
+    CNB_REQUIRE(x && y && n > 0 && act_code_ok(act), "act_fwd: bad arguments");
+    CNB_DISPATCH_DTYPE(dtype, {
+        CNB_LAUNCH((act_fwd_kernel<T>), dim3(stream_grid(n)), dim3(256), 0, (cudaStream_t)stream, (const T*)x, (T*)y, (long)n, act);
+    });
+    CNB_CHECK_LAUNCH("act_fwd_kernel");
+    return CNB_OK;
+}
+
+int cnb_silu_fwd(const void* x, void* y, int64_t n, int dtype, void* stream) { return cnb_act_fwd(x, y, n, CNB_ACT_SILU, dtype, stream); }
+
+int cnb_act_bwd(const void* x, const void* dy, void* dx, int64_t n, int act, int dtype, void* stream) {
+    CNB_REQUIRE(x && dy && dx && n > 0 && act_code_ok(act), "act_bwd: bad arguments");
+    CNB_DISPATCH_DTYPE(dtype, {
+        CNB_LAUNCH((act_bwd_kernel<T>), dim3(stream_grid(n)), dim3(256), 0, (cudaStream_t)stream, (const T*)x, (const T*)dy, (T*)dx, (long)n, act);
+    });
+    CNB_CHECK_LAUNCH("act_bwd_kernel");
     return CNB_OK;
 }
 
 int cnb_silu_bwd(const void* x, const void* dy, void* dx, int64_t n, int dtype, void* stream) {
-    CNB_REQUIRE(x && dy && dx && n > 0, "silu_bwd: bad arguments");
-    CNB_DISPATCH_DTYPE(dtype, {
-        CNB_LAUNCH((silu_bwd_kernel<T>), dim3(stream_grid(n)), dim3(256), 0, (cudaStream_t)stream, (const T*)x, (const T*)dy, (T*)dx, (long)n);
-    });
-    CNB_CHECK_LAUNCH("silu_bwd_kernel");
-    return CNB_OK;
+    return cnb_act_bwd(x, dy, dx, n, CNB_ACT_SILU, dtype, stream);
 }
 
 // column tiles and pixel slices of the (slice, sample, column tile) grids of the attention pooling / apply-backward kernels

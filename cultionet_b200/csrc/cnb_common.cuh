@@ -213,6 +213,65 @@ __device__ __forceinline__ float cnb_silu_grad_t(float x) {
     const float s = cnb_sigmoid_t<T>(x);
     return s * (1.0f + x * (1.0f - s));
 }
+// ---------------------------------------------------------------------------------------------
+// activation codes (cultionet_b200.h CNB_ACT_*): the reference builds `getattr(torch.nn, activation_type)()` (activations.py:5-24);
+// SiLU is its default and the code every fused kernel is tuned for -- the other codes take one out-of-line call per element.
+// ---------------------------------------------------------------------------------------------
+#ifdef CNB_EMU
+#define CNB_NOINLINE
+#else
+#define CNB_NOINLINE __noinline__
+#endif
+__device__ CNB_NOINLINE float cnb_act_other(float z, int act) {
+    switch (act) {
+        case CNB_ACT_RELU: return z > 0.f ? z : 0.f;
+        case CNB_ACT_LEAKY_RELU: return z > 0.f ? z : 0.01f * z;
+        case CNB_ACT_GELU: return 0.5f * z * (1.0f + erff(z * 0.70710678118654752f));
+        case CNB_ACT_MISH: {
+            const float sp = z > 20.f ? z : log1pf(expf(z));  // softplus, torch threshold 20
+            return z * tanhf(sp);
+        }
+        case CNB_ACT_ELU: return z > 0.f ? z : expm1f(z);
+        case CNB_ACT_TANH: return tanhf(z);
+        case CNB_ACT_SIGMOID: return 1.0f / (1.0f + expf(-z));
+        case CNB_ACT_HARDSWISH: return z <= -3.f ? 0.f : (z >= 3.f ? z : z * (z + 3.f) * (1.0f / 6.0f));
+        default: return z;
+    }
+}
+__device__ CNB_NOINLINE float cnb_act_grad_other(float z, int act) {
+    switch (act) {
+        case CNB_ACT_RELU: return z > 0.f ? 1.f : 0.f;
+        case CNB_ACT_LEAKY_RELU: return z > 0.f ? 1.f : 0.01f;
+        case CNB_ACT_GELU:
+            return 0.5f * (1.0f + erff(z * 0.70710678118654752f)) + z * 0.3989422804014327f * expf(-0.5f * z * z);
+        case CNB_ACT_MISH: {
+            const float sp = z > 20.f ? z : log1pf(expf(z));
+            const float t = tanhf(sp);
+            const float sg = 1.0f / (1.0f + expf(-z));  // d softplus / dz
+            return t + z * (1.0f - t * t) * sg;
+        }
+        case CNB_ACT_ELU: return z > 0.f ? 1.f : expf(z);
+        case CNB_ACT_TANH: {
+            const float t = tanhf(z);
+            return 1.0f - t * t;
+        }
+        case CNB_ACT_SIGMOID: {
+            const float sg = 1.0f / (1.0f + expf(-z));
+            return sg * (1.0f - sg);
+        }
+        case CNB_ACT_HARDSWISH: return z <= -3.f ? 0.f : (z >= 3.f ? 1.f : (2.0f * z + 3.0f) * (1.0f / 6.0f));  // torch: open interval
+        default: return 1.f;
+    }
+}
+// act(z) / act'(z) for an activation code; T selects the SiLU flavour (bf16 kernels: one-MUFU sigmoid)
+template <typename T>
+__device__ __forceinline__ float cnb_act_t(float z, int act) {
+    return act == CNB_ACT_SILU ? cnb_silu_t<T>(z) : (act == CNB_ACT_NONE ? z : cnb_act_other(z, act));
+}
+template <typename T>
+__device__ __forceinline__ float cnb_act_grad_t(float z, int act) {
+    return act == CNB_ACT_SILU ? cnb_silu_grad_t<T>(z) : (act == CNB_ACT_NONE ? 1.f : cnb_act_grad_other(z, act));
+}
 __device__ __forceinline__ float cnb_silu(float x) { return x * cnb_sigmoid(x); }
 // d/dx [x * sigmoid(x)]
 __device__ __forceinline__ float cnb_silu_grad(float x) {

@@ -524,7 +524,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                             if (p.bias) f += __ldg(p.bias + col0 + j);
                             if (p.ep_scale) {
                                 f = fmaf(f, __ldg(p.ep_scale + col0 + j), __ldg(p.ep_shift + col0 + j));
-                                if (p.ep_act) f = cnb_silu_t<bf16_t>(f);
+                                f = cnb_act_t<bf16_t>(f, p.ep_act);
                             }
                             ochunk[j] = __float2bfloat16(f);
                         }
@@ -542,7 +542,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                             float f1 = fmaf(has_taps ? __uint_as_float(v[4 * q + 1]) : 0.f, sc.y, sh.y);
                             float f2 = fmaf(has_taps ? __uint_as_float(v[4 * q + 2]) : 0.f, sc.z, sh.z);
                             float f3 = fmaf(has_taps ? __uint_as_float(v[4 * q + 3]) : 0.f, sc.w, sh.w);
-                            if (p.ep_act) f0 = cnb_silu_t<bf16_t>(f0), f1 = cnb_silu_t<bf16_t>(f1), f2 = cnb_silu_t<bf16_t>(f2), f3 = cnb_silu_t<bf16_t>(f3);
+                            if (p.ep_act)
+                                f0 = cnb_act_t<bf16_t>(f0, p.ep_act), f1 = cnb_act_t<bf16_t>(f1, p.ep_act), f2 = cnb_act_t<bf16_t>(f2, p.ep_act),
+                                f3 = cnb_act_t<bf16_t>(f3, p.ep_act);
                             packed[2 * q] = cnb_pack_bf16x2(f0, f1);
                             packed[2 * q + 1] = cnb_pack_bf16x2(f2, f3);
                         }
@@ -552,7 +554,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                             float f0 = fmaf(has_taps ? __uint_as_float(v[2 * j]) : 0.f, __ldg(p.ep_scale + col0 + 2 * j), __ldg(p.ep_shift + col0 + 2 * j));
                             float f1 = fmaf(has_taps ? __uint_as_float(v[2 * j + 1]) : 0.f, __ldg(p.ep_scale + col0 + 2 * j + 1),
                                             __ldg(p.ep_shift + col0 + 2 * j + 1));
-                            if (p.ep_act) f0 = cnb_silu_t<bf16_t>(f0), f1 = cnb_silu_t<bf16_t>(f1);
+                            if (p.ep_act) f0 = cnb_act_t<bf16_t>(f0, p.ep_act), f1 = cnb_act_t<bf16_t>(f1, p.ep_act);
                             packed[j] = cnb_pack_bf16x2(f0, f1);
                         }
                     }

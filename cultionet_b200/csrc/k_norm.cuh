@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const T* __restrict__ x
             continue;
         }
         float z = fmaf(cnb_ld(x + i), scale[ch], shift[ch]);
-        if (act) z = cnb_silu(z);
+        z = cnb_act_t<float>(z, act);
         if (residual) z += cnb_ld(residual + i);
         cnb_st(y + i, z);
     }
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(const T* __restr
         for (long i = gid; i < total; i += stride) {
             const float xh = (cnb_ld(x + i) - mu) * rs;
             float dz = cnb_ld(dy + i);
-            if (act) dz *= cnb_silu_grad(fmaf(xh, g, b));
+            if (act) dz *= cnb_act_grad_t<float>(fmaf(xh, g, b), act);
             s += dz;
             sx = fmaf(dz, xh, sx);
         }
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(const T* __restri
         const float g = gamma ? gamma[ch] : 1.f, b = beta ? beta[ch] : 0.f;
         const float xh = (cnb_ld(x + i) - mean[ch]) * rs;
         float dz = cnb_ld(dy + i);
-        if (act) dz *= cnb_silu_grad(fmaf(xh, g, b));
+        if (act) dz *= cnb_act_grad_t<float>(fmaf(xh, g, b), act);
         float r;
         if (train_stats)
             r = g * rs * (dz - dsums[ch] * inv_count - xh * dsums[C + ch] * inv_count);

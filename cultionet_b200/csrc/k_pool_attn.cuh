@@ -108,19 +108,19 @@ __global__ void __launch_bounds__(256) adaptive_maxpool_bwd_kernel(const T* __re
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// stand-alone SiLU (fp32 or bf16)
+// stand-alone activation (fp32 or bf16); act = a CNB_ACT_* code
 // ---------------------------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(256) silu_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long n) {
+__global__ void __launch_bounds__(256) act_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long n, int act) {
     CNB_PDL_SYNC();
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
-        cnb_st(y + i, cnb_silu_t<T>(cnb_ld(x + i)));
+        cnb_st(y + i, cnb_act_t<T>(cnb_ld(x + i), act));
 }
 template <typename T>
-__global__ void __launch_bounds__(256) silu_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx, long n) {
+__global__ void __launch_bounds__(256) act_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx, long n, int act) {
     CNB_PDL_SYNC();
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
-        cnb_st(dx + i, cnb_ld(dy + i) * cnb_silu_grad_t<T>(cnb_ld(x + i)));
+        cnb_st(dx + i, cnb_ld(dy + i) * cnb_act_grad_t<T>(cnb_ld(x + i), act));
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(THREADS, 2) bn_act_fwd_stream_kernel(const bf1
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     float z = fmaf(v[j], sc[j], sf[j]);
-                    z = act ? cnb_silu_t<bf16_t>(z) : z;
+                    z = cnb_act_t<bf16_t>(z, act);
                     v[j] = RES ? z + w[j] : z;
                 }
                 *reinterpret_cast<uint4*>(y + (v0 + (long)u * THREADS) * 8) = s_pack(v);
@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(THREADS, 2) bn_train_fwd_stream_kernel(const b
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     float z = fmaf(v[j], sc[j], sf[j]);
-                    z = act ? cnb_silu_t<bf16_t>(z) : z;
+                    z = cnb_act_t<bf16_t>(z, act);
                     v[j] = RES ? z + w[j] : z;
                 }
                 *reinterpret_cast<uint4*>(y + (v0 + (long)u * THREADS) * 8) = s_pack(v);
@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(THREADS, 2) bn_act_bwd_reduce_stream_kernel(co
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     float dz = dv[j];
-                    if (act) dz *= cnb_silu_grad_t<bf16_t>(fmaf(xv[j], A[j], Bc[j]));
+                    if (act) dz *= cnb_act_grad_t<bf16_t>(fmaf(xv[j], A[j], Bc[j]), act);
                     s[j] += dz;
                     sx[j] = fmaf(dz, xv[j] - mu[j], sx[j]);
                 }
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(THREADS, 2) bn_act_bwd_apply_stream_kernel(con
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     float dz = dv[j];
-                    if (act) dz *= cnb_silu_grad_t<bf16_t>(fmaf(xv[j], A[j], Bc[j]));
+                    if (act) dz *= cnb_act_grad_t<bf16_t>(fmaf(xv[j], A[j], Bc[j]), act);
                     xv[j] = fmaf(A[j], dz, fmaf(-xv[j], K1[j], Q[j]));
                 }
                 *reinterpret_cast<uint4*>(dx + (v0 + (long)u * THREADS) * 8) = s_pack(xv);
@@ -396,6 +396,16 @@ static inline int grid(long total_v) {
     const long ntiles = (total_v + TILE_V - 1) / TILE_V;
     const long cap = 2L * CNB_NUM_SMS;
     return (int)(ntiles < cap ? ntiles : cap);
+}
+// the reducing kernels end with 2C shared + 2C global atomics per CTA: on a small tensor (level c: 3.5 tiles per CTA at the grid above)
+// that flush was most of the launch (28.6 us for 33 MB against 20.8 us for the apply kernel that moves half as much again), so they
+// run at least 8 tiles per CTA
+static inline int grid_reduce(long total_v) {
+    const long ntiles = (total_v + TILE_V - 1) / TILE_V;
+    const long cap = 2L * CNB_NUM_SMS;
+    long g = (ntiles + 7) / 8;
+    if (g > cap) g = cap;
+    return (int)(g < 1 ? 1 : g);
 }
 
 }  // namespace st

@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(256) bn_act_fwd_vec_kernel(const T* __restrict
 #pragma unroll
                 for (int j = 0; j < V; ++j) {
                     float z = fmaf(v[u][j], sc[j], sf[j]);
-                    z = act ? cnb_silu_t<T>(z) : z;
+                    z = cnb_act_t<T>(z, act);
                     v[u][j] = residual ? z + r[u][j] : z;
                 }
                 cnb_stv(y + (i + u * stride_v) * V, v[u]);
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(256, 3) bn_act_bwd_reduce_vec_kernel(const T* 
 #pragma unroll
                     for (int j = 0; j < V; ++j) {
                         float dz = dv[u][j];
-                        if (act) dz *= cnb_silu_grad_t<T>(fmaf(xv[u][j], A[j], Bc[j]));
+                        if (act) dz *= cnb_act_grad_t<T>(fmaf(xv[u][j], A[j], Bc[j]), act);
                         s[j] += dz;
                         sx[j] = fmaf(dz, xv[u][j] - mu[j], sx[j]);
                     }
@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(256, 3) bn_act_bwd_apply_vec_kernel(const T* _
 #pragma unroll
                 for (int j = 0; j < V; ++j) {
                     float dz = dv[u][j];
-                    if (act) dz *= cnb_silu_grad_t<T>(fmaf(xv[u][j], A[j], Bc[j]));
+                    if (act) dz *= cnb_act_grad_t<T>(fmaf(xv[u][j], A[j], Bc[j]), act);
                     xv[u][j] = fmaf(A[j], dz, fmaf(-xv[u][j], K1[j], Q[j]));
                 }
                 cnb_stv(dx + (i + u * stride_v) * V, xv[u]);

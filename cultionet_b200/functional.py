@@ -293,14 +293,17 @@ class direct_param_grads:
         return False
 
 
-def _direct_grad_target(param, like_shape):
-    """(gradient buffer, accumulate flag) when the kernel may write ``param.grad`` itself, else (None, 0)."""
+def _direct_grad_target(param, like_shape, full_overwrite: bool = False):
+    """(gradient buffer, accumulate flag) when the kernel may write ``param.grad`` itself, else (None, 0).  ``full_overwrite``: the
+    kernel stores every element (the weight-gradient unpack), so a first contribution overwrites even when the buffer is known to be
+    zero -- no read of the buffer; kernels that ATOMICALLY add (bias / column sums) accumulate into known-zero buffers instead of
+    clearing them first."""
     if not DIRECT_PARAM_GRAD[0] or not isinstance(param, torch.nn.Parameter):
         return None, 0
     g = param.grad
     if g is None or g.dtype != torch.float32 or not g.is_contiguous() or tuple(g.shape) != tuple(like_shape) or g.requires_grad:
         return None, 0
-    first = id(param) not in _DIRECT_WRITTEN and not _DIRECT_ZEROED[0]
+    first = id(param) not in _DIRECT_WRITTEN and (full_overwrite or not _DIRECT_ZEROED[0])
     _DIRECT_WRITTEN.add(id(param))
     return g, 0 if first else 1
 
@@ -591,7 +594,7 @@ class _Conv2dFn(torch.autograd.Function):
 
         dw = None
         if need_w:
-            target, acc_flag = _direct_grad_target(ctx.params[0], weight.shape)
+            target, acc_flag = _direct_grad_target(ctx.params[0], weight.shape, full_overwrite=True)
             derived = None
             if target is not None:
                 dwp = _wgrad_accumulator(ctx.params[0], taps, N, Ctot, dev)  # zero on entry: cleared by the previous unpack
@@ -1299,14 +1302,28 @@ def adaptive_max_pool2d(x: torch.Tensor, size) -> torch.Tensor:
     return _AdaptiveMaxPoolFn.apply(x, int(size[0]), int(size[1]))
 
 
-class _SiLUFn(torch.autograd.Function):
+# Activation codes of the C ABI (include/cultionet_b200.h CNB_ACT_*).  The reference builds ``getattr(torch.nn, activation_type)()``
+# (nn/modules/activations.py:5-24) with default arguments: these are the torch.nn classes whose default form the kernels implement.
+ACT_CODES = {"Identity": 0, "SiLU": 1, "ReLU": 2, "LeakyReLU": 3, "GELU": 4, "Mish": 5, "ELU": 6, "Tanh": 7, "Sigmoid": 8, "Hardswish": 9}
+
+
+def act_code(activation_type) -> int:
+    """``activation_type`` (a torch.nn class name, as the reference's ``SetActivation`` takes it) -> CNB_ACT_* code."""
+    name = str(getattr(activation_type, "value", activation_type))
+    if name not in ACT_CODES:
+        raise NotImplementedError(f"cultionet_b200: activation_type={name!r} is not built (available: {', '.join(ACT_CODES)})")
+    return ACT_CODES[name]
+
+
+class _ActFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x):
+    def forward(ctx, x, act):
         check_device(x)
         x = _contig(x)
         y = torch.empty_like(x)
-        call("cnb_silu_fwd", ptr(x), ptr(y), x.numel(), dtype_code(x.dtype), stream_ptr(x))
+        call("cnb_act_fwd", ptr(x), ptr(y), x.numel(), int(act), dtype_code(x.dtype), stream_ptr(x))
         ctx.save_for_backward(x)
+        ctx.act = int(act)
         return y
 
     @staticmethod
@@ -1314,12 +1331,17 @@ class _SiLUFn(torch.autograd.Function):
         (x,) = ctx.saved_tensors
         dy = _contig(dy)
         dx = torch.empty_like(x)
-        call("cnb_silu_bwd", ptr(x), ptr(dy), ptr(dx), x.numel(), dtype_code(x.dtype), stream_ptr(x))
-        return dx
+        call("cnb_act_bwd", ptr(x), ptr(dy), ptr(dx), x.numel(), ctx.act, dtype_code(x.dtype), stream_ptr(x))
+        return dx, None
+
+
+def activation(x: torch.Tensor, act: int = 1) -> torch.Tensor:
+    """Stand-alone activation by CNB_ACT_* code (``act_code(name)``)."""
+    return x if int(act) == 0 else _ActFn.apply(x, int(act))
 
 
 def silu(x: torch.Tensor) -> torch.Tensor:
-    return _SiLUFn.apply(x)
+    return _ActFn.apply(x, 1)
 
 
 class _ScaPoolFn(torch.autograd.Function):

@@ -25,18 +25,19 @@ class Conv3d(nn.Module):
 
     def __init__(self, in_channels: int, in_time: int, out_channels: int, kernel_size: int, activation_type: str):
         super().__init__()
-        if activation_type != "SiLU":
-            raise NotImplementedError("cultionet_b200 fuses SiLU into its normalisation kernels")
+        from ..nn.modules.convolution import _act_module
+
+        self.act = F.act_code(activation_type)
         remaining_time = in_time - kernel_size + 1
         self.remaining_time = remaining_time
         self.seq = nn.Sequential(
             nn.Conv3d(in_channels, in_channels, kernel_size=(kernel_size, 1, 1), padding=0, bias=False),
             nn.BatchNorm3d(in_channels),
-            nn.SiLU(),
+            _act_module(activation_type),
             nn.Conv3d(in_channels, out_channels, kernel_size=(remaining_time, 1, 1), padding=0, bias=False),
             nn.Identity(),  # einops Rearrange('b c 1 h w -> b c h w') in the reference
             nn.BatchNorm2d(out_channels),
-            nn.SiLU(),
+            _act_module(activation_type),
         )
 
     def forward(self, x: torch.Tensor, dtype: torch.dtype, xp: T.Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -46,10 +47,10 @@ class Conv3d(nn.Module):
             u = F.pretime_conv_gemm(xp, conv1.weight, x.shape[2])
         else:
             u = F.pretime_conv(x, conv1.weight, dtype)
-        a = batchnorm_act(bn1, u, act=True, ch_div=self.remaining_time)
+        a = batchnorm_act(bn1, u, act=self.act, ch_div=self.remaining_time)
         w2 = F.tag_derived(conv2.weight.view(conv2.weight.shape[0], -1), conv2.weight, "flat")
         v = F.linear(a, w2, None, in_features=w2.shape[1])
-        return batchnorm_act(bn2, v, act=True)
+        return batchnorm_act(bn2, v, act=self.act)
 
 
 class PreTimeReduction(nn.Module):

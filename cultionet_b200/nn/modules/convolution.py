@@ -23,11 +23,15 @@ def _as_sources(x: Sources) -> T.List[torch.Tensor]:
     return [x] if isinstance(x, torch.Tensor) else list(x)
 
 
-def _require_silu(activation_type: str) -> None:
-    if activation_type != "SiLU":
-        raise NotImplementedError(
-            f"cultionet_b200 fuses SiLU into its normalisation kernels; activation_type={activation_type!r} is not built"
-        )
+def _act_module(activation_type: str) -> nn.Module:
+    """The parameter-free activation module the reference's ``SetActivation`` builds (``activations.py:18-21``); it only keeps the
+    ``nn.Sequential`` indices (and with them the state_dict keys) of the reference -- the arithmetic runs inside the fused kernels."""
+    F.act_code(activation_type)  # raises for a name the kernels do not implement
+    cls = getattr(nn, str(getattr(activation_type, "value", activation_type)))
+    try:
+        return cls(inplace=False)
+    except TypeError:
+        return cls()
 
 
 # `num_batches_tracked += 1` is one tiny kernel per BatchNorm layer (52 per TowerUNet step).  A training loop may collect the counters
@@ -58,9 +62,10 @@ def bump_batch_counter(bn: nn.modules.batchnorm._BatchNorm) -> None:
             bn.num_batches_tracked.add_(1)
 
 
-def batchnorm_act(bn: nn.modules.batchnorm._BatchNorm, x: torch.Tensor, act: bool, ch_div: int = 1,
+def batchnorm_act(bn: nn.modules.batchnorm._BatchNorm, x: torch.Tensor, act: T.Union[bool, int], ch_div: int = 1,
                   sums: T.Optional[torch.Tensor] = None, residual: T.Optional[torch.Tensor] = None) -> torch.Tensor:
-    """BatchNorm2d/3d (+SiLU) (+ residual) with the module's parameters; batch statistics iff the module is in training mode."""
+    """BatchNorm2d/3d (+ activation: True = SiLU, or a ``F.act_code``) (+ residual) with the module's parameters; batch statistics iff
+    the module is in training mode."""
     training = bn.training
     if training:
         bump_batch_counter(bn)
@@ -97,12 +102,12 @@ class ConvBlock2d(nn.Module):
     def __init__(self, in_channels: int, out_channels: int, kernel_size: int, padding: int = 0, dilation: int = 1,
                  stride: int = 1, add_activation: bool = True, activation_type: str = "SiLU", batchnorm_first: bool = False):
         super().__init__()
-        _require_silu(activation_type)
+        self.act = F.act_code(activation_type)
         self.batchnorm_first = batchnorm_first
         if batchnorm_first:
             layers = [
                 nn.BatchNorm2d(in_channels),
-                nn.SiLU(),
+                _act_module(activation_type),
                 nn.Conv2d(in_channels, out_channels, kernel_size=kernel_size, padding=padding, dilation=dilation, stride=stride),
             ]
         else:
@@ -111,7 +116,7 @@ class ConvBlock2d(nn.Module):
                 nn.BatchNorm2d(out_channels),
             ]
             if add_activation:
-                layers.append(nn.SiLU())
+                layers.append(_act_module(activation_type))
         self.add_activation = add_activation
         self.seq = nn.Sequential(*layers)
 
@@ -124,7 +129,8 @@ class ConvBlock2d(nn.Module):
         if not bn.training and not torch.is_grad_enabled() and residual is None:
             # inference: BatchNorm (running statistics) and SiLU ride in the convolution epilogue -- one launch, one write
             y = F.conv2d_bn_act_eval(_as_sources(x), conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps,
-                                     self.add_activation, ksize=conv.kernel_size[0], stride=conv.stride[0], pad=conv.padding[0],
+                                     self.act if self.add_activation else 0, ksize=conv.kernel_size[0], stride=conv.stride[0],
+                                     pad=conv.padding[0],
                                      dil=conv.dilation[0])
             if y is not None:
                 return y
@@ -134,13 +140,13 @@ class ConvBlock2d(nn.Module):
         sums = None
         if bn.training:
             y, sums = y
-        return batchnorm_act(bn, y, act=self.add_activation, sums=sums, residual=residual)
+        return batchnorm_act(bn, y, act=self.act if self.add_activation else 0, sums=sums, residual=residual)
 
     def _forward_bn_first(self, sources: T.List[torch.Tensor]) -> torch.Tensor:
         """BatchNorm over the (virtual) channel concatenation = BatchNorm of every source with its slice of the parameters."""
         bn, conv = self.seq[0], self.seq[2]
         if len(sources) == 1:
-            normed = [batchnorm_act(bn, sources[0], act=True)]
+            normed = [batchnorm_act(bn, sources[0], act=self.act)]
         else:
             if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
                 if _PENDING_COUNTERS is not None:
@@ -151,7 +157,7 @@ class ConvBlock2d(nn.Module):
             for s in sources:
                 c1 = c0 + s.shape[-1]
                 normed.append(F.batchnorm_act(s, bn.weight[c0:c1], bn.bias[c0:c1], bn.running_mean[c0:c1], bn.running_var[c0:c1],
-                                              bn.training, momentum=bn.momentum if bn.momentum is not None else 0.1, eps=bn.eps, act=True))
+                                              bn.training, momentum=bn.momentum if bn.momentum is not None else 0.1, eps=bn.eps, act=self.act))
                 c0 = c1
         return F.conv2d(normed, conv.weight, conv.bias, ksize=conv.kernel_size[0], stride=conv.stride[0], pad=conv.padding[0],
                         dil=conv.dilation[0])
@@ -195,18 +201,17 @@ class ChannelAttention(nn.Module):
 
     def __init__(self, in_channels: int, activation_type: str):
         super().__init__()
-        _require_silu(activation_type)
+        self.act = F.act_code(activation_type)
 
         def mlp():
-            return nn.Sequential(nn.Conv2d(in_channels, in_channels // 2, kernel_size=1, padding=0, bias=False), nn.SiLU(),
+            return nn.Sequential(nn.Conv2d(in_channels, in_channels // 2, kernel_size=1, padding=0, bias=False), _act_module(activation_type),
                                  nn.Conv2d(in_channels // 2, in_channels, kernel_size=1, padding=0, bias=False))
 
         self.fc1 = mlp()
         self.fc2 = mlp()
 
-    @staticmethod
-    def _mlp(seq: nn.Sequential, v: torch.Tensor) -> torch.Tensor:
-        h = F.silu(F.conv2d([v], seq[0].weight, None, ksize=1, stride=1, pad=0))
+    def _mlp(self, seq: nn.Sequential, v: torch.Tensor) -> torch.Tensor:
+        h = F.activation(F.conv2d([v], seq[0].weight, None, ksize=1, stride=1, pad=0), self.act)
         return F.conv2d([h], seq[2].weight, None, ksize=1, stride=1, pad=0)
 
     def logits(self, ch_avg: torch.Tensor, ch_max: torch.Tensor) -> torch.Tensor:

@@ -153,7 +153,7 @@ class TowerUNetFinal(nn.Module):
             for bn in bns:
                 bump_batch_counter(bn)
         h = F.batchnorm_act(h, gamma, beta, rm, rv, training, momentum=bns[0].momentum if bns[0].momentum is not None else 0.1,
-                            eps=bns[0].eps, act=True, sums=sums)
+                            eps=bns[0].eps, act=blocks[0].act, sums=sums)
         # 3 x (3 -> 1) as one block-diagonal 9 -> 3 convolution: stream i's [1,3,3,3] filter sits at input channels 3i..3i+2 of output i
         w2 = F.stack_params([s.conv[1].weight for s in streams], [0, 108, 216], 243)
         w2 = F.tag_derived(w2.view(3, 9, 3, 3), w2)

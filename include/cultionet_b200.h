@@ -75,7 +75,7 @@ typedef struct {
     int32_t out_seg_stride[CNB_MAX_SRC];
     /* Fused epilogue for inference (ConvBlock2d in eval mode, convolution.py:88-116: Conv2d -> BatchNorm2d(running statistics) -> [SiLU]):
      *   y[n] = act(acc[n] * ep_scale[n] + ep_shift[n]),  ep_scale = gamma * rsqrt(var + eps), ep_shift = beta - mean * ep_scale
-     * (fp32 [N] each, as cnb_bn_finalize produces them), ep_act: 0 = identity, 1 = SiLU.  ep_scale == NULL: off.  The normalised
+     * (fp32 [N] each, as cnb_bn_finalize produces them), ep_act: a CNB_ACT_* code.  ep_scale == NULL: off.  The normalised
      * activation is written once instead of conv out -> read -> write.  Only the tcgen05 kernel implements it (bias must be NULL,
      * single output); the other kernels return CNB_ERR_UNSUPPORTED. */
     const float* ep_scale;
@@ -177,7 +177,19 @@ int cnb_bn_stats(const void* x, int64_t P, int L, int C, int ch_div, float* sums
 int cnb_bn_finalize(const float* sums, int64_t count, int C, const float* gamma, const float* beta, float eps, float momentum,
                     float* running_mean, float* running_var, float* save_mean, float* save_rstd, float* scale, float* shift,
                     void* stream);
-/* y = act(x*scale[ch] + shift[ch]) (+ residual) ; act: 0 none, 1 SiLU */
+/* Activation codes of every `act` / `ep_act` argument (reference nn/modules/activations.py:5-24 builds getattr(torch.nn, name)();
+ * SiLU is the reference's default): */
+#define CNB_ACT_NONE 0
+#define CNB_ACT_SILU 1
+#define CNB_ACT_RELU 2
+#define CNB_ACT_LEAKY_RELU 3 /* negative_slope 0.01 */
+#define CNB_ACT_GELU 4       /* erf form (approximate='none') */
+#define CNB_ACT_MISH 5
+#define CNB_ACT_ELU 6        /* alpha 1 */
+#define CNB_ACT_TANH 7
+#define CNB_ACT_SIGMOID 8
+#define CNB_ACT_HARDSWISH 9
+/* y = act(x*scale[ch] + shift[ch]) (+ residual) ; act: a CNB_ACT_* code */
 int cnb_bn_act_fwd(const void* x, const float* scale, const float* shift, const void* residual, void* y,
                    int64_t P, int L, int C, int ch_div, int act, int dtype, void* stream);
 /* training-mode cnb_bn_finalize + cnb_bn_act_fwd as one call (one launch on the bulk-copy path: the apply kernel derives scale/shift
@@ -345,6 +357,9 @@ int cnb_adaptive_maxpool_bwd(const void* dy, const void* idx, void* dx, int B, i
 /* SetActivation("SiLU") as a stand-alone operator (the channel MLP of ChannelAttention, nn/modules/attention.py:19-52) */
 int cnb_silu_fwd(const void* x, void* y, int64_t n, int dtype, void* stream);
 int cnb_silu_bwd(const void* x, const void* dy, void* dx, int64_t n, int dtype, void* stream);
+/* y = act(x), dx = dy * act'(x) for any CNB_ACT_* code (SetActivation, nn/modules/activations.py:5-24) */
+int cnb_act_fwd(const void* x, void* y, int64_t n, int act, int dtype, void* stream);
+int cnb_act_bwd(const void* x, const void* dy, void* dx, int64_t n, int act, int dtype, void* stream);
 
 /* SpatialChannelAttention, pooling side (nn/modules/attention.py:54-63, :78-86) over x[B][HW][C]:
  *   sp[B*HW][2]  = per-pixel (mean, max) over channels; ties[B*HW] = number of channels equal to that max (torch.amax shares the

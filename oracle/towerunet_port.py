@@ -149,8 +149,10 @@ def synth_state_dict(spec: Sequence[Tuple[str, tuple]], seed: int = 0) -> Dict[s
 # forward
 # ---------------------------------------------------------------------------------------------------------------------
 class _Ctx:
-    def __init__(self, sd: Dict[str, torch.Tensor], training: bool, bn_out: Optional[dict]):
+    def __init__(self, sd: Dict[str, torch.Tensor], training: bool, bn_out: Optional[dict], activation_type: str = "SiLU"):
         self.sd, self.training, self.bn_out = sd, training, bn_out
+        # SetActivation (nn/modules/activations.py:15-24): getattr(torch.nn, activation_type)() with default arguments
+        self.act = getattr(torch.nn, activation_type)()
 
     def bn(self, x, p):  # nn.BatchNorm2d/3d: batch statistics in training, running statistics in eval
         sd = self.sd
@@ -186,7 +188,7 @@ def _conv_block_fwd(c: _Ctx, x, p, k, stride=1, pad=None, dil=1, act=True):  # c
     pad = (0 if k == 1 else k // 2) if pad is None else pad
     y = _conv2d(x, c.sd[p + ".seq.0.weight"], None, stride=stride, padding=pad, dilation=dil)
     y = c.bn(y, p + ".seq.1")
-    return F.silu(y) if act else y
+    return c.act(y) if act else y
 
 
 def _natten_block(c: _Ctx, skip, p, heads, k, d):  # convolution.py:338-353 + natten 0.17.1 module
@@ -234,9 +236,9 @@ def _pre_unet(c: _Ctx, x):  # models/nunet.py:18-105
     for name in ("conv3", "conv5"):
         p = f"pre_unet.{name}.seq"
         h = F.conv3d(x, sd[p + ".0.weight"])
-        h = F.silu(c.bn(h, p + ".1"))
+        h = c.act(c.bn(h, p + ".1"))
         h = F.conv3d(h, sd[p + ".3.weight"]).squeeze(2)
-        outs.append(F.silu(c.bn(h, p + ".5")))
+        outs.append(c.act(c.bn(h, p + ".5")))
     s = (outs[0] + outs[1]).permute(0, 2, 3, 1)
     s = F.layer_norm(s, (s.shape[-1],), sd["pre_unet.layer_norm.1.weight"], sd["pre_unet.layer_norm.1.bias"], 1e-5)
     return s.permute(0, 3, 1, 2)
@@ -254,11 +256,11 @@ def _final(c: _Ctx, x, p, size=None, stride=2):  # unet_parts.py:281-309
 
 
 def towerunet_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, dilations: Sequence[int] = (1, 2), training: bool = True,
-                      bn_out: Optional[dict] = None, natten_params: Optional[dict] = None, taps: Optional[dict] = None
-                      ) -> Dict[str, torch.Tensor]:
+                      bn_out: Optional[dict] = None, natten_params: Optional[dict] = None, taps: Optional[dict] = None,
+                      activation_type: str = "SiLU") -> Dict[str, torch.Tensor]:
     """TowerUNet.forward (models/nunet.py:213-265).  ``bn_out`` (optional dict) receives the updated running statistics;
     ``taps`` (optional dict) receives named intermediate activations in NCHW."""
-    c = _Ctx(sd, training, bn_out)
+    c = _Ctx(sd, training, bn_out, activation_type)
     nat = natten_params or NATTEN_PARAMS
     dil = list(dilations)
     e0 = _pre_unet(c, x)

@@ -136,6 +136,36 @@ def batchnorm_case(dev, dtype, B, H, W, C, training=True, act=True, with_res=Tru
         _check(f"bn grad {i}", a, c, tol * (3 if dtype == torch.bfloat16 else 5))
 
 
+def activation_case(dev, dtype, name, seed=0):
+    """Every activation code: stand-alone kernel and the fused BatchNorm + activation (+ residual) kernels, forward and backward, against
+    ``getattr(torch.nn, name)()`` -- what the reference's SetActivation builds (nn/modules/activations.py:15-24)."""
+    torch.manual_seed(seed)
+    code = F.act_code(name)
+    ref = getattr(torch.nn, name)()
+    tol = _tol(dtype)
+    x = _mk((2, 7, 9, 16), dev, dtype, scale=2.5)
+    y = F.activation(x, code)
+    xr = _f(x)
+    yr = ref(xr)
+    _check(f"{name} fwd", y, yr, tol)
+    g = torch.randn_like(yr)
+    _check(f"{name} grad", torch.autograd.grad(y, x, g.to(dtype))[0], torch.autograd.grad(yr, xr, g.to(dtype).float())[0], tol * 2)
+    # fused with BatchNorm (training statistics) and a residual
+    x = _mk((2, 9, 11, 16), dev, dtype, scale=2.0, shift=0.4)
+    gam = (torch.rand(16, device=dev) + 0.5).requires_grad_(True)
+    bet = torch.randn(16, device=dev, requires_grad=True)
+    res = _mk((2, 9, 11, 16), dev, dtype)
+    rm, rv = torch.zeros(16, device=dev), torch.ones(16, device=dev)
+    y = F.batchnorm_act(x, gam, bet, rm, rv, True, 0.1, 1e-5, code, 1, res)
+    xr, rr = _f(x), _f(res)
+    yr = ref(TF.batch_norm(xr.permute(0, 3, 1, 2), None, None, gam, bet, True, 0.1, 1e-5).permute(0, 2, 3, 1)) + rr
+    _check(f"bn+{name} fwd", y, yr, tol)
+    g = torch.randn_like(yr)
+    for i, (a, c) in enumerate(zip(torch.autograd.grad(y, [x, gam, bet, res], g.to(dtype)),
+                                   torch.autograd.grad(yr, [xr, gam, bet, rr], g.to(dtype).float()))):
+        _check(f"bn+{name} grad {i}", a, c, tol * (4 if dtype == torch.bfloat16 else 5))
+
+
 def batchnorm3d_case(dev, dtype, B, H, W, C, Tp, seed=0):
     torch.manual_seed(seed)
     u = _mk((B, H, W, C * Tp), dev, dtype)
@@ -386,7 +416,8 @@ def model_vs_port(dev, cfg, dtype=torch.float32, training=True, seed=3, check_gr
     sdo = {k: v.to(odev) for k, v in sd.items()}
     sdo = {k: (v.requires_grad_(True) if v.is_floating_point() and "running" not in k else v) for k, v in sdo.items()}
     with torch.set_grad_enabled(bool(training and check_grads)):  # a forward-only comparison keeps no autograd graph (full-size cases)
-        want = port.towerunet_forward(sdo, x.to(odev), cfg["dilations"], training=training, natten_params=cfg.get("natten"))
+        want = port.towerunet_forward(sdo, x.to(odev), cfg["dilations"], training=training, natten_params=cfg.get("natten"),
+                                      activation_type=cfg.get("activation_type", "SiLU"))
         out = model(x.to(dev))
     tol = TOL_OUT_FP32 if dtype == torch.float32 else TOL_OUT_BF16
     errs = {k: rel_err(out[k], want[k]) for k in ("distance", "edge", "crop")}
@@ -707,7 +738,9 @@ def conv_bn_act_eval_case(dev, B, H, W, cins, cout, k, stride=1, act=True, seed=
         two = F.batchnorm_act(y, gamma, beta, mean, var, False, eps=1e-5, act=act)
         xr = torch.cat([_f(x) for x in xs], dim=-1).permute(0, 3, 1, 2)
         ref = TF.batch_norm(TF.conv2d(xr, w, None, stride=stride, padding=pad), mean, var, gamma, beta, False, 0.0, 1e-5)
-        ref = (TF.silu(ref) if act else ref).permute(0, 2, 3, 1)
+        code = int(act)  # True = SiLU, or a CNB_ACT_* code
+        names = {v: k for k, v in F.ACT_CODES.items()}
+        ref = (getattr(torch.nn, names[code])()(ref) if code else ref).permute(0, 2, 3, 1)
     tol = _tol(dtype)
     _check("fused eval epilogue vs torch", fused, ref, tol)
     _check("fused eval epilogue vs two launches", fused, two, tol)

@@ -134,6 +134,20 @@ def test_model_reproduces_reference_golden(dev, name):
     cases.model_vs_golden(dev, name)
 
 
+@pytest.mark.parametrize("name", ["ReLU", "LeakyReLU", "GELU", "Mish", "ELU", "Tanh", "Sigmoid", "Hardswish"])
+def test_activation_codes(dev, name):
+    cases.activation_case(dev, F32, name)
+    cases.activation_case(dev, BF16, name)
+
+
+@pytest.mark.parametrize("name", ["ReLU", "GELU"])
+def test_model_with_another_activation_type(dev, name):
+    """``activation_type`` other than the default SiLU (reference ``model.py:58``, ``activations.py``): training-mode forward, loss and
+    every gradient against the oracle port (which ``test_port_matches_reference_module`` pins to the real reference for these names)."""
+    cfg = dict(B=1, C=2, T=6, H=16, W=16, hidden=8, dilations=[1, 2], activation_type=name)
+    cases.model_vs_port(dev, cfg, training=True)
+
+
 def test_model_eval_mode_matches_port(dev):
     cfg = dict(B=1, C=2, T=6, H=16, W=16, hidden=8, dilations=[1, 2])
     cases.model_vs_port(dev, cfg, training=False)

@@ -83,13 +83,14 @@ def test_port_reproduces_golden(name):
 
 
 @pytest.mark.skipif(not reference_available(), reason="/root/reference is only present in the authoring container")
-def test_port_matches_reference_module():
+@pytest.mark.parametrize("activation_type", ["SiLU", "ReLU", "GELU", "LeakyReLU"])
+def test_port_matches_reference_module(activation_type):
     from oracle.ref_loader import load_reference
 
     ref = load_reference()
     torch.manual_seed(5)
     B, C, T, H, W, hid = 1, 4, 9, 26, 22, 8
-    model = ref.TowerUNet(in_channels=C, in_time=T, hidden_channels=hid, dilations=[1, 2])
+    model = ref.TowerUNet(in_channels=C, in_time=T, hidden_channels=hid, dilations=[1, 2], activation_type=activation_type)
     spec = port.param_spec(C, T, hid, [1, 2])
     sd_ref = model.state_dict()
     assert sorted(n for n, _ in spec) == sorted(sd_ref.keys())
@@ -98,7 +99,7 @@ def test_port_matches_reference_module():
     for training in (True, False):
         model.train(training)
         sd = {k: v.clone() for k, v in model.state_dict().items()}
-        got = port.towerunet_forward(sd, x, [1, 2], training=training)
+        got = port.towerunet_forward(sd, x, [1, 2], training=training, activation_type=activation_type)
         want = model(x)
         for k in ("distance", "edge", "crop"):
             assert rel_err(got[k], want[k]) < 1e-5

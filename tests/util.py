@@ -56,7 +56,8 @@ def mine_from_state_dict(cfg: dict, sd: dict, device: str, dtype=torch.float32):
     import cultionet_b200 as cb
     from oracle.make_golden import variant_kwargs
 
+    extra = {"activation_type": cfg["activation_type"]} if "activation_type" in cfg else {}
     m = cb.TowerUNet(in_channels=cfg["C"], in_time=cfg["T"], hidden_channels=cfg["hidden"], dilations=cfg["dilations"], compute_dtype=dtype,
-                     **variant_kwargs(cfg))
+                     **variant_kwargs(cfg), **extra)
     m.load_state_dict(sd, strict=True)
     return m.to(device)
