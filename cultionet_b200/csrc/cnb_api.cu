@@ -1039,17 +1039,22 @@ int cnb_resize_bilinear_bwd_colsum(const void* dy, void* dx, int B, int Hin, int
         }();
         if (!persistent) {
             const size_t smem_row = (size_t)Win * (1 + nc) * 4 + (1 + nc) * 4 + (fuse_sum ? (size_t)C * 4 : 0);
+#define CNB_RESIZE_ROW(NCV, CS)                                                                                                              \
+    do {                                                                                                                                     \
+        CNB_SET_SMEM((resize_bilinear_bwd_row_kernel<T, NCV, CS>), smem_row);                                                                \
+        CNB_LAUNCH((resize_bilinear_bwd_row_kernel<T, NCV, CS>), dim3(B * Hin), dim3(256), smem_row, (cudaStream_t)stream, (const T*)dy,     \
+                   (T*)dx, B, Hin, Win, Hout, Wout, C, rh_, rw_, cs);                                                                        \
+    } while (0)
             CNB_DISPATCH_DTYPE(dtype, {
                 if (near1) {
-                    CNB_SET_SMEM((resize_bilinear_bwd_row_kernel<T, RB_NC_NEAR1>), smem_row);
-                    CNB_LAUNCH((resize_bilinear_bwd_row_kernel<T, RB_NC_NEAR1>), dim3(B * Hin), dim3(256), smem_row, (cudaStream_t)stream,
-                               (const T*)dy, (T*)dx, B, Hin, Win, Hout, Wout, C, rh_, rw_, cs);
+                    if (cs) CNB_RESIZE_ROW(RB_NC_NEAR1, true);
+                    else CNB_RESIZE_ROW(RB_NC_NEAR1, false);
                 } else {
-                    CNB_SET_SMEM((resize_bilinear_bwd_row_kernel<T, RB_NC>), smem_row);
-                    CNB_LAUNCH((resize_bilinear_bwd_row_kernel<T, RB_NC>), dim3(B * Hin), dim3(256), smem_row, (cudaStream_t)stream, (const T*)dy,
-                               (T*)dx, B, Hin, Win, Hout, Wout, C, rh_, rw_, cs);
+                    if (cs) CNB_RESIZE_ROW(RB_NC, true);
+                    else CNB_RESIZE_ROW(RB_NC, false);
                 }
             });
+#undef CNB_RESIZE_ROW
             CNB_CHECK_LAUNCH("resize_bilinear_bwd_row_kernel");
             if (colsum && !fuse_sum) return cnb_bias_grad(dx, C, (int64_t)B * Hin * Win, C, colsum, accumulate, dtype, stream);
             return CNB_OK;

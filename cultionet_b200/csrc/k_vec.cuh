@@ -586,10 +586,11 @@ __device__ __forceinline__ void bilinear_support(int i, float rscale, int in_len
 }
 
 // One CTA per input row (the x-axis table is rebuilt by every CTA, but 4064 short CTAs fill and drain the machine better than ~1000
-// persistent ones: 199 vs 218 us at level a).  With `colsum` the CTA also adds the per-channel sums of the row it wrote to colsum[C]
+// persistent ones).  COLSUM is a template parameter: the eight extra accumulators cost a resident CTA per SM (56 registers: four CTAs
+// instead of six), which this latency-bound kernel pays for in full (ncu: 159 -> 212 us at level a when the plain variant carried them).  With `colsum` the CTA also adds the per-channel sums of the row it wrote to colsum[C]
 // (the bias gradient of the ConvTranspose2d whose output was resized).
-template <typename T, int NC>
-__global__ void __launch_bounds__(256) resize_bilinear_bwd_row_kernel(const T* __restrict__ dy, T* __restrict__ dx, int B, int Hin, int Win,
+template <typename T, int NC, bool COLSUM>
+__global__ void __launch_bounds__(256, COLSUM ? 5 : 6) resize_bilinear_bwd_row_kernel(const T* __restrict__ dy, T* __restrict__ dx, int B, int Hin, int Win,
                                                                      int Hout, int Wout, int C, float rh, float rw,
                                                                      float* __restrict__ colsum) {
     CNB_PDL_SYNC();
@@ -611,7 +612,7 @@ __global__ void __launch_bounds__(256) resize_bilinear_bwd_row_kernel(const T* _
 #pragma unroll
         for (int a = 0; a < NC; ++a) wxs[ix * NC + a] = w[a];
     }
-    if (colsum)
+    if (COLSUM)
         for (int i = threadIdx.x; i < C; i += blockDim.x) csum[i] = 0.f;
     if (threadIdx.x == 0) {
         float w[NC];
@@ -657,10 +658,12 @@ __global__ void __launch_bounds__(256) resize_bilinear_bwd_row_kernel(const T* _
             }
         }
         cnb_stv(orow + ix * C + c, acc);
+        if (COLSUM) {
 #pragma unroll
-        for (int j = 0; j < V; ++j) cs[j] += acc[j];
+            for (int j = 0; j < V; ++j) cs[j] += acc[j];
+        }
     }
-    if (colsum) {  // uniform; blockDim % CV == 0: a thread stays on one channel vector
+    if (COLSUM) {  // blockDim % CV == 0: a thread stays on one channel vector
         if ((int)threadIdx.x < n) {
             const int c = ((int)threadIdx.x % CV) * V;
 #pragma unroll

@@ -213,6 +213,43 @@ def na_case(dev, dtype, B, H, W, heads, hd, k, d, seed=0):
     _check("na grad", torch.autograd.grad(y, qkv, g.to(dtype))[0], torch.autograd.grad(yr, qr, g.to(dtype).float())[0], tol * 2)
 
 
+def na_module_case(dev, dtype, B, H, W, dim, heads, k, d, direct: bool, seed=0):
+    """``nn.modules.attention.NeighborhoodAttention2D`` (qkv Linear -> neighbourhood attention -> proj Linear) against the same arithmetic
+    in torch fp32 (oracle/natten_ref.py), every parameter gradient included.  ``direct``: parameter gradients written straight into
+    ``param.grad``."""
+    from cultionet_b200.nn.modules.attention import NeighborhoodAttention2D
+
+    torch.manual_seed(seed)
+    m = NeighborhoodAttention2D(dim, heads, k, d).to(dev)
+    hd = dim // heads
+    x = _mk((B, H, W, dim), dev, dtype)
+    g = torch.randn(B, H, W, dim, device=dev).to(dtype)
+    xr = _f(x)
+    ps = [m.qkv.weight, m.qkv.bias, m.proj.weight, m.proj.bias]
+    qkv = TF.linear(xr, m.qkv.weight, m.qkv.bias)
+    if dtype == torch.bfloat16:
+        qkv = qkv.to(dtype).float()  # the product stores qkv in bf16 between the projection and the attention
+    t = qkv.reshape(B, H, W, 3, heads, hd).permute(3, 0, 4, 1, 2, 5)
+    a = natten_ref.na2d_qk(t[0] * hd ** -0.5, t[1], k, d).softmax(-1)
+    o = natten_ref.na2d_av(a, t[2], k, d).permute(0, 2, 3, 1, 4).reshape(B, H, W, dim)
+    yr = TF.linear(o, m.proj.weight, m.proj.bias)
+    gr = torch.autograd.grad(yr, [xr, *ps], g.float())
+    m.train()
+    y = m(x)
+    tol = _tol(dtype)
+    _check("na module fwd", y, yr, tol * 2)
+    if direct:
+        for p in ps:
+            p.grad = torch.full_like(p, 3.0)  # stale contents: the first contribution overwrites
+        with F.direct_param_grads():
+            y.backward(g, inputs=[x, *ps])
+        got = [x.grad] + [p.grad for p in ps]
+    else:
+        got = torch.autograd.grad(y, [x, *ps], g)
+    for i, (a_, c) in enumerate(zip(got, gr)):
+        _check(f"na module grad {i}", a_, c, tol * 3)
+
+
 def resize_case(dev, dtype, B, hi, wi, ho, wo, C, seed=0):
     torch.manual_seed(seed)
     x = _mk((B, hi, wi, C), dev, dtype)

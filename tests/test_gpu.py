@@ -23,6 +23,14 @@ def test_conv_ragged_channels(dev):
 
 
 @pytest.mark.parametrize("direct", [False, True])
+def test_attention_module_against_torch(dev, direct):
+    cases.na_module_case(dev, F32, 1, 9, 10, 16, 2, 3, 1, direct)
+    cases.na_module_case(dev, BF16, 2, 40, 36, 128, 4, 3, 2, direct)   # head_dim 32, dilation 2 (image-space key-side tiles)
+    cases.na_module_case(dev, BF16, 2, 33, 47, 256, 4, 3, 1, direct)   # head_dim 64, the config 2 level-a module
+    cases.na_module_case(dev, BF16, 1, 40, 40, 256, 4, 7, 2, direct)   # kernel 7: tensor-core band kernels
+
+
+@pytest.mark.parametrize("direct", [False, True])
 def test_upconv_bias_gradient_from_resize_backward(dev, direct):
     cases.upconv_case(dev, F32, 2, 13, 9, 8, direct)
     cases.upconv_case(dev, BF16, 2, 32, 32, 256, direct)   # the persistent table kernel with the fused column sum

@@ -25,6 +25,15 @@ def test_conv_transpose(dev, stride):
 
 
 @pytest.mark.parametrize("direct", [False, True])
+def test_attention_module_against_torch(dev, direct):
+    cases.na_module_case(dev, F32, 1, 9, 10, 16, 2, 3, 1, direct)      # generic kernels
+    if direct:
+        cases.na_module_case(dev, BF16, 1, 10, 18, 64, 2, 3, 2, direct)   # specialised bf16 kernels (head_dim 32)
+    else:
+        cases.na_module_case(dev, BF16, 1, 9, 17, 128, 2, 3, 1, direct)   # head_dim 64: two vectors per lane
+
+
+@pytest.mark.parametrize("direct", [False, True])
 def test_upconv_bias_gradient_from_resize_backward(dev, direct):
     cases.upconv_case(dev, F32, 2, 5, 6, 8, direct)
     cases.upconv_case(dev, BF16, 1, 7, 5, 16, direct)

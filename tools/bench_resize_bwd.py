@@ -11,6 +11,10 @@ from cultionet_b200._lib import call, dtype_code, ptr, stream_ptr
 
 dev, dt = "cuda", torch.bfloat16
 B, Hi, Wi, Ho, Wo, C = 32, 127, 127, 128, 128, 256
+if len(sys.argv) > 1:  # output size of the fix-up: 128 (level a), 64 (level b), 32 (level c)
+    Ho = Wo = int(sys.argv[1])
+    Hi = Wi = Ho - 1
+print("resize backward", Hi, "<-", Ho)
 dy = torch.randn(B, Ho, Wo, C, device=dev).to(dt)
 dx = torch.empty(B, Hi, Wi, C, device=dev, dtype=dt)
 cs = torch.zeros(C, device=dev)
