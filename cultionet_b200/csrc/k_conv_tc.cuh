@@ -69,6 +69,17 @@ struct ConvTcParams {
     // weights-resident mode (one N tile, all taps x chunks of B fit beside >= 4 A stages): B is loaded ONCE per CTA into the first
     // res_bytes of the ring region and the pipeline stages carry the A operand only
     int b_resident, res_bytes, nstages;
+    // Patch mode (weights-resident 3x3, stride 1, one 64-channel chunk: the 64 -> 64 layers).  Nine tap-shifted boxes of a tile overlap
+    // almost completely, and ncu showed these layers waiting on TMA (0.9 GB of L2 -> SM traffic for a 67 MB input).  Here ONE box per
+    // column shift dx, TH + 2 rows high, is staged (tmA[1]); the three taps that share dx read it through UMMA descriptors whose start
+    // address is shifted by whole pixel rows -- TW * 128 bytes, a multiple of the 1024-byte swizzle atom for TW >= 8, so the 128-byte
+    // swizzle phase of every row is unchanged.  Three TMA boxes (60 KB at TH = 8) per tile instead of nine (144 KB) plus nine B tiles.
+    int patch;               // 0 = off
+    int patch_bytes;         // (TH + 2 * halo) * TW * 128
+    short patch_dx[3];       // column shift of group g
+    short patch_y;           // row shift of the box origin (the smallest tap_dy)
+    short patch_tap[3][3];   // group g, member m: absolute tap index (its resident B tile), -1 = none
+    short patch_row[3][3];   // ... and its row offset inside the patch: tap_dy - patch_y
     int prefetch;  // tiles (per CTA) the producer prefetches ahead into L2; 0 = off
     int dbg;  // diagnostics only (CNB_EPI_DEBUG bit mask, timing experiments): 1 = epilogue skips its global stores, 2 = skips the BatchNorm sums
     // split output (cnb_conv_desc::nout): columns [seg_begin[i], seg_begin[i+1]) of the GEMM go to seg_out[i]; boundaries are
@@ -287,7 +298,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     volatile uint32_t* slot_ptr =
         reinterpret_cast<volatile uint32_t*>(base_ptr + C::RING_BYTES + EPI_STAGING_BYTES + 8 * (2 * MAX_STAGES + 5));
     const int nstages = p.nstages;
-    const uint32_t stage_bytes = p.b_resident ? (uint32_t)A_BYTES : (uint32_t)C::STAGE_BYTES;
+    const uint32_t stage_bytes = p.patch ? (uint32_t)p.patch_bytes : (p.b_resident ? (uint32_t)A_BYTES : (uint32_t)C::STAGE_BYTES);
     const uint32_t ring0 = base + (uint32_t)p.res_bytes;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -359,6 +370,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 decode_tile(p, tile, BN, tc);
                 if (p.prefetch) prefetch_tile(tile + (p.prefetch + 1) * (int)gridDim.x);
+                if (p.patch) {
+                    for (int gq = 0; gq < 3; ++gq) {
+                        mbar_wait(empty_bar(stage), phase ^ 1u);
+                        mbar_arrive_expect_tx(full_bar(stage), (uint32_t)p.patch_bytes);
+                        tma_load_4d(ring0 + stage * stage_bytes, &p.tmA[1], full_bar(stage), 0, tc.x0 + p.patch_dx[gq], tc.y0 + p.patch_y, tc.b);
+                        if (++stage == nstages) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                    }
+                    continue;
+                }
                 for (int t = p.ph_tap0[tc.ph]; t < p.ph_tap0[tc.ph + 1]; ++t) {
                     const int cy = tc.y0 + p.tap_dy[t], cx = tc.x0 + p.tap_dx[t], wt = p.tap_w[t];
                     for (int s = 0; s < p.nsrc; ++s) {
@@ -400,6 +423,32 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+                if (p.patch) {
+                    uint32_t accum = 0u;  // the first MMA of the tile overwrites the accumulator
+                    for (int gq = 0; gq < 3; ++gq) {
+                        mbar_wait(full_bar(stage), phase);
+                        tc_fence_after();
+                        const uint32_t patch_addr = ring0 + stage * stage_bytes;
+                        for (int m = 0; m < 3; ++m) {
+                            const int t = p.patch_tap[gq][m];
+                            if (t < 0) continue;
+                            const uint64_t adesc = umma_desc_sw128(patch_addr + (uint32_t)(p.patch_row[gq][m] * p.TW) * 128u);
+                            const uint64_t bdesc = umma_desc_sw128(base + (uint32_t)t * (uint32_t)C::B_BYTES);
+#pragma unroll
+                            for (int k = 0; k < BK / 16; ++k) {
+                                umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accum);
+                                accum = 1u;
+                            }
+                        }
+                        umma_commit(empty_bar(stage));
+                        if (++stage == nstages) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                    }
+                    umma_commit(tfull_bar(acc));
+                    continue;
+                }
                 for (int c = 0; c < total_chunks; ++c) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
@@ -801,6 +850,13 @@ inline void plan_ring(ConvTcParams& p, int total_b_tiles) {
     static const bool allow = env_on("CNB_B_RESIDENT");
     p.b_resident = 0, p.res_bytes = 0, p.nstages = Cfg<BN>::STAGES;
     const long res = (long)total_b_tiles * Cfg<BN>::B_BYTES;
+    if (p.patch) {  // conv_tc_launch has checked that B and three patches fit and that the launch is big enough
+        int stages = (int)((Cfg<BN>::RING_BYTES - res) / p.patch_bytes);
+        p.b_resident = 1;
+        p.res_bytes = (int)res;
+        p.nstages = stages < MAX_STAGES ? stages : MAX_STAGES;
+        return;
+    }
     if (!allow || p.num_tiles != p.m_tiles || total_b_tiles <= 0 || res > Cfg<BN>::RING_BYTES) return;
     const int stages = (int)((Cfg<BN>::RING_BYTES - res) / A_BYTES);
     if (stages < 4 || p.m_tiles < 4 * num_sms()) return;
@@ -927,6 +983,54 @@ inline int conv_tc_launch(const cnb_conv_desc* d, cudaStream_t stream) {
     }
     if (p.nphases < 1) return 3;
     pick_tile(dom_h, dom_w, &p.TH, &p.TW);
+    // ---- patch mode (see ConvTcParams::patch): 3x3, stride 1, dilation 1, one source of at most 64 channels, one N tile, all nine
+    // B tiles resident beside at least three patches, enough pixel tiles per CTA (the plan_ring rule) ----
+    {
+        static const bool allow = env_on("CNB_TC_PATCH") && env_on("CNB_B_RESIDENT");
+        const int b_bytes = BN * BK * 2;
+        bool ok = allow && s == 1 && d->dil == 1 && d->KH == 3 && d->KW == 3 && d->nsrc == 1 && d->src_c[0] <= BK && d->N <= BN &&
+                  p.nphases == 1 && p.ph_tap0[1] == 9;
+        if (ok) {
+            // a tile at least two rows high whose rows are whole swizzle atoms (TW >= 8): prefer TH = 8 (patch overhead 10 / 8)
+            long best = -1;
+            int bth = 0, btw = 0;
+            for (int tw = 64; tw >= 8; tw >>= 1) {
+                const int th = BM / tw;
+                const long cover = (long)cnb_div_up(dom_w, tw) * tw * cnb_div_up(dom_h, th) * (th + 2);
+                if (best < 0 || cover < best) best = cover, bth = th, btw = tw;
+            }
+            const int patch_bytes = (bth + 2) * btw * 128;
+            const long tiles = (long)d->B * cnb_div_up(dom_h, bth) * cnb_div_up(dom_w, btw);
+            ok = 9L * b_bytes + 3L * patch_bytes <= (long)(BN == 256 ? Cfg<256>::RING_BYTES : BN == 128 ? Cfg<128>::RING_BYTES
+                                                            : BN == 64 ? Cfg<64>::RING_BYTES : Cfg<32>::RING_BYTES) &&
+                 tiles >= 4L * num_sms();
+            if (ok) {
+                p.TH = bth, p.TW = btw;
+                p.patch = 1;
+                p.patch_bytes = patch_bytes;
+                int miny = 0;
+                for (int t = 0; t < 9; ++t) miny = p.tap_dy[t] < miny ? p.tap_dy[t] : miny;
+                p.patch_y = (short)miny;
+                int ng = 0;
+                for (int gq = 0; gq < 3; ++gq)
+                    for (int m = 0; m < 3; ++m) p.patch_tap[gq][m] = -1;
+                for (int t = 0; t < 9; ++t) {
+                    int gq = 0;
+                    while (gq < ng && p.patch_dx[gq] != p.tap_dx[t]) ++gq;
+                    if (gq == ng) {
+                        if (ng == 3) return 3;
+                        p.patch_dx[ng++] = p.tap_dx[t];
+                    }
+                    int m = 0;
+                    while (m < 3 && p.patch_tap[gq][m] >= 0) ++m;
+                    if (m == 3 || p.tap_dy[t] - miny > 2) return 3;
+                    p.patch_tap[gq][m] = (short)t;
+                    p.patch_row[gq][m] = (short)(p.tap_dy[t] - miny);
+                }
+                if (ng != 3) return 3;
+            }
+        }
+    }
     int mt = 0;
     for (int ph = 0; ph < p.nphases; ++ph) {
         p.ph_tile0[ph] = mt;
@@ -955,6 +1059,7 @@ inline int conv_tc_launch(const cnb_conv_desc* d, cudaStream_t stream) {
         for (int si = 0; si < d->nsrc; ++si)
             if (make_act_map(&p.tmA[si], d->src[si], d->src_c[si], d->Win, d->Hin, d->B, d->src_stride[si], p.TW, p.TH)) return 2;
     }
+    if (p.patch && make_act_map(&p.tmA[1], d->src[0], d->src_c[0], d->Win, d->Hin, d->B, d->src_stride[0], p.TW, p.TH + 2)) return 2;
     if (make_weight_map(&p.tmB, d->w_packed, koff, d->N, taps, d->w_row_stride, d->w_tap_stride, BN)) return 2;
 
     p.N = d->N;

@@ -77,6 +77,10 @@ def test_conv_tensor_core_shapes(dev):
         cases.conv_case(dev, BF16, 2, 32, 32, [64, 128, 256], 256, 3, 1, 1, 1)  # tower-like concat: 3-tap, 2-tap and 1-tap weight-gradient tiles
         cases.conv_case(dev, BF16, 1, 30, 34, [128], 72, 3, 1, 2, 2)        # dilation 2, two taps per tile, ragged N
         cases.conv_case(dev, BF16, 2, 16, 16, [88], 256, 1, 1, 0, 1)        # 1x1: one tap, nothing to group
+        # patch mode of the tcgen05 kernel (3x3, <= 64 channels, >= 4 pixel tiles per SM): one TH+2-row box per column shift, taps through
+        # row-shifted descriptors; full tiles, ragged tiles / partial channel chunk / partial N tile
+        cases.conv_case(dev, BF16, 8, 128, 128, [64], 64, 3, 1, 1, 1)
+        cases.conv_case(dev, BF16, 6, 100, 121, [40], 48, 3, 1, 1, 1)
         cases.convT_case(dev, BF16, 2, 25, 25, 128, 128, 2)                  # 25 -> 49
         cases.convT_case(dev, BF16, 2, 13, 13, 64, 64, 4)                    # 13 -> 49 (final_c)
     finally:
