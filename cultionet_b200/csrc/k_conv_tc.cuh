@@ -893,6 +893,12 @@ inline int launch_bn(ConvTcParams& p, cudaStream_t stream) {
 // Output-tile width: the padded column count times a penalty for narrow tiles (a narrow tile re-stages the A operand more often per
 // output column).  N = 960 (merged data gradient of a tower convolution) takes 4 tiles of 256 with the last one masked, not 15 of 64.
 inline int pick_bn(int N) {
+    static const int forced = [] {  // CNB_TC_BN=32|64|128|256: one tile width for every launch (timing experiments)
+        const char* e = getenv("CNB_TC_BN");
+        const int v = e ? atoi(e) : 0;
+        return (v == 32 || v == 64 || v == 128 || v == 256) ? v : 0;
+    }();
+    if (forced) return forced;
     if (N <= 32) return 32;
     const int bns[4] = {256, 128, 64, 32};
     const float penalty[4] = {1.0f, 1.15f, 1.6f, 2.5f};
