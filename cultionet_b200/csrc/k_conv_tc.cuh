@@ -8,10 +8,12 @@
 //   IS the convolution's zero padding.  Box rows are 128 bytes => the K-major SWIZZLE_128B canonical UMMA layout (SBO 1024 B).
 // * B tile = BN rows of the packed weights [tap][N][Ctot] (3-D map, box {64, BN, 1}), same layout.
 // * the K loop walks taps x sources x chunks, so the UNet3+ concatenation is never materialised (one tensor map per source).
-// * accumulators are double-buffered in TMEM (2 x BN fp32 columns): the 4 epilogue warps drain tile i (tcgen05.ld -> +bias ->
-//   bf16 -> global) while the MMA warp already runs tile i+1.
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue (TMEM lane
-// quadrant = warp_id % 4).  One CTA per SM, static round-robin tile schedule.
+// * accumulators are double-buffered in TMEM (2 x BN fp32 columns): the epilogue warps drain tile i (tcgen05.ld -> +bias / BatchNorm
+//   scale-shift-activation / batch-statistics sums -> bf16 -> staged row-contiguous stores) while the MMA warp already runs tile i+1.
+// * two optional layouts of the ring: weights-resident (B loaded once per CTA, A-only stages) and patch mode (one TH+2-row box per
+//   column shift, the taps read through row-shifted descriptors) -- see ConvTcParams.
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = epilogue (TMEM lane
+// quadrant = warp_id % 4, two warps per quadrant alternating 32-column chunks).  One CTA per SM, static round-robin tile schedule.
 #pragma once
 #ifndef CNB_EMU
 #include <cuda.h>
