@@ -1258,8 +1258,16 @@ int cnb_tanimoto_fwd(const cnb_tanimoto_term* terms, int nterms, int B, int64_t 
         if (terms[t].C > cmax) cmax = terms[t].C;
     }
     CNB_MEMSET_ASYNC(sums, 0, sizeof(double) * 4 * nterms * B, (cudaStream_t)stream);
-    const int chunks = cnb_clamp_grid(cnb_div_up((long)cmax * HW, 256 * 8), cnb_div_up(4L * CNB_NUM_SMS, (long)B * nterms));
-    CNB_LAUNCH(tanimoto_sums_kernel, dim3(chunks, B, nterms), dim3(256), 0, (cudaStream_t)stream, pack, B, (long)HW, sums);
+    const void* shared_labels = nullptr;
+    if (nterms > 1 && tanimoto_shared_labels(terms, nterms, (long)HW, &shared_labels)) {
+        // every term in one pass over the pixels: the label tensor is read once (24 instead of 40 bytes per pixel for the TowerUNet loss)
+        const int chunks = cnb_clamp_grid(cnb_div_up((long)HW, 256 * 4 * 2), cnb_div_up(4L * CNB_NUM_SMS, (long)B));
+        CNB_LAUNCH(tanimoto_sums_fused_kernel, dim3(chunks, B), dim3(256), 0, (cudaStream_t)stream, pack, nterms, B, (long)HW,
+                   (const long long*)shared_labels, sums);
+    } else {
+        const int chunks = cnb_clamp_grid(cnb_div_up((long)cmax * HW, 256 * 8), cnb_div_up(4L * CNB_NUM_SMS, (long)B * nterms));
+        CNB_LAUNCH(tanimoto_sums_kernel, dim3(chunks, B, nterms), dim3(256), 0, (cudaStream_t)stream, pack, B, (long)HW, sums);
+    }
     CNB_MEMSET_ASYNC(loss, 0, sizeof(float) * (1 + nterms), (cudaStream_t)stream);
     CNB_LAUNCH(tanimoto_finalize_kernel, dim3(cnb_div_up((long)nterms * B, 256)), dim3(256), 0, (cudaStream_t)stream, pack, nterms, B, (long)HW,
                smooth, depth, variant, (const double*)sums, coef, loss);
@@ -1278,8 +1286,15 @@ int cnb_tanimoto_bwd(const cnb_tanimoto_term* terms, int nterms, int B, int64_t 
         pack.t[t] = terms[t];
         if (terms[t].C > cmax) cmax = terms[t].C;
     }
-    const int chunks = cnb_clamp_grid(cnb_div_up((long)cmax * HW, 256 * 4), cnb_div_up(8L * CNB_NUM_SMS, (long)B * nterms));
-    CNB_LAUNCH(tanimoto_bwd_kernel, dim3(chunks, B, nterms), dim3(256), 0, (cudaStream_t)stream, pack, B, (long)HW, coef, gscale);
+    const void* shared_labels = nullptr;
+    if (nterms > 1 && tanimoto_shared_labels(terms, nterms, (long)HW, &shared_labels)) {
+        const int chunks = cnb_clamp_grid(cnb_div_up((long)HW, 256 * 4), cnb_div_up(8L * CNB_NUM_SMS, (long)B));
+        CNB_LAUNCH(tanimoto_bwd_fused_kernel, dim3(chunks, B), dim3(256), 0, (cudaStream_t)stream, pack, nterms, B, (long)HW,
+                   (const long long*)shared_labels, coef, gscale);
+    } else {
+        const int chunks = cnb_clamp_grid(cnb_div_up((long)cmax * HW, 256 * 4), cnb_div_up(8L * CNB_NUM_SMS, (long)B * nterms));
+        CNB_LAUNCH(tanimoto_bwd_kernel, dim3(chunks, B, nterms), dim3(256), 0, (cudaStream_t)stream, pack, B, (long)HW, coef, gscale);
+    }
     CNB_CHECK_LAUNCH("tanimoto_bwd_kernel");
     return CNB_OK;
 }

@@ -45,7 +45,7 @@ __device__ __forceinline__ void tanimoto_elem(const cnb_tanimoto_term& tm, long 
 // Four consecutive pixels of a single-channel term (C == 1, HW % 4 == 0, 16-byte aligned operands: every term of the TowerUNet loss):
 // one 16-byte load per fp32 operand and two per int64 label quad instead of 4 x (a 64-bit division + scalar loads).  The scalar
 // version ran at 1.8 TB/s at a scaled size (B = 512), issue-bound (ncu: 59 % issue slots busy for 24 bytes per pixel).
-__device__ __forceinline__ bool tanimoto_vec_ok(const cnb_tanimoto_term& tm, long HW) {
+__host__ __device__ __forceinline__ bool tanimoto_vec_ok(const cnb_tanimoto_term& tm, long HW) {
     auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
     return tm.C == 1 && (HW & 3) == 0 && al(tm.pred) && al(tm.target) && (tm.mask_mode == 0 || al(tm.mask)) &&
            (tm.dpred == nullptr || al(tm.dpred)) && (tm.target_mode != 0 || tm.tgt_c == 1);
@@ -91,6 +91,125 @@ __device__ __forceinline__ void tanimoto_elem4(const cnb_tanimoto_term& tm, long
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) tq[j] = t[j] * m[j], pq[j] = p[j] * m[j], mk[j] = m[j];
+}
+
+// ---------------------------------------------------------------------------------------------
+// All terms in ONE pass (the TowerUNet loss: three single-channel terms whose label-typed operands -- the targets of the edge / crop
+// terms and every term's mask -- are the SAME int64 label tensor).  The per-term kernels read 40 bytes per pixel (the 8-byte labels
+// three times over: L2 hits at 4 MB, DRAM traffic at a scaled size) for 24 algorithmic ones; here the labels of a pixel quad are loaded
+// once and serve every term.
+// ---------------------------------------------------------------------------------------------
+// the one label tensor the terms share (NULL when no term has a label-typed operand), or false when they do not share one
+static inline bool tanimoto_shared_labels(const cnb_tanimoto_term* t, int nterms, long HW, const void** labels) {
+    const void* lab = nullptr;
+    for (int i = 0; i < nterms; ++i) {
+        if (!tanimoto_vec_ok(t[i], HW)) return false;
+        const void* cand[2] = {t[i].target_mode != 0 ? (const void*)t[i].target : nullptr, t[i].mask_mode >= 2 ? (const void*)t[i].mask : nullptr};
+        for (int k = 0; k < 2; ++k) {
+            if (!cand[k]) continue;
+            if (lab && cand[k] != lab) return false;
+            lab = cand[k];
+        }
+    }
+    *labels = lab;
+    return true;
+}
+// tanimoto_elem4 with the label quad already in registers
+__device__ __forceinline__ void tanimoto_elem4_shared(const cnb_tanimoto_term& tm, long i, const long long (&lab)[4], float (&tq)[4],
+                                                      float (&pq)[4], float (&mk)[4]) {
+    const float4 p4 = *reinterpret_cast<const float4*>(tm.pred + i);
+    const float p[4] = {p4.x, p4.y, p4.z, p4.w};
+    float t[4];
+    if (tm.target_mode == 0) {
+        const float4 t4 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(tm.target) + i);
+        t[0] = t4.x, t[1] = t4.y, t[2] = t4.z, t[3] = t4.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            t[j] = tm.target_mode == 1 ? (lab[j] == 0 ? 1.f : 0.f)
+                                       : (tm.target_mode == 2 ? (lab[j] == tm.edge_class ? 1.f : 0.f) : ((lab[j] > 0 && lab[j] < tm.edge_class) ? 1.f : 0.f));
+    }
+    float m[4] = {1.f, 1.f, 1.f, 1.f};
+    if (tm.mask_mode == 1) {
+        const float4 m4 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(tm.mask) + i);
+        m[0] = m4.x, m[1] = m4.y, m[2] = m4.z, m[3] = m4.w;
+    } else if (tm.mask_mode >= 2) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) m[j] = tm.mask_mode == 2 ? (float)lab[j] : (lab[j] != -1 ? 1.f : 0.f);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) tq[j] = t[j] * m[j], pq[j] = p[j] * m[j], mk[j] = m[j];
+}
+
+// grid = (chunks, B); the same sums as tanimoto_sums_kernel for every term
+__global__ void __launch_bounds__(256) tanimoto_sums_fused_kernel(TanimotoTerms terms, int nterms, int B, long HW, const long long* __restrict__ labels,
+                                                                  double* __restrict__ sums) {
+    CNB_PDL_SYNC();
+    __shared__ double sh[TN_MAX_TERMS * 4];
+    if (threadIdx.x < TN_MAX_TERMS * 4) sh[threadIdx.x] = 0.0;
+    __syncthreads();
+    const long b = blockIdx.y;
+    float a[TN_MAX_TERMS][4];
+#pragma unroll
+    for (int t = 0; t < TN_MAX_TERMS; ++t)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) a[t][k] = 0.f;
+    for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q * 4 < HW; q += (long)gridDim.x * blockDim.x) {
+        const long i = b * HW + q * 4;
+        long long lab[4] = {0, 0, 0, 0};
+        if (labels) tanimoto_labels4(labels, i, lab);
+#pragma unroll
+        for (int t = 0; t < TN_MAX_TERMS; ++t) {
+            if (t >= nterms) break;
+            float tq[4], pq[4], mk[4];
+            tanimoto_elem4_shared(terms.t[t], i, lab, tq, pq, mk);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                a[t][0] = fmaf(tq[j], pq[j], a[t][0]);
+                a[t][1] += tq[j] * tq[j] + pq[j] * pq[j];
+                a[t][2] += tq[j];
+                a[t][3] += pq[j];
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < TN_MAX_TERMS; ++t) {
+        if (t >= nterms) break;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const double w = cnb_warp_sum((double)a[t][k]);
+            if ((threadIdx.x & 31) == 0) atomicAdd(&sh[t * 4 + k], w);
+        }
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < nterms * 4) atomicAdd(sums + ((long)(threadIdx.x / 4) * B + b) * 4 + (threadIdx.x & 3), sh[threadIdx.x]);
+}
+
+// grid = (chunks, B); tanimoto_bwd_kernel for every term in one pass
+__global__ void __launch_bounds__(256) tanimoto_bwd_fused_kernel(TanimotoTerms terms, int nterms, int B, long HW, const long long* __restrict__ labels,
+                                                                 const float* __restrict__ coef, const float* __restrict__ gscale) {
+    CNB_PDL_SYNC();
+    const long b = blockIdx.y;
+    const float g = gscale ? gscale[0] : 1.f;
+    float c[TN_MAX_TERMS][4];
+#pragma unroll
+    for (int t = 0; t < TN_MAX_TERMS; ++t)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) c[t][k] = t < nterms ? coef[((long)t * B + b) * 4 + k] * g : 0.f;
+    for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q * 4 < HW; q += (long)gridDim.x * blockDim.x) {
+        const long i = b * HW + q * 4;
+        long long lab[4] = {0, 0, 0, 0};
+        if (labels) tanimoto_labels4(labels, i, lab);
+#pragma unroll
+        for (int t = 0; t < TN_MAX_TERMS; ++t) {
+            if (t >= nterms) break;
+            float tq[4], pq[4], mk[4], d[4];
+            tanimoto_elem4_shared(terms.t[t], i, lab, tq, pq, mk);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) d[j] = mk[j] * (c[t][0] * tq[j] + c[t][1] * pq[j] + c[t][2] * (1.f - tq[j]) + c[t][3] * (1.f - pq[j]));
+            *reinterpret_cast<float4*>(terms.t[t].dpred + i) = make_float4(d[0], d[1], d[2], d[3]);
+        }
+    }
 }
 
 // grid = (chunks, B, nterms); sums[(term*B + b)*4 + {P, S, St, Sp}] in fp64
