@@ -643,17 +643,39 @@ __global__ void __launch_bounds__(256, COLSUM ? 5 : 6) resize_bilinear_bwd_row_k
         float acc[V];
 #pragma unroll
         for (int j = 0; j < V; ++j) acc[j] = 0.f;
+        if (NC == 3 && wy[2] == 0.f && wx[2] == 0.f) {
+            // the 2H-1 -> 2H fix-up: exactly two outputs read an input index per axis (a third only through a rounding of the last
+            // output's source coordinate).  Four unconditional loads, issued together, instead of nine guarded candidates: the same
+            // shape as the forward kernel, which streams at 0.73 of the copy rate where this loop reached 0.5.
+            const long r1 = wy[1] != 0.f ? (long)Wout * C : 0, c1 = wx[1] != 0.f ? C : 0;  // stay inside the tensor when the weight is 0
+            const uint4 q00 = cnb_ldraw(col), q01 = cnb_ldraw(col + c1), q10 = cnb_ldraw(col + r1), q11 = cnb_ldraw(col + r1 + c1);
+            const float w00 = wy[0] * wx[0], w01 = wy[0] * wx[1], w10 = wy[1] * wx[0], w11 = wy[1] * wx[1];
+            float v[V];
+            cnb_expand(q00, v, col);
 #pragma unroll
-        for (int a = 0; a < NC; ++a) {
-            if (wy[a] == 0.f) continue;  // CTA-uniform
+            for (int j = 0; j < V; ++j) acc[j] = w00 * v[j];
+            cnb_expand(q01, v, col);
 #pragma unroll
-            for (int bb = 0; bb < NC; ++bb) {
-                const float w = wy[a] * wx[bb];
-                if (w != 0.f) {
-                    float v[V];
-                    cnb_ldv(col + ((long)a * Wout + bb) * C, v);
+            for (int j = 0; j < V; ++j) acc[j] = fmaf(w01, v[j], acc[j]);
+            cnb_expand(q10, v, col);
 #pragma unroll
-                    for (int j = 0; j < V; ++j) acc[j] = fmaf(w, v[j], acc[j]);
+            for (int j = 0; j < V; ++j) acc[j] = fmaf(w10, v[j], acc[j]);
+            cnb_expand(q11, v, col);
+#pragma unroll
+            for (int j = 0; j < V; ++j) acc[j] = fmaf(w11, v[j], acc[j]);
+        } else {
+#pragma unroll
+            for (int a = 0; a < NC; ++a) {
+                if (wy[a] == 0.f) continue;  // CTA-uniform
+#pragma unroll
+                for (int bb = 0; bb < NC; ++bb) {
+                    const float w = wy[a] * wx[bb];
+                    if (w != 0.f) {
+                        float v[V];
+                        cnb_ldv(col + ((long)a * Wout + bb) * C, v);
+#pragma unroll
+                        for (int j = 0; j < V; ++j) acc[j] = fmaf(w, v[j], acc[j]);
+                    }
                 }
             }
         }
@@ -733,17 +755,36 @@ __global__ void __launch_bounds__(256) resize_bilinear_bwd_tab_kernel(const T* _
             float acc[V];
 #pragma unroll
             for (int j = 0; j < V; ++j) acc[j] = 0.f;
+            if (NC == 3 && wy[2] == 0.f && wx[2] == 0.f) {  // the 2 x 2 case of the row kernel above
+                const long r1 = wy[1] != 0.f ? (long)Wout * C : 0, c1 = wx[1] != 0.f ? C : 0;
+                const uint4 q00 = cnb_ldraw(col), q01 = cnb_ldraw(col + c1), q10 = cnb_ldraw(col + r1), q11 = cnb_ldraw(col + r1 + c1);
+                const float w00 = wy[0] * wx[0], w01 = wy[0] * wx[1], w10 = wy[1] * wx[0], w11 = wy[1] * wx[1];
+                float v[V];
+                cnb_expand(q00, v, col);
 #pragma unroll
-            for (int a = 0; a < NC; ++a) {
-                if (wy[a] == 0.f) continue;  // CTA-uniform
+                for (int j = 0; j < V; ++j) acc[j] = w00 * v[j];
+                cnb_expand(q01, v, col);
 #pragma unroll
-                for (int bb = 0; bb < NC; ++bb) {
-                    const float w = wy[a] * wx[bb];
-                    if (w != 0.f) {
-                        float v[V];
-                        cnb_ldv(col + ((long)a * Wout + bb) * C, v);
+                for (int j = 0; j < V; ++j) acc[j] = fmaf(w01, v[j], acc[j]);
+                cnb_expand(q10, v, col);
 #pragma unroll
-                        for (int j = 0; j < V; ++j) acc[j] = fmaf(w, v[j], acc[j]);
+                for (int j = 0; j < V; ++j) acc[j] = fmaf(w10, v[j], acc[j]);
+                cnb_expand(q11, v, col);
+#pragma unroll
+                for (int j = 0; j < V; ++j) acc[j] = fmaf(w11, v[j], acc[j]);
+            } else {
+#pragma unroll
+                for (int a = 0; a < NC; ++a) {
+                    if (wy[a] == 0.f) continue;  // CTA-uniform
+#pragma unroll
+                    for (int bb = 0; bb < NC; ++bb) {
+                        const float w = wy[a] * wx[bb];
+                        if (w != 0.f) {
+                            float v[V];
+                            cnb_ldv(col + ((long)a * Wout + bb) * C, v);
+#pragma unroll
+                            for (int j = 0; j < V; ++j) acc[j] = fmaf(w, v[j], acc[j]);
+                        }
                     }
                 }
             }
