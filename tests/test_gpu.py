@@ -93,6 +93,7 @@ def test_conv_skinny_gemm_plus_shift_add(dev):
     cases.conv_skinny_case(dev, BF16, 2, 25, 31, 128, 9)
     cases.conv_skinny_case(dev, BF16, 1, 33, 20, 64, 3, k=3, pad=2, dil=2)
     cases.conv_skinny_case(dev, F32, 2, 20, 20, 32, 9)
+    cases.conv_skinny_case(dev, BF16, 2, 40, 150, 64, 9)   # rows wider than one 64-pixel strip of the tiled shift kernels, ragged last strip
 
 
 @pytest.mark.parametrize("dtype", [F32, BF16])

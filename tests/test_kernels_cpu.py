@@ -110,6 +110,7 @@ def test_conv_skinny_gemm_plus_shift_add(dev):
     cases.conv_skinny_case(dev, F32, 2, 9, 11, 16, 9)
     cases.conv_skinny_case(dev, F32, 1, 7, 6, 8, 3, k=3, pad=2, dil=2)
     cases.conv_skinny_case(dev, BF16, 1, 10, 12, 32, 9)
+    cases.conv_skinny_case(dev, BF16, 1, 5, 70, 16, 9)   # two 64-pixel strips per row (tiled shift-add / gather kernels), ragged second strip
 
 
 @pytest.mark.parametrize("k", [3, 5])
