@@ -225,3 +225,22 @@ def test_tile_and_checkpoint_argument_errors(dev, tmp_path):
     torch.save({"state_dict": {}, "hyper_parameters": {}}, bad)
     with pytest.raises(KeyError):
         M.load_from_checkpoint(bad)  # no in_channels / in_time: must be passed as keyword arguments
+
+
+def test_loss_reader_returns_every_value_in_order():
+    """engine.LossReader: pipelined read-back of per-step scalars (each value exactly once, in push order, for any depth)."""
+    import torch
+
+    from cultionet_b200.engine import LossReader
+
+    for depth in (1, 2, 3):
+        r = LossReader(depth)
+        got = []
+        for i in range(7):
+            v = r.push(torch.tensor([float(i)]) if i % 2 else torch.tensor(float(i)))
+            if v is not None:
+                got.append(v)
+            assert len(r.pending) <= depth
+        got += r.drain()
+        assert got == [float(i) for i in range(7)], (depth, got)
+        assert r.drain() == []
